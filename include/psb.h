@@ -1,0 +1,203 @@
+/*
+ * psb.h -- C ABI of libpsb_b200.so: the B200 (sm_100a) implementation of the
+ * embedding-scoring hot path of kepingbi/ProdSearch.
+ *
+ * The reference has no FFI / plugin registry: the hot path is reached through
+ * PyTorch nn.Module methods.  This header is the boundary a
+ * maintainer binds instead of the ATen call sites listed per entry point
+ * (paths are relative to the reference repository).  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - tables and activations are row-major contiguous fp32, row length d
+ *     (d % 4 == 0, d <= 512, base pointers 16-byte aligned);
+ *   - indices are int64 exactly as the reference's batches carry them
+ *     (data/batch_data.py:18-22); masks are uint8 (batch_data.py:174);
+ *   - no entry point allocates, synchronises with the host or keeps state:
+ *     work is enqueued on `stream` (a cudaStream_t) and workspace is supplied
+ *     by the caller, sized by the matching *_workspace_bytes query;
+ *   - return value: 0 ok, < 0 invalid argument (PSB_E_*), > 0 a cudaError_t.
+ *     The Python mirror raises RuntimeError on any non-zero status, matching
+ *     the reference's "plain exceptions" error behaviour (trainer.py:215).
+ */
+#ifndef PSB_H_
+#define PSB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* psb_stream_t; /* cudaStream_t */
+
+#define PSB_OK 0
+#define PSB_E_ARG (-1)       /* null pointer / negative size */
+#define PSB_E_DIM (-2)       /* d not a multiple of 4 or > 512, k out of range */
+#define PSB_E_WORKSPACE (-3) /* workspace too small */
+#define PSB_E_ALIGN (-4)     /* pointer not 16-byte aligned */
+#define PSB_E_UNSUPPORTED (-5)
+
+#define PSB_ABI_VERSION 1
+
+int psb_abi_version(void);
+const char* psb_status_string(int status);
+/* Number of kernels this library has launched since load (host counter; lets
+ * bench.py report gpu_launches without a profiler). */
+int64_t psb_launch_count(void);
+
+/* ------------------------------------------------------------------ G1 ---
+ * out[i,:] = table[idx[i],:]                                   (bit-exact copy)
+ * Replaces aten::embedding at models/item_transformer.py:449,:464-469,:262-263,
+ * :269; models/ps_model.py:257,:261,:303,:326-332; models/PV.py:53,:58;
+ * models/PVC.py:76,:84.  Out-of-range indices set *err_flag (optional) to 1 and
+ * produce a zero row (the reference raises IndexError on the host). */
+int psb_gather_rows(const float* table, int64_t table_rows, int64_t d,
+                    const int64_t* idx, int64_t n, float* out,
+                    int32_t* err_flag, psb_stream_t stream);
+
+/* ------------------------------------------------------------------ G4 ---
+ * Fused gather + masked mean (+ optional dropout multiplier, + optional
+ * tanh(W x + b) "fs" projection): models/text_encoder.py:6-16 get_vector_mean,
+ * :75-82 AVGEncoder.forward, :32-40 FSEncoder.forward, on rows gathered by
+ * models/item_transformer.py:449-450, models/ps_model.py:257-258,
+ * models/PVC.py:57-60,:76-79.
+ *
+ *   valid[i,j] = mask ? mask[i,j] != 0 : (pad_idx < 0 || idx[i,j] != pad_idx)
+ *   mean[i,:]  = sum_j valid * tok_scale[i,j] * table[idx[i,j],:] / max(#valid,1)
+ *   mean      *= keep_scale[i,:]           (dropout mask already scaled by 1/(1-p))
+ *   out[i,:]   = fs_weight ? tanh(fs_weight . mean[i,:] + fs_bias) : mean[i,:]
+ *
+ * tok_scale implements the PVC corruption (0 or 1/(1-rate), PVC.py:46-54).
+ * mean_out (optional unless fs_weight given) receives the post-dropout mean
+ * that the backward pass needs; inv_count (optional) receives 1/max(#valid,1). */
+int psb_gather_meanpool_fwd(const float* table, int64_t table_rows, int64_t d,
+                            const int64_t* idx, int64_t n, int64_t w, int64_t pad_idx,
+                            const uint8_t* mask, const float* tok_scale,
+                            const float* keep_scale,
+                            const float* fs_weight, const float* fs_bias,
+                            float* mean_out, float* out, float* inv_count,
+                            psb_stream_t stream);
+
+/* Backward of the fs projection (autograd of text_encoder.py:35-39):
+ *   dz = grad_out * (1 - out^2); grad_weight[j,k] = sum_i dz[i,j] mean[i,k];
+ *   grad_bias[j] = sum_i dz[i,j]; grad_mean[i,k] = keep_scale * sum_j dz[i,j] W[j,k].
+ * Sums over i run in ascending i (deterministic).  The word-table gradient is a
+ * scatter-reduce contribution (src = grad_mean, src_div = w, scale = valid/count). */
+int psb_fs_bwd(const float* grad_out, const float* out, const float* mean,
+               const float* keep_scale, const float* fs_weight, int64_t n, int64_t d,
+               float* grad_weight, float* grad_bias, float* grad_mean,
+               psb_stream_t stream);
+
+/* Per-token weights valid/max(#valid,1) used by the scatter-reduce contribution of a
+ * mean-pool: tok_weight[i,j] (the PVC quirk: the corruption scale is NOT applied in
+ * backward). */
+int psb_meanpool_token_weights(const int64_t* idx, int64_t n, int64_t w, int64_t pad_idx,
+                               const uint8_t* mask, float* tok_weight, psb_stream_t stream);
+
+/* --------------------------------------------------------------- G3 / A4 ---
+ * Fused gather + dot + bias + BCE-with-logits negative-sampling loss, forward and
+ * the analytic score gradient in one pass.  Covers
+ *   item_to_words        models/item_transformer.py:260-283  (anchor = product row)
+ *   ParagraphVector      models/PV.py:57-65                   (anchor = review row)
+ *   PVC                  models/PVC.py:83-91                  (anchor = corrupted mean)
+ *   TEM score+loss tail  models/item_transformer.py:485,:493-514
+ *                        (anchor_a = pos_out, anchor_b = neg_out, w = 1)
+ *
+ *   x[i,j,0]   = <anchor_a[i], table[pos_idx[i,j]]> (+ bias[pos_idx[i,j]])
+ *   x[i,j,1+c] = <anchor(i,c), table[neg_idx[i,j,c]]> (+ bias[...]),
+ *                anchor(i,c) = anchor_b ? anchor_b[i*k+c] : anchor_a[i]
+ *   l[i,j]     = pos_weight*bce(x0,1) + sum_c nw[i,c]*bce(x_c,0)
+ *   valid[i,j] = mask ? mask[i,j] : (pad_idx < 0 || pos_idx[i,j] != pad_idx)
+ *   loss[i]    = sum_j valid*l[i,j] / max(#valid,1)
+ *   coef_pos[i,j]   = d loss[i] / d x[i,j,0],  coef_neg[i,j,c] = d loss[i] / d x[i,j,1+c]
+ *   grad_anchor_a[i,:] = sum coef * row  over the scores that used anchor_a[i]
+ *   grad_anchor_b[i*k+c,:] = coef_neg[i,0,c] * table[neg_idx[i,0,c]]
+ * bce(x,t) = max(x,0) - x t + log1p(exp(-|x|)); its derivative sigmoid(x) - t. */
+int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b,
+                    const float* table, int64_t table_rows, int64_t d, const float* bias,
+                    const int64_t* pos_idx, const int64_t* neg_idx,
+                    const uint8_t* mask, int64_t pad_idx,
+                    const float* neg_weight, float pos_weight,
+                    int64_t n, int64_t w, int64_t k,
+                    float* loss, float* coef_pos, float* coef_neg,
+                    float* grad_anchor_a, float* grad_anchor_b,
+                    psb_stream_t stream);
+
+/* ------------------------------------------------------------------ G2 ---
+ * Deterministic embedding backward: sort-then-segmented-reduce instead of float
+ * atomics.  Replaces aten::embedding_dense_backward (autograd of every K1 site).
+ * A table's gradient is the sum of "contributions"; contribution c adds, for
+ * each slot i < n:
+ *     grad[idx[i], :] += s(i) * src[row(i), :]
+ *     row(i) = src_row ? src_row[i] : i / src_div
+ *     s(i)   = (scale ? scale[i] : 1) * (scale2 ? scale2[i / scale2_div] : 1)
+ * and, when to_bias != 0, bias_grad[idx[i]] += s(i) (word_bias / product_bias,
+ * item_transformer.py:272-275,:495-499).  Slots whose idx equals drop_idx (the
+ * table's padding_idx: nn.Embedding zeroes that gradient row) are skipped.
+ * Within one destination row the terms are added in ascending (contribution,
+ * slot) order, so results are bit-reproducible and independent of the grid. */
+typedef struct psb_contrib {
+  const int64_t* idx;     /* [n] destination rows */
+  int64_t n;
+  const float* src;       /* [*, d] source rows */
+  const int64_t* src_row; /* optional [n] */
+  int64_t src_div;        /* used when src_row == NULL (>= 1) */
+  const float* scale;     /* optional [n] */
+  const float* scale2;    /* optional [ceil(n / scale2_div)] */
+  int64_t scale2_div;     /* >= 1 */
+  int32_t to_bias;
+  int32_t reserved;
+} psb_contrib_t;
+
+#define PSB_MAX_CONTRIBS 8
+
+int64_t psb_scatter_reduce_workspace_bytes(int64_t n_total, int64_t table_rows);
+
+/* contribs: HOST array of n_contribs descriptors (device pointers inside).
+ * Outputs: unique_rows[u] ascending, reduced[u,:], reduced_bias[u] (each optional,
+ * capacity n_total), *n_unique (device int32).  If dense_grad / dense_bias_grad are
+ * given, row unique_rows[u] of them is OVERWRITTEN with the reduced value (the
+ * caller keeps the rest zero, see psb_zero_rows). */
+int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs,
+                            int64_t table_rows, int64_t d, int64_t drop_idx,
+                            void* workspace, int64_t workspace_bytes,
+                            int32_t* unique_rows, float* reduced, float* reduced_bias,
+                            int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                            psb_stream_t stream);
+
+/* dense[rows[u], :] = 0 (and dense_bias[rows[u]] = 0) for u < *n_rows: clears the
+ * rows a previous step touched so a persistent dense .grad costs O(batch). */
+int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows,
+                  int64_t d, float* dense, float* dense_bias, psb_stream_t stream);
+
+/* ------------------------------------------------------------------ G5 ---
+ * Full-catalog scoring with fused top-k: S = Q . E^T (+ bias), top-k per query,
+ * ties broken by LOWER item id.  Replaces test_dotproduct
+ * (models/item_transformer.py:111-146) + Trainer.get_prod_scores
+ * (trainer.py:189-226) + host argsort (trainer.py:136,:152) for the TEM path; the
+ * [M, N] score matrix is never materialised.
+ *   queries [m, d], table [n_items, d] (rows >= n_items, e.g. the pad row, are not
+ *   candidates), bias optional [n_items], id_base/id_stride map local row r to
+ *   the global item id id_base + r * id_stride (row-sharded catalogs).
+ * Outputs: out_ids [m, k] int64 (-1 where fewer than k candidates), out_scores
+ * [m, k] fp32, descending score / ascending id.
+ * mode: PSB_TOPK_EXACT  fp32 FFMA scoring (reference arithmetic, CUDA cores)
+ *       PSB_TOPK_TC     tcgen05 TF32 shortlist + exact fp32 rescoring (same result) */
+#define PSB_TOPK_EXACT 0
+#define PSB_TOPK_TC 1
+
+int64_t psb_catalog_topk_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k, int32_t mode);
+int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_t n_items,
+                     int64_t d, const float* bias, int64_t k, int64_t id_base, int64_t id_stride,
+                     int32_t mode, void* workspace, int64_t workspace_bytes,
+                     int64_t* out_ids, float* out_scores, psb_stream_t stream);
+
+/* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
+ * lays them out) into the global top-k with the same ordering rule. */
+int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,
+                   int64_t* out_ids, float* out_scores, psb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of libpsb_b200.so (the C ABI declared in include/psb.h).
+
+There is NO fallback: if the library is missing or a call returns a non-zero
+status this module raises.  PyTorch is used only to own device memory and
+streams; every op below runs hand-written sm_100a CUDA.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpsb_b200.so")
+
+c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
+
+MAX_CONTRIBS = 8
+TOPK_EXACT, TOPK_TC = 0, 1
+
+
+class Contrib(ctypes.Structure):
+    """psb_contrib_t (include/psb.h)."""
+    _fields_ = [("idx", c_vp), ("n", c_i64), ("src", c_vp), ("src_row", c_vp), ("src_div", c_i64),
+                ("scale", c_vp), ("scale2", c_vp), ("scale2_div", c_i64), ("to_bias", c_i32),
+                ("reserved", c_i32)]
+
+
+# name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
+SIGNATURES = {
+    "psb_abi_version": (c_i32, []),
+    "psb_status_string": (ctypes.c_char_p, [c_i32]),
+    "psb_launch_count": (c_i64, []),
+    "psb_gather_rows": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "psb_gather_meanpool_fwd": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_fs_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "psb_meanpool_token_weights": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "psb_ns_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32,
+                                c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_scatter_reduce_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "psb_scatter_reduce_rows": (c_i32, [ctypes.POINTER(Contrib), c_i32, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_zero_rows": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "psb_catalog_topk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i32]),
+    "psb_catalog_topk": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp,
+                                 c_i64, c_vp, c_vp, c_vp]),
+    "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "prodsearch_b200: %s is missing -- build it with `python -m prodsearch_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.psb_abi_version() != 1:
+            raise ImportError("prodsearch_b200: ABI version mismatch in %s" % LIB_PATH)
+        _lib = lib
+    return _lib
+
+
+def status_string(st):
+    return load().psb_status_string(st).decode()
+
+
+def check(st, what):
+    if st != 0:
+        raise RuntimeError("%s failed: status %d (%s)" % (what, st, status_string(st)))
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None, allow_none=True):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        if not allow_none:
+            raise ValueError("tensor required")
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("prodsearch_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("prodsearch_b200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def launch_count():
+    return int(load().psb_launch_count())

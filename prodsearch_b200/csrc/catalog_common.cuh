@@ -1,0 +1,35 @@
+// Shared definitions of the catalog-scoring (G5) translation units.
+#pragma once
+#include "psb_common.cuh"
+
+namespace psb {
+
+constexpr int kKMax = 128;  // largest supported k (reference writes cutoff = 100, trainer.py:140)
+
+// (s, id) ranks before (ts, tid): higher score, ties -> lower item id
+__device__ __forceinline__ bool beats(float s, int64_t id, float ts, int64_t tid) {
+  return s > ts || (s == ts && id < tid);
+}
+
+// strict total order with a position tie-break (only empty slots share (score, id))
+__device__ __forceinline__ bool before(float su, int64_t iu, int pu, float se, int64_t ie, int pe) {
+  return su > se || (su == se && (iu < ie || (iu == ie && pu < pe)));
+}
+
+// canonical fp32 score recurrence (see catalog_topk.cu header)
+__device__ __forceinline__ float canonical_dot(const float* __restrict__ q, const float* __restrict__ e, int d) {
+  float acc = 0.f;
+  for (int c = 0; c < d; ++c) acc = fmaf(q[c], e[c], acc);
+  return acc;
+}
+
+int64_t exact_workspace_bytes(int64_t m, int64_t n_items);
+int catalog_topk_exact(const float* queries, int64_t m, const float* table, int64_t n_items, int64_t d,
+                       const float* bias, int64_t k, int64_t id_base, int64_t id_stride, void* workspace,
+                       int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s);
+int64_t tc_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k);
+int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t n_items, int64_t d,
+                    const float* bias, int64_t k, int64_t id_base, int64_t id_stride, void* workspace,
+                    int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s);
+
+}  // namespace psb

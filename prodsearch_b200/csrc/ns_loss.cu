@@ -1,0 +1,174 @@
+// G3 / A4: fused gather + dot + bias + BCE-with-logits negative-sampling loss.
+//
+// One warp owns one anchor i.  For every target position j it loads the positive row
+// and the k sampled-negative rows (1 + k independent LDG.128 per lane in flight), scores
+// them against the anchor with warp-shuffle reductions, evaluates the loss and its
+// analytic derivative, and accumulates d loss / d anchor on the fly -- every table row is
+// read from HBM exactly once per use and no [n, w, 1+k, d] tensor is ever materialised.
+// HBM-bound: algorithmic bytes per anchor = w * (1 + k) * d * 4 (rows) + d * 4 (anchor)
+// + d * 4 (grad_anchor) (+ k * d * 8 when per-negative anchors are used).
+#include "psb_common.cuh"
+
+namespace psb {
+
+constexpr int kMaxNeg = 16;
+
+__device__ __forceinline__ float bce_value(float x, float t) {
+  // max(x,0) - x t + log1p(exp(-|x|))     
+  return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) {
+  // stable for both signs
+  const float e = expf(-fabsf(x));
+  return x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+ns_loss_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ anchor_b,
+               const float4* __restrict__ table, int64_t table_rows, int d4,
+               const float* __restrict__ bias, const int64_t* __restrict__ pos_idx,
+               const int64_t* __restrict__ neg_idx, const uint8_t* __restrict__ mask, int64_t pad_idx,
+               const float* __restrict__ neg_weight, float pos_weight, int64_t n, int w, int k,
+               float* __restrict__ loss, float* __restrict__ coef_pos, float* __restrict__ coef_neg,
+               float4* __restrict__ grad_a, float4* __restrict__ grad_b) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int64_t i = warp; i < n; i += nwarps) {
+    // number of valid target positions (the masked-mean denominator)
+    int cnt = 0;
+    for (int j0 = 0; j0 < w; j0 += 32) {
+      const int j = j0 + lane;
+      bool valid = false;
+      if (j < w) valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pos_idx[i * w + j] != pad_idx);
+      cnt += __popc(__ballot_sync(kFull, valid));
+    }
+    const float denom = static_cast<float>(cnt > 0 ? cnt : 1);
+
+    float4 a[C], ga[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      a[c] = col < d4 ? anchor_a[i * d4 + col] : zero4();
+      ga[c] = zero4();
+    }
+    float loss_acc = 0.f;
+    for (int j = 0; j < w; ++j) {
+      const int64_t pj = pos_idx[i * w + j];
+      const bool valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pj != pad_idx);
+      const float m = valid ? 1.f : 0.f;
+      // positive (slot 0) and negatives (slots 1..k), processed in groups of 4 rows in flight
+      float lsum = 0.f;
+      for (int s0 = 0; s0 <= k; s0 += 4) {
+        int64_t r[4];
+        float4 row[4][C];
+        float4 anc[4][C];
+        float part[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = s0 + u;
+          r[u] = -1;
+          if (s <= k) r[u] = s == 0 ? pj : neg_idx[(i * w + j) * k + (s - 1)];
+          if (r[u] < 0 || r[u] >= table_rows) r[u] = -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = s0 + u;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int col = lane + 32 * c;
+            row[u][c] = (r[u] >= 0 && col < d4) ? ldg_row4(table + r[u] * d4 + col) : zero4();
+            if (anchor_b != nullptr && s >= 1 && s <= k)
+              anc[u][c] = col < d4 ? anchor_b[(i * k + (s - 1)) * d4 + col] : zero4();
+            else
+              anc[u][c] = a[c];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float t = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) t += dot4(anc[u][c], row[u][c]);
+          part[u] = t;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) part[u] = warp_sum(part[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = s0 + u;
+          if (s > k) continue;
+          float x = part[u];
+          if (bias != nullptr && r[u] >= 0) x += bias[r[u]];
+          const float t = s == 0 ? 1.f : 0.f;
+          const float wt = s == 0 ? pos_weight : (neg_weight != nullptr ? neg_weight[i * k + (s - 1)] : 1.f);
+          lsum += wt * bce_value(x, t);
+          const float g = m * wt * (sigmoidf_(x) - t) / denom;
+          if (lane == 0) {
+            if (s == 0) coef_pos[i * w + j] = g;
+            else coef_neg[(i * w + j) * k + (s - 1)] = g;
+          }
+          if (anchor_b != nullptr && s >= 1) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const int col = lane + 32 * c;
+              if (col < d4) {
+                float4 o = zero4();
+                fma4(o, g, row[u][c]);
+                grad_b[(i * k + (s - 1)) * d4 + col] = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) fma4(ga[c], g, row[u][c]);
+          }
+        }
+      }
+      loss_acc += m * lsum;
+    }
+    if (lane == 0) loss[i] = loss_acc / denom;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      if (col < d4) grad_a[i * d4 + col] = ga[c];
+    }
+  }
+}
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, const float* table,
+                               int64_t table_rows, int64_t d, const float* bias, const int64_t* pos_idx,
+                               const int64_t* neg_idx, const uint8_t* mask, int64_t pad_idx,
+                               const float* neg_weight, float pos_weight, int64_t n, int64_t w, int64_t k,
+                               float* loss, float* coef_pos, float* coef_neg, float* grad_anchor_a,
+                               float* grad_anchor_b, psb_stream_t stream) {
+  int st = check_table_args(table, table_rows, d);
+  if (st != PSB_OK) return st;
+  if (n < 0 || w <= 0 || k < 0 || k > kMaxNeg) return k > kMaxNeg ? PSB_E_DIM : PSB_E_ARG;
+  if (n == 0) return PSB_OK;
+  if (anchor_a == nullptr || pos_idx == nullptr || (k > 0 && neg_idx == nullptr) || loss == nullptr ||
+      coef_pos == nullptr || (k > 0 && coef_neg == nullptr) || grad_anchor_a == nullptr)
+    return PSB_E_ARG;
+  if (anchor_b != nullptr && (w != 1 || grad_anchor_b == nullptr)) return PSB_E_ARG;
+  if (misaligned16(anchor_a) || misaligned16(anchor_b) || misaligned16(grad_anchor_a) ||
+      misaligned16(grad_anchor_b))
+    return PSB_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n, 8);
+  const int d4 = static_cast<int>(d / 4);
+#define PSB_NS_LAUNCH(C)                                                                                   \
+  ns_loss_kernel<C><<<grid, 256, 0, s>>>(                                                                  \
+      reinterpret_cast<const float4*>(anchor_a), reinterpret_cast<const float4*>(anchor_b),                \
+      reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx,       \
+      neg_weight, pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,       \
+      reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b))
+  if (d4 <= 32) PSB_NS_LAUNCH(1);
+  else if (d4 <= 64) PSB_NS_LAUNCH(2);
+  else PSB_NS_LAUNCH(4);
+#undef PSB_NS_LAUNCH
+  return launch_status();
+}

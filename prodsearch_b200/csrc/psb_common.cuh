@@ -1,0 +1,72 @@
+// Shared device/host helpers for libpsb_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/psb.h"
+
+namespace psb {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr unsigned kFull = 0xffffffffu;
+
+extern int64_t g_launches;  // host-side launch counter (psb_launch_count)
+
+inline int check_table_args(const void* table, int64_t rows, int64_t d) {
+  if (table == nullptr || rows <= 0) return PSB_E_ARG;
+  if (d <= 0 || (d & 3) != 0 || d > 512) return PSB_E_DIM;
+  if ((reinterpret_cast<uintptr_t>(table) & 15) != 0) return PSB_E_ALIGN;
+  return PSB_OK;
+}
+
+inline bool misaligned16(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
+inline int launch_status() {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PSB_OK : static_cast<int>(e);
+}
+
+inline int grid_for(int64_t work_items, int items_per_block, int max_waves = 16) {
+  int64_t need = (work_items + items_per_block - 1) / items_per_block;
+  int64_t cap = static_cast<int64_t>(kNumSMs) * max_waves;
+  if (need < 1) need = 1;
+  return static_cast<int>(need < cap ? need : cap);
+}
+
+// 128-bit streaming load of table rows: read-only path, do not allocate in L1 (each
+// gathered row is used once by the loading warp).
+__device__ __forceinline__ float4 ldg_row4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void stg4(float4* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+}  // namespace psb

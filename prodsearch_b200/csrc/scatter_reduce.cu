@@ -1,0 +1,582 @@
+// G2: deterministic embedding backward = stable LSD radix sort of (destination row, slot)
+// pairs, segment detection, then a fixed-order segmented reduction (no float atomics).
+//
+// Two regimes, same arithmetic:
+//   * n_total <= 16384 (a TEM step: ~10k item slots, ~7k word slots): ONE single-CTA
+//     kernel packs keys, sorts them in shared memory (all radix passes), finds the
+//     segments and writes the sorted slot list -> 2 launches per table per step.
+//   * larger batches: multi-CTA radix sort (histogram / per-digit scan / stable scatter per
+//     8-bit pass) + 3-kernel segment compaction.
+// The reduction kernel (one warp per destination row, 128-bit row loads, 4 source rows in
+// flight) is the HBM-bound part: algorithmic bytes = n_slots * d * 4 read (when sources
+// are materialised rows) + n_unique * d * 4 written + metadata; sort traffic is overhead.
+#include "psb_common.cuh"
+
+namespace psb {
+
+struct ContribTable {
+  psb_contrib_t c[PSB_MAX_CONTRIBS];
+  uint32_t off[PSB_MAX_CONTRIBS + 1];
+  int n;
+};
+
+__device__ __forceinline__ int locate(const ContribTable& T, uint32_t slot) {
+  int c = 0;
+  while (c + 1 < T.n && slot >= T.off[c + 1]) ++c;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t make_key(const ContribTable& T, uint32_t slot, int64_t table_rows,
+                                             int64_t drop_idx) {
+  const int c = locate(T, slot);
+  const int64_t r = T.c[c].idx[slot - T.off[c]];
+  return (r < 0 || r >= table_rows || r == drop_idx) ? static_cast<uint32_t>(table_rows)
+                                                       : static_cast<uint32_t>(r);
+}
+
+// Exclusive block scan of one int per thread.  `sm` holds NT/32 ints.
+template <int NT>
+__device__ __forceinline__ int block_excl_scan(int v, int* sm, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sm[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int t = lane < NT / 32 ? sm[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFull, t, o);
+      if (lane >= o) t += u;
+    }
+    if (lane < NT / 32) sm[lane] = t;
+  }
+  __syncthreads();
+  const int base = wid > 0 ? sm[wid - 1] : 0;
+  if (total != nullptr) *total = sm[NT / 32 - 1];
+  __syncthreads();
+  return base + incl - v;
+}
+
+// Stable rank of every key of a tile among keys with the same 8-bit digit.
+// Layout: warp w, round r, lane l  <->  tile position w*32*IPT + r*32 + l.
+// On return pos[r] = position of the key in the tile sorted (stably) by digit,
+// dstart[256] = first sorted position of each digit.  whist: [NT/32][256] ints.
+template <int NT, int IPT>
+__device__ __forceinline__ void tile_rank(const uint32_t (&key)[IPT], const bool (&valid)[IPT], int shift,
+                                          int (&pos)[IPT], int* whist, int* dstart, int* scan_sm) {
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int t = threadIdx.x; t < NW * 256; t += NT) whist[t] = 0;
+  __syncthreads();
+  int* mine = whist + wid * 256;
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    const int dg = valid[r] ? static_cast<int>((key[r] >> shift) & 255u) : 256;
+    const unsigned peers = __match_any_sync(kFull, dg);
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (dg < 256) old = mine[dg];
+    __syncwarp();
+    if (dg < 256 && lane == leader) mine[dg] = old + __popc(peers);
+    __syncwarp();
+    pos[r] = old + __popc(peers & lt);
+  }
+  __syncthreads();
+  int tot = 0;
+  if (threadIdx.x < 256) {
+    int run = 0;
+#pragma unroll 4
+    for (int w2 = 0; w2 < NW; ++w2) {
+      const int c = whist[w2 * 256 + threadIdx.x];
+      whist[w2 * 256 + threadIdx.x] = run;
+      run += c;
+    }
+    tot = run;
+  }
+  const int ex = block_excl_scan<NT>(threadIdx.x < 256 ? tot : 0, scan_sm, nullptr);
+  if (threadIdx.x < 256) dstart[threadIdx.x] = ex;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    if (valid[r]) {
+      const int dg = static_cast<int>((key[r] >> shift) & 255u);
+      pos[r] += dstart[dg] + mine[dg];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Small regime: everything up to the segment table in one CTA.
+// ------------------------------------------------------------------------------------
+constexpr int kSmallNT = 1024;
+constexpr int kSmallIPT = 16;
+constexpr int kSmallCap = kSmallNT * kSmallIPT;  // 16384 slots
+
+__global__ void __launch_bounds__(kSmallNT, 1)
+small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, int64_t table_rows, int64_t drop_idx, int passes,
+                           uint32_t* __restrict__ sorted_slots, int32_t* __restrict__ seg_start,
+                           int32_t* __restrict__ unique_rows, int32_t* __restrict__ n_unique) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* sk = reinterpret_cast<uint32_t*>(smem_raw);          // [cap] keys
+  uint32_t* sv = sk + kSmallCap;                                 // [cap] slots
+  int* whist = reinterpret_cast<int*>(sv + kSmallCap);           // [32][256]
+  int* dstart = whist + (kSmallNT / 32) * 256;                   // [256]
+  int* scan_sm = dstart + 256;                                   // [32]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t sentinel = static_cast<uint32_t>(table_rows);
+
+  uint32_t key[kSmallIPT], val[kSmallIPT];
+  bool valid[kSmallIPT];
+  int pos[kSmallIPT];
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    const int p = wid * 32 * kSmallIPT + r * 32 + lane;
+    valid[r] = p < n_total;
+    val[r] = static_cast<uint32_t>(p);
+    key[r] = valid[r] ? make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx) : 0xffffffffu;
+  }
+  for (int pass = 0; pass < passes; ++pass) {
+    tile_rank<kSmallNT, kSmallIPT>(key, valid, pass * 8, pos, whist, dstart, scan_sm);
+#pragma unroll
+    for (int r = 0; r < kSmallIPT; ++r)
+      if (valid[r]) {
+        sk[pos[r]] = key[r];
+        sv[pos[r]] = val[r];
+      }
+    __syncthreads();
+    if (pass + 1 < passes) {
+#pragma unroll
+      for (int r = 0; r < kSmallIPT; ++r) {
+        const int p = wid * 32 * kSmallIPT + r * 32 + lane;
+        if (p < n_total) {
+          key[r] = sk[p];
+          val[r] = sv[p];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // Segment heads over the sorted keys; thread t owns positions [t*IPT, (t+1)*IPT).
+  int heads = 0;
+  const int p0 = threadIdx.x * kSmallIPT;
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    const int p = p0 + r;
+    if (p < n_total) {
+      const uint32_t kk = sk[p];
+      if (kk != sentinel && (p == 0 || sk[p - 1] != kk)) ++heads;
+    }
+  }
+  int total = 0;
+  int seg = block_excl_scan<kSmallNT>(heads, scan_sm, &total);
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    const int p = p0 + r;
+    if (p < n_total) {
+      const uint32_t kk = sk[p];
+      sorted_slots[p] = sv[p];
+      if (kk != sentinel && (p == 0 || sk[p - 1] != kk)) {
+        seg_start[seg] = p;
+        unique_rows[seg] = static_cast<int32_t>(kk);
+        ++seg;
+      }
+      // end marker: first dropped slot, or the end of the list
+      if (kk == sentinel && (p == 0 || sk[p - 1] != sentinel)) seg_start[total] = p;
+      if (p == n_total - 1 && kk != sentinel) seg_start[total] = n_total;
+    }
+  }
+  if (threadIdx.x == 0) {
+    *n_unique = total;
+    if (n_total == 0) seg_start[0] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Large regime: multi-CTA radix sort.
+// ------------------------------------------------------------------------------------
+constexpr int kNT = 256;
+constexpr int kIPT = 16;
+constexpr int kTile = kNT * kIPT;  // 4096 keys per CTA
+
+__global__ void __launch_bounds__(256)
+pack_keys_kernel(const __grid_constant__ ContribTable T, int64_t n_total, int64_t table_rows, int64_t drop_idx,
+                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n_total;
+       s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    keys[s] = make_key(T, static_cast<uint32_t>(s), table_rows, drop_idx);
+    vals[s] = static_cast<uint32_t>(s);
+  }
+}
+
+// hist[digit * nblocks + block]
+__global__ void __launch_bounds__(kNT)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r) {
+    const int64_t p = base + r * kNT + threadIdx.x;
+    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1);  // integer counts: order-free
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// One CTA per digit: exclusive scan of its row of per-block counts; totals[digit].
+__global__ void __launch_bounds__(256)
+radix_scan_kernel(int* __restrict__ hist, int nblocks, int* __restrict__ totals) {
+  __shared__ int sm[8];
+  int* row = hist + static_cast<int64_t>(blockIdx.x) * nblocks;
+  int carry = 0;
+  for (int b0 = 0; b0 < nblocks; b0 += 256) {
+    const int b = b0 + threadIdx.x;
+    const int v = b < nblocks ? row[b] : 0;
+    int tot = 0;
+    const int ex = block_excl_scan<256>(v, sm, &tot);
+    if (b < nblocks) row[b] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(kNT)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+                     int shift, int nblocks, const int* __restrict__ hist, const int* __restrict__ totals,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t sk[kTile];
+  __shared__ uint32_t sv[kTile];
+  __shared__ int whist[(kNT / 32) * 256];
+  __shared__ int dstart[256];
+  __shared__ int gbase[256];
+  __shared__ int scan_sm[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+  const int tile_valid = static_cast<int>(min(static_cast<int64_t>(kTile), n - base));
+  // global base of each digit = exclusive scan of digit totals + this block's offset in the digit
+  {
+    const int ex = block_excl_scan<kNT>(totals[threadIdx.x], scan_sm, nullptr);
+    gbase[threadIdx.x] = ex + hist[threadIdx.x * nblocks + blockIdx.x];
+  }
+  uint32_t key[kIPT], val[kIPT];
+  bool valid[kIPT];
+  int pos[kIPT];
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r) {
+    const int p = wid * 32 * kIPT + r * 32 + lane;
+    valid[r] = p < tile_valid;
+    key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
+    val[r] = valid[r] ? vals_in[base + p] : 0u;
+  }
+  tile_rank<kNT, kIPT>(key, valid, shift, pos, whist, dstart, scan_sm);
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r)
+    if (valid[r]) {
+      sk[pos[r]] = key[r];
+      sv[pos[r]] = val[r];
+    }
+  __syncthreads();
+  for (int p = threadIdx.x; p < tile_valid; p += kNT) {
+    const uint32_t kk = sk[p];
+    const int dg = static_cast<int>((kk >> shift) & 255u);
+    const int64_t o = static_cast<int64_t>(gbase[dg]) + (p - dstart[dg]);
+    keys_out[o] = kk;
+    vals_out[o] = sv[p];
+  }
+}
+
+// Segment compaction (large regime).  Element n (virtual) is a sentinel.
+__device__ __forceinline__ bool is_head(const uint32_t* keys, int64_t p, int64_t n, uint32_t sentinel) {
+  if (p >= n) return false;
+  const uint32_t kk = keys[p];
+  return kk != sentinel && (p == 0 || keys[p - 1] != kk);
+}
+
+__global__ void __launch_bounds__(kNT)
+heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel, int* __restrict__ counts) {
+  __shared__ int sm[8];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x * kIPT;
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r) c += is_head(keys, base + r, n, sentinel) ? 1 : 0;
+  int tot = 0;
+  block_excl_scan<kNT>(c, sm, &tot);
+  if (threadIdx.x == 0) counts[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256)
+heads_scan_kernel(int* __restrict__ counts, int nblocks, int32_t* __restrict__ n_unique) {
+  __shared__ int sm[8];
+  int carry = 0;
+  for (int b0 = 0; b0 < nblocks; b0 += 256) {
+    const int b = b0 + threadIdx.x;
+    const int v = b < nblocks ? counts[b] : 0;
+    int tot = 0;
+    const int ex = block_excl_scan<256>(v, sm, &tot);
+    if (b < nblocks) counts[b] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *n_unique = carry;
+}
+
+__global__ void __launch_bounds__(kNT)
+heads_write_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel,
+                   const int* __restrict__ block_base, const int32_t* __restrict__ n_unique,
+                   int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows) {
+  __shared__ int sm[8];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x * kIPT;
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r) c += is_head(keys, base + r, n, sentinel) ? 1 : 0;
+  int seg = block_base[blockIdx.x] + block_excl_scan<kNT>(c, sm, nullptr);
+  const int total = *n_unique;
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r) {
+    const int64_t p = base + r;
+    if (p < n) {
+      const uint32_t kk = keys[p];
+      if (is_head(keys, p, n, sentinel)) {
+        seg_start[seg] = static_cast<int32_t>(p);
+        unique_rows[seg] = static_cast<int32_t>(kk);
+        ++seg;
+      }
+      if (kk == sentinel && (p == 0 || keys[p - 1] != sentinel)) seg_start[total] = static_cast<int32_t>(p);
+      if (p == n - 1 && kk != sentinel) seg_start[total] = static_cast<int32_t>(n);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Segmented reduction: one warp per destination row, terms added in sorted (= slot) order.
+// ------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __restrict__ sorted_slots,
+                  const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
+                  const int32_t* __restrict__ n_unique, int d4, float4* __restrict__ reduced,
+                  float* __restrict__ reduced_bias, float4* __restrict__ dense,
+                  float* __restrict__ dense_bias) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nu = *n_unique;
+  constexpr int U = 4;
+  for (int seg = warp; seg < nu; seg += nwarps) {
+    const int lo = seg_start[seg], hi = seg_start[seg + 1];
+    float4 acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = zero4();
+    float bacc = 0.f;
+    for (int p = lo; p < hi; p += U) {
+      const float4* srcp[U];
+      float sc[U];
+      bool tb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        srcp[u] = nullptr;
+        sc[u] = 0.f;
+        tb[u] = false;
+        if (p + u < hi) {
+          const uint32_t slot = sorted_slots[p + u];
+          const int ci = locate(T, slot);
+          const psb_contrib_t& cc = T.c[ci];
+          const uint32_t i = slot - T.off[ci];
+          const int64_t row = cc.src_row != nullptr ? cc.src_row[i]
+                                                    : static_cast<int64_t>(i / static_cast<uint32_t>(cc.src_div));
+          float s = cc.scale != nullptr ? cc.scale[i] : 1.f;
+          if (cc.scale2 != nullptr) s *= cc.scale2[i / static_cast<uint32_t>(cc.scale2_div)];
+          sc[u] = s;
+          tb[u] = cc.to_bias != 0;
+          srcp[u] = reinterpret_cast<const float4*>(cc.src) + row * d4;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int col = lane + 32 * c;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (srcp[u] != nullptr && col < d4) ? __ldg(srcp[u] + col) : zero4();
+#pragma unroll
+        for (int u = 0; u < U; ++u) fma4(acc[c], sc[u], v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (tb[u]) bacc += sc[u];
+    }
+    const int64_t drow = unique_rows[seg];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      if (col < d4) {
+        if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+        if (dense != nullptr) dense[drow * d4 + col] = acc[c];
+      }
+    }
+    if (lane == 0) {
+      if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+      if (dense_bias != nullptr) dense_bias[drow] = bacc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows, int d4,
+                 float4* __restrict__ dense, float* __restrict__ dense_bias) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int n = *n_rows;
+  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += nwarps) {
+    const int64_t r = rows[u];
+    if (dense != nullptr)
+      for (int col = lane; col < d4; col += 32) dense[r * d4 + col] = zero4();
+    if (dense_bias != nullptr && lane == 0) dense_bias[r] = 0.f;
+  }
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct WorkspaceLayout {
+  int64_t keys_a, vals_a, keys_b, vals_b, hist, totals, counts, seg_start, total;
+};
+
+static WorkspaceLayout layout_for(int64_t n_total) {
+  WorkspaceLayout L;
+  const int64_t nblocks = (n_total + kTile - 1) / kTile + 1;
+  int64_t o = 0;
+  L.keys_a = o; o += align_up(4 * n_total, 256);
+  L.vals_a = o; o += align_up(4 * n_total, 256);
+  L.keys_b = o; o += align_up(4 * n_total, 256);
+  L.vals_b = o; o += align_up(4 * n_total, 256);
+  L.hist = o; o += align_up(4 * 256 * nblocks, 256);
+  L.totals = o; o += 1024;
+  L.counts = o; o += align_up(4 * (nblocks + 1), 256);
+  L.seg_start = o; o += align_up(4 * (n_total + 2), 256);
+  L.total = o + 256;
+  return L;
+}
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" int64_t psb_scatter_reduce_workspace_bytes(int64_t n_total, int64_t table_rows) {
+  (void)table_rows;
+  if (n_total < 0) return PSB_E_ARG;
+  return layout_for(n_total > 0 ? n_total : 1).total;
+}
+
+extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
+                                       int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                                       int32_t* unique_rows, float* reduced, float* reduced_bias,
+                                       int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                                       psb_stream_t stream) {
+  if (contribs == nullptr || n_contribs <= 0 || n_contribs > PSB_MAX_CONTRIBS || workspace == nullptr ||
+      unique_rows == nullptr || n_unique == nullptr || table_rows <= 0 || table_rows >= (1ll << 31))
+    return PSB_E_ARG;
+  if (d <= 0 || (d & 3) != 0 || d > 512) return PSB_E_DIM;
+  if (misaligned16(reduced) || misaligned16(dense_grad) || misaligned16(workspace)) return PSB_E_ALIGN;
+  ContribTable T;
+  T.n = n_contribs;
+  int64_t n_total = 0;
+  for (int c = 0; c < n_contribs; ++c) {
+    const psb_contrib_t& cc = contribs[c];
+    if (cc.n < 0 || (cc.n > 0 && (cc.idx == nullptr || cc.src == nullptr))) return PSB_E_ARG;
+    if (cc.src_row == nullptr && cc.src_div < 1) return PSB_E_ARG;
+    if (cc.scale2 != nullptr && cc.scale2_div < 1) return PSB_E_ARG;
+    if (misaligned16(cc.src)) return PSB_E_ALIGN;
+    T.c[c] = cc;
+    T.off[c] = static_cast<uint32_t>(n_total);
+    n_total += cc.n;
+  }
+  if (n_total >= (1ll << 31)) return PSB_E_ARG;
+  for (int c = n_contribs; c <= PSB_MAX_CONTRIBS; ++c) T.off[c] = static_cast<uint32_t>(n_total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const WorkspaceLayout L = layout_for(n_total > 0 ? n_total : 1);
+  if (workspace_bytes < L.total) return PSB_E_WORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* keys_a = reinterpret_cast<uint32_t*>(ws + L.keys_a);
+  uint32_t* vals_a = reinterpret_cast<uint32_t*>(ws + L.vals_a);
+  uint32_t* keys_b = reinterpret_cast<uint32_t*>(ws + L.keys_b);
+  uint32_t* vals_b = reinterpret_cast<uint32_t*>(ws + L.vals_b);
+  int* hist = reinterpret_cast<int*>(ws + L.hist);
+  int* totals = reinterpret_cast<int*>(ws + L.totals);
+  int* counts = reinterpret_cast<int*>(ws + L.counts);
+  int32_t* seg_start = reinterpret_cast<int32_t*>(ws + L.seg_start);
+
+  int bits = 1;
+  while ((static_cast<int64_t>(1) << bits) <= table_rows) ++bits;  // sentinel == table_rows must fit
+  const int passes = (bits + 7) / 8;
+  const uint32_t* sorted_slots = nullptr;
+  int st;
+
+  if (n_total <= kSmallCap) {
+    static bool attr_set = false;
+    const size_t smem = static_cast<size_t>(kSmallCap) * 8 + (kSmallNT / 32) * 256 * 4 + 256 * 4 + 32 * 4;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(small_sort_segments_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set = true;
+    }
+    small_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
+                                                         passes, vals_a, seg_start, unique_rows, n_unique);
+    if ((st = launch_status()) != PSB_OK) return st;
+    sorted_slots = vals_a;
+  } else {
+    const int nblocks = static_cast<int>((n_total + kTile - 1) / kTile);
+    pack_keys_kernel<<<grid_for(n_total, 256 * 4), 256, 0, s>>>(T, n_total, table_rows, drop_idx, keys_a, vals_a);
+    if ((st = launch_status()) != PSB_OK) return st;
+    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    for (int pass = 0; pass < passes; ++pass) {
+      radix_hist_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, pass * 8, nblocks, hist);
+      if ((st = launch_status()) != PSB_OK) return st;
+      radix_scan_kernel<<<256, 256, 0, s>>>(hist, nblocks, totals);
+      if ((st = launch_status()) != PSB_OK) return st;
+      radix_scatter_kernel<<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
+      if ((st = launch_status()) != PSB_OK) return st;
+      uint32_t* t = ki; ki = ko; ko = t;
+      t = vi; vi = vo; vo = t;
+    }
+    const uint32_t sentinel = static_cast<uint32_t>(table_rows);
+    heads_count_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts);
+    if ((st = launch_status()) != PSB_OK) return st;
+    heads_scan_kernel<<<1, 256, 0, s>>>(counts, nblocks, n_unique);
+    if ((st = launch_status()) != PSB_OK) return st;
+    heads_write_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts, n_unique, seg_start, unique_rows);
+    if ((st = launch_status()) != PSB_OK) return st;
+    sorted_slots = vi;
+  }
+
+  if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
+    const int grid = grid_for(n_total, 8, 8);
+    const int d4 = static_cast<int>(d / 4);
+#define PSB_SR_LAUNCH(C)                                                                                      \
+  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, seg_start, unique_rows, n_unique, d4,            \
+                                            reinterpret_cast<float4*>(reduced), reduced_bias,                 \
+                                            reinterpret_cast<float4*>(dense_grad), dense_bias_grad)
+    if (d4 <= 32) PSB_SR_LAUNCH(1);
+    else if (d4 <= 64) PSB_SR_LAUNCH(2);
+    else PSB_SR_LAUNCH(4);
+#undef PSB_SR_LAUNCH
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  return PSB_OK;
+}
+
+extern "C" int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows, int64_t d,
+                             float* dense, float* dense_bias, psb_stream_t stream) {
+  if (rows == nullptr || n_rows == nullptr || max_rows < 0) return PSB_E_ARG;
+  if (d <= 0 || (d & 3) != 0 || d > 512) return PSB_E_DIM;
+  if (misaligned16(dense)) return PSB_E_ALIGN;
+  if (max_rows == 0) return PSB_OK;
+  zero_rows_kernel<<<grid_for(max_rows, 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rows, n_rows, static_cast<int>(d / 4), reinterpret_cast<float4*>(dense), dense_bias);
+  return launch_status();
+}

@@ -1,0 +1,166 @@
+"""Thin Python mirrors of the C-ABI entry points (include/psb.h), on torch CUDA tensors.
+
+No autograd here and no fallback: these are the operator-level calls; the nn.Module
+surface (autograd.Functions, gradient sink) is in ``functional.py`` / the model files.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Contrib, check, load, ptr, stream_ptr
+
+f32, i64, i32, u8 = torch.float32, torch.int64, torch.int32, torch.uint8
+
+
+def _idx(t):
+    if t.dtype != i64:
+        t = t.long()
+    return t.contiguous()
+
+
+def gather_rows(table, idx, err_flag=None):
+    """out[..., :] = table[idx[...], :]   (psb_gather_rows; aten::embedding forward)."""
+    idx = _idx(idx)
+    n, d = idx.numel(), table.shape[1]
+    out = torch.empty(idx.shape + (d,), dtype=f32, device=table.device)
+    check(load().psb_gather_rows(ptr(table, f32), table.shape[0], d, ptr(idx), n, ptr(out), ptr(err_flag),
+                                 stream_ptr()), "psb_gather_rows")
+    return out
+
+
+def gather_meanpool(table, idx, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
+                    fs_bias=None, want_mean=False, want_inv_count=False):
+    """Fused gather + masked mean (+dropout multiplier, +fs projection); psb_gather_meanpool_fwd.
+    idx [n, w].  Returns (out [n,d], mean or None, inv_count or None)."""
+    idx = _idx(idx)
+    n, w = idx.shape
+    d = table.shape[1]
+    dev = table.device
+    out = torch.empty((n, d), dtype=f32, device=dev)
+    need_mean = want_mean or fs_weight is not None
+    mean = torch.empty((n, d), dtype=f32, device=dev) if need_mean else None
+    inv = torch.empty((n,), dtype=f32, device=dev) if want_inv_count else None
+    if mask is not None and mask.dtype != u8:
+        mask = mask.to(u8)
+    check(load().psb_gather_meanpool_fwd(
+        ptr(table, f32), table.shape[0], d, ptr(idx), n, w, int(pad_idx),
+        ptr(mask.contiguous() if mask is not None else None), ptr(tok_scale, f32), ptr(keep_scale, f32),
+        ptr(fs_weight, f32), ptr(fs_bias, f32), ptr(mean), ptr(out), ptr(inv), stream_ptr()),
+        "psb_gather_meanpool_fwd")
+    return out, mean, inv
+
+
+def fs_bwd(grad_out, out, mean, keep_scale, fs_weight):
+    n, d = out.shape
+    dev = out.device
+    gw = torch.empty((d, d), dtype=f32, device=dev)
+    gb = torch.empty((d,), dtype=f32, device=dev)
+    gm = torch.empty((n, d), dtype=f32, device=dev)
+    check(load().psb_fs_bwd(ptr(grad_out.contiguous(), f32), ptr(out, f32), ptr(mean, f32), ptr(keep_scale, f32),
+                            ptr(fs_weight, f32), n, d, ptr(gw), ptr(gb), ptr(gm), stream_ptr()), "psb_fs_bwd")
+    return gw, gb, gm
+
+
+def token_weights(idx, pad_idx=-1, mask=None):
+    """valid / max(#valid, 1) per token, the backward weights of a masked mean."""
+    idx = _idx(idx)
+    n, w = idx.shape
+    tw = torch.empty((n, w), dtype=f32, device=idx.device)
+    if mask is not None and mask.dtype != u8:
+        mask = mask.to(u8)
+    check(load().psb_meanpool_token_weights(ptr(idx), n, w, int(pad_idx),
+                                            ptr(mask.contiguous() if mask is not None else None), ptr(tw),
+                                            stream_ptr()), "psb_meanpool_token_weights")
+    return tw
+
+
+def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=None, pad_idx=-1,
+            neg_weight=None, pos_weight=1.0):
+    """Fused negative-sampling loss forward + analytic score gradient (psb_ns_loss_fwd).
+    pos_idx [n,w], neg_idx [n,w,k].  Returns loss [n], coef_pos [n,w], coef_neg [n,w,k],
+    grad_anchor_a [n,d], grad_anchor_b [n*k,d] or None."""
+    pos_idx = _idx(pos_idx)
+    neg_idx = _idx(neg_idx)
+    n, w = pos_idx.shape
+    k = neg_idx.numel() // max(n * w, 1)
+    d = table.shape[1]
+    dev = table.device
+    loss = torch.empty((n,), dtype=f32, device=dev)
+    cp = torch.empty((n, w), dtype=f32, device=dev)
+    cn = torch.empty((n, w, k), dtype=f32, device=dev)
+    ga = torch.empty((n, d), dtype=f32, device=dev)
+    gb = torch.empty((n * k, d), dtype=f32, device=dev) if anchor_b is not None else None
+    if mask is not None and mask.dtype != u8:
+        mask = mask.to(u8)
+    check(load().psb_ns_loss_fwd(
+        ptr(anchor_a, f32), ptr(anchor_b, f32), ptr(table, f32), table.shape[0], d, ptr(bias, f32), ptr(pos_idx),
+        ptr(neg_idx), ptr(mask.contiguous() if mask is not None else None), int(pad_idx), ptr(neg_weight, f32),
+        float(pos_weight), n, w, k, ptr(loss), ptr(cp), ptr(cn), ptr(ga), ptr(gb), stream_ptr()),
+        "psb_ns_loss_fwd")
+    return loss, cp, cn, ga, gb
+
+
+def make_contrib(idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
+    """One gradient contribution (psb_contrib_t).  Returns (struct, keepalive tensors)."""
+    idx = _idx(idx).reshape(-1)
+    keep = [idx, src, src_row, scale, scale2]
+    c = Contrib(ptr(idx), idx.numel(), ptr(src, f32), ptr(src_row, i64), int(src_div), ptr(scale, f32),
+                ptr(scale2, f32), int(scale2_div), 1 if to_bias else 0, 0)
+    return c, keep
+
+
+def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_bias_grad=None,
+                   want_rows=True, want_bias=False, device=None):
+    """Deterministic sort + segmented-reduce embedding backward (psb_scatter_reduce_rows).
+    contribs: list of (Contrib, keepalive).  Returns (unique_rows [n_total] int32, reduced or None,
+    reduced_bias or None, n_unique device int32 [1])."""
+    n_total = sum(int(c.n) for c, _ in contribs)
+    if device is None:
+        device = contribs[0][1][1].device
+    arr = (Contrib * len(contribs))(*[c for c, _ in contribs])
+    ws_bytes = int(load().psb_scatter_reduce_workspace_bytes(n_total, table_rows))
+    ws = torch.empty((ws_bytes,), dtype=u8, device=device)
+    cap = max(n_total, 1)
+    uniq = torch.empty((cap,), dtype=i32, device=device)
+    red = torch.empty((cap, d), dtype=f32, device=device) if want_rows else None
+    redb = torch.empty((cap,), dtype=f32, device=device) if want_bias else None
+    nu = torch.zeros((1,), dtype=i32, device=device)
+    if n_total > 0:
+        check(load().psb_scatter_reduce_rows(arr, len(contribs), table_rows, d, int(drop_idx), ptr(ws), ws_bytes,
+                                             ptr(uniq), ptr(red), ptr(redb), ptr(nu), ptr(dense_grad, f32),
+                                             ptr(dense_bias_grad, f32), stream_ptr()), "psb_scatter_reduce_rows")
+    return uniq, red, redb, nu
+
+
+def zero_rows(rows, n_rows, d, dense=None, dense_bias=None):
+    check(load().psb_zero_rows(ptr(rows, i32), ptr(n_rows, i32), rows.numel(), d, ptr(dense, f32),
+                               ptr(dense_bias, f32), stream_ptr()), "psb_zero_rows")
+
+
+def catalog_topk(queries, table, k, n_items=None, bias=None, id_base=0, id_stride=1, mode=_lib.TOPK_EXACT):
+    """Top-k items per query over the whole table with fused selection (psb_catalog_topk).
+    Returns (ids [m,k] int64, scores [m,k] fp32), descending score / ascending id."""
+    m, d = queries.shape
+    n_items = table.shape[0] if n_items is None else int(n_items)
+    dev = queries.device
+    ws_bytes = int(load().psb_catalog_topk_workspace_bytes(m, n_items, d, k, mode))
+    if ws_bytes < 0:
+        check(ws_bytes, "psb_catalog_topk_workspace_bytes")
+    ws = torch.empty((ws_bytes,), dtype=u8, device=dev)
+    ids = torch.empty((m, k), dtype=i64, device=dev)
+    sc = torch.empty((m, k), dtype=f32, device=dev)
+    check(load().psb_catalog_topk(ptr(queries, f32), m, ptr(table, f32), n_items, d, ptr(bias, f32), k,
+                                  int(id_base), int(id_stride), mode, ptr(ws), ws_bytes, ptr(ids), ptr(sc),
+                                  stream_ptr()), "psb_catalog_topk")
+    return ids, sc
+
+
+def topk_merge(ids, scores):
+    """Merge per-shard lists [g, m, k] (all_gather layout) into the global top-k [m, k]."""
+    g, m, k = ids.shape
+    out_i = torch.empty((m, k), dtype=i64, device=ids.device)
+    out_s = torch.empty((m, k), dtype=f32, device=ids.device)
+    check(load().psb_topk_merge(ptr(ids, i64), ptr(scores, f32), g, m, k, ptr(out_i), ptr(out_s), stream_ptr()),
+          "psb_topk_merge")
+    return out_i, out_s

@@ -1,0 +1,56 @@
+"""CPU: libpsb_b200.so loads and exports every symbol include/psb.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "psb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(psb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from prodsearch_b200 import _lib
+    from prodsearch_b200.build import build_library
+    build_library()
+    names = _declared()
+    assert len(names) >= 13
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "no ctypes signature for " + n
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.load().psb_abi_version() == 1
+    assert _lib.status_string(0) == "ok" and "aligned" in _lib.status_string(-4)
+
+
+def test_contrib_struct_layout():
+    from prodsearch_b200 import _lib
+    assert ctypes.sizeof(_lib.Contrib) == 72          # psb_contrib_t: 8 x 8-byte fields + 2 x int32
+
+
+def test_argument_validation_without_gpu():
+    """Host-side argument checks return PSB_E_* before any CUDA call."""
+    from prodsearch_b200 import _lib
+    lib = _lib.load()
+    assert lib.psb_gather_rows(None, 10, 128, None, 0, None, None, None) == -1          # null table
+    assert lib.psb_gather_rows(16, 10, 130, None, 0, None, None, None) == -2            # d % 4 != 0
+    assert lib.psb_gather_rows(8, 10, 128, None, 0, None, None, None) == -4             # misaligned
+    assert lib.psb_gather_rows(16, 10, 128, None, 0, None, None, None) == 0             # n == 0: no launch
+    assert lib.psb_scatter_reduce_workspace_bytes(1000, 50) > 16 * 1000
+    assert lib.psb_catalog_topk_workspace_bytes(4, 100, 128, 10, 7) == -5               # bad mode
+    assert lib.psb_launch_count() == 0
+
+
+def test_no_oracle_or_reference_in_product():
+    """The product path may not import the oracle or read /root/reference."""
+    pkg = os.path.join(ROOT, "prodsearch_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "/root/reference" not in src, f
