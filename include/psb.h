@@ -123,6 +123,13 @@ int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b,
                     float* grad_anchor_a, float* grad_anchor_b,
                     psb_stream_t stream);
 
+/* scores[i,c] = <anchor[i], table[idx[i,c]]> (+ bias[idx[i,c]]): candidate scoring of
+ * test_dotproduct (models/item_transformer.py:141-145) for an explicit candidate list
+ * idx [n, c_per] (the reference's 500-candidate segments, item_pv_dataset.py:65-68). */
+int psb_score_rows(const float* anchor, const float* table, int64_t table_rows, int64_t d,
+                   const float* bias, const int64_t* idx, int64_t n, int64_t c_per, float* scores,
+                   psb_stream_t stream);
+
 /* ------------------------------------------------------------------ G2 ---
  * Deterministic embedding backward: sort-then-segmented-reduce instead of float
  * atomics.  Replaces aten::embedding_dense_backward (autograd of every K1 site).

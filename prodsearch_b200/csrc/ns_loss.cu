@@ -136,9 +136,86 @@ ns_loss_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ a
   }
 }
 
+// scores[i, c] = <anchor[i], table[idx[i, c]]> (+ bias[idx[i, c]]): the candidate scoring of
+// test_dotproduct (item_transformer.py:141-145).  One warp per query, 4 candidate rows in flight.
+template <int C>
+__global__ void __launch_bounds__(256)
+score_rows_kernel(const float4* __restrict__ anchor, const float4* __restrict__ table, int64_t table_rows, int d4,
+                  const float* __restrict__ bias, const int64_t* __restrict__ idx, int64_t n, int c_per,
+                  float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int groups = (c_per + 31) / 32;   // a warp handles 32 candidates of one query at a time
+  for (int64_t item = warp; item < n * groups; item += nwarps) {
+    const int64_t i = item / groups;
+    const int c0 = static_cast<int>(item % groups) * 32;
+    float4 a[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      a[c] = col < d4 ? anchor[i * d4 + col] : zero4();
+    }
+    const int cn = min(32, c_per - c0);
+    int64_t my = -1;
+    if (lane < cn) {
+      my = idx[i * c_per + c0 + lane];
+      if (my < 0 || my >= table_rows) my = -1;
+    }
+    float mine = 0.f;
+    for (int j = 0; j < cn; j += 4) {
+      int64_t r[4];
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = __shfl_sync(kFull, my, min(j + u, 31));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float t = 0.f;
+        if (j + u < cn && r[u] >= 0) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int col = lane + 32 * c;
+            if (col < d4) t += dot4(a[c], ldg_row4(table + r[u] * d4 + col));
+          }
+        }
+        part[u] = t;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float t = warp_sum(part[u]);
+        if (lane == j + u) mine = t;
+      }
+    }
+    if (lane < cn) scores[i * c_per + c0 + lane] = mine + ((bias != nullptr && my >= 0) ? bias[my] : 0.f);
+  }
+}
+
 }  // namespace psb
 
 using namespace psb;
+
+extern "C" int psb_score_rows(const float* anchor, const float* table, int64_t table_rows, int64_t d,
+                              const float* bias, const int64_t* idx, int64_t n, int64_t c_per, float* scores,
+                              psb_stream_t stream) {
+  int st = check_table_args(table, table_rows, d);
+  if (st != PSB_OK) return st;
+  if (n < 0 || c_per <= 0) return PSB_E_ARG;
+  if (n == 0) return PSB_OK;
+  if (anchor == nullptr || idx == nullptr || scores == nullptr) return PSB_E_ARG;
+  if (misaligned16(anchor)) return PSB_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int d4 = static_cast<int>(d / 4);
+  const int grid = grid_for(n * ((c_per + 31) / 32), 8);
+#define PSB_SC_LAUNCH(C)                                                                                     \
+  score_rows_kernel<C><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(anchor),                         \
+                                            reinterpret_cast<const float4*>(table), table_rows, d4, bias, idx, n, \
+                                            static_cast<int>(c_per), scores)
+  if (d4 <= 32) PSB_SC_LAUNCH(1);
+  else if (d4 <= 64) PSB_SC_LAUNCH(2);
+  else PSB_SC_LAUNCH(4);
+#undef PSB_SC_LAUNCH
+  return launch_status();
+}
 
 extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, const float* table,
                                int64_t table_rows, int64_t d, const float* bias, const int64_t* pos_idx,

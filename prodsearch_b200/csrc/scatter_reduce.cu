@@ -354,61 +354,149 @@ heads_write_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentin
 }
 
 // ------------------------------------------------------------------------------------
-// Segmented reduction: one warp per destination row, terms added in sorted (= slot) order.
+// Segmented reduction.  The sorted slot list is cut into fixed units of 2^ch_shift positions; one
+// warp reduces one unit, walking the destination-row segments inside it in order.  A segment that
+// lies inside one unit is written directly; a segment spanning several units (a popular row:
+// Zipf head, the 4-row segment table) leaves one partial per unit, and the fix-up kernel adds the
+// partials in unit order.  Terms are therefore always added in ascending (contribution, slot)
+// order with a bracketing that depends only on (n_total, data): bit-reproducible, no atomics.
 // ------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void accumulate_run(const ContribTable& T, const uint32_t* __restrict__ sorted_slots,
+                                               int lo, int hi, int d4, int lane, float4 (&acc)[C], float& bacc) {
+  constexpr int U = 4;
+  for (int p = lo; p < hi; p += U) {
+    const float4* srcp[U];
+    float sc[U];
+    bool tb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      srcp[u] = nullptr;
+      sc[u] = 0.f;
+      tb[u] = false;
+      if (p + u < hi) {
+        const uint32_t slot = sorted_slots[p + u];
+        const int ci = locate(T, slot);
+        const psb_contrib_t& cc = T.c[ci];
+        const uint32_t i = slot - T.off[ci];
+        const int64_t row = cc.src_row != nullptr ? cc.src_row[i]
+                                                  : static_cast<int64_t>(i / static_cast<uint32_t>(cc.src_div));
+        float s = cc.scale != nullptr ? cc.scale[i] : 1.f;
+        if (cc.scale2 != nullptr) s *= cc.scale2[i / static_cast<uint32_t>(cc.scale2_div)];
+        sc[u] = s;
+        tb[u] = cc.to_bias != 0;
+        srcp[u] = reinterpret_cast<const float4*>(cc.src) + row * d4;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (srcp[u] != nullptr && col < d4) ? __ldg(srcp[u] + col) : zero4();
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma4(acc[c], sc[u], v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (tb[u]) bacc += sc[u];
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __restrict__ sorted_slots,
                   const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
-                  const int32_t* __restrict__ n_unique, int d4, float4* __restrict__ reduced,
-                  float* __restrict__ reduced_bias, float4* __restrict__ dense,
-                  float* __restrict__ dense_bias) {
+                  const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
+                  float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
+                  float4* __restrict__ partial, float* __restrict__ partial_bias) {
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nu = *n_unique;
-  constexpr int U = 4;
-  for (int seg = warp; seg < nu; seg += nwarps) {
-    const int lo = seg_start[seg], hi = seg_start[seg + 1];
+  if (nu == 0) return;
+  const int n_valid = seg_start[nu];
+  const int ch = 1 << ch_shift;
+  const int n_units = (n_valid + ch - 1) >> ch_shift;
+  for (int unit = warp; unit < n_units; unit += nwarps) {
+    const int u_lo = unit << ch_shift;
+    const int u_hi = min(u_lo + ch, n_valid);
+    // segment containing position u_lo: largest seg with seg_start[seg] <= u_lo
+    int a = 0, b = nu;  // invariant: seg_start[a] <= u_lo < seg_start[b]
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (seg_start[mid] <= u_lo) a = mid; else b = mid;
+    }
+    int seg = a;
+    int p = u_lo;
+    while (p < u_hi) {
+      const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
+      const int r_hi = min(s_hi, u_hi);
+      float4 acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = zero4();
+      float bacc = 0.f;
+      accumulate_run<C>(T, sorted_slots, p, r_hi, d4, lane, acc, bacc);
+      const bool starts_here = s_lo >= u_lo;
+      const bool ends_here = s_hi <= u_hi;
+      if (starts_here && ends_here) {
+        const int64_t drow = unique_rows[seg];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = lane + 32 * c;
+          if (col < d4) {
+            if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+            if (dense != nullptr) dense[drow * d4 + col] = acc[c];
+          }
+        }
+        if (lane == 0) {
+          if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+          if (dense_bias != nullptr) dense_bias[drow] = bacc;
+        }
+      } else {
+        const int64_t ps = static_cast<int64_t>(unit) * 2 + (starts_here ? 1 : 0);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = lane + 32 * c;
+          if (col < d4) partial[ps * d4 + col] = acc[c];
+        }
+        if (lane == 0) partial_bias[ps] = bacc;
+      }
+      p = r_hi;
+      ++seg;
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
+                 const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
+                 float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
+                 const float4* __restrict__ partial, const float* __restrict__ partial_bias) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nu = *n_unique;
+  for (int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < nu; seg += nwarps) {
+    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
+    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
+    if (u_first == u_last) continue;  // written directly by seg_reduce_kernel
     float4 acc[C];
+    float bacc = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = zero4();
-    float bacc = 0.f;
-    for (int p = lo; p < hi; p += U) {
-      const float4* srcp[U];
-      float sc[U];
-      bool tb[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        srcp[u] = nullptr;
-        sc[u] = 0.f;
-        tb[u] = false;
-        if (p + u < hi) {
-          const uint32_t slot = sorted_slots[p + u];
-          const int ci = locate(T, slot);
-          const psb_contrib_t& cc = T.c[ci];
-          const uint32_t i = slot - T.off[ci];
-          const int64_t row = cc.src_row != nullptr ? cc.src_row[i]
-                                                    : static_cast<int64_t>(i / static_cast<uint32_t>(cc.src_div));
-          float s = cc.scale != nullptr ? cc.scale[i] : 1.f;
-          if (cc.scale2 != nullptr) s *= cc.scale2[i / static_cast<uint32_t>(cc.scale2_div)];
-          sc[u] = s;
-          tb[u] = cc.to_bias != 0;
-          srcp[u] = reinterpret_cast<const float4*>(cc.src) + row * d4;
-        }
-      }
+    for (int u = u_first; u <= u_last; ++u) {
+      // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
+      const int64_t ps = static_cast<int64_t>(u) * 2 + (u == u_first ? 1 : 0);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int col = lane + 32 * c;
-        float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = (srcp[u] != nullptr && col < d4) ? __ldg(srcp[u] + col) : zero4();
-#pragma unroll
-        for (int u = 0; u < U; ++u) fma4(acc[c], sc[u], v[u]);
+        if (col < d4) {
+          const float4 v = partial[ps * d4 + col];
+          acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+        }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (tb[u]) bacc += sc[u];
+      bacc += partial_bias[ps];
     }
     const int64_t drow = unique_rows[seg];
 #pragma unroll
@@ -443,10 +531,17 @@ zero_rows_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ n
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
-  int64_t keys_a, vals_a, keys_b, vals_b, hist, totals, counts, seg_start, total;
+  int64_t keys_a, vals_a, keys_b, vals_b, hist, totals, counts, seg_start, partial, partial_bias, total;
 };
 
-static WorkspaceLayout layout_for(int64_t n_total) {
+// unit size of the segmented reduction: a pure function of n_total (~4k+ units, 8..256 slots each)
+static int unit_shift_for(int64_t n_total) {
+  int sh = 3;
+  while (sh < 8 && (n_total >> sh) > 8192) ++sh;
+  return sh;
+}
+
+static WorkspaceLayout layout_for(int64_t n_total, int64_t d = 512) {
   WorkspaceLayout L;
   const int64_t nblocks = (n_total + kTile - 1) / kTile + 1;
   int64_t o = 0;
@@ -458,6 +553,9 @@ static WorkspaceLayout layout_for(int64_t n_total) {
   L.totals = o; o += 1024;
   L.counts = o; o += align_up(4 * (nblocks + 1), 256);
   L.seg_start = o; o += align_up(4 * (n_total + 2), 256);
+  const int64_t n_units = (n_total >> unit_shift_for(n_total)) + 2;
+  L.partial = o; o += align_up(2 * n_units * d * 4, 256);
+  L.partial_bias = o; o += align_up(2 * n_units * 4, 256);
   L.total = o + 256;
   return L;
 }
@@ -555,15 +653,25 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   }
 
   if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
-    const int grid = grid_for(n_total, 8, 8);
+    const int ch_shift = unit_shift_for(n_total);
+    const int grid = grid_for((n_total >> ch_shift) + 1, 8, 16);
+    const int grid_fix = grid_for(n_total, 8 * 8, 8);
     const int d4 = static_cast<int>(d / 4);
+    float4* partial = reinterpret_cast<float4*>(ws + L.partial);
+    float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);
 #define PSB_SR_LAUNCH(C)                                                                                      \
-  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, seg_start, unique_rows, n_unique, d4,            \
+  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, seg_start, unique_rows, n_unique, d4, ch_shift,  \
                                             reinterpret_cast<float4*>(reduced), reduced_bias,                 \
-                                            reinterpret_cast<float4*>(dense_grad), dense_bias_grad)
-    if (d4 <= 32) PSB_SR_LAUNCH(1);
-    else if (d4 <= 64) PSB_SR_LAUNCH(2);
-    else PSB_SR_LAUNCH(4);
+                                            reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial,  \
+                                            partial_bias);                                                    \
+  if ((st = launch_status()) != PSB_OK) return st;                                                            \
+  seg_fixup_kernel<C><<<grid_fix, 256, 0, s>>>(seg_start, unique_rows, n_unique, d4, ch_shift,                \
+                                               reinterpret_cast<float4*>(reduced), reduced_bias,              \
+                                               reinterpret_cast<float4*>(dense_grad), dense_bias_grad,        \
+                                               partial, partial_bias)
+    if (d4 <= 32) { PSB_SR_LAUNCH(1); }
+    else if (d4 <= 64) { PSB_SR_LAUNCH(2); }
+    else { PSB_SR_LAUNCH(4); }
 #undef PSB_SR_LAUNCH
     if ((st = launch_status()) != PSB_OK) return st;
   }

@@ -1,0 +1,194 @@
+"""Autograd surface over the C-ABI ops: the piece that lets ``loss.backward()`` in the
+reference's trainer (trainer.py:77) drive the sm_100a kernels.
+
+Embedding-table gradients never flow through autograd as dense [rows, d] tensors (the
+reference's embedding_dense_backward).  Each op *registers a contribution*
+(indices + source rows + per-slot scales) with the table's ``RowGradSink``; when the backward
+pass finishes, one deterministic sort + segmented-reduce per table (psb_scatter_reduce_rows)
+produces the gradient, either scattered into a persistent dense ``.grad`` (drop-in for the
+reference's dense Adam) or kept row-sparse as ``param.row_grad = (rows, values, n_rows)``.
+"""
+import torch
+from torch.autograd import Function, Variable
+
+from . import ops
+
+
+class RowGradSink(object):
+    """Gradient collector for one embedding table (and the bias vector indexed like it)."""
+
+    def __init__(self, weight, drop_idx=-1, bias=None, mode="dense"):
+        self.weight = weight
+        self.bias = bias
+        self.drop_idx = drop_idx
+        self.mode = mode              # "dense" | "rowsparse"
+        self._pending = []
+        self._queued = False
+        self._dense = None
+        self._dense_bias = None
+        self._prev = None             # (unique_rows, n_unique) written into the dense buffers last time
+
+    # -- called from Function.backward ------------------------------------------------
+    def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
+        if not self.weight.requires_grad and not (to_bias and self.bias is not None and self.bias.requires_grad):
+            return
+        self._pending.append(ops.make_contrib(idx, src, src_row, src_div, scale, scale2, scale2_div,
+                                              to_bias and self.bias is not None))
+        if not self._queued:
+            self._queued = True
+            Variable._execution_engine.queue_callback(self.finalize)
+
+    # -- runs once, after the whole backward graph has executed --------------------------
+    def finalize(self):
+        self._queued = False
+        pending, self._pending = self._pending, []
+        if not pending:
+            return
+        w = self.weight
+        rows, d = w.shape
+        want_bias = self.bias is not None and any(c.to_bias for c, _ in pending)
+        for lo in range(0, len(pending), ops._lib.MAX_CONTRIBS):
+            chunk = pending[lo:lo + ops._lib.MAX_CONTRIBS]
+            first = lo == 0
+            if self.mode == "dense":
+                self._prepare_dense(want_bias, clear=first)
+                if not first:
+                    raise RuntimeError("more than %d contributions to one table in a step" % ops._lib.MAX_CONTRIBS)
+                uniq, _, _, nu = ops.scatter_reduce(chunk, rows, d, self.drop_idx, dense_grad=self._dense,
+                                                    dense_bias_grad=self._dense_bias if want_bias else None,
+                                                    want_rows=False, device=w.device)
+                self._prev = (uniq, nu)
+                self._attach(w, self._dense)
+                if want_bias:
+                    self._attach(self.bias, self._dense_bias)
+            else:
+                uniq, red, redb, nu = ops.scatter_reduce(chunk, rows, d, self.drop_idx, want_rows=True,
+                                                         want_bias=want_bias, device=w.device)
+                w.row_grad = (uniq, red, nu)
+                if want_bias:
+                    self.bias.row_grad = (uniq, redb, nu)
+
+    def _prepare_dense(self, want_bias, clear):
+        w = self.weight
+        if self._dense is None:
+            self._dense = torch.zeros_like(w)
+            self._prev = None
+        if want_bias and self._dense_bias is None:
+            self._dense_bias = torch.zeros_like(self.bias)
+        if clear and self._prev is not None:
+            uniq, nu = self._prev
+            if w.numel() * 4 <= (64 << 20):       # small table: a memset beats a row list
+                self._dense.zero_()
+                if self._dense_bias is not None:
+                    self._dense_bias.zero_()
+            else:
+                ops.zero_rows(uniq, nu, w.shape[1], self._dense, self._dense_bias)
+            self._prev = None
+
+    @staticmethod
+    def _attach(param, buf):
+        if param.grad is None or param.grad is buf:
+            param.grad = buf
+        else:                          # user-side gradient accumulation: keep torch semantics
+            param.grad = param.grad + buf
+
+
+def _dropout_keep(shape, p, training, device):
+    """Dropout mask already scaled by 1/(1-p) (None when inactive)."""
+    if not training or p <= 0.0:
+        return None
+    return torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
+
+
+class GatherRowsFn(Function):
+    """aten::embedding with the backward routed to the table's RowGradSink."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, sink):
+        ctx.sink, ctx.idx = sink, idx
+        return ops.gather_rows(weight, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        d = g.shape[-1]
+        ctx.sink.add(ctx.idx.reshape(-1), g.contiguous().view(-1, d))
+        return None, None, None
+
+
+class MeanPoolFn(Function):
+    """Fused gather + masked mean (+dropout, +fs); psb_gather_meanpool_fwd / psb_fs_bwd."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale):
+        out, mean, _ = ops.gather_meanpool(weight, idx, pad_idx=pad_idx, mask=mask, tok_scale=tok_scale,
+                                           keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias)
+        ctx.sink, ctx.idx, ctx.pad_idx, ctx.mask, ctx.keep = sink, idx, pad_idx, mask, keep_scale
+        ctx.fs = fs_weight is not None
+        if ctx.fs:
+            ctx.save_for_backward(out, mean, fs_weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        gw = gb = None
+        if ctx.fs:
+            out, mean, fs_weight = ctx.saved_tensors
+            gw, gb, gm = ops.fs_bwd(g, out, mean, ctx.keep, fs_weight)
+        else:
+            gm = g if ctx.keep is None else g * ctx.keep
+        idx = ctx.idx
+        tw = ops.token_weights(idx, pad_idx=ctx.pad_idx, mask=ctx.mask)
+        ctx.sink.add(idx.reshape(-1), gm, src_div=idx.shape[1], scale=tw.view(-1))
+        return None, None, gw, gb, None, None, None, None, None
+
+
+class NSLossFn(Function):
+    """Fused negative-sampling loss (psb_ns_loss_fwd); returns the per-anchor loss [n]."""
+
+    @staticmethod
+    def forward(ctx, anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
+                pos_weight):
+        loss, cp, cn, ga, gb = ops.ns_loss(anchor_a, weight, pos_idx, neg_idx, anchor_b=anchor_b, bias=bias,
+                                           mask=mask, pad_idx=pad_idx, neg_weight=neg_weight,
+                                           pos_weight=pos_weight)
+        ctx.sink, ctx.pos_idx, ctx.neg_idx = sink, pos_idx, neg_idx
+        ctx.has_b, ctx.has_bias = anchor_b is not None, bias is not None
+        ctx.save_for_backward(anchor_a, anchor_b, cp, cn, ga, gb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        anchor_a, anchor_b, cp, cn, ga, gb = ctx.saved_tensors
+        g = g.contiguous()
+        n, w = ctx.pos_idx.shape
+        k = cn.shape[-1]
+        ctx.sink.add(ctx.pos_idx.reshape(-1), anchor_a, src_div=w, scale=cp.view(-1), scale2=g, scale2_div=w,
+                     to_bias=ctx.has_bias)
+        if k > 0:
+            if ctx.has_b:
+                ctx.sink.add(ctx.neg_idx.reshape(-1), anchor_b, src_div=1, scale=cn.view(-1), scale2=g,
+                             scale2_div=w * k, to_bias=ctx.has_bias)
+            else:
+                ctx.sink.add(ctx.neg_idx.reshape(-1), anchor_a, src_div=w * k, scale=cn.view(-1), scale2=g,
+                             scale2_div=w * k, to_bias=ctx.has_bias)
+        grad_a = ga * g.unsqueeze(1) if ctx.needs_input_grad[0] else None
+        grad_b = None
+        if ctx.has_b and ctx.needs_input_grad[1]:
+            grad_b = gb * g.repeat_interleave(k).unsqueeze(1)
+        return grad_a, grad_b, None, None, None, None, None, None, None, None, None
+
+
+def gather_rows(weight, idx, sink):
+    return GatherRowsFn.apply(weight, idx, sink)
+
+
+def meanpool(weight, idx, sink, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
+             fs_bias=None):
+    return MeanPoolFn.apply(weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale)
+
+
+def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, pad_idx=-1, mask=None,
+            neg_weight=None, pos_weight=1.0):
+    return NSLossFn.apply(anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
+                          pos_weight)

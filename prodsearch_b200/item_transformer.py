@@ -1,0 +1,203 @@
+"""TEM: ``ItemTransformerRanker`` (reference models/item_transformer.py) on the sm_100a hot path.
+
+Drop-in for the reference class behind ``model(batch)`` / ``model.test(batch)``
+(trainer.py:74,:201): same constructor, same state_dict keys, same ``ps_loss`` /
+``item_loss`` / ``clear_loss()`` bookkeeping, same RNG draw order (item negatives, then word
+negatives: item_transformer.py:447,:268).  Implemented paths: ``forward_dotproduct`` (:440),
+``test_dotproduct`` (:111), ``item_to_words`` (:260) -- the defaults of the reference
+(``--use_dot_prod True``).  The ``*_trans`` / ``*_attn`` / ``*_seq`` variants are out of scope
+(SURVEY.md 2.1 C1).  New, additive: ``rank_catalog`` (full-catalog top-k without the
+[M, N] matrix) and ``encode_queries``.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import functional as F_
+from . import ops
+from .text_encoder import AVGEncoder, FSEncoder
+from .transformer import TransformerEncoder
+
+
+class ItemTransformerRanker(nn.Module):
+    def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None,
+                 grad_mode="dense"):
+        super().__init__()
+        if args.model_name != "item_transformer" or not args.use_dot_prod:
+            raise NotImplementedError("only the default TEM path (item_transformer + use_dot_prod) is built")
+        if getattr(args, "pretrain_emb_dir", "") or getattr(args, "pretrain_up_emb_dir", ""):
+            import os
+            if os.path.exists(args.pretrain_emb_dir) or os.path.exists(args.pretrain_up_emb_dir):
+                raise NotImplementedError("pretrained embedding files: load them with load_state_dict")
+        self.args = args
+        self.device = device
+        self.train_review_only = args.train_review_only
+        self.embedding_size = args.embedding_size
+        self.vocab_words = vocab_words
+        self.word_dists = None
+        if word_dists is not None:
+            self.word_dists = torch.as_tensor(word_dists, dtype=torch.float32, device=device)
+        self.prod_dists = torch.ones(product_size, device=device)
+        self.prod_pad_idx = product_size
+        self.word_pad_idx = vocab_size - 1
+        self.seg_pad_idx = 3
+        self.emb_dropout = args.dropout
+        d = self.embedding_size
+        self.product_emb = nn.Embedding(product_size + 1, d, padding_idx=self.prod_pad_idx)
+        if args.sep_prod_emb:
+            self.hist_product_emb = nn.Embedding(product_size + 1, d, padding_idx=self.prod_pad_idx)
+        self.product_bias = nn.Parameter(torch.zeros(product_size + 1), requires_grad=True)
+        self.word_bias = nn.Parameter(torch.zeros(vocab_size), requires_grad=True)
+        self.word_embeddings = nn.Embedding(vocab_size, d, padding_idx=self.word_pad_idx)
+        self.transformer_encoder = TransformerEncoder(d, args.ff_size, args.heads, args.dropout, args.inter_layers)
+        if args.query_encoder_name == "fs":
+            self.query_encoder = FSEncoder(d, self.emb_dropout)
+        else:
+            self.query_encoder = AVGEncoder(d, self.emb_dropout)
+        self.seg_embeddings = nn.Embedding(4, d, padding_idx=self.seg_pad_idx)
+        self.initialize_parameters()
+        self.to(device)
+        self.grad_mode = grad_mode
+        self._make_sinks()
+        self.injected_negatives = None      # (neg_item_idxs [B,K], neg_word_idxs [B*W*K]) for parity runs
+        self._ps_acc = None
+        self._item_acc = None
+
+    # ---- bookkeeping the trainer reads (trainer.py:88-98) ---------------------------------
+    def _make_sinks(self):
+        # nn.Embedding(padding_idx) zeroes the pad row's gradient -> drop_idx
+        self.item_sink = F_.RowGradSink(self.product_emb.weight, self.prod_pad_idx, self.product_bias,
+                                        self.grad_mode)
+        self.hist_sink = (F_.RowGradSink(self.hist_product_emb.weight, self.prod_pad_idx, None, self.grad_mode)
+                          if self.args.sep_prod_emb else self.item_sink)
+        self.word_sink = F_.RowGradSink(self.word_embeddings.weight, self.word_pad_idx, self.word_bias,
+                                        self.grad_mode)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if hasattr(self, "item_sink"):
+            self._make_sinks()              # parameters may have been re-created (.to / .cuda)
+        return out
+
+    @property
+    def ps_loss(self):
+        return 0 if self._ps_acc is None else float(self._ps_acc)
+
+    @property
+    def item_loss(self):
+        return 0 if self._item_acc is None else float(self._item_acc)
+
+    def clear_loss(self):
+        self._ps_acc = None
+        self._item_acc = None
+
+    def load_cp(self, pt, strict=True):
+        self.load_state_dict(pt["model"], strict=strict)
+
+    def initialize_parameters(self, logger=None):
+        """item_transformer.py:576-586: N(0,1) word and segment tables (pad row included),
+        default nn.Embedding init for product tables (pad row zero)."""
+        nn.init.normal_(self.word_embeddings.weight)
+        nn.init.normal_(self.seg_embeddings.weight)
+        self.query_encoder.initialize_parameters(logger)
+        self.transformer_encoder.initialize_parameters(logger)
+
+    # ---- shared front half -----------------------------------------------------------
+    def encode_queries(self, query_word_idxs, u_item_idxs, copies=1):
+        """Query encoder + history gather + transformer encode -> [B*copies, d]
+        (item_transformer.py:449-484 / :118-140)."""
+        B, L = u_item_idxs.shape
+        q_emb = self.query_encoder.encode_indices(self.word_embeddings.weight, query_word_idxs, self.word_sink,
+                                                  pad_idx=self.word_pad_idx)
+        hist_w = self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight
+        u_emb = F_.gather_rows(hist_w, u_item_idxs, self.hist_sink)
+        seq = torch.cat([q_emb.unsqueeze(1), u_emb], dim=1)
+        mask = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=seq.device),
+                          u_item_idxs.ne(self.prod_pad_idx)], dim=1)
+        if copies > 1:
+            seq = seq.unsqueeze(1).expand(-1, copies, -1, -1).reshape(B * copies, 1 + L, -1)
+            mask = mask.unsqueeze(1).expand(-1, copies, -1).reshape(B * copies, 1 + L)
+        out_pos = -1 if self.args.use_item_pos else 0
+        top = self.transformer_encoder.encode(seq, mask, use_pos=self.args.use_pos_emb)
+        return top[:, out_pos, :]
+
+    # ---- training -----------------------------------------------------------------------
+    def forward(self, batch_data, train_pv=False):
+        return self.forward_dotproduct(batch_data)
+
+    def _draw_negatives(self, B, W, K):
+        if self.injected_negatives is not None:
+            neg_items, neg_words = self.injected_negatives
+            return neg_items.view(B, K), neg_words.view(B, W, K)
+        neg_items = torch.multinomial(self.prod_dists, B * K, replacement=True).view(B, K)
+        return neg_items, None
+
+    def forward_dotproduct(self, batch_data, train_pv=False):
+        query_word_idxs = batch_data.query_word_idxs
+        target_prod_idxs = batch_data.target_prod_idxs
+        u_item_idxs = batch_data.u_item_idxs
+        pos_iword_idxs = batch_data.pos_iword_idxs
+        B, _ = u_item_idxs.shape
+        K = self.args.neg_per_pos
+        W = pos_iword_idxs.shape[1]
+        neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+        stochastic = self.training and self.args.dropout > 0
+        if stochastic:
+            # dropout makes the K negative encodes differ (transformer.py:56, neural.py:226)
+            pos_out = self.encode_queries(query_word_idxs, u_item_idxs)
+            neg_out = self.encode_queries(query_word_idxs, u_item_idxs, copies=K)
+        else:
+            # deterministic encoder: the K copies the reference re-encodes (:473-476) are identical
+            pos_out = self.encode_queries(query_word_idxs, u_item_idxs)
+            neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
+        bias = self.product_bias if self.args.sim_func == "bias_product" else None
+        pos_weight = float(K) if self.args.pos_weight else 1.0
+        ps = F_.ns_loss(pos_out.contiguous(), self.product_emb.weight, target_prod_idxs.view(B, 1),
+                        neg_item_idxs.view(B, 1, K), self.item_sink, anchor_b=neg_out.contiguous(), bias=bias,
+                        pos_weight=pos_weight)
+        ps_loss = ps.mean()
+        item_loss = self.item_to_words(target_prod_idxs, pos_iword_idxs, K, neg_word_idxs)
+        with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here)
+            self._ps_acc = ps_loss.detach() if self._ps_acc is None else self._ps_acc + ps_loss.detach()
+            self._item_acc = item_loss.detach() if self._item_acc is None else self._item_acc + item_loss.detach()
+        return ps_loss + item_loss
+
+    def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None):
+        """item_transformer.py:260-283."""
+        B, W = target_word_idxs.shape
+        if neg_sample_idxs is None:
+            neg_sample_idxs = torch.multinomial(self.word_dists, B * W * n_negs, replacement=True)
+        anchor = F_.gather_rows(self.product_emb.weight, target_prod_idxs, self.item_sink)
+        loss = F_.ns_loss(anchor, self.word_embeddings.weight, target_word_idxs,
+                          neg_sample_idxs.view(B, W, n_negs), self.word_sink, bias=self.word_bias,
+                          pad_idx=self.word_pad_idx)
+        return loss.mean()
+
+    # ---- evaluation ---------------------------------------------------------------------
+    def test(self, batch_data):
+        return self.test_dotproduct(batch_data)
+
+    def test_dotproduct(self, batch_data):
+        """Scores of an explicit candidate list [B, candi_k] (item_transformer.py:111-146).  The
+        encoder output does not depend on the candidate, so it is computed once
+        per query instead of candi_k times."""
+        with torch.no_grad():
+            q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs).contiguous()
+            bias = self.product_bias if self.args.sim_func == "bias_product" else None
+            return ops.score_rows(q, self.product_emb.weight, batch_data.candi_prod_idxs, bias)
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_EXACT):
+        """Top-k over the whole catalog (items 0..P-1) with fused selection; replaces
+        get_prod_scores + host argsort (trainer.py:189-226,:152).  Returns (ids [M,k], scores [M,k])."""
+        with torch.no_grad():
+            if torch.is_tensor(batch_or_queries):
+                q = batch_or_queries
+            else:
+                q = self.encode_queries(batch_or_queries.query_word_idxs, batch_or_queries.u_item_idxs)
+            bias = self.product_bias if self.args.sim_func == "bias_product" else None
+            return ops.catalog_topk(q.contiguous(), self.product_emb.weight, k, n_items=self.prod_pad_idx,
+                                    bias=bias, mode=mode)
+
+
+# the north star names the class ProdSearchModel; the reference's real name is kept as primary
+ProdSearchModel = ItemTransformerRanker

@@ -101,6 +101,16 @@ def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=No
     return loss, cp, cn, ga, gb
 
 
+def score_rows(anchor, table, idx, bias=None):
+    """scores[i,c] = <anchor[i], table[idx[i,c]]> (+bias) for an explicit candidate list (psb_score_rows)."""
+    idx = _idx(idx)
+    n, c = idx.shape
+    out = torch.empty((n, c), dtype=f32, device=table.device)
+    check(load().psb_score_rows(ptr(anchor, f32), ptr(table, f32), table.shape[0], table.shape[1], ptr(bias, f32),
+                                ptr(idx), n, c, ptr(out), stream_ptr()), "psb_score_rows")
+    return out
+
+
 def make_contrib(idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
     """One gradient contribution (psb_contrib_t).  Returns (struct, keepalive tensors)."""
     idx = _idx(idx).reshape(-1)

@@ -1,0 +1,96 @@
+"""Query / text encoders (reference models/text_encoder.py) on the fused gather + mean-pool kernel.
+
+Two call forms:
+  * ``forward(inputs, input_mask)``: the reference's signature on already-gathered
+    embeddings [B, W, d] (text_encoder.py:32,:75); runs the same kernel with an identity
+    index so every caller of the reference's encoders keeps working;
+  * ``encode_indices(table, idx, sink, ...)``: the fused path the model classes use --
+    rows are gathered, masked, averaged, dropped-out and (fs) projected in ONE pass and the
+    [B, W, d] tensor of the reference never exists.
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import functional as F_
+from . import ops
+
+
+class _DenseMeanFn(Function):
+    """masked mean of dense rows; backward = grad * valid / count, spread over tokens."""
+
+    @staticmethod
+    def forward(ctx, inputs, mask):
+        n, w, d = inputs.shape
+        flat = inputs.contiguous().view(n * w, d)
+        idx = torch.arange(n * w, device=inputs.device).view(n, w)
+        out, _, _ = ops.gather_meanpool(flat, idx, mask=mask)
+        ctx.mask, ctx.idx = mask, idx
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        tw = ops.token_weights(ctx.idx, mask=ctx.mask)
+        return g.unsqueeze(1) * tw.unsqueeze(-1), None
+
+
+def get_vector_mean(inputs, input_mask):
+    """text_encoder.py:6-16.  inputs [B,W,d] (or [B,W,1] losses), input_mask [B,W]."""
+    if inputs.shape[-1] % 4 != 0:
+        # the d=1 use of the reference (averaging per-word losses, item_transformer.py:281) is
+        # folded into psb_ns_loss_fwd; a tiny generic form is kept for API compatibility
+        m = input_mask.to(inputs.dtype).unsqueeze(-1)
+        cnt = input_mask.sum(-1)
+        cnt = cnt.masked_fill(cnt.eq(0), 1).unsqueeze(-1)
+        return (inputs * m).sum(1) / cnt.to(inputs.dtype)
+    return _DenseMeanFn.apply(inputs, input_mask.to(torch.uint8).contiguous())
+
+
+class AVGEncoder(nn.Module):
+    def __init__(self, embedding_size, dropout=0.0):
+        super().__init__()
+        self.dropout_ = dropout
+        self.output_size_ = embedding_size
+        self.drop_layer = nn.Dropout(p=self.dropout_)
+
+    @property
+    def size(self):
+        return self.output_size_
+
+    def forward(self, inputs, input_mask):
+        return self.drop_layer(get_vector_mean(inputs, input_mask))
+
+    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None):
+        keep = F_._dropout_keep((idx.shape[0], table.shape[1]), self.dropout_, self.training, table.device)
+        return F_.meanpool(table, idx, sink, pad_idx=pad_idx, mask=mask, keep_scale=keep)
+
+    def initialize_parameters(self, logger=None):
+        pass
+
+
+class FSEncoder(nn.Module):
+    def __init__(self, embedding_size, dropout=0.0):
+        super().__init__()
+        self.dropout_ = dropout
+        self.output_size_ = embedding_size
+        self.f_W = nn.Linear(embedding_size, embedding_size)
+        self.drop_layer = nn.Dropout(p=self.dropout_)
+
+    @property
+    def size(self):
+        return self.output_size_
+
+    def forward(self, inputs, input_mask):
+        mean = get_vector_mean(inputs, input_mask)
+        mean = torch.dropout(mean, p=self.dropout_, train=self.training)
+        return torch.tanh(self.f_W(mean))
+
+    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None):
+        keep = F_._dropout_keep((idx.shape[0], table.shape[1]), self.dropout_, self.training, table.device)
+        return F_.meanpool(table, idx, sink, pad_idx=pad_idx, mask=mask, keep_scale=keep,
+                           fs_weight=self.f_W.weight, fs_bias=self.f_W.bias)
+
+    def initialize_parameters(self, logger=None):
+        """xavier-normal weight, zero bias (text_encoder.py:42-55)."""
+        nn.init.xavier_normal_(self.f_W.weight)
+        nn.init.constant_(self.f_W.bias, 0)

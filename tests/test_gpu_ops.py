@@ -187,7 +187,10 @@ def test_score_loss_tail_vs_oracle(ops):
 
 # ---------------------------------------------------------------- G2
 def _dense_ref(table_rows, d, parts, drop):
+    """fp64 scatter-add reference + the per-entry sum of |terms| (fp32 accumulation of n terms
+    is only accurate to ~eps * sum|terms|, so tolerances scale with it)."""
     gt = torch.zeros(table_rows, d, dtype=torch.float64)
+    ga = torch.zeros(table_rows, d, dtype=torch.float64)
     gb = torch.zeros(table_rows, dtype=torch.float64)
     for p in parts:
         idx = p["idx"].view(-1)
@@ -197,14 +200,23 @@ def _dense_ref(table_rows, d, parts, drop):
         if p.get("scale2") is not None:
             s = s * p["scale2"].double()[torch.arange(n) // p.get("scale2_div", 1)]
         keep = idx != drop
-        gt.index_add_(0, idx[keep], p["src"].double()[row[keep]] * s[keep].unsqueeze(1))
+        terms = p["src"].double()[row[keep]] * s[keep].unsqueeze(1)
+        gt.index_add_(0, idx[keep], terms)
+        ga.index_add_(0, idx[keep], terms.abs())
         if p.get("to_bias"):
             gb.index_add_(0, idx[keep], s[keep])
-    return gt, gb
+    return gt, gb, ga
+
+
+def close_sum(a, ref, abs_sum):
+    """|a - ref| <= 1e-6 * sum|terms| + 1e-6: a few fp32 ulps of the accumulated magnitude."""
+    a, ref = a.detach().cpu().double(), ref.double()
+    assert bool(((a - ref).abs() <= 1e-6 * abs_sum + 1e-6).all()), float((a - ref).abs().max())
 
 
 @pytest.mark.parametrize("n,rows,d", [(700, 300, 128), (16384, 18001, 128), (16385, 18001, 128),
-                                      (250_000, 1_000_003, 128), (9000, 40, 64), (5000, 70000, 260)])
+                                      (250_000, 1_000_003, 128), (9000, 40, 64), (5000, 70000, 260),
+                                      (120_000, 5, 128), (2_000_000, 16_000_001, 128)])
 def test_scatter_reduce_vs_index_add(ops, n, rows, d):
     g = torch.Generator().manual_seed(n + rows)
     drop = rows - 1
@@ -219,7 +231,7 @@ def test_scatter_reduce_vs_index_add(ops, n, rows, d):
     scale2 = torch.randn((n2 + 5) // 6, generator=g)
     parts = [dict(idx=idx1, src=src1),
              dict(idx=idx2, src=anchors, src_div=6, scale=scale, scale2=scale2, scale2_div=6, to_bias=True)]
-    gt, gb = _dense_ref(rows, d, parts, drop)
+    gt, gb, ga = _dense_ref(rows, d, parts, drop)
     contribs = [ops.make_contrib(dev(idx1), dev(src1)),
                 ops.make_contrib(dev(idx2), dev(anchors), src_div=6, scale=dev(scale), scale2=dev(scale2),
                                  scale2_div=6, to_bias=True)]
@@ -231,10 +243,10 @@ def test_scatter_reduce_vs_index_add(ops, n, rows, d):
     expect_rows = torch.unique(torch.cat([idx1[idx1 != drop], idx2]))
     assert nu == expect_rows.numel()
     assert torch.equal(uniq[:nu].cpu().long(), expect_rows)          # ascending, bit-exact row ids
-    close(red[:nu], gt[expect_rows], rtol=1e-5, atol=1e-5)
-    close(redb[:nu], gb[expect_rows], rtol=1e-5, atol=1e-5)
-    close(dense, gt, rtol=1e-5, atol=1e-5)
-    close(dense_b, gb, rtol=1e-5, atol=1e-5)
+    close_sum(red[:nu], gt[expect_rows], ga[expect_rows])
+    close(redb[:nu], gb[expect_rows], rtol=1e-5, atol=1e-4)
+    close_sum(dense, gt, ga)
+    close(dense_b, gb, rtol=1e-5, atol=1e-4)
     assert float(dense[drop].abs().sum()) == 0.0                    # padding_idx row stays zero
     # run-to-run bit reproducibility (no float atomics)
     uniq2, red2, redb2, nu2 = ops.scatter_reduce(contribs, rows, d, drop_idx=drop, want_bias=True)
