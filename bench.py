@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the ProdSearch embedding-scoring hot path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one TEM training step (ItemTransformerRanker.forward_dotproduct + backward + the
+reference's clipped Adam) on BASELINE.json configs[1]: Amazon-Sports-shaped synthetic data,
+P=18k items, V=32k words, d=128, 1 layer / 8 heads / ff 512, uprev_review_limit 20, batch 384 per GPU,
+5 negatives, dropout 0.1 (the reference default).  Rank 0 prints ONE JSON line.
+
+  value  : samples/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same step through the module API from pinned HOST batches (H2D inside) + loss.item()
+  roofline / extra : the dominant hand-written kernel of the step, and every hot-path kernel in the
+           bandwidth regime on a 16M x 128 table (the regime the HBM-roofline target is defined on)
+  cpu_baseline : the oracle's CPU restatement of the same step on this box's host cores
+  --impl reference : times that CPU path alone (all host threads), same metric / config
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(model="TEM item_transformer", product_size=18000, vocab_size=32000, user_size=35000,
+                embedding_size=128, inter_layers=1, heads=8, ff_size=512, uprev_review_limit=20,
+                batch_per_gpu=384, neg_per_pos=5, pv_window_size=1, dropout=0.1, lr=0.0005, max_grad_norm=5.0)
+
+
+def model_args(dropout):
+    return argparse.Namespace(
+        train_review_only=True, embedding_size=WORKLOAD["embedding_size"], dropout=dropout, pretrain_emb_dir="",
+        pretrain_up_emb_dir="", sep_prod_emb=False, model_name="item_transformer", ff_size=WORKLOAD["ff_size"],
+        heads=WORKLOAD["heads"], inter_layers=WORKLOAD["inter_layers"], query_encoder_name="fs", use_dot_prod=True,
+        use_pos_emb=True, use_item_pos=False, sim_func="product", pos_weight=False,
+        neg_per_pos=WORKLOAD["neg_per_pos"], optim="adam", lr=WORKLOAD["lr"],
+        max_grad_norm=WORKLOAD["max_grad_norm"], beta1=0.9, beta2=0.999, decay_method="adam", warmup_steps=8000,
+        l2_lambda=0.0, train_from="")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm=z["hbm_gbs"], bf16=z["bf16_tflops"], bf16_sustained=z["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference step (forward + backward + clipped Adam)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(steps, warmup, dropout, seed=666):
+    import torch
+    import oracle
+    from prodsearch_b200 import synth
+    from prodsearch_b200.transformer import TransformerEncoder
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_args(dropout)
+    P, V, d, B = WORKLOAD["product_size"], WORKLOAD["vocab_size"], WORKLOAD["embedding_size"], WORKLOAD["batch_per_gpu"]
+    g = torch.Generator().manual_seed(seed)
+    enc = TransformerEncoder(d, cfg.ff_size, cfg.heads, dropout, cfg.inter_layers)
+    enc.initialize_parameters()
+    params = {"transformer_encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    params["product_emb.weight"] = torch.randn(P + 1, d, generator=g)
+    params["product_emb.weight"][P] = 0
+    params["word_embeddings.weight"] = torch.randn(V, d, generator=g)
+    params["product_bias"] = torch.zeros(P + 1)
+    params["word_bias"] = torch.zeros(V)
+    params["query_encoder.f_W.weight"] = torch.randn(d, d, generator=g) * (1.0 / d) ** 0.5
+    params["query_encoder.f_W.bias"] = torch.zeros(d)
+    leaves = []
+    for k, v in params.items():
+        if not k.endswith("pos_emb.pe"):
+            v.requires_grad_(True)
+            leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=cfg.lr, betas=(0.9, 0.999), eps=1e-9)
+    wd = torch.as_tensor(synth.word_dists(V))
+    pd = torch.ones(P)
+    times = []
+    for it in range(warmup + steps):
+        batch, _, _ = synth.tem_batch(B, P, V, seed=seed + it)
+        t0 = time.perf_counter()
+        neg_items = torch.multinomial(pd, B * cfg.neg_per_pos, replacement=True).view(B, -1)
+        neg_words = torch.multinomial(wd, B * cfg.neg_per_pos, replacement=True)
+        loss, _, _ = oracle.tem_forward(params, cfg, batch.query_word_idxs, batch.target_prod_idxs,
+                                        batch.u_item_idxs, batch.pos_iword_idxs, neg_items, neg_words, training=True)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(leaves, cfg.max_grad_norm)
+        opt.step()
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), cores
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = WORKLOAD["batch_per_gpu"]
+    sec, cores = cpu_reference_step_time(a.steps, a.warmup, a.dropout)
+    value = B / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "tem_train_samples_per_s", "value": value, "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(WORKLOAD, workload="BASELINE configs[1]: TEM train step, batch 384, CPU path", dropout=a.dropout),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d full TEM train steps (fwd+bwd+clipped Adam) of batch 384 on the oracle port "
+                                   "(same ATen CPU kernels as the reference modules)" % a.steps},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def timed(fn, iters, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3
+
+
+def bandwidth_regime(peaks, rows=16_000_000, d=128):
+    """Every hot-path kernel on a table far larger than L2 (8.2 GB): achieved algorithmic GB/s."""
+    import torch
+    from prodsearch_b200 import _lib, ops, synth
+    out = {}
+    dev = "cuda"
+    table = torch.empty(rows + 1, d, device=dev).normal_()
+    table[rows] = 0
+    GB = 1e9
+
+    def entry(name, sec, nbytes, note):
+        out[name] = {"ms": sec * 1e3, "achieved": nbytes / sec / GB, "unit": "GB/s", "peak": peaks["hbm"],
+                     "frac": nbytes / sec / GB / peaks["hbm"], "algorithmic_bytes": nbytes, "note": note}
+
+    n = 4_000_000
+    idx = synth.gather_indices(n, rows, seed=1, dist="uniform").to(dev)
+    sec = timed(lambda: ops.gather_rows(table, idx), 10)
+    entry("G1_gather_rows", sec, n * (d * 4 * 2 + 8), "4M uniform rows: read + materialised write + int64 idx")
+    idz = synth.gather_indices(n, rows, seed=2, dist="zipf").to(dev)
+    sec = timed(lambda: ops.gather_rows(table, idz), 10)
+    entry("G1_gather_rows_zipf", sec, n * (d * 4 * 2 + 8), "4M Zipf(1.0) rows")
+    nq, w = 400_000, 10
+    idx2 = idx[:nq * w].view(nq, w).contiguous()
+    sec = timed(lambda: ops.gather_meanpool(table, idx2, pad_idx=rows), 10)
+    entry("G4_gather_meanpool", sec, nq * w * (d * 4 + 8) + nq * d * 4, "400k pools of 10 rows (output 1 row each)")
+    na, k = 500_000, 5
+    anchor = torch.randn(na, d, device=dev)
+    pos = idx[:na].view(na, 1).contiguous()
+    neg = idx[na:na + na * k].view(na, 1, k).contiguous()
+    sec = timed(lambda: ops.ns_loss(anchor, table, pos, neg), 10)
+    entry("G3_ns_loss", sec, na * (1 + k) * (d * 4 + 8) + na * d * 4 * 2, "500k anchors x (1+5) rows, fwd + score grad")
+    src = torch.randn(n, d, device=dev)
+    contrib = [ops.make_contrib(idx, src)]
+    holder = {}
+
+    def sr():
+        holder["r"] = ops.scatter_reduce(contrib, rows + 1, d, drop_idx=rows)
+    sec = timed(sr, 5)
+    nu = int(holder["r"][3].item())
+    entry("G2_scatter_reduce", sec, n * (d * 4 + 8) + nu * d * 4, "4M uniform slots -> %d rows, sort included in time" % nu)
+    contrib_z = [ops.make_contrib(idz, src)]
+
+    def srz():
+        holder["z"] = ops.scatter_reduce(contrib_z, rows + 1, d, drop_idx=rows)
+    sec = timed(srz, 5)
+    nuz = int(holder["z"][3].item())
+    entry("G2_scatter_reduce_zipf", sec, n * (d * 4 + 8) + nuz * d * 4, "4M Zipf slots -> %d rows" % nuz)
+    # catalog scoring: 1M items, top-100
+    n_items = 1_000_000
+    cat = {}
+    for m in (24, 384):
+        q = torch.randn(m, d, device=dev)
+        for mode, mname in ((_lib.TOPK_EXACT, "exact_fp32"), (_lib.TOPK_TC, "tcgen05_tf32")):
+            try:
+                sec = timed(lambda: ops.catalog_topk(q, table, 100, n_items=n_items, mode=mode), 3, warmup=1)
+            except RuntimeError as ex:
+                cat["%s_m%d" % (mname, m)] = {"unavailable": str(ex)[:80]}
+                continue
+            flops = 2.0 * m * n_items * d
+            cat["%s_m%d" % (mname, m)] = {"ms": sec * 1e3, "queries_per_s": m / sec, "tflops": flops / sec / 1e12,
+                                          "table_GBps": n_items * d * 4 / sec / GB}
+    out["G5_catalog_topk_1M"] = cat
+    return out
+
+
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from prodsearch_b200 import _lib, ops, synth
+    from prodsearch_b200.item_transformer import ItemTransformerRanker
+    from prodsearch_b200.optimizers import build_optim
+    from prodsearch_b200 import sharded
+    peaks = load_peaks()
+    args = model_args(a.dropout)
+    P, V, B = WORKLOAD["product_size"], WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
+    torch.manual_seed(666)
+    model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+    optim = build_optim(args, model)
+    model.train()
+    ddp = sharded.DenseGradAllReduce(model) if world > 1 else None
+    n_total = a.warmup + a.steps
+    host, devb = [], []
+    for it in range(n_total):
+        b, _, _ = synth.tem_batch(B, P, V, seed=666 + 1000 * rank + it)
+        hb = argparse.Namespace(**{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in vars(b).items()})
+        host.append(hb)
+        devb.append(argparse.Namespace(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vars(b).items()}))
+    h2d = sum(v.numel() * v.element_size() for v in vars(host[0]).values() if torch.is_tensor(v))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(batch):
+        loss = model(batch)
+        model.zero_grad()
+        loss.backward()
+        if ddp is not None:
+            ddp.reduce()
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(a.warmup):
+        step(devb[it])
+    # ---- timed region 1: device-resident batches, CUDA events per step, L2 flushed between steps
+    barrier()
+    l0 = _lib.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    with ClockSampler(local) as clocks:
+        for it in range(a.steps):
+            flush.zero_()
+            starts[it].record()
+            step(devb[a.warmup + it])
+            ends[it].record()
+        barrier()
+    launches = _lib.launch_count() - l0
+    dev_sec = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+    # ---- timed region 2: end to end from pinned host batches (H2D + step + loss.item())
+    barrier()
+    e2e_sec = 0.0
+    for it in range(a.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hb = host[a.warmup + it]
+        db = argparse.Namespace(**{k: (v.cuda(non_blocking=True) if torch.is_tensor(v) else v) for k, v in vars(hb).items()})
+        float(step(db).item())
+        e2e_sec += time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([dev_sec, e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_sec, e2e_sec = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- per-op timing of the hand-written kernels inside the same step (separate pass)
+    ops.PROFILE = {}
+    for it in range(min(a.steps, 10)):
+        flush.zero_()
+        step(devb[a.warmup + it])
+    torch.cuda.synchronize()
+    prof = {k: (sum(s.elapsed_time(e) for s, e in v) / len(v), len(v) // min(a.steps, 10)) for k, v in ops.PROFILE.items()}
+    ops.PROFILE = None
+    d = WORKLOAD["embedding_size"]
+    K, L, W = WORKLOAD["neg_per_pos"], WORKLOAD["uprev_review_limit"], 1
+    alg = {  # algorithmic bytes per launch at this config
+        "ns_loss": B * (1 + K) * (d * 4 + 8) + B * d * 4 * 2 + B * K * d * 4 * 2,
+        "gather_rows": B * L * (d * 4 * 2 + 8),
+        "gather_meanpool": B * 12 * (d * 4 + 8) + B * d * 4 * 2 + d * d * 4,
+        "scatter_reduce": B * (L + 2 + K) * (d * 4 + 8),
+        "fs_bwd": B * d * 4 * 4 + d * d * 4 * 2,
+        "token_weights": B * 12 * 12,
+    }
+    dom = max(prof.items(), key=lambda kv: kv[1][0] * kv[1][1]) if prof else None
+    roofline = None
+    if dom is not None:
+        name, (ms, per_step) = dom
+        ach = alg.get(name, 0) / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "psb_" + name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                    "launch_ms": ms, "launches_per_step": per_step,
+                    "regime": "latency-bound: %d KB per launch at batch 384 (see extra.bandwidth_regime for the "
+                              "HBM-roofline regime)" % (alg.get(name, 0) // 1024),
+                    "all_ops_ms": {k: round(v[0] * v[1], 4) for k, v in prof.items()}}
+    extra = None
+    if world == 1 and not a.no_extra:
+        extra = {"bandwidth_regime": bandwidth_regime(peaks), "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        sec, cores = cpu_reference_step_time(a.cpu_steps, 2, a.dropout)
+        cpu = {"value": B / sec, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "%d TEM train steps of batch 384 (fwd+bwd+clipped Adam) on the oracle port, %.0f ms/step"
+                         % (a.cpu_steps, sec * 1e3)}
+    value = B * a.steps * world / dev_sec
+    print(json.dumps({
+        "metric": "tem_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_sec / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(WORKLOAD, workload="BASELINE configs[1]: TEM item_transformer train step, batch 384/GPU",
+                       dropout=a.dropout, l2="flushed between timed steps (256 MiB write), flush not timed",
+                       parallelism="dp%d, item/word tables %s" % (world, "row-sharded" if world > 1 else "local")),
+        "clocks": clocks.summary(),
+        "e2e": {"value": B * a.steps * world / e2e_sec, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_sec / a.steps * 1e3},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dropout", type=float, default=WORKLOAD["dropout"])
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,3 +174,26 @@ def topk_merge(ids, scores):
     check(load().psb_topk_merge(ptr(ids, i64), ptr(scores, f32), g, m, k, ptr(out_i), ptr(out_s), stream_ptr()),
           "psb_topk_merge")
     return out_i, out_s
+
+
+# ---- optional per-op device timing (bench.py roofline leg) ----------------------------------
+PROFILE = None   # dict name -> list of (start_event, end_event) when enabled
+
+
+def _profiled(name, fn):
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*a, **k)
+        e.record()
+        PROFILE.setdefault(name, []).append((s, e))
+        return out
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
+for _n in ("gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
+           "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge"):
+    globals()[_n] = _profiled(_n, globals()[_n])

@@ -139,7 +139,7 @@ def test_tem_vs_oracle_amazon_shape(B):
         if k in ("product_emb.weight", "word_embeddings.weight"):
             g[-1] = 0
         scale = float(g.abs().max()) + 1e-12
-        close(p.grad, g, rtol=1e-4, atol=2e-5 * scale)
+        close(p.grad, g, rtol=1e-4, atol=max(2e-5 * scale, 2e-7))   # key-bias grads are pure fp32 noise
 
 
 # ---------------------------------------------------------------- PV / PVC vs golden

@@ -264,9 +264,14 @@ def test_scatter_reduce_all_dropped_and_single(ops):
     idx[:] = 4
     uniq, red, _, nu = ops.scatter_reduce([ops.make_contrib(dev(idx), dev(src))], 10, 128, drop_idx=9)
     assert int(nu.item()) == 1 and int(uniq[0]) == 4
+    # the kernel's fixed bracketing: sequential sums over units of 8 slots (n_total <= 65536),
+    # unit partials added in unit order -- reproduced here term by term, so equality is bit-exact
     seq = torch.zeros(128)
-    for r in src:                         # ascending-slot sequential sum == the kernel's order
-        seq = seq + r
+    for u0 in range(0, 50, 8):
+        part = torch.zeros(128)
+        for r in src[u0:u0 + 8]:
+            part = part + r
+        seq = seq + part
     assert torch.equal(red[0].cpu(), seq)
 
 
