@@ -196,8 +196,14 @@ int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows,
 int64_t psb_catalog_topk_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k, int32_t mode);
 int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_t n_items,
                      int64_t d, const float* bias, int64_t k, int64_t id_base, int64_t id_stride,
-                     int32_t mode, void* workspace, int64_t workspace_bytes,
+                     int32_t mode, const float* max_row_sqnorm, void* workspace, int64_t workspace_bytes,
                      int64_t* out_ids, float* out_scores, psb_stream_t stream);
+
+/* max_r |table[r,:]|^2 as a device scalar: the bound the TC mode's error margin needs.  Pass it
+ * to psb_catalog_topk (max_row_sqnorm) to skip the extra table pass when the table is static
+ * (evaluation); NULL there makes the call compute it itself. */
+int psb_table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out,
+                             psb_stream_t stream);
 
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */

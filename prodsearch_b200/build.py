@@ -55,7 +55,7 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: %s" % " ".join(cmd))
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-lcuda"]
+    link = [nvcc, "-shared", "-o", LIB] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

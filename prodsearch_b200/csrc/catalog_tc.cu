@@ -1,14 +1,723 @@
-// G5 (tensor-core mode): tcgen05 TF32 shortlist + exact rescoring.  Placeholder until the
-// kernel lands; the exact mode in catalog_topk.cu is complete.
+// G5 (tensor-core mode): full-catalog scoring as a tcgen05 / TMEM TF32 GEMM fed by TMA, with the
+// top-k selection fused into the epilogue so the [M, N] score matrix is never written.
+//
+// TF32 products cannot give reference-exact scores, so the tensor cores only
+// SHORTLIST: with |approx - exact| <= eps_q = 2^-8 |q| max|e| (Cauchy-Schwarz on the per-product
+// truncation error, 2x headroom), every item of the exact top-k has approx >= tau - 2 eps_q for ANY
+// valid lower bound tau of the k-th best approx score.  Pipeline (all on `stream`, no host sync):
+//   1. pilot   : tc_score_kernel<DUMP> over a strided sample of 128-item tiles -> scores [M, S]
+//   2. kth     : per query, k-th largest pilot score (radix select) -> thr = kth - 2 eps
+//   3. main    : tc_score_kernel<FILTER> over the whole table; the epilogue (one thread per query
+//                row reading its TMEM lane) appends (score, id) >= thr to a per-(row, CTA) list
+//   4. final   : per query, k-th best of the candidates, prune by 2 eps, EXACT fp32 rescoring with
+//                the canonical recurrence of catalog_topk.cu, rank-sort (score desc, id asc)
+//   5. fallback: rows whose lists overflowed (degenerate ties) are redone by an exact streaming
+//                scan -- always correct, only slow for pathological data.
+// tc_score_kernel: grid (item slices, query tiles of 128), 192 threads = TMA producer warp, MMA
+// issuer warp (one elected thread issues tcgen05.mma.kind::tf32, M=128 N=128 K=8), 4 epilogue
+// warps (tcgen05.ld 32x32b.x32).  smem: Q tile resident (d/32 k-blocks of 128x32 fp32, 128B
+// swizzle), 2-stage ring of item tiles, TMEM: 2 accumulators x 128 columns (double buffered).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "catalog_common.cuh"
 
 namespace psb {
 
-int64_t tc_workspace_bytes(int64_t, int64_t, int64_t, int64_t) { return 0; }
+constexpr int kTM = 128;          // queries per CTA (UMMA M, TMEM lanes)
+constexpr int kTN = 128;          // items per tile (UMMA N, TMEM columns per accumulator)
+constexpr int kKB = 32;           // fp32 per k-block = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kParts = 4;          // epilogue column quarters (16 epilogue warps, 4 per SM sub-partition)
+constexpr int kTcThreads = 64 + 4 * 32 * kParts;
+constexpr uint32_t kKBBytes = kTM * kKB * 4;  // 16 KB per k-block of either operand
+constexpr float kEpsFactor = 1.0f / 256.0f;
 
-int catalog_topk_tc(const float*, int64_t, const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t,
-                    void*, int64_t, int64_t*, float*, cudaStream_t) {
-  return PSB_E_UNSUPPORTED;
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (done == 0);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows x 32 fp32, 8-row atoms of 1024 B): UMMA shared
+// memory descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30) = 1,
+// SBO>>4 [32,46) = 1024>>4, version [46,48) = 1, layout [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10)/[10,13), K-major A and B,
+// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kTN >> 3) << 17) |
+                            (static_cast<uint32_t>(kTM >> 4) << 24);
+
+struct TcParams {
+  int m, n_items, kblocks;          // kblocks = d / 32
+  int tile_begin, tile_step, n_tiles;  // tiles enumerated p = 0..n_tiles-1 -> item tile tile_begin + p*tile_step
+  const float* bias;
+  const float* thr;                 // [m] filter thresholds (FILTER)
+  float* dump;                      // [m_pad, ld_dump] (DUMP)
+  int ld_dump;
+  float* cand_s;                    // [m_pad * n_slices * cap]
+  int32_t* cand_i;
+  int32_t* cand_n;                  // [m_pad * n_slices]
+  int cap;
+  int debug;                        // experiment switches (PSB_TC_DEBUG): 1 = skip epilogue scan, 2 = skip MMA
+};
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
+                const TcParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 128-byte-swizzled operand tiles need a 1024-byte aligned base
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_bytes = static_cast<uint32_t>(P.kblocks) * kKBBytes;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tile_bytes * (1 + kStages));
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = bars + 1 + kStages;
+  uint64_t* t_full = bars + 1 + 2 * kStages;
+  uint64_t* t_empty = bars + 3 + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kStages);
+
+  const int n_slices = gridDim.x, slice = blockIdx.x, mtile = blockIdx.y;
+  const int per = (P.n_tiles + n_slices - 1) / n_slices;
+  const int p_lo = slice * per;
+  const int p_hi = min(P.n_tiles, p_lo + per);
+  const int my_tiles = max(0, p_hi - p_lo);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(t_full + a, 1);
+      mbar_init(t_empty + a, 4 * kParts);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulators x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * kTN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, tile_bytes);
+      for (int kb = 0; kb < P.kblocks; ++kb) tma_load_2d(sA + kb * kKBBytes, &map_q, kb * kKB, mtile * kTM, a_full);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(b_empty + st, ph ^ 1);
+        mbar_expect_tx(b_full + st, tile_bytes);
+        const int tile = P.tile_begin + (p_lo + it) * P.tile_step;
+        for (int kb = 0; kb < P.kblocks; ++kb)
+          tma_load_2d(sB + st * tile_bytes + kb * kKBBytes, &map_e, kb * kKB, tile * kTN, b_full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(t_empty + acc, aph ^ 1);
+        mbar_wait(b_full + st, ph);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTN);
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          const uint32_t a_addr = smem_u32(sA + kb * kKBBytes);
+          const uint32_t b_addr = smem_u32(sB + st * tile_bytes + kb * kKBBytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K = 8 tf32 = 32 bytes) inside one 128-byte swizzle row
+            if (!(P.debug & 2)) tc_mma_tf32(d_addr, umma_desc(a_addr + k4 * 32), umma_desc(b_addr + k4 * 32), kIdesc,
+                        (kb | k4) != 0 ? 1u : 0u);
+        }
+        tc_commit(b_empty + st);   // smem stage free once these MMAs have read it
+        tc_commit(t_full + acc);   // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; thread = (query row = TMEM lane, half of the tile's 128 columns) =====
+    // A warp may only touch TMEM lanes 32*(warp%4)..+31; warps 2..9 cover each lane quarter twice,
+    // the second copy taking columns 64..127.  Every thread keeps its own candidate list.
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int row = mtile * kTM + quarter * 32 + lane;
+    const bool row_ok = row < P.m;
+    float thr = INFINITY;
+    if (!DUMP && row_ok) thr = P.thr[row];
+    int cnt = 0;
+    const int n_lists = n_slices * kParts;
+    const int64_t list = (static_cast<int64_t>(row) * n_lists + slice * kParts + part) * P.cap;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int p = p_lo + it;
+      const int tile = P.tile_begin + p * P.tile_step;
+      const bool full_tile = (tile + 1) * kTN <= P.n_items && P.bias == nullptr;
+      mbar_wait(t_full + acc, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = part * (kTN / kParts); c0 < (part + 1) * (kTN / kParts); c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tc_ld32(lane_addr + static_cast<uint32_t>(acc * kTN + c0), v);
+        const int id0 = tile * kTN + c0;
+        if (DUMP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float s = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) s += P.bias[id];
+            if (row_ok) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * kTN + c0 + i] = id < P.n_items ? s : -INFINITY;
+          }
+        } else if (full_tile) {
+          // branch once per 8 scores: almost every group is below the threshold
+#pragma unroll
+          for (int g8 = 0; g8 < 32; g8 += 8) {
+            float mx = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
+                             fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
+            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
+                                 fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
+            if (mx >= thr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float s = __uint_as_float(v[g8 + i]);
+                if (s >= thr) {
+                  if (cnt < P.cap) {
+                    P.cand_s[list + cnt] = s;
+                    P.cand_i[list + cnt] = id0 + g8 + i;
+                  }
+                  ++cnt;
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float s = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) s += P.bias[id];
+            if (s >= thr && id < P.n_items) {
+              if (cnt < P.cap) {
+                P.cand_s[list + cnt] = s;
+                P.cand_i[list + cnt] = id;
+              }
+              ++cnt;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+    }
+    if (!DUMP && row_ok) P.cand_n[static_cast<int64_t>(row) * n_lists + slice * kParts + part] = cnt;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTN));
+  }
+}
+
+// ------------------------------------------------------------------ helpers
+__global__ void __launch_bounds__(256)
+max_row_norm_kernel(const float4* __restrict__ table, int64_t rows, int d4, float* __restrict__ out_sq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  float best = 0.f;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); r < rows; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = ldg_row4(table + r * d4 + c);
+      s += dot4(v, v);
+    }
+    s = warp_sum(s);
+    best = fmaxf(best, s);
+  }
+  // max over non-negative floats == max over their bit patterns; order-free, so deterministic
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out_sq), __float_as_int(best));
+}
+
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // ascending key order == ascending float order
+}
+
+// k-th largest of vals[0..n) by 4-pass MSB radix select; all 256 threads must call.  n >= k required.
+__device__ float block_kth_largest(const float* vals, int n, int k, int* hist /*[256] smem*/, uint32_t* sh /*[2] smem*/) {
+  uint32_t prefix = 0, mask = 0;
+  int need = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const uint32_t key = order_key(vals[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0, b = 255;
+      for (; b > 0; --b) {
+        if (run + hist[b] >= need) break;
+        run += hist[b];
+      }
+      sh[0] = static_cast<uint32_t>(b);
+      sh[1] = static_cast<uint32_t>(need - run);
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    mask |= 255u << shift;
+    need = static_cast<int>(sh[1]);
+    __syncthreads();
+  }
+  const uint32_t key = prefix;
+  const uint32_t bits = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __uint_as_float(bits);
+}
+
+// pilot scores -> thr[row] = kth - 2 eps_row ; eps_row = 2^-8 |q_row| max|e|
+__global__ void __launch_bounds__(256)
+pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int k, const float* __restrict__ Q, int d,
+                       const float* __restrict__ max_sq, float* __restrict__ thr, float* __restrict__ eps) {
+  __shared__ int hist[256];
+  __shared__ uint32_t sh[2];
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    const float v = Q[static_cast<int64_t>(row) * d + c];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float qsq = 0.f;
+  for (int w = 0; w < 8; ++w) qsq += red[w];
+  const float e = kEpsFactor * sqrtf(qsq) * sqrtf(*max_sq) + 1e-30f;
+  const float* vals = dump + static_cast<int64_t>(row) * ld;
+  // count finite entries: with fewer than k valid pilot items nothing can be pruned
+  int valid = 0;
+  for (int i = threadIdx.x; i < n_pilot; i += 256) valid += vals[i] > -INFINITY ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(kFull, valid, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = static_cast<float>(valid);
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  float t = -INFINITY;
+  if (static_cast<int>(tot) >= k) t = block_kth_largest(vals, n_pilot, k, hist, sh) - 2.f * e;
+  if (threadIdx.x == 0) {
+    thr[row] = t;
+    eps[row] = e;
+  }
+}
+
+constexpr int kFinalCap = 14336;   // candidates a final-select CTA can hold in shared memory
+constexpr int kKeepCap = 1024;
+constexpr int kMaxLists = kNumSMs * 4;  // n_slices * kParts upper bound     // candidates that survive the 2-eps prune and get exact scores
+
+// per query row: candidates -> prune -> exact rescoring -> ordered top-k.  Rows that cannot be
+// finished here (overflowed lists / too many survivors) are flagged for the exact fallback.
+__global__ void __launch_bounds__(256)
+final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
+                    const int32_t* __restrict__ cand_n, int n_slices, int cap, const float* __restrict__ eps,
+                    const float* __restrict__ Q, const float* __restrict__ E, int d, const float* __restrict__ bias,
+                    int k, int64_t id_base, int64_t id_stride, int64_t* __restrict__ out_ids,
+                    float* __restrict__ out_scores, int32_t* __restrict__ fallback_flag) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
+  int32_t* ci = reinterpret_cast<int32_t*>(cs + kFinalCap);      // [kFinalCap]
+  float* ks = reinterpret_cast<float*>(ci + kFinalCap);          // [kKeepCap] exact scores
+  int32_t* ki = reinterpret_cast<int32_t*>(ks + kKeepCap);       // [kKeepCap]
+  float* qrow = reinterpret_cast<float*>(ki + kKeepCap);         // [d]
+  __shared__ int hist[256];
+  __shared__ uint32_t sh[2];
+  __shared__ int s_total, s_over, s_keep;
+  __shared__ int offs[kMaxLists + 1];
+  const int row = blockIdx.x;
+  // list sizes -> exclusive offsets (n_slices here = number of lists of this row, <= kMaxLists)
+  for (int l = threadIdx.x; l < n_slices; l += 256) offs[l + 1] = cand_n[static_cast<int64_t>(row) * n_slices + l];
+  for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0, over = 0;
+    offs[0] = 0;
+    for (int l = 0; l < n_slices; ++l) {
+      const int c = offs[l + 1];
+      over |= c > cap;
+      tot += min(c, cap);
+      offs[l + 1] = tot;
+    }
+    s_total = tot;
+    s_over = over | (tot > kFinalCap);
+    s_keep = 0;
+  }
+  __syncthreads();
+  if (s_over) {
+    if (threadIdx.x == 0) fallback_flag[row] = 1;
+    return;
+  }
+  // gather the lists, one warp per list (order irrelevant: the final ordering is a strict total order)
+  for (int l = threadIdx.x >> 5; l < n_slices; l += 8) {
+    const int base = offs[l], c = offs[l + 1] - offs[l];
+    const int64_t src = (static_cast<int64_t>(row) * n_slices + l) * cap;
+    for (int i = threadIdx.x & 31; i < c; i += 32) {
+      cs[base + i] = cand_s[src + i];
+      ci[base + i] = cand_i[src + i];
+    }
+  }
+  __syncthreads();
+  const int total = s_total;
+  float cut = -INFINITY;
+  if (total > k) cut = block_kth_largest(cs, total, k, hist, sh) - 2.f * eps[row];
+  for (int i = threadIdx.x; i < total; i += 256) {
+    if (cs[i] >= cut) {
+      const int slot = atomicAdd(&s_keep, 1);
+      if (slot < kKeepCap) ki[slot] = ci[i];
+    }
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  if (keep > kKeepCap) {
+    if (threadIdx.x == 0) fallback_flag[row] = 1;
+    return;
+  }
+  // exact fp32 scores with the canonical recurrence (bit-identical to the exact mode)
+  for (int i = threadIdx.x; i < keep; i += 256) {
+    const int32_t id = ki[i];
+    ks[i] = canonical_dot(qrow, E + static_cast<int64_t>(id) * d, d) + (bias != nullptr ? bias[id] : 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < keep; i += 256) {
+    const float es = ks[i];
+    const int32_t ei = ki[i];
+    int rank = 0;
+    for (int u = 0; u < keep; ++u) rank += beats(ks[u], ki[u], es, ei) ? 1 : 0;
+    if (rank < k) {
+      out_ids[static_cast<int64_t>(row) * k + rank] = id_base + static_cast<int64_t>(ei) * id_stride;
+      out_scores[static_cast<int64_t>(row) * k + rank] = es;
+    }
+  }
+  for (int r = keep + threadIdx.x; r < k; r += 256) {
+    out_ids[static_cast<int64_t>(row) * k + r] = -1;
+    out_scores[static_cast<int64_t>(row) * k + r] = -INFINITY;
+  }
+}
+
+// exact streaming scan for flagged rows (degenerate inputs only).
+__global__ void __launch_bounds__(256)
+fallback_rows_kernel(const int32_t* __restrict__ flag, const float* __restrict__ Q, const float* __restrict__ E,
+                     int64_t n_items, int d, const float* __restrict__ bias, int k, int64_t id_base,
+                     int64_t id_stride, int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+  const int row = blockIdx.x;
+  if (flag[row] == 0) return;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* qrow = reinterpret_cast<float*>(sm_raw);   // [d]
+  __shared__ float bs[kKMax], cs[256], ns[kKMax];
+  __shared__ int32_t bi[kKMax], ci[256], ni[kKMax];
+  __shared__ int wc[8];
+  for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
+  if (threadIdx.x < kKMax) {
+    bs[threadIdx.x] = -INFINITY;
+    bi[threadIdx.x] = 0x7fffffff;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n_items; base += 256) {
+    const int64_t j = base + threadIdx.x;
+    float s = 0.f;
+    int32_t id = 0;
+    bool pass = false;
+    if (j < n_items) {
+      id = static_cast<int32_t>(j);
+      s = canonical_dot(qrow, E + j * d, d) + (bias != nullptr ? bias[j] : 0.f);
+      pass = beats(s, id, bs[k - 1], bi[k - 1]);
+    }
+    const unsigned bal = __ballot_sync(kFull, pass);
+    if (lane == 0) wc[wid] = __popc(bal);
+    __syncthreads();
+    int nb = 0, total = 0;
+    for (int w2 = 0; w2 < 8; ++w2) {
+      if (w2 < wid) nb += wc[w2];
+      total += wc[w2];
+    }
+    if (total > 0) {
+      const int my = nb + __popc(bal & ((1u << lane) - 1u));
+      if (pass) {
+        cs[my] = s;
+        ci[my] = id;
+      }
+      __syncthreads();
+      // rank-merge best[kKMax] with cand[total <= 256] in two halves of the thread block
+      for (int e = threadIdx.x; e < kKMax + total; e += 256) {
+        const bool fb = e < kKMax;
+        const float es = fb ? bs[e] : cs[e - kKMax];
+        const int32_t ei = fb ? bi[e] : ci[e - kKMax];
+        int rank = 0;
+        for (int u = 0; u < kKMax; ++u) rank += (u != e && before(bs[u], bi[u], u, es, ei, e)) ? 1 : 0;
+        for (int u = 0; u < total; ++u) rank += (kKMax + u != e && before(cs[u], ci[u], kKMax + u, es, ei, e)) ? 1 : 0;
+        if (rank < kKMax) {
+          ns[rank] = es;
+          ni[rank] = ei;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < kKMax) {
+        bs[threadIdx.x] = ns[threadIdx.x];
+        bi[threadIdx.x] = ni[threadIdx.x];
+      }
+    }
+    __syncthreads();
+  }
+  for (int r = threadIdx.x; r < k; r += 256) {
+    const bool empty = bi[r] == 0x7fffffff;
+    out_ids[static_cast<int64_t>(row) * k + r] = empty ? -1 : id_base + static_cast<int64_t>(bi[r]) * id_stride;
+    out_scores[static_cast<int64_t>(row) * k + r] = empty ? -INFINITY : bs[r];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows x d fp32 row-major -> boxes of 128 rows x 32 floats, 128-byte swizzle, OOB rows read as zero
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t d) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return PSB_E_UNSUPPORTED;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(d) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKB), static_cast<cuuint32_t>(kTM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PSB_OK : PSB_E_ARG;
+}
+
+struct TcPlan {
+  int m_tiles, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap;
+  int64_t off_thr, off_eps, off_maxsq, off_flag, off_cand_n, off_dump, off_cand_s, off_cand_i, total;
+};
+
+static int64_t up256(int64_t x) { return (x + 255) / 256 * 256; }
+
+static TcPlan plan_for(int64_t m, int64_t n_items, int64_t k) {
+  TcPlan p;
+  p.m_tiles = static_cast<int>((m + kTM - 1) / kTM);
+  p.m_pad = p.m_tiles * kTM;
+  p.total_tiles = static_cast<int>((n_items + kTN - 1) / kTN);
+  p.n_slices = kNumSMs / p.m_tiles;
+  if (p.n_slices < 1) p.n_slices = 1;
+  if (p.n_slices > p.total_tiles) p.n_slices = p.total_tiles;
+  p.pilot_tiles = p.total_tiles / 64 > 128 ? p.total_tiles / 64 : 128;
+  if (p.pilot_tiles > p.total_tiles) p.pilot_tiles = p.total_tiles;
+  p.pilot_step = p.total_tiles / p.pilot_tiles;
+  const double expect = static_cast<double>(k) * p.total_tiles / p.pilot_tiles / (p.n_slices * kParts);
+  p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
+  int64_t o = 0;
+  p.off_thr = o; o += up256(p.m_pad * 4);
+  p.off_eps = o; o += up256(p.m_pad * 4);
+  p.off_maxsq = o; o += 256;
+  p.off_flag = o; o += up256(p.m_pad * 4);
+  p.off_cand_n = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * 4);
+  p.off_dump = o; o += up256(static_cast<int64_t>(p.m_pad) * p.pilot_tiles * kTN * 4);
+  p.off_cand_s = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
+  p.off_cand_i = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
+  p.total = o + 256;
+  return p;
+}
+
+int64_t tc_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k) {
+  (void)d;
+  return plan_for(m, n_items, k).total;
+}
+
+static bool tc_supported(int64_t m, int64_t n_items, int64_t d) {
+  return d % kKB == 0 && d <= 128 && n_items >= 32768 && m <= kNumSMs * kTM;
+}
+
+int table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out, cudaStream_t s) {
+  cudaMemsetAsync(out, 0, 4, s);
+  max_row_norm_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(table), rows,
+                                                  static_cast<int>(d / 4), out);
+  return launch_status();
+}
+
+int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t n_items, int64_t d,
+                    const float* bias, int64_t k, int64_t id_base, int64_t id_stride, const float* max_row_sqnorm,
+                    void* workspace, int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  if (!tc_supported(m, n_items, d))   // shapes the tensor path does not cover run the exact kernels
+    return catalog_topk_exact(queries, m, table, n_items, d, bias, k, id_base, id_stride, workspace,
+                              workspace_bytes, out_ids, out_scores, s);
+  const TcPlan pl = plan_for(m, n_items, k);
+  const int64_t ex_bytes = (exact_workspace_bytes(m, n_items) + 255) / 256 * 256;
+  if (workspace_bytes < ex_bytes + pl.total) return PSB_E_WORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace) + ex_bytes;
+  float* thr = reinterpret_cast<float*>(ws + pl.off_thr);
+  float* eps = reinterpret_cast<float*>(ws + pl.off_eps);
+  float* maxsq = reinterpret_cast<float*>(ws + pl.off_maxsq);
+  int32_t* flag = reinterpret_cast<int32_t*>(ws + pl.off_flag);
+  int32_t* cand_n = reinterpret_cast<int32_t*>(ws + pl.off_cand_n);
+  float* dump = reinterpret_cast<float*>(ws + pl.off_dump);
+  float* cand_s = reinterpret_cast<float*>(ws + pl.off_cand_s);
+  int32_t* cand_i = reinterpret_cast<int32_t*>(ws + pl.off_cand_i);
+
+  alignas(64) CUtensorMap map_q, map_e;
+  int st;
+  if ((st = make_map(&map_q, queries, m, d)) != PSB_OK) return st;
+  if ((st = make_map(&map_e, table, n_items, d)) != PSB_OK) return st;
+
+  const int kblocks = static_cast<int>(d / kKB);
+  const size_t smem = static_cast<size_t>(kblocks) * kKBBytes * (1 + kStages) + 256 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(tc_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(tc_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e3 = cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return static_cast<int>(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+    attr_done = true;
+  }
+  cudaMemsetAsync(flag, 0, static_cast<size_t>(pl.m_pad) * 4, s);
+  if (max_row_sqnorm == nullptr) {   // one extra pass over the table; callers with a static table cache it
+    if ((st = table_max_row_sqnorm(table, n_items, d, maxsq, s)) != PSB_OK) return st;
+    max_row_sqnorm = maxsq;
+  }
+
+  TcParams P;
+  P.m = static_cast<int>(m);
+  P.n_items = static_cast<int>(n_items);
+  P.kblocks = kblocks;
+  P.bias = bias;
+  P.thr = thr;
+  P.dump = dump;
+  P.ld_dump = pl.pilot_tiles * kTN;
+  P.cand_s = cand_s;
+  P.cand_i = cand_i;
+  P.cand_n = cand_n;
+  P.cap = pl.cap;
+  { const char* e = getenv("PSB_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  // 1. pilot
+  P.tile_begin = 0;
+  P.tile_step = pl.pilot_step;
+  P.n_tiles = pl.pilot_tiles;
+  {
+    int slices = pl.n_slices < pl.pilot_tiles ? pl.n_slices : pl.pilot_tiles;
+    dim3 grid(slices, pl.m_tiles);
+    tc_score_kernel<true><<<grid, kTcThreads, smem, s>>>(map_q, map_e, P);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  // 2. thresholds
+  pilot_threshold_kernel<<<static_cast<int>(m), 256, 0, s>>>(dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries,
+                                                             static_cast<int>(d), max_row_sqnorm, thr, eps);
+  if ((st = launch_status()) != PSB_OK) return st;
+  // 3. main pass
+  P.tile_step = 1;
+  P.n_tiles = pl.total_tiles;
+  {
+    dim3 grid(pl.n_slices, pl.m_tiles);
+    tc_score_kernel<false><<<grid, kTcThreads, smem, s>>>(map_q, map_e, P);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  // 4. final select + exact rescoring
+  const size_t fsmem = static_cast<size_t>(kFinalCap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
+  final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
+                                                              table, static_cast<int>(d), bias, static_cast<int>(k),
+                                                              id_base, id_stride, out_ids, out_scores, flag);
+  if ((st = launch_status()) != PSB_OK) return st;
+  // 5. exact fallback for flagged rows (returns immediately for unflagged ones)
+  fallback_rows_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(d) * 4, s>>>(
+      flag, queries, table, n_items, static_cast<int>(d), bias, static_cast<int>(k), id_base, id_stride, out_ids,
+      out_scores);
+  return launch_status();
 }
 
 }  // namespace psb

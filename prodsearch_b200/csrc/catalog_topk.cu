@@ -272,8 +272,9 @@ extern "C" int64_t psb_catalog_topk_workspace_bytes(int64_t m, int64_t n_items, 
 
 extern "C" int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_t n_items,
                                 int64_t d, const float* bias, int64_t k, int64_t id_base, int64_t id_stride,
-                                int32_t mode, void* workspace, int64_t workspace_bytes, int64_t* out_ids,
-                                float* out_scores, psb_stream_t stream) {
+                                int32_t mode, const float* max_row_sqnorm, void* workspace,
+                                int64_t workspace_bytes, int64_t* out_ids, float* out_scores,
+                                psb_stream_t stream) {
   if (queries == nullptr || table == nullptr || workspace == nullptr || out_ids == nullptr ||
       out_scores == nullptr || m <= 0 || n_items <= 0 || n_items >= (1ll << 31) || m >= (1 << 24))
     return PSB_E_ARG;
@@ -284,9 +285,17 @@ extern "C" int psb_catalog_topk(const float* queries, int64_t m, const float* ta
     return catalog_topk_exact(queries, m, table, n_items, d, bias, k, id_base, id_stride, workspace,
                               workspace_bytes, out_ids, out_scores, s);
   if (mode == PSB_TOPK_TC)
-    return catalog_topk_tc(queries, m, table, n_items, d, bias, k, id_base, id_stride, workspace,
+    return catalog_topk_tc(queries, m, table, n_items, d, bias, k, id_base, id_stride, max_row_sqnorm, workspace,
                            workspace_bytes, out_ids, out_scores, s);
   return PSB_E_UNSUPPORTED;
+}
+
+extern "C" int psb_table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out,
+                                        psb_stream_t stream) {
+  int st = check_table_args(table, rows, d);
+  if (st != PSB_OK) return st;
+  if (out == nullptr) return PSB_E_ARG;
+  return table_max_row_sqnorm(table, rows, d, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,

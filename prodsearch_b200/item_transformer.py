@@ -186,17 +186,28 @@ class ItemTransformerRanker(nn.Module):
             bias = self.product_bias if self.args.sim_func == "bias_product" else None
             return ops.score_rows(q, self.product_emb.weight, batch_data.candi_prod_idxs, bias)
 
-    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_EXACT):
+    def _max_row_sqnorm(self):
+        """|e|^2 bound of the tensor-core shortlist, cached while the item table is unchanged."""
+        w = self.product_emb.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_norm_cache", (None, None))[0] != key:
+            self._norm_cache = (key, ops.table_max_row_sqnorm(w, self.prod_pad_idx))
+        return self._norm_cache[1]
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):
         """Top-k over the whole catalog (items 0..P-1) with fused selection; replaces
-        get_prod_scores + host argsort (trainer.py:189-226,:152).  Returns (ids [M,k], scores [M,k])."""
+        get_prod_scores + host argsort (trainer.py:189-226,:152).  Returns (ids [M,k], scores [M,k]).
+        mode TOPK_TC: tcgen05 TF32 shortlist + exact fp32 rescoring (identical results to TOPK_EXACT;
+        shapes it does not cover run the exact kernels)."""
         with torch.no_grad():
             if torch.is_tensor(batch_or_queries):
                 q = batch_or_queries
             else:
                 q = self.encode_queries(batch_or_queries.query_word_idxs, batch_or_queries.u_item_idxs)
             bias = self.product_bias if self.args.sim_func == "bias_product" else None
+            norm = self._max_row_sqnorm() if mode == _lib.TOPK_TC else None
             return ops.catalog_topk(q.contiguous(), self.product_emb.weight, k, n_items=self.prod_pad_idx,
-                                    bias=bias, mode=mode)
+                                    bias=bias, mode=mode, max_row_sqnorm=norm)
 
 
 # the north star names the class ProdSearchModel; the reference's real name is kept as primary

@@ -148,7 +148,17 @@ def zero_rows(rows, n_rows, d, dense=None, dense_bias=None):
                                ptr(dense_bias, f32), stream_ptr()), "psb_zero_rows")
 
 
-def catalog_topk(queries, table, k, n_items=None, bias=None, id_base=0, id_stride=1, mode=_lib.TOPK_EXACT):
+def table_max_row_sqnorm(table, n_rows=None):
+    """Device scalar max_r |table[r]|^2 (psb_table_max_row_sqnorm); cache it while the table is static."""
+    out = torch.empty((1,), dtype=f32, device=table.device)
+    n_rows = table.shape[0] if n_rows is None else int(n_rows)
+    check(load().psb_table_max_row_sqnorm(ptr(table, f32), n_rows, table.shape[1], ptr(out), stream_ptr()),
+          "psb_table_max_row_sqnorm")
+    return out
+
+
+def catalog_topk(queries, table, k, n_items=None, bias=None, id_base=0, id_stride=1, mode=_lib.TOPK_EXACT,
+                 max_row_sqnorm=None):
     """Top-k items per query over the whole table with fused selection (psb_catalog_topk).
     Returns (ids [m,k] int64, scores [m,k] fp32), descending score / ascending id."""
     m, d = queries.shape
@@ -161,7 +171,8 @@ def catalog_topk(queries, table, k, n_items=None, bias=None, id_base=0, id_strid
     ids = torch.empty((m, k), dtype=i64, device=dev)
     sc = torch.empty((m, k), dtype=f32, device=dev)
     check(load().psb_catalog_topk(ptr(queries, f32), m, ptr(table, f32), n_items, d, ptr(bias, f32), k,
-                                  int(id_base), int(id_stride), mode, ptr(ws), ws_bytes, ptr(ids), ptr(sc),
+                                  int(id_base), int(id_stride), mode, ptr(max_row_sqnorm, f32), ptr(ws), ws_bytes,
+                                  ptr(ids), ptr(sc),
                                   stream_ptr()), "psb_catalog_topk")
     return ids, sc
 
@@ -194,6 +205,6 @@ def _profiled(name, fn):
     return wrapper
 
 
-for _n in ("gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
+for _n in ("table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
            "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge"):
     globals()[_n] = _profiled(_n, globals()[_n])

@@ -351,3 +351,45 @@ def test_topk_merge_matches_global(ops):
     assert torch.equal(mi, gi) and torch.equal(ms, gs)
     ref_i, _ = oracle.merge_shard_topk([p.cpu().numpy() for p in parts_i], [p.cpu().numpy() for p in parts_s], k)
     assert np.array_equal(mi.cpu().numpy(), ref_i)
+
+
+# ---------------------------------------------------------------- G5 tensor-core mode (tcgen05 + TMA)
+@pytest.mark.parametrize("m,n,k,with_bias", [(24, 100_000, 100, False), (130, 70_001, 100, True),
+                                             (384, 1_000_000, 100, False), (5, 40_000, 10, True)])
+def test_catalog_topk_tc_equals_exact(ops, m, n, k, with_bias):
+    """The TF32 shortlist + exact rescoring returns bit-identical (ids, scores) to the fp32 mode."""
+    from prodsearch_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    E = torch.randn(n + 1, 128, generator=g, device="cuda")
+    Q = torch.randn(m, 128, generator=g, device="cuda")
+    bias = (torch.randn(n + 1, generator=g, device="cuda") * 0.1) if with_bias else None
+    ids_e, sc_e = ops.catalog_topk(Q, E, k, n_items=n, bias=bias, mode=_lib.TOPK_EXACT)
+    ids_t, sc_t = ops.catalog_topk(Q, E, k, n_items=n, bias=bias, mode=_lib.TOPK_TC)
+    assert torch.equal(ids_e, ids_t)
+    assert torch.equal(sc_e, sc_t)
+    if n <= 100_000:
+        _check_topk(ids_t, sc_t, Q.cpu(), E.cpu(), bias.cpu() if with_bias else None, k, n)
+
+
+def test_catalog_topk_tc_degenerate_falls_back(ops):
+    """Massive ties (every item identical) overflow the shortlist; the exact fallback still returns
+    the lower-id-first answer."""
+    from prodsearch_b200 import _lib
+    n, m, k = 50_000, 3, 100
+    E = torch.ones(n, 128, device="cuda")
+    Q = torch.ones(m, 128, device="cuda")
+    ids, sc = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_TC)
+    assert torch.equal(ids.cpu(), torch.arange(k).repeat(m, 1))
+    assert bool((sc == 128.0).all())
+
+
+def test_catalog_topk_tc_scaled_rows(ops):
+    """Rows with very different norms (the eps bound uses the max row norm)."""
+    from prodsearch_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, m, k = 200_000, 64, 100
+    E = torch.randn(n, 128, generator=g, device="cuda") * torch.logspace(-2, 1, n, device="cuda").unsqueeze(1)
+    Q = torch.randn(m, 128, generator=g, device="cuda")
+    a = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_EXACT)
+    b = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_TC)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
