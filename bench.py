@@ -254,17 +254,18 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from prodsearch_b200 import _lib, ops, synth
-    from prodsearch_b200.item_transformer import ItemTransformerRanker
+    from prodsearch_b200.item_transformer import ItemTransformerRanker, ShardedItemTransformerRanker
     from prodsearch_b200.optimizers import build_optim
-    from prodsearch_b200 import sharded
     peaks = load_peaks()
     args = model_args(a.dropout)
     P, V, B = WORKLOAD["product_size"], WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
     torch.manual_seed(666)
-    model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+    if world > 1:   # item table row-sharded over the ranks, lookups exchanged by all-to-all
+        model = ShardedItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+    else:
+        model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
     optim = build_optim(args, model)
     model.train()
-    ddp = sharded.DenseGradAllReduce(model) if world > 1 else None
     n_total = a.warmup + a.steps
     host, devb = [], []
     for it in range(n_total):
@@ -279,8 +280,8 @@ def run_b200_arm(a):
         loss = model(batch)
         model.zero_grad()
         loss.backward()
-        if ddp is not None:
-            ddp.reduce()
+        if world > 1:
+            model.sync_grads()
         optim.step()
         return loss
 

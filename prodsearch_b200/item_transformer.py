@@ -103,14 +103,17 @@ class ItemTransformerRanker(nn.Module):
         self.transformer_encoder.initialize_parameters(logger)
 
     # ---- shared front half -----------------------------------------------------------
-    def encode_queries(self, query_word_idxs, u_item_idxs, copies=1):
+    def encode_queries(self, query_word_idxs, u_item_idxs, copies=1, hist=None):
         """Query encoder + history gather + transformer encode -> [B*copies, d]
-        (item_transformer.py:449-484 / :118-140)."""
+        (item_transformer.py:449-484 / :118-140).  ``hist`` = (weight, sink, remapped idx) when the
+        item table is sharded and the rows live in a fetched mini table."""
         B, L = u_item_idxs.shape
         q_emb = self.query_encoder.encode_indices(self.word_embeddings.weight, query_word_idxs, self.word_sink,
                                                   pad_idx=self.word_pad_idx)
-        hist_w = self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight
-        u_emb = F_.gather_rows(hist_w, u_item_idxs, self.hist_sink)
+        if hist is None:
+            hist_w = self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight
+            hist = (hist_w, self.hist_sink, u_item_idxs)
+        u_emb = F_.gather_rows(hist[0], hist[2], hist[1])
         seq = torch.cat([q_emb.unsqueeze(1), u_emb], dim=1)
         mask = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=seq.device),
                           u_item_idxs.ne(self.prod_pad_idx)], dim=1)
@@ -120,6 +123,11 @@ class ItemTransformerRanker(nn.Module):
         out_pos = -1 if self.args.use_item_pos else 0
         top = self.transformer_encoder.encode(seq, mask, use_pos=self.args.use_pos_emb)
         return top[:, out_pos, :]
+
+    def _resolve_item_rows(self, target_prod_idxs, neg_item_idxs, u_item_idxs):
+        """(item weight, item sink, target idx, negative idx, hist triple or None) of this step.
+        Single GPU: the full local table.  The sharded subclass fetches a mini table instead."""
+        return self.product_emb.weight, self.item_sink, target_prod_idxs, neg_item_idxs, None
 
     # ---- training -----------------------------------------------------------------------
     def forward(self, batch_data, train_pv=False):
@@ -141,33 +149,37 @@ class ItemTransformerRanker(nn.Module):
         K = self.args.neg_per_pos
         W = pos_iword_idxs.shape[1]
         neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+        item_w, item_sink, tgt_idx, neg_idx, hist = self._resolve_item_rows(target_prod_idxs, neg_item_idxs,
+                                                                            u_item_idxs)
         stochastic = self.training and self.args.dropout > 0
         if stochastic:
             # dropout makes the K negative encodes differ (transformer.py:56, neural.py:226)
-            pos_out = self.encode_queries(query_word_idxs, u_item_idxs)
-            neg_out = self.encode_queries(query_word_idxs, u_item_idxs, copies=K)
+            pos_out = self.encode_queries(query_word_idxs, u_item_idxs, hist=hist)
+            neg_out = self.encode_queries(query_word_idxs, u_item_idxs, copies=K, hist=hist)
         else:
             # deterministic encoder: the K copies the reference re-encodes (:473-476) are identical
-            pos_out = self.encode_queries(query_word_idxs, u_item_idxs)
+            pos_out = self.encode_queries(query_word_idxs, u_item_idxs, hist=hist)
             neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
         bias = self.product_bias if self.args.sim_func == "bias_product" else None
         pos_weight = float(K) if self.args.pos_weight else 1.0
-        ps = F_.ns_loss(pos_out.contiguous(), self.product_emb.weight, target_prod_idxs.view(B, 1),
-                        neg_item_idxs.view(B, 1, K), self.item_sink, anchor_b=neg_out.contiguous(), bias=bias,
-                        pos_weight=pos_weight)
+        ps = F_.ns_loss(pos_out.contiguous(), item_w, tgt_idx.view(B, 1), neg_idx.view(B, 1, K), item_sink,
+                        anchor_b=neg_out.contiguous(), bias=bias, pos_weight=pos_weight)
         ps_loss = ps.mean()
-        item_loss = self.item_to_words(target_prod_idxs, pos_iword_idxs, K, neg_word_idxs)
+        item_loss = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink)
         with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here)
             self._ps_acc = ps_loss.detach() if self._ps_acc is None else self._ps_acc + ps_loss.detach()
             self._item_acc = item_loss.detach() if self._item_acc is None else self._item_acc + item_loss.detach()
         return ps_loss + item_loss
 
-    def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None):
+    def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None, item_w=None,
+                      item_sink=None):
         """item_transformer.py:260-283."""
         B, W = target_word_idxs.shape
         if neg_sample_idxs is None:
             neg_sample_idxs = torch.multinomial(self.word_dists, B * W * n_negs, replacement=True)
-        anchor = F_.gather_rows(self.product_emb.weight, target_prod_idxs, self.item_sink)
+        if item_w is None:
+            item_w, item_sink = self.product_emb.weight, self.item_sink
+        anchor = F_.gather_rows(item_w, target_prod_idxs, item_sink)
         loss = F_.ns_loss(anchor, self.word_embeddings.weight, target_word_idxs,
                           neg_sample_idxs.view(B, W, n_negs), self.word_sink, bias=self.word_bias,
                           pad_idx=self.word_pad_idx)
@@ -212,3 +224,75 @@ class ItemTransformerRanker(nn.Module):
 
 # the north star names the class ProdSearchModel; the reference's real name is kept as primary
 ProdSearchModel = ItemTransformerRanker
+
+
+class ShardedItemTransformerRanker(ItemTransformerRanker):
+    """TEM with the item table row-sharded over the ranks of a process group.
+
+    ``product_emb`` holds only this rank's rows (owner = id % G, local row = id // G).  Each step
+    fetches the unique rows it needs into a mini table (index + row all-to-all), runs the same fused
+    kernels on it, and ``sync_grads()`` pushes the mini table's gradient rows back to the owners and
+    all-reduces the replicated dense parameters.  Call order per step (all ranks, SPMD):
+    ``loss = model(batch); model.zero_grad(); loss.backward(); model.sync_grads(); optim.step()``."""
+
+    def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None, group=None,
+                 grad_mode="dense"):
+        if args.sep_prod_emb or args.sim_func == "bias_product":
+            raise NotImplementedError("sharded TEM: sep_prod_emb / bias_product are not sharded yet")
+        import torch.distributed as dist
+        from . import sharded
+        self._group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        super().__init__(args, device, vocab_size, product_size, vocab_words, word_dists, grad_mode)
+        full = self.product_emb.weight.detach()
+        fold_sink = {}
+
+        def fold(weight, ids, grads):
+            sink = fold_sink.get("s")
+            if sink is None or sink.weight is not weight:
+                pad_local = self.prod_pad_idx // world if self.prod_pad_idx % world == rank else -1
+                sink = fold_sink["s"] = F_.RowGradSink(weight, pad_local, None, grad_mode)
+            sink._pending.append(ops.make_contrib(ids, grads))
+            sink.finalize()
+
+        self.item_table = sharded.ShardedTable.from_full(full, group, ops.gather_rows, fold, device,
+                                                         pad_idx=self.prod_pad_idx)
+        # the module's parameter becomes the local shard (same state_dict key, 1/G of the rows)
+        self.product_emb = nn.Embedding(self.item_table.local_rows, self.embedding_size)
+        self.product_emb.weight = self.item_table.weight
+        self._make_sinks()
+        self._mini = None
+        self._dense = sharded.DenseGradAllReduce(self, skip=("product_emb.weight",), group=group)
+
+    def _resolve_item_rows(self, target_prod_idxs, neg_item_idxs, u_item_idxs):
+        mini, (tgt, neg, hist), pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs])
+        sink = F_.RowGradSink(mini, pad, None, "dense")
+        self._mini = mini
+        return mini, sink, tgt, neg, (mini, sink, hist)
+
+    def sync_grads(self):
+        if self._mini is not None:
+            g = self._mini.grad if self._mini.grad is not None else torch.zeros_like(self._mini)
+            # data-parallel mean over ranks, like the replicated parameters
+            self.item_table.push_grads(g / self.item_table.world)
+            self._mini = None
+        self._dense.reduce()
+
+    def test_dotproduct(self, batch_data):
+        with torch.no_grad():
+            mini, (cand, hist), _ = self.item_table.fetch([batch_data.candi_prod_idxs, batch_data.u_item_idxs])
+            q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs, hist=(mini, None, hist))
+            return ops.score_rows(q.contiguous(), mini, cand, None)
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):
+        from . import sharded
+        with torch.no_grad():
+            if torch.is_tensor(batch_or_queries):
+                q = batch_or_queries
+            else:
+                raise NotImplementedError("sharded rank_catalog takes encoded query vectors")
+
+            def topk(qa, w, kk, n_local, base, stride, bias):
+                return ops.catalog_topk(qa, w, kk, n_items=n_local, bias=bias, id_base=base, id_stride=stride, mode=mode)
+            return sharded.sharded_rank_catalog(q.contiguous(), self.item_table, self.prod_pad_idx, k, topk,
+                                                ops.topk_merge)
