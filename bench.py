@@ -322,18 +322,19 @@ def run_b200_arm(a):
         t = torch.tensor([dev_sec, e2e_sec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_sec, e2e_sec = float(t[0]), float(t[1])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # ---- per-op timing of the hand-written kernels inside the same step (separate pass)
+    # ---- per-op timing of the hand-written kernels inside the same step (separate pass, all ranks
+    #      take part because the sharded step contains collectives)
     ops.PROFILE = {}
     for it in range(min(a.steps, 10)):
         flush.zero_()
         step(devb[a.warmup + it])
-    torch.cuda.synchronize()
+    barrier()
     prof = {k: (sum(s.elapsed_time(e) for s, e in v) / len(v), len(v) // min(a.steps, 10)) for k, v in ops.PROFILE.items()}
     ops.PROFILE = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     d = WORKLOAD["embedding_size"]
     K, L, W = WORKLOAD["neg_per_pos"], WORKLOAD["uprev_review_limit"], 1
     alg = {  # algorithmic bytes per launch at this config
