@@ -136,6 +136,120 @@ ns_loss_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ a
   }
 }
 
+// Fast path for d <= 128 and 1 + k <= 8: all rows of one target position are loaded before any
+// arithmetic (up to 8 independent 512 B row reads per warp), the 8 partial dot products are reduced
+// together with a halving butterfly (9 shuffles instead of 40), and each score's loss / gradient is
+// evaluated by the lanes that hold its sum instead of redundantly by all 32.
+template <bool HAS_B>
+__global__ void __launch_bounds__(256)
+ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ anchor_b,
+                    const float4* __restrict__ table, int64_t table_rows, int d4,
+                    const float* __restrict__ bias, const int64_t* __restrict__ pos_idx,
+                    const int64_t* __restrict__ neg_idx, const uint8_t* __restrict__ mask, int64_t pad_idx,
+                    const float* __restrict__ neg_weight, float pos_weight, int64_t n, int w, int k,
+                    float* __restrict__ loss, float* __restrict__ coef_pos, float* __restrict__ coef_neg,
+                    float4* __restrict__ grad_a, float4* __restrict__ grad_b) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool col_ok = lane < d4;
+  // which score this lane owns after the butterfly, and the lane that is its designated writer
+  const int my_s = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool writer = (lane & 3) == 0;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int cnt = 0;
+    for (int j0 = 0; j0 < w; j0 += 32) {
+      const int j = j0 + lane;
+      bool valid = false;
+      if (j < w) valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pos_idx[i * w + j] != pad_idx);
+      cnt += __popc(__ballot_sync(kFull, valid));
+    }
+    const float denom = static_cast<float>(cnt > 0 ? cnt : 1);
+    const float4 a = col_ok ? anchor_a[i * d4 + lane] : zero4();
+    float4 ga = zero4();
+    float loss_acc = 0.f;
+    for (int j = 0; j < w; ++j) {
+      // lane s <= k fetches the index / bias / weight of score s
+      int64_t myidx = -1;
+      float mybias = 0.f, mywt = 0.f;
+      if (lane <= k) {
+        myidx = lane == 0 ? pos_idx[i * w + j] : neg_idx[(i * w + j) * k + (lane - 1)];
+        mywt = lane == 0 ? pos_weight : (neg_weight != nullptr ? neg_weight[i * k + (lane - 1)] : 1.f);
+      }
+      const int64_t pj = __shfl_sync(kFull, myidx, 0);
+      const bool valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pj != pad_idx);
+      if (myidx < 0 || myidx >= table_rows) myidx = -1;
+      if (bias != nullptr && myidx >= 0) mybias = bias[myidx];
+      float4 row[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int64_t r = __shfl_sync(kFull, myidx, s);
+        row[s] = (r >= 0 && col_ok) ? ldg_row4(table + r * d4 + lane) : zero4();
+      }
+      float v[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        float4 anc = a;
+        if (HAS_B && s >= 1 && s <= k && col_ok) anc = anchor_b[(i * k + (s - 1)) * d4 + lane];
+        v[s] = dot4(anc, row[s]);
+      }
+      // halving butterfly: 8 values x 32 lanes -> lane L holds the full sum of value my_s
+      float u[4], t2[2];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float mine = (lane & 16) ? v[t + 4] : v[t];
+        const float other = (lane & 16) ? v[t] : v[t + 4];
+        u[t] = mine + __shfl_xor_sync(kFull, other, 16);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const float mine = (lane & 8) ? u[t + 2] : u[t];
+        const float other = (lane & 8) ? u[t] : u[t + 2];
+        t2[t] = mine + __shfl_xor_sync(kFull, other, 8);
+      }
+      float z;
+      {
+        const float mine = (lane & 4) ? t2[1] : t2[0];
+        const float other = (lane & 4) ? t2[0] : t2[1];
+        z = mine + __shfl_xor_sync(kFull, other, 4);
+      }
+      z += __shfl_xor_sync(kFull, z, 2);
+      z += __shfl_xor_sync(kFull, z, 1);
+      const float b_s = __shfl_sync(kFull, mybias, my_s);
+      const float wt = __shfl_sync(kFull, mywt, my_s);
+      const float x = z + b_s;
+      const float tgt = my_s == 0 ? 1.f : 0.f;
+      const float m = valid ? 1.f : 0.f;
+      float g = 0.f, lterm = 0.f;
+      if (my_s <= k) {
+        g = m * wt * (sigmoidf_(x) - tgt) / denom;
+        if (writer) {
+          lterm = wt * bce_value(x, tgt);
+          if (my_s == 0) coef_pos[i * w + j] = g;
+          else coef_neg[(i * w + j) * k + (my_s - 1)] = g;
+        }
+      }
+      loss_acc += m * warp_sum(lterm);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int holder = ((s >> 2) & 1) * 16 + ((s >> 1) & 1) * 8 + (s & 1) * 4;
+        const float gs = __shfl_sync(kFull, g, holder);
+        if (HAS_B && s >= 1) {
+          if (s <= k && col_ok) {
+            float4 o = zero4();
+            fma4(o, gs, row[s]);
+            grad_b[(i * k + (s - 1)) * d4 + lane] = o;
+          }
+        } else {
+          fma4(ga, gs, row[s]);   // gs == 0 for s > k
+        }
+      }
+    }
+    if (lane == 0) loss[i] = loss_acc / denom;
+    if (col_ok) grad_a[i * d4 + lane] = ga;
+  }
+}
+
 // scores[i, c] = <anchor[i], table[idx[i, c]]> (+ bias[idx[i, c]]): the candidate scoring of
 // test_dotproduct (item_transformer.py:141-145).  One warp per query, 4 candidate rows in flight.
 template <int C>
@@ -243,7 +357,22 @@ extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, con
       reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx,       \
       neg_weight, pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,       \
       reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b))
-  if (d4 <= 32) PSB_NS_LAUNCH(1);
+  if (d4 <= 32 && k <= 7) {
+    const int gridf = grid_for(n, 8, 32);
+    if (anchor_b != nullptr)
+      ns_loss_fast_kernel<true><<<gridf, 256, 0, s>>>(
+          reinterpret_cast<const float4*>(anchor_a), reinterpret_cast<const float4*>(anchor_b),
+          reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx, neg_weight,
+          pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,
+          reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b));
+    else
+      ns_loss_fast_kernel<false><<<gridf, 256, 0, s>>>(
+          reinterpret_cast<const float4*>(anchor_a), reinterpret_cast<const float4*>(anchor_b),
+          reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx, neg_weight,
+          pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,
+          reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b));
+  }
+  else if (d4 <= 32) PSB_NS_LAUNCH(1);
   else if (d4 <= 64) PSB_NS_LAUNCH(2);
   else PSB_NS_LAUNCH(4);
 #undef PSB_NS_LAUNCH

@@ -120,8 +120,9 @@ constexpr int kSmallCap = kSmallNT * kSmallIPT;  // 16384 slots
 
 __global__ void __launch_bounds__(kSmallNT, 1)
 small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, int64_t table_rows, int64_t drop_idx, int passes,
-                           uint32_t* __restrict__ sorted_slots, int32_t* __restrict__ seg_start,
-                           int32_t* __restrict__ unique_rows, int32_t* __restrict__ n_unique) {
+                           uint32_t* __restrict__ sorted_slots, uint32_t* __restrict__ sorted_keys,
+                           int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows,
+                           int32_t* __restrict__ n_unique) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* sk = reinterpret_cast<uint32_t*>(smem_raw);          // [cap] keys
   uint32_t* sv = sk + kSmallCap;                                 // [cap] slots
@@ -181,6 +182,7 @@ small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, 
     if (p < n_total) {
       const uint32_t kk = sk[p];
       sorted_slots[p] = sv[p];
+      sorted_keys[p] = kk;
       if (kk != sentinel && (p == 0 || sk[p - 1] != kk)) {
         seg_start[seg] = p;
         unique_rows[seg] = static_cast<int32_t>(kk);
@@ -362,51 +364,9 @@ heads_write_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentin
 // order with a bracketing that depends only on (n_total, data): bit-reproducible, no atomics.
 // ------------------------------------------------------------------------------------
 template <int C>
-__device__ __forceinline__ void accumulate_run(const ContribTable& T, const uint32_t* __restrict__ sorted_slots,
-                                               int lo, int hi, int d4, int lane, float4 (&acc)[C], float& bacc) {
-  constexpr int U = 4;
-  for (int p = lo; p < hi; p += U) {
-    const float4* srcp[U];
-    float sc[U];
-    bool tb[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      srcp[u] = nullptr;
-      sc[u] = 0.f;
-      tb[u] = false;
-      if (p + u < hi) {
-        const uint32_t slot = sorted_slots[p + u];
-        const int ci = locate(T, slot);
-        const psb_contrib_t& cc = T.c[ci];
-        const uint32_t i = slot - T.off[ci];
-        const int64_t row = cc.src_row != nullptr ? cc.src_row[i]
-                                                  : static_cast<int64_t>(i / static_cast<uint32_t>(cc.src_div));
-        float s = cc.scale != nullptr ? cc.scale[i] : 1.f;
-        if (cc.scale2 != nullptr) s *= cc.scale2[i / static_cast<uint32_t>(cc.scale2_div)];
-        sc[u] = s;
-        tb[u] = cc.to_bias != 0;
-        srcp[u] = reinterpret_cast<const float4*>(cc.src) + row * d4;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int col = lane + 32 * c;
-      float4 v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = (srcp[u] != nullptr && col < d4) ? __ldg(srcp[u] + col) : zero4();
-#pragma unroll
-      for (int u = 0; u < U; ++u) fma4(acc[c], sc[u], v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (tb[u]) bacc += sc[u];
-  }
-}
-
-template <int C>
 __global__ void __launch_bounds__(256)
 seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __restrict__ sorted_slots,
-                  const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
+                  const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ seg_start,
                   const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
                   float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
                   float4* __restrict__ partial, float* __restrict__ partial_bias) {
@@ -418,52 +378,115 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
   const int n_valid = seg_start[nu];
   const int ch = 1 << ch_shift;
   const int n_units = (n_valid + ch - 1) >> ch_shift;
+  constexpr int U = 8;  // source rows in flight per warp
   for (int unit = warp; unit < n_units; unit += nwarps) {
     const int u_lo = unit << ch_shift;
     const int u_hi = min(u_lo + ch, n_valid);
-    // segment containing position u_lo: largest seg with seg_start[seg] <= u_lo
-    int a = 0, b = nu;  // invariant: seg_start[a] <= u_lo < seg_start[b]
+    int a = 0, b = nu;  // largest seg with seg_start[seg] <= u_lo
     while (b - a > 1) {
       const int mid = (a + b) >> 1;
       if (seg_start[mid] <= u_lo) a = mid; else b = mid;
     }
     int seg = a;
-    int p = u_lo;
-    while (p < u_hi) {
-      const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
-      const int r_hi = min(s_hi, u_hi);
-      float4 acc[C];
+    bool started_here = seg_start[seg] == u_lo;
+    float4 acc[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = zero4();
-      float bacc = 0.f;
-      accumulate_run<C>(T, sorted_slots, p, r_hi, d4, lane, acc, bacc);
-      const bool starts_here = s_lo >= u_lo;
-      const bool ends_here = s_hi <= u_hi;
-      if (starts_here && ends_here) {
-        const int64_t drow = unique_rows[seg];
+    for (int c = 0; c < C; ++c) acc[c] = zero4();
+    float bacc = 0.f;
+    bool open = false;
+    for (int p = u_lo; p < u_hi; p += 32) {
+      // lane-parallel metadata of the next (up to) 32 sorted slots
+      const int q = p + lane;
+      const bool in = q < u_hi;
+      uint32_t key = 0xffffffffu;
+      unsigned long long src = 0;
+      float sc = 0.f;
+      bool tb = false;
+      if (in) {
+        const uint32_t slot = sorted_slots[q];
+        key = sorted_keys[q];
+        const int ci = locate(T, slot);
+        const psb_contrib_t& cc = T.c[ci];
+        const uint32_t i = slot - T.off[ci];
+        const int64_t row = cc.src_row != nullptr ? cc.src_row[i]
+                                                  : static_cast<int64_t>(i / static_cast<uint32_t>(cc.src_div));
+        sc = cc.scale != nullptr ? cc.scale[i] : 1.f;
+        if (cc.scale2 != nullptr) sc *= cc.scale2[i / static_cast<uint32_t>(cc.scale2_div)];
+        tb = cc.to_bias != 0;
+        src = reinterpret_cast<unsigned long long>(reinterpret_cast<const float4*>(cc.src) + row * d4);
+      }
+      // a slot closes its segment when the next sorted key differs (or the valid range ends)
+      uint32_t key_next = __shfl_down_sync(kFull, key, 1);
+      if (lane == 31 || q + 1 >= u_hi) key_next = (q + 1 < n_valid) ? sorted_keys[min(q + 1, n_valid - 1)] : 0xfffffffeu;
+      const unsigned last_mask = __ballot_sync(kFull, in && key_next != key);
+      const unsigned bias_mask = __ballot_sync(kFull, tb);
+      const int cnt = min(32, u_hi - p);
+      for (int u0 = 0; u0 < cnt; u0 += U) {
+        float4 v[U][C];
+        float su[U];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = lane + 32 * c;
-          if (col < d4) {
-            if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
-            if (dense != nullptr) dense[drow * d4 + col] = acc[c];
+        for (int u = 0; u < U; ++u) {
+          const int srcl = min(u0 + u, 31);
+          const unsigned long long ptr = __shfl_sync(kFull, src, srcl);
+          su[u] = __shfl_sync(kFull, sc, srcl);
+          const bool ok = u0 + u < cnt;
+          if (!ok) su[u] = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int col = lane + 32 * c;
+            v[u][c] = (ok && col < d4) ? __ldg(reinterpret_cast<const float4*>(ptr) + col) : zero4();
           }
         }
-        if (lane == 0) {
-          if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
-          if (dense_bias != nullptr) dense_bias[drow] = bacc;
-        }
-      } else {
-        const int64_t ps = static_cast<int64_t>(unit) * 2 + (starts_here ? 1 : 0);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = lane + 32 * c;
-          if (col < d4) partial[ps * d4 + col] = acc[c];
+        for (int u = 0; u < U; ++u) {
+          if (u0 + u >= cnt) break;
+#pragma unroll
+          for (int c = 0; c < C; ++c) fma4(acc[c], su[u], v[u][c]);
+          if ((bias_mask >> (u0 + u)) & 1u) bacc += su[u];
+          open = true;
+          if ((last_mask >> (u0 + u)) & 1u) {
+            // segment `seg` ends at sorted position p + u0 + u
+            const uint32_t drow = __shfl_sync(kFull, key, u0 + u);
+            if (started_here) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const int col = lane + 32 * c;
+                if (col < d4) {
+                  if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+                  if (dense != nullptr) dense[static_cast<int64_t>(drow) * d4 + col] = acc[c];
+                }
+              }
+              if (lane == 0) {
+                if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+                if (dense_bias != nullptr) dense_bias[drow] = bacc;
+              }
+            } else {  // a run that began in an earlier unit: partial, combined by the fix-up kernel
+              const int64_t ps = static_cast<int64_t>(unit) * 2;
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const int col = lane + 32 * c;
+                if (col < d4) partial[ps * d4 + col] = acc[c];
+              }
+              if (lane == 0) partial_bias[ps] = bacc;
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = zero4();
+            bacc = 0.f;
+            ++seg;
+            started_here = true;
+            open = false;
+          }
         }
-        if (lane == 0) partial_bias[ps] = bacc;
       }
-      p = r_hi;
-      ++seg;
+    }
+    if (open) {  // the last run continues into the next unit
+      const int64_t ps = static_cast<int64_t>(unit) * 2 + (started_here ? 1 : 0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int col = lane + 32 * c;
+        if (col < d4) partial[ps * d4 + col] = acc[c];
+      }
+      if (lane == 0) partial_bias[ps] = bacc;
     }
   }
 }
@@ -612,6 +635,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   while ((static_cast<int64_t>(1) << bits) <= table_rows) ++bits;  // sentinel == table_rows must fit
   const int passes = (bits + 7) / 8;
   const uint32_t* sorted_slots = nullptr;
+  const uint32_t* sorted_keys = nullptr;
   int st;
 
   if (n_total <= kSmallCap) {
@@ -624,9 +648,10 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
       attr_set = true;
     }
     small_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
-                                                         passes, vals_a, seg_start, unique_rows, n_unique);
+                                                         passes, vals_a, keys_a, seg_start, unique_rows, n_unique);
     if ((st = launch_status()) != PSB_OK) return st;
     sorted_slots = vals_a;
+    sorted_keys = keys_a;
   } else {
     const int nblocks = static_cast<int>((n_total + kTile - 1) / kTile);
     pack_keys_kernel<<<grid_for(n_total, 256 * 4), 256, 0, s>>>(T, n_total, table_rows, drop_idx, keys_a, vals_a);
@@ -650,6 +675,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     heads_write_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts, n_unique, seg_start, unique_rows);
     if ((st = launch_status()) != PSB_OK) return st;
     sorted_slots = vi;
+    sorted_keys = ki;
   }
 
   if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
@@ -660,7 +686,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     float4* partial = reinterpret_cast<float4*>(ws + L.partial);
     float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);
 #define PSB_SR_LAUNCH(C)                                                                                      \
-  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, seg_start, unique_rows, n_unique, d4, ch_shift,  \
+  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, sorted_keys, seg_start, n_unique, d4, ch_shift,   \
                                             reinterpret_cast<float4*>(reduced), reduced_bias,                 \
                                             reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial,  \
                                             partial_bias);                                                    \
