@@ -210,6 +210,79 @@ int psb_table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float*
 int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,
                    int64_t* out_ids, float* out_scores, psb_stream_t stream);
 
+/* ------------------------------------------------------------------ N1 ---
+ * Fused single-layer sequence encoder restricted to ONE output position: the last
+ * TransformerEncoderLayer + final LayerNorm of models/transformer.py:37-88 as used by
+ * ItemTransformerRanker.forward_dotproduct / test_dotproduct
+ * (models/item_transformer.py:478-491,:118-140) and ProductRanker (models/ps_model.py:336-339),
+ * which read only top_vecs[:, out_pos, :].  Per input sequence s (S of them, T tokens):
+ *
+ *   x[t]   = valid[t] * in[t] + pe[t]                      (transformer.py:75-80)
+ *   xn[t]  = pre_ln ? LayerNorm_attn(x[t]) : x[t]          (transformer.py:47-50; layer 0: no LN)
+ *   K,V    = xn Wk^T + bk, xn Wv^T + bv; q = (xn[o] Wq^T + bq) / sqrt(d/heads)   (neural.py:190-205)
+ *   P[h,:] = softmax_t(q_h . K_h[t], masked -> -1e18)      (neural.py:206-213)
+ * and per copy c < copies (the reference re-encodes the SAME sequence for the positive and
+ * every negative item, item_transformer.py:478-487; only the dropout masks differ):
+ *   ctx    = sum_t drop1(P)[h,t] V_h[t];  y = drop2(ctx Wo^T + bo) + x[o]         (neural.py:222-226, transformer.py:56)
+ *   z      = drop4(drop3(gelu(LN_ff(y) W1^T + b1)) W2^T + b2) + y                 (neural.py:30-33)
+ *   out[s*copies + c, :] = LayerNorm_out(z)                                        (transformer.py:86)
+ * Tokens: either first[s] (token 0) followed by table[idx[s, t-1]] (valid iff idx != pad_idx)
+ * -- the TEM layout [query, purchased items] -- or a dense [S,T,d] tensor with a uint8 mask
+ * (1 = real token; NULL = all real).  Masked keys get probability exactly 0; a sequence with no
+ * valid token attends uniformly, as the reference's softmax over equal -1e18 scores does.
+ * Dropout uses Philox4x32-10 keyed by *seed_dev (device uint64; a CUDA-graph replay sees the new
+ * seed), stream 1..4 = {attention, context, ff inner, ff output}, element index as laid out
+ * above; p_drop == 0 disables it.  All arithmetic fp32 (FFMA), fixed summation order.
+ * Shapes supported: d % 4 == 0, d <= 128, ff % 4 == 0, ff <= 1024, T <= 64, d % heads == 0. */
+typedef struct psb_encoder_params {
+  /* nn.Linear layout [out, in]; names follow models/neural.py / models/transformer.py */
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+  const float *ln_attn_g, *ln_attn_b; /* TransformerEncoderLayer.layer_norm (pre_ln only) */
+  const float *ln_ff_g, *ln_ff_b;     /* feed_forward.layer_norm */
+  const float *w1, *b1, *w2, *b2;     /* feed_forward.w_1 [ff,d], w_2 [d,ff] */
+  const float *ln_out_g, *ln_out_b;   /* TransformerEncoder.layer_norm */
+} psb_encoder_params_t;
+
+typedef struct psb_encoder_grads { /* same shapes; every pointer is OVERWRITTEN (not accumulated) */
+  float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+  float *ln_attn_g, *ln_attn_b, *ln_ff_g, *ln_ff_b, *w1, *b1, *w2, *b2, *ln_out_g, *ln_out_b;
+} psb_encoder_grads_t;
+
+typedef struct psb_encoder_cfg {
+  int64_t S, T, d, heads, ff, copies, out_pos; /* out_pos in [0, T) */
+  int32_t pre_ln;
+  int32_t raw_input; /* dense input only: rows are a previous layer's output -- the mask removes KEYS but
+                        rows are not zeroed and pe is not added (layers > 0 of a deeper encoder) */
+  float ln_eps, p_drop;
+  const uint64_t* seed_dev; /* device; required when p_drop > 0 */
+  const float* first;       /* [S,d] token 0, with table/idx [S,T-1] for tokens 1.. */
+  const float* table;
+  int64_t table_rows;
+  const int64_t* idx;
+  int64_t pad_idx;
+  const float* dense;       /* alternative input [S,T,d] (first/table/idx NULL) */
+  const uint8_t* mask;      /* [S,T] for the dense input */
+  const float* pe;          /* [T,d] positional rows or NULL (use_pos False) */
+} psb_encoder_cfg_t;
+
+/* Byte sizes of the caller-owned buffers: `saved` carries forward state to the backward call,
+ * `workspace` is scratch (backward != 0: size for psb_encoder_bwd).  < 0: invalid cfg. */
+int64_t psb_encoder_saved_bytes(const psb_encoder_cfg_t* cfg);
+int64_t psb_encoder_workspace_bytes(const psb_encoder_cfg_t* cfg, int32_t backward);
+
+/* out [S*copies, d].  cfg / params are HOST structs holding device pointers. */
+int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_params_t* params,
+                    void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes,
+                    float* out, psb_stream_t stream);
+
+/* Backward of psb_encoder_fwd for grad_out [S*copies, d] (same cfg, params, saved buffer).
+ * grad_first [S,d] + grad_rest [S,T-1,d] (TEM layout; rows of invalid tokens are zero) or
+ * grad_dense [S,T,d]; parameter gradients into `grads` (NULL members are skipped). */
+int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_params_t* params,
+                    const void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes,
+                    const float* grad_out, float* grad_first, float* grad_rest, float* grad_dense,
+                    const psb_encoder_grads_t* grads, psb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

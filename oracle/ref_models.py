@@ -106,7 +106,12 @@ def gelu_tanh(x):
     return 0.5 * x * (1 + torch.tanh(math.sqrt(2 / math.pi) * (x + 0.044715 * torch.pow(x, 3))))
 
 
-def multi_head_attention(P, pre, key, value, query, pad_mask, heads, p=0.0, training=False):
+def _drop(x, p, training, mul=None):
+    """nn.Dropout; ``mul`` supplies the keep/scale multipliers instead of drawing them (parity runs)."""
+    return x * mul if mul is not None else F.dropout(x, p=p, training=training)
+
+
+def multi_head_attention(P, pre, key, value, query, pad_mask, heads, p=0.0, training=False, attn_mul=None):
     """MultiHeadedAttention.forward, models/neural.py:98-231 (layer_cache=None path).
 
     pad_mask: bool [B,Tq or 1,Tk], True where the key is padding (filled with -1e18
@@ -124,31 +129,32 @@ def multi_head_attention(P, pre, key, value, query, pad_mask, heads, p=0.0, trai
     scores = torch.matmul(q, k.transpose(2, 3))
     if pad_mask is not None:
         scores = scores.masked_fill(pad_mask.unsqueeze(1).expand_as(scores), -1e18)
-    attn = F.dropout(torch.softmax(scores, dim=-1), p=p, training=training)
+    attn = _drop(torch.softmax(scores, dim=-1), p, training, attn_mul)
     ctx = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, -1, heads * dh)
     return F.linear(ctx, P[pre + "final_linear.weight"], P[pre + "final_linear.bias"])
 
 
-def encoder_layer(P, pre, i, x, pad_mask, heads, p=0.0, training=False):
+def encoder_layer(P, pre, i, x, pad_mask, heads, p=0.0, training=False, muls=None):
     """TransformerEncoderLayer.forward, models/transformer.py:47-57 and
     PositionwiseFeedForward.forward, models/neural.py:30-33.  Layer 0 skips the
-    pre-attention LayerNorm (:48-51)."""
+    pre-attention LayerNorm (:48-51).  ``muls`` = dict(attn [S,H,T,T], ctx [S,T,d], inner [S,T,ff],
+    out [S,T,d]) replaces the four dropout draws by supplied multipliers."""
     d = x.shape[-1]
+    m = muls or {}
     h = x if i == 0 else F.layer_norm(x, (d,), P[pre + "layer_norm.weight"],
                                       P[pre + "layer_norm.bias"], 1e-6)
     ctx = multi_head_attention(P, pre + "self_attn.", h, h, h, pad_mask.unsqueeze(1),
-                               heads, p, training)
-    out = F.dropout(ctx, p=p, training=training) + x
+                               heads, p, training, m.get("attn"))
+    out = _drop(ctx, p, training, m.get("ctx")) + x
     ff = pre + "feed_forward."
     n = F.layer_norm(out, (d,), P[ff + "layer_norm.weight"], P[ff + "layer_norm.bias"], 1e-6)
-    inter = F.dropout(gelu_tanh(F.linear(n, P[ff + "w_1.weight"], P[ff + "w_1.bias"])),
-                      p=p, training=training)
-    y = F.dropout(F.linear(inter, P[ff + "w_2.weight"], P[ff + "w_2.bias"]), p=p, training=training)
+    inter = _drop(gelu_tanh(F.linear(n, P[ff + "w_1.weight"], P[ff + "w_1.bias"])), p, training, m.get("inner"))
+    y = _drop(F.linear(inter, P[ff + "w_2.weight"], P[ff + "w_2.bias"]), p, training, m.get("out"))
     return y + out
 
 
 def encoder_encode(P, cfg, x, valid_mask, use_pos=True, pre="transformer_encoder.",
-                   training=False):
+                   training=False, last_layer_muls=None):
     """TransformerEncoder.encode, models/transformer.py:71-88.
 
     x [S,T,d]; valid_mask [S,T] (1 = real token).  Input rows are zeroed where
@@ -161,7 +167,8 @@ def encoder_encode(P, cfg, x, valid_mask, use_pos=True, pre="transformer_encoder
         h = h + P[pre + "pos_emb.pe"][:, :T]
     for i in range(cfg.inter_layers):
         h = encoder_layer(P, "%stransformer_inter.%d." % (pre, i), i, h, ~valid, cfg.heads,
-                          cfg.dropout, training)
+                          cfg.dropout, training,
+                          last_layer_muls if i == cfg.inter_layers - 1 else None)
     return F.layer_norm(h, (d,), P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-6)
 
 

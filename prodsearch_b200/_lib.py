@@ -25,6 +25,23 @@ class Contrib(ctypes.Structure):
                 ("reserved", c_i32)]
 
 
+_ENC_NAMES = ("wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln_attn_g", "ln_attn_b", "ln_ff_g", "ln_ff_b",
+              "w1", "b1", "w2", "b2", "ln_out_g", "ln_out_b")
+
+
+class EncoderParams(ctypes.Structure):
+    """psb_encoder_params_t (also the layout of psb_encoder_grads_t)."""
+    _fields_ = [(n, c_vp) for n in _ENC_NAMES]
+
+
+class EncoderCfg(ctypes.Structure):
+    """psb_encoder_cfg_t."""
+    _fields_ = [("S", c_i64), ("T", c_i64), ("d", c_i64), ("heads", c_i64), ("ff", c_i64), ("copies", c_i64),
+                ("out_pos", c_i64), ("pre_ln", c_i32), ("raw_input", c_i32), ("ln_eps", c_f32), ("p_drop", c_f32),
+                ("seed_dev", c_vp), ("first", c_vp), ("table", c_vp), ("table_rows", c_i64), ("idx", c_vp),
+                ("pad_idx", c_i64), ("dense", c_vp), ("mask", c_vp), ("pe", c_vp)]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
 SIGNATURES = {
     "psb_abi_version": (c_i32, []),
@@ -47,6 +64,12 @@ SIGNATURES = {
                                  c_i64, c_vp, c_vp, c_vp]),
     "psb_table_max_row_sqnorm": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
+    "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
+    "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,
+                                c_vp, c_vp]),
+    "psb_encoder_bwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,
+                                c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(EncoderParams), c_vp]),
 }
 
 _lib = None

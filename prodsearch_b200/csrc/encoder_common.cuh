@@ -1,0 +1,286 @@
+// Building blocks of the fused sequence encoder (encoder_fwd.cu / encoder_bwd.cu): Philox dropout,
+// the CTA-tile FFMA product every projection runs through, LayerNorm rows, saved-state layout.
+//
+// Work shape: after restricting the last layer to the one output position the
+// model reads, a TEM step has S*copies = 2304 rows of 128..512-wide projections and ~3.3k token
+// rows of K/V projections -- ~1.2 GFLOP forward.  That is far too little for 128-row tcgen05 tiles
+// to fill 148 SMs, and fp32 parity (1e-5) rules TF32 out, so the projections run as fp32 FFMA
+// CTA tiles of R = 16/24 rows: ~100-200 CTAs, one per SM, weights streamed from L2 exactly once
+// per CTA with register prefetch, activations broadcast from shared memory.
+#pragma once
+#include "psb_common.cuh"
+
+namespace psb {
+namespace enc {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct Drop {
+  uint2 key;
+  uint32_t thr;  // keep iff (bits >> 8) >= thr, thr = round(p * 2^24); 0 = dropout off
+  float scale;   // 1 / (1 - p)
+  __device__ __forceinline__ bool on() const { return thr != 0u; }
+  // multipliers of elements e .. e+3 (e % 4 == 0) of dropout stream `sid`
+  __device__ __forceinline__ float4 mul4(uint32_t sid, uint64_t e) const {
+    const uint64_t c = e >> 2;
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), sid, 0u), key);
+    return make_float4((r.x >> 8) >= thr ? scale : 0.f, (r.y >> 8) >= thr ? scale : 0.f,
+                       (r.z >> 8) >= thr ? scale : 0.f, (r.w >> 8) >= thr ? scale : 0.f);
+  }
+  __device__ __forceinline__ float mul1(uint32_t sid, uint64_t e) const {
+    const uint64_t c = e >> 2;
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), sid, 0u), key);
+    const uint32_t q = static_cast<uint32_t>(e & 3);
+    const uint32_t b = q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;
+    return (b >> 8) >= thr ? scale : 0.f;
+  }
+};
+
+__device__ __forceinline__ Drop make_drop(const uint64_t* seed_dev, uint32_t thr, float scale) {
+  Drop d;
+  d.thr = thr;
+  d.scale = scale;
+  d.key = make_uint2(0u, 0u);
+  if (thr != 0u) {
+    const uint64_t s = *seed_dev;
+    d.key = make_uint2(static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32));
+  }
+  return d;
+}
+
+// ------------------------------------------------------------------ CTA-tile product
+// Y[R x J] = A[R x I] . B[I x J]: A lives in shared memory as float4 A4[i/4][r] (four consecutive
+// i of row r), B row-major in global memory (read once per CTA, 128-bit coalesced, prefetched one
+// 4-row block ahead).  The 8 warps split the J columns into cg groups of 128 (lane = 4 columns)
+// and the I range into ks = 8 / cg slices; each warp writes its partial tile to `red`
+// ([ks][R][J + 4] floats) and the caller combines the slices in fixed order (deterministic).
+struct Split {
+  int cg, ks;
+};
+__host__ __device__ inline Split split_for(int J) {
+  int cg = (J + 127) / 128;
+  cg = cg <= 1 ? 1 : cg <= 2 ? 2 : cg <= 4 ? 4 : 8;
+  return Split{cg, 8 / cg};
+}
+__host__ __device__ inline int red_floats(int R, int J) { return split_for(J).ks * R * (J + 4); }
+__host__ __device__ inline int a4_floats(int R, int I) { return I * R; }
+
+template <int R>
+__device__ __forceinline__ void tile_gemm(const float4* __restrict__ A4, int I, const float* __restrict__ B, int J,
+                                          float* __restrict__ red) {
+  static_assert(R % 4 == 0, "tile rows");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Split sp = split_for(J);
+  const int cgi = warp % sp.cg, ksi = warp / sp.cg;
+  const int col = cgi * 128 + lane * 4;
+  const int n4 = I >> 2;                       // blocks of 4 rows of B
+  const int per = (n4 + sp.ks - 1) / sp.ks;
+  const int b0 = min(n4, ksi * per), b1 = min(n4, b0 + per);
+  if (col >= J) return;
+  float4 acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = zero4();
+  if (b0 < b1) {
+    const float* bp = B + static_cast<size_t>(b0) * 4 * J + col;
+    float4 b[4], bn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = ldg_row4(reinterpret_cast<const float4*>(bp + static_cast<size_t>(u) * J));
+    for (int blk = b0; blk < b1; ++blk) {
+      const bool more = blk + 1 < b1;
+      bp += static_cast<size_t>(4) * J;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        bn[u] = more ? ldg_row4(reinterpret_cast<const float4*>(bp + static_cast<size_t>(u) * J)) : zero4();
+      const float4* a = A4 + static_cast<size_t>(blk) * R;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 av = a[r];
+        fma4(acc[r], av.x, b[0]);
+        fma4(acc[r], av.y, b[1]);
+        fma4(acc[r], av.z, b[2]);
+        fma4(acc[r], av.w, b[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) b[u] = bn[u];
+    }
+  }
+  float* rp = red + static_cast<size_t>(ksi) * R * (J + 4) + col;
+#pragma unroll
+  for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(rp + static_cast<size_t>(r) * (J + 4)) = acc[r];
+}
+
+// Combine the ks slices of `red` and hand each (row, 4 columns) to f(r, j, v).  Lanes run along
+// the rows, so transposed (A4) and padded row-major stores from f are bank-conflict free.
+template <int R, typename F>
+__device__ __forceinline__ void tile_epilogue(const float* __restrict__ red, int J, F&& f) {
+  const int ks = split_for(J).ks;
+  const int nj4 = J >> 2;
+  const int JP = J + 4;
+  for (int e = threadIdx.x; e < R * nj4; e += kThreads) {
+    const int r = e % R, j = (e / R) * 4;
+    float4 v = *reinterpret_cast<const float4*>(red + static_cast<size_t>(r) * JP + j);
+    for (int k = 1; k < ks; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(red + (static_cast<size_t>(k) * R + r) * JP + j);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    f(r, j, v);
+  }
+}
+
+// store 4 consecutive i (columns j..j+3 of a row-major activation) of row r into an A4 operand
+template <int R>
+__device__ __forceinline__ void a4_store(float4* A4, int r, int j, const float4& v) { A4[(j >> 2) * R + r] = v; }
+
+// ------------------------------------------------------------------ LayerNorm on one row per warp
+// lane holds columns lane*4 .. lane*4+3 (d <= 128); lanes beyond d hold zeros and `act` = false.
+struct RowStats {
+  float mean, rstd;
+};
+__device__ __forceinline__ RowStats row_stats(const float4& v, bool act, int d, float eps) {
+  float s = act ? (v.x + v.y) + (v.z + v.w) : 0.f;
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.f;
+  if (act) {
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
+    q = (a * a + b * b) + (c * c + e * e);
+  }
+  const float var = warp_sum(q) / static_cast<float>(d);
+  return RowStats{mean, 1.f / sqrtf(var + eps)};
+}
+__device__ __forceinline__ float4 ln_apply(const float4& v, const RowStats& st, const float4& g, const float4& b) {
+  return make_float4((v.x - st.mean) * st.rstd * g.x + b.x, (v.y - st.mean) * st.rstd * g.y + b.y,
+                     (v.z - st.mean) * st.rstd * g.z + b.z, (v.w - st.mean) * st.rstd * g.w + b.w);
+}
+// dx of y = LN(x) given dy (per row): rstd * (gy*g - mean(gy*g) - xhat * mean(gy*g*xhat)); also
+// returns xhat so the caller can accumulate the gamma gradient.
+__device__ __forceinline__ float4 ln_bwd_row(const float4& x, const float4& gy, const float4& g, bool act, int d,
+                                             float eps, float4* xhat_out) {
+  const RowStats st = row_stats(x, act, d, eps);
+  float4 xh = make_float4((x.x - st.mean) * st.rstd, (x.y - st.mean) * st.rstd, (x.z - st.mean) * st.rstd,
+                          (x.w - st.mean) * st.rstd);
+  float4 gg = make_float4(gy.x * g.x, gy.y * g.y, gy.z * g.z, gy.w * g.w);
+  if (!act) {
+    xh = zero4();
+    gg = zero4();
+  }
+  const float m1 = warp_sum((gg.x + gg.y) + (gg.z + gg.w)) / static_cast<float>(d);
+  const float m2 = warp_sum((gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w)) / static_cast<float>(d);
+  *xhat_out = xh;
+  return make_float4(st.rstd * (gg.x - m1 - xh.x * m2), st.rstd * (gg.y - m1 - xh.y * m2),
+                     st.rstd * (gg.z - m1 - xh.z * m2), st.rstd * (gg.w - m1 - xh.w * m2));
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   models/neural.py:7-8
+  const float c = 0.7978845608028654f;
+  return 0.5f * x * (1.f + tanhf(c * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float c = 0.7978845608028654f;
+  const float t = tanhf(c * (x + 0.044715f * x * x * x));
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * c * (1.f + 3.f * 0.044715f * x * x);
+}
+
+// ------------------------------------------------------------------ problem dimensions + saved state
+struct Dims {
+  int S, T, d, H, dh, F, C, o, pre_ln;
+  int R;     // tile rows of the per-copy kernels (16 or 24)
+  int spt;   // sequences per tile = R / C (>= 1)
+  int ntile; // ceil(S / spt)
+  float eps, qscale;
+  uint32_t thr;
+  float keep;
+};
+
+// float offsets inside the `saved` buffer (all sections 16-byte aligned)
+struct Saved {
+  size_t nact, off, tok;            // int32 [S], [S+1 (+pad)], [S*T]
+  size_t xo, xno, qv;               // [S,d]
+  size_t xn, kv, p;                 // compact token rows: [S*T,d], [S*T,2d], [S*T,H]
+  size_t ctx, y, n, z, pre1, h1;    // [S*C,d] x4, [S*C,F] x2
+  size_t total;                     // floats
+};
+__host__ inline size_t align4(size_t x) { return (x + 3) & ~static_cast<size_t>(3); }
+__host__ inline Saved saved_layout(const Dims& D) {
+  Saved L;
+  size_t p = 0;
+  const size_t S = D.S, T = D.T, d = D.d, F = D.F, SC = static_cast<size_t>(D.S) * D.C, H = D.H;
+  L.nact = p; p += align4(S);
+  L.off = p; p += align4(S + 1);
+  L.tok = p; p += align4(S * T);
+  L.xo = p; p += S * d;
+  L.xno = p; p += S * d;
+  L.qv = p; p += S * d;
+  L.xn = p; p += S * T * d;
+  L.kv = p; p += S * T * 2 * d;
+  L.p = p; p += align4(S * T * H);
+  L.ctx = p; p += SC * d;
+  L.y = p; p += SC * d;
+  L.n = p; p += SC * d;
+  L.z = p; p += SC * d;
+  L.pre1 = p; p += SC * F;
+  L.h1 = p; p += SC * F;
+  L.total = p;
+  return L;
+}
+
+// forward workspace: transposed weights (float offsets)
+struct FwdWs {
+  size_t wq_t, wkv_t, wo_t, w1_t, w2_t, bkv, total;
+};
+__host__ inline FwdWs fwd_ws_layout(const Dims& D) {
+  FwdWs W;
+  size_t p = 0;
+  const size_t d = D.d, F = D.F;
+  W.wq_t = p; p += d * d;
+  W.wkv_t = p; p += d * 2 * d;
+  W.wo_t = p; p += d * d;
+  W.w1_t = p; p += d * F;
+  W.w2_t = p; p += F * d;
+  W.bkv = p; p += 2 * d;
+  W.total = p;
+  return W;
+}
+
+struct TokSrc {
+  const float* first;
+  const float* table;
+  int64_t table_rows;
+  const int64_t* idx;
+  int64_t pad_idx;
+  const float* dense;
+  const uint8_t* mask;
+  const float* pe;
+  int raw;  // dense rows are raw layer inputs: never zeroed by the mask
+};
+
+__device__ __forceinline__ bool tok_valid(const TokSrc& ts, int s, int t, int T) {
+  if (ts.first != nullptr) {
+    if (t == 0) return true;
+    const int64_t v = ts.idx[static_cast<int64_t>(s) * (T - 1) + (t - 1)];
+    return v != ts.pad_idx && v >= 0 && v < ts.table_rows;
+  }
+  return ts.mask == nullptr || ts.mask[static_cast<int64_t>(s) * T + t] != 0;
+}
+
+int dims_from_cfg(const psb_encoder_cfg_t* cfg, Dims* D);
+size_t tail_bwd_smem_floats(int R, int d, int F, int H, int T, int spt);
+int launch_rows_gemm(const float* A, int lda, const int32_t* m_dev, int m_host, int m_max, int I, const float* B,
+                     int J, const float* bias, float* out, int ldo, cudaStream_t s);
+
+}  // namespace enc
+}  // namespace psb

@@ -179,6 +179,34 @@ class NSLossFn(Function):
         return grad_a, grad_b, None, None, None, None, None, None, None, None, None
 
 
+class SeqEncoderFn(Function):
+    """Fused last encoder layer + final LayerNorm at one output position (psb_encoder_fwd / _bwd).
+    Token inputs: (first [S,d], table, idx [S,T-1]) -- gradients of the table rows go to ``sink`` --
+    or a dense [S,T,d] tensor."""
+
+    @staticmethod
+    def forward(ctx, first, dense, table, idx, sink, pad_idx, mask, pe, opts, names, *weights):
+        params = dict(zip(names, weights))
+        out, call = ops.encoder_fwd(params, opts["heads"], first=first, table=table, idx=idx, pad_idx=pad_idx,
+                                    dense=dense, mask=mask, pe=pe, copies=opts["copies"], out_pos=opts["out_pos"],
+                                    pre_ln=opts["pre_ln"], eps=opts["eps"], p_drop=opts["p_drop"],
+                                    seed=opts["seed"], raw_input=opts.get("raw_input", False))
+        ctx.call, ctx.sink, ctx.idx, ctx.names = call, sink, idx, names
+        ctx.shapes = {n: tuple(w.shape) for n, w in zip(names, weights)}
+        ctx.pre_ln = opts["pre_ln"]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shapes = ctx.shapes if ctx.pre_ln else {n: s for n, s in ctx.shapes.items() if not n.startswith("ln_attn")}
+        g_first, g_rest, g_dense, grads = ops.encoder_bwd(ctx.call, g, shapes)
+        if ctx.call.tem and ctx.sink is not None and ctx.call.T > 1:
+            ctx.sink.add(ctx.idx.reshape(-1), g_rest.view(-1, g_rest.shape[-1]))
+        ctx.call = None
+        return (g_first, g_dense, None, None, None, None, None, None, None, None) + tuple(
+            grads.get(n) for n in ctx.names)
+
+
 def gather_rows(weight, idx, sink):
     return GatherRowsFn.apply(weight, idx, sink)
 
@@ -192,3 +220,10 @@ def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, 
             neg_weight=None, pos_weight=1.0):
     return NSLossFn.apply(anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
                           pos_weight)
+
+
+def seq_encoder(params, opts, first=None, table=None, idx=None, sink=None, pad_idx=-1, dense=None, mask=None,
+                pe=None):
+    """params: ordered dict name -> Parameter (psb_encoder_params_t member names)."""
+    names = tuple(params.keys())
+    return SeqEncoderFn.apply(first, dense, table, idx, sink, pad_idx, mask, pe, opts, names, *params.values())

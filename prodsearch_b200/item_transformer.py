@@ -104,25 +104,19 @@ class ItemTransformerRanker(nn.Module):
 
     # ---- shared front half -----------------------------------------------------------
     def encode_queries(self, query_word_idxs, u_item_idxs, copies=1, hist=None):
-        """Query encoder + history gather + transformer encode -> [B*copies, d]
-        (item_transformer.py:449-484 / :118-140).  ``hist`` = (weight, sink, remapped idx) when the
-        item table is sharded and the rows live in a fetched mini table."""
-        B, L = u_item_idxs.shape
+        """Query encoder + [query, purchased items] sequence through the transformer, read at ``out_pos``
+        (item_transformer.py:449-484 / :118-140) -> [B*copies, d], copy-minor.  The history rows are
+        gathered inside the fused encoder kernels.  ``hist`` = (weight, sink, remapped idx, pad idx) when
+        the item table is sharded and the rows live in a fetched mini table."""
         q_emb = self.query_encoder.encode_indices(self.word_embeddings.weight, query_word_idxs, self.word_sink,
                                                   pad_idx=self.word_pad_idx)
         if hist is None:
             hist_w = self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight
-            hist = (hist_w, self.hist_sink, u_item_idxs)
-        u_emb = F_.gather_rows(hist[0], hist[2], hist[1])
-        seq = torch.cat([q_emb.unsqueeze(1), u_emb], dim=1)
-        mask = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=seq.device),
-                          u_item_idxs.ne(self.prod_pad_idx)], dim=1)
-        if copies > 1:
-            seq = seq.unsqueeze(1).expand(-1, copies, -1, -1).reshape(B * copies, 1 + L, -1)
-            mask = mask.unsqueeze(1).expand(-1, copies, -1).reshape(B * copies, 1 + L)
+            hist = (hist_w, self.hist_sink, u_item_idxs, self.prod_pad_idx)
         out_pos = -1 if self.args.use_item_pos else 0
-        top = self.transformer_encoder.encode(seq, mask, use_pos=self.args.use_pos_emb)
-        return top[:, out_pos, :]
+        return self.transformer_encoder.encode_position(
+            first=q_emb.contiguous(), table=hist[0], idx=hist[2], sink=hist[1], pad_idx=hist[3],
+            use_pos=self.args.use_pos_emb, out_pos=out_pos, copies=copies)
 
     def _resolve_item_rows(self, target_prod_idxs, neg_item_idxs, u_item_idxs):
         """(item weight, item sink, target idx, negative idx, hist triple or None) of this step.
@@ -153,9 +147,11 @@ class ItemTransformerRanker(nn.Module):
                                                                             u_item_idxs)
         stochastic = self.training and self.args.dropout > 0
         if stochastic:
-            # dropout makes the K negative encodes differ (transformer.py:56, neural.py:226)
-            pos_out = self.encode_queries(query_word_idxs, u_item_idxs, hist=hist)
-            neg_out = self.encode_queries(query_word_idxs, u_item_idxs, copies=K, hist=hist)
+            # dropout makes the positive and the K negative encodes differ (transformer.py:56, neural.py:226):
+            # 1 + K dropout draws of the SAME sequence, K/V projections shared between them
+            out = self.encode_queries(query_word_idxs, u_item_idxs, copies=1 + K, hist=hist).view(B, 1 + K, -1)
+            pos_out = out[:, 0].contiguous()
+            neg_out = out[:, 1:].reshape(B * K, -1)
         else:
             # deterministic encoder: the K copies the reference re-encodes (:473-476) are identical
             pos_out = self.encode_queries(query_word_idxs, u_item_idxs, hist=hist)
@@ -268,7 +264,7 @@ class ShardedItemTransformerRanker(ItemTransformerRanker):
         mini, (tgt, neg, hist), pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs])
         sink = F_.RowGradSink(mini, pad, None, "dense")
         self._mini = mini
-        return mini, sink, tgt, neg, (mini, sink, hist)
+        return mini, sink, tgt, neg, (mini, sink, hist, pad)
 
     def sync_grads(self):
         if self._mini is not None:
@@ -280,8 +276,8 @@ class ShardedItemTransformerRanker(ItemTransformerRanker):
 
     def test_dotproduct(self, batch_data):
         with torch.no_grad():
-            mini, (cand, hist), _ = self.item_table.fetch([batch_data.candi_prod_idxs, batch_data.u_item_idxs])
-            q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs, hist=(mini, None, hist))
+            mini, (cand, hist), pad = self.item_table.fetch([batch_data.candi_prod_idxs, batch_data.u_item_idxs])
+            q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs, hist=(mini, None, hist, pad))
             return ops.score_rows(q.contiguous(), mini, cand, None)
 
     def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):

@@ -187,6 +187,93 @@ def topk_merge(ids, scores):
     return out_i, out_s
 
 
+# ---- fused single-position sequence encoder (psb_encoder_fwd / psb_encoder_bwd) ---------------
+class EncoderCall(object):
+    """Host-side handle of one encoder forward: the cfg / params structs, the saved-state buffer
+    and the tensors that must stay alive until the backward call."""
+    __slots__ = ("cfg", "params", "saved", "keep", "S", "T", "d", "copies", "tem", "names")
+
+
+def encoder_fwd(params, heads, first=None, table=None, idx=None, pad_idx=-1, dense=None, mask=None, pe=None,
+                copies=1, out_pos=0, pre_ln=False, eps=1e-6, p_drop=0.0, seed=None, raw_input=False):
+    """One TransformerEncoderLayer + final LayerNorm evaluated at ONE output position (include/psb.h N1).
+    params: dict name -> fp32 CUDA tensor with the psb_encoder_params_t member names.  Tokens: ``first`` [S,d]
+    + ``table`` / ``idx`` [S,T-1] (TEM), or ``dense`` [S,T,d] (+ ``mask`` [S,T] uint8/bool, 1 = real).
+    ``seed``: int64 CUDA tensor [1] (required when p_drop > 0).  Returns (out [S*copies, d], EncoderCall)."""
+    tem = first is not None
+    if tem:
+        S, d = first.shape
+        idx = _idx(idx)
+        T = 1 + idx.shape[1]
+        dev = first.device
+    else:
+        S, T, d = dense.shape
+        dev = dense.device
+        if mask is not None and mask.dtype != u8:
+            mask = mask.to(u8)
+        if mask is not None:
+            mask = mask.contiguous()
+    if out_pos < 0:
+        out_pos += T
+    ff = params["w1"].shape[0]
+    if pe is not None:
+        pe = pe.reshape(-1, d)[:T].contiguous()
+    P = _lib.EncoderParams()
+    keep = [first, table, idx, dense, mask, pe, seed]
+    for n in _lib._ENC_NAMES:
+        t = params.get(n)
+        if t is not None:
+            t = t.detach()
+            keep.append(t)
+        setattr(P, n, ptr(t, f32))
+    cfg = _lib.EncoderCfg(S, T, d, int(heads), ff, int(copies), int(out_pos), 1 if pre_ln else 0, 1 if raw_input else 0, float(eps),
+                          float(p_drop), ptr(seed, i64), ptr(first, f32), ptr(table, f32),
+                          table.shape[0] if table is not None else 0, ptr(idx), int(pad_idx), ptr(dense, f32),
+                          ptr(mask), ptr(pe, f32))
+    lib = load()
+    sb = int(lib.psb_encoder_saved_bytes(ctypes.byref(cfg)))
+    if sb < 0:
+        check(sb, "psb_encoder_saved_bytes")
+    wb = int(lib.psb_encoder_workspace_bytes(ctypes.byref(cfg), 0))
+    saved = torch.empty((sb,), dtype=u8, device=dev)
+    ws = torch.empty((wb,), dtype=u8, device=dev)
+    out = torch.empty((S * copies, d), dtype=f32, device=dev)
+    check(lib.psb_encoder_fwd(ctypes.byref(cfg), ctypes.byref(P), ptr(saved), sb, ptr(ws), wb, ptr(out),
+                              stream_ptr()), "psb_encoder_fwd")
+    call = EncoderCall()
+    call.cfg, call.params, call.saved, call.keep = cfg, P, saved, keep
+    call.S, call.T, call.d, call.copies, call.tem = S, T, d, copies, tem
+    call.names = [n for n in _lib._ENC_NAMES if params.get(n) is not None]
+    return out, call
+
+
+def encoder_bwd(call, grad_out, shapes):
+    """Backward of encoder_fwd.  ``shapes``: dict name -> shape of every parameter to differentiate.
+    Returns (grad_first, grad_rest, grad_dense, grads dict)."""
+    S, T, d = call.S, call.T, call.d
+    dev = grad_out.device
+    g_first = g_rest = g_dense = None
+    if call.tem:
+        g_first = torch.empty((S, d), dtype=f32, device=dev)
+        g_rest = torch.empty((S, T - 1, d), dtype=f32, device=dev)
+    else:
+        g_dense = torch.empty((S, T, d), dtype=f32, device=dev)
+    G = _lib.EncoderParams()
+    grads = {}
+    for n in _lib._ENC_NAMES:
+        t = None
+        if n in shapes:
+            t = grads[n] = torch.empty(shapes[n], dtype=f32, device=dev)
+        setattr(G, n, ptr(t, f32))
+    lib = load()
+    wb = int(lib.psb_encoder_workspace_bytes(ctypes.byref(call.cfg), 1))
+    ws = torch.empty((wb,), dtype=u8, device=dev)
+    check(lib.psb_encoder_bwd(ctypes.byref(call.cfg), ctypes.byref(call.params), ptr(call.saved),
+                              call.saved.numel(), ptr(ws), wb, ptr(grad_out.contiguous(), f32), ptr(g_first),
+                              ptr(g_rest), ptr(g_dense), ctypes.byref(G), stream_ptr()), "psb_encoder_bwd")
+    return g_first, g_rest, g_dense, grads
+
+
 # ---- optional per-op device timing (bench.py roofline leg) ----------------------------------
 PROFILE = None   # dict name -> list of (start_event, end_event) when enabled
 
@@ -206,5 +293,5 @@ def _profiled(name, fn):
 
 
 for _n in ("table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
-           "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge"):
+           "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge", "encoder_fwd", "encoder_bwd"):
     globals()[_n] = _profiled(_n, globals()[_n])

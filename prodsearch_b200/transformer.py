@@ -8,6 +8,7 @@ C5/C6: "stays torch"); it is row N1 of the "next" list.  This implementation run
 arithmetic through cuBLAS/ATen on the device and is the piece a fused sm_100a encoder replaces.
 """
 import math
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
@@ -124,8 +125,74 @@ class TransformerEncoder(nn.Module):
         return self.layer_norm(x)
 
     def forward(self, input_vecs, mask, use_pos=True, out_pos=0):
-        x = self.encode(input_vecs, mask, use_pos)
-        return self.wo(x[:, out_pos, :]).squeeze(-1)
+        x = self.encode_position(dense=input_vecs, mask=mask, use_pos=use_pos, out_pos=out_pos)
+        return self.wo(x).squeeze(-1)
+
+    # ---- the hot path: only top_vecs[:, out_pos, :] is ever read (item_transformer.py:479,:487,
+    #      ps_model.py:336-339), so the last layer runs for that one position in fused sm_100a kernels
+    def _last_layer_params(self):
+        L = self.transformer_inter[-1]
+        a, f = L.self_attn, L.feed_forward
+        return OrderedDict([
+            ("wq", a.linear_query.weight), ("bq", a.linear_query.bias), ("wk", a.linear_keys.weight),
+            ("bk", a.linear_keys.bias), ("wv", a.linear_values.weight), ("bv", a.linear_values.bias),
+            ("wo", a.final_linear.weight), ("bo", a.final_linear.bias), ("ln_attn_g", L.layer_norm.weight),
+            ("ln_attn_b", L.layer_norm.bias), ("ln_ff_g", f.layer_norm.weight), ("ln_ff_b", f.layer_norm.bias),
+            ("w1", f.w_1.weight), ("b1", f.w_1.bias), ("w2", f.w_2.weight), ("b2", f.w_2.bias),
+            ("ln_out_g", self.layer_norm.weight), ("ln_out_b", self.layer_norm.bias)])
+
+    def encode_position(self, first=None, table=None, idx=None, sink=None, pad_idx=-1, dense=None, mask=None,
+                        use_pos=True, out_pos=0, copies=1):
+        """encode(...)[:, out_pos, :] for ``copies`` independent dropout draws of every sequence ->
+        [S*copies, d] (copy-minor).  Tokens: ``first`` [S,d] + rows ``table[idx]`` (idx [S,T-1], invalid =
+        ``pad_idx``) or ``dense`` [S,T,d] with ``mask`` [S,T].  Layers before the last (inter_layers > 1)
+        need every position and stay on cuBLAS/ATen with the reference's arithmetic; the last layer + the
+        final LayerNorm are the fused kernels."""
+        from . import functional as F_
+        nl = self.num_inter_layers
+        p_drop = self.transformer_inter[0].dropout.p if (nl > 0 and self.training) else 0.0
+        if nl == 0:
+            raise NotImplementedError("inter_layers == 0 (LayerNorm only) is not built")
+        if nl > 1:
+            if dense is None:
+                rows = F_.gather_rows(table, idx, sink)
+                dense = torch.cat([first.unsqueeze(1), rows], dim=1)
+                mask = torch.cat([torch.ones_like(idx[:, :1], dtype=torch.bool), idx.ne(pad_idx)], dim=1)
+                first = table = idx = sink = None
+            valid = mask.bool() if mask is not None else torch.ones(dense.shape[:2], dtype=torch.bool,
+                                                                    device=dense.device)
+            if copies > 1:
+                dense = dense.repeat_interleave(copies, dim=0)
+                valid = valid.repeat_interleave(copies, dim=0)
+                copies = 1
+            x = dense * valid.unsqueeze(-1).to(dense.dtype)
+            if use_pos:
+                x = x + self.pos_emb.pe[:, :dense.size(1)]
+            for i in range(nl - 1):
+                x = self.transformer_inter[i](i, x, ~valid)
+            # raw layer input: masked rows keep their activations, the mask only removes keys
+            T = x.shape[1]
+            seed = self._next_seed(x.device) if p_drop > 0 else None
+            opts = dict(heads=self.transformer_inter[-1].self_attn.head_count, copies=1, out_pos=out_pos % T,
+                        pre_ln=True, eps=1e-6, p_drop=p_drop, seed=seed, raw_input=True)
+            return F_.seq_encoder(self._last_layer_params(), opts, dense=x.contiguous(), mask=valid, pe=None)
+        T = (1 + idx.shape[1]) if first is not None else dense.shape[1]
+        dev = first.device if first is not None else dense.device
+        seed = self._next_seed(dev) if p_drop > 0 else None
+        opts = dict(heads=self.transformer_inter[-1].self_attn.head_count, copies=copies, out_pos=out_pos % T,
+                    pre_ln=False, eps=1e-6, p_drop=p_drop, seed=seed, raw_input=False)
+        pe = self.pos_emb.pe[0, :T] if use_pos else None
+        if dense is not None:
+            dense = dense.contiguous()
+        return F_.seq_encoder(self._last_layer_params(), opts, first=first, table=table, idx=idx, sink=sink,
+                              pad_idx=pad_idx, dense=dense, mask=mask, pe=pe)
+
+    def _next_seed(self, device):
+        s = getattr(self, "_drop_seed", None)
+        if s is None or s.device != torch.empty(0, device=device).device:
+            s = self._drop_seed = torch.zeros(1, dtype=torch.int64, device=device)
+        s.random_()          # device generator: a fresh key every call, CUDA-graph safe
+        return s
 
     def initialize_parameters(self, logger=None):
         """xavier-normal matrices, zero biases, N(0,1) for LayerNorm gains -- the rule at

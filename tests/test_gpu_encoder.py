@@ -1,0 +1,177 @@
+"""GPU parity of the fused single-position encoder (psb_encoder_fwd / _bwd) against
+the CPU oracle's FULL encoder (oracle.encoder_encode, itself pinned by the reference's golden outputs):
+the fused kernels compute only top_vecs[:, out_pos, :], which must equal the full computation there.
+fp32 tolerances: outputs 1e-5 relative, gradients 1e-4 relative with an absolute floor scaled by the
+magnitude of the summed terms.  Dropout runs use the Philox multipliers the kernels draw (oracle/philox.py)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle.philox import encoder_dropout_muls
+
+pytestmark = pytest.mark.gpu
+
+PSB2REF = {"wq": "self_attn.linear_query.weight", "bq": "self_attn.linear_query.bias",
+           "wk": "self_attn.linear_keys.weight", "bk": "self_attn.linear_keys.bias",
+           "wv": "self_attn.linear_values.weight", "bv": "self_attn.linear_values.bias",
+           "wo": "self_attn.final_linear.weight", "bo": "self_attn.final_linear.bias",
+           "ln_attn_g": "layer_norm.weight", "ln_attn_b": "layer_norm.bias",
+           "ln_ff_g": "feed_forward.layer_norm.weight", "ln_ff_b": "feed_forward.layer_norm.bias",
+           "w1": "feed_forward.w_1.weight", "b1": "feed_forward.w_1.bias",
+           "w2": "feed_forward.w_2.weight", "b2": "feed_forward.w_2.bias"}
+
+
+def make_params(d, ff, seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = dict(wq=(d, d), bq=(d,), wk=(d, d), bk=(d,), wv=(d, d), bv=(d,), wo=(d, d), bo=(d,),
+                  ln_attn_g=(d,), ln_attn_b=(d,), ln_ff_g=(d,), ln_ff_b=(d,), w1=(ff, d), b1=(ff,),
+                  w2=(d, ff), b2=(d,), ln_out_g=(d,), ln_out_b=(d,))
+    P = {}
+    for k, s in shapes.items():
+        if len(s) == 2:
+            P[k] = torch.randn(s, generator=g) * (2.0 / (s[0] + s[1])) ** 0.5
+        elif k.endswith("_g"):
+            P[k] = 1.0 + 0.3 * torch.randn(s, generator=g)
+        else:
+            P[k] = 0.1 * torch.randn(s, generator=g)
+    return P
+
+
+def ref_params(P, layer=0):
+    R = {}
+    pre = "transformer_encoder.transformer_inter.%d." % layer
+    for k, name in PSB2REF.items():
+        R[pre + name] = P[k]
+    R["transformer_encoder.layer_norm.weight"] = P["ln_out_g"]
+    R["transformer_encoder.layer_norm.bias"] = P["ln_out_b"]
+    return R
+
+
+def close(a, b, rtol, atol, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    assert bool((err <= bound).all()), "%s: max err %g (ref scale %g)" % (what, float(err.max()), float(b.abs().max()))
+
+
+def run_oracle(P, x, valid, heads, out_pos, copies, pre_ln, raw, pe, muls):
+    """Full reference computation on CPU for S*copies replicated sequences; returns out + grads via autograd."""
+    S, T, d = x.shape
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xin = x.clone().requires_grad_(True)
+    R = ref_params(leaves, layer=1 if pre_ln else 0)
+    cfg = argparse.Namespace(inter_layers=1, heads=heads, dropout=0.0)
+    xr = xin.repeat_interleave(copies, 0)
+    vr = valid.repeat_interleave(copies, 0)
+    h = xr if raw else xr * vr.unsqueeze(-1).float()
+    if pe is not None:
+        h = h + pe[:T]
+    tm = {k: torch.from_numpy(v) for k, v in muls.items()} if muls is not None else None
+    pre = "transformer_encoder.transformer_inter.%d." % (1 if pre_ln else 0)
+    h = oracle.encoder_layer(R, pre, 1 if pre_ln else 0, h, ~vr, heads, 0.0, False, tm)
+    top = F.layer_norm(h, (d,), leaves["ln_out_g"], leaves["ln_out_b"], 1e-6)[:, out_pos]
+    return top, leaves, xin
+
+
+def run_case(S, T, d, ff, heads, copies, out_pos, p_drop=0.0, tem=True, pre_ln=False, raw=False, seed=0,
+             full_mask_row=False):
+    from prodsearch_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    P = make_params(d, ff, seed + 1)
+    rows = 500
+    table = torch.randn(rows + 1, d, generator=g)
+    table[rows] = 0
+    hist_len = torch.randint(0, T, (S,), generator=g)
+    idx = torch.randint(0, rows, (S, T - 1), generator=g)
+    idx[torch.arange(T - 1)[None, :] >= hist_len[:, None]] = rows
+    first = torch.randn(S, d, generator=g)
+    valid = torch.cat([torch.ones(S, 1, dtype=torch.bool), idx.ne(rows)], 1)
+    x = torch.cat([first.unsqueeze(1), table[idx]], 1)
+    if not tem:
+        valid = torch.rand(S, T, generator=g) > 0.4
+        valid[:, 0] |= torch.rand(S, generator=g) > 0.3          # sometimes the output position is masked
+        if full_mask_row:
+            valid[1] = False
+        x = torch.randn(S, T, d, generator=g)
+    pe = oracle.sinusoid_table(64, d)[0] if not raw else None
+    seed_val = 0x1234ABCD5678 + seed
+    muls = encoder_dropout_muls(seed_val, p_drop, S, copies, T, heads, d, ff, out_pos % T) if p_drop > 0 else None
+    ref, leaves, xin = run_oracle(P, x, valid, heads, out_pos, copies, pre_ln, raw, pe, muls)
+    gout = torch.randn(S * copies, d, generator=g)
+    (ref * gout).sum().backward()
+
+    dev = {k: v.cuda() for k, v in P.items()}
+    seed_t = torch.tensor([seed_val], dtype=torch.int64, device="cuda") if p_drop > 0 else None
+    kw = dict(copies=copies, out_pos=out_pos, pre_ln=pre_ln, p_drop=p_drop, seed=seed_t, raw_input=raw,
+              pe=pe.cuda() if pe is not None else None)
+    if tem:
+        out, call = ops.encoder_fwd(dev, heads, first=first.cuda(), table=table.cuda(), idx=idx.cuda(), pad_idx=rows, **kw)
+    else:
+        out, call = ops.encoder_fwd(dev, heads, dense=x.cuda(), mask=valid.cuda(), **kw)
+    close(out, ref, 1e-5, 2e-6, "out")
+    shapes = {k: tuple(v.shape) for k, v in P.items() if pre_ln or not k.startswith("ln_attn")}
+    g_first, g_rest, g_dense, grads = ops.encoder_bwd(call, gout.cuda(), shapes)
+    gx = xin.grad
+    scale = float(gout.abs().sum() / d)
+    if tem:
+        close(g_first, gx[:, 0], 1e-4, 1e-6 * scale ** 0.5, "g_first")
+        close(g_rest, gx[:, 1:] * valid[:, 1:, None].float(), 1e-4, 1e-6 * scale ** 0.5, "g_rest")
+    else:
+        close(g_dense, gx, 1e-4, 1e-6 * scale ** 0.5, "g_dense")
+    for k in shapes:
+        ref_g = leaves[k].grad
+        atol = 2e-6 * max(1.0, float(ref_g.abs().max()))
+        if k == "bk":      # exactly 0 in exact arithmetic (softmax is shift-invariant): both sides are rounding noise
+            atol = 1e-5 * max(1.0, scale / S)
+        close(grads[k], ref_g, 1e-4, atol, "grad " + k)
+    # determinism: a second run is bit-identical
+    if tem:
+        out2, call2 = ops.encoder_fwd(dev, heads, first=first.cuda(), table=table.cuda(), idx=idx.cuda(), pad_idx=rows, **kw)
+    else:
+        out2, call2 = ops.encoder_fwd(dev, heads, dense=x.cuda(), mask=valid.cuda(), **kw)
+    assert torch.equal(out, out2)
+    _, _, _, grads2 = ops.encoder_bwd(call2, gout.cuda(), shapes)
+    for k in shapes:
+        assert torch.equal(grads[k], grads2[k]), k
+
+
+@pytest.mark.parametrize("S,T,d,ff,heads,copies", [
+    (37, 21, 128, 512, 8, 1), (37, 21, 128, 512, 8, 6), (19, 21, 128, 32, 8, 3), (50, 9, 64, 64, 8, 1),
+    (23, 12, 32, 48, 4, 5), (384, 21, 128, 512, 8, 6), (5, 1, 128, 512, 8, 2), (40, 51, 128, 512, 8, 1)])
+def test_encoder_tem_layout_vs_full_oracle(S, T, d, ff, heads, copies):
+    run_case(S, T, d, ff, heads, copies, out_pos=0)
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+@pytest.mark.parametrize("S,T,d,ff,heads,copies", [(37, 21, 128, 512, 8, 6), (23, 12, 32, 48, 4, 3)])
+def test_encoder_dropout_philox_vs_oracle(S, T, d, ff, heads, copies, p):
+    run_case(S, T, d, ff, heads, copies, out_pos=0, p_drop=p, seed=3)
+
+
+@pytest.mark.parametrize("out_pos", [0, -1, 3])
+def test_encoder_dense_masked_and_out_pos(out_pos):
+    run_case(29, 13, 128, 256, 8, 2, out_pos=out_pos, tem=False, seed=5, full_mask_row=True)
+    run_case(29, 13, 64, 64, 4, 1, out_pos=out_pos, tem=False, p_drop=0.2, seed=6)
+
+
+def test_encoder_pre_ln_raw_input():
+    """Layer index > 0: pre-attention LayerNorm, rows are a previous layer's output (not re-masked)."""
+    run_case(31, 10, 128, 512, 8, 1, out_pos=0, tem=False, pre_ln=True, raw=True, seed=7)
+    run_case(31, 10, 32, 48, 4, 2, out_pos=-1, tem=False, pre_ln=True, raw=True, p_drop=0.1, seed=8)
+    run_case(17, 6, 64, 64, 8, 1, out_pos=0, tem=True, pre_ln=True, seed=9)
+
+
+def test_encoder_argument_errors():
+    from prodsearch_b200 import ops
+    P = {k: v.cuda() for k, v in make_params(128, 512, 0).items()}
+    x = torch.randn(4, 5, 128, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.encoder_fwd(P, 7, dense=x)                       # d % heads != 0
+    with pytest.raises(RuntimeError):
+        ops.encoder_fwd(P, 8, dense=x, p_drop=0.1)           # dropout without a seed tensor
+    with pytest.raises(RuntimeError):
+        ops.encoder_fwd(P, 8, dense=x.cpu())                 # no CPU fallback

@@ -17,7 +17,8 @@ def close(a, b, rtol=1e-5, atol=2e-6):
     a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
     err = (a - b).abs()
     bound = atol + rtol * b.abs()
-    assert bool((err <= bound).all()), "max err %g at bound %g" % (float(err.max()), float(bound[err.argmax()] if err.numel() else 0))
+    assert bool((err <= bound).all()), "max err %g at bound %g" % (
+        float(err.max()), float(bound.flatten()[err.argmax()] if err.numel() else 0))
 
 
 def cuda_batch(ns):
@@ -84,7 +85,8 @@ def test_tem_golden(name, grad_mode):
             close(dense, ref, rtol=1e-4)
             assert p.grad is None
     model.eval()
-    close(model.test(batch), G.outputs["test_scores"])
+    # scores are d-term dot products of O(1) values: 1e-5 relative to the operand scale |q||e| ~ d
+    close(model.test(batch), G.outputs["test_scores"], rtol=1e-5, atol=3e-5)
     # full-catalog ranking == canonical (lower-id-first) ranking of the oracle's score matrix
     k = min(10, Pn)
     ids, sc = model.rank_catalog(batch, k=k)
