@@ -283,6 +283,32 @@ int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_params_t* pa
                     const float* grad_out, float* grad_first, float* grad_rest, float* grad_dense,
                     const psb_encoder_grads_t* grads, psb_stream_t stream);
 
+/* ------------------------------------------------------------------ N2 ---
+ * Fused global-norm clip + Adam over all parameter tensors of the model: replaces
+ * clip_grad_norm_(params, max_grad_norm) + torch.optim.Adam(eps=1e-9).step() as driven by
+ * models/optimizers.py:205-243 (noam schedule :214-219 when noam != 0).  Dense semantics, identical
+ * to the reference: every element of every tensor is updated every step.
+ *   total = sqrt(sum_t |g_t|^2); c = min(1, max_grad_norm / (total + 1e-6))   (max_grad_norm <= 0: c = 1)
+ *   g' = c g (+ weight_decay p); m += (1-b1)(g' - m); v = b2 v + (1-b2) g'^2
+ *   p -= lr_t / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),  t = ++(*step_dev)
+ * No host sync: t, total^2 (sqnorm_dev, readable afterwards) live in device memory, so the call
+ * replays inside a CUDA graph.  Gradients are NOT rescaled in place. */
+typedef struct psb_adam_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} psb_adam_tensor_t;
+
+#define PSB_ADAM_MAX_TENSORS 64
+
+int64_t psb_adam_workspace_bytes(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors);
+int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float max_grad_norm, int32_t noam,
+                  float warmup_steps, int64_t* step_dev, float* sqnorm_dev, void* workspace,
+                  int64_t workspace_bytes, psb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,13 @@ class EncoderCfg(ctypes.Structure):
                 ("pad_idx", c_i64), ("dense", c_vp), ("mask", c_vp), ("pe", c_vp)]
 
 
+class AdamTensor(ctypes.Structure):
+    """psb_adam_tensor_t."""
+    _fields_ = [("p", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("n", c_i64)]
+
+
+ADAM_MAX_TENSORS = 64
+
 # name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
 SIGNATURES = {
     "psb_abi_version": (c_i32, []),
@@ -64,6 +71,9 @@ SIGNATURES = {
                                  c_i64, c_vp, c_vp, c_vp]),
     "psb_table_max_row_sqnorm": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "psb_adam_workspace_bytes": (c_i64, [ctypes.POINTER(AdamTensor), c_i32]),
+    "psb_adam_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32,
+                              c_f32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
     "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,

@@ -27,6 +27,8 @@ class RowGradSink(object):
         self._dense = None
         self._dense_bias = None
         self._prev = None             # (unique_rows, n_unique) written into the dense buffers last time
+        self._uniq_buf = None         # persistent: a CUDA-graph replay reads last replay's rows from here
+        self._nu_buf = None
 
     # -- called from Function.backward ------------------------------------------------
     def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
@@ -54,9 +56,14 @@ class RowGradSink(object):
                 self._prepare_dense(want_bias, clear=first)
                 if not first:
                     raise RuntimeError("more than %d contributions to one table in a step" % ops._lib.MAX_CONTRIBS)
+                n_total = sum(int(c.n) for c, _ in chunk)
+                if self._uniq_buf is None or self._uniq_buf.numel() < n_total:
+                    self._uniq_buf = torch.empty(max(n_total, 1), dtype=torch.int32, device=w.device)
+                    self._nu_buf = torch.zeros(1, dtype=torch.int32, device=w.device)
                 uniq, _, _, nu = ops.scatter_reduce(chunk, rows, d, self.drop_idx, dense_grad=self._dense,
                                                     dense_bias_grad=self._dense_bias if want_bias else None,
-                                                    want_rows=False, device=w.device)
+                                                    want_rows=False, device=w.device, out_uniq=self._uniq_buf,
+                                                    out_nu=self._nu_buf)
                 self._prev = (uniq, nu)
                 self._attach(w, self._dense)
                 if want_bias:

@@ -1,0 +1,120 @@
+"""One training step -- forward, backward, gradient sinks, clipped Adam -- captured in a CUDA graph.
+
+At batch 384 a TEM step moves a few MB and runs ~50 short kernels: launching them one by one from Python
+costs more than executing them.  ``GraphedTrainStep`` runs the reference's step sequence
+(trainer.py:74-78: ``loss = model(batch); zero_grad; loss.backward(); optim.step()``) once under stream
+capture and replays it with new batch contents copied into static input buffers.  Everything the step
+needs is device-resident and replay-safe: negatives come from the device generator (``torch.multinomial``,
+Philox offsets advance per replay), dropout keys from a device seed, the Adam step counter / clip norm
+live in device memory, the gradient sinks keep their touched-row lists in persistent buffers.
+"""
+import argparse
+
+import torch
+
+
+class GraphedTrainStep(object):
+    def __init__(self, model, optim, sample_batch, pad_values=None, warmup=3, sync_grads=None):
+        """sample_batch: a batch whose tensor fields have the LARGEST shapes that will be fed (narrower
+        batches are right-padded with ``pad_values[field]``, e.g. the word / item pad ids).
+        sync_grads: optional callable run between backward and the optimizer (data-parallel reduce)."""
+        self.model, self.optim = model, optim
+        self.pad_values = dict(pad_values or {})
+        self.static = argparse.Namespace()
+        dev = next(model.parameters()).device
+        for k, v in vars(sample_batch).items():
+            setattr(self.static, k, v.to(dev).clone() if torch.is_tensor(v) else v)
+        self.sync_grads = sync_grads
+        from . import _lib
+        snap = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):        # allocates optimizer state, dense gradient buffers, smem attributes
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap)                # the warm-up steps must not count as training
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step_body()
+        self.launches_per_replay = _lib.launch_count() - n0   # hand-written kernels captured in the graph
+        torch.cuda.synchronize()
+
+    def _snapshot(self):
+        opt = getattr(self.optim, "optimizer", None)
+        snap = dict(params=[p.detach().clone() for p in self.model.parameters()], host_step=getattr(self.optim, "_step", 0),
+                    opt_state=None, opt_step=None, acc=None)
+        if opt is not None and hasattr(opt, "_step_dev"):
+            snap["opt_state"] = {p: (st["exp_avg"].clone(), st["exp_avg_sq"].clone()) for p, st in opt.state.items()}
+            snap["opt_step"] = None if opt._step_dev is None else opt._step_dev.clone()
+        elif opt is not None:
+            import copy
+            snap["opt_state"] = copy.deepcopy(opt.state_dict())
+        if getattr(self.model, "_ps_acc", None) is not None:
+            snap["acc"] = (self.model._ps_acc.clone(), self.model._item_acc.clone())
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for p, v in zip(self.model.parameters(), snap["params"]):
+                p.copy_(v)
+            opt = getattr(self.optim, "optimizer", None)
+            if opt is not None and hasattr(opt, "_step_dev"):
+                for p, st in opt.state.items():
+                    old = snap["opt_state"].get(p)
+                    if old is None:
+                        st["exp_avg"].zero_()
+                        st["exp_avg_sq"].zero_()
+                    else:
+                        st["exp_avg"].copy_(old[0])
+                        st["exp_avg_sq"].copy_(old[1])
+                if opt._step_dev is not None:
+                    if snap["opt_step"] is None:
+                        opt._step_dev.zero_()
+                    else:
+                        opt._step_dev.copy_(snap["opt_step"])
+            elif opt is not None:
+                opt.load_state_dict(snap["opt_state"])
+            if hasattr(self.optim, "_step"):
+                self.optim._step = snap["host_step"]
+            if getattr(self.model, "_ps_acc", None) is not None:
+                if snap["acc"] is None:
+                    self.model._ps_acc.zero_()
+                    self.model._item_acc.zero_()
+                else:
+                    self.model._ps_acc.copy_(snap["acc"][0])
+                    self.model._item_acc.copy_(snap["acc"][1])
+
+    def _step_body(self):
+        loss = self.model(self.static)
+        self.model.zero_grad()
+        loss.backward()
+        if self.sync_grads is not None:
+            self.sync_grads()
+        self.optim.step()
+        return loss.detach()
+
+    def load(self, batch, non_blocking=True):
+        """Copy a (host or device) batch into the static input buffers, right-padding narrower tensors."""
+        for k, v in vars(batch).items():
+            if not torch.is_tensor(v):
+                continue
+            dst = getattr(self.static, k)
+            if v.shape == dst.shape:
+                dst.copy_(v, non_blocking=non_blocking)
+                continue
+            if v.dim() != dst.dim() or v.shape[0] != dst.shape[0] or any(a > b for a, b in zip(v.shape, dst.shape)):
+                raise ValueError("batch field %s has shape %s, graph was captured for %s" % (k, tuple(v.shape), tuple(dst.shape)))
+            if k not in self.pad_values:
+                raise ValueError("no pad value for the narrower batch field " + k)
+            dst.fill_(self.pad_values[k])
+            dst[tuple(slice(0, n) for n in v.shape)].copy_(v, non_blocking=non_blocking)
+
+    def __call__(self, batch=None):
+        """Run one step; returns the (static, device) loss tensor of that step."""
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.loss

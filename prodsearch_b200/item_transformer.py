@@ -88,8 +88,9 @@ class ItemTransformerRanker(nn.Module):
         return 0 if self._item_acc is None else float(self._item_acc)
 
     def clear_loss(self):
-        self._ps_acc = None
-        self._item_acc = None
+        if self._ps_acc is not None:
+            self._ps_acc.zero_()
+            self._item_acc.zero_()
 
     def load_cp(self, pt, strict=True):
         self.load_state_dict(pt["model"], strict=strict)
@@ -162,9 +163,12 @@ class ItemTransformerRanker(nn.Module):
                         anchor_b=neg_out.contiguous(), bias=bias, pos_weight=pos_weight)
         ps_loss = ps.mean()
         item_loss = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink)
-        with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here)
-            self._ps_acc = ps_loss.detach() if self._ps_acc is None else self._ps_acc + ps_loss.detach()
-            self._item_acc = item_loss.detach() if self._item_acc is None else self._item_acc + item_loss.detach()
+        with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here); in place,
+            if self._ps_acc is None:   # so a CUDA-graph replay keeps accumulating into the same buffers
+                self._ps_acc = torch.zeros((), device=ps_loss.device)
+                self._item_acc = torch.zeros((), device=ps_loss.device)
+            self._ps_acc.add_(ps_loss.detach())
+            self._item_acc.add_(item_loss.detach())
         return ps_loss + item_loss
 
     def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None, item_w=None,

@@ -121,7 +121,7 @@ def make_contrib(idx, src, src_row=None, src_div=1, scale=None, scale2=None, sca
 
 
 def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_bias_grad=None,
-                   want_rows=True, want_bias=False, device=None):
+                   want_rows=True, want_bias=False, device=None, out_uniq=None, out_nu=None):
     """Deterministic sort + segmented-reduce embedding backward (psb_scatter_reduce_rows).
     contribs: list of (Contrib, keepalive).  Returns (unique_rows [n_total] int32, reduced or None,
     reduced_bias or None, n_unique device int32 [1])."""
@@ -132,10 +132,11 @@ def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_
     ws_bytes = int(load().psb_scatter_reduce_workspace_bytes(n_total, table_rows))
     ws = torch.empty((ws_bytes,), dtype=u8, device=device)
     cap = max(n_total, 1)
-    uniq = torch.empty((cap,), dtype=i32, device=device)
+    # out_uniq / out_nu: caller-owned persistent buffers (a CUDA-graph replay must find last step's rows there)
+    uniq = out_uniq if out_uniq is not None and out_uniq.numel() >= cap else torch.empty((cap,), dtype=i32, device=device)
     red = torch.empty((cap, d), dtype=f32, device=device) if want_rows else None
     redb = torch.empty((cap,), dtype=f32, device=device) if want_bias else None
-    nu = torch.zeros((1,), dtype=i32, device=device)
+    nu = out_nu.zero_() if out_nu is not None else torch.zeros((1,), dtype=i32, device=device)
     if n_total > 0:
         check(load().psb_scatter_reduce_rows(arr, len(contribs), table_rows, d, int(drop_idx), ptr(ws), ws_bytes,
                                              ptr(uniq), ptr(red), ptr(redb), ptr(nu), ptr(dense_grad, f32),
