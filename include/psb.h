@@ -45,6 +45,14 @@ const char* psb_status_string(int status);
  * bench.py report gpu_launches without a profiler). */
 int64_t psb_launch_count(void);
 
+/* Per-kernel timing without an external profiler.  While enabled, every kernel this library launches
+ * outside CUDA-graph capture is bracketed by two CUDA events on its own stream.  psb_profile_dump
+ * synchronises the device, writes one text line per kernel name -- "name launches total_ms min_ms max_ms" --
+ * into buf (host, NUL-terminated; returns the byte count, < 0 on error) and clears the record.
+ * Host-side state: not thread-safe, meant for bench.py's roofline leg and tests. */
+int psb_profile_enable(int32_t on);
+int64_t psb_profile_dump(char* buf /* host */, int64_t cap);
+
 /* ------------------------------------------------------------------ G1 ---
  * out[i,:] = table[idx[i],:]                                   (bit-exact copy)
  * Replaces aten::embedding at models/item_transformer.py:449,:464-469,:262-263,
@@ -292,7 +300,8 @@ int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_params_t* pa
  *   g' = c g (+ weight_decay p); m += (1-b1)(g' - m); v = b2 v + (1-b2) g'^2
  *   p -= lr_t / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),  t = ++(*step_dev)
  * No host sync: t, total^2 (sqnorm_dev, readable afterwards) live in device memory, so the call
- * replays inside a CUDA graph.  Gradients are NOT rescaled in place. */
+ * replays inside a CUDA graph.  Gradients are NOT rescaled in place.  Hyper-parameters are doubles, as the
+ * reference passes them: 1 - beta and the bias corrections are formed in double and then rounded, like torch. */
 typedef struct psb_adam_tensor {
   float* p;
   const float* g;
@@ -304,9 +313,9 @@ typedef struct psb_adam_tensor {
 #define PSB_ADAM_MAX_TENSORS 64
 
 int64_t psb_adam_workspace_bytes(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors);
-int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, float max_grad_norm, int32_t noam,
-                  float warmup_steps, int64_t* step_dev, float* sqnorm_dev, void* workspace,
+int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, double max_grad_norm, int32_t noam,
+                  double warmup_steps, int64_t* step_dev, float* sqnorm_dev, void* workspace,
                   int64_t workspace_bytes, psb_stream_t stream);
 
 #ifdef __cplusplus

@@ -13,6 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libpsb_b200.so")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
+c_f64 = ctypes.c_double
 
 MAX_CONTRIBS = 8
 TOPK_EXACT, TOPK_TC = 0, 1
@@ -54,6 +55,8 @@ SIGNATURES = {
     "psb_abi_version": (c_i32, []),
     "psb_status_string": (ctypes.c_char_p, [c_i32]),
     "psb_launch_count": (c_i64, []),
+    "psb_profile_enable": (c_i32, [c_i32]),
+    "psb_profile_dump": (c_i64, [ctypes.c_char_p, c_i64]),
     "psb_gather_rows": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "psb_gather_meanpool_fwd": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -72,8 +75,8 @@ SIGNATURES = {
     "psb_table_max_row_sqnorm": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "psb_adam_workspace_bytes": (c_i64, [ctypes.POINTER(AdamTensor), c_i32]),
-    "psb_adam_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32,
-                              c_f32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "psb_adam_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i32,
+                              c_f64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
     "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,
@@ -133,3 +136,21 @@ def ptr(t, dtype=None, allow_none=True):
 
 def launch_count():
     return int(load().psb_launch_count())
+
+
+def profile_enable(on=True):
+    """Bracket every kernel the library launches (outside graph capture) with CUDA events."""
+    check(load().psb_profile_enable(1 if on else 0), "psb_profile_enable")
+
+
+def profile_dump():
+    """{kernel name: (launches, total_ms, min_ms, max_ms)} since profile_enable / the last dump (synchronises)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = load().psb_profile_dump(buf, len(buf))
+    if n < 0:
+        raise RuntimeError("psb_profile_dump failed: %d" % n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, tot, mn, mx = line.split()
+        out[name] = (int(cnt), float(tot), float(mn), float(mx))
+    return out

@@ -627,6 +627,7 @@ static bool tc_supported(int64_t m, int64_t n_items, int64_t d) {
 
 int table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out, cudaStream_t s) {
   cudaMemsetAsync(out, 0, 4, s);
+  PSB_PROF("max_row_norm_kernel", s);
   max_row_norm_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(table), rows,
                                                   static_cast<int>(d / 4), out);
   return launch_status();
@@ -692,10 +693,12 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
   {
     int slices = pl.n_slices < pl.pilot_tiles ? pl.n_slices : pl.pilot_tiles;
     dim3 grid(slices, pl.m_tiles);
+    PSB_PROF("tc_score_kernel", s);
     tc_score_kernel<true><<<grid, kTcThreads, smem, s>>>(map_q, map_e, P);
     if ((st = launch_status()) != PSB_OK) return st;
   }
   // 2. thresholds
+  PSB_PROF("pilot_threshold_kernel", s);
   pilot_threshold_kernel<<<static_cast<int>(m), 256, 0, s>>>(dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries,
                                                              static_cast<int>(d), max_row_sqnorm, thr, eps);
   if ((st = launch_status()) != PSB_OK) return st;
@@ -704,16 +707,19 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
   P.n_tiles = pl.total_tiles;
   {
     dim3 grid(pl.n_slices, pl.m_tiles);
+    PSB_PROF("tc_score_kernel", s);
     tc_score_kernel<false><<<grid, kTcThreads, smem, s>>>(map_q, map_e, P);
     if ((st = launch_status()) != PSB_OK) return st;
   }
   // 4. final select + exact rescoring
   const size_t fsmem = static_cast<size_t>(kFinalCap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
+  PSB_PROF("final_select_kernel", s);
   final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
                                                               table, static_cast<int>(d), bias, static_cast<int>(k),
                                                               id_base, id_stride, out_ids, out_scores, flag);
   if ((st = launch_status()) != PSB_OK) return st;
   // 5. exact fallback for flagged rows (returns immediately for unflagged ones)
+  PSB_PROF("fallback_rows_kernel", s);
   fallback_rows_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(d) * 4, s>>>(
       flag, queries, table, n_items, static_cast<int>(d), bias, static_cast<int>(k), id_base, id_stride, out_ids,
       out_scores);

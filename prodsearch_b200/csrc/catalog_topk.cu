@@ -241,17 +241,21 @@ int catalog_topk_exact(const float* queries, int64_t m, const float* table, int6
   float* best_s = reinterpret_cast<float*>(ws + ((m * ld * 4 + 255) / 256) * 256);
   int32_t* best_i = reinterpret_cast<int32_t*>(best_s + m * kKMax);
   int st;
+  PSB_PROF("init_best_kernel", s);
   init_best_kernel<<<static_cast<int>((m * kKMax + 255) / 256), 256, 0, s>>>(best_s, best_i, m * kKMax);
   if ((st = launch_status()) != PSB_OK) return st;
   for (int64_t c0 = 0; c0 < n_items; c0 += ch) {
     const int cn = static_cast<int>(n_items - c0 < ch ? n_items - c0 : ch);
     dim3 grid((cn + kTI - 1) / kTI, static_cast<unsigned>((m + kTQ - 1) / kTQ));
+    PSB_PROF("exact_scores_kernel", s);
     exact_scores_kernel<<<grid, 256, 0, s>>>(queries, static_cast<int>(m), table, c0, cn, static_cast<int>(d),
                                              bias, S, ld);
     if ((st = launch_status()) != PSB_OK) return st;
+    PSB_PROF("row_select_kernel", s);
     row_select_kernel<<<static_cast<int>(m), 256, 0, s>>>(S, ld, c0, cn, static_cast<int>(k), best_s, best_i);
     if ((st = launch_status()) != PSB_OK) return st;
   }
+  PSB_PROF("write_topk_kernel", s);
   write_topk_kernel<<<static_cast<int>((m * k + 255) / 256), 256, 0, s>>>(
       best_s, best_i, static_cast<int>(m), static_cast<int>(k), id_base, id_stride, out_ids, out_scores);
   return launch_status();
@@ -305,10 +309,12 @@ extern "C" int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g
     return PSB_E_ARG;
   if (g * k > 4096) return PSB_E_DIM;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("fill_empty_kernel", s);
   fill_empty_kernel<<<static_cast<int>((m * k + 255) / 256), 256, 0, s>>>(out_ids, out_scores, m * k);
   int st = launch_status();
   if (st != PSB_OK) return st;
   const size_t smem = static_cast<size_t>((g * k + 1) / 2 * 2) * 4 + static_cast<size_t>(g * k) * 8;
+  PSB_PROF("topk_merge_kernel", s);
   topk_merge_kernel<<<static_cast<int>(m), 256, smem, s>>>(ids, scores, static_cast<int>(g), static_cast<int>(m),
                                                            static_cast<int>(k), out_ids, out_scores);
   return launch_status();

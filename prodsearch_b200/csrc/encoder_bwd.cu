@@ -290,6 +290,7 @@ static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
+  PSB_PROF("tail_bwd_kernel", s);
   tail_bwd_kernel<R><<<D.ntile, kThreads, smem, s>>>(a);
   return launch_status();
 }
@@ -598,6 +599,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   eb.ln_g = p->ln_attn_g;
   eb.g_first = grad_first; eb.g_rest = grad_rest; eb.g_dense = grad_dense;
   eb.lnp = ws + W.lnp_e;
+  PSB_PROF("embed_bwd_kernel", s);
   embed_bwd_kernel<<<D.S, 128, 0, s>>>(eb);
   if ((st = launch_status()) != PSB_OK) return st;
 
@@ -620,6 +622,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(3, ws + W.gkv, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWk, dbk
   add(4, ws + W.gkv + d, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWv, dbv
   add(5, ws + W.g_qlin, d, sv + L.xno, d, nullptr, D.S, D.S, d, d);        // dWq, dbq
+  PSB_PROF("wgrad_kernel", s);
   wgrad_kernel<<<total_tiles, 256, 0, s>>>(probs);
   if ((st = launch_status()) != PSB_OK) return st;
 
@@ -647,6 +650,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     red(ws + W.lnp_e + d, gr->ln_attn_b, d, 2 * d, nullptr, D.S, 1);
   }
   if (total_blocks > 0) {
+    PSB_PROF("reduce_kernel", s);
     reduce_kernel<<<total_blocks, 256, 0, s>>>(jobs);
     if ((st = launch_status()) != PSB_OK) return st;
   }

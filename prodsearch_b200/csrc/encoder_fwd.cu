@@ -267,6 +267,7 @@ int launch_rows_gemm(const float* A, int lda, const int32_t* m_dev, int m_host, 
   }
   const int grid = (m_max + R - 1) / R;
   if (grid <= 0) return PSB_OK;
+  PSB_PROF("rows_gemm_kernel", s);
   rows_gemm_kernel<R><<<grid, kThreads, smem, s>>>(A, lda, m_dev, m_host, I, B, J, bias, out, ldo);
   return launch_status();
 }
@@ -498,6 +499,7 @@ static int launch_tail_fwd(const TailFwdArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
+  PSB_PROF("tail_fwd_kernel", s);
   tail_fwd_kernel<R><<<D.ntile, kThreads, smem, s>>>(a);
   return launch_status();
 }
@@ -543,6 +545,7 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   const TokSrc ts{cfg->first, cfg->table, cfg->table_rows, cfg->idx, cfg->pad_idx, cfg->dense, cfg->mask, cfg->pe, cfg->raw_input != 0 && cfg->first == nullptr};
   const int d = D.d, F = D.F;
 
+  PSB_PROF("plan_kernel", s);
   plan_kernel<<<1, 1024, 0, s>>>(ts, D.S, D.T, nact, off, tok);
   if ((st = launch_status()) != PSB_OK) return st;
 
@@ -559,9 +562,11 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(p->w2, ws + W.w2_t, d, F, d, 0);           // W2 [d][F] -> [F][d]
   add(p->bk, ws + W.bkv, d, 1, 2 * d, 0);        // bias concat as 1-column "transposes"
   add(p->bv, ws + W.bkv, d, 1, 2 * d, d);
+  PSB_PROF("transpose_kernel", s);
   transpose_kernel<<<tr_blocks(jobs), 256, 0, s>>>(jobs);
   if ((st = launch_status()) != PSB_OK) return st;
 
+  PSB_PROF("embed_kernel", s);
   embed_kernel<<<D.S, 128, 0, s>>>(ts, D, p->ln_attn_g, p->ln_attn_b, nact, off, tok, sv + L.xn, sv + L.xo,
                                    sv + L.xno);
   if ((st = launch_status()) != PSB_OK) return st;
@@ -572,6 +577,7 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   st = launch_rows_gemm(sv + L.xno, d, nullptr, D.S, D.S, d, ws + W.wq_t, d, p->bq, sv + L.qv, d, s);
   if (st != PSB_OK) return st;
 
+  PSB_PROF("attn_fwd_kernel", s);
   attn_fwd_kernel<<<D.S, 128, static_cast<size_t>(D.H) * D.T * sizeof(float), s>>>(D, nact, off, tok, ts, sv + L.qv,
                                                                                    sv + L.kv, sv + L.p);
   if ((st = launch_status()) != PSB_OK) return st;

@@ -9,7 +9,6 @@
 
 namespace psb {
 
-int64_t g_launches = 0;
 
 // ---------------------------------------------------------------- G1 -----
 template <int R>
@@ -277,7 +276,6 @@ using namespace psb;
 
 extern "C" int psb_abi_version(void) { return PSB_ABI_VERSION; }
 
-extern "C" int64_t psb_launch_count(void) { return psb::g_launches; }
 
 extern "C" const char* psb_status_string(int status) {
   switch (status) {
@@ -301,6 +299,7 @@ extern "C" int psb_gather_rows(const float* table, int64_t table_rows, int64_t d
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   constexpr int R = 8;
   const int grid = grid_for(n, 8 * R);
+  PSB_PROF("gather_rows_kernel", s);
   gather_rows_kernel<R><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(table), table_rows,
                                              static_cast<int>(d / 4), idx, n,
                                              reinterpret_cast<float4*>(out), err_flag);
@@ -317,6 +316,7 @@ static int launch_meanpool(const float* table, int64_t table_rows, int64_t d, co
   const float4* k4 = reinterpret_cast<const float4*>(keep_scale);
   const float4* w4 = reinterpret_cast<const float4*>(fs_weight);
   float4* m4 = reinterpret_cast<float4*>(mean_out);
+  PSB_PROF("meanpool_kernel", s);
   if (fs_weight != nullptr)
     meanpool_kernel<C, true><<<grid, 256, 0, s>>>(t4, table_rows, static_cast<int>(d / 4), idx, n,
                                                   static_cast<int>(w), pad_idx, mask, tok_scale, k4, w4,
@@ -357,6 +357,7 @@ extern "C" int psb_meanpool_token_weights(const int64_t* idx, int64_t n, int64_t
                                           const uint8_t* mask, float* tok_weight, psb_stream_t stream) {
   if (n < 0 || w <= 0 || tok_weight == nullptr || (idx == nullptr && mask == nullptr)) return PSB_E_ARG;
   if (n == 0) return PSB_OK;
+  PSB_PROF("token_weights_kernel", static_cast<cudaStream_t>(stream));
   token_weights_kernel<<<grid_for(n, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       idx, n, static_cast<int>(w), pad_idx, mask, tok_weight);
   return launch_status();
@@ -373,6 +374,7 @@ extern "C" int psb_fs_bwd(const float* grad_out, const float* out, const float* 
       misaligned16(grad_mean))
     return PSB_E_ALIGN;
   const int rows_blocks = grid_for(n, 8, 4);
+  PSB_PROF("fs_bwd_kernel", static_cast<cudaStream_t>(stream));
   fs_bwd_kernel<<<rows_blocks + static_cast<int>(d), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       grad_out, out, reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(keep_scale),
       reinterpret_cast<const float4*>(fs_weight), n, static_cast<int>(d / 4), rows_blocks,

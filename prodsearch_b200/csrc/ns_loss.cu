@@ -324,6 +324,7 @@ extern "C" int psb_score_rows(const float* anchor, const float* table, int64_t t
   score_rows_kernel<C><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(anchor),                         \
                                             reinterpret_cast<const float4*>(table), table_rows, d4, bias, idx, n, \
                                             static_cast<int>(c_per), scores)
+  PSB_PROF("score_rows_kernel", s);
   if (d4 <= 32) PSB_SC_LAUNCH(1);
   else if (d4 <= 64) PSB_SC_LAUNCH(2);
   else PSB_SC_LAUNCH(4);
@@ -359,6 +360,7 @@ extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, con
       reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b))
   if (d4 <= 32 && k <= 7) {
     const int gridf = grid_for(n, 8, 32);
+    PSB_PROF("ns_loss_fast_kernel", s);
     if (anchor_b != nullptr)
       ns_loss_fast_kernel<true><<<gridf, 256, 0, s>>>(
           reinterpret_cast<const float4*>(anchor_a), reinterpret_cast<const float4*>(anchor_b),
@@ -372,9 +374,9 @@ extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, con
           pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,
           reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b));
   }
-  else if (d4 <= 32) PSB_NS_LAUNCH(1);
-  else if (d4 <= 64) PSB_NS_LAUNCH(2);
-  else PSB_NS_LAUNCH(4);
+  else if (d4 <= 32) { PSB_PROF("ns_loss_kernel", s); PSB_NS_LAUNCH(1); }
+  else if (d4 <= 64) { PSB_PROF("ns_loss_kernel", s); PSB_NS_LAUNCH(2); }
+  else { PSB_PROF("ns_loss_kernel", s); PSB_NS_LAUNCH(4); }
 #undef PSB_NS_LAUNCH
   return launch_status();
 }

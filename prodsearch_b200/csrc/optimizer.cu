@@ -80,18 +80,23 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restri
   }
 }
 
-struct AdamHyper {
-  float lr, beta1, beta2, eps, max_norm, weight_decay;
+struct AdamHyper {  // the reference's hyper-parameters are Python doubles: 1 - beta is formed in double, then rounded
+  double lr, beta1, beta2;
+  float b1, b2, omb1, omb2, eps, max_norm, weight_decay;
   int noam;
   float warmup;
 };
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float clip, float wd, float b1,
-                                         float b2, float step_size, float inv_bc2_sqrt, float eps) {
-  g *= clip;
+struct AdamCoef {
+  float clip, wd, omb1, b2, omb2, step_size, inv_bc2_sqrt, eps;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamCoef& c) {
+  const float wd = c.wd, step_size = c.step_size, inv_bc2_sqrt = c.inv_bc2_sqrt, eps = c.eps;
+  g *= c.clip;
   if (wd != 0.f) g = fmaf(wd, p, g);
-  m = fmaf(1.f - b1, g - m, m);               // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf((1.f - b2) * g, g, v * b2);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  m = fmaf(c.omb1, g - m, m);                 // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(c.omb2, g * g, v * c.b2);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
   p = fmaf(-step_size, m / denom, p);         // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
@@ -108,12 +113,22 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, const Ad
     const float total = sqrtf(*sqnorm);
     clip = fminf(h.max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
   }
-  float lr = h.lr;
-  if (h.noam) lr = h.lr * fminf(rsqrtf(step), step * powf(h.warmup, -1.5f));  // optimizers.py:214-219
-  const double bc1 = 1.0 - pow(static_cast<double>(h.beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(h.beta2), static_cast<double>(step));
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
-  const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  double lr = h.lr;
+  if (h.noam) {  // optimizers.py:214-219
+    const double sd = static_cast<double>(step);
+    lr = h.lr * fmin(1.0 / sqrt(sd), sd * pow(static_cast<double>(h.warmup), -1.5));
+  }
+  const double bc1 = 1.0 - pow(h.beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(h.beta2, static_cast<double>(step));
+  AdamCoef c;
+  c.clip = clip;
+  c.wd = h.weight_decay;
+  c.omb1 = h.omb1;
+  c.b2 = h.b2;
+  c.omb2 = h.omb2;
+  c.step_size = static_cast<float>(lr / bc1);
+  c.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  c.eps = h.eps;
   const psb_adam_tensor_t t = T.t[ti];
   const int64_t end = min(t.n, start + kAdamChunk);
   const bool al = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
@@ -125,21 +140,21 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, const Ad
         const float4 g = *reinterpret_cast<const float4*>(t.g + i);
         float4 m = *reinterpret_cast<float4*>(t.m + i);
         float4 v = *reinterpret_cast<float4*>(t.v + i);
-        adam_one(p.x, g.x, m.x, v.x, clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
-        adam_one(p.y, g.y, m.y, v.y, clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
-        adam_one(p.z, g.z, m.z, v.z, clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
-        adam_one(p.w, g.w, m.w, v.w, clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
+        adam_one(p.x, g.x, m.x, v.x, c);
+        adam_one(p.y, g.y, m.y, v.y, c);
+        adam_one(p.z, g.z, m.z, v.z, c);
+        adam_one(p.w, g.w, m.w, v.w, c);
         *reinterpret_cast<float4*>(t.p + i) = p;
         *reinterpret_cast<float4*>(t.m + i) = m;
         *reinterpret_cast<float4*>(t.v + i) = v;
       } else {
         for (int64_t j = i; j < end; ++j)
-          adam_one(t.p[j], t.g[j], t.m[j], t.v[j], clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
+          adam_one(t.p[j], t.g[j], t.m[j], t.v[j], c);
       }
     }
   } else {
     for (int64_t i = start + threadIdx.x; i < end; i += 256)
-      adam_one(t.p[i], t.g[i], t.m[i], t.v[i], clip, h.weight_decay, h.beta1, h.beta2, step_size, inv_bc2_sqrt, h.eps);
+      adam_one(t.p[i], t.g[i], t.m[i], t.v[i], c);
   }
 }
 
@@ -158,8 +173,8 @@ extern "C" int64_t psb_adam_workspace_bytes(const psb_adam_tensor_t* tensors, in
   return (adam_chunks(tensors, n_tensors) + 4) * static_cast<int64_t>(sizeof(float));
 }
 
-extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors, float lr, float beta1, float beta2,
-                             float eps, float weight_decay, float max_grad_norm, int32_t noam, float warmup_steps,
+extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors, double lr, double beta1, double beta2,
+                             double eps, double weight_decay, double max_grad_norm, int32_t noam, double warmup_steps,
                              int64_t* step_dev, float* sqnorm_dev, void* workspace, int64_t workspace_bytes,
                              psb_stream_t stream) {
   if (tensors == nullptr || n_tensors <= 0 || n_tensors > PSB_ADAM_MAX_TENSORS || step_dev == nullptr ||
@@ -179,11 +194,26 @@ extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   int st;
+  PSB_PROF("sqnorm_partial_kernel", s);
   sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
   if ((st = launch_status()) != PSB_OK) return st;
+  PSB_PROF("sqnorm_final_kernel", s);
   sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks), sqnorm_dev, step_dev);
   if ((st = launch_status()) != PSB_OK) return st;
-  AdamHyper h{lr, beta1, beta2, eps, max_grad_norm, weight_decay, noam, warmup_steps};
+  AdamHyper h;
+  h.lr = lr;
+  h.beta1 = beta1;
+  h.beta2 = beta2;
+  h.b1 = static_cast<float>(beta1);
+  h.b2 = static_cast<float>(beta2);
+  h.omb1 = static_cast<float>(1.0 - beta1);
+  h.omb2 = static_cast<float>(1.0 - beta2);
+  h.eps = static_cast<float>(eps);
+  h.max_norm = static_cast<float>(max_grad_norm);
+  h.weight_decay = static_cast<float>(weight_decay);
+  h.noam = noam;
+  h.warmup = static_cast<float>(warmup_steps);
+  PSB_PROF("adam_kernel", s);
   adam_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, h, sqnorm_dev, step_dev);
   return launch_status();
 }

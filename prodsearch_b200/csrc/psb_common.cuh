@@ -22,9 +22,21 @@ inline int check_table_args(const void* table, int64_t rows, int64_t d) {
 
 inline bool misaligned16(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 
+// Per-kernel timing (runtime.cu): when psb_profile_enable(1) is in effect, PSB_PROF records a CUDA event on the
+// launching stream right before a kernel and launch_status() records one right after it; psb_profile_dump sums
+// the elapsed times per kernel name.  Disabled (the default): one predictable branch per launch.
+extern bool g_prof_on;
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end();
+#define PSB_PROF(name, stream) \
+  do {                         \
+    if (::psb::g_prof_on) ::psb::prof_begin(name, stream); \
+  } while (0)
+
 inline int launch_status() {
   ++g_launches;
   cudaError_t e = cudaGetLastError();
+  if (g_prof_on) prof_end();
   return e == cudaSuccess ? PSB_OK : static_cast<int>(e);
 }
 

@@ -647,6 +647,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
       if (e != cudaSuccess) return static_cast<int>(e);
       attr_set = true;
     }
+    PSB_PROF("small_sort_segments_kernel", s);
     small_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
                                                          passes, vals_a, keys_a, seg_start, unique_rows, n_unique);
     if ((st = launch_status()) != PSB_OK) return st;
@@ -654,24 +655,31 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     sorted_keys = keys_a;
   } else {
     const int nblocks = static_cast<int>((n_total + kTile - 1) / kTile);
+    PSB_PROF("pack_keys_kernel", s);
     pack_keys_kernel<<<grid_for(n_total, 256 * 4), 256, 0, s>>>(T, n_total, table_rows, drop_idx, keys_a, vals_a);
     if ((st = launch_status()) != PSB_OK) return st;
     uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
     for (int pass = 0; pass < passes; ++pass) {
+      PSB_PROF("radix_hist_kernel", s);
       radix_hist_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, pass * 8, nblocks, hist);
       if ((st = launch_status()) != PSB_OK) return st;
+      PSB_PROF("radix_scan_kernel", s);
       radix_scan_kernel<<<256, 256, 0, s>>>(hist, nblocks, totals);
       if ((st = launch_status()) != PSB_OK) return st;
+      PSB_PROF("radix_scatter_kernel", s);
       radix_scatter_kernel<<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
       if ((st = launch_status()) != PSB_OK) return st;
       uint32_t* t = ki; ki = ko; ko = t;
       t = vi; vi = vo; vo = t;
     }
     const uint32_t sentinel = static_cast<uint32_t>(table_rows);
+    PSB_PROF("heads_count_kernel", s);
     heads_count_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts);
     if ((st = launch_status()) != PSB_OK) return st;
+    PSB_PROF("heads_scan_kernel", s);
     heads_scan_kernel<<<1, 256, 0, s>>>(counts, nblocks, n_unique);
     if ((st = launch_status()) != PSB_OK) return st;
+    PSB_PROF("heads_write_kernel", s);
     heads_write_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts, n_unique, seg_start, unique_rows);
     if ((st = launch_status()) != PSB_OK) return st;
     sorted_slots = vi;
@@ -686,11 +694,13 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     float4* partial = reinterpret_cast<float4*>(ws + L.partial);
     float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);
 #define PSB_SR_LAUNCH(C)                                                                                      \
+  PSB_PROF("seg_reduce_kernel", s);                                                                            \
   seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, sorted_keys, seg_start, n_unique, d4, ch_shift,   \
                                             reinterpret_cast<float4*>(reduced), reduced_bias,                 \
                                             reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial,  \
                                             partial_bias);                                                    \
   if ((st = launch_status()) != PSB_OK) return st;                                                            \
+  PSB_PROF("seg_fixup_kernel", s);                                                                            \
   seg_fixup_kernel<C><<<grid_fix, 256, 0, s>>>(seg_start, unique_rows, n_unique, d4, ch_shift,                \
                                                reinterpret_cast<float4*>(reduced), reduced_bias,              \
                                                reinterpret_cast<float4*>(dense_grad), dense_bias_grad,        \
@@ -710,6 +720,7 @@ extern "C" int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t
   if (d <= 0 || (d & 3) != 0 || d > 512) return PSB_E_DIM;
   if (misaligned16(dense)) return PSB_E_ALIGN;
   if (max_rows == 0) return PSB_OK;
+  PSB_PROF("zero_rows_kernel", static_cast<cudaStream_t>(stream));
   zero_rows_kernel<<<grid_for(max_rows, 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       rows, n_rows, static_cast<int>(d / 4), reinterpret_cast<float4*>(dense), dense_bias);
   return launch_status();
