@@ -260,12 +260,24 @@ def run_b200_arm(a):
     args = model_args(a.dropout)
     P, V, B = WORKLOAD["product_size"], WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
     torch.manual_seed(666)
-    if world > 1:   # item table row-sharded over the ranks, lookups exchanged by all-to-all
-        model = ShardedItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+    transport = "local"
+    if world > 1:
+        # item + word tables row-sharded over the ranks.  Preferred transport: NVLink peer memory (P2P loads inside
+        # the kernels, whole step = one CUDA graph per rank); if CUDA IPC is unavailable, NCCL all-to-all (eager).
+        from prodsearch_b200 import peer
+        pg = None if a.transport == "nccl" else peer.try_create()
+        if pg is not None:
+            from prodsearch_b200.item_transformer import PeerShardedItemTransformerRanker
+            model = PeerShardedItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V), peer=pg)
+            transport = "nvlink-peer"
+        else:
+            model = ShardedItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+            transport = "nccl-all-to-all"
     else:
         model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
     optim = build_optim(args, model)
     model.train()
+    torch.manual_seed(666 + 7919 * rank)      # per-rank negatives / dropout masks from here on
     n_total = a.warmup + a.steps
     host, devb = [], []
     for it in range(n_total):
@@ -280,20 +292,25 @@ def run_b200_arm(a):
         loss = model(batch)
         model.zero_grad()
         loss.backward()
-        if world > 1:
+        if transport == "nvlink-peer":
+            model.sync_grads(optim)
+        elif world > 1:
             model.sync_grads()
         optim.step()
         return loss
 
     graphed = None
-    if world == 1 and not a.eager:
+    if transport in ("local", "nvlink-peer") and not a.eager:
         # the whole step (fwd + bwd + gradient sinks + clipped Adam) replays as ONE CUDA graph; batches are
         # copied into its static input buffers (query matrix right-padded to the widest batch)
         from prodsearch_b200.graph_step import GraphedTrainStep
         wq = max(b.query_word_idxs.shape[1] for b in host)
         sample = argparse.Namespace(**vars(host[0]))
         sample.query_word_idxs = torch.full((B, wq), V - 1, dtype=torch.int64)
-        graphed = GraphedTrainStep(model, optim, sample, pad_values={"query_word_idxs": V - 1, "u_item_idxs": P})
+        wq = max(wq, 12)      # synthetic queries have at most 12 words: the same static shape on every rank
+        sample.query_word_idxs = torch.full((B, wq), V - 1, dtype=torch.int64)
+        graphed = GraphedTrainStep(model, optim, sample, pad_values={"query_word_idxs": V - 1, "u_item_idxs": P},
+                                   sync_grads=(lambda: model.sync_grads(optim)) if transport == "nvlink-peer" else None)
 
     def step(batch):
         return graphed(batch) if graphed is not None else eager_step(batch)
@@ -340,61 +357,96 @@ def run_b200_arm(a):
         t = torch.tensor([dev_sec, e2e_sec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_sec, e2e_sec = float(t[0]), float(t[1])
-    # ---- per-op timing of the hand-written kernels inside the same step (separate pass, all ranks
-    #      take part because the sharded step contains collectives)
-    ops.PROFILE = {}
-    for it in range(min(a.steps, 10)):
+    # ---- per-KERNEL timing inside the same step: a separate eager pass with the library's own profiler
+    #      (CUDA events on the launching stream around every hand-written kernel, L2 flushed between steps);
+    #      all ranks take part because the sharded step contains cross-GPU barriers
+    n_prof = min(a.steps, 10)
+    for it in range(2):
+        eager_step(devb[a.warmup + it])
+    barrier()
+    _lib.profile_enable(True)
+    for it in range(n_prof):
         flush.zero_()
         eager_step(devb[a.warmup + it])
     barrier()
-    prof = {k: (sum(s.elapsed_time(e) for s, e in v) / len(v), len(v) // min(a.steps, 10)) for k, v in ops.PROFILE.items()}
-    ops.PROFILE = None
+    kprof = _lib.profile_dump()
+    _lib.profile_enable(False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     d = WORKLOAD["embedding_size"]
-    K, L, W = WORKLOAD["neg_per_pos"], WORKLOAD["uprev_review_limit"], 1
-    alg = {  # algorithmic bytes per launch at this config
-        "ns_loss": B * (1 + K) * (d * 4 + 8) + B * d * 4 * 2 + B * K * d * 4 * 2,
-        "gather_rows": B * L * (d * 4 * 2 + 8),
-        "gather_meanpool": B * 12 * (d * 4 + 8) + B * d * 4 * 2 + d * d * 4,
-        "scatter_reduce": B * (L + 2 + K) * (d * 4 + 8),
-        "fs_bwd": B * d * 4 * 4 + d * d * 4 * 2,
-        "token_weights": B * 12 * 12,
-    }
-    # the optimizer sweeps every parameter: p, g, m, v read + p, m, v written
-    n_param = sum(p.numel() for p in model.parameters() if p.grad is not None)
-    alg["adam_step"] = n_param * 28
-    hbm_ops = {k: v for k, v in prof.items() if k in alg}
-    dom = max(hbm_ops.items(), key=lambda kv: kv[1][0] * kv[1][1]) if hbm_ops else None
-    roofline = None
-    if dom is not None:
-        name, (ms, per_step) = dom
-        ach = alg.get(name, 0) / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "psb_" + name, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                    "launch_ms": ms, "launches_per_step": per_step,
-                    "regime": "dominant HBM-bound op of the step, %d KB algorithmic per launch at batch 384, timed "
-                              "eagerly with a cold L2 (see extra.bandwidth_regime for every gather/scatter kernel "
-                              "in the HBM-roofline regime)" % (alg.get(name, 0) // 1024),
-                    "all_ops_ms": {k: round(v[0] * v[1], 4) for k, v in prof.items()}}
-    # the fused encoder is fp32-FFMA-bound, not HBM-bound: report it against the CUDA-core fp32 peak
+    K, L, W, F = WORKLOAD["neg_per_pos"], WORKLOAD["uprev_review_limit"], 1, WORKLOAD["ff_size"]
     hb = devb[a.warmup]
+    Wq = int(hb.query_word_idxs.shape[1])
     ntok = int(B + (hb.u_item_idxs != P).sum().item())
-    C, F = 1 + K, WORKLOAD["ff_size"]
-    fwd_flop = 2.0 * (ntok * d * 2 * d + B * d * d + B * C * (d * d + 2 * d * F))
+    C = 1 + K
+    n_item_slots = B * (L + 2 + K)            # history + target (loss) + negatives + target (item->word anchor)
+    n_word_slots = B * (Wq + W + W * K)
+    n_param = sum(p.numel() for p in model.parameters() if p.grad is not None)
+    row = d * 4 + 8
+    tail_flop = 2.0 * B * C * (d * d + 2 * d * F)
+    # ALGORITHMIC work per STEP of every hand-written kernel: ("hbm", bytes) | ("tensor", flop)
+    alg = {
+        "meanpool_kernel": ("hbm", B * Wq * row + B * d * 4 * 2 + d * d * 4),
+        "fs_bwd_kernel": ("hbm", B * d * 4 * 4 + d * d * 4 * 2),
+        "token_weights_kernel": ("hbm", B * Wq * 12),
+        "gather_rows_kernel": ("hbm", B * (d * 4 * 2 + 8)),
+        "ns_loss_fast_kernel": ("hbm", B * (1 + K) * row + B * d * 4 * 2 + B * K * d * 4 * 2      # score + loss tail
+                                + B * W * (1 + K) * row + B * d * 4 * 2),                         # item -> words
+        "small_sort_segments_kernel": ("hbm", (n_item_slots + n_word_slots) * 8),
+        "seg_reduce_kernel": ("hbm", (n_item_slots + n_word_slots) * row),
+        "seg_fixup_kernel": ("hbm", 0),
+        "sqnorm_partial_kernel": ("hbm", n_param * 4),
+        "adam_kernel": ("hbm", n_param * 28),
+        "embed_kernel": ("hbm", ntok * d * 4 * 3),
+        "embed_bwd_kernel": ("hbm", ntok * d * 4 * 3),
+        "peer_gather_rows_kernel": ("hbm", (n_item_slots - B + n_word_slots) * (d * 4 * 2 + 8)),
+        "peer_fold_rows_kernel": ("hbm", (n_item_slots + n_word_slots) * (d * 4 * 3 + 4)),
+        "peer_allreduce_kernel": ("hbm", 0),
+        "rows_gemm_kernel": ("tensor", 2.0 * (ntok * d * 2 * d + B * d * d) * 2),    # K|V and q projections + their dgrads
+        "attn_fwd_kernel": ("tensor", 2.0 * 2 * ntok * d),
+        "tail_fwd_kernel": ("tensor", tail_flop),
+        "tail_bwd_kernel": ("tensor", tail_flop),                                    # dgrad half; dW is wgrad_kernel
+        "wgrad_kernel": ("tensor", tail_flop + 2.0 * (ntok * d * 2 * d + B * d * d)),
+    }
     sm_mhz = (clocks.summary().get("sm_mhz") or 1965.0)
     ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    compute = {}
-    for name, mult in (("encoder_fwd", 1.0), ("encoder_bwd", 2.0)):
-        if name in prof:
-            ms = prof[name][0]
-            compute[name] = {"bound": "fp32_ffma", "ms": ms, "gflop": fwd_flop * mult / 1e9,
-                             "achieved": fwd_flop * mult / (ms * 1e-3) / 1e12, "peak": ffma_peak, "unit": "TFLOP/s",
-                             "frac": fwd_flop * mult / (ms * 1e-3) / 1e12 / ffma_peak,
-                             "note": "all launches of the op (plan, transposes, projections, tail, wgrad); peak = "
-                                     "148 SMs x 128 FFMA/clk x 2 at the sampled SM clock"}
+    tf32_peak = peaks["bf16"] / 2.0
+    kernels = {}
+    for name, (cnt, tot_ms, mn, mx) in kprof.items():
+        per_step_ms = tot_ms / n_prof
+        ent = {"launches_per_step": cnt / n_prof, "ms_per_step": round(per_step_ms, 5),
+               "avg_launch_us": round(tot_ms / cnt * 1e3, 3)}
+        if name in alg and alg[name][1] > 0:
+            bound, amount = alg[name]
+            if bound == "hbm":
+                ach = amount / (per_step_ms * 1e-3) / 1e9
+                ent.update(bound="hbm", algorithmic_bytes_per_step=int(amount), achieved=round(ach, 2), unit="GB/s",
+                           peak=peaks["hbm"], frac=round(ach / peaks["hbm"], 5))
+            else:
+                ach = amount / (per_step_ms * 1e-3) / 1e12
+                ent.update(bound="tensor", algorithmic_flop_per_step=amount, achieved=round(ach, 3), unit="TFLOP/s",
+                           peak=tf32_peak, frac=round(ach / tf32_peak, 5), frac_of_fp32_ffma_peak=round(ach / ffma_peak, 4))
+        kernels[name] = ent
+    roofline = None
+    if kernels:
+        name, ent = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])
+        roofline = {"kernel": name, "bound": ent.get("bound", "hbm"), "achieved": ent.get("achieved"),
+                    "peak": ent.get("peak"), "unit": ent.get("unit"), "frac": ent.get("frac"), "traffic": None,
+                    "peak_source": peaks["src"] + (" bf16 cuBLAS burst / 2 (TF32 rate)" if ent.get("bound") == "tensor" else " copy bandwidth"),
+                    "launch_us": ent["avg_launch_us"], "launches_per_step": ent["launches_per_step"],
+                    "regime": "dominant hand-written kernel of the batch-384 step (%.0f%% of the %.3f ms of kernel time "
+                              "per step), timed per launch with CUDA events in an eager pass with a cold L2.  The step moves "
+                              "~25 MB and ~3 GFLOP: every kernel is latency-bound at this size; extra.bandwidth_regime has "
+                              "the same gather / loss / scatter kernels on a 16M-row table where the roofline binds."
+                              % (100.0 * ent["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
+                                 sum(k["ms_per_step"] for k in kernels.values()))}
+        if ent.get("bound") == "tensor":
+            roofline["note"] = ("GEMM-shaped (B*(1+K) rows x 128 -> 512 -> 128) but computed in fp32 FFMA on CUDA cores to "
+                                "hold the 1e-5 parity bar; %.1f%% of the fp32 FFMA peak (%.1f TFLOP/s at the sampled clock)"
+                                % (100.0 * ent.get("frac_of_fp32_ffma_peak", 0.0), ffma_peak))
+    compute = None
     extra = None
     if world == 1 and not a.no_extra:
         extra = {"bandwidth_regime": bandwidth_regime(peaks), "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
@@ -411,12 +463,12 @@ def run_b200_arm(a):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(WORKLOAD, workload="BASELINE configs[1]: TEM item_transformer train step, batch 384/GPU",
                        dropout=a.dropout, l2="flushed between timed steps (256 MiB write), flush not timed",
-                       parallelism="dp%d, item/word tables %s" % (world, "row-sharded" if world > 1 else "local"),
+                       parallelism="dp%d, item/word tables %s" % (world, "row-sharded (%s)" % transport if world > 1 else "local"),
                        launch="CUDA graph replay of the whole step" if graphed is not None else "eager"),
         "clocks": clocks.summary(),
         "e2e": {"value": B * a.steps * world / e2e_sec, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_sec / a.steps * 1e3},
-        "gpu_launches": launches, "roofline": roofline, "compute_roofline": compute, "cpu_baseline": cpu,
+        "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "extra": extra,
     }))
     if world > 1:
@@ -433,6 +485,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],
+                    help="N>1: auto = NVLink peer memory when CUDA IPC works, else NCCL all-to-all; nccl forces the latter")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)

@@ -315,8 +315,62 @@ typedef struct psb_adam_tensor {
 int64_t psb_adam_workspace_bytes(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors);
 int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors, double lr, double beta1,
                   double beta2, double eps, double weight_decay, double max_grad_norm, int32_t noam,
-                  double warmup_steps, int64_t* step_dev, float* sqnorm_dev, void* workspace,
+                  double warmup_steps, int32_t norm_given, int64_t* step_dev, float* sqnorm_dev, void* workspace,
                   int64_t workspace_bytes, psb_stream_t stream);
+/* norm_given != 0: *sqnorm_dev already holds the GLOBAL squared gradient norm (row-sharded training: the
+ * caller sums psb_grad_sqnorm of every rank's shard gradients and of the replicated ones) and is used as is. */
+
+/* *sqnorm_out (device) = sum over the tensors' gradients of |g|^2, fixed summation order.  Workspace as for
+ * psb_adam_step. */
+int psb_grad_sqnorm(const psb_adam_tensor_t* tensors /* host; only g and n are read */, int32_t n_tensors,
+                    float* sqnorm_out, void* workspace, int64_t workspace_bytes, psb_stream_t stream);
+
+/* ------------------------------------------------------------ multi-GPU ---
+ * Row-sharded tables over NVLink peer memory: owner of row id = id % G, local row =
+ * id / G.  One process per GPU; buffers that peers read (table shards, gradient staging lists, the flat
+ * dense-gradient bucket, barrier flags) are allocated with psb_peer_alloc, exported as a 64-byte handle that
+ * the host side exchanges (torch.distributed all_gather), and opened by every other rank: after that a peer
+ * buffer is an ordinary device pointer and the exchange is plain loads inside the kernels below.  Replaces
+ * the index / row / gradient all-to-alls of the NCCL transport (prodsearch_b200/sharded.py).  No entry point
+ * synchronises with the host, so a whole multi-GPU training step replays as one CUDA graph per rank. */
+#define PSB_PEER_HANDLE_BYTES 64
+#define PSB_PEER_MAX 16
+
+int psb_peer_alloc(int64_t bytes, void** out /* host */);      /* cudaMalloc + zero fill (IPC-exportable) */
+int psb_peer_free(void* p);
+int psb_peer_export(void* p, void* handle /* host, 64 bytes */);
+int psb_peer_open(const void* handle /* host */, void** out /* host */); /* maps the peer allocation, enables P2P */
+int psb_peer_close(void* p);
+
+/* Cross-GPU barrier on the launching streams of all G ranks.  flag_blocks: HOST array of G device pointers,
+ * flag_blocks[r] = rank r's flag block (uint32[PSB_PEER_MAX], zero-initialised peer memory).  *epoch_dev (local
+ * device uint32, starts at 0) counts the barriers of this rank.  A rank that waits longer than timeout_cycles
+ * (<= 0: about 2 s) stops waiting and writes 1 + the missing peer into *err_dev instead of hanging. */
+int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
+                     int32_t* err_dev, int64_t timeout_cycles, psb_stream_t stream);
+
+/* out[i,:] = shard[idx[i] % G][idx[i] / G, :]: the forward "fetch" of a row-sharded table (bit-exact copies,
+ * 128-bit loads over NVLink for remote owners) into a local mini table.  shards: HOST array of G device
+ * pointers.  remap_out (optional, [n]): the position each index is read at afterwards, remap_out[i] =
+ * idx[i] == pad_id ? pad_pos : i, so that all pad entries share ONE mini-table position and the consuming
+ * kernels keep their "idx != pad_idx" validity rule. */
+int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_t rows_total, int64_t d,
+                         const int64_t* idx, int64_t n, float* out, int64_t* remap_out, int64_t pad_id,
+                         int64_t pad_pos, int32_t* err_flag, psb_stream_t stream);
+
+/* Owner-side gradient fold of ONE peer's compact list (the unique_rows / reduced / reduced_bias / n_unique
+ * outputs of that peer's psb_scatter_reduce_rows over GLOBAL row ids, read in place from peer memory):
+ *   dense[id / G, :] += scale * vals[i, :]   and   dense_bias[id / G] += scale * bias_vals[i]
+ * for every slot i < min(*n_rows, cap) with id = rows[i], id % G == rank.  Each row occurs at most once per
+ * list, so there are no atomics; call once per peer in rank order for a reproducible sum. */
+int psb_peer_fold_rows(const int32_t* rows, const float* vals, const float* bias_vals, const int32_t* n_rows,
+                       int64_t cap, int32_t rank, int32_t G, int64_t d, float scale, float* dense,
+                       float* dense_bias, int64_t shard_rows, psb_stream_t stream);
+
+/* out[i] = scale * sum_r bufs[r][i], r ascending (one-shot all-reduce of the replicated dense gradients;
+ * every rank computes the identical sum).  bufs: HOST array of G device pointers (peer memory). */
+int psb_peer_allreduce(const void* const* bufs, int32_t G, int64_t n, float scale, float* out,
+                       psb_stream_t stream);
 
 #ifdef __cplusplus
 }

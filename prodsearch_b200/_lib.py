@@ -49,6 +49,8 @@ class AdamTensor(ctypes.Structure):
 
 
 ADAM_MAX_TENSORS = 64
+PEER_MAX = 16
+PEER_HANDLE_BYTES = 64
 
 # name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
 SIGNATURES = {
@@ -76,7 +78,19 @@ SIGNATURES = {
     "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "psb_adam_workspace_bytes": (c_i64, [ctypes.POINTER(AdamTensor), c_i32]),
     "psb_adam_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i32,
-                              c_f64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+                              c_f64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "psb_grad_sqnorm": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "psb_peer_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),
+    "psb_peer_free": (c_i32, [c_vp]),
+    "psb_peer_export": (c_i32, [c_vp, ctypes.c_char_p]),
+    "psb_peer_open": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "psb_peer_close": (c_i32, [c_vp]),
+    "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "psb_peer_gather_rows": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
+                                     c_vp, c_vp]),
+    "psb_peer_fold_rows": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64, c_f32, c_vp, c_vp, c_i64,
+                                   c_vp]),
+    "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_f32, c_vp, c_vp]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
     "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,

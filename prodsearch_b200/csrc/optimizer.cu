@@ -76,9 +76,11 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restri
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += wsum[w];
     *sqnorm = static_cast<float>(s);
-    *step += 1;
+    if (step != nullptr) *step += 1;
   }
 }
+
+__global__ void bump_step_kernel(int64_t* __restrict__ step) { *step += 1; }
 
 struct AdamHyper {  // the reference's hyper-parameters are Python doubles: 1 - beta is formed in double, then rounded
   double lr, beta1, beta2;
@@ -175,7 +177,7 @@ extern "C" int64_t psb_adam_workspace_bytes(const psb_adam_tensor_t* tensors, in
 
 extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors, double lr, double beta1, double beta2,
                              double eps, double weight_decay, double max_grad_norm, int32_t noam, double warmup_steps,
-                             int64_t* step_dev, float* sqnorm_dev, void* workspace, int64_t workspace_bytes,
+                             int32_t norm_given, int64_t* step_dev, float* sqnorm_dev, void* workspace, int64_t workspace_bytes,
                              psb_stream_t stream) {
   if (tensors == nullptr || n_tensors <= 0 || n_tensors > PSB_ADAM_MAX_TENSORS || step_dev == nullptr ||
       sqnorm_dev == nullptr || workspace == nullptr)
@@ -194,12 +196,18 @@ extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   int st;
-  PSB_PROF("sqnorm_partial_kernel", s);
-  sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
-  if ((st = launch_status()) != PSB_OK) return st;
-  PSB_PROF("sqnorm_final_kernel", s);
-  sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks), sqnorm_dev, step_dev);
-  if ((st = launch_status()) != PSB_OK) return st;
+  if (norm_given) {
+    PSB_PROF("bump_step_kernel", s);
+    bump_step_kernel<<<1, 1, 0, s>>>(step_dev);
+    if ((st = launch_status()) != PSB_OK) return st;
+  } else {
+    PSB_PROF("sqnorm_partial_kernel", s);
+    sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
+    if ((st = launch_status()) != PSB_OK) return st;
+    PSB_PROF("sqnorm_final_kernel", s);
+    sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks), sqnorm_dev, step_dev);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
   AdamHyper h;
   h.lr = lr;
   h.beta1 = beta1;
@@ -215,5 +223,31 @@ extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors
   h.warmup = static_cast<float>(warmup_steps);
   PSB_PROF("adam_kernel", s);
   adam_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, h, sqnorm_dev, step_dev);
+  return launch_status();
+}
+
+
+extern "C" int psb_grad_sqnorm(const psb_adam_tensor_t* tensors, int32_t n_tensors, float* sqnorm_out, void* workspace,
+                               int64_t workspace_bytes, psb_stream_t stream) {
+  if (tensors == nullptr || n_tensors <= 0 || n_tensors > PSB_ADAM_MAX_TENSORS || sqnorm_out == nullptr ||
+      workspace == nullptr)
+    return PSB_E_ARG;
+  AdamTensors T;
+  T.n = n_tensors;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (tensors[i].g == nullptr || tensors[i].n <= 0) return PSB_E_ARG;
+    T.t[i] = tensors[i];
+  }
+  const int64_t chunks = adam_chunks(tensors, n_tensors);
+  if (chunks > (1ll << 30)) return PSB_E_DIM;
+  if (workspace_bytes < (chunks + 4) * static_cast<int64_t>(sizeof(float))) return PSB_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  int st;
+  PSB_PROF("sqnorm_partial_kernel", s);
+  sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
+  if ((st = launch_status()) != PSB_OK) return st;
+  PSB_PROF("sqnorm_final_kernel", s);
+  sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks), sqnorm_out, nullptr);
   return launch_status();
 }

@@ -296,3 +296,207 @@ class ShardedItemTransformerRanker(ItemTransformerRanker):
                 return ops.catalog_topk(qa, w, kk, n_items=n_local, bias=bias, id_base=base, id_stride=stride, mode=mode)
             return sharded.sharded_rank_catalog(q.contiguous(), self.item_table, self.prod_pad_idx, k, topk,
                                                 ops.topk_merge)
+
+
+class PeerShardedItemTransformerRanker(ItemTransformerRanker):
+    """TEM with the item AND word tables row-sharded over NVLink peer memory (prodsearch_b200/peer.py).
+
+    ``product_emb`` / ``word_embeddings`` hold this rank's rows (owner = id % G, local row = id // G; same
+    state_dict keys, 1/G of the rows); encoder, fs projection and biases are replicated.  Per step every rank
+    fetches the rows its batch needs with P2P loads into two mini tables, runs the unchanged fused kernels,
+    reduces its gradient contributions by GLOBAL row id into a peer-visible compact list, and -- in
+    ``sync_grads`` -- folds the slots it owns of every peer's list into its shard gradient, all-reduces the
+    replicated gradients over peer memory and forms the global clip norm.  No host synchronisation anywhere:
+    ``GraphedTrainStep(model, optim, batch, sync_grads=lambda: model.sync_grads(optim))`` replays the whole
+    multi-GPU step as one CUDA graph per rank.  Gradients are the data-parallel MEAN over ranks, i.e. the
+    model behaves like the unsharded one trained on the concatenated batch."""
+
+    def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None, peer=None,
+                 grad_mode="dense"):
+        if args.sep_prod_emb or args.sim_func == "bias_product":
+            raise NotImplementedError("peer-sharded TEM: sep_prod_emb / bias_product are not sharded yet")
+        from . import peer as peer_mod
+        super().__init__(args, device, vocab_size, product_size, vocab_words, word_dists, grad_mode)
+        self.peer = peer if peer is not None else peer_mod.PeerGroup(device=device)
+        d = self.embedding_size
+        full_items = self.product_emb.weight.detach()
+        full_words = self.word_embeddings.weight.detach()
+        self.item_table = peer_mod.PeerShardedTable(product_size + 1, d, self.peer, self.prod_pad_idx, full=full_items)
+        self.word_table = peer_mod.PeerShardedTable(vocab_size, d, self.peer, self.word_pad_idx, full=full_words,
+                                                    bias=self.word_bias)
+        self.product_emb = nn.Embedding(self.item_table.local_rows, d)
+        self.product_emb.weight = self.item_table.weight
+        self.word_embeddings = nn.Embedding(self.word_table.local_rows, d)
+        self.word_embeddings.weight = self.word_table.weight
+        del full_items, full_words
+        self._make_sinks()
+        skip = {"product_emb.weight", "word_embeddings.weight"}
+        dense = [p for n, p in self.named_parameters() if p.requires_grad and n not in skip]
+        self._bucket = peer_mod.DenseBucket(self.peer, dense)
+        self._sq = self.peer.alloc(16)                      # this rank's shard-gradient |g|^2 (peer-visible)
+        self._sq_local = self._sq.view(torch.float32, (4,))
+        self._sq_total = torch.zeros(4, dtype=torch.float32, device=self.peer.device)
+        self._sq_dense = torch.zeros(1, dtype=torch.float32, device=self.peer.device)
+        self._norm_ws = None
+
+    def _make_sinks(self):
+        if hasattr(self, "item_table"):
+            self.item_sink = self.hist_sink = self.item_table.sink
+            self.word_sink = self.word_table.sink
+        else:
+            super()._make_sinks()
+
+    def _apply(self, fn, *a, **k):
+        if hasattr(self, "item_table"):
+            raise RuntimeError("a peer-sharded model cannot be moved / cast after construction")
+        return super()._apply(fn, *a, **k)
+
+    # ---- training ----------------------------------------------------------------------------------------
+    def forward_dotproduct(self, batch_data, train_pv=False):
+        query_word_idxs = batch_data.query_word_idxs
+        target_prod_idxs = batch_data.target_prod_idxs
+        u_item_idxs = batch_data.u_item_idxs
+        pos_iword_idxs = batch_data.pos_iword_idxs
+        B, _ = u_item_idxs.shape
+        K = self.args.neg_per_pos
+        W = pos_iword_idxs.shape[1]
+        neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+        if neg_word_idxs is None:
+            neg_word_idxs = torch.multinomial(self.word_dists, B * W * K, replacement=True).view(B, W, K)
+        L = u_item_idxs.shape[1]
+        self.item_table.reserve_stage(2 * B * (L + 2 + K))                       # collective on first use only
+        self.word_table.reserve_stage(2 * B * (query_word_idxs.shape[1] + W * (1 + K)))
+        self.peer.barrier()        # every owner has finished last step's optimizer update / staging reads
+        items, (tgt, neg, hist), item_pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs])
+        words, (qw, pw, nw), word_pad = self.word_table.fetch([query_word_idxs, pos_iword_idxs, neg_word_idxs])
+        isink, wsink = self.item_table.sink, self.word_table.sink
+        q_emb = self.query_encoder.encode_indices(words, qw, wsink, pad_idx=word_pad)
+        out_pos = -1 if self.args.use_item_pos else 0
+        stochastic = self.training and self.args.dropout > 0
+        copies = 1 + K if stochastic else 1
+        out = self.transformer_encoder.encode_position(first=q_emb.contiguous(), table=items, idx=hist, sink=isink,
+                                                       pad_idx=item_pad, use_pos=self.args.use_pos_emb,
+                                                       out_pos=out_pos, copies=copies)
+        if stochastic:
+            out = out.view(B, 1 + K, -1)
+            pos_out = out[:, 0].contiguous()
+            neg_out = out[:, 1:].reshape(B * K, -1)
+        else:
+            pos_out = out
+            neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
+        pos_weight = float(K) if self.args.pos_weight else 1.0
+        ps = F_.ns_loss(pos_out.contiguous(), items, tgt.view(B, 1), neg.view(B, 1, K), isink,
+                        anchor_b=neg_out.contiguous(), pos_weight=pos_weight)
+        ps_loss = ps.mean()
+        anchor = F_.gather_rows(items, tgt, isink)
+        wb = self.word_bias
+        bias_mini = None
+        if wb is not None:     # bias values at the mini positions (the bias vector itself is replicated)
+            bias_mini = _BiasAtFn.apply(wb, self.word_table.sink._ids)
+        il = F_.ns_loss(anchor, words, pw, nw.view(B, W, K), wsink, bias=bias_mini, pad_idx=word_pad)
+        item_loss = il.mean()
+        with torch.no_grad():
+            if self._ps_acc is None:
+                self._ps_acc = torch.zeros((), device=ps_loss.device)
+                self._item_acc = torch.zeros((), device=ps_loss.device)
+            self._ps_acc.add_(ps_loss.detach())
+            self._item_acc.add_(item_loss.detach())
+        return ps_loss + item_loss
+
+    def sync_grads(self, optim=None):
+        """Between ``loss.backward()`` and ``optim.step()`` (all ranks): fold the peers' gradient lists into the
+        owned shards, all-reduce the replicated gradients, hand the GLOBAL clip norm to the optimizer.  Three
+        phases separated by peer barriers (the single-process simulation of the tests calls them in lockstep)."""
+        self.sync_stage()
+        self.peer.barrier()        # every rank's compact lists and dense bucket are complete
+        self.sync_fold()
+        if optim is None or not hasattr(getattr(optim, "optimizer", optim), "set_global_sqnorm"):
+            return
+        self.peer.barrier()        # every rank's shard norm is published
+        self.sync_norm(optim)
+
+    def sync_stage(self):
+        self._bucket.stage()
+
+    def sync_fold(self):
+        G = self.peer.world
+        self.item_table.fold(1.0 / G)
+        self.word_table.fold(1.0 / G)
+        self._bucket.reduce()
+        lib = _lib.load()
+        shard = (_lib.AdamTensor * 2)(
+            _lib.AdamTensor(None, self.item_table.grad.data_ptr(), None, None, self.item_table.grad.numel()),
+            _lib.AdamTensor(None, self.word_table.grad.data_ptr(), None, None, self.word_table.grad.numel()))
+        dense = (_lib.AdamTensor * 1)(_lib.AdamTensor(None, self._bucket.red.data_ptr(), None, None, self._bucket.n))
+        wb = max(int(lib.psb_adam_workspace_bytes(shard, 2)), int(lib.psb_adam_workspace_bytes(dense, 1)))
+        if self._norm_ws is None or self._norm_ws.numel() < wb:
+            self._norm_ws = torch.empty(wb, dtype=torch.uint8, device=self.peer.device)
+        _lib.check(lib.psb_grad_sqnorm(shard, 2, self._sq_local.data_ptr(), self._norm_ws.data_ptr(), wb,
+                                       _lib.stream_ptr()), "psb_grad_sqnorm")
+        _lib.check(lib.psb_grad_sqnorm(dense, 1, self._sq_dense.data_ptr(), self._norm_ws.data_ptr(), wb,
+                                       _lib.stream_ptr()), "psb_grad_sqnorm")
+
+    def sync_norm(self, optim):
+        self.peer.allreduce(self._sq, 4, self._sq_total, scale=1.0)
+        getattr(optim, "optimizer", optim).set_global_sqnorm(self._sq_total[:1] + self._sq_dense)
+
+    # ---- evaluation -----------------------------------------------------------------------------------------
+    def encode_queries(self, query_word_idxs, u_item_idxs, copies=1, hist=None):
+        with torch.no_grad():
+            items, (h,), item_pad = self.item_table.fetch([u_item_idxs])
+            words, (qw,), word_pad = self.word_table.fetch([query_word_idxs])
+            q_emb = self.query_encoder.encode_indices(words, qw, None, pad_idx=word_pad)
+            out_pos = -1 if self.args.use_item_pos else 0
+            return self.transformer_encoder.encode_position(first=q_emb.contiguous(), table=items, idx=h, sink=None,
+                                                            pad_idx=item_pad, use_pos=self.args.use_pos_emb,
+                                                            out_pos=out_pos, copies=copies)
+
+    def test_dotproduct(self, batch_data):
+        with torch.no_grad():
+            q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs).contiguous()
+            items, (cand,), _ = self.item_table.fetch([batch_data.candi_prod_idxs])
+            return ops.score_rows(q, items, cand, None)
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):
+        """Sharded full-catalog top-k: every rank scores the all-gathered queries against its shard
+        (id = rank + G * local row), the per-shard lists are all-gathered and merged (psb_topk_merge)."""
+        import torch.distributed as dist
+        with torch.no_grad():
+            q = batch_or_queries if torch.is_tensor(batch_or_queries) else self.encode_queries(
+                batch_or_queries.query_word_idxs, batch_or_queries.u_item_idxs)
+            q = q.contiguous()
+            G, r = self.peer.world, self.peer.rank
+            n_local = max(0, (self.prod_pad_idx - r + G - 1) // G)
+            if G == 1:
+                return ops.catalog_topk(q, self.item_table.weight.detach(), k, n_items=n_local, mode=mode)
+            m = torch.tensor([q.shape[0]], device=q.device)
+            ms = [torch.empty_like(m) for _ in range(G)]
+            dist.all_gather(ms, m, group=self.peer.group)
+            m_all = [int(x) for x in ms]
+            m_max = max(m_all)
+            q_pad = q.new_zeros((m_max, q.shape[1]))
+            q_pad[:q.shape[0]] = q
+            qs = [torch.empty_like(q_pad) for _ in range(G)]
+            dist.all_gather(qs, q_pad, group=self.peer.group)
+            ids, sc = ops.catalog_topk(torch.cat(qs, 0), self.item_table.weight.detach(), k, n_items=n_local,
+                                       id_base=r, id_stride=G, mode=mode)
+            ids_all = [torch.empty_like(ids) for _ in range(G)]
+            sc_all = [torch.empty_like(sc) for _ in range(G)]
+            dist.all_gather(ids_all, ids, group=self.peer.group)
+            dist.all_gather(sc_all, sc, group=self.peer.group)
+            mi, ms_ = ops.topk_merge(torch.stack(ids_all), torch.stack(sc_all))
+            lo = r * m_max
+            return mi[lo:lo + q.shape[0]], ms_[lo:lo + q.shape[0]]
+
+
+class _BiasAtFn(torch.autograd.Function):
+    """bias[ids] for the mini-table positions; the gradient reaches the bias through the table's sink
+    (``to_bias`` contributions), so nothing flows back here."""
+
+    @staticmethod
+    def forward(ctx, bias, ids):
+        return bias.detach()[ids]
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None

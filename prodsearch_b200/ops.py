@@ -121,7 +121,7 @@ def make_contrib(idx, src, src_row=None, src_div=1, scale=None, scale2=None, sca
 
 
 def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_bias_grad=None,
-                   want_rows=True, want_bias=False, device=None, out_uniq=None, out_nu=None):
+                   want_rows=True, want_bias=False, device=None, out_uniq=None, out_nu=None, out_red=None):
     """Deterministic sort + segmented-reduce embedding backward (psb_scatter_reduce_rows).
     contribs: list of (Contrib, keepalive).  Returns (unique_rows [n_total] int32, reduced or None,
     reduced_bias or None, n_unique device int32 [1])."""
@@ -134,7 +134,12 @@ def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_
     cap = max(n_total, 1)
     # out_uniq / out_nu: caller-owned persistent buffers (a CUDA-graph replay must find last step's rows there)
     uniq = out_uniq if out_uniq is not None and out_uniq.numel() >= cap else torch.empty((cap,), dtype=i32, device=device)
-    red = torch.empty((cap, d), dtype=f32, device=device) if want_rows else None
+    if out_red is not None and want_rows:     # caller-owned (e.g. peer-visible staging) row buffer
+        if out_red.shape[0] < cap or out_red.shape[1] != d:
+            raise RuntimeError("scatter_reduce: out_red too small")
+        red = out_red
+    else:
+        red = torch.empty((cap, d), dtype=f32, device=device) if want_rows else None
     redb = torch.empty((cap,), dtype=f32, device=device) if want_bias else None
     nu = out_nu.zero_() if out_nu is not None else torch.zeros((1,), dtype=i32, device=device)
     if n_total > 0:

@@ -24,6 +24,7 @@ class FusedAdam(object):
         self._step_dev = None
         self._sqnorm = None
         self._ws = None
+        self._norm_given = False
 
     def _ensure(self, dev):
         if self._step_dev is None:
@@ -36,6 +37,13 @@ class FusedAdam(object):
             st = self.state[p] = dict(exp_avg=torch.zeros_like(p, memory_format=torch.contiguous_format),
                                       exp_avg_sq=torch.zeros_like(p, memory_format=torch.contiguous_format))
         return st
+
+    def set_global_sqnorm(self, sq):
+        """Row-sharded training: the caller supplies the GLOBAL squared gradient norm (device tensor [1]; this
+        rank's parameters are only a shard) for the next ``step``.  Stream-ordered copy, CUDA-graph safe."""
+        self._ensure(sq.device)
+        self._sqnorm.copy_(sq.reshape(1))
+        self._norm_given = True
 
     @property
     def total_norm(self):
@@ -71,8 +79,10 @@ class FusedAdam(object):
             ev[0].record()
         _lib.check(lib.psb_adam_step(arr, len(live), float(g["lr"]), float(b1), float(b2), float(g["eps"]),
                                      float(g["weight_decay"]), float(max_grad_norm or 0.0), 1 if noam else 0,
-                                     float(warmup_steps), self._step_dev.data_ptr(), self._sqnorm.data_ptr(),
+                                     float(warmup_steps), 1 if self._norm_given else 0, self._step_dev.data_ptr(),
+                                     self._sqnorm.data_ptr(),
                                      self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()), "psb_adam_step")
+        self._norm_given = False
         if ev is not None:
             ev[1].record()
             ops.PROFILE.setdefault("adam_step", []).append(ev)

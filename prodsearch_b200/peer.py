@@ -1,0 +1,355 @@
+"""Row-sharded embedding tables over NVLink peer memory (C ABI: the psb_peer_* block of
+include/psb.h).
+
+One process per GPU.  Every buffer a peer must read -- table shards, the compact gradient lists each rank
+produces, the flat bucket of replicated dense gradients, barrier flags -- is allocated by ``PeerGroup.alloc``,
+exported as a CUDA IPC handle, exchanged once through ``torch.distributed`` (plumbing) and mapped by every
+other rank.  From then on the exchange steps are loads inside hand-written kernels:
+
+  fetch   ``PeerShardedTable.fetch``: out[i] = shard[id % G][id / G]  (psb_peer_gather_rows) into a small
+          local *mini table*; the unchanged single-GPU fused kernels then run on it with remapped indices
+  push    the table's ``PeerGradSink`` runs the usual deterministic sort + segmented reduce over GLOBAL row
+          ids into a peer-visible compact list (rows, values, count)
+  fold    after a barrier every owner folds the slots it owns of each peer's list, peer by peer in rank order,
+          into its dense shard gradient (psb_peer_fold_rows): reproducible, no float atomics, no second sort
+  dense   replicated parameters: one-shot all-reduce over the peers' flat buckets (psb_peer_allreduce)
+
+Nothing here synchronises with the host, so ``model(batch); backward; sync_grads; optim.step`` is captured
+and replayed as ONE CUDA graph per rank (graph_step.GraphedTrainStep).  For the unit tests several ranks can be
+simulated inside one process on one GPU (``PeerGroup.simulate``): the kernels only see pointer arrays.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_vp, check, load, stream_ptr
+
+
+class _Raw(object):
+    """Raw device allocation exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes, owner=None):
+        self.ptr, self.nbytes, self.owner = ptr, nbytes, owner
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(ptr, nbytes, device, keep):
+    t = torch.as_tensor(_Raw(ptr, nbytes, keep), device=device)
+    return t
+
+
+class PeerBuffer(object):
+    """One symmetric allocation: ``local`` (uint8 tensor view of this rank's copy) and the device pointers of
+    every rank's copy (``ptrs``), usable from this rank's kernels."""
+
+    def __init__(self, group, seq, ptr, nbytes):
+        self.group, self.seq, self.ptr, self.nbytes = group, seq, ptr, nbytes
+        self.local = _as_tensor(ptr, nbytes, group.device, self)
+        self._ptrs = None
+
+    @property
+    def ptrs(self):
+        if self._ptrs is None:
+            self._ptrs = self.group._resolve(self)
+        return self._ptrs
+
+    def ptr_array(self, offset=0):
+        """HOST array of G device pointers (ctypes), each advanced by ``offset`` bytes."""
+        return (c_vp * len(self.ptrs))(*[p + offset for p in self.ptrs])
+
+    def view(self, dtype, shape, offset=0):
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        return self.local[offset:offset + nb].view(dtype).view(shape)
+
+
+class _SimHub(object):
+    """Shared registry of the simulated ranks of one process (tests)."""
+
+    def __init__(self, world):
+        self.world, self.table = world, {}
+
+
+class PeerGroup(object):
+    def __init__(self, group=None, device=None, _sim=None, _rank=None):
+        import torch.distributed as dist
+        self._sim = _sim
+        if _sim is not None:
+            self.world, self.rank = _sim.world, _rank
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.PEER_MAX:
+            raise RuntimeError("PeerGroup: at most %d ranks" % _lib.PEER_MAX)
+        self.group = group
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self._seq = 0
+        self._opened = []
+        self.flags = self.alloc(4 * _lib.PEER_MAX)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.timeout_cycles = 0
+
+    @classmethod
+    def simulate(cls, world, device="cuda"):
+        """``world`` ranks inside this process, all on ``device`` (unit tests of the kernels and host logic)."""
+        hub = _SimHub(world)
+        return [cls(device=device, _sim=hub, _rank=r) for r in range(world)]
+
+    # ---- allocation (collective: every rank calls alloc in the same order with the same size) -------------
+    def alloc(self, nbytes):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        out = c_vp()
+        with torch.cuda.device(self.device):
+            check(load().psb_peer_alloc(nbytes, ctypes.byref(out)), "psb_peer_alloc")
+        buf = PeerBuffer(self, self._seq, out.value, nbytes)
+        self._seq += 1
+        if self._sim is not None:
+            self._sim.table[(buf.seq, self.rank)] = buf.ptr
+        elif self.world > 1:
+            buf._ptrs = self._exchange(buf)
+        else:
+            buf._ptrs = [buf.ptr]
+        return buf
+
+    def _resolve(self, buf):
+        if self._sim is None:
+            return buf._ptrs
+        return [self._sim.table[(buf.seq, r)] for r in range(self.world)]
+
+    def _exchange(self, buf):
+        import torch.distributed as dist
+        handle = ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        check(load().psb_peer_export(buf.ptr, handle), "psb_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.rank, buf.seq, buf.nbytes, handle.raw), group=self.group)
+        ptrs = []
+        for r, (rr, seq, nb, raw) in enumerate(handles):
+            if rr != r or seq != buf.seq or nb != buf.nbytes:
+                raise RuntimeError("PeerGroup.alloc called out of step across ranks")
+            if r == self.rank:
+                ptrs.append(buf.ptr)
+                continue
+            out = c_vp()
+            check(load().psb_peer_open(raw, ctypes.byref(out)), "psb_peer_open (CUDA IPC / NVLink P2P)")
+            self._opened.append(out.value)
+            ptrs.append(out.value)
+        return ptrs
+
+    # ---- synchronisation ----------------------------------------------------------------------------------
+    def barrier(self):
+        """Stream-ordered barrier of all ranks (graph-capturable).  The simulated ranks of one process share
+        a stream and are driven phase by phase in lockstep by the tests, so stream order already is the barrier."""
+        if self.world == 1 or self._sim is not None:
+            return
+        check(load().psb_peer_barrier(self.flags.ptr_array(), self.rank, self.world, self.epoch.data_ptr(),
+                                      self.err.data_ptr(), int(self.timeout_cycles), stream_ptr()),
+              "psb_peer_barrier")
+
+    def check_errors(self):
+        """Host-synchronising check of the barrier time-out flag."""
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError("peer barrier timed out waiting for rank %d" % (e - 1))
+
+    def allreduce(self, buf, n, out, scale=1.0, offset=0):
+        """out[:n] = scale * sum over ranks of the fp32 vectors at ``offset`` of the symmetric ``buf``."""
+        check(load().psb_peer_allreduce(buf.ptr_array(offset), self.world, int(n), float(scale), out.data_ptr(),
+                                        stream_ptr()), "psb_peer_allreduce")
+        return out
+
+
+def try_create(group=None, device=None):
+    """PeerGroup of ``group`` if CUDA IPC + P2P work between all its ranks, else None -- the same answer on every
+    rank (callers fall back to the NCCL all-to-all transport of sharded.py)."""
+    import torch.distributed as dist
+    pg, ok = None, 1
+    try:
+        pg = PeerGroup(group, device)
+    except RuntimeError as ex:
+        ok = 0
+        import sys
+        sys.stderr.write("peer memory unavailable on rank %d: %s\n" % (dist.get_rank(group), ex))
+    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return pg if int(t.item()) == 1 else None
+
+
+class PeerShardedTable(object):
+    """A [rows, d] fp32 table row-sharded cyclically (owner = id % G, local row = id // G)."""
+
+    def __init__(self, rows, d, peer, pad_idx, full=None, bias=None, stage_cap=0):
+        self.rows, self.d, self.peer, self.pad_idx = int(rows), int(d), peer, int(pad_idx)
+        G, r = peer.world, peer.rank
+        self.local_rows = (self.rows - r + G - 1) // G
+        self.shard = peer.alloc(max(self.local_rows, 1) * d * 4)
+        w = self.shard.view(torch.float32, (self.local_rows, d))
+        if full is not None:
+            with torch.no_grad():
+                w.copy_(full[r::G].to(w.device))
+        self.weight = torch.nn.Parameter(w)
+        self.grad = torch.zeros_like(w)                    # dense shard gradient (what Adam reads)
+        self.bias = bias                                   # replicated bias vector indexed like the table
+        self.bias_grad = torch.zeros_like(bias) if bias is not None else None
+        self._stage = None
+        self._cap = 0
+        if stage_cap:
+            self._ensure_stage(stage_cap)
+        self.sink = PeerGradSink(self)
+
+    # staging layout (peer-visible): [n_rows int32 | pad to 256][rows int32 cap][vals fp32 cap x d]
+    def _ensure_stage(self, cap):
+        if self._stage is not None:
+            raise RuntimeError("the gradient staging list is sized once (stage_cap / the first step)")
+        cap = (cap + 63) // 64 * 64
+        self._off_rows = 256
+        self._off_vals = 256 + cap * 4
+        self._stage = self.peer.alloc(self._off_vals + cap * self.d * 4)   # collective
+        self._cap = cap
+        self.stage_n = self._stage.view(torch.int32, (1,), 0)
+        self.stage_rows = self._stage.view(torch.int32, (cap,), self._off_rows)
+        self.stage_vals = self._stage.view(torch.float32, (cap, self.d), self._off_vals)
+
+    def reserve_stage(self, cap):
+        """Size the peer-visible gradient list for ``cap`` contribution slots per step.  Collective (and
+        host-synchronising) when it has to grow, free otherwise; growing inside graph capture is an error."""
+        if self._stage is None:
+            if self.peer.world > 1 and self.peer._sim is None:     # ragged batches: agree on the largest request
+                import torch.distributed as dist
+                t = torch.tensor([int(cap)], dtype=torch.int64, device=self.peer.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.peer.group)
+                cap = int(t.item())
+            self._ensure_stage(cap)
+
+    def fetch(self, index_tensors):
+        """Gather the rows of ``index_tensors`` (global ids) from their owners into a local mini table.
+        Returns (mini [n+1, d], remapped index tensors, pad position): positions of pad ids are remapped to
+        the single position n (which holds the pad row), so kernels keep their ``idx != pad_idx`` validity rule."""
+        flats = [t.reshape(-1) for t in index_tensors]
+        n = sum(f.numel() for f in flats)
+        dev = self.weight.device
+        pad_t = getattr(self, "_pad_t", None)
+        if pad_t is None:
+            pad_t = self._pad_t = torch.full((1,), self.pad_idx, dtype=torch.int64, device=dev)
+        ids = torch.cat(flats + [pad_t])
+        mini = torch.empty((n + 1, self.d), dtype=torch.float32, device=dev)
+        remap = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+        check(load().psb_peer_gather_rows(self.shard.ptr_array(), self.peer.world, self.rows, self.d, ids.data_ptr(),
+                                          n + 1, mini.data_ptr(), remap.data_ptr(), self.pad_idx, n, None, stream_ptr()),
+              "psb_peer_gather_rows")
+        # a leaf that requires grad, so the autograd Functions reading it run their backward (which routes the row
+        # gradients to the sink; nothing is ever accumulated into mini.grad)
+        mini.requires_grad_(self.weight.requires_grad and torch.is_grad_enabled())
+        outs, off = [], 0
+        origin = {}
+        for t, f in zip(index_tensors, flats):
+            r = remap[off:off + f.numel()].view(t.shape)
+            outs.append(r)
+            origin[r.data_ptr()] = f
+            off += f.numel()
+        self.sink.begin(ids, origin)
+        return mini, outs, n
+
+    def fold(self, scale):
+        """Owner side: shard gradient = scale * sum over peers (rank order) of the owned slots of their lists."""
+        self.grad.zero_()
+        lib = load()
+        st = self._stage
+        for r in range(self.peer.world):
+            base = st.ptrs[r]
+            check(lib.psb_peer_fold_rows(base + self._off_rows, base + self._off_vals, None, base, self._cap,
+                                         self.peer.rank, self.peer.world, self.d, float(scale), self.grad.data_ptr(),
+                                         None, self.local_rows, stream_ptr()), "psb_peer_fold_rows")
+        self.weight.grad = self.grad
+
+
+class PeerGradSink(object):
+    """RowGradSink counterpart of a peer-sharded table: contributions arrive with mini-table positions, are
+    translated back to GLOBAL row ids, and one sort + segmented reduce writes the compact list the owners fold."""
+
+    def __init__(self, table):
+        self.table = table
+        self._pending = []
+        self._queued = False
+        self._ids = None
+        self._origin = {}
+        self.weight = table.weight
+
+    def begin(self, ids, origin):
+        self._ids, self._origin = ids, origin
+
+    def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
+        from . import ops
+        from torch.autograd import Variable
+        g = self._origin.get(idx.data_ptr())
+        if g is None or g.numel() != idx.numel():
+            g = self._ids[idx.reshape(-1)]
+        self._pending.append(ops.make_contrib(g, src, src_row, src_div, scale, scale2, scale2_div,
+                                              to_bias and self.table.bias is not None))
+        if not self._queued:
+            self._queued = True
+            Variable._execution_engine.queue_callback(self.finalize)
+
+    def finalize(self):
+        from . import ops
+        self._queued = False
+        pending, self._pending = self._pending, []
+        if not pending:
+            return
+        t = self.table
+        if len(pending) > _lib.MAX_CONTRIBS:
+            raise RuntimeError("more than %d contributions to one table in a step" % _lib.MAX_CONTRIBS)
+        n_total = sum(int(c.n) for c, _ in pending)
+        if n_total > t._cap:
+            raise RuntimeError("gradient staging list too small (%d slots, %d needed): call reserve_stage with the "
+                               "largest step first" % (t._cap, n_total))
+        want_bias = t.bias is not None and any(c.to_bias for c, _ in pending)
+        if want_bias:
+            t.bias_grad.zero_()
+        ops.scatter_reduce(pending, t.rows, t.d, t.pad_idx, dense_bias_grad=t.bias_grad if want_bias else None,
+                           want_rows=True, device=t.weight.device, out_uniq=t.stage_rows, out_nu=t.stage_n,
+                           out_red=t.stage_vals)
+        if want_bias:
+            t.bias.grad = t.bias_grad
+
+
+class DenseBucket(object):
+    """Flat peer-visible bucket of the replicated parameters' gradients + the one-shot all-reduce."""
+
+    def __init__(self, peer, params):
+        self.peer = peer
+        self.params = list(params)
+        self.n = sum(p.numel() for p in self.params)
+        n_pad = (self.n + 3) // 4 * 4
+        self.buf = peer.alloc(n_pad * 4)
+        self.flat = self.buf.view(torch.float32, (n_pad,))
+        self.red = torch.zeros(n_pad, dtype=torch.float32, device=peer.device)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.red[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+
+    def stage(self):
+        """Copy the local gradients into the bucket (before the barrier)."""
+        zeros = None
+        parts = []
+        for p in self.params:
+            if p.grad is None:
+                if zeros is None:
+                    zeros = {}
+                z = zeros.get(p.numel())
+                if z is None:
+                    z = zeros[p.numel()] = torch.zeros(p.numel(), dtype=torch.float32, device=self.peer.device)
+                parts.append(z)
+            else:
+                parts.append(p.grad.reshape(-1))
+        torch.cat(parts, out=self.flat[:self.n])
+
+    def reduce(self):
+        """After the barrier: mean over ranks into the local reduced bucket; gradients become views of it."""
+        self.peer.allreduce(self.buf, self.flat.numel(), self.red, scale=1.0 / self.peer.world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v

@@ -73,7 +73,104 @@ def main():
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, worst relative gradient error %.2e, sharded top-100 == unsharded" % (world, worst))
+    peer_check(rank, world, cfg, ref, batches, dev)
     dist.destroy_process_group()
+
+
+def peer_check(rank, world, cfg, ref, batches, dev):
+    """The NVLink peer-memory transport (prodsearch_b200/peer.py): one eager step against the unsharded model,
+    then the same step captured and replayed as one CUDA graph per rank."""
+    from prodsearch_b200 import peer, synth
+    from prodsearch_b200.graph_step import GraphedTrainStep
+    from prodsearch_b200.item_transformer import PeerShardedItemTransformerRanker
+    from prodsearch_b200.optimizers import build_optim
+    pg = peer.try_create()
+    if pg is None:
+        if rank == 0:
+            print("peer_check SKIPPED: CUDA IPC / P2P unavailable on this box")
+        return
+    P, V, B = 40000, 5000, 96
+    for k_, v_ in dict(optim="adam", lr=0.01, max_grad_norm=0.05, beta1=0.9, beta2=0.999, decay_method="adam",
+                       warmup_steps=8000, l2_lambda=0.0, train_from="").items():
+        setattr(cfg, k_, v_)
+    torch.manual_seed(1)
+    m = PeerShardedItemTransformerRanker(cfg, "cuda", V, P, None, word_dists=synth.word_dists(V), peer=pg)
+    opt = build_optim(cfg, m)
+    ref_opt = build_optim(cfg, ref)
+    m.train()
+    wq = max(b.query_word_idxs.shape[1] for b, _, _ in batches)
+
+    def padded(b):
+        out = dev(b)
+        q = torch.full((B, wq), V - 1, dtype=torch.int64, device="cuda")
+        q[:, :out.query_word_idxs.shape[1]] = out.query_word_idxs
+        out.query_word_idxs = q
+        return out
+    b, ni, nw = batches[rank]
+    m.injected_negatives = (ni.cuda(), nw.cuda())
+    loss = m(padded(b))
+    m.zero_grad()
+    loss.backward()
+    m.sync_grads(opt)
+    ref.zero_grad()
+    total = None
+    for r in range(world):
+        br, nir, nwr = batches[r]
+        ref.injected_negatives = (nir.cuda(), nwr.cuda())
+        l = ref(padded(br))
+        if r == rank:
+            assert abs(float(l) - float(loss)) <= 1e-5 * abs(float(l)), (float(l), float(loss))
+        total = l if total is None else total + l
+    (total / world).backward()
+    refp = dict(ref.named_parameters())
+    sharded_keys = ("product_emb.weight", "word_embeddings.weight")
+    worst = 0.0
+    for k, p in m.named_parameters():
+        g_ref = refp[k].grad if refp[k].grad is not None else torch.zeros_like(refp[k])
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        if k in sharded_keys:
+            g_ref = g_ref[rank::world]
+        scale = float(g_ref.abs().max()) + 1e-12
+        err = float((g - g_ref).abs().max())
+        assert err <= 1e-4 * scale + 2e-7, (k, err, scale)
+        worst = max(worst, err / scale)
+    opt.step()
+    ref_opt.step()
+    tn = float(ref_opt.optimizer.total_norm)
+    assert abs(float(opt.optimizer.total_norm) - tn) <= 1e-4 * tn
+    for k, p in m.named_parameters():
+        w_ref = refp[k].detach()
+        if k in sharded_keys:
+            w_ref = w_ref[rank::world]
+        assert torch.allclose(p.detach(), w_ref, rtol=1e-4, atol=2e-6), k
+    pg.check_errors()
+    # sharded catalog ranking through the peer model == unsharded (the tables were just updated identically)
+    q = torch.randn(5 + rank, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(19 + rank))
+    ids, sc = m.rank_catalog(q, k=100)
+    ids_r, sc_r = ref.rank_catalog(q, k=100)
+    assert torch.equal(ids, ids_r) and torch.allclose(sc, sc_r, rtol=1e-5, atol=1e-5)
+    # ---- the whole multi-GPU step as one CUDA graph per rank
+    m.injected_negatives = None
+    torch.manual_seed(100 + rank)
+    graphed = GraphedTrainStep(m, opt, padded(b), pad_values={"query_word_idxs": V - 1, "u_item_idxs": P},
+                               sync_grads=lambda: m.sync_grads(opt))
+    losses = []
+    for it in range(4):
+        bb, _, _ = synth.tem_batch(B, P, V, seed=500 + 10 * it + rank)
+        losses.append(graphed(padded(bb)).clone())
+    torch.cuda.synchronize()
+    pg.check_errors()
+    vals = [float(x) for x in losses]
+    assert all(v == v and 0 < v < 100 for v in vals), vals
+    # replicated parameters stay bit-identical across ranks
+    chk = torch.stack([p.detach().double().sum() for k, p in m.named_parameters() if k not in sharded_keys])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    assert all(torch.equal(allc[0], c) for c in allc)
+    dist.barrier()
+    if rank == 0:
+        print("peer_check ok: world=%d, worst relative gradient error %.2e, graph-replayed losses %s" %
+              (world, worst, ["%.4f" % v for v in vals]))
 
 
 if __name__ == "__main__":
