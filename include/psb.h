@@ -358,14 +358,28 @@ int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_t rows_tota
                          const int64_t* idx, int64_t n, float* out, int64_t* remap_out, int64_t pad_id,
                          int64_t pad_pos, int32_t* err_flag, psb_stream_t stream);
 
-/* Owner-side gradient fold of ONE peer's compact list (the unique_rows / reduced / reduced_bias / n_unique
- * outputs of that peer's psb_scatter_reduce_rows over GLOBAL row ids, read in place from peer memory):
- *   dense[id / G, :] += scale * vals[i, :]   and   dense_bias[id / G] += scale * bias_vals[i]
- * for every slot i < min(*n_rows, cap) with id = rows[i], id % G == rank.  Each row occurs at most once per
- * list, so there are no atomics; call once per peer in rank order for a reproducible sum. */
-int psb_peer_fold_rows(const int32_t* rows, const float* vals, const float* bias_vals, const int32_t* n_rows,
-                       int64_t cap, int32_t rank, int32_t G, int64_t d, float scale, float* dense,
-                       float* dense_bias, int64_t shard_rows, psb_stream_t stream);
+/* Owner-side gradient fold.  Every rank r publishes a compact list in peer memory -- the unique_rows / reduced /
+ * n_unique outputs of its psb_scatter_reduce_rows over GLOBAL row ids.  For every row this rank owns
+ * (id % G == rank, local row id / G) that occurs in at least one list:
+ *     dense[id / G, :] = scale * sum_r vals_r[slot_r(id), :]      (r ascending: reproducible, no atomics)
+ * in two launches for up to two tables, independent of G: "mark" writes (stamp, slot) of every owned slot into
+ * posmap[r][local]; "sum" lets the lowest peer holding a row add the later peers' rows and OVERWRITE the dense
+ * row once.  Rows no list holds are not written: the caller keeps them zero (psb_zero_rows with the `touched`
+ * list of the previous fold, or a memset).  *stamp_dev must be constant during the call and differ from the
+ * previous call's value (the barrier epoch); posmap is uint64[G * shard_rows], zero-initialised once. */
+typedef struct psb_fold_table {
+  const int32_t* rows[PSB_PEER_MAX];   /* per peer: [cap] ascending unique global ids (peer memory) */
+  const float* vals[PSB_PEER_MAX];     /* per peer: [cap, d] */
+  const int32_t* n_rows[PSB_PEER_MAX]; /* per peer: device count */
+  int64_t cap, d, shard_rows;
+  void* posmap;
+  float* dense;                        /* [shard_rows, d] */
+  int32_t* touched;                    /* optional [G * cap]: local rows written, unordered */
+  int32_t* n_touched;                  /* device counter for `touched` (caller zeroes it) */
+} psb_fold_table_t;
+
+int psb_peer_fold_lists(const psb_fold_table_t* tables /* host */, int32_t n_tables, int32_t rank, int32_t G,
+                        float scale, const uint32_t* stamp_dev, psb_stream_t stream);
 
 /* out[i] = scale * sum_r bufs[r][i], r ascending (one-shot all-reduce of the replicated dense gradients;
  * every rank computes the identical sum).  bufs: HOST array of G device pointers (peer memory). */

@@ -52,6 +52,14 @@ ADAM_MAX_TENSORS = 64
 PEER_MAX = 16
 PEER_HANDLE_BYTES = 64
 
+
+class FoldTable(ctypes.Structure):
+    """psb_fold_table_t."""
+    _fields_ = [("rows", c_vp * PEER_MAX), ("vals", c_vp * PEER_MAX), ("n_rows", c_vp * PEER_MAX), ("cap", c_i64),
+                ("d", c_i64), ("shard_rows", c_i64), ("posmap", c_vp), ("dense", c_vp), ("touched", c_vp),
+                ("n_touched", c_vp)]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
 SIGNATURES = {
     "psb_abi_version": (c_i32, []),
@@ -88,8 +96,7 @@ SIGNATURES = {
     "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "psb_peer_gather_rows": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
                                      c_vp, c_vp]),
-    "psb_peer_fold_rows": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64, c_f32, c_vp, c_vp, c_i64,
-                                   c_vp]),
+    "psb_peer_fold_lists": (c_i32, [ctypes.POINTER(FoldTable), c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_f32, c_vp, c_vp]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),

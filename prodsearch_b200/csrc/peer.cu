@@ -4,9 +4,8 @@
 // whole multi-GPU training step replays as one CUDA graph per rank.
 //
 //   peer_gather_rows   out[i] = shard[id % G][id / G]      (forward "fetch": P2P 128-bit row loads)
-//   peer_fold_rows     owner-side gradient fold: dense[id / G] += scale * vals[i] for the slots of ONE
-//                      peer's compact (sorted unique rows, values) list that this rank owns; launched once
-//                      per peer in rank order => deterministic, no float atomics
+//   peer_fold_lists    owner-side gradient fold of all peers' compact (sorted unique rows, values) lists in two
+//                      launches (mark + leader sum, see below): rank-ordered sums, no float atomics
 //   peer_allreduce     one-shot sum of the replicated dense gradients: every rank reads all G buffers and
 //                      adds them in rank order (bit-identical result on every rank)
 //   peer_barrier       cross-GPU barrier on flag words in peer memory (release/acquire at system scope),
@@ -97,30 +96,91 @@ peer_gather_rows_kernel(PeerPtrs shards, int G, int64_t rows_total, int d4, cons
   }
 }
 
-// One peer's compact list: rows[0..*n_rows) ascending global ids (each at most once), vals[i,:].  A warp per slot.
-__global__ void __launch_bounds__(256)
-peer_fold_rows_kernel(const int32_t* __restrict__ rows, const float4* __restrict__ vals, const float* __restrict__ bias_vals,
-                      const int32_t* __restrict__ n_rows, int64_t cap, int rank, int G, int d4, float scale,
-                      float4* __restrict__ dense, float* __restrict__ dense_bias, int64_t shard_rows) {
+// ---- owner-side gradient fold ---------------------------------------------------------------------------
+// Every peer r publishes a compact list (rows_r[0..n_r) ascending unique GLOBAL ids, vals_r[i,:]).  The owner of
+// a row must add the peers' values in rank order (reproducible) without atomics and without a launch per peer:
+//   mark  posmap[r][local] = (stamp, i + 1) for every slot (r, i) this rank owns          (parallel, no conflicts)
+//   sum   the slot of the LOWEST peer holding a row is its leader: it walks the later peers' posmap entries,
+//         adds their value rows in rank order and OVERWRITES dense[local] once            (parallel, no RMW)
+// posmap entries carry a stamp that is constant during one fold and different for the next one (the barrier
+// epoch), so the map never needs clearing.
+struct FoldTable {
+  const int32_t* rows[kMaxPeers];
+  const float4* vals[kMaxPeers];
+  const int32_t* n_rows[kMaxPeers];
+  int64_t cap, shard_rows;
+  int d4;
+  unsigned long long* posmap;  // [G][shard_rows]
+  float4* dense;
+  int32_t* touched;            // optional [G * cap]: local rows written (for the next step's row-wise zeroing)
+  int32_t* n_touched;
+};
+
+struct FoldArgs {
+  FoldTable t[2];
+  int n_tables, rank, G;
+  float scale;
+  const uint32_t* stamp;
+};
+
+template <bool SUM>
+__global__ void __launch_bounds__(256) peer_fold_kernel(const FoldArgs a) {
+  const FoldTable& t = a.t[blockIdx.y];
+  const int r = blockIdx.z, G = a.G, rank = a.rank;
   const int lane = threadIdx.x & 31;
+  const unsigned long long stamp = static_cast<unsigned long long>(*a.stamp) << 32;
+  int64_t n = *t.n_rows[r];
+  n = n < t.cap ? n : t.cap;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  int64_t n = *n_rows;
-  n = n < cap ? n : cap;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
-    const int32_t g = rows[i];
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (!SUM) {
+    for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x); i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int32_t g = t.rows[r][i];
+      if (g < 0 || g % G != rank) continue;
+      const int64_t local = g / G;
+      if (local < t.shard_rows) t.posmap[r * t.shard_rows + local] = stamp | static_cast<unsigned long long>(i + 1);
+    }
+    return;
+  }
+  for (int64_t i = w0; i < n; i += nwarps) {
+    const int32_t g = t.rows[r][i];
     if (g < 0 || g % G != rank) continue;
     const int64_t local = g / G;
-    if (local >= shard_rows) continue;
-    if (dense != nullptr) {
-      for (int c = lane; c < d4; c += 32) {
-        const float4 v = ldg_row4(vals + i * d4 + c);
-        float4 a = dense[local * d4 + c];
-        fma4(a, scale, v);
-        dense[local * d4 + c] = a;
+    if (local >= t.shard_rows) continue;
+    bool leader = true;
+    for (int q = 0; q < r; ++q)
+      if ((t.posmap[q * t.shard_rows + local] >> 32 << 32) == stamp) leader = false;
+    if (!leader) continue;
+    int64_t slot[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+      slot[q] = -1;
+      if (q == r) slot[q] = i;
+      if (q > r && q < G) {
+        const unsigned long long e = t.posmap[q * t.shard_rows + local];
+        if ((e >> 32 << 32) == stamp) slot[q] = static_cast<int64_t>(e & 0xffffffffull) - 1;
       }
     }
-    if (dense_bias != nullptr && bias_vals != nullptr && lane == 0)
-      dense_bias[local] = fmaf(scale, bias_vals[i], dense_bias[local]);
+    for (int c = lane; c < t.d4; c += 32) {
+      float4 acc = zero4();
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q) {
+        if (slot[q] >= 0) {
+          const float4 v = ldg_row4(t.vals[q] + slot[q] * t.d4 + c);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+      }
+      acc.x *= a.scale;
+      acc.y *= a.scale;
+      acc.z *= a.scale;
+      acc.w *= a.scale;
+      t.dense[local * t.d4 + c] = acc;
+    }
+    if (t.touched != nullptr && lane == 0) t.touched[atomicAdd(t.n_touched, 1)] = static_cast<int32_t>(local);
   }
 }
 
@@ -237,20 +297,54 @@ extern "C" int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_
   return launch_status();
 }
 
-extern "C" int psb_peer_fold_rows(const int32_t* rows, const float* vals, const float* bias_vals, const int32_t* n_rows,
-                                  int64_t cap, int32_t rank, int32_t G, int64_t d, float scale, float* dense,
-                                  float* dense_bias, int64_t shard_rows, psb_stream_t stream) {
-  if (rows == nullptr || n_rows == nullptr || cap < 0 || G <= 0 || rank < 0 || rank >= G || shard_rows <= 0)
+extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tables, int32_t rank, int32_t G,
+                                   float scale, const uint32_t* stamp_dev, psb_stream_t stream) {
+  if (tables == nullptr || n_tables <= 0 || n_tables > 2 || G <= 0 || G > kMaxPeers || rank < 0 || rank >= G ||
+      stamp_dev == nullptr)
     return PSB_E_ARG;
-  if (dense != nullptr && vals == nullptr) return PSB_E_ARG;
-  if (d <= 0 || (d & 3) != 0 || d > 512) return PSB_E_DIM;
-  if (misaligned16(vals) || misaligned16(dense)) return PSB_E_ALIGN;
-  if (cap == 0) return PSB_OK;
+  FoldArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_tables = n_tables;
+  a.rank = rank;
+  a.G = G;
+  a.scale = scale;
+  a.stamp = stamp_dev;
+  int64_t cap_max = 0;
+  for (int k = 0; k < n_tables; ++k) {
+    const psb_fold_table_t& in = tables[k];
+    if (in.rows == nullptr || in.vals == nullptr || in.n_rows == nullptr || in.posmap == nullptr ||
+        in.dense == nullptr || in.cap <= 0 || in.shard_rows <= 0)
+      return PSB_E_ARG;
+    if (in.d <= 0 || (in.d & 3) != 0 || in.d > 512) return PSB_E_DIM;
+    if (misaligned16(in.dense)) return PSB_E_ALIGN;
+    FoldTable& t = a.t[k];
+    for (int r = 0; r < G; ++r) {
+      if (in.rows[r] == nullptr || in.vals[r] == nullptr || in.n_rows[r] == nullptr) return PSB_E_ARG;
+      if (misaligned16(in.vals[r])) return PSB_E_ALIGN;
+      t.rows[r] = in.rows[r];
+      t.vals[r] = reinterpret_cast<const float4*>(in.vals[r]);
+      t.n_rows[r] = in.n_rows[r];
+    }
+    t.cap = in.cap;
+    t.shard_rows = in.shard_rows;
+    t.d4 = static_cast<int>(in.d / 4);
+    t.posmap = reinterpret_cast<unsigned long long*>(in.posmap);
+    t.dense = reinterpret_cast<float4*>(in.dense);
+    t.touched = in.touched;
+    t.n_touched = in.n_touched;
+    cap_max = in.cap > cap_max ? in.cap : cap_max;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  PSB_PROF("peer_fold_rows_kernel", s);
-  peer_fold_rows_kernel<<<grid_for(cap, 8, 8), 256, 0, s>>>(rows, reinterpret_cast<const float4*>(vals), bias_vals, n_rows,
-                                                           cap, rank, G, static_cast<int>(d / 4), scale,
-                                                           reinterpret_cast<float4*>(dense), dense_bias, shard_rows);
+  int st;
+  {
+    dim3 grid(grid_for(cap_max, 256, 2), n_tables, G);
+    PSB_PROF("peer_fold_mark_kernel", s);
+    peer_fold_kernel<false><<<grid, 256, 0, s>>>(a);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  dim3 grid(grid_for(cap_max, 8, 2), n_tables, G);
+  PSB_PROF("peer_fold_sum_kernel", s);
+  peer_fold_kernel<true><<<grid, 256, 0, s>>>(a);
   return launch_status();
 }
 

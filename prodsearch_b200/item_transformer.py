@@ -420,8 +420,8 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
 
     def sync_fold(self):
         G = self.peer.world
-        self.item_table.fold(1.0 / G)
-        self.word_table.fold(1.0 / G)
+        from .peer import fold_tables
+        fold_tables([self.item_table, self.word_table], 1.0 / G)
         self._bucket.reduce()
         lib = _lib.load()
         shard = (_lib.AdamTensor * 2)(

@@ -11,7 +11,8 @@ other rank.  From then on the exchange steps are loads inside hand-written kerne
   push    the table's ``PeerGradSink`` runs the usual deterministic sort + segmented reduce over GLOBAL row
           ids into a peer-visible compact list (rows, values, count)
   fold    after a barrier every owner folds the slots it owns of each peer's list, peer by peer in rank order,
-          into its dense shard gradient (psb_peer_fold_rows): reproducible, no float atomics, no second sort
+          into its dense shard gradient (psb_peer_fold_lists: two launches whatever G is): reproducible, no
+          float atomics, no second sort
   dense   replicated parameters: one-shot all-reduce over the peers' flat buckets (psb_peer_allreduce)
 
 Nothing here synchronises with the host, so ``model(batch); backward; sync_grads; optim.step`` is captured
@@ -84,7 +85,7 @@ class PeerGroup(object):
         if self.world > _lib.PEER_MAX:
             raise RuntimeError("PeerGroup: at most %d ranks" % _lib.PEER_MAX)
         self.group = group
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._seq = 0
         self._opened = []
         self.flags = self.alloc(4 * _lib.PEER_MAX)
@@ -148,6 +149,17 @@ class PeerGroup(object):
                                       self.err.data_ptr(), int(self.timeout_cycles), stream_ptr()),
               "psb_peer_barrier")
 
+    def fold_stamp(self):
+        """Device pointer of a uint32 that is constant during one fold and new for the next: the barrier epoch
+        (two barriers separate consecutive folds); the simulated ranks, whose barrier is stream order, bump a
+        private counter instead."""
+        if self._sim is None and self.world > 1:
+            return self.epoch.data_ptr()
+        if not hasattr(self, "_stamp"):
+            self._stamp = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._stamp.add_(1)
+        return self._stamp.data_ptr()
+
     def check_errors(self):
         """Host-synchronising check of the barrier time-out flag."""
         e = int(self.err.item())
@@ -172,7 +184,7 @@ def try_create(group=None, device=None):
         ok = 0
         import sys
         sys.stderr.write("peer memory unavailable on rank %d: %s\n" % (dist.get_rank(group), ex))
-    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     t = torch.tensor([ok], dtype=torch.int32, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return pg if int(t.item()) == 1 else None
@@ -185,7 +197,7 @@ class PeerShardedTable(object):
         self.rows, self.d, self.peer, self.pad_idx = int(rows), int(d), peer, int(pad_idx)
         G, r = peer.world, peer.rank
         self.local_rows = (self.rows - r + G - 1) // G
-        self.shard = peer.alloc(max(self.local_rows, 1) * d * 4)
+        self.shard = peer.alloc(max((self.rows + G - 1) // G, 1) * d * 4)    # the same size on every rank
         w = self.shard.view(torch.float32, (self.local_rows, d))
         if full is not None:
             with torch.no_grad():
@@ -196,6 +208,7 @@ class PeerShardedTable(object):
         self.bias_grad = torch.zeros_like(bias) if bias is not None else None
         self._stage = None
         self._cap = 0
+        self._posmap = None
         if stage_cap:
             self._ensure_stage(stage_cap)
         self.sink = PeerGradSink(self)
@@ -254,16 +267,44 @@ class PeerShardedTable(object):
         return mini, outs, n
 
     def fold(self, scale):
-        """Owner side: shard gradient = scale * sum over peers (rank order) of the owned slots of their lists."""
-        self.grad.zero_()
-        lib = load()
+        fold_tables([self], scale)
+
+    def _fold_desc(self):
+        """psb_fold_table_t of this table; clears the rows the previous fold wrote."""
+        from . import ops
+        G = self.peer.world
+        if self._posmap is None:
+            self._posmap = torch.zeros(G * self.local_rows, dtype=torch.int64, device=self.weight.device)
+            self._rowwise_zero = self.grad.numel() * 4 > (64 << 20)     # big shard: clear touched rows, not a memset
+            if self._rowwise_zero:
+                self._touched = torch.zeros(G * self._cap, dtype=torch.int32, device=self.weight.device)
+                self._n_touched = torch.zeros(1, dtype=torch.int32, device=self.weight.device)
+        if self._rowwise_zero:
+            ops.zero_rows(self._touched, self._n_touched, self.d, self.grad, None)
+            self._n_touched.zero_()
+        else:
+            self.grad.zero_()
+        t = _lib.FoldTable()
         st = self._stage
-        for r in range(self.peer.world):
+        for r in range(G):
             base = st.ptrs[r]
-            check(lib.psb_peer_fold_rows(base + self._off_rows, base + self._off_vals, None, base, self._cap,
-                                         self.peer.rank, self.peer.world, self.d, float(scale), self.grad.data_ptr(),
-                                         None, self.local_rows, stream_ptr()), "psb_peer_fold_rows")
-        self.weight.grad = self.grad
+            t.rows[r], t.vals[r], t.n_rows[r] = base + self._off_rows, base + self._off_vals, base
+        t.cap, t.d, t.shard_rows = self._cap, self.d, self.local_rows
+        t.posmap, t.dense = self._posmap.data_ptr(), self.grad.data_ptr()
+        t.touched = self._touched.data_ptr() if self._rowwise_zero else None
+        t.n_touched = self._n_touched.data_ptr() if self._rowwise_zero else None
+        return t
+
+
+def fold_tables(tables, scale):
+    """Owner side, after the barrier: for up to two tables at once, shard gradient = scale * (rank-ordered sum over
+    the peers' compact lists of the rows this rank owns); two launches in total (psb_peer_fold_lists)."""
+    peer = tables[0].peer
+    arr = (_lib.FoldTable * len(tables))(*[t._fold_desc() for t in tables])
+    check(load().psb_peer_fold_lists(arr, len(tables), peer.rank, peer.world, float(scale), peer.fold_stamp(),
+                                     stream_ptr()), "psb_peer_fold_lists")
+    for t in tables:
+        t.weight.grad = t.grad
 
 
 class PeerGradSink(object):

@@ -98,7 +98,7 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     opt = build_optim(cfg, m)
     ref_opt = build_optim(cfg, ref)
     m.train()
-    wq = max(b.query_word_idxs.shape[1] for b, _, _ in batches)
+    wq = 12                      # synth.tem_batch draws at most 12 query words
 
     def padded(b):
         out = dev(b)
@@ -150,6 +150,9 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     ids_r, sc_r = ref.rank_catalog(q, k=100)
     assert torch.equal(ids, ids_r) and torch.allclose(sc, sc_r, rtol=1e-5, atol=1e-5)
     # ---- the whole multi-GPU step as one CUDA graph per rank
+    del loss, total, l           # drop the eager autograd graphs (their AccumulateGrad nodes live on this stream)
+    m.zero_grad()
+    ref.zero_grad()
     m.injected_negatives = None
     torch.manual_seed(100 + rank)
     graphed = GraphedTrainStep(m, opt, padded(b), pad_values={"query_word_idxs": V - 1, "u_item_idxs": P},
