@@ -318,7 +318,8 @@ int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors
                   double warmup_steps, int32_t norm_given, int64_t* step_dev, float* sqnorm_dev, void* workspace,
                   int64_t workspace_bytes, psb_stream_t stream);
 /* norm_given != 0: *sqnorm_dev already holds the GLOBAL squared gradient norm (row-sharded training: the
- * caller sums psb_grad_sqnorm of every rank's shard gradients and of the replicated ones) and is used as is. */
+ * caller sums psb_grad_sqnorm of every rank's shard gradients and of the replicated ones) and is used as is;
+ * norm_given == 2: *step_dev has been advanced by the caller as well (psb_peer_sum_sqnorm). */
 
 /* *sqnorm_out (device) = sum over the tensors' gradients of |g|^2, fixed summation order.  Workspace as for
  * psb_adam_step. */
@@ -385,6 +386,12 @@ int psb_peer_fold_lists(const psb_fold_table_t* tables /* host */, int32_t n_tab
  * every rank computes the identical sum).  bufs: HOST array of G device pointers (peer memory). */
 int psb_peer_allreduce(const void* const* bufs, int32_t G, int64_t n, float scale, float* out,
                        psb_stream_t stream);
+
+/* *sqnorm_out = sum_r *slots[r] (r ascending): the GLOBAL squared gradient norm from the partial norms every rank
+ * published (psb_grad_sqnorm of its shard gradients; rank 0 adds the replicated ones).  step_dev != NULL: the
+ * optimizer's step counter is advanced here, for psb_adam_step(norm_given = 2). */
+int psb_peer_sum_sqnorm(const void* const* slots, int32_t G, float* sqnorm_out, int64_t* step_dev,
+                        psb_stream_t stream);
 
 #ifdef __cplusplus
 }

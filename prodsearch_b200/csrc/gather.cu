@@ -236,6 +236,7 @@ fs_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ outv
 #pragma unroll
   for (int c = 0; c < 4; ++c) acc[c] = zero4();
   float accb = 0.f;
+#pragma unroll 4   // four rows of independent loads in flight; the additions keep their ascending-i order
   for (int64_t i = lo; i < hi; ++i) {
     const float o = outv[i * d + j];
     const float dz = grad_out[i * d + j] * (1.f - o * o);

@@ -196,7 +196,9 @@ extern "C" int psb_adam_step(const psb_adam_tensor_t* tensors, int32_t n_tensors
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   int st;
-  if (norm_given) {
+  if (norm_given == 2) {
+    // norm and step counter were both written by the caller
+  } else if (norm_given) {
     PSB_PROF("bump_step_kernel", s);
     bump_step_kernel<<<1, 1, 0, s>>>(step_dev);
     if ((st = launch_status()) != PSB_OK) return st;

@@ -210,6 +210,15 @@ peer_allreduce_kernel(PeerPtrs bufs, int G, int64_t n, float scale, float* __res
   }
 }
 
+// total squared gradient norm = sum over ranks of the published partial norms (rank order); optionally advances
+// the optimizer's step counter so psb_adam_step(norm_given = 2) needs no launch of its own for it.
+__global__ void peer_sum_sqnorm_kernel(PeerPtrs slots, int G, float* __restrict__ out, int64_t* __restrict__ step) {
+  float acc = 0.f;
+  for (int r = 0; r < G; ++r) acc += *static_cast<const float*>(slots.p[r]);
+  *out = acc;
+  if (step != nullptr) *step += 1;
+}
+
 }  // namespace psb
 
 using namespace psb;
@@ -361,5 +370,17 @@ extern "C" int psb_peer_allreduce(const void* const* bufs, int32_t G, int64_t n,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("peer_allreduce_kernel", s);
   peer_allreduce_kernel<<<grid_for(n, 256 * 4, 4), 256, 0, s>>>(B, G, n, scale, out);
+  return launch_status();
+}
+
+extern "C" int psb_peer_sum_sqnorm(const void* const* slots, int32_t G, float* sqnorm_out, int64_t* step_dev,
+                                   psb_stream_t stream) {
+  PeerPtrs S;
+  int st = fill_ptrs(&S, slots, G);
+  if (st != PSB_OK) return st;
+  if (sqnorm_out == nullptr) return PSB_E_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("peer_sum_sqnorm_kernel", s);
+  peer_sum_sqnorm_kernel<<<1, 1, 0, s>>>(S, G, sqnorm_out, step_dev);
   return launch_status();
 }

@@ -200,6 +200,150 @@ small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, 
 }
 
 // ------------------------------------------------------------------------------------
+// Small regime, small table (n_total <= 16384 slots AND table_rows + 1 <= 48128 bins: every table of the
+// Amazon-shaped TEM step): counting sort with one shared-memory bin per destination row instead of radix passes.
+//   bins   shared-memory histogram of the keys (integer atomics: order-free)
+//   scan   exclusive scan of the bins, packed with the running count of non-empty bins -> segment table
+//   place  every slot takes a position inside its row's run (atomic cursor: arbitrary order within the run)
+//   rank   the order inside a run is made canonical again: a slot's final position is the number of slots of
+//          its run with a smaller slot number, so the sorted list is exactly the stable sort's -- the
+//          reduction order, and with it every bit of the gradient, is independent of the atomics' timing
+// Same outputs as small_sort_segments_kernel.  Dropped slots (sentinel key) land behind the valid ones.
+// ------------------------------------------------------------------------------------
+constexpr int kCsMaxPer = 33;      // bins per thread (odd: conflict-free strided scan); 33 * 1024 = 33792 bins
+constexpr int kCsLongMin = 33;     // runs at least this long are ordered by the bitmap path
+constexpr int kCsMaxLong = kSmallCap / kCsLongMin + 1;
+constexpr int kCsBitmaps = 16;     // warps 0..15 each own a 16384-bit bitmap + 512 prefix counts
+
+__global__ void __launch_bounds__(kSmallNT, 1)
+count_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, int64_t table_rows, int64_t drop_idx, int per,
+                           uint32_t* __restrict__ sorted_slots, uint32_t* __restrict__ sorted_keys,
+                           int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows,
+                           int32_t* __restrict__ n_unique) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbins = per * kSmallNT;
+  uint32_t* bins = reinterpret_cast<uint32_t*>(smem_raw);                        // [nbins]
+  uint32_t* bitmap = bins + nbins;                                               // [kCsBitmaps][512]
+  uint32_t* long_key = bitmap + kCsBitmaps * 512;                                // [kCsMaxLong]
+  unsigned short* sv = reinterpret_cast<unsigned short*>(long_key + kCsMaxLong + 3);   // [kSmallCap]
+  unsigned short* pref = sv + kSmallCap;                                         // [kCsBitmaps][512]
+  int* scan_sm = reinterpret_cast<int*>(pref + kCsBitmaps * 512);                // [32]
+  int* n_long = scan_sm + 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t sentinel = static_cast<uint32_t>(table_rows);
+  {
+    uint4* b4 = reinterpret_cast<uint4*>(bins);
+    for (int i = threadIdx.x; i < nbins / 4; i += kSmallNT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) *n_long = 0;
+  }
+  __syncthreads();
+  uint32_t key[kSmallIPT];
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    const int p = r * kSmallNT + threadIdx.x;
+    key[r] = 0xffffffffu;
+    if (p < n_total) key[r] = make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx);
+  }
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r)
+    if (key[r] != 0xffffffffu) atomicAdd(&bins[key[r]], 1u);
+  __syncthreads();
+  // packed exclusive scan: low 16 bits = slots before the bin, high 16 bits = non-empty bins before it
+  const int b0 = threadIdx.x * per;
+  uint32_t mine = 0;
+  for (int j = 0; j < per; ++j) {
+    const uint32_t c = bins[b0 + j];
+    mine += c + ((c != 0u && static_cast<uint32_t>(b0 + j) != sentinel) ? 0x10000u : 0u);
+  }
+  int total = 0;
+  uint32_t run = static_cast<uint32_t>(block_excl_scan<kSmallNT>(static_cast<int>(mine), scan_sm, &total));
+  for (int j = 0; j < per; ++j) {
+    const uint32_t b = static_cast<uint32_t>(b0 + j);
+    const uint32_t c = bins[b];
+    bins[b] = run;
+    if (b == sentinel) seg_start[static_cast<uint32_t>(total) >> 16] = static_cast<int32_t>(run & 0xffffu);  // end marker
+    if (c != 0u && b != sentinel) {
+      seg_start[run >> 16] = static_cast<int32_t>(run & 0xffffu);
+      unique_rows[run >> 16] = static_cast<int32_t>(b);
+      if (c >= static_cast<uint32_t>(kCsLongMin)) long_key[atomicAdd(n_long, 1)] = b;
+      run += 0x10000u;
+    }
+    run += c;
+  }
+  if (threadIdx.x == 0) *n_unique = static_cast<int32_t>(static_cast<uint32_t>(total) >> 16);
+  __syncthreads();
+  int pos[kSmallIPT];
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    pos[r] = -1;
+    if (key[r] != 0xffffffffu) {
+      pos[r] = static_cast<int>(atomicAdd(&bins[key[r]], 1u) & 0xffffu);
+      sv[pos[r]] = static_cast<unsigned short>(r * kSmallNT + threadIdx.x);
+    }
+  }
+  __syncthreads();
+  // short runs (and the dropped slots): the owner of a slot counts the smaller slot numbers of its run
+#pragma unroll
+  for (int r = 0; r < kSmallIPT; ++r) {
+    const int p = r * kSmallNT + threadIdx.x;
+    if (p >= n_total) continue;
+    const uint32_t k = key[r];
+    int out = pos[r];
+    if (k != sentinel) {
+      const int end = static_cast<int>(bins[k] & 0xffffu);
+      const int start = k == 0u ? 0 : static_cast<int>(bins[k - 1] & 0xffffu);
+      if (end - start >= kCsLongMin) continue;
+      int rank = 0;
+      for (int q = start; q < end; ++q) rank += sv[q] < static_cast<unsigned short>(p) ? 1 : 0;
+      out = start + rank;
+    }
+    sorted_slots[out] = static_cast<uint32_t>(p);
+    sorted_keys[out] = k;
+  }
+  // long runs: one warp per run marks its slot numbers in a bitmap; rank = number of set bits below
+  if (wid < kCsBitmaps) {
+    uint32_t* bm = bitmap + wid * 512;
+    unsigned short* pf = pref + wid * 512;
+    const int nl = *n_long;
+    for (int li = wid; li < nl; li += kCsBitmaps) {
+      const uint32_t k = long_key[li];
+      const int end = static_cast<int>(bins[k] & 0xffffu);
+      const int start = k == 0u ? 0 : static_cast<int>(bins[k - 1] & 0xffffu);
+      for (int w = lane; w < 512; w += 32) bm[w] = 0u;
+      __syncwarp();
+      for (int q = start + lane; q < end; q += 32) {
+        const uint32_t v = sv[q];
+        atomicOr(&bm[v >> 5], 1u << (v & 31u));
+      }
+      __syncwarp();
+      int cnt = 0;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) cnt += __popc(bm[lane * 16 + w]);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int runc = incl - cnt;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        pf[lane * 16 + w] = static_cast<unsigned short>(runc);
+        runc += __popc(bm[lane * 16 + w]);
+      }
+      __syncwarp();
+      for (int q = start + lane; q < end; q += 32) {
+        const uint32_t v = sv[q];
+        const int rank = pf[v >> 5] + __popc(bm[v >> 5] & ((1u << (v & 31u)) - 1u));
+        sorted_slots[start + rank] = v;
+        sorted_keys[start + rank] = k;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Large regime: multi-CTA radix sort.
 // ------------------------------------------------------------------------------------
 constexpr int kNT = 256;
@@ -638,7 +782,25 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   const uint32_t* sorted_keys = nullptr;
   int st;
 
-  if (n_total <= kSmallCap) {
+  const int64_t cs_per = ((table_rows + 1 + kSmallNT - 1) / kSmallNT) | 1;   // odd number of bins per thread
+  if (n_total <= kSmallCap && cs_per <= kCsMaxPer) {
+    static size_t attr_smem = 0;
+    const size_t smem = static_cast<size_t>(cs_per) * kSmallNT * 4 + kCsBitmaps * 512 * 4 + (kCsMaxLong + 3) * 4 +
+                        static_cast<size_t>(kSmallCap) * 2 + kCsBitmaps * 512 * 2 + 33 * 4;
+    if (smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(count_sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_smem = smem;
+    }
+    PSB_PROF("count_sort_segments_kernel", s);
+    count_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
+                                                         static_cast<int>(cs_per), vals_a, keys_a, seg_start,
+                                                         unique_rows, n_unique);
+    if ((st = launch_status()) != PSB_OK) return st;
+    sorted_slots = vals_a;
+    sorted_keys = keys_a;
+  } else if (n_total <= kSmallCap) {
     static bool attr_set = false;
     const size_t smem = static_cast<size_t>(kSmallCap) * 8 + (kSmallNT / 32) * 256 * 4 + 256 * 4 + 32 * 4;
     if (!attr_set) {

@@ -423,22 +423,23 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         from .peer import fold_tables
         fold_tables([self.item_table, self.word_table], 1.0 / G)
         self._bucket.reduce()
+        # partial |g|^2 of this rank: its two shard gradients; rank 0 adds the (replicated, identical) dense bucket
         lib = _lib.load()
-        shard = (_lib.AdamTensor * 2)(
+        n = 3 if self.peer.rank == 0 else 2
+        arr = (_lib.AdamTensor * 3)(
             _lib.AdamTensor(None, self.item_table.grad.data_ptr(), None, None, self.item_table.grad.numel()),
-            _lib.AdamTensor(None, self.word_table.grad.data_ptr(), None, None, self.word_table.grad.numel()))
-        dense = (_lib.AdamTensor * 1)(_lib.AdamTensor(None, self._bucket.red.data_ptr(), None, None, self._bucket.n))
-        wb = max(int(lib.psb_adam_workspace_bytes(shard, 2)), int(lib.psb_adam_workspace_bytes(dense, 1)))
+            _lib.AdamTensor(None, self.word_table.grad.data_ptr(), None, None, self.word_table.grad.numel()),
+            _lib.AdamTensor(None, self._bucket.red.data_ptr(), None, None, self._bucket.n))
+        wb = int(lib.psb_adam_workspace_bytes(arr, n))
         if self._norm_ws is None or self._norm_ws.numel() < wb:
             self._norm_ws = torch.empty(wb, dtype=torch.uint8, device=self.peer.device)
-        _lib.check(lib.psb_grad_sqnorm(shard, 2, self._sq_local.data_ptr(), self._norm_ws.data_ptr(), wb,
-                                       _lib.stream_ptr()), "psb_grad_sqnorm")
-        _lib.check(lib.psb_grad_sqnorm(dense, 1, self._sq_dense.data_ptr(), self._norm_ws.data_ptr(), wb,
+        _lib.check(lib.psb_grad_sqnorm(arr, n, self._sq_local.data_ptr(), self._norm_ws.data_ptr(), wb,
                                        _lib.stream_ptr()), "psb_grad_sqnorm")
 
     def sync_norm(self, optim):
-        self.peer.allreduce(self._sq, 4, self._sq_total, scale=1.0)
-        getattr(optim, "optimizer", optim).set_global_sqnorm(self._sq_total[:1] + self._sq_dense)
+        sq, step = getattr(optim, "optimizer", optim).global_norm_slots(self.peer.device)
+        _lib.check(_lib.load().psb_peer_sum_sqnorm(self._sq.ptr_array(), self.peer.world, sq.data_ptr(), step.data_ptr(),
+                                                   _lib.stream_ptr()), "psb_peer_sum_sqnorm")
 
     # ---- evaluation -----------------------------------------------------------------------------------------
     def encode_queries(self, query_word_idxs, u_item_idxs, copies=1, hist=None):

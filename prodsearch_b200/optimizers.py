@@ -24,7 +24,7 @@ class FusedAdam(object):
         self._step_dev = None
         self._sqnorm = None
         self._ws = None
-        self._norm_given = False
+        self._norm_given = 0
 
     def _ensure(self, dev):
         if self._step_dev is None:
@@ -43,7 +43,13 @@ class FusedAdam(object):
         rank's parameters are only a shard) for the next ``step``.  Stream-ordered copy, CUDA-graph safe."""
         self._ensure(sq.device)
         self._sqnorm.copy_(sq.reshape(1))
-        self._norm_given = True
+        self._norm_given = 1
+
+    def global_norm_slots(self, device):
+        """(sqnorm, step) device tensors a caller fills itself (psb_peer_sum_sqnorm) for the next ``step``."""
+        self._ensure(device)
+        self._norm_given = 2
+        return self._sqnorm, self._step_dev
 
     @property
     def total_norm(self):
@@ -79,10 +85,10 @@ class FusedAdam(object):
             ev[0].record()
         _lib.check(lib.psb_adam_step(arr, len(live), float(g["lr"]), float(b1), float(b2), float(g["eps"]),
                                      float(g["weight_decay"]), float(max_grad_norm or 0.0), 1 if noam else 0,
-                                     float(warmup_steps), 1 if self._norm_given else 0, self._step_dev.data_ptr(),
+                                     float(warmup_steps), int(self._norm_given), self._step_dev.data_ptr(),
                                      self._sqnorm.data_ptr(),
                                      self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()), "psb_adam_step")
-        self._norm_given = False
+        self._norm_given = 0
         if ev is not None:
             ev[1].record()
             ops.PROFILE.setdefault("adam_step", []).append(ev)

@@ -256,6 +256,24 @@ def test_scatter_reduce_vs_index_add(ops, n, rows, d):
     assert float(dense.abs().sum()) == 0.0 and float(dense_b.abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("n,rows", [(10_000, 18_001), (7_000, 32_000), (16_384, 50), (3, 33_000)])
+def test_count_sort_path_equals_radix_path_bitwise(ops, n, rows):
+    """Small tables take the shared-memory counting sort (one bin per row), larger ones the radix sort: both must
+    produce THE stable order, so the reduced rows agree bit for bit (declaring more rows than the indices use
+    switches the same data to the radix path)."""
+    g = torch.Generator().manual_seed(n * 31 + rows)
+    idx = (torch.rand(n, generator=g) ** 4 * (rows - 1)).long()          # heavy head: runs of hundreds of slots
+    idx[::13] = rows - 1                                                  # dropped
+    src = torch.randn(n, 128, generator=g)
+    scale = torch.randn(n, generator=g)
+    c = [ops.make_contrib(dev(idx), dev(src), scale=dev(scale), to_bias=True)]
+    u1, r1, b1, n1 = ops.scatter_reduce(c, rows, 128, drop_idx=rows - 1, want_bias=True)
+    u2, r2, b2, n2 = ops.scatter_reduce(c, 1_000_000, 128, drop_idx=rows - 1, want_bias=True)
+    k = int(n1.item())
+    assert k == int(n2.item()) and torch.equal(u1[:k], u2[:k])
+    assert torch.equal(r1[:k], r2[:k]) and torch.equal(b1[:k], b2[:k])
+
+
 def test_scatter_reduce_all_dropped_and_single(ops):
     idx = torch.full((50,), 9, dtype=torch.int64)
     src = torch.randn(50, 128)
