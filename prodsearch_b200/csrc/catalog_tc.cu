@@ -330,14 +330,42 @@ __device__ float block_kth_largest(const float* vals, int n, int k, int* hist /*
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int run = 0, b = 255;
-      for (; b > 0; --b) {
-        if (run + hist[b] >= need) break;
-        run += hist[b];
+    if (threadIdx.x < 32) {
+      // bins are walked from 255 down until `need` entries are covered; lane l owns the 8 bins 255-8l .. 248-8l
+      const int lane = threadIdx.x;
+      int c[8], mine = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        c[u] = hist[255 - (lane * 8 + u)];
+        mine += c[u];
       }
-      sh[0] = static_cast<uint32_t>(b);
-      sh[1] = static_cast<uint32_t>(need - run);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int before = incl - mine;
+      const unsigned hit = __ballot_sync(kFull, before < need && incl >= need);
+      const int total = __shfl_sync(kFull, incl, 31);
+      if (hit == 0u) {          // fewer than `need` entries above bin 0: the scalar walk stops at bin 0
+        if (lane == 31) {
+          sh[0] = 0u;
+          sh[1] = static_cast<uint32_t>(need - (total - c[7]));
+        }
+      } else if (lane == __ffs(hit) - 1) {
+        int run = before, u = 0;
+        for (; u < 7; ++u) {
+          if (run + c[u] >= need) break;
+          run += c[u];
+        }
+        int b = 255 - (lane * 8 + u);
+        if (b == 0) {           // bin 0 is never "selected by break": same arithmetic as the scalar walk
+          run = total - c[7];
+        }
+        sh[0] = static_cast<uint32_t>(b);
+        sh[1] = static_cast<uint32_t>(need - run);
+      }
     }
     __syncthreads();
     prefix |= sh[0] << shift;
@@ -353,7 +381,7 @@ __device__ float block_kth_largest(const float* vals, int n, int k, int* hist /*
 // pilot scores -> thr[row] = kth - 2 eps_row ; eps_row = 2^-8 |q_row| max|e|
 __global__ void __launch_bounds__(256)
 pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int k, const float* __restrict__ Q, int d,
-                       const float* __restrict__ max_sq, float* __restrict__ thr, float* __restrict__ eps) {
+                       const float* __restrict__ max_sq, float* __restrict__ thr, float* __restrict__ eps, int stage) {
   __shared__ int hist[256];
   __shared__ uint32_t sh[2];
   __shared__ float red[8];
@@ -372,6 +400,16 @@ pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int 
   const float* vals = dump + static_cast<int64_t>(row) * ld;
   // count finite entries: with fewer than k valid pilot items nothing can be pruned
   int valid = 0;
+  if (stage) {   // the pilot scores fit in shared memory: read them once, select there
+    extern __shared__ __align__(16) unsigned char thr_raw[];
+    float* sv = reinterpret_cast<float*>(thr_raw);
+    for (int i = threadIdx.x * 4; i < n_pilot; i += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(vals + i);   // ld and n_pilot are multiples of 128
+      *reinterpret_cast<float4*>(sv + i) = v;
+      valid += (v.x > -INFINITY ? 1 : 0) + (v.y > -INFINITY ? 1 : 0) + (v.z > -INFINITY ? 1 : 0) + (v.w > -INFINITY ? 1 : 0);
+    }
+    vals = sv;
+  } else
   for (int i = threadIdx.x; i < n_pilot; i += 256) valid += vals[i] > -INFINITY ? 1 : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(kFull, valid, o);
@@ -413,33 +451,70 @@ final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict_
   const int row = blockIdx.x;
   // list sizes -> exclusive offsets (n_slices here = number of lists of this row, <= kMaxLists)
   for (int l = threadIdx.x; l < n_slices; l += 256) offs[l + 1] = cand_n[static_cast<int64_t>(row) * n_slices + l];
+  if (threadIdx.x == 0) offs[0] = 0;
   for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0, over = 0;
-    offs[0] = 0;
-    for (int l = 0; l < n_slices; ++l) {
-      const int c = offs[l + 1];
-      over |= c > cap;
-      tot += min(c, cap);
-      offs[l + 1] = tot;
+  // exclusive scan of the clamped list sizes (n_slices <= kMaxLists = 592 lists: 3 per thread)
+  {
+    constexpr int kPer = (kMaxLists + 255) / 256;
+    int c[kPer], mine = 0, over = 0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int l = threadIdx.x * kPer + u;
+      c[u] = l < n_slices ? offs[l + 1] : 0;
+      over |= c[u] > cap;
+      c[u] = min(c[u], cap);
+      mine += c[u];
     }
-    s_total = tot;
-    s_over = over | (tot > kFinalCap);
-    s_keep = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) hist[wid] = incl;
+    over = __any_sync(kFull, over) ? 1 : 0;
+    if (lane == 0) hist[8 + wid] = over;
+    __syncthreads();
+    int base = 0, any_over = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < wid) base += hist[w];
+      any_over |= hist[8 + w];
+    }
+    int run = base + incl - mine;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int l = threadIdx.x * kPer + u;
+      if (l < n_slices) offs[l] = run;
+      run += c[u];
+    }
+    if (threadIdx.x == 255) {
+      offs[n_slices] = run;
+      s_total = run;
+      s_over = any_over | (run > kFinalCap);
+      s_keep = 0;
+    }
   }
   __syncthreads();
   if (s_over) {
     if (threadIdx.x == 0) fallback_flag[row] = 1;
     return;
   }
-  // gather the lists, one warp per list (order irrelevant: the final ordering is a strict total order)
-  for (int l = threadIdx.x >> 5; l < n_slices; l += 8) {
-    const int base = offs[l], c = offs[l + 1] - offs[l];
-    const int64_t src = (static_cast<int64_t>(row) * n_slices + l) * cap;
-    for (int i = threadIdx.x & 31; i < c; i += 32) {
-      cs[base + i] = cand_s[src + i];
-      ci[base + i] = cand_i[src + i];
+  // gather the lists flat: candidate i belongs to the list whose offset range holds i (binary search), so all
+  // loads of a thread are independent (order irrelevant: the final ordering is a strict total order)
+  {
+    const int tot = s_total;
+    for (int i = threadIdx.x; i < tot; i += 256) {
+      int a = 0, b = n_slices;           // largest l with offs[l] <= i
+      while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (offs[mid] <= i) a = mid; else b = mid;
+      }
+      const int64_t src = (static_cast<int64_t>(row) * n_slices + a) * cap + (i - offs[a]);
+      cs[i] = cand_s[src];
+      ci[i] = cand_i[src];
     }
   }
   __syncthreads();
@@ -664,6 +739,8 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
     cudaError_t e1 = cudaFuncSetAttribute(tc_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaError_t e2 = cudaFuncSetAttribute(tc_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaError_t e3 = cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e3 == cudaSuccess)
+      e3 = cudaFuncSetAttribute(pilot_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return static_cast<int>(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
     attr_done = true;
   }
@@ -699,8 +776,10 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
   }
   // 2. thresholds
   PSB_PROF("pilot_threshold_kernel", s);
-  pilot_threshold_kernel<<<static_cast<int>(m), 256, 0, s>>>(dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries,
-                                                             static_cast<int>(d), max_row_sqnorm, thr, eps);
+  const bool stage_pilot = static_cast<size_t>(P.ld_dump) * 4 <= 160 * 1024;
+  pilot_threshold_kernel<<<static_cast<int>(m), 256, stage_pilot ? static_cast<size_t>(P.ld_dump) * 4 : 0, s>>>(
+      dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries, static_cast<int>(d), max_row_sqnorm, thr, eps,
+      stage_pilot ? 1 : 0);
   if ((st = launch_status()) != PSB_OK) return st;
   // 3. main pass
   P.tile_step = 1;

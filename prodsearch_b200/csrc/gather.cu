@@ -181,6 +181,7 @@ token_weights_kernel(const int64_t* __restrict__ idx, int64_t n, int w, int64_t 
 // Block roles: blockIdx.x < rows_blocks -> grad_mean rows (one warp per row);
 // the remaining d blocks -> grad_weight[j,:] / grad_bias[j] (8 warps split i into 8
 // contiguous ranges, partials combined in warp order: deterministic for a given n).
+template <int C>
 __global__ void __launch_bounds__(256)
 fs_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ outv,
               const float4* __restrict__ mean, const float4* __restrict__ keep_scale,
@@ -194,9 +195,9 @@ fs_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ outv
   __shared__ float part_b[8];
   if (static_cast<int>(blockIdx.x) < rows_blocks) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + wid; i < n; i += static_cast<int64_t>(rows_blocks) * 8) {
-      float4 acc[4];
+      float4 acc[C];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = zero4();
+      for (int c = 0; c < C; ++c) acc[c] = zero4();
       for (int j0 = 0; j0 < d; j0 += 32) {
         const int j = j0 + lane;
         float dz = 0.f;
@@ -205,17 +206,30 @@ fs_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ outv
           dz = grad_out[i * d + j] * (1.f - o * o);
         }
         const int nj = min(32, d - j0);
-        for (int jj = 0; jj < nj; ++jj) {
-          const float s = __shfl_sync(kFull, dz, jj);
+        // 8 rows of W in flight per batch (the loads do not depend on the running sums)
+        for (int jb = 0; jb < nj; jb += 8) {
+          float4 w[8][C];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = lane + 32 * c;
-            if (col < d4) fma4(acc[c], s, __ldg(W + static_cast<int64_t>(j0 + jj) * d4 + col));
+          for (int u = 0; u < 8; ++u) {
+            const bool ok = jb + u < nj;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const int col = lane + 32 * c;
+              w[u][c] = (ok && col < d4) ? __ldg(W + static_cast<int64_t>(j0 + jb + u) * d4 + col) : zero4();
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float sdz = __shfl_sync(kFull, dz, (jb + u) & 31);
+            if (jb + u < nj) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) fma4(acc[c], sdz, w[u][c]);
+            }
           }
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < C; ++c) {
         const int col = lane + 32 * c;
         if (col < d4) {
           if (keep_scale != nullptr) {
@@ -232,23 +246,44 @@ fs_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ outv
   const int64_t per = (n + 7) / 8;
   const int64_t lo = per * wid;
   const int64_t hi = (lo + per < n) ? lo + per : n;
-  float4 acc[4];
+  float4 acc[C];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) acc[c] = zero4();
+  for (int c = 0; c < C; ++c) acc[c] = zero4();
   float accb = 0.f;
-#pragma unroll 4   // four rows of independent loads in flight; the additions keep their ascending-i order
-  for (int64_t i = lo; i < hi; ++i) {
-    const float o = outv[i * d + j];
-    const float dz = grad_out[i * d + j] * (1.f - o * o);
-    accb += dz;
+  // 32 rows per round: lane l computes dz of row i0 + l (independent loads), then the rows are consumed in
+  // ascending order -- the summation order of a scalar loop -- with 8 rows of `mean` in flight
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    const int64_t il = i0 + lane;
+    float dzl = 0.f;
+    if (il < hi) {
+      const float o = outv[il * d + j];
+      dzl = grad_out[il * d + j] * (1.f - o * o);
+    }
+    const int cnt = static_cast<int>(hi - i0 < 32 ? hi - i0 : 32);
+    for (int u0 = 0; u0 < cnt; u0 += 8) {
+      float4 m[8][C];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col = lane + 32 * c;
-      if (col < d4) fma4(acc[c], dz, mean[i * d4 + col]);
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = u0 + u < cnt;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = lane + 32 * c;
+          m[u][c] = (ok && col < d4) ? mean[(i0 + u0 + u) * d4 + col] : zero4();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float dz = __shfl_sync(kFull, dzl, (u0 + u) & 31);
+        if (u0 + u < cnt) {
+          accb += dz;
+#pragma unroll
+          for (int c = 0; c < C; ++c) fma4(acc[c], dz, m[u][c]);
+        }
+      }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < C; ++c) {
     const int col = lane + 32 * c;
     if (col < d4) part[wid][col] = acc[c];
   }
@@ -375,10 +410,16 @@ extern "C" int psb_fs_bwd(const float* grad_out, const float* out, const float* 
       misaligned16(grad_mean))
     return PSB_E_ALIGN;
   const int rows_blocks = grid_for(n, 8, 4);
-  PSB_PROF("fs_bwd_kernel", static_cast<cudaStream_t>(stream));
-  fs_bwd_kernel<<<rows_blocks + static_cast<int>(d), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad_out, out, reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(keep_scale),
-      reinterpret_cast<const float4*>(fs_weight), n, static_cast<int>(d / 4), rows_blocks,
-      reinterpret_cast<float4*>(grad_weight), grad_bias, reinterpret_cast<float4*>(grad_mean));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("fs_bwd_kernel", s);
+#define PSB_FS_LAUNCH(C)                                                                                            \
+  fs_bwd_kernel<C><<<rows_blocks + static_cast<int>(d), 256, 0, s>>>(                                               \
+      grad_out, out, reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(keep_scale),            \
+      reinterpret_cast<const float4*>(fs_weight), n, static_cast<int>(d / 4), rows_blocks,                          \
+      reinterpret_cast<float4*>(grad_weight), grad_bias, reinterpret_cast<float4*>(grad_mean))
+  if (d <= 128) PSB_FS_LAUNCH(1);
+  else if (d <= 256) PSB_FS_LAUNCH(2);
+  else PSB_FS_LAUNCH(4);
+#undef PSB_FS_LAUNCH
   return launch_status();
 }

@@ -33,7 +33,12 @@ for n in sizes:
             if mode == _lib.TOPK_EXACT and (n > 2_000_000 or m > 384):
                 continue
             sec = timed(lambda: ops.catalog_topk(q, table, 100, n_items=n, mode=mode, max_row_sqnorm=norm))
-            print(json.dumps({"n_items": n, "m": m, "mode": name, "ms": round(sec * 1e3, 4),
+            _lib.profile_enable(True)          # per-kernel split of the same call (CUDA events per launch)
+            for _ in range(3):
+                ops.catalog_topk(q, table, 100, n_items=n, mode=mode, max_row_sqnorm=norm)
+            split = {k_: round(v[1] / 3 * 1e3, 1) for k_, v in _lib.profile_dump().items()}
+            _lib.profile_enable(False)
+            print(json.dumps({"n_items": n, "m": m, "mode": name, "ms": round(sec * 1e3, 4), "kernel_us": split,
                               "queries_per_s": round(m / sec, 1), "tflops": round(2.0 * m * n * d / sec / 1e12, 2),
                               "table_GBps": round(n * d * 4 / sec / 1e9, 1)}))
     del table
