@@ -200,6 +200,7 @@ int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows,
  *       PSB_TOPK_TC     tcgen05 TF32 shortlist + exact fp32 rescoring (same result) */
 #define PSB_TOPK_EXACT 0
 #define PSB_TOPK_TC 1
+#define PSB_TOPK_TC16 2 /* workspace query only: psb_catalog_topk_f16 takes the prepared fp16 copy */
 
 int64_t psb_catalog_topk_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k, int32_t mode);
 int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_t n_items,
@@ -212,6 +213,21 @@ int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_
  * (evaluation); NULL there makes the call compute it itself. */
 int psb_table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out,
                              psb_stream_t stream);
+
+/* fp16 shortlist on a half-precision COPY of a static (evaluation) table -- same results as the exact mode.
+ * psb_catalog_prepare_f16 converts table[0..n_items) to fp16 (round to nearest) into table_f16 [n_items, d] and
+ * writes stats[0] = max_r |e_r|^2, stats[1] = max_r |e_r - half(e_r)|^2, stats[2] = 1 if a value does not fit
+ * fp16 (stats: 4 device floats, 16-byte aligned).  psb_catalog_topk_f16 then shortlists with tcgen05 kind::f16
+ * (half the table bytes per pass, up to 512 queries per pass over the table), bounds the shortlist error from the
+ * MEASURED quantisation errors, and rescoring the survivors exactly in fp32 from `table` as PSB_TOPK_TC does.
+ * A table that overflows fp16 (stats[2] != 0) makes every row take the exact streaming fallback: still correct,
+ * slow -- callers use PSB_TOPK_TC for such tables.  Workspace: psb_catalog_topk_workspace_bytes(mode TC16). */
+int psb_catalog_prepare_f16(const float* table, int64_t n_items, int64_t d, void* table_f16, float* stats,
+                            psb_stream_t stream);
+int psb_catalog_topk_f16(const float* queries, int64_t m, const float* table, const void* table_f16,
+                         const float* stats, int64_t n_items, int64_t d, const float* bias, int64_t k,
+                         int64_t id_base, int64_t id_stride, void* workspace, int64_t workspace_bytes,
+                         int64_t* out_ids, float* out_scores, psb_stream_t stream);
 
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */

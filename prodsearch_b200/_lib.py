@@ -16,7 +16,7 @@ c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctyp
 c_f64 = ctypes.c_double
 
 MAX_CONTRIBS = 8
-TOPK_EXACT, TOPK_TC = 0, 1
+TOPK_EXACT, TOPK_TC, TOPK_TC16 = 0, 1, 2
 
 
 class Contrib(ctypes.Structure):
@@ -82,6 +82,9 @@ SIGNATURES = {
     "psb_catalog_topk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i32]),
     "psb_catalog_topk": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp,
                                  c_i64, c_vp, c_vp, c_vp]),
+    "psb_catalog_prepare_f16": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "psb_catalog_topk_f16": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                     c_vp, c_vp, c_vp]),
     "psb_table_max_row_sqnorm": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_topk_merge": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "psb_adam_workspace_bytes": (c_i64, [ctypes.POINTER(AdamTensor), c_i32]),

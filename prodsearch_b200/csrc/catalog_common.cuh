@@ -39,5 +39,10 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
                     const float* bias, int64_t k, int64_t id_base, int64_t id_stride, const float* max_row_sqnorm,
                     void* workspace, int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s);
 int table_max_row_sqnorm(const float* table, int64_t rows, int64_t d, float* out, cudaStream_t s);
+int64_t tc16_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k);
+int catalog_prepare_f16(const float* table, int64_t n_items, int64_t d, void* table_f16, float* stats, cudaStream_t s);
+int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const void* table_f16, const float* stats,
+                      int64_t n_items, int64_t d, const float* bias, int64_t k, int64_t id_base, int64_t id_stride,
+                      void* workspace, int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s);
 
 }  // namespace psb

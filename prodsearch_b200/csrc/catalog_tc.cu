@@ -18,6 +18,7 @@
 // warps (tcgen05.ld 32x32b.x32).  smem: Q tile resident (d/32 k-blocks of 128x32 fp32, 128B
 // swizzle), 2-stage ring of item tiles, TMEM: 2 accumulators x 128 columns (double buffered).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "catalog_common.cuh"
@@ -294,6 +295,313 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ fp16 shortlist (PSB_TOPK_TC16)
+// Same pipeline with the shortlist GEMM in fp16 (tcgen05 kind::f16, fp32 accumulation in TMEM) on a half-precision
+// COPY of the (static) evaluation table: half the HBM bytes per pass, twice the tensor rate, and -- because a
+// 128 x 128 fp16 query tile is 32 KB instead of 64 KB -- one CTA keeps up to FOUR query tiles resident and scores
+// all of them against every item tile it streams: M <= 512 queries per pass over the table, 148 independent
+// streams with a 5..8-stage TMA ring (the tf32 kernel re-streams the table once per 128 queries from L2 with a
+// 2-stage ring and is latency-bound there).  The error bound is measured, not assumed: the conversion pass
+// records max_r |e_r - half(e_r)| and max_r |e_r|, the query pass |q - half(q)| and |half(q)|, so
+//   |q.e - half(q).half(e)| <= |q - hq| max|e| + |hq| max|e - he| + 2^-14 |hq| max|e|   (last term: fp32 accumulation)
+// and the final stage rescored exactly in fp32 as before -> results identical to the exact mode.
+constexpr int kKB16 = 64;                       // halves per k-block = one 128-byte swizzle row
+constexpr uint32_t kQBlock16 = kTM * 128;       // bytes of one 128-row k-block (16 KB)
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Tc16Params {
+  int m, n_items, kblocks;             // kblocks = d / 64
+  int tile_begin, tile_step, n_tiles;  // item tiles of TN items
+  int stages;
+  const float* bias;
+  const float* thr;
+  float* dump;
+  int ld_dump;
+  float* cand_s;
+  int32_t* cand_i;
+  int32_t* cand_n;
+  int cap;
+};
+
+// MT query tiles per CTA; item tile TN = 128 (MT <= 2) or 64 (MT = 3, 4): two accumulator sets of MT * TN
+// TMEM columns.  grid (item slices, query groups of MT tiles), 64 + 512 threads as tc_score_kernel.
+template <bool DUMP, int MT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
+                  const Tc16Params P) {
+  constexpr int TN = MT <= 2 ? 128 : 64;
+  constexpr int kAccCols = MT * TN;
+  constexpr int kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+  constexpr uint32_t kIdesc16 = (1u << 4) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(kTM >> 4) << 24);
+  constexpr int kMaxStages = 8;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q_bytes = static_cast<uint32_t>(MT * P.kblocks) * kQBlock16;
+  const uint32_t e_block = static_cast<uint32_t>(TN) * 128u;                 // bytes of one item k-block
+  const uint32_t stage_bytes = static_cast<uint32_t>(P.kblocks) * e_block;
+  const int S = P.stages;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = bars + 1 + kMaxStages;
+  uint64_t* t_full = bars + 1 + 2 * kMaxStages;
+  uint64_t* t_empty = bars + 3 + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kMaxStages);
+
+  const int n_slices = gridDim.x, slice = blockIdx.x, mtile0 = blockIdx.y * MT;
+  const int per = (P.n_tiles + n_slices - 1) / n_slices;
+  const int p_lo = slice * per;
+  const int p_hi = min(P.n_tiles, p_lo + per);
+  const int my_tiles = max(0, p_hi - p_lo);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int st = 0; st < S; ++st) {
+      mbar_init(b_full + st, 1);
+      mbar_init(b_empty + st, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(t_full + a, 1);
+      mbar_init(t_empty + a, 4 * kParts);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, q_bytes);
+      for (int mt = 0; mt < MT; ++mt)
+        for (int kb = 0; kb < P.kblocks; ++kb)
+          tma_load_2d(sA + (mt * P.kblocks + kb) * kQBlock16, &map_q, kb * kKB16, (mtile0 + mt) * kTM, a_full);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(b_empty + st, ph ^ 1);
+        mbar_expect_tx(b_full + st, stage_bytes);
+        const int tile = P.tile_begin + (p_lo + it) * P.tile_step;
+        for (int kb = 0; kb < P.kblocks; ++kb)
+          tma_load_2d(sB + static_cast<size_t>(st) * stage_bytes + kb * e_block, &map_e, kb * kKB16, tile * TN, b_full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(t_empty + acc, aph ^ 1);
+        mbar_wait(b_full + st, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols + mt * TN);
+          for (int kb = 0; kb < P.kblocks; ++kb) {
+            const uint32_t a_addr = smem_u32(sA + (mt * P.kblocks + kb) * kQBlock16);
+            const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(st) * stage_bytes + kb * e_block);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K = 16 halves = 32 bytes) inside one 128-byte swizzle row
+              tc_mma_f16(d_addr, umma_desc(a_addr + k4 * 32), umma_desc(b_addr + k4 * 32), kIdesc16, (kb | k4) != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(b_empty + st);
+        tc_commit(t_full + acc);
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps; thread = (TMEM lane = query row inside a tile, part); 32-column chunks of the
+    // MT accumulators are dealt round-robin to the 4 parts
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int kChunksPerTile = TN / 32;
+    float thr[MT];
+    int cnt[MT];
+    int64_t list[MT];
+    bool row_ok[MT];
+    const int n_lists = n_slices * kParts;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
+      row_ok[mt] = row < P.m;
+      thr[mt] = INFINITY;
+      if (!DUMP && row_ok[mt]) thr[mt] = P.thr[row];
+      cnt[mt] = 0;
+      list[mt] = (static_cast<int64_t>(row) * n_lists + slice * kParts + part) * P.cap;
+    }
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int p = p_lo + it;
+      const int tile = P.tile_begin + p * P.tile_step;
+      const bool full_tile = (tile + 1) * TN <= P.n_items && P.bias == nullptr;
+      mbar_wait(t_full + acc, aph);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerTile; ++cc) {
+          if (((mt * kChunksPerTile + cc) & (kParts - 1)) != part) continue;   // warp-uniform
+          const int c0 = cc * 32;
+          uint32_t v[32];
+          __syncwarp();
+          tc_ld32(lane_addr + static_cast<uint32_t>(acc * kAccCols + mt * TN + c0), v);
+          const int id0 = tile * TN + c0;
+          if (DUMP) {
+            const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int id = id0 + i;
+              float sc = __uint_as_float(v[i]);
+              if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+              if (row_ok[mt]) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * TN + c0 + i] = id < P.n_items ? sc : -INFINITY;
+            }
+          } else if (full_tile) {
+#pragma unroll
+            for (int g8 = 0; g8 < 32; g8 += 8) {
+              float mx = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
+                               fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
+              mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
+                                   fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
+              if (!(mx < thr[mt])) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sc = __uint_as_float(v[g8 + i]);
+                  if (!(sc < thr[mt])) {
+                    if (cnt[mt] < P.cap) {
+                      P.cand_s[list[mt] + cnt[mt]] = sc;
+                      P.cand_i[list[mt] + cnt[mt]] = id0 + g8 + i;
+                    }
+                    ++cnt[mt];
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int id = id0 + i;
+              float sc = __uint_as_float(v[i]);
+              if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+              if (!(sc < thr[mt]) && id < P.n_items) {
+                if (cnt[mt] < P.cap) {
+                  P.cand_s[list[mt] + cnt[mt]] = sc;
+                  P.cand_i[list[mt] + cnt[mt]] = id;
+                }
+                ++cnt[mt];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+    }
+    if (!DUMP) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
+        if (row_ok[mt]) P.cand_n[static_cast<int64_t>(row) * n_lists + slice * kParts + part] = cnt[mt];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// fp32 table -> fp16 copy (round to nearest) + stats[0] = max |e|^2, stats[1] = max |e - half(e)|^2,
+// stats[2] = 1.0 if any element overflows fp16.  One warp per row; maxima via integer atomicMax (order-free).
+__global__ void __launch_bounds__(256)
+prep_f16_kernel(const float4* __restrict__ table, int64_t rows, int d4, uint2* __restrict__ half_out,
+                float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  float best = 0.f, best_err = 0.f;
+  bool over = false;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); r < rows; r += nwarps) {
+    float sq = 0.f, er = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = ldg_row4(table + r * d4 + c);
+      const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      over |= isinf(f01.x) || isinf(f01.y) || isinf(f23.x) || isinf(f23.y) || !(v.x == v.x) || !(v.y == v.y) ||
+              !(v.z == v.z) || !(v.w == v.w);
+      sq += dot4(v, v);
+      const float4 e = make_float4(v.x - f01.x, v.y - f01.y, v.z - f23.x, v.w - f23.y);
+      er += dot4(e, e);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h01);
+      o.y = *reinterpret_cast<const uint32_t*>(&h23);
+      half_out[r * d4 + c] = o;
+    }
+    sq = warp_sum(sq);
+    er = warp_sum(er);
+    best = fmaxf(best, sq);
+    best_err = fmaxf(best_err, er);
+  }
+  over = __any_sync(kFull, over);
+  if (lane == 0) {
+    atomicMax(reinterpret_cast<int*>(stats), __float_as_int(best));
+    atomicMax(reinterpret_cast<int*>(stats + 1), __float_as_int(best_err));
+    if (over) atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(1.f));
+  }
+}
+
+// queries -> fp16 rows (rows >= m zero) + eps[row] (see the error bound above).  One warp per row.
+__global__ void __launch_bounds__(256)
+q16_kernel(const float* __restrict__ Q, int m, int m_pad, int d, const float* __restrict__ stats,
+           __half* __restrict__ q16, float* __restrict__ eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= m_pad) return;
+  float qn = 0.f, dq = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float v = 0.f;
+    if (row < m) v = Q[static_cast<int64_t>(row) * d + c];
+    const __half h = __float2half_rn(v);
+    const float f = __half2float(h);
+    q16[static_cast<int64_t>(row) * d + c] = h;
+    qn += f * f;
+    dq += (v - f) * (v - f);
+  }
+  qn = warp_sum(qn);
+  dq = warp_sum(dq);
+  if (lane == 0) {
+    const float E = sqrtf(stats[0]), dE = sqrtf(stats[1]);
+    const float hq = sqrtf(qn);
+    // 1.01: rounding of the norms themselves; 2^-14 |hq| max|e|: fp32 accumulation inside the tensor core
+    float e = 1.01f * (sqrtf(dq) * E + hq * dE) + 6.1035156e-5f * hq * E + 1e-30f;
+    if (stats[2] != 0.f || !(e < 3.0e38f)) e = INFINITY;   // table does not fit fp16: no pruning, rows fall back
+    eps[row] = row < m ? e : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ helpers
 __global__ void __launch_bounds__(256)
 max_row_norm_kernel(const float4* __restrict__ table, int64_t rows, int d4, float* __restrict__ out_sq) {
@@ -381,7 +689,8 @@ __device__ float block_kth_largest(const float* vals, int n, int k, int* hist /*
 // pilot scores -> thr[row] = kth - 2 eps_row ; eps_row = 2^-8 |q_row| max|e|
 __global__ void __launch_bounds__(256)
 pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int k, const float* __restrict__ Q, int d,
-                       const float* __restrict__ max_sq, float* __restrict__ thr, float* __restrict__ eps, int stage) {
+                       const float* __restrict__ max_sq, const float* __restrict__ eps_in, float* __restrict__ thr,
+                       float* __restrict__ eps, int stage) {
   __shared__ int hist[256];
   __shared__ uint32_t sh[2];
   __shared__ float red[8];
@@ -396,7 +705,7 @@ pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int 
   __syncthreads();
   float qsq = 0.f;
   for (int w = 0; w < 8; ++w) qsq += red[w];
-  const float e = kEpsFactor * sqrtf(qsq) * sqrtf(*max_sq) + 1e-30f;
+  const float e = eps_in != nullptr ? eps_in[row] : kEpsFactor * sqrtf(qsq) * sqrtf(*max_sq) + 1e-30f;
   const float* vals = dump + static_cast<int64_t>(row) * ld;
   // count finite entries: with fewer than k valid pilot items nothing can be pruned
   int valid = 0;
@@ -420,6 +729,7 @@ pilot_threshold_kernel(const float* __restrict__ dump, int ld, int n_pilot, int 
   for (int w = 0; w < 8; ++w) tot += red[w];
   float t = -INFINITY;
   if (static_cast<int>(tot) >= k) t = block_kth_largest(vals, n_pilot, k, hist, sh) - 2.f * e;
+  if (!(e < 3.0e38f)) t = -INFINITY;      // unbounded shortlist error: nothing may be pruned
   if (threadIdx.x == 0) {
     thr[row] = t;
     eps[row] = e;
@@ -521,8 +831,9 @@ final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict_
   const int total = s_total;
   float cut = -INFINITY;
   if (total > k) cut = block_kth_largest(cs, total, k, hist, sh) - 2.f * eps[row];
+  if (!(eps[row] < 3.0e38f)) cut = -INFINITY;
   for (int i = threadIdx.x; i < total; i += 256) {
-    if (cs[i] >= cut) {
+    if (!(cs[i] < cut)) {
       const int slot = atomicAdd(&s_keep, 1);
       if (slot < kKeepCap) ki[slot] = ci[i];
     }
@@ -778,7 +1089,7 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
   PSB_PROF("pilot_threshold_kernel", s);
   const bool stage_pilot = static_cast<size_t>(P.ld_dump) * 4 <= 160 * 1024;
   pilot_threshold_kernel<<<static_cast<int>(m), 256, stage_pilot ? static_cast<size_t>(P.ld_dump) * 4 : 0, s>>>(
-      dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries, static_cast<int>(d), max_row_sqnorm, thr, eps,
+      dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries, static_cast<int>(d), max_row_sqnorm, nullptr, thr, eps,
       stage_pilot ? 1 : 0);
   if ((st = launch_status()) != PSB_OK) return st;
   // 3. main pass
@@ -798,6 +1109,188 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
                                                               id_base, id_stride, out_ids, out_scores, flag);
   if ((st = launch_status()) != PSB_OK) return st;
   // 5. exact fallback for flagged rows (returns immediately for unflagged ones)
+  PSB_PROF("fallback_rows_kernel", s);
+  fallback_rows_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(d) * 4, s>>>(
+      flag, queries, table, n_items, static_cast<int>(d), bias, static_cast<int>(k), id_base, id_stride, out_ids,
+      out_scores);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------ fp16 shortlist: host side
+static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t d, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return PSB_E_UNSUPPORTED;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(d) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKB16), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PSB_OK : PSB_E_ARG;
+}
+
+struct Tc16Plan {
+  int m_tiles, groups, MT, TN, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap, stages;
+  size_t smem;
+  int64_t off_thr, off_eps, off_epsin, off_flag, off_cand_n, off_q16, off_dump, off_cand_s, off_cand_i, total;
+};
+
+static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
+  Tc16Plan p;
+  p.m_tiles = static_cast<int>((m + kTM - 1) / kTM);
+  p.groups = (p.m_tiles + 3) / 4;
+  p.MT = (p.m_tiles + p.groups - 1) / p.groups;
+  p.TN = p.MT <= 2 ? 128 : 64;
+  p.m_pad = p.groups * p.MT * kTM;
+  p.total_tiles = static_cast<int>((n_items + p.TN - 1) / p.TN);
+  p.n_slices = kNumSMs / p.groups;
+  if (p.n_slices < 1) p.n_slices = 1;
+  if (p.n_slices > p.total_tiles) p.n_slices = p.total_tiles;
+  // pilot: 1/32 of the table (at least 16384 items): the k-th best pilot score lets ~32 k candidates through
+  const int min_tiles = 16384 / p.TN;
+  p.pilot_tiles = p.total_tiles / 32 > min_tiles ? p.total_tiles / 32 : min_tiles;
+  if (p.pilot_tiles > p.total_tiles) p.pilot_tiles = p.total_tiles;
+  p.pilot_step = p.total_tiles / p.pilot_tiles;
+  const double expect = static_cast<double>(k) * p.total_tiles / p.pilot_tiles / (p.n_slices * kParts);
+  p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
+  const int kblocks = static_cast<int>(d / kKB16);
+  const size_t q_bytes = static_cast<size_t>(p.MT) * kblocks * kQBlock16;
+  const size_t stage_bytes = static_cast<size_t>(kblocks) * p.TN * 128;
+  size_t st = (220 * 1024 - q_bytes) / stage_bytes;
+  p.stages = static_cast<int>(st > 8 ? 8 : st);
+  p.smem = q_bytes + p.stages * stage_bytes + 512 + 1024;
+  int64_t o = 0;
+  p.off_thr = o; o += up256(p.m_pad * 4);
+  p.off_eps = o; o += up256(p.m_pad * 4);
+  p.off_epsin = o; o += up256(p.m_pad * 4);
+  p.off_flag = o; o += up256(p.m_pad * 4);
+  p.off_cand_n = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * 4);
+  p.off_q16 = o; o += up256(static_cast<int64_t>(p.m_pad) * d * 2);
+  p.off_dump = o; o += up256(static_cast<int64_t>(p.m_pad) * p.pilot_tiles * p.TN * 4);
+  p.off_cand_s = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
+  p.off_cand_i = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
+  p.total = o + 256;
+  return p;
+}
+
+static bool tc16_supported(int64_t m, int64_t n_items, int64_t d) {
+  return d % kKB16 == 0 && d <= 128 && n_items >= 32768 && m <= static_cast<int64_t>(kNumSMs) * 4 * kTM;
+}
+
+int64_t tc16_workspace_bytes(int64_t m, int64_t n_items, int64_t d, int64_t k) {
+  if (!tc16_supported(m, n_items, d)) return 0;
+  return plan16_for(m, n_items, d, k).total;
+}
+
+int catalog_prepare_f16(const float* table, int64_t n_items, int64_t d, void* table_f16, float* stats, cudaStream_t s) {
+  cudaMemsetAsync(stats, 0, 16, s);
+  PSB_PROF("prep_f16_kernel", s);
+  prep_f16_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(table), n_items, static_cast<int>(d / 4),
+                                              static_cast<uint2*>(table_f16), stats);
+  return launch_status();
+}
+
+template <bool DUMP>
+static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& mq, const CUtensorMap& me,
+                       const Tc16Params& P) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int lim = 227 * 1024;
+    cudaError_t e = cudaSuccess;
+#define PSB_TC16_ATTR(D, M) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_kernel<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+    PSB_TC16_ATTR(true, 1); PSB_TC16_ATTR(true, 2); PSB_TC16_ATTR(true, 3); PSB_TC16_ATTR(true, 4);
+    PSB_TC16_ATTR(false, 1); PSB_TC16_ATTR(false, 2); PSB_TC16_ATTR(false, 3); PSB_TC16_ATTR(false, 4);
+#undef PSB_TC16_ATTR
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done = true;
+  }
+  PSB_PROF("tc16_score_kernel", s);
+  switch (MT) {
+    case 1: tc16_score_kernel<DUMP, 1><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+    case 2: tc16_score_kernel<DUMP, 2><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+    case 3: tc16_score_kernel<DUMP, 3><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+    default: tc16_score_kernel<DUMP, 4><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+  }
+  return launch_status();
+}
+
+int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const void* table_f16, const float* stats,
+                      int64_t n_items, int64_t d, const float* bias, int64_t k, int64_t id_base, int64_t id_stride,
+                      void* workspace, int64_t workspace_bytes, int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  if (!tc16_supported(m, n_items, d))
+    return catalog_topk_exact(queries, m, table, n_items, d, bias, k, id_base, id_stride, workspace,
+                              workspace_bytes, out_ids, out_scores, s);
+  const Tc16Plan pl = plan16_for(m, n_items, d, k);
+  const int64_t ex_bytes = (exact_workspace_bytes(m, n_items) + 255) / 256 * 256;
+  if (workspace_bytes < ex_bytes + pl.total) return PSB_E_WORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace) + ex_bytes;
+  float* thr = reinterpret_cast<float*>(ws + pl.off_thr);
+  float* eps = reinterpret_cast<float*>(ws + pl.off_eps);
+  float* eps_in = reinterpret_cast<float*>(ws + pl.off_epsin);
+  int32_t* flag = reinterpret_cast<int32_t*>(ws + pl.off_flag);
+  int32_t* cand_n = reinterpret_cast<int32_t*>(ws + pl.off_cand_n);
+  __half* q16 = reinterpret_cast<__half*>(ws + pl.off_q16);
+  float* dump = reinterpret_cast<float*>(ws + pl.off_dump);
+  float* cand_s = reinterpret_cast<float*>(ws + pl.off_cand_s);
+  int32_t* cand_i = reinterpret_cast<int32_t*>(ws + pl.off_cand_i);
+
+  alignas(64) CUtensorMap map_q, map_e;
+  int st;
+  if ((st = make_map16(&map_q, q16, pl.m_pad, d, kTM)) != PSB_OK) return st;
+  if ((st = make_map16(&map_e, table_f16, n_items, d, pl.TN)) != PSB_OK) return st;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(pilot_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return static_cast<int>(e1 != cudaSuccess ? e1 : e2);
+    attr_done = true;
+  }
+  cudaMemsetAsync(flag, 0, static_cast<size_t>(pl.m_pad) * 4, s);
+  PSB_PROF("q16_kernel", s);
+  q16_kernel<<<(pl.m_pad + 7) / 8, 256, 0, s>>>(queries, static_cast<int>(m), pl.m_pad, static_cast<int>(d), stats, q16, eps_in);
+  if ((st = launch_status()) != PSB_OK) return st;
+
+  Tc16Params P;
+  P.m = static_cast<int>(m);
+  P.n_items = static_cast<int>(n_items);
+  P.kblocks = static_cast<int>(d / kKB16);
+  P.stages = pl.stages;
+  P.bias = bias;
+  P.thr = thr;
+  P.dump = dump;
+  P.ld_dump = pl.pilot_tiles * pl.TN;
+  P.cand_s = cand_s;
+  P.cand_i = cand_i;
+  P.cand_n = cand_n;
+  P.cap = pl.cap;
+  // 1. pilot
+  P.tile_begin = 0;
+  P.tile_step = pl.pilot_step;
+  P.n_tiles = pl.pilot_tiles;
+  {
+    const int slices = pl.n_slices < pl.pilot_tiles ? pl.n_slices : pl.pilot_tiles;
+    if ((st = launch_tc16<true>(pl.MT, dim3(slices, pl.groups), pl.smem, s, map_q, map_e, P)) != PSB_OK) return st;
+  }
+  // 2. thresholds (eps from the measured quantisation errors)
+  const bool stage_pilot = static_cast<size_t>(P.ld_dump) * 4 <= 160 * 1024;
+  PSB_PROF("pilot_threshold_kernel", s);
+  pilot_threshold_kernel<<<static_cast<int>(m), 256, stage_pilot ? static_cast<size_t>(P.ld_dump) * 4 : 0, s>>>(
+      dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries, static_cast<int>(d), stats, eps_in, thr, eps,
+      stage_pilot ? 1 : 0);
+  if ((st = launch_status()) != PSB_OK) return st;
+  // 3. main pass
+  P.tile_step = 1;
+  P.n_tiles = pl.total_tiles;
+  if ((st = launch_tc16<false>(pl.MT, dim3(pl.n_slices, pl.groups), pl.smem, s, map_q, map_e, P)) != PSB_OK) return st;
+  // 4. final select + exact fp32 rescoring, 5. exact fallback for flagged rows
+  const size_t fsmem = static_cast<size_t>(kFinalCap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
+  PSB_PROF("final_select_kernel", s);
+  final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
+                                                              table, static_cast<int>(d), bias, static_cast<int>(k),
+                                                              id_base, id_stride, out_ids, out_scores, flag);
+  if ((st = launch_status()) != PSB_OK) return st;
   PSB_PROF("fallback_rows_kernel", s);
   fallback_rows_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(d) * 4, s>>>(
       flag, queries, table, n_items, static_cast<int>(d), bias, static_cast<int>(k), id_base, id_stride, out_ids,

@@ -271,7 +271,31 @@ extern "C" int64_t psb_catalog_topk_workspace_bytes(int64_t m, int64_t n_items, 
   const int64_t ex = exact_workspace_bytes(m, n_items);
   if (mode == PSB_TOPK_EXACT) return ex;
   if (mode == PSB_TOPK_TC) return ex + tc_workspace_bytes(m, n_items, d, k);
+  if (mode == PSB_TOPK_TC16) return ex + tc16_workspace_bytes(m, n_items, d, k) + 256;
   return PSB_E_UNSUPPORTED;
+}
+
+extern "C" int psb_catalog_prepare_f16(const float* table, int64_t n_items, int64_t d, void* table_f16, float* stats,
+                                       psb_stream_t stream) {
+  int st = check_table_args(table, n_items, d);
+  if (st != PSB_OK) return st;
+  if (table_f16 == nullptr || stats == nullptr) return PSB_E_ARG;
+  if (misaligned16(table_f16) || misaligned16(stats)) return PSB_E_ALIGN;
+  return catalog_prepare_f16(table, n_items, d, table_f16, stats, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int psb_catalog_topk_f16(const float* queries, int64_t m, const float* table, const void* table_f16,
+                                    const float* stats, int64_t n_items, int64_t d, const float* bias, int64_t k,
+                                    int64_t id_base, int64_t id_stride, void* workspace, int64_t workspace_bytes,
+                                    int64_t* out_ids, float* out_scores, psb_stream_t stream) {
+  if (queries == nullptr || table == nullptr || table_f16 == nullptr || stats == nullptr || workspace == nullptr ||
+      out_ids == nullptr || out_scores == nullptr || m <= 0 || n_items <= 0 || n_items >= (1ll << 31) || m >= (1 << 24))
+    return PSB_E_ARG;
+  if (d <= 0 || (d & 3) != 0 || d > 512 || k <= 0 || k > kKMax) return PSB_E_DIM;
+  if (misaligned16(queries) || misaligned16(table) || misaligned16(table_f16) || misaligned16(workspace))
+    return PSB_E_ALIGN;
+  return catalog_topk_tc16(queries, m, table, table_f16, stats, n_items, d, bias, k, id_base, id_stride, workspace,
+                           workspace_bytes, out_ids, out_scores, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int psb_catalog_topk(const float* queries, int64_t m, const float* table, int64_t n_items,

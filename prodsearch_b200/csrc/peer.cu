@@ -321,8 +321,7 @@ extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tab
   int64_t cap_max = 0;
   for (int k = 0; k < n_tables; ++k) {
     const psb_fold_table_t& in = tables[k];
-    if (in.rows == nullptr || in.vals == nullptr || in.n_rows == nullptr || in.posmap == nullptr ||
-        in.dense == nullptr || in.cap <= 0 || in.shard_rows <= 0)
+    if (in.posmap == nullptr || in.dense == nullptr || in.cap <= 0 || in.shard_rows <= 0)
       return PSB_E_ARG;
     if (in.d <= 0 || (in.d & 3) != 0 || in.d > 512) return PSB_E_DIM;
     if (misaligned16(in.dense)) return PSB_E_ALIGN;

@@ -206,20 +206,34 @@ class ItemTransformerRanker(nn.Module):
             self._norm_cache = (key, ops.table_max_row_sqnorm(w, self.prod_pad_idx))
         return self._norm_cache[1]
 
-    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):
+    def _prepared_catalog(self):
+        """fp16 shortlist copy of the item table, rebuilt when the table changes (evaluation: once)."""
+        w = self.product_emb.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_prep_cache", (None, None))[0] != key:
+            self._prep_cache = (key, ops.catalog_prepare_f16(w.detach(), self.prod_pad_idx))
+        return self._prep_cache[1]
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC16):
         """Top-k over the whole catalog (items 0..P-1) with fused selection; replaces
         get_prod_scores + host argsort (trainer.py:189-226,:152).  Returns (ids [M,k], scores [M,k]).
-        mode TOPK_TC: tcgen05 TF32 shortlist + exact fp32 rescoring (identical results to TOPK_EXACT;
-        shapes it does not cover run the exact kernels)."""
+        mode TOPK_TC16 (default): tcgen05 fp16 shortlist on a cached half-precision copy of the table + exact fp32
+        rescoring; TOPK_TC: tf32 shortlist straight from the fp32 table.  Both return exactly what TOPK_EXACT
+        returns; shapes they do not cover (and tables that overflow fp16) run the next mode down."""
         with torch.no_grad():
             if torch.is_tensor(batch_or_queries):
                 q = batch_or_queries
             else:
                 q = self.encode_queries(batch_or_queries.query_word_idxs, batch_or_queries.u_item_idxs)
             bias = self.product_bias if self.args.sim_func == "bias_product" else None
+            prepared = None
+            if mode == _lib.TOPK_TC16:
+                prepared = self._prepared_catalog()
+                if not prepared.fits:
+                    mode, prepared = _lib.TOPK_TC, None
             norm = self._max_row_sqnorm() if mode == _lib.TOPK_TC else None
             return ops.catalog_topk(q.contiguous(), self.product_emb.weight, k, n_items=self.prod_pad_idx,
-                                    bias=bias, mode=mode, max_row_sqnorm=norm)
+                                    bias=bias, mode=mode, max_row_sqnorm=norm, prepared=prepared)
 
 
 # the north star names the class ProdSearchModel; the reference's real name is kept as primary

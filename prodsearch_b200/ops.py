@@ -163,13 +163,48 @@ def table_max_row_sqnorm(table, n_rows=None):
     return out
 
 
+class PreparedCatalog(object):
+    """fp16 copy of a static evaluation table + its measured quantisation statistics (psb_catalog_prepare_f16)."""
+    __slots__ = ("half", "stats", "n_items", "fits")
+
+
+def catalog_prepare_f16(table, n_items=None):
+    """One pass over table[0..n_items): fp16 copy, max |e|^2, max |e - half(e)|^2, overflow flag.  ``fits`` (read
+    once on the host) says whether the fp16 shortlist may be used; callers fall back to TOPK_TC otherwise."""
+    n_items = table.shape[0] if n_items is None else int(n_items)
+    d = table.shape[1]
+    p = PreparedCatalog()
+    p.half = torch.empty((n_items, d), dtype=torch.float16, device=table.device)
+    p.stats = torch.zeros((4,), dtype=f32, device=table.device)
+    p.n_items = n_items
+    check(load().psb_catalog_prepare_f16(ptr(table, f32), n_items, d, p.half.data_ptr(), ptr(p.stats), stream_ptr()),
+          "psb_catalog_prepare_f16")
+    p.fits = float(p.stats[2].item()) == 0.0
+    return p
+
+
 def catalog_topk(queries, table, k, n_items=None, bias=None, id_base=0, id_stride=1, mode=_lib.TOPK_EXACT,
-                 max_row_sqnorm=None):
+                 max_row_sqnorm=None, prepared=None):
     """Top-k items per query over the whole table with fused selection (psb_catalog_topk).
-    Returns (ids [m,k] int64, scores [m,k] fp32), descending score / ascending id."""
+    Returns (ids [m,k] int64, scores [m,k] fp32), descending score / ascending id.
+    mode TOPK_TC16 needs ``prepared`` (catalog_prepare_f16 of the same table)."""
     m, d = queries.shape
     n_items = table.shape[0] if n_items is None else int(n_items)
     dev = queries.device
+    if mode == _lib.TOPK_TC16:
+        if prepared is None or prepared.n_items != n_items:
+            raise RuntimeError("TOPK_TC16 needs catalog_prepare_f16(table, n_items) of the same table")
+        ws_bytes = int(load().psb_catalog_topk_workspace_bytes(m, n_items, d, k, mode))
+        if ws_bytes < 0:
+            check(ws_bytes, "psb_catalog_topk_workspace_bytes")
+        ws = torch.empty((ws_bytes,), dtype=u8, device=dev)
+        ids = torch.empty((m, k), dtype=i64, device=dev)
+        sc = torch.empty((m, k), dtype=f32, device=dev)
+        check(load().psb_catalog_topk_f16(ptr(queries, f32), m, ptr(table, f32), prepared.half.data_ptr(),
+                                          ptr(prepared.stats), n_items, d, ptr(bias, f32), k, int(id_base),
+                                          int(id_stride), ptr(ws), ws_bytes, ptr(ids), ptr(sc), stream_ptr()),
+              "psb_catalog_topk_f16")
+        return ids, sc
     ws_bytes = int(load().psb_catalog_topk_workspace_bytes(m, n_items, d, k, mode))
     if ws_bytes < 0:
         check(ws_bytes, "psb_catalog_topk_workspace_bytes")
@@ -298,6 +333,6 @@ def _profiled(name, fn):
     return wrapper
 
 
-for _n in ("table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
+for _n in ("catalog_prepare_f16", "table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
            "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge", "encoder_fwd", "encoder_bwd"):
     globals()[_n] = _profiled(_n, globals()[_n])

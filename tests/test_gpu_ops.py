@@ -411,3 +411,48 @@ def test_catalog_topk_tc_scaled_rows(ops):
     a = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_EXACT)
     b = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_TC)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ---------------------------------------------------------------- G5 fp16 shortlist (tcgen05 kind::f16, up to 512 queries / pass)
+@pytest.mark.parametrize("m,n,k,with_bias", [(24, 100_000, 100, False), (130, 70_001, 100, True),
+                                             (384, 1_000_000, 100, False), (5, 40_000, 10, True),
+                                             (300, 250_000, 100, True), (513, 120_000, 50, False),
+                                             (1100, 90_000, 100, False)])
+def test_catalog_topk_f16_equals_exact(ops, m, n, k, with_bias):
+    """fp16 shortlist (1..4 query tiles per CTA, 1..3 query groups) + exact fp32 rescoring == the fp32 mode,
+    bit for bit, incl. ragged last item tile / last query tile and the bias path."""
+    from prodsearch_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    E = torch.randn(n + 1, 128, generator=g, device="cuda")
+    Q = torch.randn(m, 128, generator=g, device="cuda")
+    bias = (torch.randn(n + 1, generator=g, device="cuda") * 0.1) if with_bias else None
+    prep = ops.catalog_prepare_f16(E, n)
+    assert prep.fits and torch.equal(prep.half, E[:n].half())
+    assert abs(float(prep.stats[0]) - float((E[:n] ** 2).sum(1).max())) <= 1e-4 * float(prep.stats[0])
+    ids_e, sc_e = ops.catalog_topk(Q, E, k, n_items=n, bias=bias, mode=_lib.TOPK_EXACT)
+    ids_t, sc_t = ops.catalog_topk(Q, E, k, n_items=n, bias=bias, mode=_lib.TOPK_TC16, prepared=prep)
+    assert torch.equal(ids_e, ids_t)
+    assert torch.equal(sc_e, sc_t)
+
+
+def test_catalog_topk_f16_scaled_rows_ties_and_overflow(ops):
+    from prodsearch_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, m, k = 200_000, 64, 100
+    E = torch.randn(n, 128, generator=g, device="cuda") * torch.logspace(-2, 1, n, device="cuda").unsqueeze(1)
+    Q = torch.randn(m, 128, generator=g, device="cuda")
+    a = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_EXACT)
+    b = ops.catalog_topk(Q, E, k, mode=_lib.TOPK_TC16, prepared=ops.catalog_prepare_f16(E))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # massive ties: the shortlist overflows, the exact fallback answers lower-id-first
+    E1, Q1 = torch.ones(50_000, 128, device="cuda"), torch.ones(3, 128, device="cuda")
+    ids, sc = ops.catalog_topk(Q1, E1, k, mode=_lib.TOPK_TC16, prepared=ops.catalog_prepare_f16(E1))
+    assert torch.equal(ids.cpu(), torch.arange(k).repeat(3, 1)) and bool((sc == 128.0).all())
+    # a value outside the fp16 range: flagged by the conversion pass, and the call still returns the exact answer
+    E2 = E.clone()
+    E2[12345, 7] = 1.0e6
+    prep = ops.catalog_prepare_f16(E2)
+    assert not prep.fits
+    a = ops.catalog_topk(Q[:4], E2, k, mode=_lib.TOPK_EXACT)
+    b = ops.catalog_topk(Q[:4], E2, k, mode=_lib.TOPK_TC16, prepared=prep)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
