@@ -458,62 +458,77 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const bool full_tile = (tile + 1) * TN <= P.n_items && P.bias == nullptr;
       mbar_wait(t_full + acc, aph);
       tc_fence_after();
+      // ONE loop body (no unrolling over chunks: 16 warps x unrolled bodies thrash the instruction cache);
+      // the per-query-tile state is selected into scalars and written back
+#pragma unroll 1
+      for (int w = part; w < MT * kChunksPerTile; w += kParts) {
+        const int mt = w / kChunksPerTile;
+        const int c0 = (w % kChunksPerTile) * 32;
+        float th = thr[0];
+        int cn = cnt[0];
+        int64_t li = list[0];
+        bool ok = row_ok[0];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+        for (int j = 1; j < MT; ++j)
+          if (mt == j) {
+            th = thr[j];
+            cn = cnt[j];
+            li = list[j];
+            ok = row_ok[j];
+          }
+        uint32_t v[32];
+        __syncwarp();
+        tc_ld32(lane_addr + static_cast<uint32_t>(acc * kAccCols + mt * TN + c0), v);
+        const int id0 = tile * TN + c0;
+        if (DUMP) {
+          const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
 #pragma unroll
-        for (int cc = 0; cc < kChunksPerTile; ++cc) {
-          if (((mt * kChunksPerTile + cc) & (kParts - 1)) != part) continue;   // warp-uniform
-          const int c0 = cc * 32;
-          uint32_t v[32];
-          __syncwarp();
-          tc_ld32(lane_addr + static_cast<uint32_t>(acc * kAccCols + mt * TN + c0), v);
-          const int id0 = tile * TN + c0;
-          if (DUMP) {
-            const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float sc = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+            if (ok) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * TN + c0 + i] = id < P.n_items ? sc : -INFINITY;
+          }
+        } else if (full_tile) {
+          // branch once per 8 scores: almost every group is below the threshold
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int id = id0 + i;
-              float sc = __uint_as_float(v[i]);
-              if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
-              if (row_ok[mt]) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * TN + c0 + i] = id < P.n_items ? sc : -INFINITY;
-            }
-          } else if (full_tile) {
+          for (int g8 = 0; g8 < 32; g8 += 8) {
+            float mx = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
+                             fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
+            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
+                                 fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
+            if (!(mx < th)) {
 #pragma unroll
-            for (int g8 = 0; g8 < 32; g8 += 8) {
-              float mx = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
-                               fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
-              mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
-                                   fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
-              if (!(mx < thr[mt])) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float sc = __uint_as_float(v[g8 + i]);
-                  if (!(sc < thr[mt])) {
-                    if (cnt[mt] < P.cap) {
-                      P.cand_s[list[mt] + cnt[mt]] = sc;
-                      P.cand_i[list[mt] + cnt[mt]] = id0 + g8 + i;
-                    }
-                    ++cnt[mt];
+              for (int i = 0; i < 8; ++i) {
+                const float sc = __uint_as_float(v[g8 + i]);
+                if (!(sc < th)) {
+                  if (cn < P.cap) {
+                    P.cand_s[li + cn] = sc;
+                    P.cand_i[li + cn] = id0 + g8 + i;
                   }
+                  ++cn;
                 }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int id = id0 + i;
-              float sc = __uint_as_float(v[i]);
-              if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
-              if (!(sc < thr[mt]) && id < P.n_items) {
-                if (cnt[mt] < P.cap) {
-                  P.cand_s[list[mt] + cnt[mt]] = sc;
-                  P.cand_i[list[mt] + cnt[mt]] = id;
-                }
-                ++cnt[mt];
               }
             }
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float sc = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+            if (!(sc < th) && id < P.n_items) {
+              if (cn < P.cap) {
+                P.cand_s[li + cn] = sc;
+                P.cand_i[li + cn] = id;
+              }
+              ++cn;
+            }
+          }
         }
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+          if (mt == j) cnt[j] = cn;
       }
       tc_fence_before();
       __syncwarp();
