@@ -320,6 +320,7 @@ struct Tc16Params {
   int m, n_items, kblocks;             // kblocks = d / 64
   int tile_begin, tile_step, n_tiles;  // item tiles of TN items
   int stages;
+  int append;                          // FILTER: continue the candidate lists an earlier segment started
   const float* bias;
   const float* thr;
   float* dump;
@@ -447,6 +448,7 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       thr[mt] = INFINITY;
       if (!DUMP && row_ok[mt]) thr[mt] = P.thr[row];
       cnt[mt] = 0;
+      if (!DUMP && P.append && row_ok[mt]) cnt[mt] = P.cand_n[static_cast<int64_t>(row) * n_lists + slice * kParts + part];
       list[mt] = (static_cast<int64_t>(row) * n_lists + slice * kParts + part) * P.cap;
     }
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -755,38 +757,25 @@ constexpr int kFinalCap = 14336;   // candidates a final-select CTA can hold in 
 constexpr int kKeepCap = 1024;
 constexpr int kMaxLists = kNumSMs * 4;  // n_slices * kParts upper bound     // candidates that survive the 2-eps prune and get exact scores
 
-// per query row: candidates -> prune -> exact rescoring -> ordered top-k.  Rows that cannot be
-// finished here (overflowed lists / too many survivors) are flagged for the exact fallback.
-__global__ void __launch_bounds__(256)
-final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
-                    const int32_t* __restrict__ cand_n, int n_slices, int cap, const float* __restrict__ eps,
-                    const float* __restrict__ Q, const float* __restrict__ E, int d, const float* __restrict__ bias,
-                    int k, int64_t id_base, int64_t id_stride, int64_t* __restrict__ out_ids,
-                    float* __restrict__ out_scores, int32_t* __restrict__ fallback_flag) {
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
-  int32_t* ci = reinterpret_cast<int32_t*>(cs + kFinalCap);      // [kFinalCap]
-  float* ks = reinterpret_cast<float*>(ci + kFinalCap);          // [kKeepCap] exact scores
-  int32_t* ki = reinterpret_cast<int32_t*>(ks + kKeepCap);       // [kKeepCap]
-  float* qrow = reinterpret_cast<float*>(ki + kKeepCap);         // [d]
-  __shared__ int hist[256];
-  __shared__ uint32_t sh[2];
-  __shared__ int s_total, s_over, s_keep;
-  __shared__ int offs[kMaxLists + 1];
-  const int row = blockIdx.x;
-  // list sizes -> exclusive offsets (n_slices here = number of lists of this row, <= kMaxLists)
-  for (int l = threadIdx.x; l < n_slices; l += 256) offs[l + 1] = cand_n[static_cast<int64_t>(row) * n_slices + l];
+// Candidates of one query row: n_lists per-(CTA, epilogue part) lists of at most `cap` entries -> cs / ci (ci optional)
+// in shared memory.  *s_over is set when a list overflowed or the total exceeds kFinalCap (nothing is loaded then).
+// All 256 threads must call; ends with a __syncthreads().
+__device__ __forceinline__ void load_candidate_lists(int row, const float* __restrict__ cand_s,
+                                                     const int32_t* __restrict__ cand_i,
+                                                     const int32_t* __restrict__ cand_n, int n_lists, int cap,
+                                                     float* cs, int32_t* ci, int* offs, int* hist, int* s_total,
+                                                     int* s_over) {
+  for (int l = threadIdx.x; l < n_lists; l += 256) offs[l + 1] = cand_n[static_cast<int64_t>(row) * n_lists + l];
   if (threadIdx.x == 0) offs[0] = 0;
-  for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
   __syncthreads();
-  // exclusive scan of the clamped list sizes (n_slices <= kMaxLists = 592 lists: 3 per thread)
+  // exclusive scan of the clamped list sizes (n_lists <= kMaxLists = 592: 3 per thread)
   {
     constexpr int kPer = (kMaxLists + 255) / 256;
     int c[kPer], mine = 0, over = 0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
       const int l = threadIdx.x * kPer + u;
-      c[u] = l < n_slices ? offs[l + 1] : 0;
+      c[u] = l < n_lists ? offs[l + 1] : 0;
       over |= c[u] > cap;
       c[u] = min(c[u], cap);
       mine += c[u];
@@ -812,37 +801,79 @@ final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict_
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
       const int l = threadIdx.x * kPer + u;
-      if (l < n_slices) offs[l] = run;
+      if (l < n_lists) offs[l] = run;
       run += c[u];
     }
     if (threadIdx.x == 255) {
-      offs[n_slices] = run;
-      s_total = run;
-      s_over = any_over | (run > kFinalCap);
-      s_keep = 0;
+      offs[n_lists] = run;
+      *s_total = run;
+      *s_over = any_over | (run > kFinalCap);
     }
   }
   __syncthreads();
+  if (*s_over) return;
+  // flat gather: candidate i belongs to the list whose offset range holds i (binary search), so all loads of a
+  // thread are independent (order irrelevant: the final ordering is a strict total order)
+  const int tot = *s_total;
+  for (int i = threadIdx.x; i < tot; i += 256) {
+    int a = 0, b = n_lists;           // largest l with offs[l] <= i
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (offs[mid] <= i) a = mid; else b = mid;
+    }
+    const int64_t src = (static_cast<int64_t>(row) * n_lists + a) * cap + (i - offs[a]);
+    cs[i] = cand_s[src];
+    if (ci != nullptr) ci[i] = cand_i[src];
+  }
+  __syncthreads();
+}
+
+// Threshold refinement between segments of the main pass: with the candidates collected so far the k-th best
+// approximate score is a (much) tighter lower bound than the pilot's, so thr[row] = max(thr[row], kth - 2 eps).
+__global__ void __launch_bounds__(256)
+refine_threshold_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_n, int n_lists, int cap,
+                        const float* __restrict__ eps, int k, float* __restrict__ thr) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
+  __shared__ int hist[256];
+  __shared__ uint32_t sh[2];
+  __shared__ int s_total, s_over;
+  __shared__ int offs[kMaxLists + 1];
+  const int row = blockIdx.x;
+  load_candidate_lists(row, cand_s, nullptr, cand_n, n_lists, cap, cs, nullptr, offs, hist, &s_total, &s_over);
+  if (s_over || s_total < k) return;      // keep the current threshold (an overflowed row ends in the fallback)
+  const float e = eps[row];
+  if (!(e < 3.0e38f)) return;
+  const float t = block_kth_largest(cs, s_total, k, hist, sh) - 2.f * e;
+  if (threadIdx.x == 0 && t > thr[row]) thr[row] = t;
+}
+
+// per query row: candidates -> prune -> exact rescoring -> ordered top-k.  Rows that cannot be
+// finished here (overflowed lists / too many survivors) are flagged for the exact fallback.
+__global__ void __launch_bounds__(256)
+final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
+                    const int32_t* __restrict__ cand_n, int n_slices, int cap, const float* __restrict__ eps,
+                    const float* __restrict__ Q, const float* __restrict__ E, int d, const float* __restrict__ bias,
+                    int k, int64_t id_base, int64_t id_stride, int64_t* __restrict__ out_ids,
+                    float* __restrict__ out_scores, int32_t* __restrict__ fallback_flag) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
+  int32_t* ci = reinterpret_cast<int32_t*>(cs + kFinalCap);      // [kFinalCap]
+  float* ks = reinterpret_cast<float*>(ci + kFinalCap);          // [kKeepCap] exact scores
+  int32_t* ki = reinterpret_cast<int32_t*>(ks + kKeepCap);       // [kKeepCap]
+  float* qrow = reinterpret_cast<float*>(ki + kKeepCap);         // [d]
+  __shared__ int hist[256];
+  __shared__ uint32_t sh[2];
+  __shared__ int s_total, s_over, s_keep;
+  __shared__ int offs[kMaxLists + 1];
+  const int row = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
+  if (threadIdx.x == 0) s_keep = 0;
+  load_candidate_lists(row, cand_s, cand_i, cand_n, n_slices, cap, cs, ci, offs, hist, &s_total, &s_over);
   if (s_over) {
     if (threadIdx.x == 0) fallback_flag[row] = 1;
     return;
   }
-  // gather the lists flat: candidate i belongs to the list whose offset range holds i (binary search), so all
-  // loads of a thread are independent (order irrelevant: the final ordering is a strict total order)
-  {
-    const int tot = s_total;
-    for (int i = threadIdx.x; i < tot; i += 256) {
-      int a = 0, b = n_slices;           // largest l with offs[l] <= i
-      while (b - a > 1) {
-        const int mid = (a + b) >> 1;
-        if (offs[mid] <= i) a = mid; else b = mid;
-      }
-      const int64_t src = (static_cast<int64_t>(row) * n_slices + a) * cap + (i - offs[a]);
-      cs[i] = cand_s[src];
-      ci[i] = cand_i[src];
-    }
-  }
-  __syncthreads();
   const int total = s_total;
   float cut = -INFINITY;
   if (total > k) cut = block_kth_largest(cs, total, k, hist, sh) - 2.f * eps[row];
@@ -1147,6 +1178,7 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 
 struct Tc16Plan {
   int m_tiles, groups, MT, TN, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap, stages;
+  int seg[3];   // main-pass segment ends in tiles: [0, seg0) | [seg0, seg1) | [seg1, total)
   size_t smem;
   int64_t off_thr, off_eps, off_epsin, off_flag, off_cand_n, off_q16, off_dump, off_cand_s, off_cand_i, total;
 };
@@ -1162,12 +1194,22 @@ static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   p.n_slices = kNumSMs / p.groups;
   if (p.n_slices < 1) p.n_slices = 1;
   if (p.n_slices > p.total_tiles) p.n_slices = p.total_tiles;
-  // pilot: 1/32 of the table (at least 16384 items): the k-th best pilot score lets ~32 k candidates through
-  const int min_tiles = 16384 / p.TN;
-  p.pilot_tiles = p.total_tiles / 32 > min_tiles ? p.total_tiles / 32 : min_tiles;
+  // pilot: 8192 items spread over the table.  Its k-th best score only has to carry the first segment of the
+  // main pass: the threshold is then refined from the candidates found so far (see catalog_topk_tc16)
+  p.pilot_tiles = 8192 / p.TN;
   if (p.pilot_tiles > p.total_tiles) p.pilot_tiles = p.total_tiles;
   p.pilot_step = p.total_tiles / p.pilot_tiles;
-  const double expect = static_cast<double>(k) * p.total_tiles / p.pilot_tiles / (p.n_slices * kParts);
+  p.seg[0] = static_cast<int>(10ll * 8192 / p.TN);             // ~80k items at the pilot threshold
+  p.seg[1] = p.seg[0] + static_cast<int>(40ll * 8192 / p.TN);  // ~320k items at the first refinement
+  if (p.seg[0] > p.total_tiles) p.seg[0] = p.total_tiles;
+  if (p.seg[1] > p.total_tiles) p.seg[1] = p.total_tiles;
+  p.seg[2] = p.total_tiles;
+  // expected candidates per row: k * (seg0 / pilot + (seg1 - seg0) / seg0 + (total - seg1) / seg1)
+  const double pil = static_cast<double>(p.pilot_tiles);
+  double cands = static_cast<double>(k) * p.seg[0] / pil;
+  if (p.seg[1] > p.seg[0]) cands += static_cast<double>(k) * (p.seg[1] - p.seg[0]) / p.seg[0];
+  if (p.seg[2] > p.seg[1]) cands += static_cast<double>(k) * (p.seg[2] - p.seg[1]) / p.seg[1];
+  const double expect = cands / (p.n_slices * kParts);
   p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
   const int kblocks = static_cast<int>(d / kKB16);
   const size_t q_bytes = static_cast<size_t>(p.MT) * kblocks * kQBlock16;
@@ -1259,6 +1301,8 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
   if (!attr_done) {
     cudaError_t e1 = cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaError_t e2 = cudaFuncSetAttribute(pilot_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e2 == cudaSuccess)
+      e2 = cudaFuncSetAttribute(refine_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e1 != cudaSuccess || e2 != cudaSuccess) return static_cast<int>(e1 != cudaSuccess ? e1 : e2);
     attr_done = true;
   }
@@ -1280,6 +1324,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
   P.cand_i = cand_i;
   P.cand_n = cand_n;
   P.cap = pl.cap;
+  P.append = 0;
   // 1. pilot
   P.tile_begin = 0;
   P.tile_step = pl.pilot_step;
@@ -1295,10 +1340,29 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
       dump, P.ld_dump, P.ld_dump, static_cast<int>(k), queries, static_cast<int>(d), stats, eps_in, thr, eps,
       stage_pilot ? 1 : 0);
   if ((st = launch_status()) != PSB_OK) return st;
-  // 3. main pass
+  // 3. main pass in three growing segments; after each of the first two the threshold is refined from the
+  //    candidates found so far (the k-th best of 80k / 400k items prunes 10x / 40x harder than the pilot's), which
+  //    keeps the epilogue's slow path -- appending a candidate -- rare for most of the table
   P.tile_step = 1;
-  P.n_tiles = pl.total_tiles;
-  if ((st = launch_tc16<false>(pl.MT, dim3(pl.n_slices, pl.groups), pl.smem, s, map_q, map_e, P)) != PSB_OK) return st;
+  P.append = 0;
+  int seg_lo = 0;
+  for (int sgi = 0; sgi < 3; ++sgi) {
+    const int seg_hi = pl.seg[sgi];
+    if (seg_hi > seg_lo) {
+      P.tile_begin = seg_lo;
+      P.n_tiles = seg_hi - seg_lo;
+      const int slices = pl.n_slices;   // the bucket index of a candidate list must not depend on the segment
+      if ((st = launch_tc16<false>(pl.MT, dim3(slices, pl.groups), pl.smem, s, map_q, map_e, P)) != PSB_OK) return st;
+      P.append = 1;
+      if (sgi < 2 && seg_hi < pl.total_tiles) {
+        PSB_PROF("refine_threshold_kernel", s);
+        refine_threshold_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(kFinalCap) * 4, s>>>(
+            cand_s, cand_n, pl.n_slices * kParts, pl.cap, eps, static_cast<int>(k), thr);
+        if ((st = launch_status()) != PSB_OK) return st;
+      }
+    }
+    seg_lo = seg_hi > seg_lo ? seg_hi : seg_lo;
+  }
   // 4. final select + exact fp32 rescoring, 5. exact fallback for flagged rows
   const size_t fsmem = static_cast<size_t>(kFinalCap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
   PSB_PROF("final_select_kernel", s);
