@@ -195,13 +195,14 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_wait(b_full + st, ph);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTN);
+        const uint64_t a_base = umma_desc(smem_u32(sA));
+        const uint64_t b_base = umma_desc(smem_u32(sB + st * tile_bytes));
+#pragma unroll 4
         for (int kb = 0; kb < P.kblocks; ++kb) {
-          const uint32_t a_addr = smem_u32(sA + kb * kKBBytes);
-          const uint32_t b_addr = smem_u32(sB + st * tile_bytes + kb * kKBBytes);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K = 8 tf32 = 32 bytes) inside one 128-byte swizzle row
-            if (!(P.debug & 2)) tc_mma_tf32(d_addr, umma_desc(a_addr + k4 * 32), umma_desc(b_addr + k4 * 32), kIdesc,
-                        (kb | k4) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_addr, a_base + static_cast<uint64_t>(kb) * (kKBBytes >> 4) + k4 * 2,
+                        b_base + static_cast<uint64_t>(kb) * (kKBBytes >> 4) + k4 * 2, kIdesc, (kb | k4) != 0 ? 1u : 0u);
         }
         tc_commit(b_empty + st);   // smem stage free once these MMAs have read it
         tc_commit(t_full + acc);   // accumulator ready for the epilogue
@@ -407,6 +408,11 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ===== MMA issuer =====
     if (lane == 0) {
       mbar_wait(a_full, 0);
+      // one thread issues every MMA of the CTA, so its instruction stream is on the critical path: descriptors
+      // are the base descriptor plus an address offset (>> 4, low 14 bits), never rebuilt per MMA
+      const uint64_t a_base = umma_desc(smem_u32(sA));
+      const uint64_t b_base = umma_desc(smem_u32(sB));
+      const uint32_t kb_a = kQBlock16 >> 4, kb_b = e_block >> 4, st_b = stage_bytes >> 4;
       for (int it = 0; it < my_tiles; ++it) {
         const int st = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -415,15 +421,17 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(t_empty + acc, aph ^ 1);
         mbar_wait(b_full + st, ph);
         tc_fence_after();
+        const uint64_t b_tile = b_base + static_cast<uint64_t>(st) * st_b;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols + mt * TN);
+          const uint64_t a_tile = a_base + static_cast<uint64_t>(mt * P.kblocks) * kb_a;
+#pragma unroll 2
           for (int kb = 0; kb < P.kblocks; ++kb) {
-            const uint32_t a_addr = smem_u32(sA + (mt * P.kblocks + kb) * kQBlock16);
-            const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(st) * stage_bytes + kb * e_block);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K = 16 halves = 32 bytes) inside one 128-byte swizzle row
-              tc_mma_f16(d_addr, umma_desc(a_addr + k4 * 32), umma_desc(b_addr + k4 * 32), kIdesc16, (kb | k4) != 0 ? 1u : 0u);
+              tc_mma_f16(d_addr, a_tile + static_cast<uint64_t>(kb) * kb_a + k4 * 2, b_tile + static_cast<uint64_t>(kb) * kb_b + k4 * 2,
+                         kIdesc16, (kb | k4) != 0 ? 1u : 0u);
           }
         }
         tc_commit(b_empty + st);
@@ -492,23 +500,31 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (ok) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * TN + c0 + i] = id < P.n_items ? sc : -INFINITY;
           }
         } else if (full_tile) {
-          // branch once per 8 scores: almost every group is below the threshold
+          // one branch per 32 scores (almost never taken once the threshold is refined), then one per 8
+          float mx8[4];
 #pragma unroll
-          for (int g8 = 0; g8 < 32; g8 += 8) {
-            float mx = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
-                             fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
-            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
-                                 fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
-            if (!(mx < th)) {
+          for (int g = 0; g < 4; ++g) {
+            const int g8 = g * 8;
+            const float m0 = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
+                                   fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
+            mx8[g] = fmaxf(m0, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
+                                     fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
+          }
+          if (!(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])) < th)) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float sc = __uint_as_float(v[g8 + i]);
-                if (!(sc < th)) {
-                  if (cn < P.cap) {
-                    P.cand_s[li + cn] = sc;
-                    P.cand_i[li + cn] = id0 + g8 + i;
+            for (int g = 0; g < 4; ++g) {
+              const int g8 = g * 8;
+              if (!(mx8[g] < th)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sc = __uint_as_float(v[g8 + i]);
+                  if (!(sc < th)) {
+                    if (cn < P.cap) {
+                      P.cand_s[li + cn] = sc;
+                      P.cand_i[li + cn] = id0 + g8 + i;
+                    }
+                    ++cn;
                   }
-                  ++cn;
                 }
               }
             }
@@ -764,7 +780,7 @@ __device__ __forceinline__ void load_candidate_lists(int row, const float* __res
                                                      const int32_t* __restrict__ cand_i,
                                                      const int32_t* __restrict__ cand_n, int n_lists, int cap,
                                                      float* cs, int32_t* ci, int* offs, int* hist, int* s_total,
-                                                     int* s_over) {
+                                                     int* s_over, int final_cap) {
   for (int l = threadIdx.x; l < n_lists; l += 256) offs[l + 1] = cand_n[static_cast<int64_t>(row) * n_lists + l];
   if (threadIdx.x == 0) offs[0] = 0;
   __syncthreads();
@@ -807,7 +823,7 @@ __device__ __forceinline__ void load_candidate_lists(int row, const float* __res
     if (threadIdx.x == 255) {
       offs[n_lists] = run;
       *s_total = run;
-      *s_over = any_over | (run > kFinalCap);
+      *s_over = any_over | (run > final_cap);
     }
   }
   __syncthreads();
@@ -832,7 +848,7 @@ __device__ __forceinline__ void load_candidate_lists(int row, const float* __res
 // approximate score is a (much) tighter lower bound than the pilot's, so thr[row] = max(thr[row], kth - 2 eps).
 __global__ void __launch_bounds__(256)
 refine_threshold_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_n, int n_lists, int cap,
-                        const float* __restrict__ eps, int k, float* __restrict__ thr) {
+                        const float* __restrict__ eps, int k, float* __restrict__ thr, int final_cap) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
   __shared__ int hist[256];
@@ -840,7 +856,7 @@ refine_threshold_kernel(const float* __restrict__ cand_s, const int32_t* __restr
   __shared__ int s_total, s_over;
   __shared__ int offs[kMaxLists + 1];
   const int row = blockIdx.x;
-  load_candidate_lists(row, cand_s, nullptr, cand_n, n_lists, cap, cs, nullptr, offs, hist, &s_total, &s_over);
+  load_candidate_lists(row, cand_s, nullptr, cand_n, n_lists, cap, cs, nullptr, offs, hist, &s_total, &s_over, final_cap);
   if (s_over || s_total < k) return;      // keep the current threshold (an overflowed row ends in the fallback)
   const float e = eps[row];
   if (!(e < 3.0e38f)) return;
@@ -855,11 +871,11 @@ final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict_
                     const int32_t* __restrict__ cand_n, int n_slices, int cap, const float* __restrict__ eps,
                     const float* __restrict__ Q, const float* __restrict__ E, int d, const float* __restrict__ bias,
                     int k, int64_t id_base, int64_t id_stride, int64_t* __restrict__ out_ids,
-                    float* __restrict__ out_scores, int32_t* __restrict__ fallback_flag) {
+                    float* __restrict__ out_scores, int32_t* __restrict__ fallback_flag, int final_cap) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  float* cs = reinterpret_cast<float*>(sm_raw);                 // [kFinalCap]
-  int32_t* ci = reinterpret_cast<int32_t*>(cs + kFinalCap);      // [kFinalCap]
-  float* ks = reinterpret_cast<float*>(ci + kFinalCap);          // [kKeepCap] exact scores
+  float* cs = reinterpret_cast<float*>(sm_raw);                 // [final_cap]
+  int32_t* ci = reinterpret_cast<int32_t*>(cs + final_cap);      // [final_cap]
+  float* ks = reinterpret_cast<float*>(ci + final_cap);          // [kKeepCap] exact scores
   int32_t* ki = reinterpret_cast<int32_t*>(ks + kKeepCap);       // [kKeepCap]
   float* qrow = reinterpret_cast<float*>(ki + kKeepCap);         // [d]
   __shared__ int hist[256];
@@ -869,7 +885,7 @@ final_select_kernel(const float* __restrict__ cand_s, const int32_t* __restrict_
   const int row = blockIdx.x;
   for (int c = threadIdx.x; c < d; c += 256) qrow[c] = Q[static_cast<int64_t>(row) * d + c];
   if (threadIdx.x == 0) s_keep = 0;
-  load_candidate_lists(row, cand_s, cand_i, cand_n, n_slices, cap, cs, ci, offs, hist, &s_total, &s_over);
+  load_candidate_lists(row, cand_s, cand_i, cand_n, n_slices, cap, cs, ci, offs, hist, &s_total, &s_over, final_cap);
   if (s_over) {
     if (threadIdx.x == 0) fallback_flag[row] = 1;
     return;
@@ -1152,7 +1168,7 @@ int catalog_topk_tc(const float* queries, int64_t m, const float* table, int64_t
   PSB_PROF("final_select_kernel", s);
   final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
                                                               table, static_cast<int>(d), bias, static_cast<int>(k),
-                                                              id_base, id_stride, out_ids, out_scores, flag);
+                                                              id_base, id_stride, out_ids, out_scores, flag, kFinalCap);
   if ((st = launch_status()) != PSB_OK) return st;
   // 5. exact fallback for flagged rows (returns immediately for unflagged ones)
   PSB_PROF("fallback_rows_kernel", s);
@@ -1179,6 +1195,7 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 struct Tc16Plan {
   int m_tiles, groups, MT, TN, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap, stages;
   int seg[3];   // main-pass segment ends in tiles: [0, seg0) | [seg0, seg1) | [seg1, total)
+  int final_cap; // candidates per row the select kernels hold in shared memory (4x the expectation: several CTAs / SM)
   size_t smem;
   int64_t off_thr, off_eps, off_epsin, off_flag, off_cand_n, off_q16, off_dump, off_cand_s, off_cand_i, total;
 };
@@ -1211,6 +1228,8 @@ static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   if (p.seg[2] > p.seg[1]) cands += static_cast<double>(k) * (p.seg[2] - p.seg[1]) / p.seg[1];
   const double expect = cands / (p.n_slices * kParts);
   p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
+  p.final_cap = (static_cast<int>(4.0 * cands) + 1024 + 255) / 256 * 256;
+  if (p.final_cap > kFinalCap) p.final_cap = kFinalCap;
   const int kblocks = static_cast<int>(d / kKB16);
   const size_t q_bytes = static_cast<size_t>(p.MT) * kblocks * kQBlock16;
   const size_t stage_bytes = static_cast<size_t>(kblocks) * p.TN * 128;
@@ -1356,19 +1375,19 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
       P.append = 1;
       if (sgi < 2 && seg_hi < pl.total_tiles) {
         PSB_PROF("refine_threshold_kernel", s);
-        refine_threshold_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(kFinalCap) * 4, s>>>(
-            cand_s, cand_n, pl.n_slices * kParts, pl.cap, eps, static_cast<int>(k), thr);
+        refine_threshold_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(pl.final_cap) * 4, s>>>(
+            cand_s, cand_n, pl.n_slices * kParts, pl.cap, eps, static_cast<int>(k), thr, pl.final_cap);
         if ((st = launch_status()) != PSB_OK) return st;
       }
     }
     seg_lo = seg_hi > seg_lo ? seg_hi : seg_lo;
   }
   // 4. final select + exact fp32 rescoring, 5. exact fallback for flagged rows
-  const size_t fsmem = static_cast<size_t>(kFinalCap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
+  const size_t fsmem = static_cast<size_t>(pl.final_cap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
   PSB_PROF("final_select_kernel", s);
   final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
                                                               table, static_cast<int>(d), bias, static_cast<int>(k),
-                                                              id_base, id_stride, out_ids, out_scores, flag);
+                                                              id_base, id_stride, out_ids, out_scores, flag, pl.final_cap);
   if ((st = launch_status()) != PSB_OK) return st;
   PSB_PROF("fallback_rows_kernel", s);
   fallback_rows_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(d) * 4, s>>>(
