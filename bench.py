@@ -60,6 +60,8 @@ class ClockSampler(object):
         self.rows, self.proc, self.index = [], None, index
 
     def __enter__(self):
+        if self.index is None:      # other ranks: no sampler (one nvidia-smi poller per box is enough)
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -268,6 +270,14 @@ def run_b200_arm(a):
         raise RuntimeError("bench.py --impl b200 needs a GPU (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # one launching thread per rank on its own cores: the replayed step is ~1 ms, so a descheduled host thread
+        # on one rank stalls every rank at the next cross-GPU barrier
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from prodsearch_b200 import _lib, ops, synth
     from prodsearch_b200.item_transformer import ItemTransformerRanker, ShardedItemTransformerRanker
@@ -340,16 +350,30 @@ def run_b200_arm(a):
         step(devb[it])
     # ---- timed region 1: device-resident batches, CUDA events per step, L2 flushed between steps
     barrier()
+    if transport == "nvlink-peer":
+        pg.wait_cycles.zero_()
     l0 = _lib.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local if rank == 0 else None) as clocks:
         for it in range(a.steps):
             flush.zero_()
             starts[it].record()
             step(devb[a.warmup + it])
             ends[it].record()
         barrier()
+    barrier_wait = None
+    if transport == "nvlink-peer":
+        # SM cycles every rank spent inside the three cross-GPU barriers of a step (waiting for the slowest peer)
+        wc = pg.wait_cycles.to(torch.float64) / a.steps / 1965.0      # us per step at the nominal SM clock
+        allw = [torch.empty_like(wc) for _ in range(world)]
+        dist.all_gather(allw, wc)
+        st_ = torch.stack(allw)
+        barrier_wait = {"per_position_us_mean_over_ranks": [round(float(x), 1) for x in st_.mean(0)],
+                        "per_position_us_max_over_ranks": [round(float(x), 1) for x in st_.max(0).values],
+                        "total_us_rank0": round(float(st_[0].sum()), 1),
+                        "note": "position = barrier epoch % 4 (three barriers per step rotate through the slots)"}
+        pg.check_errors()
     launches = _lib.launch_count() - l0
     if graphed is not None:       # replays do not pass through the library's host counter
         launches = graphed.launches_per_replay * a.steps
@@ -480,7 +504,8 @@ def run_b200_arm(a):
         "config": dict(WORKLOAD, workload="BASELINE configs[1]: TEM item_transformer train step, batch 384/GPU",
                        dropout=a.dropout, l2="flushed between timed steps (256 MiB write), flush not timed",
                        parallelism="dp%d, item/word tables %s" % (world, "row-sharded (%s)" % transport if world > 1 else "local"),
-                       launch="CUDA graph replay of the whole step" if graphed is not None else "eager"),
+                       launch="CUDA graph replay of the whole step" if graphed is not None else "eager",
+                       peer_barrier_wait=barrier_wait),
         "clocks": clocks.summary(),
         "e2e": {"value": B * a.steps * world / e2e_sec, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_sec / a.steps * 1e3},

@@ -362,9 +362,11 @@ int psb_peer_close(void* p);
 /* Cross-GPU barrier on the launching streams of all G ranks.  flag_blocks: HOST array of G device pointers,
  * flag_blocks[r] = rank r's flag block (uint32[PSB_PEER_MAX], zero-initialised peer memory).  *epoch_dev (local
  * device uint32, starts at 0) counts the barriers of this rank.  A rank that waits longer than timeout_cycles
- * (<= 0: about 2 s) stops waiting and writes 1 + the missing peer into *err_dev instead of hanging. */
+ * (<= 0: about 2 s) stops waiting and writes 1 + the missing peer into *err_dev instead of hanging.
+ * wait_cycles_dev (optional, uint64[4]): SM cycles this rank spent inside the barrier, accumulated per
+ * epoch % 4 -- how long a rank waits for its peers at each barrier position of a replayed step. */
 int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
-                     int32_t* err_dev, int64_t timeout_cycles, psb_stream_t stream);
+                     int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, psb_stream_t stream);
 
 /* out[i,:] = shard[idx[i] % G][idx[i] / G, :]: the forward "fetch" of a row-sharded table (bit-exact copies,
  * 128-bit loads over NVLink for remote owners) into a local mini table.  shards: HOST array of G device
@@ -398,9 +400,10 @@ typedef struct psb_fold_table {
 int psb_peer_fold_lists(const psb_fold_table_t* tables /* host */, int32_t n_tables, int32_t rank, int32_t G,
                         float scale, const uint32_t* stamp_dev, psb_stream_t stream);
 
-/* out[i] = scale * sum_r bufs[r][i], r ascending (one-shot all-reduce of the replicated dense gradients;
- * every rank computes the identical sum).  bufs: HOST array of G device pointers (peer memory). */
-int psb_peer_allreduce(const void* const* bufs, int32_t G, int64_t n, float scale, float* out,
+/* out[i] = scale * sum_r bufs[r][i], added in ascending r (one-shot all-reduce of the replicated dense
+ * gradients; every rank computes the identical sum) but LOADED starting at the caller's own rank, so the G
+ * readers never all pull from the same GPU at once.  bufs: HOST array of G device pointers (peer memory). */
+int psb_peer_allreduce(const void* const* bufs, int32_t G, int32_t rank, int64_t n, float scale, float* out,
                        psb_stream_t stream);
 
 /* *sqnorm_out = sum_r *slots[r] (r ascending): the GLOBAL squared gradient norm from the partial norms every rank

@@ -96,12 +96,12 @@ SIGNATURES = {
     "psb_peer_export": (c_i32, [c_vp, ctypes.c_char_p]),
     "psb_peer_open": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "psb_peer_close": (c_i32, [c_vp]),
-    "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "psb_peer_gather_rows": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
                                      c_vp, c_vp]),
     "psb_peer_fold_lists": (c_i32, [ctypes.POINTER(FoldTable), c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "psb_peer_sum_sqnorm": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_vp, c_vp, c_vp]),
-    "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_f32, c_vp, c_vp]),
+    "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
     "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,

@@ -35,9 +35,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // flags.p[r] = rank r's flag block (uint32[kMaxPeers], in r's peer memory).  Thread t signals peer t by writing
 // the new epoch into flags[t][rank] and waits until flags[rank][t] reaches it.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int rank, int G, uint32_t* __restrict__ epoch,
-                                                          int32_t* __restrict__ err, long long timeout_cycles) {
+                                                          int32_t* __restrict__ err, long long timeout_cycles,
+                                                          unsigned long long* __restrict__ wait_cycles) {
   __shared__ uint32_t e_sh;
   const int t = threadIdx.x;
+  const long long t_in = clock64();
   if (t == 0) {
     e_sh = *epoch + 1u;
     *epoch = e_sh;
@@ -58,6 +60,10 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int ra
       __nanosleep(64);
     }
     __threadfence_system();
+  }
+  if (wait_cycles != nullptr) {   // time this rank spent in the barrier, per position of the barrier in the step
+    __syncwarp();
+    if (t == 0) wait_cycles[e & 3u] += static_cast<unsigned long long>(clock64() - t_in);
   }
 }
 
@@ -184,18 +190,36 @@ __global__ void __launch_bounds__(256) peer_fold_kernel(const FoldArgs a) {
   }
 }
 
+// Loads are issued in a STAGGERED peer order (rank, rank + 1, ...: every rank starts with a different source, so
+// no GPU's NVLink egress serves all readers at once) but added in rank order 0..G-1, so every rank computes the
+// bit-identical sum.
 __global__ void __launch_bounds__(256)
-peer_allreduce_kernel(PeerPtrs bufs, int G, int64_t n, float scale, float* __restrict__ out) {
+peer_allreduce_kernel(PeerPtrs bufs, int G, int rank, int64_t n, float scale, float* __restrict__ out) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t n4 = n >> 2;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v[kMaxPeers];
+#pragma unroll
+    for (int j = 0; j < kMaxPeers; ++j) {
+      if (j < G) {
+        int r = rank + j;
+        r = r >= G ? r - G : r;
+        const float4 x = ldg_row4(static_cast<const float4*>(bufs.p[r]) + i);
+        // place by source rank without dynamic register indexing
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+          if (q == r) v[q] = x;
+      }
+    }
     float4 acc = zero4();
-    for (int r = 0; r < G; ++r) {
-      const float4 v = ldg_row4(static_cast<const float4*>(bufs.p[r]) + i);
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+      if (q < G) {
+        acc.x += v[q].x;
+        acc.y += v[q].y;
+        acc.z += v[q].z;
+        acc.w += v[q].w;
+      }
     }
     acc.x *= scale;
     acc.y *= scale;
@@ -273,7 +297,7 @@ static int fill_ptrs(PeerPtrs* P, const void* const* host_ptrs, int32_t G) {
 }
 
 extern "C" int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
-                                int32_t* err_dev, int64_t timeout_cycles, psb_stream_t stream) {
+                                int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, psb_stream_t stream) {
   PeerPtrs F;
   int st = fill_ptrs(&F, flag_blocks, G);
   if (st != PSB_OK) return st;
@@ -281,7 +305,8 @@ extern "C" int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, in
   if (timeout_cycles <= 0) timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("peer_barrier_kernel", s);
-  peer_barrier_kernel<<<1, 32, 0, s>>>(F, rank, G, epoch_dev, err_dev, timeout_cycles);
+  peer_barrier_kernel<<<1, 32, 0, s>>>(F, rank, G, epoch_dev, err_dev, timeout_cycles,
+                                       reinterpret_cast<unsigned long long*>(wait_cycles_dev));
   return launch_status();
 }
 
@@ -356,19 +381,19 @@ extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tab
   return launch_status();
 }
 
-extern "C" int psb_peer_allreduce(const void* const* bufs, int32_t G, int64_t n, float scale, float* out,
+extern "C" int psb_peer_allreduce(const void* const* bufs, int32_t G, int32_t rank, int64_t n, float scale, float* out,
                                   psb_stream_t stream) {
   PeerPtrs B;
   int st = fill_ptrs(&B, bufs, G);
   if (st != PSB_OK) return st;
-  if (out == nullptr || n < 0) return PSB_E_ARG;
+  if (out == nullptr || n < 0 || rank < 0 || rank >= G) return PSB_E_ARG;
   for (int i = 0; i < G; ++i)
     if (misaligned16(B.p[i])) return PSB_E_ALIGN;
   if (misaligned16(out)) return PSB_E_ALIGN;
   if (n == 0) return PSB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("peer_allreduce_kernel", s);
-  peer_allreduce_kernel<<<grid_for(n, 256 * 4, 4), 256, 0, s>>>(B, G, n, scale, out);
+  peer_allreduce_kernel<<<grid_for(n, 256 * 4, 4), 256, 0, s>>>(B, G, rank, n, scale, out);
   return launch_status();
 }
 

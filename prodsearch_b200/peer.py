@@ -91,6 +91,7 @@ class PeerGroup(object):
         self.flags = self.alloc(4 * _lib.PEER_MAX)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.wait_cycles = torch.zeros(4, dtype=torch.int64, device=self.device)   # per barrier position (epoch % 4)
         self.timeout_cycles = 0
 
     @classmethod
@@ -146,7 +147,8 @@ class PeerGroup(object):
         if self.world == 1 or self._sim is not None:
             return
         check(load().psb_peer_barrier(self.flags.ptr_array(), self.rank, self.world, self.epoch.data_ptr(),
-                                      self.err.data_ptr(), int(self.timeout_cycles), stream_ptr()),
+                                      self.err.data_ptr(), int(self.timeout_cycles), self.wait_cycles.data_ptr(),
+                                      stream_ptr()),
               "psb_peer_barrier")
 
     def fold_stamp(self):
@@ -168,7 +170,7 @@ class PeerGroup(object):
 
     def allreduce(self, buf, n, out, scale=1.0, offset=0):
         """out[:n] = scale * sum over ranks of the fp32 vectors at ``offset`` of the symmetric ``buf``."""
-        check(load().psb_peer_allreduce(buf.ptr_array(offset), self.world, int(n), float(scale), out.data_ptr(),
+        check(load().psb_peer_allreduce(buf.ptr_array(offset), self.world, self.rank, int(n), float(scale), out.data_ptr(),
                                         stream_ptr()), "psb_peer_allreduce")
         return out
 

@@ -44,20 +44,11 @@ def main():
     shd.zero_grad()
     loss.backward()
     shd.sync_grads()
-    total = None
-    ref.zero_grad()
-    for r in range(world):
-        br, nir, nwr = batches[r]
-        ref.injected_negatives = (nir.cuda(), nwr.cuda())
-        l = ref(dev(br))
-        if r == rank:
-            assert abs(float(l) - float(loss)) <= 1e-5 * abs(float(l)), (float(l), float(loss))
-        total = l if total is None else total + l
-    (total / world).backward()
+    ref_grads = reference_grads(ref, batches, dev, world, rank, float(loss))
     worst = 0.0
     for (k, p), (k2, p2) in zip(ref.named_parameters(), shd.named_parameters()):
         assert k == k2
-        g_ref = p.grad if p.grad is not None else torch.zeros_like(p)
+        g_ref = ref_grads[k]
         g = p2.grad if p2.grad is not None else torch.zeros_like(p2)
         if k == "product_emb.weight":
             g_ref = g_ref[rank::world]
@@ -75,6 +66,25 @@ def main():
         print("multi_gpu_check ok: world=%d, worst relative gradient error %.2e, sharded top-100 == unsharded" % (world, worst))
     peer_check(rank, world, cfg, ref, batches, dev)
     dist.destroy_process_group()
+
+
+def reference_grads(ref, batches, dev, world, rank, my_loss):
+    """Gradients of the UNsharded model for the mean over all ranks' batch losses.  One backward per batch (a
+    dense gradient sink holds at most 8 contributions and rewrites its buffer per backward), summed by hand."""
+    acc = {k: torch.zeros_like(p) for k, p in ref.named_parameters()}
+    for r in range(world):
+        br, nir, nwr = batches[r]
+        ref.injected_negatives = (nir.cuda(), nwr.cuda())
+        ref.zero_grad()
+        l = ref(dev(br))
+        if r == rank:
+            assert abs(float(l) - my_loss) <= 1e-5 * abs(float(l)), (float(l), my_loss)
+        (l / world).backward()
+        for k, p in ref.named_parameters():
+            if p.grad is not None:
+                acc[k] += p.grad
+    ref.zero_grad()
+    return acc
 
 
 def peer_check(rank, world, cfg, ref, batches, dev):
@@ -112,21 +122,12 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     m.zero_grad()
     loss.backward()
     m.sync_grads(opt)
-    ref.zero_grad()
-    total = None
-    for r in range(world):
-        br, nir, nwr = batches[r]
-        ref.injected_negatives = (nir.cuda(), nwr.cuda())
-        l = ref(padded(br))
-        if r == rank:
-            assert abs(float(l) - float(loss)) <= 1e-5 * abs(float(l)), (float(l), float(loss))
-        total = l if total is None else total + l
-    (total / world).backward()
+    ref_grads = reference_grads(ref, batches, padded, world, rank, float(loss))
     refp = dict(ref.named_parameters())
     sharded_keys = ("product_emb.weight", "word_embeddings.weight")
     worst = 0.0
     for k, p in m.named_parameters():
-        g_ref = refp[k].grad if refp[k].grad is not None else torch.zeros_like(refp[k])
+        g_ref = ref_grads[k]
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         if k in sharded_keys:
             g_ref = g_ref[rank::world]
@@ -134,6 +135,8 @@ def peer_check(rank, world, cfg, ref, batches, dev):
         err = float((g - g_ref).abs().max())
         assert err <= 1e-4 * scale + 2e-7, (k, err, scale)
         worst = max(worst, err / scale)
+    for k, p in ref.named_parameters():       # hand the summed gradients to the reference optimizer
+        p.grad = ref_grads[k]
     opt.step()
     ref_opt.step()
     tn = float(ref_opt.optimizer.total_norm)
@@ -147,10 +150,23 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     # sharded catalog ranking through the peer model == unsharded (the tables were just updated identically)
     q = torch.randn(5 + rank, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(19 + rank))
     ids, sc = m.rank_catalog(q, k=100)
-    ids_r, sc_r = ref.rank_catalog(q, k=100)
-    assert torch.equal(ids, ids_r) and torch.allclose(sc, sc_r, rtol=1e-5, atol=1e-5)
+    # reference: exact top-k over the table re-assembled from the shards (the shards just took an optimizer step;
+    # ranking against the separately updated unsharded copy would compare two slightly different tables)
+    from prodsearch_b200 import _lib, ops
+    shard = m.item_table.weight.detach()
+    rows_max = (P + 1 + world - 1) // world
+    pad = torch.zeros(rows_max, shard.shape[1], device="cuda")
+    pad[:shard.shape[0]] = shard
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    full = torch.zeros(P + 1, shard.shape[1], device="cuda")
+    for r in range(world):
+        n_r = (P + 1 - r + world - 1) // world
+        full[r::world] = parts[r][:n_r]
+    ids_r, sc_r = ops.catalog_topk(q, full, 100, n_items=P, mode=_lib.TOPK_EXACT)
+    assert torch.equal(ids, ids_r) and torch.equal(sc, sc_r)
     # ---- the whole multi-GPU step as one CUDA graph per rank
-    del loss, total, l           # drop the eager autograd graphs (their AccumulateGrad nodes live on this stream)
+    del loss                     # drop the eager autograd graphs (their AccumulateGrad nodes live on this stream)
     m.zero_grad()
     ref.zero_grad()
     m.injected_negatives = None
