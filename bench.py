@@ -356,11 +356,13 @@ def run_b200_arm(a):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     with ClockSampler(local if rank == 0 else None) as clocks:
+        t_host = time.perf_counter()
         for it in range(a.steps):
             flush.zero_()
             starts[it].record()
             step(devb[a.warmup + it])
             ends[it].record()
+        host_enqueue_ms = (time.perf_counter() - t_host) / a.steps * 1e3     # host time to enqueue one step
         barrier()
     barrier_wait = None
     if transport == "nvlink-peer":
@@ -369,10 +371,14 @@ def run_b200_arm(a):
         allw = [torch.empty_like(wc) for _ in range(world)]
         dist.all_gather(allw, wc)
         st_ = torch.stack(allw)
-        barrier_wait = {"per_position_us_mean_over_ranks": [round(float(x), 1) for x in st_.mean(0)],
-                        "per_position_us_max_over_ranks": [round(float(x), 1) for x in st_.max(0).values],
-                        "total_us_rank0": round(float(st_[0].sum()), 1),
-                        "note": "position = barrier epoch % 4 (three barriers per step rotate through the slots)"}
+        mine = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)) / a.steps, host_enqueue_ms],
+                            device="cuda", dtype=torch.float64)
+        allm = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        barrier_wait = {"us_per_step_by_rank": [[round(float(x), 1) for x in r_[:3]] for r_ in st_],
+                        "slots": ["A: step start", "B: gradient lists complete", "C: shard norms published"],
+                        "device_ms_per_step_by_rank": [round(float(x[0]), 4) for x in allm],
+                        "host_enqueue_ms_per_step_by_rank": [round(float(x[1]), 4) for x in allm]}
         pg.check_errors()
     launches = _lib.launch_count() - l0
     if graphed is not None:       # replays do not pass through the library's host counter

@@ -363,16 +363,18 @@ int psb_peer_close(void* p);
  * flag_blocks[r] = rank r's flag block (uint32[PSB_PEER_MAX], zero-initialised peer memory).  *epoch_dev (local
  * device uint32, starts at 0) counts the barriers of this rank.  A rank that waits longer than timeout_cycles
  * (<= 0: about 2 s) stops waiting and writes 1 + the missing peer into *err_dev instead of hanging.
- * wait_cycles_dev (optional, uint64[4]): SM cycles this rank spent inside the barrier, accumulated per
- * epoch % 4 -- how long a rank waits for its peers at each barrier position of a replayed step. */
+ * wait_cycles_dev (optional, uint64[4]): SM cycles this rank spent inside the barrier are added to
+ * wait_cycles_dev[wait_slot & 3] -- how long a rank waits for its peers at each barrier of a replayed step. */
 int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
-                     int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, psb_stream_t stream);
+                     int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, int32_t wait_slot,
+                     psb_stream_t stream);
 
 /* out[i,:] = shard[idx[i] % G][idx[i] / G, :]: the forward "fetch" of a row-sharded table (bit-exact copies,
  * 128-bit loads over NVLink for remote owners) into a local mini table.  shards: HOST array of G device
  * pointers.  remap_out (optional, [n]): the position each index is read at afterwards, remap_out[i] =
  * idx[i] == pad_id ? pad_pos : i, so that all pad entries share ONE mini-table position and the consuming
- * kernels keep their "idx != pad_idx" validity rule. */
+ * kernels keep their "idx != pad_idx" validity rule; the rows of pad entries other than position pad_pos are
+ * then not fetched (out is zero there). */
 int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_t rows_total, int64_t d,
                          const int64_t* idx, int64_t n, float* out, int64_t* remap_out, int64_t pad_id,
                          int64_t pad_pos, int32_t* err_flag, psb_stream_t stream);

@@ -96,7 +96,7 @@ SIGNATURES = {
     "psb_peer_export": (c_i32, [c_vp, ctypes.c_char_p]),
     "psb_peer_open": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "psb_peer_close": (c_i32, [c_vp]),
-    "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "psb_peer_barrier": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
     "psb_peer_gather_rows": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
                                      c_vp, c_vp]),
     "psb_peer_fold_lists": (c_i32, [ctypes.POINTER(FoldTable), c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // the new epoch into flags[t][rank] and waits until flags[rank][t] reaches it.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int rank, int G, uint32_t* __restrict__ epoch,
                                                           int32_t* __restrict__ err, long long timeout_cycles,
-                                                          unsigned long long* __restrict__ wait_cycles) {
+                                                          unsigned long long* __restrict__ wait_cycles, int slot) {
   __shared__ uint32_t e_sh;
   const int t = threadIdx.x;
   const long long t_in = clock64();
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int ra
   }
   if (wait_cycles != nullptr) {   // time this rank spent in the barrier, per position of the barrier in the step
     __syncwarp();
-    if (t == 0) wait_cycles[e & 3u] += static_cast<unsigned long long>(clock64() - t_in);
+    if (t == 0) wait_cycles[slot & 3] += static_cast<unsigned long long>(clock64() - t_in);
   }
 }
 
@@ -86,6 +86,9 @@ peer_gather_rows_kernel(PeerPtrs shards, int G, int64_t rows_total, int d4, cons
         if (remap != nullptr && lane == 0) remap[row] = v == pad_id ? pad_pos : row;
         if (v < 0 || v >= rows_total) {
           if (err != nullptr && lane == 0) *err = 1;
+        } else if (remap != nullptr && v == pad_id && row != pad_pos) {
+          // a pad entry is read at pad_pos, never at its own position: do not fetch the pad row thousands of
+          // times from its one owner (same-address peer reads serialise on that GPU's memory system)
         } else {
           src[i] = static_cast<const float4*>(shards.p[v % G]) + (v / G) * d4;
         }
@@ -297,7 +300,8 @@ static int fill_ptrs(PeerPtrs* P, const void* const* host_ptrs, int32_t G) {
 }
 
 extern "C" int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
-                                int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, psb_stream_t stream) {
+                                int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, int32_t wait_slot,
+                                psb_stream_t stream) {
   PeerPtrs F;
   int st = fill_ptrs(&F, flag_blocks, G);
   if (st != PSB_OK) return st;
@@ -306,7 +310,7 @@ extern "C" int psb_peer_barrier(const void* const* flag_blocks, int32_t rank, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("peer_barrier_kernel", s);
   peer_barrier_kernel<<<1, 32, 0, s>>>(F, rank, G, epoch_dev, err_dev, timeout_cycles,
-                                       reinterpret_cast<unsigned long long*>(wait_cycles_dev));
+                                       reinterpret_cast<unsigned long long*>(wait_cycles_dev), wait_slot);
   return launch_status();
 }
 

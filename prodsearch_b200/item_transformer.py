@@ -380,7 +380,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         L = u_item_idxs.shape[1]
         self.item_table.reserve_stage(2 * B * (L + 2 + K))                       # collective on first use only
         self.word_table.reserve_stage(2 * B * (query_word_idxs.shape[1] + W * (1 + K)))
-        self.peer.barrier()        # every owner has finished last step's optimizer update / staging reads
+        self.peer.barrier(0)       # every owner has finished last step's optimizer update / staging reads
         items, (tgt, neg, hist), item_pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs])
         words, (qw, pw, nw), word_pad = self.word_table.fetch([query_word_idxs, pos_iword_idxs, neg_word_idxs])
         isink, wsink = self.item_table.sink, self.word_table.sink
@@ -422,11 +422,11 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         owned shards, all-reduce the replicated gradients, hand the GLOBAL clip norm to the optimizer.  Three
         phases separated by peer barriers (the single-process simulation of the tests calls them in lockstep)."""
         self.sync_stage()
-        self.peer.barrier()        # every rank's compact lists and dense bucket are complete
+        self.peer.barrier(1)       # every rank's compact lists and dense bucket are complete
         self.sync_fold()
         if optim is None or not hasattr(getattr(optim, "optimizer", optim), "set_global_sqnorm"):
             return
-        self.peer.barrier()        # every rank's shard norm is published
+        self.peer.barrier(2)       # every rank's shard norm is published
         self.sync_norm(optim)
 
     def sync_stage(self):

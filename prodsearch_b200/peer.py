@@ -91,7 +91,7 @@ class PeerGroup(object):
         self.flags = self.alloc(4 * _lib.PEER_MAX)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.wait_cycles = torch.zeros(4, dtype=torch.int64, device=self.device)   # per barrier position (epoch % 4)
+        self.wait_cycles = torch.zeros(4, dtype=torch.int64, device=self.device)   # per barrier call site (slot)
         self.timeout_cycles = 0
 
     @classmethod
@@ -141,14 +141,15 @@ class PeerGroup(object):
         return ptrs
 
     # ---- synchronisation ----------------------------------------------------------------------------------
-    def barrier(self):
-        """Stream-ordered barrier of all ranks (graph-capturable).  The simulated ranks of one process share
+    def barrier(self, slot=0):
+        """Stream-ordered barrier of all ranks (graph-capturable); ``slot`` (0..3) names the call site in the
+        ``wait_cycles`` statistics.  The simulated ranks of one process share
         a stream and are driven phase by phase in lockstep by the tests, so stream order already is the barrier."""
         if self.world == 1 or self._sim is not None:
             return
         check(load().psb_peer_barrier(self.flags.ptr_array(), self.rank, self.world, self.epoch.data_ptr(),
                                       self.err.data_ptr(), int(self.timeout_cycles), self.wait_cycles.data_ptr(),
-                                      stream_ptr()),
+                                      int(slot), stream_ptr()),
               "psb_peer_barrier")
 
     def fold_stamp(self):

@@ -120,13 +120,13 @@ def test_peer_barrier_two_streams_and_timeout():
     for _ in range(3):
         for g, s in zip(groups, streams):
             _lib.check(lib.psb_peer_barrier(g.flags.ptr_array(), g.rank, 2, g.epoch.data_ptr(), g.err.data_ptr(),
-                                            2_000_000_000, g.wait_cycles.data_ptr(), s.cuda_stream), "barrier")
+                                            2_000_000_000, g.wait_cycles.data_ptr(), 0, s.cuda_stream), "barrier")
     torch.cuda.synchronize()
     assert int(groups[0].err) == 0 and int(groups[1].err) == 0
     assert int(groups[0].epoch) == 3 and int(groups[1].epoch) == 3
     g = groups[0]
     _lib.check(lib.psb_peer_barrier(g.flags.ptr_array(), 0, 2, g.epoch.data_ptr(), g.err.data_ptr(), 2_000_000,
-                                    None, streams[0].cuda_stream), "barrier")
+                                    None, 0, streams[0].cuda_stream), "barrier")
     torch.cuda.synchronize()
     assert int(g.err) == 2                       # 1 + the rank that never arrived
     with pytest.raises(RuntimeError):
