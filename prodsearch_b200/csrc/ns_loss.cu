@@ -141,7 +141,7 @@ ns_loss_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ a
 // together with a halving butterfly (9 shuffles instead of 40), and each score's loss / gradient is
 // evaluated by the lanes that hold its sum instead of redundantly by all 32.
 template <bool HAS_B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3)
 ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ anchor_b,
                     const float4* __restrict__ table, int64_t table_rows, int d4,
                     const float* __restrict__ bias, const int64_t* __restrict__ pos_idx,
@@ -156,28 +156,55 @@ ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restric
   // which score this lane owns after the butterfly, and the lane that is its designated writer
   const int my_s = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const bool writer = (lane & 3) == 0;
+  // Software pipeline over (anchor, position): the index / weight / mask words of the NEXT position (and the
+  // anchor row + valid-count predicate of the next anchor) are requested right after the current position's row
+  // loads, so one anchor costs one dependent HBM round trip (its rows) instead of three (count, indices, rows).
+  auto fetch_meta = [&](int64_t i, int j, int64_t& idx_o, float& wt_o, uint8_t& mk_o) {
+    idx_o = -1;
+    wt_o = 0.f;
+    if (lane <= k) {
+      idx_o = lane == 0 ? pos_idx[i * w + j] : neg_idx[(i * w + j) * k + (lane - 1)];
+      wt_o = lane == 0 ? pos_weight : (neg_weight != nullptr ? neg_weight[i * k + (lane - 1)] : 1.f);
+    }
+    mk_o = mask != nullptr ? mask[i * w + j] : static_cast<uint8_t>(1);
+  };
+  auto count_pred = [&](int64_t i) {  // lane j < w: is position j of anchor i a valid target (w <= 32)
+    bool valid = false;
+    if (lane < w) valid = mask != nullptr ? mask[i * w + lane] != 0 : (pad_idx < 0 || pos_idx[i * w + lane] != pad_idx);
+    return valid;
+  };
+  if (warp >= n) return;
+  float4 a_n = col_ok ? anchor_a[warp * d4 + lane] : zero4();
+  bool cv_n = w <= 32 ? count_pred(warp) : false;
+  int64_t idx_n;
+  float wt_n;
+  uint8_t mk_n;
+  fetch_meta(warp, 0, idx_n, wt_n, mk_n);
   for (int64_t i = warp; i < n; i += nwarps) {
     int cnt = 0;
-    for (int j0 = 0; j0 < w; j0 += 32) {
-      const int j = j0 + lane;
-      bool valid = false;
-      if (j < w) valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pos_idx[i * w + j] != pad_idx);
-      cnt += __popc(__ballot_sync(kFull, valid));
+    if (w <= 32) {
+      cnt = __popc(__ballot_sync(kFull, cv_n));
+    } else {
+      for (int j0 = 0; j0 < w; j0 += 32) {
+        const int j = j0 + lane;
+        bool valid = false;
+        if (j < w) valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pos_idx[i * w + j] != pad_idx);
+        cnt += __popc(__ballot_sync(kFull, valid));
+      }
     }
     const float denom = static_cast<float>(cnt > 0 ? cnt : 1);
-    const float4 a = col_ok ? anchor_a[i * d4 + lane] : zero4();
+    const float4 a = a_n;
+    const int64_t i_next = i + nwarps;
     float4 ga = zero4();
     float loss_acc = 0.f;
     for (int j = 0; j < w; ++j) {
-      // lane s <= k fetches the index / bias / weight of score s
-      int64_t myidx = -1;
-      float mybias = 0.f, mywt = 0.f;
-      if (lane <= k) {
-        myidx = lane == 0 ? pos_idx[i * w + j] : neg_idx[(i * w + j) * k + (lane - 1)];
-        mywt = lane == 0 ? pos_weight : (neg_weight != nullptr ? neg_weight[i * k + (lane - 1)] : 1.f);
-      }
+      // lane s <= k holds the index / weight of score s (fetched one position ahead)
+      int64_t myidx = idx_n;
+      float mybias = 0.f;
+      const float mywt = wt_n;
+      const uint8_t mk = mk_n;
       const int64_t pj = __shfl_sync(kFull, myidx, 0);
-      const bool valid = mask != nullptr ? mask[i * w + j] != 0 : (pad_idx < 0 || pj != pad_idx);
+      const bool valid = mask != nullptr ? mk != 0 : (pad_idx < 0 || pj != pad_idx);
       if (myidx < 0 || myidx >= table_rows) myidx = -1;
       if (bias != nullptr && myidx >= 0) mybias = bias[myidx];
       float4 row[8];
@@ -185,6 +212,13 @@ ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restric
       for (int s = 0; s < 8; ++s) {
         const int64_t r = __shfl_sync(kFull, myidx, s);
         row[s] = (r >= 0 && col_ok) ? ldg_row4(table + r * d4 + lane) : zero4();
+      }
+      if (j + 1 < w) {
+        fetch_meta(i, j + 1, idx_n, wt_n, mk_n);
+      } else if (i_next < n) {
+        fetch_meta(i_next, 0, idx_n, wt_n, mk_n);
+        a_n = col_ok ? anchor_a[i_next * d4 + lane] : zero4();
+        if (w <= 32) cv_n = count_pred(i_next);
       }
       float v[8];
 #pragma unroll

@@ -507,16 +507,39 @@ heads_write_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentin
 // partials in unit order.  Terms are therefore always added in ascending (contribution, slot)
 // order with a bracketing that depends only on (n_total, data): bit-reproducible, no atomics.
 // ------------------------------------------------------------------------------------
-template <int C>
+// Largest segment index whose start is <= pos, by a warp-wide 32-ary search: every step the 32 lanes probe 32
+// evenly spaced entries of seg_start (one L2 round trip narrows the range 32x; 3 trips for a TEM step's ~10k
+// segments, 5 for millions, instead of 14 / 22 dependent loads of a binary search).  seg_start[0] == 0.
+__device__ __forceinline__ int warp_find_segment(const int32_t* __restrict__ seg_start, int nu, int pos, int lane) {
+  int lo = 0, hi = nu;
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) >> 5;
+    const int probe = lo + (lane + 1) * step;
+    const bool le = probe < hi && seg_start[probe] <= pos;
+    const int c = __popc(__ballot_sync(kFull, le));
+    lo += c * step;
+    hi = min(hi, lo + step);
+  }
+  return lo;
+}
+
+// FULL: d4 == 32 * C (no column predicate: d = 128 with C = 1 is the reference's embedding size).
+// Per 32 sorted slots the lanes fetch the slot metadata in parallel and park (source pointer, scale, key) in
+// this warp's shared-memory slice; the row loop then reads them back as broadcasts, so the only warp
+// collectives are the two ballots per 32 slots and every branch of the row loop is warp-uniform.
+template <int C, bool FULL>
 __global__ void __launch_bounds__(256)
 seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __restrict__ sorted_slots,
                   const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ seg_start,
                   const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
                   float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
                   float4* __restrict__ partial, float* __restrict__ partial_bias) {
-  const int lane = threadIdx.x & 31;
+  __shared__ unsigned long long s_ptr[8][32];
+  __shared__ float s_sc[8][32];
+  __shared__ uint32_t s_key[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = blockIdx.x * (blockDim.x >> 5) + wid;
   const int nu = *n_unique;
   if (nu == 0) return;
   const int n_valid = seg_start[nu];
@@ -526,12 +549,7 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
   for (int unit = warp; unit < n_units; unit += nwarps) {
     const int u_lo = unit << ch_shift;
     const int u_hi = min(u_lo + ch, n_valid);
-    int a = 0, b = nu;  // largest seg with seg_start[seg] <= u_lo
-    while (b - a > 1) {
-      const int mid = (a + b) >> 1;
-      if (seg_start[mid] <= u_lo) a = mid; else b = mid;
-    }
-    int seg = a;
+    int seg = warp_find_segment(seg_start, nu, u_lo, lane);
     bool started_here = seg_start[seg] == u_lo;
     float4 acc[C];
 #pragma unroll
@@ -564,71 +582,76 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
       if (lane == 31 || q + 1 >= u_hi) key_next = (q + 1 < n_valid) ? sorted_keys[min(q + 1, n_valid - 1)] : 0xfffffffeu;
       const unsigned last_mask = __ballot_sync(kFull, in && key_next != key);
       const unsigned bias_mask = __ballot_sync(kFull, tb);
+      __syncwarp();  // the previous group's broadcasts have been read
+      s_ptr[wid][lane] = src;
+      s_sc[wid][lane] = sc;
+      s_key[wid][lane] = key;
+      __syncwarp();
       const int cnt = min(32, u_hi - p);
       for (int u0 = 0; u0 < cnt; u0 += U) {
         float4 v[U][C];
         float su[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int srcl = min(u0 + u, 31);
-          const unsigned long long ptr = __shfl_sync(kFull, src, srcl);
-          su[u] = __shfl_sync(kFull, sc, srcl);
-          const bool ok = u0 + u < cnt;
-          if (!ok) su[u] = 0.f;
+          const int j = u0 + u;  // < 32
+          const float4* ptr = reinterpret_cast<const float4*>(s_ptr[wid][j]);
+          su[u] = s_sc[wid][j];
+          const bool ok = j < cnt;
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const int col = lane + 32 * c;
-            v[u][c] = (ok && col < d4) ? __ldg(reinterpret_cast<const float4*>(ptr) + col) : zero4();
+            v[u][c] = (ok && (FULL || col < d4)) ? ldg_row4(ptr + col) : zero4();
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (u0 + u >= cnt) break;
+          const int j = u0 + u;
+          if (j < cnt) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) fma4(acc[c], su[u], v[u][c]);
-          if ((bias_mask >> (u0 + u)) & 1u) bacc += su[u];
-          open = true;
-          if ((last_mask >> (u0 + u)) & 1u) {
-            // segment `seg` ends at sorted position p + u0 + u
-            const uint32_t drow = __shfl_sync(kFull, key, u0 + u);
-            if (started_here) {
+            for (int c = 0; c < C; ++c) fma4(acc[c], su[u], v[u][c]);
+            if ((bias_mask >> j) & 1u) bacc += su[u];
+            if ((last_mask >> j) & 1u) {
+              // segment `seg` ends at sorted position p + j
+              if (started_here) {
+                const int64_t drow = s_key[wid][j];
 #pragma unroll
-              for (int c = 0; c < C; ++c) {
-                const int col = lane + 32 * c;
-                if (col < d4) {
-                  if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
-                  if (dense != nullptr) dense[static_cast<int64_t>(drow) * d4 + col] = acc[c];
+                for (int c = 0; c < C; ++c) {
+                  const int col = lane + 32 * c;
+                  if (FULL || col < d4) {
+                    if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+                    if (dense != nullptr) dense[drow * d4 + col] = acc[c];
+                  }
                 }
-              }
-              if (lane == 0) {
-                if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
-                if (dense_bias != nullptr) dense_bias[drow] = bacc;
-              }
-            } else {  // a run that began in an earlier unit: partial, combined by the fix-up kernel
-              const int64_t ps = static_cast<int64_t>(unit) * 2;
+                if (lane == 0) {
+                  if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+                  if (dense_bias != nullptr) dense_bias[drow] = bacc;
+                }
+              } else {  // a run that began in an earlier unit: partial, combined by the fix-up kernel
+                const int64_t ps = static_cast<int64_t>(unit) * 2;
 #pragma unroll
-              for (int c = 0; c < C; ++c) {
-                const int col = lane + 32 * c;
-                if (col < d4) partial[ps * d4 + col] = acc[c];
+                for (int c = 0; c < C; ++c) {
+                  const int col = lane + 32 * c;
+                  if (FULL || col < d4) partial[ps * d4 + col] = acc[c];
+                }
+                if (lane == 0) partial_bias[ps] = bacc;
               }
-              if (lane == 0) partial_bias[ps] = bacc;
+#pragma unroll
+              for (int c = 0; c < C; ++c) acc[c] = zero4();
+              bacc = 0.f;
+              ++seg;
+              started_here = true;
             }
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = zero4();
-            bacc = 0.f;
-            ++seg;
-            started_here = true;
-            open = false;
           }
         }
       }
+      open = ((last_mask >> (cnt - 1)) & 1u) == 0u;
     }
     if (open) {  // the last run continues into the next unit
       const int64_t ps = static_cast<int64_t>(unit) * 2 + (started_here ? 1 : 0);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int col = lane + 32 * c;
-        if (col < d4) partial[ps * d4 + col] = acc[c];
+        if (FULL || col < d4) partial[ps * d4 + col] = acc[c];
       }
       if (lane == 0) partial_bias[ps] = bacc;
     }
@@ -857,10 +880,12 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);
 #define PSB_SR_LAUNCH(C)                                                                                      \
   PSB_PROF("seg_reduce_kernel", s);                                                                            \
-  seg_reduce_kernel<C><<<grid, 256, 0, s>>>(T, sorted_slots, sorted_keys, seg_start, n_unique, d4, ch_shift,   \
-                                            reinterpret_cast<float4*>(reduced), reduced_bias,                 \
-                                            reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial,  \
-                                            partial_bias);                                                    \
+  {                                                                                                            \
+    auto kern = d4 == 32 * C ? seg_reduce_kernel<C, true> : seg_reduce_kernel<C, false>;                       \
+    kern<<<grid, 256, 0, s>>>(T, sorted_slots, sorted_keys, seg_start, n_unique, d4, ch_shift,                 \
+                              reinterpret_cast<float4*>(reduced), reduced_bias,                                \
+                              reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial, partial_bias);  \
+  }                                                                                                            \
   if ((st = launch_status()) != PSB_OK) return st;                                                            \
   PSB_PROF("seg_fixup_kernel", s);                                                                            \
   seg_fixup_kernel<C><<<grid_fix, 256, 0, s>>>(seg_start, unique_rows, n_unique, d4, ch_shift,                \
