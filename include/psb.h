@@ -414,6 +414,62 @@ int psb_peer_allreduce(const void* const* bufs, int32_t G, int32_t rank, int64_t
 int psb_peer_sum_sqnorm(const void* const* slots, int32_t G, float* sqnorm_out, int64_t* step_dev,
                         psb_stream_t stream);
 
+/* ------------------------------------------------------------------ N4 ---
+ * On-device batch construction, metrics ranks and the ranklist writer for the item-transformer (TEM) path
+ * (SURVEY.md 8(f) N4).  The corpus relations the reference keeps as nested Python lists
+ * (data/data_util.py:165-203) live in HBM as flat CSR arrays; one launch replaces the per-sample list
+ * comprehensions of ItemPVDataloader.get_train_batch / get_test_batch / get_user_review_idxs
+ * (data/item_pv_dataloader.py:122-143,:31-49,:85-105). */
+typedef struct psb_corpus {
+  const int32_t* review_user;    /* [n_reviews] review -> user   (global_data.review_u_p[r][0]) */
+  const int32_t* review_item;    /* [n_reviews] review -> item   (global_data.review_u_p[r][1]) */
+  const int32_t* review_uloc;    /* [n_reviews] position in the user's sequence (review_loc_time[r][0]); may be
+                                    NULL unless mode == PSB_HIST_SEQ */
+  const uint8_t* review_in_set;  /* [n_reviews] 1 = review of the training split (prod_data.u_reviews) */
+  const int64_t* user_seq_off;   /* [n_users + 1] CSR offsets into user_seq */
+  const int32_t* user_seq;       /* every user's reviews in time order (global_data.u_r_seq) */
+  const int64_t* item_query_off; /* [n_items + 1] CSR offsets into item_query (prod_data.product_query_idx) */
+  const int32_t* item_query;
+  const int64_t* query_words;    /* [n_queries, wq] padded with word_pad (global_data.query_words) */
+  int64_t n_reviews, n_users, n_items, n_queries, wq, word_pad;
+} psb_corpus_t;
+
+#define PSB_HIST_SEQ 0    /* do_seq_review_*: the hist_limit reviews before this one (item_pv_dataloader.py:88-91) */
+#define PSB_HIST_LAST 1   /* fix=True: last hist_limit training reviews of the user, this one excluded (:93-97) */
+#define PSB_HIST_RANDOM 2 /* fix=False: random subset of hist_limit, order kept (:98-101); the subset is the
+                             hist_limit candidates with the smallest psb_subset_key(seed, sample, position) */
+
+/* corpus: HOST struct of device pointers.  Per sample b: review_idx[b] (the purchase being predicted);
+ * user_idx / item_idx [batch] optional (NULL: taken from the review, as get_train_batch does; test batches
+ * supply them, item_pv_dataset.py:66); query_idx [batch] optional -- when NULL the query is
+ * item_query[item][query_pick[b] % n] (random.choice at item_pv_dataloader.py:131 with the random word
+ * supplied by the caller).  Outputs: target_prod_idxs [batch], query_idx_out [batch] (optional),
+ * query_word_idxs [batch, wq], u_item_idxs [batch, hist_limit] right-padded with item_pad (the reference pads
+ * to the batch maximum, util.pad: slice [:, :max(hist_len)] to reproduce its width), hist_len [batch].
+ * Samples with out-of-range ids come out all-pad and set *err_flag (optional). */
+int psb_build_item_batch(const psb_corpus_t* corpus /* host */, const int64_t* review_idx,
+                         const int64_t* user_idx, const int64_t* item_idx, const int64_t* query_idx,
+                         const uint32_t* query_pick, int64_t batch, int64_t hist_limit, int32_t mode,
+                         uint32_t seed, int64_t item_pad, int64_t* target_prod_idxs, int64_t* query_idx_out,
+                         int64_t* query_word_idxs, int64_t* u_item_idxs, int32_t* hist_len, int32_t* err_flag,
+                         psb_stream_t stream);
+
+/* The subset key of PSB_HIST_RANDOM, evaluated on the host (tests, oracle cross-check). */
+uint32_t psb_subset_key(uint32_t seed, uint32_t sample, uint32_t pos);
+
+/* rank[i] = 1-based position of target[i] in ids[i, :k], 0 if absent: the input of MRR / P@1
+ * (Trainer.calc_metrics, trainer.py:171-186) taken from the fused top-k lists. */
+int psb_target_rank(const int64_t* ids, const int64_t* target, int64_t m, int64_t k, int32_t* rank,
+                    psb_stream_t stream);
+
+/* TREC run file of Trainer.test (trainer.py:158-169): for every query i and rank r < min(cutoff, k)
+ * "%s_%d Q0 %s %d %f ReviewTransformer\n" % (user_ids[user_idx[i]], query_idx[i], product_ids[ids[i,r]],
+ * r + 1, scores[i,r]).  ALL pointers are HOST pointers (ids / scores: the [m, k] top-k lists copied back).
+ * A negative id ends a query's list.  Returns the number of lines written (< 0: PSB_E_*). */
+int64_t psb_write_ranklist(const char* path, const char* const* user_ids, const int64_t* user_idx,
+                           const int64_t* query_idx, const char* const* product_ids, const int64_t* ids,
+                           const float* scores, int64_t m, int64_t k, int64_t cutoff, int32_t append);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,3 +16,4 @@ function against them.
 """
 from .ref_models import *  # noqa: F401,F403
 from .ranking import *  # noqa: F401,F403
+from . import batches  # noqa: F401

@@ -60,6 +60,18 @@ class FoldTable(ctypes.Structure):
                 ("n_touched", c_vp)]
 
 
+class Corpus(ctypes.Structure):
+    """psb_corpus_t."""
+    _fields_ = [("review_user", c_vp), ("review_item", c_vp), ("review_uloc", c_vp), ("review_in_set", c_vp),
+                ("user_seq_off", c_vp), ("user_seq", c_vp), ("item_query_off", c_vp), ("item_query", c_vp),
+                ("query_words", c_vp), ("n_reviews", c_i64), ("n_users", c_i64), ("n_items", c_i64),
+                ("n_queries", c_i64), ("wq", c_i64), ("word_pad", c_i64)]
+
+
+HIST_SEQ, HIST_LAST, HIST_RANDOM = 0, 1, 2
+c_u32 = ctypes.c_uint32
+c_cpp = ctypes.POINTER(ctypes.c_char_p)
+
 # name -> (restype, argtypes); the CPU test-suite checks every symbol of psb.h is here and exported
 SIGNATURES = {
     "psb_abi_version": (c_i32, []),
@@ -102,6 +114,11 @@ SIGNATURES = {
     "psb_peer_fold_lists": (c_i32, [ctypes.POINTER(FoldTable), c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "psb_peer_sum_sqnorm": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_vp, c_vp, c_vp]),
     "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, c_f32, c_vp, c_vp]),
+    "psb_build_item_batch": (c_i32, [ctypes.POINTER(Corpus), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_u32,
+                                     c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_subset_key": (c_u32, [c_u32, c_u32, c_u32]),
+    "psb_target_rank": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "psb_write_ranklist": (c_i64, [ctypes.c_char_p, c_cpp, c_vp, c_vp, c_cpp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32]),
     "psb_encoder_saved_bytes": (c_i64, [ctypes.POINTER(EncoderCfg)]),
     "psb_encoder_workspace_bytes": (c_i64, [ctypes.POINTER(EncoderCfg), c_i32]),
     "psb_encoder_fwd": (c_i32, [ctypes.POINTER(EncoderCfg), ctypes.POINTER(EncoderParams), c_vp, c_i64, c_vp, c_i64,

@@ -393,7 +393,7 @@ radix_scan_kernel(int* __restrict__ hist, int nblocks, int* __restrict__ totals)
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
-__global__ void __launch_bounds__(kNT)
+__global__ void __launch_bounds__(kNT, 3)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
                      int shift, int nblocks, const int* __restrict__ hist, const int* __restrict__ totals,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
