@@ -440,6 +440,8 @@ def run_b200_arm(a):
         "gather_rows_kernel": ("hbm", B * (d * 4 * 2 + 8)),
         "ns_loss_fast_kernel": ("hbm", B * (1 + K) * row + B * d * 4 * 2 + B * K * d * 4 * 2      # score + loss tail
                                 + B * W * (1 + K) * row + B * d * 4 * 2),                         # item -> words
+        "ns_loss_w1_kernel": ("hbm", B * (1 + K) * row + B * d * 4 * 2 + B * K * d * 4 * 2
+                              + B * W * (1 + K) * row + B * d * 4 * 2),
         "small_sort_segments_kernel": ("hbm", (n_item_slots + n_word_slots) * 8),
         "seg_reduce_kernel": ("hbm", (n_item_slots + n_word_slots) * row),
         "seg_fixup_kernel": ("hbm", 0),

@@ -183,6 +183,7 @@ extern "C" int psb_build_item_batch(const psb_corpus_t* corpus, const int64_t* r
                                     int64_t* u_item_idxs, int32_t* hist_len, int32_t* err_flag, psb_stream_t stream) {
   if (corpus == nullptr || batch < 0 || hist_limit <= 0 || hist_limit > (1 << 20)) return PSB_E_ARG;
   if (mode != PSB_HIST_SEQ && mode != PSB_HIST_LAST && mode != PSB_HIST_RANDOM) return PSB_E_ARG;
+  if (batch == 0) return PSB_OK;
   const psb_corpus_t& C = *corpus;
   if (C.review_user == nullptr || C.review_item == nullptr || C.review_in_set == nullptr ||
       C.user_seq_off == nullptr || C.user_seq == nullptr || C.query_words == nullptr || C.n_reviews <= 0 ||
@@ -191,7 +192,6 @@ extern "C" int psb_build_item_batch(const psb_corpus_t* corpus, const int64_t* r
   if (mode == PSB_HIST_SEQ && C.review_uloc == nullptr) return PSB_E_ARG;
   if (query_idx == nullptr && (query_pick == nullptr || C.item_query_off == nullptr || C.item_query == nullptr))
     return PSB_E_ARG;
-  if (batch == 0) return PSB_OK;
   if (review_idx == nullptr || target_prod_idxs == nullptr || query_word_idxs == nullptr || u_item_idxs == nullptr ||
       hist_len == nullptr)
     return PSB_E_ARG;

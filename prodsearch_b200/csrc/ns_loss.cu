@@ -7,6 +7,8 @@
 // read from HBM exactly once per use and no [n, w, 1+k, d] tensor is ever materialised.
 // HBM-bound: algorithmic bytes per anchor = w * (1 + k) * d * 4 (rows) + d * 4 (anchor)
 // + d * 4 (grad_anchor) (+ k * d * 8 when per-negative anchors are used).
+#include <stdlib.h>
+
 #include "psb_common.cuh"
 
 namespace psb {
@@ -284,6 +286,159 @@ ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restric
   }
 }
 
+// w == 1 (one target position per anchor: the TEM score/loss tail, item_to_words and PV with pv_window_size 1):
+// every position is its own anchor, the masked-mean denominator is 1, and the kernel is a pure stream of
+// (anchor row, 1 + k table rows) reads.  NR = rows handled per anchor (1 + k <= NR; 6 for the reference's 5
+// negatives); row ids travel through the shuffles as int32.  DB: the rows of the NEXT anchor are requested
+// before the current anchor is evaluated (two row buffers), so the 1 + k row reads of a warp are in flight
+// during its own arithmetic instead of only during other warps' -- ncu (r01e): the previous kernel sat at
+// 24 warps/SM with half of them stalled on their rows (long scoreboard 5.4 per issue) at 0.66 of HBM peak.
+template <bool HAS_B, int NR, bool DB>
+__global__ void __launch_bounds__(256, (DB || HAS_B) ? 2 : 3)
+ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ anchor_b,
+                  const float4* __restrict__ table, int64_t table_rows, int d4,
+                  const float* __restrict__ bias, const int64_t* __restrict__ pos_idx,
+                  const int64_t* __restrict__ neg_idx, const uint8_t* __restrict__ mask, int64_t pad_idx,
+                  const float* __restrict__ neg_weight, float pos_weight, int64_t n, int k,
+                  float* __restrict__ loss, float* __restrict__ coef_pos, float* __restrict__ coef_neg,
+                  float4* __restrict__ grad_a, float4* __restrict__ grad_b) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t i = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const bool col_ok = lane < d4;
+  // which score this lane owns after the butterfly, and the lane that is its designated writer
+  const int my_s = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool writer = (lane & 3) == 0;
+  const float tgt = my_s == 0 ? 1.f : 0.f;
+  struct Meta {
+    int idx;      // lane s <= k: table row of score s (-1: out of range / no such score)
+    float wt;     // lane s <= k: loss weight of score s
+    bool valid;   // lane 0: the target position counts (mask / pad)
+  };
+  auto fetch = [&](int64_t a_i, Meta& m) {
+    int64_t r = -1;
+    m.wt = 0.f;
+    if (lane <= k) {
+      r = lane == 0 ? pos_idx[a_i] : neg_idx[a_i * k + (lane - 1)];
+      m.wt = lane == 0 ? pos_weight : (neg_weight != nullptr ? neg_weight[a_i * k + (lane - 1)] : 1.f);
+    }
+    m.valid = mask != nullptr ? mask[a_i] != 0 : (pad_idx < 0 || r != pad_idx);
+    m.idx = (r < 0 || r >= table_rows) ? -1 : static_cast<int>(r);
+  };
+  auto issue = [&](const Meta& m, int64_t a_i, float4 (&row)[NR], float4& a, float& bias_v) {
+    a = col_ok ? anchor_a[a_i * d4 + lane] : zero4();
+    bias_v = (bias != nullptr && m.idx >= 0) ? bias[m.idx] : 0.f;
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      const int r = __shfl_sync(kFull, m.idx, s);
+      row[s] = (r >= 0 && col_ok) ? ldg_row4(table + static_cast<int64_t>(r) * d4 + lane) : zero4();
+    }
+  };
+  auto compute = [&](const Meta& m, int64_t a_i, const float4 (&row)[NR], const float4& a, float bias_v) {
+    float v[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < NR) {
+        float4 anc = a;
+        if (HAS_B && s >= 1 && s <= k && col_ok) anc = anchor_b[(a_i * k + (s - 1)) * d4 + lane];
+        v[s] = dot4(anc, row[s]);
+      } else {
+        v[s] = 0.f;
+      }
+    }
+    // halving butterfly: 8 values x 32 lanes -> lane L holds the full sum of value my_s
+    float u[4], t2[2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float mine = (lane & 16) ? v[t + 4] : v[t];
+      const float other = (lane & 16) ? v[t] : v[t + 4];
+      u[t] = mine + __shfl_xor_sync(kFull, other, 16);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const float mine = (lane & 8) ? u[t + 2] : u[t];
+      const float other = (lane & 8) ? u[t] : u[t + 2];
+      t2[t] = mine + __shfl_xor_sync(kFull, other, 8);
+    }
+    float z;
+    {
+      const float mine = (lane & 4) ? t2[1] : t2[0];
+      const float other = (lane & 4) ? t2[0] : t2[1];
+      z = mine + __shfl_xor_sync(kFull, other, 4);
+    }
+    z += __shfl_xor_sync(kFull, z, 2);
+    z += __shfl_xor_sync(kFull, z, 1);
+    const float x = z + __shfl_sync(kFull, bias_v, my_s);
+    const float wt = __shfl_sync(kFull, m.wt, my_s);
+    const float mv = __shfl_sync(kFull, m.valid ? 1.f : 0.f, 0);
+    float g = 0.f, lterm = 0.f;
+    if (my_s <= k) {
+      g = mv * wt * (sigmoidf_(x) - tgt);          // masked-mean denominator is 1 when w == 1
+      if (writer) {
+        lterm = wt * bce_value(x, tgt);
+        if (my_s == 0) coef_pos[a_i] = g;
+        else coef_neg[a_i * k + (my_s - 1)] = g;
+      }
+    }
+    const float lsum = mv * warp_sum(lterm);
+    float4 ga = zero4();
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      const int holder = ((s >> 2) & 1) * 16 + ((s >> 1) & 1) * 8 + (s & 1) * 4;
+      const float gs = __shfl_sync(kFull, g, holder);
+      if (HAS_B && s >= 1) {
+        if (s <= k && col_ok) {
+          float4 o = zero4();
+          fma4(o, gs, row[s]);
+          grad_b[(a_i * k + (s - 1)) * d4 + lane] = o;
+        }
+      } else {
+        fma4(ga, gs, row[s]);   // gs == 0 for s > k
+      }
+    }
+    if (lane == 0) loss[a_i] = lsum;
+    if (col_ok) grad_a[a_i * d4 + lane] = ga;
+  };
+
+  if (!DB) {
+    Meta mn;
+    fetch(i, mn);
+    for (; i < n; i += nw) {
+      const Meta m = mn;
+      float4 row[NR], a;
+      float bv;
+      issue(m, i, row, a, bv);
+      if (i + nw < n) fetch(i + nw, mn);
+      compute(m, i, row, a, bv);
+    }
+  } else {
+    Meta mA, mB;
+    float4 rowA[NR], rowB[NR], aA, aB;
+    float bA, bB = 0.f;
+    fetch(i, mA);
+    issue(mA, i, rowA, aA, bA);
+    mB = mA;
+    if (i + nw < n) fetch(i + nw, mB);
+    // one half-step: request the next anchor's rows into the idle buffer, evaluate the current one
+    auto half = [&](float4 (&rc)[NR], float4& ac, float& bc, Meta& mc, float4 (&rn)[NR], float4& an, float& bn,
+                    Meta& mnx) -> bool {
+      const bool has_next = i + nw < n;
+      Meta mnn = mc;
+      if (has_next) {
+        issue(mnx, i + nw, rn, an, bn);
+        if (i + 2 * nw < n) fetch(i + 2 * nw, mnn);
+      }
+      compute(mc, i, rc, ac, bc);
+      mc = mnn;   // meta of the anchor after next: its rows go into this (now idle) buffer
+      i += nw;
+      return has_next;
+    };
+    while (half(rowA, aA, bA, mA, rowB, aB, bB, mB) && half(rowB, aB, bB, mB, rowA, aA, bA, mA)) {
+    }
+  }
+}
+
 // scores[i, c] = <anchor[i], table[idx[i, c]]> (+ bias[idx[i, c]]): the candidate scoring of
 // test_dotproduct (item_transformer.py:141-145).  One warp per query, 4 candidate rows in flight.
 template <int C>
@@ -342,6 +497,16 @@ score_rows_kernel(const float4* __restrict__ anchor, const float4* __restrict__ 
 
 using namespace psb;
 
+// Tuning knob read once: PSB_NS_W1 selects the w == 1 kernel variant (see psb_ns_loss_fwd).
+static int ns_w1_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSB_NS_W1");
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }
+  return v;
+}
+
 extern "C" int psb_score_rows(const float* anchor, const float* table, int64_t table_rows, int64_t d,
                               const float* bias, const int64_t* idx, int64_t n, int64_t c_per, float* scores,
                               psb_stream_t stream) {
@@ -392,7 +557,26 @@ extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, con
       reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx,       \
       neg_weight, pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,       \
       reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b))
-  if (d4 <= 32 && k <= 7) {
+  if (w == 1 && d4 <= 32 && k <= 7 && table_rows < (1ll << 31) && ns_w1_variant() != 0) {
+    // variants (PSB_NS_W1 = 0 | 1 | 2, default 2): 0 generic fast kernel, 1 single row buffer, 2 double-buffered rows
+    const bool db = ns_w1_variant() == 2 && anchor_b == nullptr;
+    const int gridf = grid_for(n, 8, db ? 8 : 32);
+    PSB_PROF("ns_loss_w1_kernel", s);
+#define PSB_W1_LAUNCH(HASB, NR, DB)                                                                          \
+  ns_loss_w1_kernel<HASB, NR, DB><<<gridf, 256, 0, s>>>(                                                      \
+      reinterpret_cast<const float4*>(anchor_a), reinterpret_cast<const float4*>(anchor_b),                  \
+      reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, mask, pad_idx, neg_weight, \
+      pos_weight, n, static_cast<int>(k), loss, coef_pos, coef_neg, reinterpret_cast<float4*>(grad_anchor_a),  \
+      reinterpret_cast<float4*>(grad_anchor_b))
+    if (anchor_b != nullptr) {
+      if (k <= 5) PSB_W1_LAUNCH(true, 6, false); else PSB_W1_LAUNCH(true, 8, false);
+    } else if (db) {
+      if (k <= 5) PSB_W1_LAUNCH(false, 6, true); else PSB_W1_LAUNCH(false, 8, true);
+    } else {
+      if (k <= 5) PSB_W1_LAUNCH(false, 6, false); else PSB_W1_LAUNCH(false, 8, false);
+    }
+#undef PSB_W1_LAUNCH
+  } else if (d4 <= 32 && k <= 7) {
     const int gridf = grid_for(n, 8, 32);
     PSB_PROF("ns_loss_fast_kernel", s);
     if (anchor_b != nullptr)

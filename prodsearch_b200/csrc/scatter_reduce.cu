@@ -10,6 +10,8 @@
 // The reduction kernel (one warp per destination row, 128-bit row loads, 4 source rows in
 // flight) is the HBM-bound part: algorithmic bytes = n_slots * d * 4 read (when sources
 // are materialised rows) + n_unique * d * 4 written + metadata; sort traffic is overhead.
+#include <stdlib.h>
+
 #include "psb_common.cuh"
 
 namespace psb {
@@ -66,7 +68,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* sm, int* total) {
 // Layout: warp w, round r, lane l  <->  tile position w*32*IPT + r*32 + l.
 // On return pos[r] = position of the key in the tile sorted (stably) by digit,
 // dstart[256] = first sorted position of each digit.  whist: [NT/32][256] ints.
-template <int NT, int IPT>
+template <int NT, int IPT, bool BALLOT = false>
 __device__ __forceinline__ void tile_rank(const uint32_t (&key)[IPT], const bool (&valid)[IPT], int shift,
                                           int (&pos)[IPT], int* whist, int* dstart, int* scan_sm) {
   constexpr int NW = NT / 32;
@@ -78,7 +80,17 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&key)[IPT], const bool
 #pragma unroll
   for (int r = 0; r < IPT; ++r) {
     const int dg = valid[r] ? static_cast<int>((key[r] >> shift) & 255u) : 256;
-    const unsigned peers = __match_any_sync(kFull, dg);
+    unsigned peers;
+    if (BALLOT) {  // lanes with the same 9-bit value, from 9 votes (MATCH.ANY issues far slower on sm_100)
+      peers = kFull;
+#pragma unroll
+      for (int bit = 0; bit < 9; ++bit) {
+        const unsigned vote = __ballot_sync(kFull, (dg >> bit) & 1);
+        peers &= ((dg >> bit) & 1) ? vote : ~vote;
+      }
+    } else {
+      peers = __match_any_sync(kFull, dg);
+    }
     const int leader = __ffs(peers) - 1;
     int old = 0;
     if (dg < 256) old = mine[dg];
@@ -393,6 +405,7 @@ radix_scan_kernel(int* __restrict__ hist, int nblocks, int* __restrict__ totals)
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
+template <bool BALLOT>
 __global__ void __launch_bounds__(kNT, 3)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
                      int shift, int nblocks, const int* __restrict__ hist, const int* __restrict__ totals,
@@ -421,7 +434,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
     val[r] = valid[r] ? vals_in[base + p] : 0u;
   }
-  tile_rank<kNT, kIPT>(key, valid, shift, pos, whist, dstart, scan_sm);
+  tile_rank<kNT, kIPT, BALLOT>(key, valid, shift, pos, whist, dstart, scan_sm);
 #pragma unroll
   for (int r = 0; r < kIPT; ++r)
     if (valid[r]) {
@@ -448,10 +461,10 @@ __device__ __forceinline__ bool is_head(const uint32_t* keys, int64_t p, int64_t
 __global__ void __launch_bounds__(kNT)
 heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel, int* __restrict__ counts) {
   __shared__ int sm[8];
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x * kIPT;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
   int c = 0;
 #pragma unroll
-  for (int r = 0; r < kIPT; ++r) c += is_head(keys, base + r, n, sentinel) ? 1 : 0;
+  for (int r = 0; r < kIPT; ++r) c += is_head(keys, base + r * kNT + threadIdx.x, n, sentinel) ? 1 : 0;  // coalesced
   int tot = 0;
   block_excl_scan<kNT>(c, sm, &tot);
   if (threadIdx.x == 0) counts[blockIdx.x] = tot;
@@ -472,30 +485,59 @@ heads_scan_kernel(int* __restrict__ counts, int nblocks, int32_t* __restrict__ n
   if (threadIdx.x == 0) *n_unique = carry;
 }
 
+// The tile's keys are staged in shared memory with coalesced loads (one pad word per 32 keys: the 16
+// consecutive keys a thread then walks hit distinct banks), every thread numbers the segment heads among its 16
+// keys, and the (start, row) pairs leave through shared memory again so the global stores are contiguous.
 __global__ void __launch_bounds__(kNT)
 heads_write_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel,
                    const int* __restrict__ block_base, const int32_t* __restrict__ n_unique,
                    int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows) {
+  __shared__ uint32_t sk[kTile + kTile / 32 + 1];
+  __shared__ int32_t out_pos[kTile];
   __shared__ int sm[8];
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x * kIPT;
-  int c = 0;
+  __shared__ uint32_t s_prev;
+  uint32_t* out_key = sk;  // reused once every thread holds its keys in registers (after the block scan)
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
 #pragma unroll
-  for (int r = 0; r < kIPT; ++r) c += is_head(keys, base + r, n, sentinel) ? 1 : 0;
-  int seg = block_base[blockIdx.x] + block_excl_scan<kNT>(c, sm, nullptr);
+  for (int r = 0; r < kIPT; ++r) {
+    const int q = r * kNT + threadIdx.x;
+    const int64_t p = base + q;
+    sk[q + (q >> 5)] = p < n ? keys[p] : sentinel;
+  }
+  if (threadIdx.x == 0) s_prev = base > 0 ? keys[base - 1] : sentinel;
+  __syncthreads();
+  const int q0 = threadIdx.x * kIPT;
+  uint32_t kk[kIPT];
+  unsigned heads = 0;
+  uint32_t prev = q0 == 0 ? s_prev : sk[(q0 - 1) + ((q0 - 1) >> 5)];
   const int total = *n_unique;
 #pragma unroll
   for (int r = 0; r < kIPT; ++r) {
-    const int64_t p = base + r;
+    const int q = q0 + r;
+    const int64_t p = base + q;
+    kk[r] = sk[q + (q >> 5)];
     if (p < n) {
-      const uint32_t kk = keys[p];
-      if (is_head(keys, p, n, sentinel)) {
-        seg_start[seg] = static_cast<int32_t>(p);
-        unique_rows[seg] = static_cast<int32_t>(kk);
-        ++seg;
-      }
-      if (kk == sentinel && (p == 0 || keys[p - 1] != sentinel)) seg_start[total] = static_cast<int32_t>(p);
-      if (p == n - 1 && kk != sentinel) seg_start[total] = static_cast<int32_t>(n);
+      const bool first = p == 0;
+      if (kk[r] != sentinel && (first || prev != kk[r])) heads |= 1u << r;
+      if (kk[r] == sentinel && (first || prev != sentinel)) seg_start[total] = static_cast<int32_t>(p);
+      if (p == n - 1 && kk[r] != sentinel) seg_start[total] = static_cast<int32_t>(n);
     }
+    prev = kk[r];
+  }
+  int tot = 0;
+  int o = block_excl_scan<kNT>(__popc(heads), sm, &tot);
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r)
+    if ((heads >> r) & 1u) {
+      out_pos[o] = static_cast<int32_t>(base + q0 + r);
+      out_key[o] = kk[r];
+      ++o;
+    }
+  __syncthreads();
+  const int64_t seg0 = block_base[blockIdx.x];
+  for (int e = threadIdx.x; e < tot; e += kNT) {
+    seg_start[seg0 + e] = out_pos[e];
+    unique_rows[seg0 + e] = static_cast<int32_t>(out_key[e]);
   }
 }
 
@@ -658,6 +700,10 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
   }
 }
 
+// Lane-parallel scan of the segment table (coalesced): a lane flags its segment when it spans more than one
+// unit (rare: popular rows); the warp then folds each flagged segment's per-unit partials in unit order, eight
+// partial rows in flight at a time.  (The first version walked the segments one per warp iteration with two
+// dependent loads each: 184 us for 3.5M single-unit segments that needed no work at all.)
 template <int C>
 __global__ void __launch_bounds__(256)
 seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
@@ -667,39 +713,66 @@ seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restric
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int nu = *n_unique;
-  for (int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < nu; seg += nwarps) {
-    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
-    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
-    if (u_first == u_last) continue;  // written directly by seg_reduce_kernel
-    float4 acc[C];
-    float bacc = 0.f;
+  constexpr int U = 8;
+  for (int seg0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; seg0 < nu; seg0 += nwarps * 32) {
+    const int mine = seg0 + lane;
+    int m_lo = 0, m_hi = 0;
+    bool multi = false;
+    if (mine < nu) {
+      m_lo = seg_start[mine];
+      m_hi = seg_start[mine + 1];
+      multi = (m_lo >> ch_shift) != ((m_hi - 1) >> ch_shift);
+    }
+    unsigned todo = __ballot_sync(kFull, multi);
+    while (todo != 0u) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int seg = seg0 + l;
+      const int s_lo = __shfl_sync(kFull, m_lo, l), s_hi = __shfl_sync(kFull, m_hi, l);
+      const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
+      float4 acc[C];
+      float bacc = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = zero4();
-    for (int u = u_first; u <= u_last; ++u) {
-      // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
-      const int64_t ps = static_cast<int64_t>(u) * 2 + (u == u_first ? 1 : 0);
+      for (int c = 0; c < C; ++c) acc[c] = zero4();
+      for (int u0 = u_first; u0 <= u_last; u0 += U) {
+        float4 v[U][C];
+        float pb[U];
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+          const int u = u0 + t;
+          // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
+          const int64_t ps = static_cast<int64_t>(min(u, u_last)) * 2 + (u == u_first ? 1 : 0);
+          pb[t] = partial_bias[ps];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int col = lane + 32 * c;
+            v[t][c] = col < d4 ? partial[ps * d4 + col] : zero4();
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+          if (u0 + t <= u_last) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              acc[c].x += v[t][c].x; acc[c].y += v[t][c].y; acc[c].z += v[t][c].z; acc[c].w += v[t][c].w;
+            }
+            bacc += pb[t];
+          }
+        }
+      }
+      const int64_t drow = unique_rows[seg];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int col = lane + 32 * c;
         if (col < d4) {
-          const float4 v = partial[ps * d4 + col];
-          acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+          if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+          if (dense != nullptr) dense[drow * d4 + col] = acc[c];
         }
       }
-      bacc += partial_bias[ps];
-    }
-    const int64_t drow = unique_rows[seg];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int col = lane + 32 * c;
-      if (col < d4) {
-        if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
-        if (dense != nullptr) dense[drow * d4 + col] = acc[c];
+      if (lane == 0) {
+        if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+        if (dense_bias != nullptr) dense_bias[drow] = bacc;
       }
-    }
-    if (lane == 0) {
-      if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
-      if (dense_bias != nullptr) dense_bias[drow] = bacc;
     }
   }
 }
@@ -753,6 +826,17 @@ static WorkspaceLayout layout_for(int64_t n_total, int64_t d = 512) {
 }  // namespace psb
 
 using namespace psb;
+
+// Tuning knob read once: PSB_RADIX_MATCH=match selects the MATCH.ANY ranking in the multi-CTA radix scatter
+// (default: ballot-based peer masks).
+static bool radix_use_ballot() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSB_RADIX_MATCH");
+    v = (e != nullptr && e[0] == 'm') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 extern "C" int64_t psb_scatter_reduce_workspace_bytes(int64_t n_total, int64_t table_rows) {
   (void)table_rows;
@@ -852,7 +936,10 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
       radix_scan_kernel<<<256, 256, 0, s>>>(hist, nblocks, totals);
       if ((st = launch_status()) != PSB_OK) return st;
       PSB_PROF("radix_scatter_kernel", s);
-      radix_scatter_kernel<<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
+      if (radix_use_ballot())
+        radix_scatter_kernel<true><<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
+      else
+        radix_scatter_kernel<false><<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
       if ((st = launch_status()) != PSB_OK) return st;
       uint32_t* t = ki; ki = ko; ko = t;
       t = vi; vi = vo; vo = t;
@@ -874,7 +961,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
     const int ch_shift = unit_shift_for(n_total);
     const int grid = grid_for((n_total >> ch_shift) + 1, 8, 16);
-    const int grid_fix = grid_for(n_total, 8 * 8, 8);
+    const int grid_fix = grid_for(n_total, 8 * 32, 8);
     const int d4 = static_cast<int>(d / 4);
     float4* partial = reinterpret_cast<float4*>(ws + L.partial);
     float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);

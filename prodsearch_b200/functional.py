@@ -15,7 +15,15 @@ from . import ops
 
 
 class RowGradSink(object):
-    """Gradient collector for one embedding table (and the bias vector indexed like it)."""
+    """Gradient collector for one embedding table (and the bias vector indexed like it).
+
+    The sort + segmented reduce of different tables are independent, and at batch 384 each is a chain of short,
+    narrow launches (one CTA of counting sort, then the reduce): with ``concurrent`` set, every dense-mode sink runs
+    its chain on its own side stream, forked from and joined back into the stream ``backward()`` ran on, so the
+    chains of the item and the word table overlap (inside a captured CUDA graph they become parallel branches)."""
+
+    concurrent = True
+    _forked = []                      # sinks whose chain is in flight on a side stream (not yet joined)
 
     def __init__(self, weight, drop_idx=-1, bias=None, mode="dense"):
         self.weight = weight
@@ -29,6 +37,8 @@ class RowGradSink(object):
         self._prev = None             # (unique_rows, n_unique) written into the dense buffers last time
         self._uniq_buf = None         # persistent: a CUDA-graph replay reads last replay's rows from here
         self._nu_buf = None
+        self._stream = None
+        self._hold = None
 
     # -- called from Function.backward ------------------------------------------------
     def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
@@ -38,7 +48,34 @@ class RowGradSink(object):
                                               to_bias and self.bias is not None))
         if not self._queued:
             self._queued = True
-            Variable._execution_engine.queue_callback(self.finalize)
+            Variable._execution_engine.queue_callback(self._finalize_callback)
+
+    def _finalize_callback(self):
+        if not (RowGradSink.concurrent and self.mode == "dense" and self.weight.is_cuda):
+            return self.finalize()
+        cur = torch.cuda.current_stream(self.weight.device)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self.weight.device)
+        self._stream.wait_stream(cur)
+        self._hold = list(self._pending)          # contribution tensors stay alive until the join
+        first = not RowGradSink._forked
+        RowGradSink._forked.append(self)
+        try:
+            with torch.cuda.stream(self._stream):
+                self.finalize()
+        except Exception:
+            RowGradSink._forked.remove(self)
+            self._hold = None
+            raise
+        if first:                                 # runs after every finalize callback already queued
+            Variable._execution_engine.queue_callback(RowGradSink._join_forked)
+
+    @staticmethod
+    def _join_forked():
+        forked, RowGradSink._forked = RowGradSink._forked, []
+        for sink in forked:
+            torch.cuda.current_stream(sink.weight.device).wait_stream(sink._stream)
+            sink._hold = None
 
     # -- runs once, after the whole backward graph has executed --------------------------
     def finalize(self):
