@@ -44,7 +44,11 @@ gather_rows_kernel(const float4* __restrict__ table, int64_t table_rows, int d4,
 
 // ---------------------------------------------------------------- G4 -----
 // C = float4 chunks per lane (d4 <= 32*C).  One warp per pooled row.
-template <int C, bool FS>
+// SMEMW (FS with d4 <= 32): the projection W [d, d] is staged once per CTA in shared memory (rows padded by 4
+// floats so the 128-bit row reads of the 32 lanes are conflict-free) and every lane produces the outputs
+// j = lane + 32 u from broadcast reads of the pooled row -- instead of 4 * d dependent L2 row loads and d warp
+// reductions per pooled row (31 us of the batch-384 step were this matvec).
+template <int C, bool FS, bool SMEMW = false>
 __global__ void __launch_bounds__(256)
 meanpool_kernel(const float4* __restrict__ table, int64_t table_rows, int d4,
                 const int64_t* __restrict__ idx, int64_t n, int w, int64_t pad_idx,
@@ -57,6 +61,16 @@ meanpool_kernel(const float4* __restrict__ table, int64_t table_rows, int d4,
   const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int d = d4 * 4;
   constexpr int U = 4;  // rows in flight per warp
+  extern __shared__ float4 smem_w4[];
+  const int ldw4 = d4 + 1;                       // padded row length of W in float4
+  float4* s_mean4 = smem_w4 + d * ldw4 + (threadIdx.x >> 5) * d4;
+  if (SMEMW) {
+    for (int e = threadIdx.x; e < d * d4; e += blockDim.x) {
+      const int j = e / d4, c4 = e - j * d4;
+      smem_w4[j * ldw4 + c4] = __ldg(fs_weight + e);
+    }
+    __syncthreads();
+  }
   for (int64_t i = warp; i < n; i += nwarps) {
     float4 acc[C];
 #pragma unroll
@@ -123,7 +137,29 @@ meanpool_kernel(const float4* __restrict__ table, int64_t table_rows, int d4,
         acc[c] = zero4();
       }
     }
-    if (FS) {
+    if (FS && SMEMW) {
+      // out[i, j] = tanh(<W[j, :], mean> + b[j]) with W and the pooled row in shared memory
+      __syncwarp();
+      if (lane < d4) s_mean4[lane] = acc[0];
+      __syncwarp();
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c4 = 0; c4 < d4; ++c4) {
+        const float4 m = s_mean4[c4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = lane + 32 * u;
+          if (j < d) {
+            const float4 wv = smem_w4[j * ldw4 + c4];
+            o[u] = fmaf(m.w, wv.w, fmaf(m.z, wv.z, fmaf(m.y, wv.y, fmaf(m.x, wv.x, o[u]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lane + 32 * u;
+        if (j < d) out[i * d + j] = tanhf(o[u] + fs_bias[j]);
+      }
+    } else if (FS) {
       // out[i, j] = tanh(<W[j, :], mean> + b[j]); W (d x d fp32) stays L1/L2 resident.
       for (int j0 = 0; j0 < d; j0 += 32) {
         float mine = 0.f;
@@ -353,7 +389,20 @@ static int launch_meanpool(const float* table, int64_t table_rows, int64_t d, co
   const float4* w4 = reinterpret_cast<const float4*>(fs_weight);
   float4* m4 = reinterpret_cast<float4*>(mean_out);
   PSB_PROF("meanpool_kernel", s);
-  if (fs_weight != nullptr)
+  if (fs_weight != nullptr && C == 1) {
+    const size_t smem = (static_cast<size_t>(d) * (d / 4 + 1) + 8 * (d / 4)) * sizeof(float4);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(meanpool_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured = smem;
+    }
+    const int grid_w = grid_for(n, 8, 2);            // W is re-staged per CTA: few, persistent CTAs
+    meanpool_kernel<1, true, true><<<grid_w, 256, smem, s>>>(t4, table_rows, static_cast<int>(d / 4), idx, n,
+                                                              static_cast<int>(w), pad_idx, mask, tok_scale, k4, w4,
+                                                              fs_bias, m4, out, inv_count);
+  } else if (fs_weight != nullptr)
     meanpool_kernel<C, true><<<grid, 256, 0, s>>>(t4, table_rows, static_cast<int>(d / 4), idx, n,
                                                   static_cast<int>(w), pad_idx, mask, tok_scale, k4, w4,
                                                   fs_bias, m4, out, inv_count);

@@ -290,9 +290,9 @@ ns_loss_fast_kernel(const float4* __restrict__ anchor_a, const float4* __restric
 // every position is its own anchor, the masked-mean denominator is 1, and the kernel is a pure stream of
 // (anchor row, 1 + k table rows) reads.  NR = rows handled per anchor (1 + k <= NR; 6 for the reference's 5
 // negatives); row ids travel through the shuffles as int32.  DB: the rows of the NEXT anchor are requested
-// before the current anchor is evaluated (two row buffers), so the 1 + k row reads of a warp are in flight
-// during its own arithmetic instead of only during other warps' -- ncu (r01e): the previous kernel sat at
-// 24 warps/SM with half of them stalled on their rows (long scoreboard 5.4 per issue) at 0.66 of HBM peak.
+// before the current anchor is evaluated (two row buffers).  Measured on the 16M-row table (profiles/r01f_ab.jsonl):
+// generic fast kernel 0.66 of HBM peak, this kernel with one row buffer 0.85, with two buffers 0.69 (103 registers
+// -> 2 CTAs/SM), so DB is kept only as a tuning variant.
 template <bool HAS_B, int NR, bool DB>
 __global__ void __launch_bounds__(256, (DB || HAS_B) ? 2 : 3)
 ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict__ anchor_b,
@@ -502,7 +502,7 @@ static int ns_w1_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSB_NS_W1");
-    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   return v;
 }
@@ -558,7 +558,8 @@ extern "C" int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b, con
       neg_weight, pos_weight, n, static_cast<int>(w), static_cast<int>(k), loss, coef_pos, coef_neg,       \
       reinterpret_cast<float4*>(grad_anchor_a), reinterpret_cast<float4*>(grad_anchor_b))
   if (w == 1 && d4 <= 32 && k <= 7 && table_rows < (1ll << 31) && ns_w1_variant() != 0) {
-    // variants (PSB_NS_W1 = 0 | 1 | 2, default 2): 0 generic fast kernel, 1 single row buffer, 2 double-buffered rows
+    // variants (PSB_NS_W1 = 0 | 1 | 2, default 1): 0 generic fast kernel, 1 single row buffer at 3 CTAs/SM
+    // (measured 0.85 of HBM peak), 2 double-buffered rows at 2 CTAs/SM (0.69: the lost occupancy costs more)
     const bool db = ns_w1_variant() == 2 && anchor_b == nullptr;
     const int gridf = grid_for(n, 8, db ? 8 : 32);
     PSB_PROF("ns_loss_w1_kernel", s);

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kSmallNT, 1)
 small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, int64_t table_rows, int64_t drop_idx, int passes,
                            uint32_t* __restrict__ sorted_slots, uint32_t* __restrict__ sorted_keys,
                            int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows,
-                           int32_t* __restrict__ n_unique) {
+                           int32_t* __restrict__ n_unique, int32_t* __restrict__ work_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* sk = reinterpret_cast<uint32_t*>(smem_raw);          // [cap] keys
   uint32_t* sv = sk + kSmallCap;                                 // [cap] slots
@@ -207,6 +207,7 @@ small_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, 
   }
   if (threadIdx.x == 0) {
     *n_unique = total;
+    *work_count = 0;
     if (n_total == 0) seg_start[0] = 0;
   }
 }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kSmallNT, 1)
 count_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, int64_t table_rows, int64_t drop_idx, int per,
                            uint32_t* __restrict__ sorted_slots, uint32_t* __restrict__ sorted_keys,
                            int32_t* __restrict__ seg_start, int32_t* __restrict__ unique_rows,
-                           int32_t* __restrict__ n_unique) {
+                           int32_t* __restrict__ n_unique, int32_t* __restrict__ work_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nbins = per * kSmallNT;
   uint32_t* bins = reinterpret_cast<uint32_t*>(smem_raw);                        // [nbins]
@@ -282,7 +283,10 @@ count_sort_segments_kernel(const __grid_constant__ ContribTable T, int n_total, 
     }
     run += c;
   }
-  if (threadIdx.x == 0) *n_unique = static_cast<int32_t>(static_cast<uint32_t>(total) >> 16);
+  if (threadIdx.x == 0) {
+    *n_unique = static_cast<int32_t>(static_cast<uint32_t>(total) >> 16);
+    *work_count = 0;
+  }
   __syncthreads();
   int pos[kSmallIPT];
 #pragma unroll
@@ -362,30 +366,33 @@ constexpr int kNT = 256;
 constexpr int kIPT = 16;
 constexpr int kTile = kNT * kIPT;  // 4096 keys per CTA
 
-__global__ void __launch_bounds__(256)
-pack_keys_kernel(const __grid_constant__ ContribTable T, int64_t n_total, int64_t table_rows, int64_t drop_idx,
-                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n_total;
-       s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    keys[s] = make_key(T, static_cast<uint32_t>(s), table_rows, drop_idx);
-    vals[s] = static_cast<uint32_t>(s);
-  }
-}
-
-// hist[digit * nblocks + block]
+// hist[digit * nblocks + block].  FIRST: the keys of pass 0 are formed on the fly from the contributions' int64
+// destination rows (no separate pack pass; the slot payload of pass 0 is the position itself).  Every warp counts
+// into its own 256 bins (shared-memory atomics on one CTA-wide histogram serialise on popular digits).
+template <bool FIRST>
 __global__ void __launch_bounds__(kNT)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
+radix_hist_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, int64_t drop_idx,
+                  const uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
+  __shared__ int h[(kNT / 32) * 256];
+  for (int t = threadIdx.x; t < (kNT / 32) * 256; t += kNT) h[t] = 0;
   __syncthreads();
+  int* mine = h + (threadIdx.x >> 5) * 256;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+  uint32_t k[kIPT];
 #pragma unroll
   for (int r = 0; r < kIPT; ++r) {
     const int64_t p = base + r * kNT + threadIdx.x;
-    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1);  // integer counts: order-free
+    k[r] = 0xffffffffu;
+    if (p < n) k[r] = FIRST ? make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx) : keys[p];
   }
+#pragma unroll
+  for (int r = 0; r < kIPT; ++r)
+    if (base + r * kNT + threadIdx.x < n) atomicAdd(&mine[(k[r] >> shift) & 255u], 1);  // integer counts: order-free
   __syncthreads();
-  hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  int tot = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kNT / 32; ++w2) tot += h[w2 * 256 + threadIdx.x];
+  hist[threadIdx.x * nblocks + blockIdx.x] = tot;
 }
 
 // One CTA per digit: exclusive scan of its row of per-block counts; totals[digit].
@@ -405,9 +412,10 @@ radix_scan_kernel(int* __restrict__ hist, int nblocks, int* __restrict__ totals)
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
-template <bool BALLOT>
+template <bool BALLOT, bool FIRST>
 __global__ void __launch_bounds__(kNT, 3)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+radix_scatter_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, int64_t drop_idx,
+                     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
                      int shift, int nblocks, const int* __restrict__ hist, const int* __restrict__ totals,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t sk[kTile];
@@ -431,8 +439,13 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int r = 0; r < kIPT; ++r) {
     const int p = wid * 32 * kIPT + r * 32 + lane;
     valid[r] = p < tile_valid;
-    key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
-    val[r] = valid[r] ? vals_in[base + p] : 0u;
+    if (FIRST) {
+      key[r] = valid[r] ? make_key(T, static_cast<uint32_t>(base + p), table_rows, drop_idx) : 0xffffffffu;
+      val[r] = static_cast<uint32_t>(base + p);
+    } else {
+      key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
+      val[r] = valid[r] ? vals_in[base + p] : 0u;
+    }
   }
   tile_rank<kNT, kIPT, BALLOT>(key, valid, shift, pos, whist, dstart, scan_sm);
 #pragma unroll
@@ -471,7 +484,8 @@ heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentin
 }
 
 __global__ void __launch_bounds__(256)
-heads_scan_kernel(int* __restrict__ counts, int nblocks, int32_t* __restrict__ n_unique) {
+heads_scan_kernel(int* __restrict__ counts, int nblocks, int32_t* __restrict__ n_unique,
+                  int32_t* __restrict__ work_count) {
   __shared__ int sm[8];
   int carry = 0;
   for (int b0 = 0; b0 < nblocks; b0 += 256) {
@@ -482,7 +496,10 @@ heads_scan_kernel(int* __restrict__ counts, int nblocks, int32_t* __restrict__ n
     if (b < nblocks) counts[b] = carry + ex;
     carry += tot;
   }
-  if (threadIdx.x == 0) *n_unique = carry;
+  if (threadIdx.x == 0) {
+    *n_unique = carry;
+    *work_count = 0;
+  }
 }
 
 // The tile's keys are staged in shared memory with coalesced loads (one pad word per 32 keys: the 16
@@ -575,7 +592,8 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
                   const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ seg_start,
                   const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
                   float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
-                  float4* __restrict__ partial, float* __restrict__ partial_bias) {
+                  float4* __restrict__ partial, float* __restrict__ partial_bias, int32_t* __restrict__ work,
+                  int32_t* __restrict__ work_count) {
   __shared__ unsigned long long s_ptr[8][32];
   __shared__ float s_sc[8][32];
   __shared__ uint32_t s_key[8][32];
@@ -695,84 +713,93 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
         const int col = lane + 32 * c;
         if (FULL || col < d4) partial[ps * d4 + col] = acc[c];
       }
-      if (lane == 0) partial_bias[ps] = bacc;
+      if (lane == 0) {
+        partial_bias[ps] = bacc;
+        // head unit of a segment that spans several units: one work item for the fix-up kernel
+        // (integer atomic: the ORDER of the list is arbitrary, every item's sum is not)
+        if (started_here) work[atomicAdd(work_count, 1)] = seg;
+      }
     }
   }
 }
 
-// Lane-parallel scan of the segment table (coalesced): a lane flags its segment when it spans more than one
-// unit (rare: popular rows); the warp then folds each flagged segment's per-unit partials in unit order, eight
-// partial rows in flight at a time.  (The first version walked the segments one per warp iteration with two
-// dependent loads each: 184 us for 3.5M single-unit segments that needed no work at all.)
+// One warp per work item (a segment that spans several units, listed by seg_reduce_kernel): the per-unit partials
+// are added in unit order, U partial rows in flight at a time.  (The first version walked ALL segments, one per
+// warp iteration with two dependent loads each: 184 us for 3.5M single-unit segments that needed no work.)
 template <int C>
 __global__ void __launch_bounds__(256)
 seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
-                 const int32_t* __restrict__ n_unique, int d4, int ch_shift, float4* __restrict__ reduced,
-                 float* __restrict__ reduced_bias, float4* __restrict__ dense, float* __restrict__ dense_bias,
-                 const float4* __restrict__ partial, const float* __restrict__ partial_bias) {
+                 const int32_t* __restrict__ work, const int32_t* __restrict__ work_count, int d4, int ch_shift,
+                 float4* __restrict__ reduced, float* __restrict__ reduced_bias, float4* __restrict__ dense,
+                 float* __restrict__ dense_bias, const float4* __restrict__ partial,
+                 const float* __restrict__ partial_bias) {
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int nu = *n_unique;
-  constexpr int U = 8;
-  for (int seg0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; seg0 < nu; seg0 += nwarps * 32) {
-    const int mine = seg0 + lane;
-    int m_lo = 0, m_hi = 0;
-    bool multi = false;
-    if (mine < nu) {
-      m_lo = seg_start[mine];
-      m_hi = seg_start[mine + 1];
-      multi = (m_lo >> ch_shift) != ((m_hi - 1) >> ch_shift);
-    }
-    unsigned todo = __ballot_sync(kFull, multi);
-    while (todo != 0u) {
-      const int l = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int seg = seg0 + l;
-      const int s_lo = __shfl_sync(kFull, m_lo, l), s_hi = __shfl_sync(kFull, m_hi, l);
-      const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
-      float4 acc[C];
-      float bacc = 0.f;
+  const int n_work = *work_count;
+  constexpr int U = C == 1 ? 16 : 8;
+  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_work; e += nwarps) {
+    const int seg = work[e];
+    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
+    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
+    float4 acc[C];
+    float bacc = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = zero4();
-      for (int u0 = u_first; u0 <= u_last; u0 += U) {
-        float4 v[U][C];
-        float pb[U];
+    for (int c = 0; c < C; ++c) acc[c] = zero4();
+    for (int u0 = u_first; u0 <= u_last; u0 += U) {
+      float4 v[U][C];
+      float pb[U];
 #pragma unroll
-        for (int t = 0; t < U; ++t) {
-          const int u = u0 + t;
-          // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
-          const int64_t ps = static_cast<int64_t>(min(u, u_last)) * 2 + (u == u_first ? 1 : 0);
-          pb[t] = partial_bias[ps];
+      for (int t = 0; t < U; ++t) {
+        const int u = min(u0 + t, u_last);
+        // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
+        const int64_t ps = static_cast<int64_t>(u) * 2 + (u == u_first ? 1 : 0);
+        pb[t] = partial_bias[ps];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = lane + 32 * c;
+          v[t][c] = col < d4 ? ldg_row4(partial + ps * d4 + col) : zero4();
+        }
+      }
+      // units past the end of the segment contribute +0; the U rows of a batch are added as a fixed binary tree
+      // (a pure function of the unit's position in the segment: reproducible), the batches in unit order
+#pragma unroll
+      for (int t = 0; t < U; ++t) {
+        if (u0 + t > u_last) {
+          pb[t] = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[t][c] = zero4();
+        }
+      }
+#pragma unroll
+      for (int w2 = 1; w2 < U; w2 <<= 1) {
+#pragma unroll
+        for (int t = 0; t + w2 < U; t += 2 * w2) {
+          pb[t] += pb[t + w2];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int col = lane + 32 * c;
-            v[t][c] = col < d4 ? partial[ps * d4 + col] : zero4();
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < U; ++t) {
-          if (u0 + t <= u_last) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              acc[c].x += v[t][c].x; acc[c].y += v[t][c].y; acc[c].z += v[t][c].z; acc[c].w += v[t][c].w;
-            }
-            bacc += pb[t];
+            v[t][c].x += v[t + w2][c].x; v[t][c].y += v[t + w2][c].y;
+            v[t][c].z += v[t + w2][c].z; v[t][c].w += v[t + w2][c].w;
           }
         }
       }
-      const int64_t drow = unique_rows[seg];
+      bacc += pb[0];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const int col = lane + 32 * c;
-        if (col < d4) {
-          if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
-          if (dense != nullptr) dense[drow * d4 + col] = acc[c];
-        }
+        acc[c].x += v[0][c].x; acc[c].y += v[0][c].y; acc[c].z += v[0][c].z; acc[c].w += v[0][c].w;
       }
-      if (lane == 0) {
-        if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
-        if (dense_bias != nullptr) dense_bias[drow] = bacc;
+    }
+    const int64_t drow = unique_rows[seg];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = lane + 32 * c;
+      if (col < d4) {
+        if (reduced != nullptr) reduced[static_cast<int64_t>(seg) * d4 + col] = acc[c];
+        if (dense != nullptr) dense[drow * d4 + col] = acc[c];
       }
+    }
+    if (lane == 0) {
+      if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
+      if (dense_bias != nullptr) dense_bias[drow] = bacc;
     }
   }
 }
@@ -794,7 +821,7 @@ zero_rows_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ n
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
-  int64_t keys_a, vals_a, keys_b, vals_b, hist, totals, counts, seg_start, partial, partial_bias, total;
+  int64_t keys_a, vals_a, keys_b, vals_b, hist, totals, counts, seg_start, partial, partial_bias, work, work_count, total;
 };
 
 // unit size of the segmented reduction: a pure function of n_total (~4k+ units, 8..256 slots each)
@@ -819,6 +846,8 @@ static WorkspaceLayout layout_for(int64_t n_total, int64_t d = 512) {
   const int64_t n_units = (n_total >> unit_shift_for(n_total)) + 2;
   L.partial = o; o += align_up(2 * n_units * d * 4, 256);
   L.partial_bias = o; o += align_up(2 * n_units * 4, 256);
+  L.work = o; o += align_up(n_units * 4, 256);
+  L.work_count = o; o += 256;
   L.total = o + 256;
   return L;
 }
@@ -881,6 +910,8 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   int* totals = reinterpret_cast<int*>(ws + L.totals);
   int* counts = reinterpret_cast<int*>(ws + L.counts);
   int32_t* seg_start = reinterpret_cast<int32_t*>(ws + L.seg_start);
+  int32_t* work = reinterpret_cast<int32_t*>(ws + L.work);
+  int32_t* work_count = reinterpret_cast<int32_t*>(ws + L.work_count);
 
   int bits = 1;
   while ((static_cast<int64_t>(1) << bits) <= table_rows) ++bits;  // sentinel == table_rows must fit
@@ -903,7 +934,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     PSB_PROF("count_sort_segments_kernel", s);
     count_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
                                                          static_cast<int>(cs_per), vals_a, keys_a, seg_start,
-                                                         unique_rows, n_unique);
+                                                         unique_rows, n_unique, work_count);
     if ((st = launch_status()) != PSB_OK) return st;
     sorted_slots = vals_a;
     sorted_keys = keys_a;
@@ -918,28 +949,29 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     }
     PSB_PROF("small_sort_segments_kernel", s);
     small_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
-                                                         passes, vals_a, keys_a, seg_start, unique_rows, n_unique);
+                                                         passes, vals_a, keys_a, seg_start, unique_rows, n_unique, work_count);
     if ((st = launch_status()) != PSB_OK) return st;
     sorted_slots = vals_a;
     sorted_keys = keys_a;
   } else {
     const int nblocks = static_cast<int>((n_total + kTile - 1) / kTile);
-    PSB_PROF("pack_keys_kernel", s);
-    pack_keys_kernel<<<grid_for(n_total, 256 * 4), 256, 0, s>>>(T, n_total, table_rows, drop_idx, keys_a, vals_a);
-    if ((st = launch_status()) != PSB_OK) return st;
     uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    const bool ballot = radix_use_ballot();
     for (int pass = 0; pass < passes; ++pass) {
       PSB_PROF("radix_hist_kernel", s);
-      radix_hist_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, pass * 8, nblocks, hist);
+      if (pass == 0) radix_hist_kernel<true><<<nblocks, kNT, 0, s>>>(T, table_rows, drop_idx, ki, n_total, 0, nblocks, hist);
+      else radix_hist_kernel<false><<<nblocks, kNT, 0, s>>>(T, table_rows, drop_idx, ki, n_total, pass * 8, nblocks, hist);
       if ((st = launch_status()) != PSB_OK) return st;
       PSB_PROF("radix_scan_kernel", s);
       radix_scan_kernel<<<256, 256, 0, s>>>(hist, nblocks, totals);
       if ((st = launch_status()) != PSB_OK) return st;
       PSB_PROF("radix_scatter_kernel", s);
-      if (radix_use_ballot())
-        radix_scatter_kernel<true><<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
-      else
-        radix_scatter_kernel<false><<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo);
+#define PSB_RS_LAUNCH(B, F)                                                                                      \
+  radix_scatter_kernel<B, F><<<nblocks, kNT, 0, s>>>(T, table_rows, drop_idx, ki, vi, n_total, pass * 8, nblocks, \
+                                                     hist, totals, ko, vo)
+      if (pass == 0) { if (ballot) PSB_RS_LAUNCH(true, true); else PSB_RS_LAUNCH(false, true); }
+      else { if (ballot) PSB_RS_LAUNCH(true, false); else PSB_RS_LAUNCH(false, false); }
+#undef PSB_RS_LAUNCH
       if ((st = launch_status()) != PSB_OK) return st;
       uint32_t* t = ki; ki = ko; ko = t;
       t = vi; vi = vo; vo = t;
@@ -949,7 +981,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     heads_count_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts);
     if ((st = launch_status()) != PSB_OK) return st;
     PSB_PROF("heads_scan_kernel", s);
-    heads_scan_kernel<<<1, 256, 0, s>>>(counts, nblocks, n_unique);
+    heads_scan_kernel<<<1, 256, 0, s>>>(counts, nblocks, n_unique, work_count);
     if ((st = launch_status()) != PSB_OK) return st;
     PSB_PROF("heads_write_kernel", s);
     heads_write_kernel<<<nblocks, kNT, 0, s>>>(ki, n_total, sentinel, counts, n_unique, seg_start, unique_rows);
@@ -961,7 +993,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
     const int ch_shift = unit_shift_for(n_total);
     const int grid = grid_for((n_total >> ch_shift) + 1, 8, 16);
-    const int grid_fix = grid_for(n_total, 8 * 32, 8);
+    const int grid_fix = grid_for((n_total >> ch_shift) + 1, 8, 8);
     const int d4 = static_cast<int>(d / 4);
     float4* partial = reinterpret_cast<float4*>(ws + L.partial);
     float* partial_bias = reinterpret_cast<float*>(ws + L.partial_bias);
@@ -971,11 +1003,12 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     auto kern = d4 == 32 * C ? seg_reduce_kernel<C, true> : seg_reduce_kernel<C, false>;                       \
     kern<<<grid, 256, 0, s>>>(T, sorted_slots, sorted_keys, seg_start, n_unique, d4, ch_shift,                 \
                               reinterpret_cast<float4*>(reduced), reduced_bias,                                \
-                              reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial, partial_bias);  \
+                              reinterpret_cast<float4*>(dense_grad), dense_bias_grad, partial, partial_bias,   \
+                              work, work_count);                                                               \
   }                                                                                                            \
   if ((st = launch_status()) != PSB_OK) return st;                                                            \
   PSB_PROF("seg_fixup_kernel", s);                                                                            \
-  seg_fixup_kernel<C><<<grid_fix, 256, 0, s>>>(seg_start, unique_rows, n_unique, d4, ch_shift,                \
+  seg_fixup_kernel<C><<<grid_fix, 256, 0, s>>>(seg_start, unique_rows, work, work_count, d4, ch_shift,         \
                                                reinterpret_cast<float4*>(reduced), reduced_bias,              \
                                                reinterpret_cast<float4*>(dense_grad), dense_bias_grad,        \
                                                partial, partial_bias)

@@ -472,9 +472,24 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             items, (cand,), _ = self.item_table.fetch([batch_data.candi_prod_idxs])
             return ops.score_rows(q, items, cand, None)
 
-    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC):
+    def _shard_topk(self, q, k, n_local, id_base, id_stride, mode):
+        """Top-k of this rank's shard; TOPK_TC16 uses a cached fp16 copy of the shard (rebuilt when it changes)."""
+        w = self.item_table.weight.detach()
+        prepared = None
+        if mode == _lib.TOPK_TC16:
+            key = (w.data_ptr(), self.item_table.weight._version, n_local)
+            if getattr(self, "_shard_prep", (None, None))[0] != key:
+                self._shard_prep = (key, ops.catalog_prepare_f16(w, n_local))
+            prepared = self._shard_prep[1]
+            if not prepared.fits:
+                mode, prepared = _lib.TOPK_TC, None
+        return ops.catalog_topk(q, w, k, n_items=n_local, id_base=id_base, id_stride=id_stride, mode=mode,
+                                prepared=prepared)
+
+    def rank_catalog(self, batch_or_queries, k=100, mode=_lib.TOPK_TC16):
         """Sharded full-catalog top-k: every rank scores the all-gathered queries against its shard
-        (id = rank + G * local row), the per-shard lists are all-gathered and merged (psb_topk_merge)."""
+        (id = rank + G * local row), the per-shard lists are all-gathered and merged (psb_topk_merge).
+        Every mode returns the exact mode's lists (the shortlists are rescored in fp32)."""
         import torch.distributed as dist
         with torch.no_grad():
             q = batch_or_queries if torch.is_tensor(batch_or_queries) else self.encode_queries(
@@ -483,7 +498,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             G, r = self.peer.world, self.peer.rank
             n_local = max(0, (self.prod_pad_idx - r + G - 1) // G)
             if G == 1:
-                return ops.catalog_topk(q, self.item_table.weight.detach(), k, n_items=n_local, mode=mode)
+                return self._shard_topk(q, k, n_local, 0, 1, mode)
             m = torch.tensor([q.shape[0]], device=q.device)
             ms = [torch.empty_like(m) for _ in range(G)]
             dist.all_gather(ms, m, group=self.peer.group)
@@ -493,8 +508,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             q_pad[:q.shape[0]] = q
             qs = [torch.empty_like(q_pad) for _ in range(G)]
             dist.all_gather(qs, q_pad, group=self.peer.group)
-            ids, sc = ops.catalog_topk(torch.cat(qs, 0), self.item_table.weight.detach(), k, n_items=n_local,
-                                       id_base=r, id_stride=G, mode=mode)
+            ids, sc = self._shard_topk(torch.cat(qs, 0), k, n_local, r, G, mode)
             ids_all = [torch.empty_like(ids) for _ in range(G)]
             sc_all = [torch.empty_like(sc) for _ in range(G)]
             dist.all_gather(ids_all, ids, group=self.peer.group)
