@@ -432,6 +432,10 @@ typedef struct psb_corpus {
   const int32_t* item_query;
   const int64_t* query_words;    /* [n_queries, wq] padded with word_pad (global_data.query_words) */
   int64_t n_reviews, n_users, n_items, n_queries, wq, word_pad;
+  /* review-transformer (RTM) batches only; NULL otherwise */
+  const int64_t* item_seq_off;   /* [n_items + 1] CSR offsets into item_seq */
+  const int32_t* item_seq;       /* every item's reviews in time order (global_data.i_r_seq) */
+  const int64_t* review_time;    /* [n_reviews] time stamp (review_loc_time[r][2]); PSB_HIST_SEQ only */
 } psb_corpus_t;
 
 #define PSB_HIST_SEQ 0    /* do_seq_review_*: the hist_limit reviews before this one (item_pv_dataloader.py:88-91) */
@@ -453,6 +457,27 @@ int psb_build_item_batch(const psb_corpus_t* corpus /* host */, const int64_t* r
                          uint32_t seed, int64_t item_pad, int64_t* target_prod_idxs, int64_t* query_idx_out,
                          int64_t* query_word_idxs, int64_t* u_item_idxs, int32_t* hist_len, int32_t* err_flag,
                          psb_stream_t stream);
+
+/* N3: candidate sequences of a review-transformer TEST batch (ProdSearchDataLoader.get_test_batch,
+ * data/prod_search_dataloader.py:44-109, which loops over every candidate of every entry in Python).  One warp per
+ * (entry b, candidate c): the user's previous reviews (get_user_review_idxs, :184-201; PSB_HIST_LAST or
+ * PSB_HIST_SEQ, at most u_limit) followed by the candidate item's reviews (get_item_review_idxs, :135-160, fix=True,
+ * at most i_limit; PSB_HIST_SEQ: those not later than the entry review's time stamp, dataset.bisect_right).
+ * width = u_limit + i_limit.  Outputs, laid out [batch, n_cand, ...]:
+ *   ridxs [.., width]      review ids, right-padded with review_pad
+ *   seg   [.., width + 1]  0 (query slot), 1 per user review, 2 per item review, then seg_pad
+ *   users [.., width + 1]  user_pad, the entry's user per user review, each item review's author, then user_pad
+ *   items [.., width + 1]  item_pad, each user review's item, the candidate per item review, then item_pad
+ *   seq_len [batch, n_cand] number of reviews (optional)
+ * A candidate id < 0 (the reference's -1 padding of short candidate lists, :92) yields an all-pad row (seg all
+ * seg_pad), exactly what util.pad_3d(dim=1) appends.  The reference pads to the batch maximum: slice
+ * [..., :max(seq_len)] (+1) to reproduce its width. */
+int psb_build_review_test_batch(const psb_corpus_t* corpus /* host */, const int64_t* review_idx,
+                                const int64_t* user_idx, const int64_t* candi_prod_idxs, int64_t batch,
+                                int64_t n_cand, int64_t u_limit, int64_t i_limit, int32_t mode,
+                                int64_t review_pad, int64_t user_pad, int64_t item_pad, int64_t seg_pad,
+                                int64_t* ridxs, int64_t* seg, int64_t* users, int64_t* items, int32_t* seq_len,
+                                int32_t* err_flag, psb_stream_t stream);
 
 /* The subset key of PSB_HIST_RANDOM, evaluated on the host (tests, oracle cross-check). */
 uint32_t psb_subset_key(uint32_t seed, uint32_t sample, uint32_t pos);

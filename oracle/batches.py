@@ -18,7 +18,8 @@ and is checked for its defining properties instead.
 """
 import numpy as np
 
-__all__ = ["subset_key", "user_review_idxs", "pad", "item_train_batch", "item_test_batch", "ranklist_lines"]
+__all__ = ["subset_key", "user_review_idxs", "item_review_idxs", "pad", "pad_3d", "item_train_batch",
+           "item_test_batch", "review_test_batch", "ranklist_lines"]
 
 _M = 0xFFFFFFFF
 
@@ -93,6 +94,82 @@ def item_test_batch(corpus, entries, limit, do_seq, prod_pad_idx):
                 u_item_idxs=np.asarray(pad(hist, prod_pad_idx), np.int64).reshape(len(entries), -1),
                 user_idxs=e[:, 1].copy(), query_idxs=e[:, 0].copy(),
                 hist_len=np.asarray([len(h) for h in hist], np.int32))
+
+
+def bisect_right(review_arr, review_loc_time, timestamp):
+    """data/prod_search_dataset.py:135-152."""
+    lo, hi = 0, len(review_arr)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if timestamp < review_loc_time[review_arr[mid]][2]:
+            hi = mid
+        else:
+            lo = mid + 1
+    return lo
+
+
+def item_review_idxs(i_r_seq, train_set, review_loc_time, prod_idx, review_idx, limit, do_seq, review_time_stamp=None):
+    """data/prod_search_dataloader.py:135-160 with fix=True."""
+    seq = i_r_seq[prod_idx]
+    if do_seq:
+        if review_idx is None:
+            loc = bisect_right(seq, review_loc_time, review_time_stamp)
+        else:
+            loc = review_loc_time[review_idx][1]
+        if loc == 0:
+            return []
+        return list(seq[:loc][-limit:])
+    cand = [x for x in seq if x in train_set[prod_idx] and x != review_idx]
+    return cand[-limit:] if len(cand) > limit else cand
+
+
+def pad_3d(data, pad_id, dim=1, width=-1):
+    """others/util.py:43-62."""
+    if width == -1:
+        if dim == 1:
+            width = max(len(d) for d in data)
+        else:
+            for entry in data:
+                width = max(width, max(len(d) for d in entry))
+    if dim == 1:
+        return [list(d[:width]) + [[pad_id] * len(data[0][0])] * (width - len(d)) for d in data]
+    return [[list(d[:width]) + [pad_id] * (width - len(d)) for d in entry] for entry in data]
+
+
+def review_test_batch(corpus, entries, candidates, u_limit, i_limit, do_seq_review_test, train_review_only, pads):
+    """data/prod_search_dataloader.py:44-109.  entries: [(query_idx, user_idx, prod_idx, review_idx)];
+    candidates: per entry list of candidate items; pads: dict(review=, user=, prod=, seg=)."""
+    total = u_limit + i_limit
+    do_seq = do_seq_review_test and not train_review_only
+    all_r, all_s, all_u, all_i = [], [], [], []
+    for (query_idx, user_idx, prod_idx, review_idx), cands in zip(entries, candidates):
+        u_prev = user_review_idxs(corpus["u_r_seq"], corpus["u_reviews"], corpus["review_loc_time"], user_idx,
+                                  review_idx, u_limit, do_seq, True)
+        ts = corpus["review_loc_time"][review_idx][2] if do_seq_review_test else None
+        u_items = [corpus["review_u_p"][x][1] for x in u_prev]
+        br, bs, bu, bi = [], [], [], []
+        for c in cands:
+            c_prev = item_review_idxs(corpus["i_r_seq"], corpus["p_reviews"], corpus["review_loc_time"], c, None,
+                                      i_limit, do_seq, ts)
+            c_users = [corpus["review_u_p"][x][0] for x in c_prev]
+            bu.append(([pads["user"]] + [user_idx] * len(u_prev) + c_users)[:total + 1])
+            bi.append(([pads["prod"]] + u_items + [c] * len(c_prev))[:total + 1])
+            bs.append(([0] + [1] * len(u_prev) + [2] * len(c_prev))[:total + 1])
+            br.append((u_prev + c_prev)[:total])
+        all_r.append(br)
+        all_s.append(bs)
+        all_u.append(bu)
+        all_i.append(bi)
+    out = {}
+    for name, data, pad_id in (("candi_prod_ridxs", all_r, pads["review"]), ("candi_seg_idxs", all_s, pads["seg"]),
+                               ("candi_seq_user_idxs", all_u, pads["user"]),
+                               ("candi_seq_item_idxs", all_i, pads["prod"])):
+        data = pad_3d(data, pad_id, dim=1)
+        data = pad_3d(data, pad_id, dim=2)
+        out[name] = np.asarray(data, np.int64)
+    out["candi_prod_idxs"] = np.asarray(pad([list(c) for c in candidates], -1), np.int64)
+    out["query_word_idxs"] = np.asarray([corpus["query_words"][e[0]] for e in entries], np.int64)
+    return out
 
 
 def ranklist_lines(user_ids, user_idxs, query_idxs, product_ids, ranked_ids, ranked_scores, cutoff):

@@ -65,7 +65,8 @@ class Corpus(ctypes.Structure):
     _fields_ = [("review_user", c_vp), ("review_item", c_vp), ("review_uloc", c_vp), ("review_in_set", c_vp),
                 ("user_seq_off", c_vp), ("user_seq", c_vp), ("item_query_off", c_vp), ("item_query", c_vp),
                 ("query_words", c_vp), ("n_reviews", c_i64), ("n_users", c_i64), ("n_items", c_i64),
-                ("n_queries", c_i64), ("wq", c_i64), ("word_pad", c_i64)]
+                ("n_queries", c_i64), ("wq", c_i64), ("word_pad", c_i64), ("item_seq_off", c_vp), ("item_seq", c_vp),
+                ("review_time", c_vp)]
 
 
 HIST_SEQ, HIST_LAST, HIST_RANDOM = 0, 1, 2
@@ -116,6 +117,8 @@ SIGNATURES = {
     "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "psb_build_item_batch": (c_i32, [ctypes.POINTER(Corpus), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_u32,
                                      c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_build_review_test_batch": (c_i32, [ctypes.POINTER(Corpus), c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i32,
+                                            c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "psb_subset_key": (c_u32, [c_u32, c_u32, c_u32]),
     "psb_target_rank": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_write_ranklist": (c_i64, [ctypes.c_char_p, c_cpp, c_vp, c_vp, c_cpp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32]),

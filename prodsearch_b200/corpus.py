@@ -46,7 +46,7 @@ class ItemCorpus(object):
     """
 
     def __init__(self, device, user_seq, review_u_p, query_words, item_queries, train_reviews=None,
-                 review_uloc=None, product_size=None, vocab_size=None):
+                 review_uloc=None, product_size=None, vocab_size=None, item_seq=None, review_time=None):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("ItemCorpus lives in GPU memory (no CPU fallback for batch construction)")
@@ -77,12 +77,24 @@ class ItemCorpus(object):
         self.user_seq_off, self.user_seq = put(seq_off), put(seq)
         self.item_query_off, self.item_query = put(iq_off), put(iq)
         self.query_words = put(qw)
+        # review-transformer batches: every item's reviews in time order + the time stamps (i_r_seq, review_loc_time[:, 2])
+        self.item_seq_off = self.item_seq = self.review_time = None
+        if item_seq is not None:
+            io, iflat = _csr(list(item_seq) + [[]] * (P - len(item_seq)))
+            self.item_seq_off, self.item_seq = put(io), put(iflat)
+        if review_time is not None:
+            self.review_time = put(np.asarray(review_time, dtype=np.int64))
+        elif review_uloc is not None and len(review_uloc) and np.ndim(review_uloc[0]) and len(review_uloc[0]) >= 3:
+            self.review_time = put(np.asarray([x[2] for x in review_uloc], dtype=np.int64))
         self.n_reviews, self.n_users, self.n_items, self.n_queries, self.wq = R, U, P, qw.shape[0], qw.shape[1]
         self.prod_pad_idx = P                                       # item_pv_dataset.py:24
         self.word_pad_idx = (int(vocab_size) if vocab_size is not None else int(qw.max()) + 1) - 1
         c = _lib.Corpus()
+        self.user_pad_idx = U                                       # prod_search_dataset.py:23
+        self.review_pad_idx = R                                     # review_count - 1 (:26; review_count = R + 1)
+        self.seg_pad_idx = 3
         for name in ("review_user", "review_item", "review_uloc", "review_in_set", "user_seq_off", "user_seq",
-                     "item_query_off", "item_query", "query_words"):
+                     "item_query_off", "item_query", "query_words", "item_seq_off", "item_seq", "review_time"):
             t = getattr(self, name)
             setattr(c, name, None if t is None else t.data_ptr())
         c.n_reviews, c.n_users, c.n_items, c.n_queries, c.wq, c.word_pad = R, U, P, qw.shape[0], qw.shape[1], \
@@ -95,7 +107,7 @@ class ItemCorpus(object):
         return cls(device, global_data.u_r_seq, global_data.review_u_p, global_data.query_words,
                    prod_data.product_query_idx, train_reviews=prod_data.u_reviews,
                    review_uloc=global_data.review_loc_time, product_size=global_data.product_size,
-                   vocab_size=global_data.vocab_size)
+                   vocab_size=global_data.vocab_size, item_seq=global_data.i_r_seq)
 
     # ------------------------------------------------------------------ batches
     def _dev_i64(self, x):
@@ -166,6 +178,46 @@ class ItemCorpus(object):
                          query_idxs=q, user_idxs=self._dev_i64(user_idxs),
                          candi_prod_idxs=self._dev_i64(candi_prod_idxs) if candi_prod_idxs is not None else [],
                          hist_len=hlen)
+
+
+def _review_test_batch(self, query_idxs, user_idxs, prod_idxs, review_idxs, candi_prod_idxs, args, trim=True):
+    """ProdSearchDataLoader.get_test_batch (data/prod_search_dataloader.py:44-109) for entries
+    (query_idx, user_idx, prod_idx, review_idx) with candidate lists candi_prod_idxs [B, C] (-1 = padding, :92):
+    one psb_build_review_test_batch launch instead of the python loop over every candidate.  The result carries the
+    attribute names of ProdSearchTestBatch (data/batch_data.py:94-135)."""
+    if self.item_seq is None:
+        raise RuntimeError("this corpus was built without item_seq (global_data.i_r_seq)")
+    do_seq = args.do_seq_review_test and not args.train_review_only
+    mode = _lib.HIST_SEQ if do_seq else _lib.HIST_LAST
+    rv, us = self._dev_i64(review_idxs), self._dev_i64(user_idxs)
+    cand = self._dev_i64(candi_prod_idxs)
+    B, C = cand.shape
+    Lu, Li = int(args.uprev_review_limit), int(args.iprev_review_limit)
+    W = Lu + Li
+    dev = self.device
+    ridxs = torch.empty(B, C, W, dtype=torch.int64, device=dev)
+    seg = torch.empty(B, C, W + 1, dtype=torch.int64, device=dev)
+    users = torch.empty(B, C, W + 1, dtype=torch.int64, device=dev)
+    items = torch.empty(B, C, W + 1, dtype=torch.int64, device=dev)
+    slen = torch.empty(B, C, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().psb_build_review_test_batch(
+        ctypes.byref(self._c), _lib.ptr(rv), _lib.ptr(us), _lib.ptr(cand), B, C, Lu, Li, mode, self.review_pad_idx,
+        self.user_pad_idx, self.prod_pad_idx, self.seg_pad_idx, _lib.ptr(ridxs), _lib.ptr(seg), _lib.ptr(users),
+        _lib.ptr(items), _lib.ptr(slen), _lib.ptr(err), _lib.stream_ptr()), "psb_build_review_test_batch")
+    if trim:
+        if int(err.item()) != 0:
+            raise IndexError("psb_build_review_test_batch: review / user / candidate id out of range")
+        w = int(slen.max().item()) if B * C else 0
+        ridxs, seg = ridxs[:, :, :w].contiguous(), seg[:, :, :w + 1].contiguous()
+        users, items = users[:, :, :w + 1].contiguous(), items[:, :, :w + 1].contiguous()
+    qi = self._dev_i64(query_idxs)
+    return ItemBatch(query_idxs=qi, user_idxs=us, target_prod_idxs=self._dev_i64(prod_idxs), candi_prod_idxs=cand,
+                     query_word_idxs=self.query_words[qi], candi_prod_ridxs=ridxs, candi_seg_idxs=seg,
+                     candi_seq_user_idxs=users, candi_seq_item_idxs=items, seq_len=slen)
+
+
+ItemCorpus.review_test_batch = _review_test_batch
 
 
 def subset_key(seed, sample, pos):

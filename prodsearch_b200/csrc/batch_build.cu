@@ -151,6 +151,145 @@ build_item_batch_kernel(const __grid_constant__ BatchArgs A) {
   }
 }
 
+// ---- N3: review-transformer test batches ------------------------------------------------------------------
+struct ReviewBatchArgs {
+  psb_corpus_t C;
+  const int64_t* review_idx;
+  const int64_t* user_idx;
+  const int64_t* candi;
+  int64_t B, n_cand;
+  int u_limit, i_limit, mode;
+  int64_t review_pad, user_pad, item_pad, seg_pad;
+  int64_t *ridxs, *seg, *users, *items;
+  int32_t* seq_len;
+  int32_t* err_flag;
+};
+
+// Order-preserving emission of the LAST `limit` flagged entries of seq[0..n) (flag = training-split review other
+// than `skip_review`), or of the plain range [first, n) when `plain`.  Calls emit(j, review) with j = 0.. in order.
+template <typename Emit>
+__device__ __forceinline__ int emit_tail(const int32_t* __restrict__ seq, int n, const uint8_t* __restrict__ in_set,
+                                         int64_t skip_review, int limit, bool plain, int plain_first, int lane,
+                                         Emit&& emit) {
+  const unsigned lt = (1u << lane) - 1u;
+  if (plain) {
+    const int cnt = n - plain_first;
+    for (int j = lane; j < cnt; j += 32) emit(j, seq[plain_first + j]);
+    return cnt;
+  }
+  int n_cand = 0;
+  for (int p0 = 0; p0 < n; p0 += 32) {
+    const int p = p0 + lane;
+    bool c = false;
+    if (p < n) {
+      const int32_t r = seq[p];
+      c = in_set[r] != 0 && r != skip_review;
+    }
+    n_cand += __popc(__ballot_sync(kFull, c));
+  }
+  const int skip = n_cand > limit ? n_cand - limit : 0;
+  int seen = 0, n_out = 0;
+  for (int p0 = 0; p0 < n; p0 += 32) {
+    const int p = p0 + lane;
+    int32_t r = -1;
+    bool c = false;
+    if (p < n) {
+      r = seq[p];
+      c = in_set[r] != 0 && r != skip_review;
+    }
+    const unsigned cm = __ballot_sync(kFull, c);
+    const bool keep = c && (seen + __popc(cm & lt)) >= skip;
+    const unsigned km = __ballot_sync(kFull, keep);
+    if (keep) emit(n_out + __popc(km & lt), r);
+    n_out += __popc(km);
+    seen += __popc(cm);
+  }
+  return n_out;
+}
+
+__global__ void __launch_bounds__(256)
+build_review_test_batch_kernel(const __grid_constant__ ReviewBatchArgs A) {
+  const psb_corpus_t& C = A.C;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int W = A.u_limit + A.i_limit;
+  const bool seq_mode = A.mode == PSB_HIST_SEQ;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); e < A.B * A.n_cand;
+       e += nwarps) {
+    const int64_t b = e / A.n_cand;
+    const int64_t cand = A.candi[e];
+    int64_t* ridx = A.ridxs + e * W;
+    int64_t* seg = A.seg + e * (W + 1);
+    int64_t* usr = A.users + e * (W + 1);
+    int64_t* itm = A.items + e * (W + 1);
+    const int64_t review = A.review_idx[b];
+    const int64_t user = A.user_idx[b];
+    const bool review_ok = review >= 0 && review < C.n_reviews;
+    const bool bad = user < 0 || user >= C.n_users || cand >= C.n_items || (seq_mode && !review_ok);
+    if (cand < 0 || bad) {  // padded candidate slot (or invalid ids): an all-pad row
+      if (bad && lane == 0 && A.err_flag != nullptr) *A.err_flag = 1;
+      for (int j = lane; j < W; j += 32) ridx[j] = A.review_pad;
+      for (int j = lane; j <= W; j += 32) {
+        seg[j] = A.seg_pad;
+        usr[j] = A.user_pad;
+        itm[j] = A.item_pad;
+      }
+      if (lane == 0 && A.seq_len != nullptr) A.seq_len[e] = 0;
+      continue;
+    }
+    if (lane == 0) {
+      seg[0] = 0;
+      usr[0] = A.user_pad;
+      itm[0] = A.item_pad;
+    }
+    // user part
+    const int64_t us0 = C.user_seq_off[user];
+    const int un = static_cast<int>(C.user_seq_off[user + 1] - us0);
+    int u_first = 0;
+    if (seq_mode) {
+      const int loc = min(max(C.review_uloc[review], 0), un);
+      u_first = max(loc - A.u_limit, 0);
+    }
+    const int nu = emit_tail(C.user_seq + us0, seq_mode ? min(max(C.review_uloc[review], 0), un) : un, C.review_in_set,
+                             review, A.u_limit, seq_mode, u_first, lane, [&](int j, int32_t r) {
+                               ridx[j] = r;
+                               seg[1 + j] = 1;
+                               usr[1 + j] = user;
+                               itm[1 + j] = C.review_item[r];
+                             });
+    // candidate item part
+    const int64_t is0 = C.item_seq_off[cand];
+    const int in = static_cast<int>(C.item_seq_off[cand + 1] - is0);
+    const int32_t* iseq = C.item_seq + is0;
+    int i_end = in, i_first = 0;
+    if (seq_mode) {  // dataset.bisect_right on the time stamps (prod_search_dataset.py:135-152)
+      const int64_t ts = C.review_time[review];
+      int lo = 0, hi = in;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ts < C.review_time[iseq[mid]]) hi = mid; else lo = mid + 1;
+      }
+      i_end = lo;
+      i_first = max(i_end - A.i_limit, 0);
+    }
+    const int ni = emit_tail(iseq, i_end, C.review_in_set, -1, A.i_limit, seq_mode, i_first, lane,
+                             [&](int j, int32_t r) {
+                               ridx[nu + j] = r;
+                               seg[1 + nu + j] = 2;
+                               usr[1 + nu + j] = C.review_user[r];
+                               itm[1 + nu + j] = cand;
+                             });
+    const int n = nu + ni;
+    for (int j = n + lane; j < W; j += 32) ridx[j] = A.review_pad;
+    for (int j = 1 + n + lane; j <= W; j += 32) {
+      seg[j] = A.seg_pad;
+      usr[j] = A.user_pad;
+      itm[j] = A.item_pad;
+    }
+    if (lane == 0 && A.seq_len != nullptr) A.seq_len[e] = n;
+  }
+}
+
 // rank[i] = 1 + position of target[i] in ids[i, :k], 0 when it is not in the list (calc_metrics,
 // trainer.py:171-186, evaluated on the fused top-k lists instead of a full argsort).
 __global__ void __launch_bounds__(256)
@@ -216,6 +355,52 @@ extern "C" int psb_build_item_batch(const psb_corpus_t* corpus, const int64_t* r
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("build_item_batch_kernel", s);
   build_item_batch_kernel<<<grid_for(batch, 8), 256, 0, s>>>(A);
+  return launch_status();
+}
+
+extern "C" int psb_build_review_test_batch(const psb_corpus_t* corpus, const int64_t* review_idx,
+                                           const int64_t* user_idx, const int64_t* candi_prod_idxs, int64_t batch,
+                                           int64_t n_cand, int64_t u_limit, int64_t i_limit, int32_t mode,
+                                           int64_t review_pad, int64_t user_pad, int64_t item_pad, int64_t seg_pad,
+                                           int64_t* ridxs, int64_t* seg, int64_t* users, int64_t* items,
+                                           int32_t* seq_len, int32_t* err_flag, psb_stream_t stream) {
+  if (corpus == nullptr || batch < 0 || n_cand < 0 || u_limit < 0 || i_limit < 0 || u_limit + i_limit <= 0 ||
+      u_limit + i_limit > (1 << 20))
+    return PSB_E_ARG;
+  if (mode != PSB_HIST_SEQ && mode != PSB_HIST_LAST) return PSB_E_ARG;
+  if (batch == 0 || n_cand == 0) return PSB_OK;
+  const psb_corpus_t& C = *corpus;
+  if (C.review_user == nullptr || C.review_item == nullptr || C.review_in_set == nullptr ||
+      C.user_seq_off == nullptr || C.user_seq == nullptr || C.item_seq_off == nullptr || C.item_seq == nullptr ||
+      C.n_reviews <= 0 || C.n_users <= 0 || C.n_items <= 0)
+    return PSB_E_ARG;
+  if (mode == PSB_HIST_SEQ && (C.review_uloc == nullptr || C.review_time == nullptr)) return PSB_E_ARG;
+  if (review_idx == nullptr || user_idx == nullptr || candi_prod_idxs == nullptr || ridxs == nullptr ||
+      seg == nullptr || users == nullptr || items == nullptr)
+    return PSB_E_ARG;
+  ReviewBatchArgs A;
+  A.C = C;
+  A.review_idx = review_idx;
+  A.user_idx = user_idx;
+  A.candi = candi_prod_idxs;
+  A.B = batch;
+  A.n_cand = n_cand;
+  A.u_limit = static_cast<int>(u_limit);
+  A.i_limit = static_cast<int>(i_limit);
+  A.mode = mode;
+  A.review_pad = review_pad;
+  A.user_pad = user_pad;
+  A.item_pad = item_pad;
+  A.seg_pad = seg_pad;
+  A.ridxs = ridxs;
+  A.seg = seg;
+  A.users = users;
+  A.items = items;
+  A.seq_len = seq_len;
+  A.err_flag = err_flag;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("build_review_test_batch_kernel", s);
+  build_review_test_batch_kernel<<<grid_for(batch * n_cand, 8), 256, 0, s>>>(A);
   return launch_status();
 }
 

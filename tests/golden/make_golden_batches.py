@@ -55,7 +55,12 @@ def make_corpus(seed=7, U=24, P=17, Q=9, V=40, wq=5):
     query_words = [[int(x) for x in rng.integers(0, V - 1, size=int(l))] + [V - 1] * (wq - int(l)) for l in qlen]
     product_query_idx = [[int(x) for x in rng.choice(Q, size=int(rng.integers(1, 4)), replace=False)]
                          for _ in range(P)]
+    p_reviews = [set() for _ in range(P)]
+    for r in range(R):
+        if in_train[r]:
+            p_reviews[review_u_p[r][1]].add(r)
     return dict(U=U, P=P, Q=Q, V=V, wq=wq, R=R, review_u_p=review_u_p, u_r_seq=u_r_seq, review_loc_time=loc,
+                i_r_seq=i_r_seq, p_reviews=p_reviews,
                 u_reviews=u_reviews, query_words=query_words, product_query_idx=product_query_idx,
                 in_train=in_train.astype(np.uint8))
 
@@ -73,6 +78,25 @@ def loader(c, set_name, **flags):
                                       set_name=set_name)
     dl.prod_pad_idx = c["P"]
     return dl
+
+
+def review_loader(c, **flags):
+    """ProdSearchDataLoader with hand-set attributes (no DataLoader machinery, no files)."""
+    from data.prod_search_dataloader import ProdSearchDataLoader
+    from data.prod_search_dataset import ProdSearchDataset
+    dl = ProdSearchDataLoader.__new__(ProdSearchDataLoader)
+    a = dict(uprev_review_limit=4, iprev_review_limit=5, do_seq_review_test=False, train_review_only=True)
+    a.update(flags)
+    dl.args = argparse.Namespace(**a)
+    dl.global_data = argparse.Namespace(query_words=c["query_words"], review_u_p=c["review_u_p"],
+                                        u_r_seq=c["u_r_seq"], i_r_seq=c["i_r_seq"],
+                                        review_loc_time=c["review_loc_time"])
+    dl.prod_data = argparse.Namespace(u_reviews=c["u_reviews"], p_reviews=c["p_reviews"], set_name="test")
+    ds = ProdSearchDataset.__new__(ProdSearchDataset)
+    object.__setattr__(dl, "_stub_dataset", ds)
+    dl.prod_pad_idx, dl.user_pad_idx, dl.review_pad_idx, dl.seg_pad_idx = c["P"], c["U"], c["R"], 3
+    dl.total_review_limit = a["uprev_review_limit"] + a["iprev_review_limit"]
+    return dl, ds
 
 
 def csr(lists):
@@ -131,6 +155,26 @@ def main():
             out["test_%s/%s" % (tag, k)] = getattr(b, k).numpy()
         out["test_%s/user_idxs" % tag] = np.asarray(b.user_idxs, np.int64)
         out["test_%s/query_idxs" % tag] = np.asarray(b.query_idxs, np.int64)
+
+    # ---- review-transformer test batches: ragged candidate lists per entry
+    out["corpus/i_r_seq_off"], out["corpus/i_r_seq"] = csr(c["i_r_seq"])
+    r_entries = entries[:12]
+    cands = [[int(x) for x in rng.choice(c["P"], size=int(rng.integers(2, 8)), replace=False)] for _ in r_entries]
+    out["rtest/entries"] = np.asarray(r_entries, np.int64)
+    out["rtest/cand_off"], out["rtest/cand"] = csr(cands)
+    import torch.utils.data.dataloader as tdl
+    for tag, flags in (("last", dict()), ("seq", dict(do_seq_review_test=True, train_review_only=False))):
+        dl, ds = review_loader(c, **flags)
+        orig_prop = tdl.DataLoader.__dict__.get("dataset")
+        type(dl).dataset = property(lambda self: self._stub_dataset)     # only bisect_right is used (:140)
+        try:
+            b = dl.get_test_batch([e + [cd] for e, cd in zip(r_entries, cands)])
+        finally:
+            del type(dl).dataset
+        for k in ("query_word_idxs", "candi_prod_ridxs", "candi_seg_idxs", "candi_seq_user_idxs",
+                  "candi_seq_item_idxs"):
+            out["rtest_%s/%s" % (tag, k)] = getattr(b, k).numpy()
+        out["rtest_%s/candi_prod_idxs" % tag] = np.asarray(b.candi_prod_idxs, np.int64)
 
     # ---- run file + metrics from Trainer.test on a supplied tie-free score matrix
     from trainer import Trainer

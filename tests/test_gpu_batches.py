@@ -9,7 +9,7 @@ import torch
 
 import oracle
 from oracle import batches as ob
-from test_oracle_batches import GOLDEN, load_corpus
+from test_oracle_batches import GOLDEN, load_corpus, rtest_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def make_corpus(c, z=None, **kw):
     from prodsearch_b200.corpus import ItemCorpus
     return ItemCorpus("cuda:0", c["u_r_seq"], c["review_u_p"], c["query_words"], c["product_query_idx"],
-                      train_reviews=c["u_reviews"], review_uloc=c["review_loc_time"], **kw)
+                      train_reviews=c["u_reviews"], review_uloc=c["review_loc_time"], item_seq=c.get("i_r_seq"), **kw)
 
 
 def flags(**kw):
@@ -100,6 +100,55 @@ def test_large_corpus_matches_oracle(mode, limit):
     # run-to-run identical
     b2 = corpus.train_batch(reviews, words, fl, query_pick=picks, seed=12345)
     assert torch.equal(b.u_item_idxs, b2.u_item_idxs)
+
+
+def test_review_test_batches_match_reference_golden():
+    """psb_build_review_test_batch against ProdSearchDataLoader.get_test_batch's own output (N3)."""
+    z = np.load(GOLDEN)
+    c = load_corpus(z)
+    corpus = make_corpus(c, product_size=int(z["corpus/P"]), vocab_size=int(z["corpus/V"]))
+    entries, cands, pads = rtest_inputs(z)
+    e = np.asarray(entries)
+    for tag, seq_test, tro in (("last", False, True), ("seq", True, False)):
+        fl = argparse.Namespace(uprev_review_limit=4, iprev_review_limit=5, do_seq_review_test=seq_test,
+                                train_review_only=tro)
+        cand = z["rtest_%s/candi_prod_idxs" % tag]
+        b = corpus.review_test_batch(e[:, 0], e[:, 1], e[:, 2], e[:, 3], cand, fl)
+        for k in ("query_word_idxs", "candi_prod_ridxs", "candi_seg_idxs", "candi_seq_user_idxs",
+                  "candi_seq_item_idxs", "candi_prod_idxs"):
+            assert np.array_equal(getattr(b, k).cpu().numpy(), z["rtest_%s/%s" % (tag, k)]), (tag, k)
+
+
+@pytest.mark.parametrize("seq", [False, True])
+def test_review_test_batches_large_match_oracle(seq):
+    c, P, V = big_corpus(21, U=200, P=120, Q=30, max_len=90)
+    rng = np.random.default_rng(8)
+    R = len(c["review_u_p"])
+    times = rng.integers(0, 5000, size=R)                      # duplicate time stamps exercise bisect_right
+    c["i_r_seq"] = [[] for _ in range(P)]
+    for r in sorted(range(R), key=lambda r: (times[r], r)):
+        c["i_r_seq"][c["review_u_p"][r][1]].append(r)
+    for r in range(R):
+        c["review_loc_time"][r][2] = int(times[r])
+    c["p_reviews"] = [set() for _ in range(P)]
+    for u_set in c["u_reviews"]:
+        for r in u_set:
+            c["p_reviews"][c["review_u_p"][r][1]].add(r)
+    corpus = make_corpus(c, product_size=P, vocab_size=V)
+    entries = []
+    for r in rng.choice(R, size=40, replace=False):
+        u, p = c["review_u_p"][int(r)]
+        entries.append((int(c["product_query_idx"][p][0]), u, p, int(r)))
+    cands = [[int(x) for x in rng.choice(P, size=int(rng.integers(1, 60)), replace=False)] for _ in entries]
+    pads = dict(review=R, user=200, prod=P, seg=3)
+    fl = argparse.Namespace(uprev_review_limit=20, iprev_review_limit=30, do_seq_review_test=seq,
+                            train_review_only=not seq)
+    ref = ob.review_test_batch(c, entries, cands, 20, 30, seq, not seq, pads)
+    e = np.asarray(entries)
+    b = corpus.review_test_batch(e[:, 0], e[:, 1], e[:, 2], e[:, 3], ref["candi_prod_idxs"], fl)
+    for k in ("query_word_idxs", "candi_prod_ridxs", "candi_seg_idxs", "candi_seq_user_idxs",
+              "candi_seq_item_idxs"):
+        assert np.array_equal(getattr(b, k).cpu().numpy(), ref[k]), k
 
 
 def test_bad_ids_raise_and_empty_batch():

@@ -19,7 +19,12 @@ def load_corpus(z):
     u_reviews = [set() for _ in u_r_seq]
     for r in np.flatnonzero(z["corpus/in_train"]):
         u_reviews[int(rup[r, 0])].add(int(r))
-    return dict(review_u_p=[[int(a), int(b)] for a, b in rup], u_r_seq=u_r_seq,
+    i_r_seq = uncsr(z["corpus/i_r_seq_off"], z["corpus/i_r_seq"])
+    p_reviews = [set() for _ in i_r_seq]
+    for r in np.flatnonzero(z["corpus/in_train"]):
+        p_reviews[int(rup[r, 1])].add(int(r))
+    return dict(i_r_seq=i_r_seq, p_reviews=p_reviews,
+                review_u_p=[[int(a), int(b)] for a, b in rup], u_r_seq=u_r_seq,
                 review_loc_time=[[int(x) for x in row] for row in z["corpus/review_loc_time"]],
                 u_reviews=u_reviews, query_words=[[int(x) for x in row] for row in z["corpus/query_words"]],
                 product_query_idx=uncsr(z["corpus/pq_off"], z["corpus/pq"]))
@@ -44,6 +49,26 @@ def test_test_batches_match_reference():
         b = ob.item_test_batch(c, entries, 6, do_seq, int(z["corpus/P"]))
         for k in ("query_word_idxs", "target_prod_idxs", "u_item_idxs", "user_idxs", "query_idxs"):
             assert np.array_equal(b[k], z["test_%s/%s" % (tag, k)]), (tag, k)
+
+
+def rtest_inputs(z):
+    entries = [tuple(int(x) for x in e) for e in z["rtest/entries"]]
+    off, flat = z["rtest/cand_off"], z["rtest/cand"]
+    cands = [[int(x) for x in flat[off[i]:off[i + 1]]] for i in range(len(entries))]
+    pads = dict(review=int(z["corpus/R"]), user=int(z["corpus/U"]), prod=int(z["corpus/P"]), seg=3)
+    return entries, cands, pads
+
+
+def test_review_test_batches_match_reference():
+    z = np.load(GOLDEN)
+    c = load_corpus(z)
+    entries, cands, pads = rtest_inputs(z)
+    assert len(set(len(x) for x in cands)) > 1                   # ragged candidate lists: -1 / all-pad rows occur
+    for tag, seq_test, tro in (("last", False, True), ("seq", True, False)):
+        b = ob.review_test_batch(c, entries, cands, 4, 5, seq_test, tro, pads)
+        for k in ("query_word_idxs", "candi_prod_ridxs", "candi_seg_idxs", "candi_seq_user_idxs",
+                  "candi_seq_item_idxs", "candi_prod_idxs"):
+            assert np.array_equal(b[k], z["rtest_%s/%s" % (tag, k)]), (tag, k)
 
 
 def _ranked(z):
