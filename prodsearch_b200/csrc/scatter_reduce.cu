@@ -366,13 +366,14 @@ constexpr int kNT = 256;
 constexpr int kIPT = 16;
 constexpr int kTile = kNT * kIPT;  // 4096 keys per CTA
 
-// hist[digit * nblocks + block].  FIRST: the keys of pass 0 are formed on the fly from the contributions' int64
-// destination rows (no separate pack pass; the slot payload of pass 0 is the position itself).  Every warp counts
-// into its own 256 bins (shared-memory atomics on one CTA-wide histogram serialise on popular digits).
+// hist[digit * nblocks + block].  FIRST (pass 0): the keys are formed here from the contributions' int64
+// destination rows and written out (the pack pass and the first histogram pass are one kernel; the slot payload
+// of pass 0 is the position itself and is never stored).  Every warp counts into its own 256 bins
+// (shared-memory atomics on one CTA-wide histogram serialise on popular digits).
 template <bool FIRST>
 __global__ void __launch_bounds__(kNT)
 radix_hist_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, int64_t drop_idx,
-                  const uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
+                  uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
   __shared__ int h[(kNT / 32) * 256];
   for (int t = threadIdx.x; t < (kNT / 32) * 256; t += kNT) h[t] = 0;
   __syncthreads();
@@ -386,8 +387,13 @@ radix_hist_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, in
     if (p < n) k[r] = FIRST ? make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx) : keys[p];
   }
 #pragma unroll
-  for (int r = 0; r < kIPT; ++r)
-    if (base + r * kNT + threadIdx.x < n) atomicAdd(&mine[(k[r] >> shift) & 255u], 1);  // integer counts: order-free
+  for (int r = 0; r < kIPT; ++r) {
+    const int64_t p = base + r * kNT + threadIdx.x;
+    if (p < n) {
+      if (FIRST) keys[p] = k[r];
+      atomicAdd(&mine[(k[r] >> shift) & 255u], 1);  // integer counts: order-free
+    }
+  }
   __syncthreads();
   int tot = 0;
 #pragma unroll
@@ -414,8 +420,7 @@ radix_scan_kernel(int* __restrict__ hist, int nblocks, int* __restrict__ totals)
 
 template <bool BALLOT, bool FIRST>
 __global__ void __launch_bounds__(kNT, 3)
-radix_scatter_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, int64_t drop_idx,
-                     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
                      int shift, int nblocks, const int* __restrict__ hist, const int* __restrict__ totals,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t sk[kTile];
@@ -439,13 +444,9 @@ radix_scatter_kernel(const __grid_constant__ ContribTable T, int64_t table_rows,
   for (int r = 0; r < kIPT; ++r) {
     const int p = wid * 32 * kIPT + r * 32 + lane;
     valid[r] = p < tile_valid;
-    if (FIRST) {
-      key[r] = valid[r] ? make_key(T, static_cast<uint32_t>(base + p), table_rows, drop_idx) : 0xffffffffu;
-      val[r] = static_cast<uint32_t>(base + p);
-    } else {
-      key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
-      val[r] = valid[r] ? vals_in[base + p] : 0u;
-    }
+    key[r] = valid[r] ? keys_in[base + p] : 0xffffffffu;
+    if (FIRST) val[r] = static_cast<uint32_t>(base + p);   // pass 0: the payload is the slot position
+    else val[r] = valid[r] ? vals_in[base + p] : 0u;
   }
   tile_rank<kNT, kIPT, BALLOT>(key, valid, shift, pos, whist, dstart, scan_sm);
 #pragma unroll
@@ -723,9 +724,64 @@ seg_reduce_kernel(const __grid_constant__ ContribTable T, const uint32_t* __rest
   }
 }
 
-// One warp per work item (a segment that spans several units, listed by seg_reduce_kernel): the per-unit partials
-// are added in unit order, U partial rows in flight at a time.  (The first version walked ALL segments, one per
-// warp iteration with two dependent loads each: 184 us for 3.5M single-unit segments that needed no work.)
+// Fix-up of the segments that span several units (listed by seg_reduce_kernel): the per-unit partials are added
+// in a fixed bracketing that is a pure function of the segment's unit range --
+//   * U consecutive units (a "batch", U partial rows in flight) are added as a binary tree, batches in unit order;
+//   * a segment of at most kFixLong units is folded by one warp;
+//   * a longer one (a Zipf-head row: ~1000 units) by a whole CTA: the unit range is cut into 8 contiguous chunks,
+//     one per warp, and the 8 chunk sums are added in chunk order -- the serial chain of the hottest row is 8x
+//     shorter (it was the critical path of the whole kernel: 150 us).
+// (The first version walked ALL segments, one per warp iteration with two dependent loads each: 184 us for 3.5M
+// single-unit segments that needed no work.)
+constexpr int kFixLong = 64;
+
+template <int C, int U>
+__device__ __forceinline__ void fix_range(const float4* __restrict__ partial, const float* __restrict__ partial_bias,
+                                          int d4, int lane, int u_first, int u_lo, int u_hi, float4 (&acc)[C],
+                                          float& bacc) {
+  for (int u0 = u_lo; u0 <= u_hi; u0 += U) {
+    float4 v[U][C];
+    float pb[U];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int u = min(u0 + t, u_hi);
+      // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
+      const int64_t ps = static_cast<int64_t>(u) * 2 + (u == u_first ? 1 : 0);
+      pb[t] = partial_bias[ps];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int col = lane + 32 * c;
+        v[t][c] = col < d4 ? ldg_row4(partial + ps * d4 + col) : zero4();
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      if (u0 + t > u_hi) {  // past the end: contributes +0
+        pb[t] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[t][c] = zero4();
+      }
+    }
+#pragma unroll
+    for (int w2 = 1; w2 < U; w2 <<= 1) {
+#pragma unroll
+      for (int t = 0; t + w2 < U; t += 2 * w2) {
+        pb[t] += pb[t + w2];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          v[t][c].x += v[t + w2][c].x; v[t][c].y += v[t + w2][c].y;
+          v[t][c].z += v[t + w2][c].z; v[t][c].w += v[t + w2][c].w;
+        }
+      }
+    }
+    bacc += pb[0];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[c].x += v[0][c].x; acc[c].y += v[0][c].y; acc[c].z += v[0][c].z; acc[c].w += v[0][c].w;
+    }
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ unique_rows,
@@ -733,61 +789,13 @@ seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restric
                  float4* __restrict__ reduced, float* __restrict__ reduced_bias, float4* __restrict__ dense,
                  float* __restrict__ dense_bias, const float4* __restrict__ partial,
                  const float* __restrict__ partial_bias) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float4 s_acc[8][C * 32];
+  __shared__ float s_b[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int n_work = *work_count;
   constexpr int U = C == 1 ? 16 : 8;
-  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_work; e += nwarps) {
-    const int seg = work[e];
-    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
-    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
-    float4 acc[C];
-    float bacc = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = zero4();
-    for (int u0 = u_first; u0 <= u_last; u0 += U) {
-      float4 v[U][C];
-      float pb[U];
-#pragma unroll
-      for (int t = 0; t < U; ++t) {
-        const int u = min(u0 + t, u_last);
-        // the run of unit u_first starts there (slot 1); later units hold a continuing run (slot 0)
-        const int64_t ps = static_cast<int64_t>(u) * 2 + (u == u_first ? 1 : 0);
-        pb[t] = partial_bias[ps];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = lane + 32 * c;
-          v[t][c] = col < d4 ? ldg_row4(partial + ps * d4 + col) : zero4();
-        }
-      }
-      // units past the end of the segment contribute +0; the U rows of a batch are added as a fixed binary tree
-      // (a pure function of the unit's position in the segment: reproducible), the batches in unit order
-#pragma unroll
-      for (int t = 0; t < U; ++t) {
-        if (u0 + t > u_last) {
-          pb[t] = 0.f;
-#pragma unroll
-          for (int c = 0; c < C; ++c) v[t][c] = zero4();
-        }
-      }
-#pragma unroll
-      for (int w2 = 1; w2 < U; w2 <<= 1) {
-#pragma unroll
-        for (int t = 0; t + w2 < U; t += 2 * w2) {
-          pb[t] += pb[t + w2];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            v[t][c].x += v[t + w2][c].x; v[t][c].y += v[t + w2][c].y;
-            v[t][c].z += v[t + w2][c].z; v[t][c].w += v[t + w2][c].w;
-          }
-        }
-      }
-      bacc += pb[0];
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        acc[c].x += v[0][c].x; acc[c].y += v[0][c].y; acc[c].z += v[0][c].z; acc[c].w += v[0][c].w;
-      }
-    }
+  auto store = [&](int seg, const float4 (&acc)[C], float bacc) {
     const int64_t drow = unique_rows[seg];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -800,6 +808,51 @@ seg_fixup_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restric
     if (lane == 0) {
       if (reduced_bias != nullptr) reduced_bias[seg] = bacc;
       if (dense_bias != nullptr) dense_bias[drow] = bacc;
+    }
+  };
+  // (1) one warp per short work item
+  for (int e = blockIdx.x * (blockDim.x >> 5) + wid; e < n_work; e += nwarps) {
+    const int seg = work[e];
+    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
+    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
+    if (u_last - u_first + 1 > kFixLong) continue;
+    float4 acc[C];
+    float bacc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = zero4();
+    fix_range<C, U>(partial, partial_bias, d4, lane, u_first, u_first, u_last, acc, bacc);
+    store(seg, acc, bacc);
+  }
+  // (2) one CTA per long work item
+  for (int e = blockIdx.x; e < n_work; e += gridDim.x) {
+    const int seg = work[e];
+    const int s_lo = seg_start[seg], s_hi = seg_start[seg + 1];
+    const int u_first = s_lo >> ch_shift, u_last = (s_hi - 1) >> ch_shift;
+    const int n_units = u_last - u_first + 1;
+    if (n_units <= kFixLong) continue;      // CTA-uniform
+    const int per = (n_units + 7) >> 3;
+    const int lo = u_first + wid * per, hi = min(lo + per - 1, u_last);
+    float4 acc[C];
+    float bacc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = zero4();
+    if (lo <= hi) fix_range<C, U>(partial, partial_bias, d4, lane, u_first, lo, hi, acc, bacc);
+    __syncthreads();                        // s_acc free (previous item's reads are done)
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_acc[wid][c * 32 + lane] = acc[c];
+    if (lane == 0) s_b[wid] = bacc;
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int w2 = 1; w2 < 8; ++w2) {
+        bacc += s_b[w2];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float4 o = s_acc[w2][c * 32 + lane];
+          acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+        }
+      }
+      store(seg, acc, bacc);
     }
   }
 }
@@ -967,8 +1020,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
       if ((st = launch_status()) != PSB_OK) return st;
       PSB_PROF("radix_scatter_kernel", s);
 #define PSB_RS_LAUNCH(B, F)                                                                                      \
-  radix_scatter_kernel<B, F><<<nblocks, kNT, 0, s>>>(T, table_rows, drop_idx, ki, vi, n_total, pass * 8, nblocks, \
-                                                     hist, totals, ko, vo)
+  radix_scatter_kernel<B, F><<<nblocks, kNT, 0, s>>>(ki, vi, n_total, pass * 8, nblocks, hist, totals, ko, vo)
       if (pass == 0) { if (ballot) PSB_RS_LAUNCH(true, true); else PSB_RS_LAUNCH(false, true); }
       else { if (ballot) PSB_RS_LAUNCH(true, false); else PSB_RS_LAUNCH(false, false); }
 #undef PSB_RS_LAUNCH

@@ -282,15 +282,56 @@ def test_scatter_reduce_all_dropped_and_single(ops):
     idx[:] = 4
     uniq, red, _, nu = ops.scatter_reduce([ops.make_contrib(dev(idx), dev(src))], 10, 128, drop_idx=9)
     assert int(nu.item()) == 1 and int(uniq[0]) == 4
-    # the kernel's fixed bracketing: sequential sums over units of 8 slots (n_total <= 65536),
-    # unit partials added in unit order -- reproduced here term by term, so equality is bit-exact
-    seq = torch.zeros(128)
-    for u0 in range(0, 50, 8):
-        part = torch.zeros(128)
-        for r in src[u0:u0 + 8]:
+    assert torch.equal(red[0].cpu(), _bracketed_sum(src, 8))
+
+
+def _bracketed_sum(src, unit, batch=16, long_units=64):
+    """The kernels' fixed bracketing, term by term (so equality is bit-exact): sequential sums inside a unit of
+    `unit` sorted slots (seg_reduce_kernel); unit partials combined by the fix-up kernel -- batches of 16 units as a
+    binary tree, batches in unit order; a segment of more than 64 units is cut into 8 contiguous chunks (one per
+    warp) whose sums are added in chunk order."""
+    parts = []
+    for u0 in range(0, src.shape[0], unit):
+        part = torch.zeros(src.shape[1])
+        for r in src[u0:u0 + unit]:
             part = part + r
-        seq = seq + part
-    assert torch.equal(red[0].cpu(), seq)
+        parts.append(part)
+    if len(parts) == 1:
+        return parts[0]
+
+    def fold(ps):
+        acc = torch.zeros(src.shape[1])
+        for b0 in range(0, len(ps), batch):
+            v = list(ps[b0:b0 + batch]) + [torch.zeros(src.shape[1])] * (batch - len(ps[b0:b0 + batch]))
+            w = 1
+            while w < batch:
+                for t in range(0, batch - w, 2 * w):
+                    v[t] = v[t] + v[t + w]
+                w *= 2
+            acc = acc + v[0]
+        return acc
+    if len(parts) <= long_units:
+        return fold(parts)
+    per = (len(parts) + 7) // 8
+    total = None
+    for w in range(8):
+        chunk = fold(parts[w * per:(w + 1) * per])
+        total = chunk if total is None else total + chunk
+    return total
+
+
+def test_scatter_reduce_long_segment_bracketing(ops):
+    """A hot row spanning > 64 units goes through the CTA-cooperative fix-up; all paths are bit-reproducible."""
+    g = torch.Generator().manual_seed(3)
+    n = 8 * 150 + 5                                       # 151 units of 8 slots: the long path
+    idx = torch.full((n,), 7, dtype=torch.int64)
+    src = torch.randn(n, 128, generator=g)
+    uniq, red, _, nu = ops.scatter_reduce([ops.make_contrib(dev(idx), dev(src))], 20, 128, drop_idx=19)
+    assert int(nu.item()) == 1 and int(uniq[0]) == 7
+    assert torch.equal(red[0].cpu(), _bracketed_sum(src, 8))
+    assert torch.allclose(red[0].cpu(), src.double().sum(0).float(), rtol=1e-5, atol=1e-4)
+    uniq2, red2, _, _ = ops.scatter_reduce([ops.make_contrib(dev(idx), dev(src))], 20, 128, drop_idx=19)
+    assert torch.equal(red, red2)
 
 
 # ---------------------------------------------------------------- G5 (exact mode) + merge
