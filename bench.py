@@ -43,6 +43,13 @@ def model_args(dropout):
         l2_lambda=0.0, train_from="")
 
 
+def load_traffic():
+    """ncu-measured DRAM bytes per launch (profiles/ncu_traffic.json, written by profiles/make_traffic.py from the
+    committed ncu exports): {regime: {kernel: {...}}}; empty when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -188,9 +195,16 @@ def bandwidth_regime(peaks, rows=16_000_000, d=128):
     table[rows] = 0
     GB = 1e9
 
+    traffic = load_traffic().get("bandwidth", {})
+    main_kernel = {"G1": "gather_rows_kernel", "G4": "meanpool_kernel", "G3": "ns_loss_w1_kernel", "G2": "seg_reduce_kernel"}
+
     def entry(name, sec, nbytes, note):
         out[name] = {"ms": sec * 1e3, "achieved": nbytes / sec / GB, "unit": "GB/s", "peak": peaks["hbm"],
                      "frac": nbytes / sec / GB / peaks["hbm"], "algorithmic_bytes": nbytes, "note": note}
+        tr = traffic.get(main_kernel.get(name[:2], ""))
+        if tr is not None and not name.endswith("_zipf"):     # ncu DRAM bytes of the entry's main kernel, one launch
+            out[name]["traffic"] = tr["dram_bytes_per_launch"]
+            out[name]["traffic_kernel"] = main_kernel[name[:2]]
 
     n = 4_000_000
     idx = synth.gather_indices(n, rows, seed=1, dist="uniform").to(dev)
@@ -490,6 +504,10 @@ def run_b200_arm(a):
                               "the same gather / loss / scatter kernels on a 16M-row table where the roofline binds."
                               % (100.0 * ent["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()),
                                  sum(k["ms_per_step"] for k in kernels.values()))}
+        tr = load_traffic().get("step", {}).get(name)
+        if tr is not None:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, " + tr["source"]
         if ent.get("bound") == "tensor":
             roofline["note"] = ("GEMM-shaped (B*(1+K) rows x 128 -> 512 -> 128) but computed in fp32 FFMA on CUDA cores to "
                                 "hold the 1e-5 parity bar; %.1f%% of the fp32 FFMA peak (%.1f TFLOP/s at the sampled clock)"

@@ -583,7 +583,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   a.gkv = ws + W.gkv;
   a.lnp = ws + W.lnp_t;
   a.seed_dev = cfg->seed_dev;
-  st = D.R == 24 ? launch_tail_bwd<24>(a, s) : launch_tail_bwd<16>(a, s);
+  st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
   if (st != PSB_OK) return st;
 
   st = launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr, ws + W.gxn, d, s);

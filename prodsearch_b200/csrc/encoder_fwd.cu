@@ -40,18 +40,26 @@ int dims_from_cfg(const psb_encoder_cfg_t* c, Dims* D) {
   D->C = static_cast<int>(c->copies);
   D->o = static_cast<int>(c->out_pos);
   D->pre_ln = c->pre_ln != 0;
-  // tile rows: whole sequences per tile; prefer the variant that wastes fewer rows, then more CTAs
-  const int spt16 = 16 / D->C, spt24 = 24 / D->C;
-  const int used16 = spt16 * D->C, used24 = spt24 * D->C;
-  bool pick24 = spt16 == 0 || used24 * 16 > used16 * 24;   // utilisation 24 strictly better
-  if (!pick24 && spt24 > 0 && used24 * 16 == used16 * 24)  // equal utilisation: 24 only when it still fills the GPU
-    pick24 = (D->S + spt24 - 1) / spt24 >= 2 * kNumSMs;
+  // tile rows R (whole sequences per tile, spt = R / copies): the tail kernels run one CTA per SM whose time is
+  // ~ (fixed latency + R), so pick the R in {16, 20, 24} with the least waves * (R + 10).  At the reference's
+  // 1 + 5 copies and batch 384: R = 20 -> 128 tiles in one wave (R = 24: 96 tiles on 148 SMs; R = 16: two waves).
   const size_t smem_cap = 227 * 1024;
-  if (pick24 && tail_bwd_smem_floats(24, D->d, D->F, D->H, D->T, spt24) * sizeof(float) > smem_cap) pick24 = false;
-  if (!pick24 && spt16 == 0) return PSB_E_UNSUPPORTED;
-  D->R = pick24 ? 24 : 16;
-  D->spt = pick24 ? spt24 : spt16;
-  if (tail_bwd_smem_floats(D->R, D->d, D->F, D->H, D->T, D->spt) * sizeof(float) > smem_cap) return PSB_E_UNSUPPORTED;
+  int best_R = 0;
+  long best_cost = 0;
+  for (int R = 16; R <= 24; R += 4) {
+    const int spt = R / D->C;
+    if (spt == 0) continue;
+    if (tail_bwd_smem_floats(R, D->d, D->F, D->H, D->T, spt) * sizeof(float) > smem_cap) continue;
+    const long tiles = (D->S + spt - 1) / spt;
+    const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * (R + 10);
+    if (best_R == 0 || cost < best_cost) {
+      best_R = R;
+      best_cost = cost;
+    }
+  }
+  if (best_R == 0) return PSB_E_UNSUPPORTED;
+  D->R = best_R;
+  D->spt = best_R / D->C;
   D->ntile = (D->S + D->spt - 1) / D->spt;
   D->eps = c->ln_eps;
   D->qscale = 1.f / sqrtf(static_cast<float>(D->dh));
@@ -591,5 +599,5 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   a.ctx = sv + L.ctx; a.y = sv + L.y; a.n = sv + L.n; a.z = sv + L.z; a.pre1 = sv + L.pre1; a.h1 = sv + L.h1;
   a.out = out;
   a.seed_dev = cfg->seed_dev;
-  return D.R == 24 ? launch_tail_fwd<24>(a, s) : launch_tail_fwd<16>(a, s);
+  return D.R == 24 ? launch_tail_fwd<24>(a, s) : D.R == 20 ? launch_tail_fwd<20>(a, s) : launch_tail_fwd<16>(a, s);
 }

@@ -371,7 +371,7 @@ constexpr int kTile = kNT * kIPT;  // 4096 keys per CTA
 // of pass 0 is the position itself and is never stored).  Every warp counts into its own 256 bins
 // (shared-memory atomics on one CTA-wide histogram serialise on popular digits).
 template <bool FIRST>
-__global__ void __launch_bounds__(kNT)
+__global__ void __launch_bounds__(kNT, 8)   // 8 CTAs/SM: the ~1000 tiles of a 4M-slot sort fit in one wave
 radix_hist_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, int64_t drop_idx,
                   uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
   __shared__ int h[(kNT / 32) * 256];
@@ -379,19 +379,23 @@ radix_hist_kernel(const __grid_constant__ ContribTable T, int64_t table_rows, in
   __syncthreads();
   int* mine = h + (threadIdx.x >> 5) * 256;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
-  uint32_t k[kIPT];
+  constexpr int G = 4;  // keys in flight per thread (kept small: 16 int64 row ids would cost 32 registers)
 #pragma unroll
-  for (int r = 0; r < kIPT; ++r) {
-    const int64_t p = base + r * kNT + threadIdx.x;
-    k[r] = 0xffffffffu;
-    if (p < n) k[r] = FIRST ? make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx) : keys[p];
-  }
+  for (int r0 = 0; r0 < kIPT; r0 += G) {
+    uint32_t k[G];
 #pragma unroll
-  for (int r = 0; r < kIPT; ++r) {
-    const int64_t p = base + r * kNT + threadIdx.x;
-    if (p < n) {
-      if (FIRST) keys[p] = k[r];
-      atomicAdd(&mine[(k[r] >> shift) & 255u], 1);  // integer counts: order-free
+    for (int g = 0; g < G; ++g) {
+      const int64_t p = base + (r0 + g) * kNT + threadIdx.x;
+      k[g] = 0xffffffffu;
+      if (p < n) k[g] = FIRST ? make_key(T, static_cast<uint32_t>(p), table_rows, drop_idx) : keys[p];
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int64_t p = base + (r0 + g) * kNT + threadIdx.x;
+      if (p < n) {
+        if (FIRST) keys[p] = k[g];
+        atomicAdd(&mine[(k[g] >> shift) & 255u], 1);  // integer counts: order-free
+      }
     }
   }
   __syncthreads();
