@@ -14,6 +14,30 @@ from torch.autograd import Function, Variable
 from . import ops
 
 
+def run_forked(sink):
+    """Run ``sink.finalize()`` on the sink's own side stream, forked from the stream ``backward()`` runs on; one
+    extra engine callback (queued by the first forked sink, so it runs after every finalize callback already queued)
+    joins all side streams back before ``backward()`` returns.  Inside a captured CUDA graph the chains become
+    parallel branches.  ``sink`` needs ``weight``, ``_pending``, ``_stream``, ``_hold`` and ``finalize()``."""
+    dev = sink.weight.device
+    cur = torch.cuda.current_stream(dev)
+    if sink._stream is None:
+        sink._stream = torch.cuda.Stream(device=dev)
+    sink._stream.wait_stream(cur)
+    sink._hold = list(sink._pending)              # contribution tensors stay alive until the join
+    first = not RowGradSink._forked
+    RowGradSink._forked.append(sink)
+    try:
+        with torch.cuda.stream(sink._stream):
+            sink.finalize()
+    except Exception:
+        RowGradSink._forked.remove(sink)
+        sink._hold = None
+        raise
+    if first:
+        Variable._execution_engine.queue_callback(RowGradSink._join_forked)
+
+
 class RowGradSink(object):
     """Gradient collector for one embedding table (and the bias vector indexed like it).
 
@@ -53,29 +77,7 @@ class RowGradSink(object):
     def _finalize_callback(self):
         if not (RowGradSink.concurrent and self.mode == "dense" and self.weight.is_cuda):
             return self.finalize()
-        cur = torch.cuda.current_stream(self.weight.device)
-        if self._stream is None:
-            self._stream = torch.cuda.Stream(device=self.weight.device)
-        self._stream.wait_stream(cur)
-        self._hold = list(self._pending)          # contribution tensors stay alive until the join
-        first = not RowGradSink._forked
-        RowGradSink._forked.append(self)
-        try:
-            with torch.cuda.stream(self._stream):
-                self.finalize()
-        except Exception:
-            RowGradSink._forked.remove(self)
-            self._hold = None
-            raise
-        if first:                                 # runs after every finalize callback already queued
-            Variable._execution_engine.queue_callback(RowGradSink._join_forked)
-
-    @staticmethod
-    def _join_forked():
-        forked, RowGradSink._forked = RowGradSink._forked, []
-        for sink in forked:
-            torch.cuda.current_stream(sink.weight.device).wait_stream(sink._stream)
-            sink._hold = None
+        run_forked(self)
 
     # -- runs once, after the whole backward graph has executed --------------------------
     def finalize(self):

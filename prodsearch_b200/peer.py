@@ -321,6 +321,15 @@ class PeerGradSink(object):
         self._ids = None
         self._origin = {}
         self.weight = table.weight
+        self._stream = None
+        self._hold = None
+
+    def _finalize_callback(self):
+        from . import functional as F_
+        if F_.RowGradSink.concurrent:
+            F_.run_forked(self)       # the item and the word table's sort + reduce chains overlap
+        else:
+            self.finalize()
 
     def begin(self, ids, origin):
         self._ids, self._origin = ids, origin
@@ -335,7 +344,7 @@ class PeerGradSink(object):
                                               to_bias and self.table.bias is not None))
         if not self._queued:
             self._queued = True
-            Variable._execution_engine.queue_callback(self.finalize)
+            Variable._execution_engine.queue_callback(self._finalize_callback)
 
     def finalize(self):
         from . import ops
