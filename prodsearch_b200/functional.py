@@ -79,6 +79,13 @@ class RowGradSink(object):
             return self.finalize()
         run_forked(self)
 
+    @staticmethod
+    def _join_forked():
+        forked, RowGradSink._forked = RowGradSink._forked, []
+        for sink in forked:
+            torch.cuda.current_stream(sink.weight.device).wait_stream(sink._stream)
+            sink._hold = None
+
     # -- runs once, after the whole backward graph has executed --------------------------
     def finalize(self):
         self._queued = False

@@ -57,7 +57,7 @@ def main():
         first = open(path).readline()
         it = wide(path) if first.startswith('"ID"') else tall(path)
         for name, rd, wr, us in it:
-            if rd is None or wr is None:
+            if rd is None or wr is None or not name:
                 continue
             prev = out.setdefault(regime or "step", {}).get(name)
             if prev is not None and prev["dram_bytes_per_launch"] >= rd + wr:

@@ -54,3 +54,13 @@ def test_no_oracle_or_reference_in_product():
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "/root/reference" not in src, f
+
+
+def test_forked_sink_plumbing_present():
+    """The gradient sinks fork their sort + reduce chains onto side streams and join them in one engine callback;
+    both ends must exist on every sink class (a missing join only shows up on a GPU box)."""
+    from prodsearch_b200 import functional as F_
+    from prodsearch_b200 import peer
+    assert callable(F_.run_forked) and callable(F_.RowGradSink._join_forked)
+    for cls in (F_.RowGradSink, peer.PeerGradSink):
+        assert callable(getattr(cls, "_finalize_callback")) and callable(getattr(cls, "finalize"))
