@@ -381,10 +381,15 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         self.item_table.reserve_stage(2 * B * (L + 2 + K))                       # collective on first use only
         self.word_table.reserve_stage(2 * B * (query_word_idxs.shape[1] + W * (1 + K)))
         self.peer.barrier(0)       # every owner has finished last step's optimizer update / staging reads
-        items, (tgt, neg, hist), item_pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs])
+        # the item rows travel on a side stream while the word rows are fetched and the queries pooled
+        if getattr(self, "_fetch_stream", None) is None:
+            self._fetch_stream = torch.cuda.Stream(device=self.peer.device)
+        items, (tgt, neg, hist), item_pad = self.item_table.fetch([target_prod_idxs, neg_item_idxs, u_item_idxs],
+                                                                  stream=self._fetch_stream)
         words, (qw, pw, nw), word_pad = self.word_table.fetch([query_word_idxs, pos_iword_idxs, neg_word_idxs])
         isink, wsink = self.item_table.sink, self.word_table.sink
         q_emb = self.query_encoder.encode_indices(words, qw, wsink, pad_idx=word_pad)
+        torch.cuda.current_stream(self.peer.device).wait_stream(self._fetch_stream)      # join: items are needed next
         out_pos = -1 if self.args.use_item_pos else 0
         stochastic = self.training and self.args.dropout > 0
         copies = 1 + K if stochastic else 1
@@ -435,8 +440,16 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
     def sync_fold(self):
         G = self.peer.world
         from .peer import fold_tables
+        # the owner-side fold of the two tables and the all-reduce of the replicated gradients are independent:
+        # the all-reduce runs on a side stream (a parallel branch of the captured graph)
+        cur = torch.cuda.current_stream(self.peer.device)
+        if getattr(self, "_reduce_stream", None) is None:
+            self._reduce_stream = torch.cuda.Stream(device=self.peer.device)
+        self._reduce_stream.wait_stream(cur)
+        with torch.cuda.stream(self._reduce_stream):
+            self._bucket.reduce()
         fold_tables([self.item_table, self.word_table], 1.0 / G)
-        self._bucket.reduce()
+        cur.wait_stream(self._reduce_stream)
         # partial |g|^2 of this rank: its two shard gradients; rank 0 adds the (replicated, identical) dense bucket
         lib = _lib.load()
         n = 3 if self.peer.rank == 0 else 2

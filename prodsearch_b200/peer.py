@@ -240,10 +240,12 @@ class PeerShardedTable(object):
                 cap = int(t.item())
             self._ensure_stage(cap)
 
-    def fetch(self, index_tensors):
+    def fetch(self, index_tensors, stream=None):
         """Gather the rows of ``index_tensors`` (global ids) from their owners into a local mini table.
         Returns (mini [n+1, d], remapped index tensors, pad position): positions of pad ids are remapped to
-        the single position n (which holds the pad row), so kernels keep their ``idx != pad_idx`` validity rule."""
+        the single position n (which holds the pad row), so kernels keep their ``idx != pad_idx`` validity rule.
+        stream: run the P2P gather on this side stream (forked from the current one; buffers are allocated on the
+        current stream); the CALLER joins it -- ``current_stream().wait_stream(stream)`` -- before the first use."""
         flats = [t.reshape(-1) for t in index_tensors]
         n = sum(f.numel() for f in flats)
         dev = self.weight.device
@@ -253,9 +255,12 @@ class PeerShardedTable(object):
         ids = torch.cat(flats + [pad_t])
         mini = torch.empty((n + 1, self.d), dtype=torch.float32, device=dev)
         remap = torch.empty((n + 1,), dtype=torch.int64, device=dev)
-        check(load().psb_peer_gather_rows(self.shard.ptr_array(), self.peer.world, self.rows, self.d, ids.data_ptr(),
-                                          n + 1, mini.data_ptr(), remap.data_ptr(), self.pad_idx, n, None, stream_ptr()),
-              "psb_peer_gather_rows")
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+            check(load().psb_peer_gather_rows(self.shard.ptr_array(), self.peer.world, self.rows, self.d,
+                                              ids.data_ptr(), n + 1, mini.data_ptr(), remap.data_ptr(), self.pad_idx, n,
+                                              None, stream_ptr()), "psb_peer_gather_rows")
         # a leaf that requires grad, so the autograd Functions reading it run their backward (which routes the row
         # gradients to the sink; nothing is ever accumulated into mini.grad)
         mini.requires_grad_(self.weight.requires_grad and torch.is_grad_enabled())
