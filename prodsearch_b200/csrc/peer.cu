@@ -152,44 +152,58 @@ __global__ void __launch_bounds__(256) peer_fold_kernel(const FoldArgs a) {
     }
     return;
   }
-  for (int64_t i = w0; i < n; i += nwarps) {
-    const int32_t g = t.rows[r][i];
-    if (g < 0 || g % G != rank) continue;
-    const int64_t local = g / G;
-    if (local >= t.shard_rows) continue;
-    bool leader = true;
-    for (int q = 0; q < r; ++q)
-      if ((t.posmap[q * t.shard_rows + local] >> 32 << 32) == stamp) leader = false;
-    if (!leader) continue;
-    int64_t slot[kMaxPeers];
+  // SUM: a warp takes 32 consecutive entries of peer r's list with ONE coalesced peer load (the first version read
+  // them one per warp iteration: a dependent NVLink round trip per entry), every lane resolves its own entry --
+  // owned here? is r the lowest peer holding the row? at which slot do the later peers hold it? -- from the local
+  // position map, then the warp folds the leader entries one after the other, 128-bit peer loads across the lanes.
+  for (int64_t i0 = w0 * 32; i0 < n; i0 += nwarps * 32) {
+    const int64_t i = i0 + lane;
+    const int32_t g = i < n ? t.rows[r][i] : -1;
+    const int64_t local = g >= 0 ? g / G : 0;
+    bool leader = g >= 0 && g % G == rank && local < t.shard_rows;
+    int32_t slot[kMaxPeers];
 #pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q) {
-      slot[q] = -1;
-      if (q == r) slot[q] = i;
-      if (q > r && q < G) {
-        const unsigned long long e = t.posmap[q * t.shard_rows + local];
-        if ((e >> 32 << 32) == stamp) slot[q] = static_cast<int64_t>(e & 0xffffffffull) - 1;
-      }
-    }
-    for (int c = lane; c < t.d4; c += 32) {
-      float4 acc = zero4();
+    for (int q = 0; q < kMaxPeers; ++q) slot[q] = -1;
+    if (leader) {
 #pragma unroll
       for (int q = 0; q < kMaxPeers; ++q) {
-        if (slot[q] >= 0) {
-          const float4 v = ldg_row4(t.vals[q] + slot[q] * t.d4 + c);
-          acc.x += v.x;
-          acc.y += v.y;
-          acc.z += v.z;
-          acc.w += v.w;
+        if (q < G && q != r) {
+          const unsigned long long e = t.posmap[q * t.shard_rows + local];
+          const bool held = (e >> 32 << 32) == stamp;
+          if (q < r && held) leader = false;
+          if (q > r && held) slot[q] = static_cast<int32_t>(e & 0xffffffffull) - 1;
         }
+        if (q == r) slot[q] = static_cast<int32_t>(i);
       }
-      acc.x *= a.scale;
-      acc.y *= a.scale;
-      acc.z *= a.scale;
-      acc.w *= a.scale;
-      t.dense[local * t.d4 + c] = acc;
     }
-    if (t.touched != nullptr && lane == 0) t.touched[atomicAdd(t.n_touched, 1)] = static_cast<int32_t>(local);
+    unsigned todo = __ballot_sync(kFull, leader);
+    while (todo != 0u) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t row = __shfl_sync(kFull, local, l);
+      int32_t sl[kMaxPeers];
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q) sl[q] = __shfl_sync(kFull, slot[q], l);
+      for (int c = lane; c < t.d4; c += 32) {
+        float4 acc = zero4();
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {
+          if (sl[q] >= 0) {
+            const float4 v = ldg_row4(t.vals[q] + static_cast<int64_t>(sl[q]) * t.d4 + c);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+          }
+        }
+        acc.x *= a.scale;
+        acc.y *= a.scale;
+        acc.z *= a.scale;
+        acc.w *= a.scale;
+        t.dense[row * t.d4 + c] = acc;
+      }
+      if (t.touched != nullptr && lane == 0) t.touched[atomicAdd(t.n_touched, 1)] = static_cast<int32_t>(row);
+    }
   }
 }
 
@@ -379,7 +393,7 @@ extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tab
     peer_fold_kernel<false><<<grid, 256, 0, s>>>(a);
     if ((st = launch_status()) != PSB_OK) return st;
   }
-  dim3 grid(grid_for(cap_max, 8, 2), n_tables, G);
+  dim3 grid(grid_for(cap_max, 8 * 32, 2), n_tables, G);
   PSB_PROF("peer_fold_sum_kernel", s);
   peer_fold_kernel<true><<<grid, 256, 0, s>>>(a);
   return launch_status();
