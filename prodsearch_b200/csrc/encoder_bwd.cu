@@ -34,7 +34,7 @@ struct TailBwdArgs {
 };
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwdArgs a) {
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
   const int d = D.d, F = D.F, H = D.H, T = D.T, C = D.C, dh = D.dh;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
   };
 
   // (0) attention dropout multipliers + P of the tile's sequences
-  for (int e = threadIdx.x; e < R * HT; e += kThreads) {
+  for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
     const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
     int s, grow;
     float v = 0.f;
@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
       v = drop.on() ? drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h) * T + a.tok[a.off[s] + al]) : 1.f;
     M1[e] = v;
   }
-  for (int e = threadIdx.x; e < D.spt * HT; e += kThreads) {
+  for (int e = threadIdx.x; e < D.spt * HT; e += kTailThreads) {
     const int sl = e / HT, rem = e - sl * HT, h = rem / T, al = rem - h * T;
     const int s = s0 + sl;
     Ps[e] = (s < D.S && al < a.nact[s]) ? a.P[static_cast<size_t>(a.off[s] + al) * H + h] : 0.f;
   }
   // (1) LN_out backward, (2) g_h2 = gz * drop4
   float4 pg = zero4(), pb = zero4();
-  for (int r = warp; r < R; r += kWarps) {
+  for (int r = warp; r < R; r += kTailWarps) {
     int s, grow;
     const bool rv = row_seq(r, &s, &grow);
     float4 gz = zero4(), gh2 = zero4();
@@ -109,16 +109,16 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
     *reinterpret_cast<float4*>(red + (warp * 2 + 1) * d + j4) = pb;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * d; e += kThreads) {
+  for (int e = threadIdx.x; e < 2 * d; e += kTailThreads) {
     float sacc = 0.f;
-    for (int w = 0; w < kWarps; ++w) sacc += red[w * 2 * d + e];
+    for (int w = 0; w < kTailWarps; ++w) sacc += red[w * 2 * d + e];
     a.lnp[(static_cast<size_t>(blockIdx.x) * 4) * d + e] = sacc;
   }
   __syncthreads();
   // (3) g_h1 = g_h2 . W2  ->  g_pre = g_h1 * drop3 * gelu'(pre1)
-  tile_gemm<R>(A4, d, a.w2, F, red);
+  tile_gemm<R, kTailWarps>(A4, d, a.w2, F, red);
   __syncthreads();
-  tile_epilogue<R>(red, F, [&](int r, int j, float4 v) {
+  tile_epilogue<R, kTailThreads>(red, F, [&](int r, int j, float4 v) {
     int s, grow;
     float4 g = zero4();
     if (row_seq(r, &s, &grow)) {
@@ -135,14 +135,14 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
   });
   __syncthreads();
   // (4) gn = g_pre . W1
-  tile_gemm<R>(A4, F, a.w1, d, red);
+  tile_gemm<R, kTailWarps>(A4, F, a.w1, d, red);
   __syncthreads();
-  tile_epilogue<R>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
+  tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
   __syncthreads();
   // (5) LN_ff backward + residual -> gy ; g_o1 = gy * drop2
   pg = zero4();
   pb = zero4();
-  for (int r = warp; r < R; r += kWarps) {
+  for (int r = warp; r < R; r += kTailWarps) {
     int s, grow;
     const bool rv = row_seq(r, &s, &grow);
     float4 gy = zero4(), go1 = zero4();
@@ -175,13 +175,13 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
     *reinterpret_cast<float4*>(red + (warp * 2 + 1) * d + j4) = pb;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * d; e += kThreads) {
+  for (int e = threadIdx.x; e < 2 * d; e += kTailThreads) {
     float sacc = 0.f;
-    for (int w = 0; w < kWarps; ++w) sacc += red[w * 2 * d + e];
+    for (int w = 0; w < kTailWarps; ++w) sacc += red[w * 2 * d + e];
     a.lnp[(static_cast<size_t>(blockIdx.x) * 4 + 2) * d + e] = sacc;
   }
   // residual gradient of x[o]: sum of gy over the copies of each sequence (copy order)
-  for (int e = threadIdx.x; e < D.spt * d; e += kThreads) {
+  for (int e = threadIdx.x; e < D.spt * d; e += kTailThreads) {
     const int sl = e / d, j = e - sl * d;
     const int s = s0 + sl;
     if (s < D.S) {
@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
   }
   __syncthreads();
   // (6) g_ctx = g_o1 . Wo
-  tile_gemm<R>(A4, d, a.wo, d, red);
+  tile_gemm<R, kTailWarps>(A4, d, a.wo, d, red);
   __syncthreads();
-  tile_epilogue<R>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
+  tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
   __syncthreads();
   // (7a) gA[r][h][al] = <g_ctx[r, head h], V[al, head h]>
-  for (int e = threadIdx.x; e < R * HT; e += kThreads) {
+  for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
     const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
     int s, grow;
     float acc = 0.f;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
   }
   __syncthreads();
   // (7b) softmax backward per (sequence, head)
-  for (int e = threadIdx.x; e < D.spt * H; e += kThreads) {
+  for (int e = threadIdx.x; e < D.spt * H; e += kTailThreads) {
     const int sl = e / H, h = e - sl * H;
     const int s = s0 + sl;
     if (s >= D.S) continue;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
   __syncthreads();
   // (7c) grad K | V rows of the tile's sequences, grad q
   const int nd4 = d >> 2;
-  for (int e = threadIdx.x; e < D.spt * T * nd4; e += kThreads) {
+  for (int e = threadIdx.x; e < D.spt * T * nd4; e += kTailThreads) {
     const int sl = e / (T * nd4), rem = e - sl * (T * nd4), al = rem / nd4, j = (rem - al * nd4) * 4;
     const int s = s0 + sl;
     if (s >= D.S || al >= a.nact[s]) continue;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_bwd_kernel(const TailBwdArgs
     *reinterpret_cast<float4*>(dst) = gk;
     *reinterpret_cast<float4*>(dst + d) = gv;
   }
-  for (int e = threadIdx.x; e < D.spt * nd4; e += kThreads) {
+  for (int e = threadIdx.x; e < D.spt * nd4; e += kTailThreads) {
     const int sl = e / nd4, j = (e - sl * nd4) * 4;
     const int s = s0 + sl;
     if (s >= D.S) continue;
@@ -291,7 +291,7 @@ static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
     configured = smem;
   }
   PSB_PROF("tail_bwd_kernel", s);
-  tail_bwd_kernel<R><<<D.ntile, kThreads, smem, s>>>(a);
+  tail_bwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);
   return launch_status();
 }
 

@@ -15,6 +15,10 @@ namespace enc {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
+// The per-copy tail kernels run ONE CTA per SM (their tiles fill shared memory); 16 warps instead of 8 double the
+// warps the scheduler can pick from (ncu: IPC 1.3-1.7 at 8 warps, no single hot line -- issue-limited).
+constexpr int kTailThreads = 512;
+constexpr int kTailWarps = 16;
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -79,21 +83,24 @@ __host__ __device__ inline Split split_for(int J) {
 __host__ __device__ inline int red_floats(int R, int J) { return split_for(J).ks * R * (J + 4); }
 __host__ __device__ inline int a4_floats(int R, int I) { return I * R; }
 
-template <int R>
+template <int R, int NW = kWarps>
 __device__ __forceinline__ void tile_gemm(const float4* __restrict__ A4, int I, const float* __restrict__ B, int J,
                                           float* __restrict__ red) {
   static_assert(R % 4 == 0, "tile rows");
+  static_assert(NW % 8 == 0 && R % (NW / 8) == 0, "warps come in groups of 8, each group owns R / groups rows");
+  constexpr int RH = R / (NW / 8);             // rows of this warp group (16 warps: two groups, each re-reads B)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w8 = warp & 7, r0 = (warp >> 3) * RH;
   const Split sp = split_for(J);
-  const int cgi = warp % sp.cg, ksi = warp / sp.cg;
+  const int cgi = w8 % sp.cg, ksi = w8 / sp.cg;
   const int col = cgi * 128 + lane * 4;
   const int n4 = I >> 2;                       // blocks of 4 rows of B
   const int per = (n4 + sp.ks - 1) / sp.ks;
   const int b0 = min(n4, ksi * per), b1 = min(n4, b0 + per);
   if (col >= J) return;
-  float4 acc[R];
+  float4 acc[RH];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = zero4();
+  for (int r = 0; r < RH; ++r) acc[r] = zero4();
   if (b0 < b1) {
     const float* bp = B + static_cast<size_t>(b0) * 4 * J + col;
     float4 b[4], bn[4];
@@ -105,9 +112,9 @@ __device__ __forceinline__ void tile_gemm(const float4* __restrict__ A4, int I, 
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         bn[u] = more ? ldg_row4(reinterpret_cast<const float4*>(bp + static_cast<size_t>(u) * J)) : zero4();
-      const float4* a = A4 + static_cast<size_t>(blk) * R;
+      const float4* a = A4 + static_cast<size_t>(blk) * R + r0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+      for (int r = 0; r < RH; ++r) {
         const float4 av = a[r];
         fma4(acc[r], av.x, b[0]);
         fma4(acc[r], av.y, b[1]);
@@ -118,19 +125,19 @@ __device__ __forceinline__ void tile_gemm(const float4* __restrict__ A4, int I, 
       for (int u = 0; u < 4; ++u) b[u] = bn[u];
     }
   }
-  float* rp = red + static_cast<size_t>(ksi) * R * (J + 4) + col;
+  float* rp = red + (static_cast<size_t>(ksi) * R + r0) * (J + 4) + col;
 #pragma unroll
-  for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(rp + static_cast<size_t>(r) * (J + 4)) = acc[r];
+  for (int r = 0; r < RH; ++r) *reinterpret_cast<float4*>(rp + static_cast<size_t>(r) * (J + 4)) = acc[r];
 }
 
 // Combine the ks slices of `red` and hand each (row, 4 columns) to f(r, j, v).  Lanes run along
 // the rows, so transposed (A4) and padded row-major stores from f are bank-conflict free.
-template <int R, typename F>
+template <int R, int NT = kThreads, typename F>
 __device__ __forceinline__ void tile_epilogue(const float* __restrict__ red, int J, F&& f) {
   const int ks = split_for(J).ks;
   const int nj4 = J >> 2;
   const int JP = J + 4;
-  for (int e = threadIdx.x; e < R * nj4; e += kThreads) {
+  for (int e = threadIdx.x; e < R * nj4; e += NT) {
     const int r = e % R, j = (e / R) * 4;
     float4 v = *reinterpret_cast<const float4*>(red + static_cast<size_t>(r) * JP + j);
     for (int k = 1; k < ks; ++k) {

@@ -340,7 +340,7 @@ __host__ __device__ inline size_t tail_smem_floats(int R, int d, int F, int H, i
 }
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 1) tail_fwd_kernel(const TailFwdArgs a) {
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
   const int d = D.d, F = D.F, H = D.H, T = D.T, C = D.C, dh = D.dh;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   };
 
   // (1) dropped attention weights of every copy row
-  for (int e = threadIdx.x; e < R * HT; e += kThreads) {
+  for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
     const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
     int s, grow;
     float v = 0.f;
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   __syncthreads();
   // (2) context rows
   const int nd4 = d >> 2;
-  for (int e = threadIdx.x; e < R * nd4; e += kThreads) {
+  for (int e = threadIdx.x; e < R * nd4; e += kTailThreads) {
     const int r = e / nd4, j = (e - r * nd4) * 4;
     int s, grow;
     float4 acc = zero4();
@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   }
   __syncthreads();
   // (3) output projection + dropout + residual
-  tile_gemm<R>(A4, d, a.wo_t, d, red);
+  tile_gemm<R, kTailWarps>(A4, d, a.wo_t, d, red);
   __syncthreads();
-  tile_epilogue<R>(red, d, [&](int r, int j, float4 v) {
+  tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) {
     int s, grow;
     if (row_seq(r, &s, &grow)) {
       const float4 b = *reinterpret_cast<const float4*>(a.bo + j);
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   });
   __syncthreads();
   // (4) feed-forward LayerNorm
-  for (int r = warp; r < R; r += kWarps) {
+  for (int r = warp; r < R; r += kTailWarps) {
     const int j = lane * 4;
     const bool act = j < d;
     int s, grow;
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   }
   __syncthreads();
   // (5) W1 + gelu + dropout
-  tile_gemm<R>(A4, d, a.w1_t, F, red);
+  tile_gemm<R, kTailWarps>(A4, d, a.w1_t, F, red);
   __syncthreads();
-  tile_epilogue<R>(red, F, [&](int r, int j, float4 v) {
+  tile_epilogue<R, kTailThreads>(red, F, [&](int r, int j, float4 v) {
     int s, grow;
     float4 h = zero4();
     if (row_seq(r, &s, &grow)) {
@@ -461,9 +461,9 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   });
   __syncthreads();
   // (6) W2 + dropout + residual
-  tile_gemm<R>(A4, F, a.w2_t, d, red);
+  tile_gemm<R, kTailWarps>(A4, F, a.w2_t, d, red);
   __syncthreads();
-  tile_epilogue<R>(red, d, [&](int r, int j, float4 v) {
+  tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) {
     int s, grow;
     if (row_seq(r, &s, &grow)) {
       const float4 b = *reinterpret_cast<const float4*>(a.b2 + j);
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_fwd_kernel(const TailFwdArgs
   });
   __syncthreads();
   // (7) final LayerNorm
-  for (int r = warp; r < R; r += kWarps) {
+  for (int r = warp; r < R; r += kTailWarps) {
     const int j = lane * 4;
     const bool act = j < d;
     int s, grow;
@@ -508,7 +508,7 @@ static int launch_tail_fwd(const TailFwdArgs& a, cudaStream_t s) {
     configured = smem;
   }
   PSB_PROF("tail_fwd_kernel", s);
-  tail_fwd_kernel<R><<<D.ntile, kThreads, smem, s>>>(a);
+  tail_fwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);
   return launch_status();
 }
 
