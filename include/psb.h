@@ -287,6 +287,10 @@ typedef struct psb_encoder_cfg {
   const float* dense;       /* alternative input [S,T,d] (first/table/idx NULL) */
   const uint8_t* mask;      /* [S,T] for the dense input */
   const float* pe;          /* [T,d] positional rows or NULL (use_pos False) */
+  void* first_ready;        /* optional cudaEvent_t (forward only): `first` is being produced on ANOTHER stream and
+                               this event marks its completion; the call enqueues its token plan and weight
+                               transposes (which do not read `first`) and makes `stream` wait for the event only
+                               before the first kernel that does -- the query pooling overlaps with them */
 } psb_encoder_cfg_t;
 
 /* Byte sizes of the caller-owned buffers: `saved` carries forward state to the backward call,

@@ -574,6 +574,10 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   transpose_kernel<<<tr_blocks(jobs), 256, 0, s>>>(jobs);
   if ((st = launch_status()) != PSB_OK) return st;
 
+  if (cfg->first_ready != nullptr) {  // `first` comes from another stream: wait for it only now
+    const cudaError_t we = cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(cfg->first_ready), 0);
+    if (we != cudaSuccess) return static_cast<int>(we);
+  }
   PSB_PROF("embed_kernel", s);
   embed_kernel<<<D.S, 128, 0, s>>>(ts, D, p->ln_attn_g, p->ln_attn_b, nact, off, tok, sv + L.xn, sv + L.xo,
                                    sv + L.xno);

@@ -172,9 +172,10 @@ class MeanPoolFn(Function):
     """Fused gather + masked mean (+dropout, +fs); psb_gather_meanpool_fwd / psb_fs_bwd."""
 
     @staticmethod
-    def forward(ctx, weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale):
+    def forward(ctx, weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale, stream=None):
         out, mean, _ = ops.gather_meanpool(weight, idx, pad_idx=pad_idx, mask=mask, tok_scale=tok_scale,
-                                           keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias)
+                                           keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias,
+                                           stream=stream)
         ctx.sink, ctx.idx, ctx.pad_idx, ctx.mask, ctx.keep = sink, idx, pad_idx, mask, keep_scale
         ctx.fs = fs_weight is not None
         if ctx.fs:
@@ -193,7 +194,7 @@ class MeanPoolFn(Function):
         idx = ctx.idx
         tw = ops.token_weights(idx, pad_idx=ctx.pad_idx, mask=ctx.mask)
         ctx.sink.add(idx.reshape(-1), gm, src_div=idx.shape[1], scale=tw.view(-1))
-        return None, None, gw, gb, None, None, None, None, None
+        return None, None, gw, gb, None, None, None, None, None, None
 
 
 class NSLossFn(Function):
@@ -243,7 +244,8 @@ class SeqEncoderFn(Function):
         out, call = ops.encoder_fwd(params, opts["heads"], first=first, table=table, idx=idx, pad_idx=pad_idx,
                                     dense=dense, mask=mask, pe=pe, copies=opts["copies"], out_pos=opts["out_pos"],
                                     pre_ln=opts["pre_ln"], eps=opts["eps"], p_drop=opts["p_drop"],
-                                    seed=opts["seed"], raw_input=opts.get("raw_input", False))
+                                    seed=opts["seed"], raw_input=opts.get("raw_input", False),
+                                    first_ready=opts.get("first_ready"))
         ctx.call, ctx.sink, ctx.idx, ctx.names = call, sink, idx, names
         ctx.shapes = {n: tuple(w.shape) for n, w in zip(names, weights)}
         ctx.pre_ln = opts["pre_ln"]
@@ -265,8 +267,8 @@ def gather_rows(weight, idx, sink):
 
 
 def meanpool(weight, idx, sink, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
-             fs_bias=None):
-    return MeanPoolFn.apply(weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale)
+             fs_bias=None, stream=None):
+    return MeanPoolFn.apply(weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale, stream)
 
 
 def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, pad_idx=-1, mask=None,

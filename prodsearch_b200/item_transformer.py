@@ -20,6 +20,8 @@ from .transformer import TransformerEncoder
 
 
 class ItemTransformerRanker(nn.Module):
+    overlap_query_pooling = True     # query pooling on a side stream under the encoder's plan / transpose kernels
+
     def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None,
                  grad_mode="dense"):
         super().__init__()
@@ -109,15 +111,25 @@ class ItemTransformerRanker(nn.Module):
         (item_transformer.py:449-484 / :118-140) -> [B*copies, d], copy-minor.  The history rows are
         gathered inside the fused encoder kernels.  ``hist`` = (weight, sink, remapped idx, pad idx) when
         the item table is sharded and the rows live in a fetched mini table."""
+        # the query pooling runs on a side stream; the encoder call enqueues its token plan and weight transposes
+        # (which do not read the pooled queries) and waits for the event only before the kernel that does
+        side = ready = None
+        if self.overlap_query_pooling and self.word_embeddings.weight.is_cuda:
+            if getattr(self, "_q_stream", None) is None:
+                self._q_stream = torch.cuda.Stream(device=self.word_embeddings.weight.device)
+                self._q_ready = torch.cuda.Event()
+            side, ready = self._q_stream, self._q_ready
         q_emb = self.query_encoder.encode_indices(self.word_embeddings.weight, query_word_idxs, self.word_sink,
-                                                  pad_idx=self.word_pad_idx)
+                                                  pad_idx=self.word_pad_idx, stream=side)
+        if ready is not None:
+            ready.record(side)
         if hist is None:
             hist_w = self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight
             hist = (hist_w, self.hist_sink, u_item_idxs, self.prod_pad_idx)
         out_pos = -1 if self.args.use_item_pos else 0
         return self.transformer_encoder.encode_position(
             first=q_emb.contiguous(), table=hist[0], idx=hist[2], sink=hist[1], pad_idx=hist[3],
-            use_pos=self.args.use_pos_emb, out_pos=out_pos, copies=copies)
+            use_pos=self.args.use_pos_emb, out_pos=out_pos, copies=copies, first_ready=ready)
 
     def _resolve_item_rows(self, target_prod_idxs, neg_item_idxs, u_item_idxs):
         """(item weight, item sink, target idx, negative idx, hist triple or None) of this step.

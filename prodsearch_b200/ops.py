@@ -30,9 +30,11 @@ def gather_rows(table, idx, err_flag=None):
 
 
 def gather_meanpool(table, idx, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
-                    fs_bias=None, want_mean=False, want_inv_count=False):
+                    fs_bias=None, want_mean=False, want_inv_count=False, stream=None):
     """Fused gather + masked mean (+dropout multiplier, +fs projection); psb_gather_meanpool_fwd.
-    idx [n, w].  Returns (out [n,d], mean or None, inv_count or None)."""
+    idx [n, w].  Returns (out [n,d], mean or None, inv_count or None).
+    stream: enqueue the kernel on this side stream (forked from the current one; the outputs are allocated on the
+    current stream).  The CALLER orders later readers after it (an event recorded on ``stream``)."""
     idx = _idx(idx)
     n, w = idx.shape
     d = table.shape[1]
@@ -43,11 +45,14 @@ def gather_meanpool(table, idx, pad_idx=-1, mask=None, tok_scale=None, keep_scal
     inv = torch.empty((n,), dtype=f32, device=dev) if want_inv_count else None
     if mask is not None and mask.dtype != u8:
         mask = mask.to(u8)
-    check(load().psb_gather_meanpool_fwd(
-        ptr(table, f32), table.shape[0], d, ptr(idx), n, w, int(pad_idx),
-        ptr(mask.contiguous() if mask is not None else None), ptr(tok_scale, f32), ptr(keep_scale, f32),
-        ptr(fs_weight, f32), ptr(fs_bias, f32), ptr(mean), ptr(out), ptr(inv), stream_ptr()),
-        "psb_gather_meanpool_fwd")
+    mask_c = mask.contiguous() if mask is not None else None
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+        check(load().psb_gather_meanpool_fwd(
+            ptr(table, f32), table.shape[0], d, ptr(idx), n, w, int(pad_idx), ptr(mask_c), ptr(tok_scale, f32),
+            ptr(keep_scale, f32), ptr(fs_weight, f32), ptr(fs_bias, f32), ptr(mean), ptr(out), ptr(inv),
+            stream_ptr()), "psb_gather_meanpool_fwd")
     return out, mean, inv
 
 
@@ -236,11 +241,13 @@ class EncoderCall(object):
 
 
 def encoder_fwd(params, heads, first=None, table=None, idx=None, pad_idx=-1, dense=None, mask=None, pe=None,
-                copies=1, out_pos=0, pre_ln=False, eps=1e-6, p_drop=0.0, seed=None, raw_input=False):
+                copies=1, out_pos=0, pre_ln=False, eps=1e-6, p_drop=0.0, seed=None, raw_input=False,
+                first_ready=None):
     """One TransformerEncoderLayer + final LayerNorm evaluated at ONE output position (include/psb.h N1).
     params: dict name -> fp32 CUDA tensor with the psb_encoder_params_t member names.  Tokens: ``first`` [S,d]
     + ``table`` / ``idx`` [S,T-1] (TEM), or ``dense`` [S,T,d] (+ ``mask`` [S,T] uint8/bool, 1 = real).
-    ``seed``: int64 CUDA tensor [1] (required when p_drop > 0).  Returns (out [S*copies, d], EncoderCall)."""
+    ``seed``: int64 CUDA tensor [1] (required when p_drop > 0).  ``first_ready``: torch.cuda.Event recorded on the
+    side stream that produces ``first`` (psb_encoder_cfg_t.first_ready).  Returns (out [S*copies, d], EncoderCall)."""
     tem = first is not None
     if tem:
         S, d = first.shape
@@ -270,7 +277,7 @@ def encoder_fwd(params, heads, first=None, table=None, idx=None, pad_idx=-1, den
     cfg = _lib.EncoderCfg(S, T, d, int(heads), ff, int(copies), int(out_pos), 1 if pre_ln else 0, 1 if raw_input else 0, float(eps),
                           float(p_drop), ptr(seed, i64), ptr(first, f32), ptr(table, f32),
                           table.shape[0] if table is not None else 0, ptr(idx), int(pad_idx), ptr(dense, f32),
-                          ptr(mask), ptr(pe, f32))
+                          ptr(mask), ptr(pe, f32), first_ready.cuda_event if first_ready is not None else None)
     lib = load()
     sb = int(lib.psb_encoder_saved_bytes(ctypes.byref(cfg)))
     if sb < 0:
@@ -281,6 +288,7 @@ def encoder_fwd(params, heads, first=None, table=None, idx=None, pad_idx=-1, den
     out = torch.empty((S * copies, d), dtype=f32, device=dev)
     check(lib.psb_encoder_fwd(ctypes.byref(cfg), ctypes.byref(P), ptr(saved), sb, ptr(ws), wb, ptr(out),
                               stream_ptr()), "psb_encoder_fwd")
+    cfg.first_ready = None                       # forward-only: the backward call must not see a stale event
     call = EncoderCall()
     call.cfg, call.params, call.saved, call.keep = cfg, P, saved, keep
     call.S, call.T, call.d, call.copies, call.tem = S, T, d, copies, tem

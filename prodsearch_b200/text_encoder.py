@@ -60,9 +60,9 @@ class AVGEncoder(nn.Module):
     def forward(self, inputs, input_mask):
         return self.drop_layer(get_vector_mean(inputs, input_mask))
 
-    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None):
+    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None, stream=None):
         keep = F_._dropout_keep((idx.shape[0], table.shape[1]), self.dropout_, self.training, table.device)
-        return F_.meanpool(table, idx, sink, pad_idx=pad_idx, mask=mask, keep_scale=keep)
+        return F_.meanpool(table, idx, sink, pad_idx=pad_idx, mask=mask, keep_scale=keep, stream=stream)
 
     def initialize_parameters(self, logger=None):
         pass
@@ -85,10 +85,10 @@ class FSEncoder(nn.Module):
         mean = torch.dropout(mean, p=self.dropout_, train=self.training)
         return torch.tanh(self.f_W(mean))
 
-    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None):
+    def encode_indices(self, table, idx, sink, pad_idx=-1, mask=None, stream=None):
         keep = F_._dropout_keep((idx.shape[0], table.shape[1]), self.dropout_, self.training, table.device)
         return F_.meanpool(table, idx, sink, pad_idx=pad_idx, mask=mask, keep_scale=keep,
-                           fs_weight=self.f_W.weight, fs_bias=self.f_W.bias)
+                           fs_weight=self.f_W.weight, fs_bias=self.f_W.bias, stream=stream)
 
     def initialize_parameters(self, logger=None):
         """xavier-normal weight, zero bias (text_encoder.py:42-55)."""

@@ -142,7 +142,7 @@ class TransformerEncoder(nn.Module):
             ("ln_out_g", self.layer_norm.weight), ("ln_out_b", self.layer_norm.bias)])
 
     def encode_position(self, first=None, table=None, idx=None, sink=None, pad_idx=-1, dense=None, mask=None,
-                        use_pos=True, out_pos=0, copies=1):
+                        use_pos=True, out_pos=0, copies=1, first_ready=None):
         """encode(...)[:, out_pos, :] for ``copies`` independent dropout draws of every sequence ->
         [S*copies, d] (copy-minor).  Tokens: ``first`` [S,d] + rows ``table[idx]`` (idx [S,T-1], invalid =
         ``pad_idx``) or ``dense`` [S,T,d] with ``mask`` [S,T].  Layers before the last (inter_layers > 1)
@@ -154,6 +154,9 @@ class TransformerEncoder(nn.Module):
         if nl == 0:
             raise NotImplementedError("inter_layers == 0 (LayerNorm only) is not built")
         if nl > 1:
+            if first_ready is not None:       # the ATen layers below read ``first`` on the current stream
+                torch.cuda.current_stream(first.device).wait_event(first_ready)
+                first_ready = None
             if dense is None:
                 rows = F_.gather_rows(table, idx, sink)
                 dense = torch.cat([first.unsqueeze(1), rows], dim=1)
@@ -180,7 +183,7 @@ class TransformerEncoder(nn.Module):
         dev = first.device if first is not None else dense.device
         seed = self._next_seed(dev) if p_drop > 0 else None
         opts = dict(heads=self.transformer_inter[-1].self_attn.head_count, copies=copies, out_pos=out_pos % T,
-                    pre_ln=False, eps=1e-6, p_drop=p_drop, seed=seed, raw_input=False)
+                    pre_ln=False, eps=1e-6, p_drop=p_drop, seed=seed, raw_input=False, first_ready=first_ready)
         pe = self.pos_emb.pe[0, :T] if use_pos else None
         if dense is not None:
             dense = dense.contiguous()
