@@ -291,6 +291,12 @@ typedef struct psb_encoder_cfg {
                                this event marks its completion; the call enqueues its token plan and weight
                                transposes (which do not read `first`) and makes `stream` wait for the event only
                                before the first kernel that does -- the query pooling overlaps with them */
+  void* wgrad_done;         /* optional cudaEvent_t (backward only): the WEIGHT gradients (split-M partial products +
+                               their fixed-order reduce: nothing on the data-gradient path needs them) are computed on
+                               a library-owned side stream, forked after the tail kernel, and this event is recorded
+                               behind them.  grad_first / grad_rest / grad_dense are complete in `stream` order as
+                               usual; the CALLER makes every consumer of `grads` (and the release of `workspace`) wait
+                               for the event.  NULL: everything runs on `stream`. */
 } psb_encoder_cfg_t;
 
 /* Byte sizes of the caller-owned buffers: `saved` carries forward state to the backward call,

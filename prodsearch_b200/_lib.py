@@ -40,7 +40,7 @@ class EncoderCfg(ctypes.Structure):
     _fields_ = [("S", c_i64), ("T", c_i64), ("d", c_i64), ("heads", c_i64), ("ff", c_i64), ("copies", c_i64),
                 ("out_pos", c_i64), ("pre_ln", c_i32), ("raw_input", c_i32), ("ln_eps", c_f32), ("p_drop", c_f32),
                 ("seed_dev", c_vp), ("first", c_vp), ("table", c_vp), ("table_rows", c_i64), ("idx", c_vp),
-                ("pad_idx", c_i64), ("dense", c_vp), ("mask", c_vp), ("pe", c_vp), ("first_ready", c_vp)]
+                ("pad_idx", c_i64), ("dense", c_vp), ("mask", c_vp), ("pe", c_vp), ("first_ready", c_vp), ("wgrad_done", c_vp)]
 
 
 class AdamTensor(ctypes.Structure):

@@ -586,22 +586,37 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
   if (st != PSB_OK) return st;
 
-  st = launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr, ws + W.gxn, d, s);
-  if (st != PSB_OK) return st;
-  st = launch_rows_gemm(ws + W.g_qlin, d, nullptr, D.S, D.S, d, p->wq, d, nullptr, ws + W.gxno, d, s);
-  if (st != PSB_OK) return st;
+  // The weight gradients depend on the tail kernel's outputs only (and, with pre_ln, on embed_bwd's LayerNorm
+  // partials): with cfg->wgrad_done they run on the library's side stream next to the data-gradient chain below.
+  const bool fork_wgrad = cfg->wgrad_done != nullptr && !D.pre_ln;
+  cudaStream_t sw = s;
+  if (fork_wgrad) {
+    cudaEvent_t fork_ev = nullptr;
+    if ((st = side_stream(&sw, &fork_ev)) != PSB_OK) return st;
+    ce = cudaEventRecord(fork_ev, s);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sw, fork_ev, 0);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+  }
+  auto data_grads = [&]() -> int {
+    st = launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr, ws + W.gxn, d, s);
+    if (st != PSB_OK) return st;
+    st = launch_rows_gemm(ws + W.g_qlin, d, nullptr, D.S, D.S, d, p->wq, d, nullptr, ws + W.gxno, d, s);
+    if (st != PSB_OK) return st;
 
-  EmbedBwdArgs eb;
-  eb.D = D;
-  eb.ts = ts;
-  eb.nact = nact; eb.off = off; eb.tok = tok;
-  eb.gxn = ws + W.gxn; eb.gxno = ws + W.gxno; eb.gxo = ws + W.gxo;
-  eb.ln_g = p->ln_attn_g;
-  eb.g_first = grad_first; eb.g_rest = grad_rest; eb.g_dense = grad_dense;
-  eb.lnp = ws + W.lnp_e;
-  PSB_PROF("embed_bwd_kernel", s);
-  embed_bwd_kernel<<<D.S, 128, 0, s>>>(eb);
-  if ((st = launch_status()) != PSB_OK) return st;
+    EmbedBwdArgs eb;
+    eb.D = D;
+    eb.ts = ts;
+    eb.nact = nact; eb.off = off; eb.tok = tok;
+    eb.gxn = ws + W.gxn; eb.gxno = ws + W.gxno; eb.gxo = ws + W.gxo;
+    eb.ln_g = p->ln_attn_g;
+    eb.g_first = grad_first; eb.g_rest = grad_rest; eb.g_dense = grad_dense;
+    eb.lnp = ws + W.lnp_e;
+    PSB_PROF("embed_bwd_kernel", s);
+    embed_bwd_kernel<<<D.S, 128, 0, s>>>(eb);
+    if ((st = launch_status()) != PSB_OK) return st;
+    return PSB_OK;
+  };
+  if (!fork_wgrad && (st = data_grads()) != PSB_OK) return st;   // pre_ln: the reduce below reads embed_bwd's partials
 
   // weight gradients
   WgProbs probs;
@@ -622,8 +637,8 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(3, ws + W.gkv, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWk, dbk
   add(4, ws + W.gkv + d, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWv, dbv
   add(5, ws + W.g_qlin, d, sv + L.xno, d, nullptr, D.S, D.S, d, d);        // dWq, dbq
-  PSB_PROF("wgrad_kernel", s);
-  wgrad_kernel<<<total_tiles, 256, 0, s>>>(probs);
+  PSB_PROF("wgrad_kernel", sw);
+  wgrad_kernel<<<total_tiles, 256, 0, sw>>>(probs);
   if ((st = launch_status()) != PSB_OK) return st;
 
   RedJobs jobs;
@@ -650,9 +665,17 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     red(ws + W.lnp_e + d, gr->ln_attn_b, d, 2 * d, nullptr, D.S, 1);
   }
   if (total_blocks > 0) {
-    PSB_PROF("reduce_kernel", s);
-    reduce_kernel<<<total_blocks, 256, 0, s>>>(jobs);
+    PSB_PROF("reduce_kernel", sw);
+    reduce_kernel<<<total_blocks, 256, 0, sw>>>(jobs);
     if ((st = launch_status()) != PSB_OK) return st;
+  }
+  if (fork_wgrad) {
+    ce = cudaEventRecord(static_cast<cudaEvent_t>(cfg->wgrad_done), sw);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+    if ((st = data_grads()) != PSB_OK) return st;
+  } else if (cfg->wgrad_done != nullptr) {
+    ce = cudaEventRecord(static_cast<cudaEvent_t>(cfg->wgrad_done), s);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
   }
   return PSB_OK;
 }

@@ -40,6 +40,10 @@ inline int launch_status() {
   return e == cudaSuccess ? PSB_OK : static_cast<int>(e);
 }
 
+// Library-owned side stream (+ fork event) of the current device, created on first use (runtime.cu): lets one ABI
+// call run an independent tail of its work next to the caller's stream; capturable (fork = event record / wait).
+int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event);
+
 inline int grid_for(int64_t work_items, int items_per_block, int max_waves = 16) {
   int64_t need = (work_items + items_per_block - 1) / items_per_block;
   int64_t cap = static_cast<int64_t>(kNumSMs) * max_waves;

@@ -47,6 +47,24 @@ void recycle() {
 }
 }  // namespace
 
+int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event) {
+  constexpr int kMaxDev = 64;
+  static cudaStream_t streams[kMaxDev] = {};
+  static cudaEvent_t events[kMaxDev] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= kMaxDev) return PSB_E_UNSUPPORTED;
+  if (streams[dev] == nullptr) {
+    e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&events[dev], cudaEventDisableTiming);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  *stream = streams[dev];
+  *fork_event = events[dev];
+  return PSB_OK;
+}
+
 void prof_begin(const char* name, cudaStream_t s) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;  // not in graphs

@@ -249,17 +249,40 @@ class SeqEncoderFn(Function):
         ctx.call, ctx.sink, ctx.idx, ctx.names = call, sink, idx, names
         ctx.shapes = {n: tuple(w.shape) for n, w in zip(names, weights)}
         ctx.pre_ln = opts["pre_ln"]
+        ctx.weights = weights
         return out
+
+    # The weight gradients (split-M partial products + their reduce, ~55 us at batch 384) are needed by nobody
+    # before the optimizer, so the library computes them on its side stream next to the rest of the backward pass
+    # (data gradients of the encoder, query-encoder backward, the tables' gradient sinks) and records an event; one
+    # engine callback at the end of backward() makes the calling stream wait for it.  Only when the weights have no
+    # gradient yet: AccumulateGrad then merely adopts the new tensors -- an in-place accumulation would read them
+    # on the calling stream too early.
+    overlap_wgrad = True
+    _events = {}
 
     @staticmethod
     def backward(ctx, g):
         shapes = ctx.shapes if ctx.pre_ln else {n: s for n, s in ctx.shapes.items() if not n.startswith("ln_attn")}
-        g_first, g_rest, g_dense, grads = ops.encoder_bwd(ctx.call, g, shapes)
+        ev = None
+        if SeqEncoderFn.overlap_wgrad and not ctx.pre_ln and all(w.grad is None for w in ctx.weights):
+            dev = g.device
+            ev = SeqEncoderFn._events.get(dev)
+            if ev is None:
+                ev = SeqEncoderFn._events[dev] = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))      # creates the underlying cudaEvent_t
+        g_first, g_rest, g_dense, grads, ws = ops.encoder_bwd(ctx.call, g, shapes, wgrad_event=ev)
+        if ev is not None:
+            def join(ev=ev, ws=ws, dev=g.device):
+                torch.cuda.current_stream(dev).wait_event(ev)
+                del ws                                          # the side stream is done with the workspace
+            Variable._execution_engine.queue_callback(join)
         if ctx.call.tem and ctx.sink is not None and ctx.call.T > 1:
             ctx.sink.add(ctx.idx.reshape(-1), g_rest.view(-1, g_rest.shape[-1]))
         ctx.call = None
+        ctx.weights = None
         return (g_first, g_dense, None, None, None, None, None, None, None, None) + tuple(
-            grads.get(n) for n in ctx.names)
+            grads.pop(n, None) for n in ctx.names)
 
 
 def gather_rows(weight, idx, sink):

@@ -296,9 +296,12 @@ def encoder_fwd(params, heads, first=None, table=None, idx=None, pad_idx=-1, den
     return out, call
 
 
-def encoder_bwd(call, grad_out, shapes):
+def encoder_bwd(call, grad_out, shapes, wgrad_event=None):
     """Backward of encoder_fwd.  ``shapes``: dict name -> shape of every parameter to differentiate.
-    Returns (grad_first, grad_rest, grad_dense, grads dict)."""
+    Returns (grad_first, grad_rest, grad_dense, grads dict, workspace).  ``wgrad_event`` (torch.cuda.Event that has
+    been recorded at least once): the weight gradients are produced on the library's side stream and the event is
+    recorded behind them -- the caller must make every reader of ``grads`` wait for it and keep ``workspace`` alive
+    until then (psb_encoder_cfg_t.wgrad_done)."""
     S, T, d = call.S, call.T, call.d
     dev = grad_out.device
     g_first = g_rest = g_dense = None
@@ -317,10 +320,12 @@ def encoder_bwd(call, grad_out, shapes):
     lib = load()
     wb = int(lib.psb_encoder_workspace_bytes(ctypes.byref(call.cfg), 1))
     ws = torch.empty((wb,), dtype=u8, device=dev)
+    call.cfg.wgrad_done = wgrad_event.cuda_event if wgrad_event is not None else None
     check(lib.psb_encoder_bwd(ctypes.byref(call.cfg), ctypes.byref(call.params), ptr(call.saved),
                               call.saved.numel(), ptr(ws), wb, ptr(grad_out.contiguous(), f32), ptr(g_first),
                               ptr(g_rest), ptr(g_dense), ctypes.byref(G), stream_ptr()), "psb_encoder_bwd")
-    return g_first, g_rest, g_dense, grads
+    call.cfg.wgrad_done = None
+    return g_first, g_rest, g_dense, grads, ws
 
 
 # ---- optional per-op device timing (bench.py roofline leg) ----------------------------------

@@ -114,7 +114,7 @@ def run_case(S, T, d, ff, heads, copies, out_pos, p_drop=0.0, tem=True, pre_ln=F
         out, call = ops.encoder_fwd(dev, heads, dense=x.cuda(), mask=valid.cuda(), **kw)
     close(out, ref, 1e-5, 2e-6, "out")
     shapes = {k: tuple(v.shape) for k, v in P.items() if pre_ln or not k.startswith("ln_attn")}
-    g_first, g_rest, g_dense, grads = ops.encoder_bwd(call, gout.cuda(), shapes)
+    g_first, g_rest, g_dense, grads, _ = ops.encoder_bwd(call, gout.cuda(), shapes)
     gx = xin.grad
     scale = float(gout.abs().sum() / d)
     if tem:
@@ -134,9 +134,25 @@ def run_case(S, T, d, ff, heads, copies, out_pos, p_drop=0.0, tem=True, pre_ln=F
     else:
         out2, call2 = ops.encoder_fwd(dev, heads, dense=x.cuda(), mask=valid.cuda(), **kw)
     assert torch.equal(out, out2)
-    _, _, _, grads2 = ops.encoder_bwd(call2, gout.cuda(), shapes)
+    _, _, _, grads2, _ = ops.encoder_bwd(call2, gout.cuda(), shapes)
     for k in shapes:
         assert torch.equal(grads[k], grads2[k]), k
+    # weight gradients on the library's side stream (psb_encoder_cfg_t.wgrad_done): same bits after the event
+    if tem:
+        out3, call3 = ops.encoder_fwd(dev, heads, first=first.cuda(), table=table.cuda(), idx=idx.cuda(), pad_idx=rows, **kw)
+    else:
+        out3, call3 = ops.encoder_fwd(dev, heads, dense=x.cuda(), mask=valid.cuda(), **kw)
+    ev = torch.cuda.Event()
+    ev.record()
+    gf3, gr3, gd3, grads3, ws3 = ops.encoder_bwd(call3, gout.cuda(), shapes, wgrad_event=ev)
+    if tem:
+        assert torch.equal(gf3, g_first) and torch.equal(gr3, g_rest)       # data gradients: current-stream order
+    else:
+        assert torch.equal(gd3, g_dense)
+    torch.cuda.current_stream().wait_event(ev)
+    for k in shapes:
+        assert torch.equal(grads[k], grads3[k]), k
+    del ws3
 
 
 @pytest.mark.parametrize("S,T,d,ff,heads,copies", [
