@@ -256,27 +256,46 @@ class SeqEncoderFn(Function):
     # before the optimizer, so the library computes them on its side stream next to the rest of the backward pass
     # (data gradients of the encoder, query-encoder backward, the tables' gradient sinks) and records an event; one
     # engine callback at the end of backward() makes the calling stream wait for it.  Only when the weights have no
-    # gradient yet: AccumulateGrad then merely adopts the new tensors -- an in-place accumulation would read them
-    # on the calling stream too early.
+    # gradient yet and no earlier node of the same pass has gradients of the same weights in flight: AccumulateGrad
+    # then merely adopts the new tensors -- an in-place accumulation would touch them on the calling stream too
+    # early, so in that case whatever is in flight is joined first and this node runs on the calling stream.
     overlap_wgrad = True
     _events = {}
+    _pending = {}          # device -> [event, [workspaces kept alive], {id(weight) in flight}]
+
+    @staticmethod
+    def _join(dev):
+        p = SeqEncoderFn._pending.pop(dev, None)
+        if p is not None:
+            torch.cuda.current_stream(dev).wait_event(p[0])
+            p[1].clear()                                        # the side stream is done with the workspaces
 
     @staticmethod
     def backward(ctx, g):
         shapes = ctx.shapes if ctx.pre_ln else {n: s for n, s in ctx.shapes.items() if not n.startswith("ln_attn")}
+        dev = g.device
+        pend = SeqEncoderFn._pending.get(dev)
+        ids = set(id(w) for w in ctx.weights)
+        clash = pend is not None and not ids.isdisjoint(pend[2])
+        fork = (SeqEncoderFn.overlap_wgrad and not ctx.pre_ln and not clash and
+                all(w.grad is None for w in ctx.weights))
+        if clash or (pend is not None and not fork):
+            SeqEncoderFn._join(dev)
+            pend = None
         ev = None
-        if SeqEncoderFn.overlap_wgrad and not ctx.pre_ln and all(w.grad is None for w in ctx.weights):
-            dev = g.device
+        if fork:
             ev = SeqEncoderFn._events.get(dev)
             if ev is None:
                 ev = SeqEncoderFn._events[dev] = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))      # creates the underlying cudaEvent_t
         g_first, g_rest, g_dense, grads, ws = ops.encoder_bwd(ctx.call, g, shapes, wgrad_event=ev)
         if ev is not None:
-            def join(ev=ev, ws=ws, dev=g.device):
-                torch.cuda.current_stream(dev).wait_event(ev)
-                del ws                                          # the side stream is done with the workspace
-            Variable._execution_engine.queue_callback(join)
+            if pend is None:
+                SeqEncoderFn._pending[dev] = [ev, [ws], ids]
+                Variable._execution_engine.queue_callback(lambda dev=dev: SeqEncoderFn._join(dev))
+            else:                    # same side stream, same event re-recorded behind the earlier work
+                pend[1].append(ws)
+                pend[2].update(ids)
         if ctx.call.tem and ctx.sink is not None and ctx.call.T > 1:
             ctx.sink.add(ctx.idx.reshape(-1), g_rest.view(-1, g_rest.shape[-1]))
         ctx.call = None
