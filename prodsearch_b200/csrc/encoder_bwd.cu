@@ -598,9 +598,15 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     if (ce != cudaSuccess) return static_cast<int>(ce);
   }
   auto data_grads = [&]() -> int {
-    st = launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr, ws + W.gxn, d, s);
-    if (st != PSB_OK) return st;
-    st = launch_rows_gemm(ws + W.g_qlin, d, nullptr, D.S, D.S, d, p->wq, d, nullptr, ws + W.gxno, d, s);
+    st = fork_join(
+        s, 1,
+        [&](cudaStream_t s2) {
+          return launch_rows_gemm(ws + W.g_qlin, d, nullptr, D.S, D.S, d, p->wq, d, nullptr, ws + W.gxno, d, s2);
+        },
+        [&]() {
+          return launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr,
+                                  ws + W.gxn, d, s);
+        });
     if (st != PSB_OK) return st;
 
     EmbedBwdArgs eb;

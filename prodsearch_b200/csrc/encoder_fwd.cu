@@ -584,9 +584,16 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   if ((st = launch_status()) != PSB_OK) return st;
 
   // [K | V] rows of the active tokens, q of the output position
-  st = launch_rows_gemm(sv + L.xn, d, off + D.S, 0, D.S * D.T, d, ws + W.wkv_t, 2 * d, ws + W.bkv, sv + L.kv, 2 * d, s);
-  if (st != PSB_OK) return st;
-  st = launch_rows_gemm(sv + L.xno, d, nullptr, D.S, D.S, d, ws + W.wq_t, d, p->bq, sv + L.qv, d, s);
+  // (independent products: the small q projection runs on the library's side stream next to the K|V one)
+  st = fork_join(
+      s, 1,
+      [&](cudaStream_t s2) {
+        return launch_rows_gemm(sv + L.xno, d, nullptr, D.S, D.S, d, ws + W.wq_t, d, p->bq, sv + L.qv, d, s2);
+      },
+      [&]() {
+        return launch_rows_gemm(sv + L.xn, d, off + D.S, 0, D.S * D.T, d, ws + W.wkv_t, 2 * d, ws + W.bkv, sv + L.kv,
+                                2 * d, s);
+      });
   if (st != PSB_OK) return st;
 
   PSB_PROF("attn_fwd_kernel", s);

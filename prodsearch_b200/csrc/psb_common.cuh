@@ -42,7 +42,24 @@ inline int launch_status() {
 
 // Library-owned side stream (+ fork event) of the current device, created on first use (runtime.cu): lets one ABI
 // call run an independent tail of its work next to the caller's stream; capturable (fork = event record / wait).
-int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event);
+int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event, int slot = 0, cudaEvent_t* join_event = nullptr);
+
+// Run `side_work(side stream)` next to `main_work()` on s: fork by event, join by event (both capturable).
+template <typename FSide, typename FMain>
+inline int fork_join(cudaStream_t s, int slot, FSide&& side_work, FMain&& main_work) {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int st = side_stream(&s2, &fork_ev, slot, &join_ev);
+  if (st != PSB_OK) return st;
+  cudaError_t e = cudaEventRecord(fork_ev, s);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, fork_ev, 0);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if ((st = side_work(s2)) != PSB_OK) return st;
+  if ((e = cudaEventRecord(join_ev, s2)) != cudaSuccess) return static_cast<int>(e);
+  if ((st = main_work()) != PSB_OK) return st;
+  if ((e = cudaStreamWaitEvent(s, join_ev, 0)) != cudaSuccess) return static_cast<int>(e);
+  return PSB_OK;
+}
 
 inline int grid_for(int64_t work_items, int items_per_block, int max_waves = 16) {
   int64_t need = (work_items + items_per_block - 1) / items_per_block;

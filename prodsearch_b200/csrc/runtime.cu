@@ -47,21 +47,24 @@ void recycle() {
 }
 }  // namespace
 
-int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event) {
-  constexpr int kMaxDev = 64;
-  static cudaStream_t streams[kMaxDev] = {};
-  static cudaEvent_t events[kMaxDev] = {};
+int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event, int slot, cudaEvent_t* join_event) {
+  constexpr int kMaxDev = 64, kSlots = 2;
+  static cudaStream_t streams[kMaxDev][kSlots] = {};
+  static cudaEvent_t forks[kMaxDev][kSlots] = {};
+  static cudaEvent_t joins[kMaxDev][kSlots] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (dev < 0 || dev >= kMaxDev) return PSB_E_UNSUPPORTED;
-  if (streams[dev] == nullptr) {
-    e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&events[dev], cudaEventDisableTiming);
+  if (dev < 0 || dev >= kMaxDev || slot < 0 || slot >= kSlots) return PSB_E_UNSUPPORTED;
+  if (streams[dev][slot] == nullptr) {
+    e = cudaStreamCreateWithFlags(&streams[dev][slot], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&forks[dev][slot], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&joins[dev][slot], cudaEventDisableTiming);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  *stream = streams[dev];
-  *fork_event = events[dev];
+  *stream = streams[dev][slot];
+  *fork_event = forks[dev][slot];
+  if (join_event != nullptr) *join_event = joins[dev][slot];
   return PSB_OK;
 }
 

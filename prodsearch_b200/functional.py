@@ -157,15 +157,15 @@ class GatherRowsFn(Function):
     """aten::embedding with the backward routed to the table's RowGradSink."""
 
     @staticmethod
-    def forward(ctx, weight, idx, sink):
+    def forward(ctx, weight, idx, sink, stream=None):
         ctx.sink, ctx.idx = sink, idx
-        return ops.gather_rows(weight, idx)
+        return ops.gather_rows(weight, idx, stream=stream)
 
     @staticmethod
     def backward(ctx, g):
         d = g.shape[-1]
         ctx.sink.add(ctx.idx.reshape(-1), g.contiguous().view(-1, d))
-        return None, None, None
+        return None, None, None, None
 
 
 class MeanPoolFn(Function):
@@ -202,10 +202,10 @@ class NSLossFn(Function):
 
     @staticmethod
     def forward(ctx, anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
-                pos_weight):
+                pos_weight, stream=None):
         loss, cp, cn, ga, gb = ops.ns_loss(anchor_a, weight, pos_idx, neg_idx, anchor_b=anchor_b, bias=bias,
                                            mask=mask, pad_idx=pad_idx, neg_weight=neg_weight,
-                                           pos_weight=pos_weight)
+                                           pos_weight=pos_weight, stream=stream)
         ctx.sink, ctx.pos_idx, ctx.neg_idx = sink, pos_idx, neg_idx
         ctx.has_b, ctx.has_bias = anchor_b is not None, bias is not None
         ctx.save_for_backward(anchor_a, anchor_b, cp, cn, ga, gb)
@@ -230,7 +230,7 @@ class NSLossFn(Function):
         grad_b = None
         if ctx.has_b and ctx.needs_input_grad[1]:
             grad_b = gb * g.repeat_interleave(k).unsqueeze(1)
-        return grad_a, grad_b, None, None, None, None, None, None, None, None, None
+        return grad_a, grad_b, None, None, None, None, None, None, None, None, None, None
 
 
 class SeqEncoderFn(Function):
@@ -304,8 +304,8 @@ class SeqEncoderFn(Function):
             grads.pop(n, None) for n in ctx.names)
 
 
-def gather_rows(weight, idx, sink):
-    return GatherRowsFn.apply(weight, idx, sink)
+def gather_rows(weight, idx, sink, stream=None):
+    return GatherRowsFn.apply(weight, idx, sink, stream)
 
 
 def meanpool(weight, idx, sink, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
@@ -314,9 +314,11 @@ def meanpool(weight, idx, sink, pad_idx=-1, mask=None, tok_scale=None, keep_scal
 
 
 def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, pad_idx=-1, mask=None,
-            neg_weight=None, pos_weight=1.0):
+            neg_weight=None, pos_weight=1.0, stream=None):
+    """stream: enqueue the forward kernel on a side stream the caller has forked and will join (the autograd node
+    -- and therefore its backward -- still belongs to the current stream)."""
     return NSLossFn.apply(anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
-                          pos_weight)
+                          pos_weight, stream)
 
 
 def seq_encoder(params, opts, first=None, table=None, idx=None, sink=None, pad_idx=-1, dense=None, mask=None,

@@ -21,6 +21,7 @@ from .transformer import TransformerEncoder
 
 class ItemTransformerRanker(nn.Module):
     overlap_query_pooling = True     # query pooling on a side stream under the encoder's plan / transpose kernels
+    overlap_item_to_words = True     # item -> word loss kernels on a side stream next to the encoder
 
     def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None,
                  grad_mode="dense"):
@@ -144,8 +145,10 @@ class ItemTransformerRanker(nn.Module):
         if self.injected_negatives is not None:
             neg_items, neg_words = self.injected_negatives
             return neg_items.view(B, K), neg_words.view(B, W, K)
+        # items first, then words: the reference's call order (item_transformer.py:447, :268)
         neg_items = torch.multinomial(self.prod_dists, B * K, replacement=True).view(B, K)
-        return neg_items, None
+        neg_words = torch.multinomial(self.word_dists, B * W * K, replacement=True).view(B, W, K)
+        return neg_items, neg_words
 
     def forward_dotproduct(self, batch_data, train_pv=False):
         query_word_idxs = batch_data.query_word_idxs
@@ -158,6 +161,17 @@ class ItemTransformerRanker(nn.Module):
         neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
         item_w, item_sink, tgt_idx, neg_idx, hist = self._resolve_item_rows(target_prod_idxs, neg_item_idxs,
                                                                             u_item_idxs)
+        # the item -> word objective shares nothing with the encoder: its two kernels run on a side stream (a
+        # parallel branch of the captured graph) and are joined before the losses are combined
+        cur = torch.cuda.current_stream(item_w.device) if item_w.is_cuda else None
+        side = None
+        if cur is not None and self.overlap_item_to_words:
+            if getattr(self, "_iw_stream", None) is None:
+                self._iw_stream = torch.cuda.Stream(device=item_w.device)
+            side = self._iw_stream
+            side.wait_stream(cur)
+        item_loss_rows = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink, stream=side,
+                                            reduce=False)
         stochastic = self.training and self.args.dropout > 0
         if stochastic:
             # dropout makes the positive and the K negative encodes differ (transformer.py:56, neural.py:226):
@@ -174,7 +188,9 @@ class ItemTransformerRanker(nn.Module):
         ps = F_.ns_loss(pos_out.contiguous(), item_w, tgt_idx.view(B, 1), neg_idx.view(B, 1, K), item_sink,
                         anchor_b=neg_out.contiguous(), bias=bias, pos_weight=pos_weight)
         ps_loss = ps.mean()
-        item_loss = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink)
+        if side is not None:
+            cur.wait_stream(side)
+        item_loss = item_loss_rows.mean()
         with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here); in place,
             if self._ps_acc is None:   # so a CUDA-graph replay keeps accumulating into the same buffers
                 self._ps_acc = torch.zeros((), device=ps_loss.device)
@@ -184,18 +200,19 @@ class ItemTransformerRanker(nn.Module):
         return ps_loss + item_loss
 
     def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None, item_w=None,
-                      item_sink=None):
-        """item_transformer.py:260-283."""
+                      item_sink=None, stream=None, reduce=True):
+        """item_transformer.py:260-283.  stream / reduce=False: forward kernels on a side stream the caller forked
+        and joins before reading the per-item losses that are then returned un-averaged."""
         B, W = target_word_idxs.shape
         if neg_sample_idxs is None:
             neg_sample_idxs = torch.multinomial(self.word_dists, B * W * n_negs, replacement=True)
         if item_w is None:
             item_w, item_sink = self.product_emb.weight, self.item_sink
-        anchor = F_.gather_rows(item_w, target_prod_idxs, item_sink)
+        anchor = F_.gather_rows(item_w, target_prod_idxs, item_sink, stream=stream)
         loss = F_.ns_loss(anchor, self.word_embeddings.weight, target_word_idxs,
                           neg_sample_idxs.view(B, W, n_negs), self.word_sink, bias=self.word_bias,
-                          pad_idx=self.word_pad_idx)
-        return loss.mean()
+                          pad_idx=self.word_pad_idx, stream=stream)
+        return loss.mean() if reduce else loss
 
     # ---- evaluation ---------------------------------------------------------------------
     def test(self, batch_data):

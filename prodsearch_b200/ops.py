@@ -19,13 +19,21 @@ def _idx(t):
     return t.contiguous()
 
 
-def gather_rows(table, idx, err_flag=None):
+def _on(stream, dev):
+    """Context that enqueues on ``stream`` (a side stream the CALLER forked from and will join into the current
+    one) or, when None, on the current stream.  Output buffers are always allocated before entering it, i.e. on
+    the current stream, so the caching allocator's stream bookkeeping stays valid."""
+    return torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev))
+
+
+def gather_rows(table, idx, err_flag=None, stream=None):
     """out[..., :] = table[idx[...], :]   (psb_gather_rows; aten::embedding forward)."""
     idx = _idx(idx)
     n, d = idx.numel(), table.shape[1]
     out = torch.empty(idx.shape + (d,), dtype=f32, device=table.device)
-    check(load().psb_gather_rows(ptr(table, f32), table.shape[0], d, ptr(idx), n, ptr(out), ptr(err_flag),
-                                 stream_ptr()), "psb_gather_rows")
+    with _on(stream, table.device):
+        check(load().psb_gather_rows(ptr(table, f32), table.shape[0], d, ptr(idx), n, ptr(out), ptr(err_flag),
+                                     stream_ptr()), "psb_gather_rows")
     return out
 
 
@@ -81,7 +89,7 @@ def token_weights(idx, pad_idx=-1, mask=None):
 
 
 def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=None, pad_idx=-1,
-            neg_weight=None, pos_weight=1.0):
+            neg_weight=None, pos_weight=1.0, stream=None):
     """Fused negative-sampling loss forward + analytic score gradient (psb_ns_loss_fwd).
     pos_idx [n,w], neg_idx [n,w,k].  Returns loss [n], coef_pos [n,w], coef_neg [n,w,k],
     grad_anchor_a [n,d], grad_anchor_b [n*k,d] or None."""
@@ -98,11 +106,12 @@ def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=No
     gb = torch.empty((n * k, d), dtype=f32, device=dev) if anchor_b is not None else None
     if mask is not None and mask.dtype != u8:
         mask = mask.to(u8)
-    check(load().psb_ns_loss_fwd(
-        ptr(anchor_a, f32), ptr(anchor_b, f32), ptr(table, f32), table.shape[0], d, ptr(bias, f32), ptr(pos_idx),
-        ptr(neg_idx), ptr(mask.contiguous() if mask is not None else None), int(pad_idx), ptr(neg_weight, f32),
-        float(pos_weight), n, w, k, ptr(loss), ptr(cp), ptr(cn), ptr(ga), ptr(gb), stream_ptr()),
-        "psb_ns_loss_fwd")
+    mask_c = mask.contiguous() if mask is not None else None
+    with _on(stream, dev):
+        check(load().psb_ns_loss_fwd(
+            ptr(anchor_a, f32), ptr(anchor_b, f32), ptr(table, f32), table.shape[0], d, ptr(bias, f32), ptr(pos_idx),
+            ptr(neg_idx), ptr(mask_c), int(pad_idx), ptr(neg_weight, f32), float(pos_weight), n, w, k, ptr(loss),
+            ptr(cp), ptr(cn), ptr(ga), ptr(gb), stream_ptr()), "psb_ns_loss_fwd")
     return loss, cp, cn, ga, gb
 
 
