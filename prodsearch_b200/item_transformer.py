@@ -417,14 +417,31 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
                                                                   stream=self._fetch_stream)
         words, (qw, pw, nw), word_pad = self.word_table.fetch([query_word_idxs, pos_iword_idxs, neg_word_idxs])
         isink, wsink = self.item_table.sink, self.word_table.sink
-        q_emb = self.query_encoder.encode_indices(words, qw, wsink, pad_idx=word_pad)
-        torch.cuda.current_stream(self.peer.device).wait_stream(self._fetch_stream)      # join: items are needed next
+        cur = torch.cuda.current_stream(self.peer.device)
+        # query pooling on a side stream: the encoder call below enqueues its plan / weight transposes first and
+        # waits for the pooled queries only before the kernel that reads them (psb_encoder_cfg_t.first_ready)
+        if getattr(self, "_q_stream", None) is None:
+            self._q_stream = torch.cuda.Stream(device=self.peer.device)
+            self._q_ready = torch.cuda.Event()
+            self._iw_stream = torch.cuda.Stream(device=self.peer.device)
+        q_emb = self.query_encoder.encode_indices(words, qw, wsink, pad_idx=word_pad, stream=self._q_stream)
+        self._q_ready.record(self._q_stream)
+        wb = self.word_bias
+        bias_mini = None
+        if wb is not None:     # bias values at the mini positions (the bias vector itself is replicated)
+            bias_mini = _BiasAtFn.apply(wb, self.word_table.sink._ids)
+        cur.wait_stream(self._fetch_stream)      # join: the item rows are needed by both branches below
+        # the item -> word objective shares nothing with the encoder: a parallel branch, joined before the sum
+        self._iw_stream.wait_stream(cur)
+        anchor = F_.gather_rows(items, tgt, isink, stream=self._iw_stream)
+        il = F_.ns_loss(anchor, words, pw, nw.view(B, W, K), wsink, bias=bias_mini, pad_idx=word_pad,
+                        stream=self._iw_stream)
         out_pos = -1 if self.args.use_item_pos else 0
         stochastic = self.training and self.args.dropout > 0
         copies = 1 + K if stochastic else 1
         out = self.transformer_encoder.encode_position(first=q_emb.contiguous(), table=items, idx=hist, sink=isink,
                                                        pad_idx=item_pad, use_pos=self.args.use_pos_emb,
-                                                       out_pos=out_pos, copies=copies)
+                                                       out_pos=out_pos, copies=copies, first_ready=self._q_ready)
         if stochastic:
             out = out.view(B, 1 + K, -1)
             pos_out = out[:, 0].contiguous()
@@ -436,12 +453,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         ps = F_.ns_loss(pos_out.contiguous(), items, tgt.view(B, 1), neg.view(B, 1, K), isink,
                         anchor_b=neg_out.contiguous(), pos_weight=pos_weight)
         ps_loss = ps.mean()
-        anchor = F_.gather_rows(items, tgt, isink)
-        wb = self.word_bias
-        bias_mini = None
-        if wb is not None:     # bias values at the mini positions (the bias vector itself is replicated)
-            bias_mini = _BiasAtFn.apply(wb, self.word_table.sink._ids)
-        il = F_.ns_loss(anchor, words, pw, nw.view(B, W, K), wsink, bias=bias_mini, pad_idx=word_pad)
+        cur.wait_stream(self._iw_stream)
         item_loss = il.mean()
         with torch.no_grad():
             if self._ps_acc is None:
