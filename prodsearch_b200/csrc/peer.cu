@@ -130,6 +130,7 @@ struct FoldArgs {
   int n_tables, rank, G;
   float scale;
   const uint32_t* stamp;
+  int entries_per_warp;
 };
 
 template <bool SUM>
@@ -156,9 +157,12 @@ __global__ void __launch_bounds__(256) peer_fold_kernel(const FoldArgs a) {
   // them one per warp iteration: a dependent NVLink round trip per entry), every lane resolves its own entry --
   // owned here? is r the lowest peer holding the row? at which slot do the later peers hold it? -- from the local
   // position map, then the warp folds the leader entries one after the other, 128-bit peer loads across the lanes.
-  for (int64_t i0 = w0 * 32; i0 < n; i0 += nwarps * 32) {
+  // E entries per warp and iteration: ~1 / G of them are owned here and are folded one after the other, so E grows
+  // with G (4 G, at most 32) to keep ~4 serial folds per warp whatever the number of ranks
+  const int E = a.entries_per_warp;
+  for (int64_t i0 = w0 * E; i0 < n; i0 += nwarps * E) {
     const int64_t i = i0 + lane;
-    const int32_t g = i < n ? t.rows[r][i] : -1;
+    const int32_t g = (lane < E && i < n) ? t.rows[r][i] : -1;
     const int64_t local = g >= 0 ? g / G : 0;
     bool leader = g >= 0 && g % G == rank && local < t.shard_rows;
     int32_t slot[kMaxPeers];
@@ -393,7 +397,8 @@ extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tab
     peer_fold_kernel<false><<<grid, 256, 0, s>>>(a);
     if ((st = launch_status()) != PSB_OK) return st;
   }
-  dim3 grid(grid_for(cap_max, 8 * 32, 2), n_tables, G);
+  a.entries_per_warp = 4 * G < 32 ? 4 * G : 32;
+  dim3 grid(grid_for(cap_max, 8 * a.entries_per_warp, 2), n_tables, G);
   PSB_PROF("peer_fold_sum_kernel", s);
   peer_fold_kernel<true><<<grid, 256, 0, s>>>(a);
   return launch_status();
