@@ -102,11 +102,4 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// Scheduling fence for a batch of loads: an empty volatile asm that "rewrites" the value.  Placed after a loop of
-// ldg_row4 calls (volatile asms keep their order) it makes every consumer come after ALL loads of the batch have
-// been issued, so ptxas cannot software-pipeline the batch down to two or three loads in flight.
-__device__ __forceinline__ void pin4(float4& v) {
-  asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w));
-}
-
 }  // namespace psb
