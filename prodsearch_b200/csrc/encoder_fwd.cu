@@ -553,10 +553,6 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   const TokSrc ts{cfg->first, cfg->table, cfg->table_rows, cfg->idx, cfg->pad_idx, cfg->dense, cfg->mask, cfg->pe, cfg->raw_input != 0 && cfg->first == nullptr};
   const int d = D.d, F = D.F;
 
-  PSB_PROF("plan_kernel", s);
-  plan_kernel<<<1, 1024, 0, s>>>(ts, D.S, D.T, nact, off, tok);
-  if ((st = launch_status()) != PSB_OK) return st;
-
   TrJobs jobs;
   jobs.n = 0;
   auto add = [&](const float* src, float* dst, int rows, int cols, int ldd, int col0) {
@@ -570,9 +566,20 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(p->w2, ws + W.w2_t, d, F, d, 0);           // W2 [d][F] -> [F][d]
   add(p->bk, ws + W.bkv, d, 1, 2 * d, 0);        // bias concat as 1-column "transposes"
   add(p->bv, ws + W.bkv, d, 1, 2 * d, d);
-  PSB_PROF("transpose_kernel", s);
-  transpose_kernel<<<tr_blocks(jobs), 256, 0, s>>>(jobs);
-  if ((st = launch_status()) != PSB_OK) return st;
+  // the token plan (one CTA) and the weight transposes are independent: side by side
+  st = fork_join(
+      s, 0,
+      [&](cudaStream_t s2) {
+        PSB_PROF("transpose_kernel", s2);
+        transpose_kernel<<<tr_blocks(jobs), 256, 0, s2>>>(jobs);
+        return launch_status();
+      },
+      [&]() {
+        PSB_PROF("plan_kernel", s);
+        plan_kernel<<<1, 1024, 0, s>>>(ts, D.S, D.T, nact, off, tok);
+        return launch_status();
+      });
+  if (st != PSB_OK) return st;
 
   if (cfg->first_ready != nullptr) {  // `first` comes from another stream: wait for it only now
     const cudaError_t we = cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(cfg->first_ready), 0);

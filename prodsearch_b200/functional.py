@@ -261,14 +261,14 @@ class SeqEncoderFn(Function):
     # early, so in that case whatever is in flight is joined first and this node runs on the calling stream.
     overlap_wgrad = True
     _events = {}
-    _pending = {}          # device -> [event, [workspaces kept alive], {id(weight) in flight}]
+    _pending = {}          # device -> [event, [(workspace, forward call, grad_out) kept alive], {id(weight) in flight}]
 
     @staticmethod
     def _join(dev):
         p = SeqEncoderFn._pending.pop(dev, None)
         if p is not None:
             torch.cuda.current_stream(dev).wait_event(p[0])
-            p[1].clear()                                        # the side stream is done with the workspaces
+            p[1].clear()                                        # the side stream is done with the buffers
 
     @staticmethod
     def backward(ctx, g):
@@ -290,11 +290,15 @@ class SeqEncoderFn(Function):
                 ev.record(torch.cuda.current_stream(dev))      # creates the underlying cudaEvent_t
         g_first, g_rest, g_dense, grads, ws = ops.encoder_bwd(ctx.call, g, shapes, wgrad_event=ev)
         if ev is not None:
+            # the side stream reads the workspace AND the forward's saved activations / inputs (ctx.call) until the
+            # event: both stay referenced until the join, or the caching allocator would hand their memory to the
+            # next allocation of the calling stream
+            alive = (ws, ctx.call, g)
             if pend is None:
-                SeqEncoderFn._pending[dev] = [ev, [ws], ids]
+                SeqEncoderFn._pending[dev] = [ev, [alive], ids]
                 Variable._execution_engine.queue_callback(lambda dev=dev: SeqEncoderFn._join(dev))
             else:                    # same side stream, same event re-recorded behind the earlier work
-                pend[1].append(ws)
+                pend[1].append(alive)
                 pend[2].update(ids)
         if ctx.call.tem and ctx.sink is not None and ctx.call.T > 1:
             ctx.sink.add(ctx.idx.reshape(-1), g_rest.view(-1, g_rest.shape[-1]))

@@ -19,11 +19,21 @@ def _idx(t):
     return t.contiguous()
 
 
-def _on(stream, dev):
+def _on(stream, dev, *inputs):
     """Context that enqueues on ``stream`` (a side stream the CALLER forked from and will join into the current
     one) or, when None, on the current stream.  Output buffers are always allocated before entering it, i.e. on
-    the current stream, so the caching allocator's stream bookkeeping stays valid."""
-    return torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev))
+    the current stream, so the caching allocator's stream bookkeeping stays valid.  ``inputs``: tensors the side
+    kernel reads; temporaries among them (a converted index / mask copy) would otherwise be freed -- and their
+    memory reused by the current stream -- as soon as the Python call returns, so the last few calls' inputs stay
+    referenced on the stream object (the caller joins the stream long before the list wraps around)."""
+    if stream is None:
+        return torch.cuda.stream(torch.cuda.current_stream(dev))
+    keep = getattr(stream, "_psb_keep", None)
+    if keep is None:
+        keep = stream._psb_keep = []
+    keep.append(tuple(t for t in inputs if t is not None))
+    del keep[:-8]
+    return torch.cuda.stream(stream)
 
 
 def gather_rows(table, idx, err_flag=None, stream=None):
@@ -31,7 +41,7 @@ def gather_rows(table, idx, err_flag=None, stream=None):
     idx = _idx(idx)
     n, d = idx.numel(), table.shape[1]
     out = torch.empty(idx.shape + (d,), dtype=f32, device=table.device)
-    with _on(stream, table.device):
+    with _on(stream, table.device, table, idx, out):
         check(load().psb_gather_rows(ptr(table, f32), table.shape[0], d, ptr(idx), n, ptr(out), ptr(err_flag),
                                      stream_ptr()), "psb_gather_rows")
     return out
@@ -56,7 +66,7 @@ def gather_meanpool(table, idx, pad_idx=-1, mask=None, tok_scale=None, keep_scal
     mask_c = mask.contiguous() if mask is not None else None
     if stream is not None:
         stream.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+    with _on(stream, dev, table, idx, mask_c, tok_scale, keep_scale, fs_weight, fs_bias, mean, out, inv):
         check(load().psb_gather_meanpool_fwd(
             ptr(table, f32), table.shape[0], d, ptr(idx), n, w, int(pad_idx), ptr(mask_c), ptr(tok_scale, f32),
             ptr(keep_scale, f32), ptr(fs_weight, f32), ptr(fs_bias, f32), ptr(mean), ptr(out), ptr(inv),
@@ -107,7 +117,7 @@ def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=No
     if mask is not None and mask.dtype != u8:
         mask = mask.to(u8)
     mask_c = mask.contiguous() if mask is not None else None
-    with _on(stream, dev):
+    with _on(stream, dev, anchor_a, anchor_b, table, bias, pos_idx, neg_idx, mask_c, neg_weight, loss, cp, cn, ga, gb):
         check(load().psb_ns_loss_fwd(
             ptr(anchor_a, f32), ptr(anchor_b, f32), ptr(table, f32), table.shape[0], d, ptr(bias, f32), ptr(pos_idx),
             ptr(neg_idx), ptr(mask_c), int(pad_idx), ptr(neg_weight, f32), float(pos_weight), n, w, k, ptr(loss),
