@@ -59,19 +59,28 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md: "start before, kill after").
+
+    The poller is started BEFORE the warm-up steps: launching nvidia-smi (NVML attach) stalls the polled GPU for a
+    fraction of a millisecond, and a bench window is only K x 0.45 ms long -- started at the window's first step
+    (as the first version did) that stall landed inside it on rank 0 and every other rank waited for it at the
+    step-start barrier (~19 us per step at K = 30).  Samples carry nvidia-smi's own time stamp; the summary uses
+    those taken between ``begin()`` and ``end()`` (+- one polling interval: the GPU is under the same load in the
+    warm-up steps before and the end-to-end steps after)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 50
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         if self.index is None:      # other ranks: no sampler (one nvidia-smi poller per box is enough)
             return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,30 +88,49 @@ class ClockSampler(object):
             self.proc = None
         return self
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def __exit__(self, *a):
+    def stop(self):
         if self.proc is not None:
-            time.sleep(0.25)
+            time.sleep(2.5 * self.PERIOD_MS / 1e3)
             self.proc.terminate()
             self.t.join(timeout=2)
+            self.proc = None
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        if not sm:
+        import datetime
+        rows = [r for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        if self.t0 is not None and self.t1 is not None:
+            pad = datetime.timedelta(milliseconds=1.5 * self.PERIOD_MS)
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                except ValueError:
+                    continue
+                if self.t0 - pad <= ts <= self.t1 + pad:
+                    inside.append(r)
+            rows = inside or rows
+        sm = [float(r[1]) for r in rows]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "poll_ms": self.PERIOD_MS}
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's restatement of the reference step (forward + backward + clipped Adam)
-# ------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(steps, warmup, dropout, seed=666):
     import torch
     import oracle
@@ -360,6 +388,7 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local if rank == 0 else None).start()     # before the warm-up: see the class docstring
     for it in range(a.warmup):
         step(devb[it])
     # ---- timed region 1: device-resident batches, CUDA events per step, L2 flushed between steps
@@ -369,15 +398,16 @@ def run_b200_arm(a):
     l0 = _lib.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    with ClockSampler(local if rank == 0 else None) as clocks:
-        t_host = time.perf_counter()
-        for it in range(a.steps):
-            flush.zero_()
-            starts[it].record()
-            step(devb[a.warmup + it])
-            ends[it].record()
-        host_enqueue_ms = (time.perf_counter() - t_host) / a.steps * 1e3     # host time to enqueue one step
-        barrier()
+    clocks.begin()
+    t_host = time.perf_counter()
+    for it in range(a.steps):
+        flush.zero_()
+        starts[it].record()
+        step(devb[a.warmup + it])
+        ends[it].record()
+    host_enqueue_ms = (time.perf_counter() - t_host) / a.steps * 1e3     # host time to enqueue one step
+    barrier()
+    clocks.end()
     barrier_wait = None
     if transport == "nvlink-peer":
         # SM cycles every rank spent inside the three cross-GPU barriers of a step (waiting for the slowest peer)
@@ -413,6 +443,7 @@ def run_b200_arm(a):
             float(step(db).item())
         e2e_sec += time.perf_counter() - t0
     barrier()
+    clocks.stop()
     if world > 1:
         t = torch.tensor([dev_sec, e2e_sec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
