@@ -1,0 +1,56 @@
+"""CPU: the parts of bench.py that run without a GPU -- the reference arm's JSON line (driver contract) and the
+clock sampler's parsing of nvidia-smi rows."""
+import datetime
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench_module():
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_arm_line():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "tem_train_samples_per_s" and line["unit"] == "samples/s"
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["warmup"] == 3 and line["value"] > 0
+    assert line["config"]["batch_per_gpu"] == 384 and "workload" in line["config"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_are_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_clock_sampler_summary_uses_the_timed_window():
+    b = _bench_module()
+    c = b.ClockSampler(None).start()            # no poller on this rank: parsing only
+    now = datetime.datetime.now()
+    c.t0, c.t1 = now, now + datetime.timedelta(milliseconds=20)
+
+    def row(dt_ms, sm, cap="Not Active", thermal="Not Active"):
+        ts = (now + datetime.timedelta(milliseconds=dt_ms)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return [ts, str(sm), "1965", "Not Active", thermal, "Not Active", cap]
+    c.rows = [row(-3000, 345, thermal="Active"), row(-40, 1965), row(10, 1950, cap="Active"), row(60, 1965),
+              row(5000, 210), ["garbage"]]
+    s = c.summary()
+    assert s["samples"] == 3 and s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0
+    assert s["reasons"] == ["sw_power_cap"]      # the idle-time thermal flag 3 s earlier is outside the window
+    c.rows = []
+    assert c.summary()["reasons"] == ["unavailable"]
+    c.stop()
