@@ -47,15 +47,9 @@ class ItemCorpus(object):
 
     def __init__(self, device, user_seq, review_u_p, query_words, item_queries, train_reviews=None,
                  review_uloc=None, product_size=None, vocab_size=None, item_seq=None, review_time=None):
-        dev = torch.device(device)
-        if dev.type != "cuda":
-            raise RuntimeError("ItemCorpus lives in GPU memory (no CPU fallback for batch construction)")
         rup = np.asarray(review_u_p, dtype=np.int64).reshape(-1, 2)
-        R, U = rup.shape[0], len(user_seq)
+        R = rup.shape[0]
         P = int(product_size) if product_size is not None else len(item_queries)
-        qw = np.asarray(query_words, dtype=np.int64)
-        if qw.ndim != 2:
-            raise ValueError("query_words must be padded to a rectangle (global_data.query_words is)")
         in_set = np.zeros(R, dtype=np.uint8)
         if train_reviews is None:
             in_set[:] = 1
@@ -63,29 +57,59 @@ class ItemCorpus(object):
             for s in train_reviews:
                 if len(s):
                     in_set[np.fromiter(s, dtype=np.int64, count=len(s))] = 1
-        seq_off, seq = _csr(user_seq)
-        iq_off, iq = _csr(list(item_queries) + [[]] * (P - len(item_queries)))
         uloc = None
         if review_uloc is not None:
             uloc = np.asarray([x[0] if np.ndim(x) else x for x in review_uloc], dtype=np.int32)
+        if review_time is None and review_uloc is not None and len(review_uloc) and np.ndim(review_uloc[0]) and \
+                len(review_uloc[0]) >= 3:
+            review_time = [x[2] for x in review_uloc]
+        self._setup(device, review_u_p=rup, review_uloc=uloc, review_time=review_time, review_in_set=in_set,
+                    user_seq=_csr(user_seq), item_seq=None if item_seq is None else
+                    _csr(list(item_seq) + [[]] * (P - len(item_seq))),
+                    item_query=_csr(list(item_queries) + [[]] * (P - len(item_queries))), query_words=query_words,
+                    product_size=P, vocab_size=vocab_size)
 
-        def put(a):
-            return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    @classmethod
+    def from_arrays(cls, device, review_u_p, review_in_set, user_seq, item_query, query_words, product_size,
+                    vocab_size=None, review_uloc=None, review_time=None, item_seq=None):
+        """From flat arrays (``data_files.CorpusFiles``): user_seq / item_seq / item_query are (offsets, flat) pairs."""
+        self = cls.__new__(cls)
+        self._setup(device, review_u_p=np.asarray(review_u_p, dtype=np.int64).reshape(-1, 2), review_uloc=review_uloc,
+                    review_time=review_time, review_in_set=np.asarray(review_in_set, dtype=np.uint8),
+                    user_seq=user_seq, item_seq=item_seq, item_query=item_query, query_words=query_words,
+                    product_size=int(product_size), vocab_size=vocab_size)
+        return self
+
+    def _setup(self, device, review_u_p, review_uloc, review_time, review_in_set, user_seq, item_seq, item_query,
+               query_words, product_size, vocab_size):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("ItemCorpus lives in GPU memory (no CPU fallback for batch construction)")
+        rup = review_u_p
+        R, P = rup.shape[0], product_size
+        U = len(user_seq[0]) - 1
+        qw = np.asarray(query_words, dtype=np.int64)
+        if qw.ndim != 2:
+            raise ValueError("query_words must be padded to a rectangle (global_data.query_words is)")
+        if len(item_query[0]) - 1 != P or (item_seq is not None and len(item_seq[0]) - 1 != P):
+            raise ValueError("item_query / item_seq need one (possibly empty) row per product")
+
+        def put(a, dtype=None):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a if dtype is None else np.asarray(a, dtype=dtype))
+            return torch.from_numpy(a).to(dev)
         self.device = dev
-        self.review_user, self.review_item = put(rup[:, 0].astype(np.int32)), put(rup[:, 1].astype(np.int32))
-        self.review_uloc, self.review_in_set = put(uloc), put(in_set)
-        self.user_seq_off, self.user_seq = put(seq_off), put(seq)
-        self.item_query_off, self.item_query = put(iq_off), put(iq)
+        self.review_user, self.review_item = put(rup[:, 0], np.int32), put(rup[:, 1], np.int32)
+        self.review_uloc, self.review_in_set = put(review_uloc, np.int32), put(review_in_set, np.uint8)
+        self.user_seq_off, self.user_seq = put(user_seq[0], np.int64), put(user_seq[1], np.int32)
+        self.item_query_off, self.item_query = put(item_query[0], np.int64), put(item_query[1], np.int32)
         self.query_words = put(qw)
         # review-transformer batches: every item's reviews in time order + the time stamps (i_r_seq, review_loc_time[:, 2])
-        self.item_seq_off = self.item_seq = self.review_time = None
+        self.item_seq_off = self.item_seq = None
         if item_seq is not None:
-            io, iflat = _csr(list(item_seq) + [[]] * (P - len(item_seq)))
-            self.item_seq_off, self.item_seq = put(io), put(iflat)
-        if review_time is not None:
-            self.review_time = put(np.asarray(review_time, dtype=np.int64))
-        elif review_uloc is not None and len(review_uloc) and np.ndim(review_uloc[0]) and len(review_uloc[0]) >= 3:
-            self.review_time = put(np.asarray([x[2] for x in review_uloc], dtype=np.int64))
+            self.item_seq_off, self.item_seq = put(item_seq[0], np.int64), put(item_seq[1], np.int32)
+        self.review_time = put(review_time, np.int64)
         self.n_reviews, self.n_users, self.n_items, self.n_queries, self.wq = R, U, P, qw.shape[0], qw.shape[1]
         self.prod_pad_idx = P                                       # item_pv_dataset.py:24
         self.word_pad_idx = (int(vocab_size) if vocab_size is not None else int(qw.max()) + 1) - 1

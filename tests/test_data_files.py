@@ -1,0 +1,73 @@
+"""CPU: the dataset-file readers (prodsearch_b200/data_files.py) against what the reference's own loaders made of
+the same files (tests/golden/files.npz from tests/golden/make_golden_files.py): every array GlobalProdSearchData /
+ProdSearchData expose, the derived distributions, and the test-entry enumeration of ItemPVDataset."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "files.npz")
+
+
+@pytest.fixture(scope="module")
+def loaded(tmp_path_factory):
+    from prodsearch_b200 import data_files
+    z = np.load(GOLDEN)
+    root = tmp_path_factory.mktemp("corpus")
+    data, inp = root / "data", root / "data" / "split"
+    inp.mkdir(parents=True)
+    for k in z.files:
+        if k.startswith("file/"):
+            _, tag, name = k.split("/")
+            (data if tag == "data" else inp).joinpath(name).write_bytes(z[k].tobytes())
+    files = data_files.CorpusFiles(str(data), str(inp))
+    return z, files, data_files
+
+
+def test_global_arrays_match_reference(loaded):
+    z, f, _ = loaded
+    assert f.product_ids == [str(x) for x in z["g/product_ids"]] and f.user_ids == [str(x) for x in z["g/user_ids"]]
+    assert f.vocab_size == int(z["g/vocab_size"]) and f.review_count == int(z["g/review_count"])
+    assert np.array_equal(f.query_words, z["g/query_words"])
+    assert np.array_equal(f.review_length, z["g/review_length"])
+    for mine, ref in (((f.review_word_off, f.review_word), ("g/review_words_off", "g/review_words")),
+                      ((f.user_seq_off, f.user_seq), ("g/u_r_seq_off", "g/u_r_seq")),
+                      ((f.item_seq_off, f.item_seq), ("g/i_r_seq_off", "g/i_r_seq"))):
+        assert np.array_equal(mine[0], z[ref[0]]) and np.array_equal(mine[1], z[ref[1]]), ref
+    assert np.array_equal(f.review_loc_time, z["g/review_loc_time"])
+    assert np.array_equal(f.review_u_p, z["g/review_u_p"])
+    assert np.array_equal(f.train_review_info, z["g/train_review_info"])
+    assert f.train_query_idxs == z["g/train_query_idxs"].tolist()
+
+
+def test_splits_match_reference(loaded):
+    z, f, df = loaded
+    tr = f.split("train", subsampling_rate=1e-3)
+    te = f.split("test", subsampling_rate=1e-3)
+    for tag, s in (("train", tr), ("test", te)):
+        assert np.array_equal(s.item_query_off, z[tag + "/pq_off"]) and np.array_equal(s.item_query, z[tag + "/pq"])
+        assert np.array_equal(s.review_info, z[tag + "/review_info"])
+        assert np.array_equal(s.product_dists, z[tag + "/product_dists"])               # bit-exact float64
+        # one byte per review replaces the per-user AND the per-item sets of training reviews
+        assert np.array_equal(f.review_in_train, z[tag + "/in_u_reviews"])
+        assert np.array_equal(f.review_in_train, z[tag + "/in_p_reviews"])
+    assert np.array_equal(tr.vocab_distribute, z["train/vocab_distribute"])
+    assert np.array_equal(tr.sub_sampling_rate, z["train/sub_sampling_rate"])           # bit-exact float64
+    assert np.array_equal(tr.word_dists, z["train/word_dists"])
+    assert te.word_dists is None and te.sub_sampling_rate is None
+    freq = f.split("train", subsampling_rate=1e-3, prod_freq_neg_sample=True)
+    assert np.array_equal(freq.product_dists, z["train_freq/product_dists"])
+    assert np.array_equal(f.split("train", subsampling_rate=0.0).sub_sampling_rate, np.ones(f.vocab_size))
+
+
+def test_test_entries_match_reference(loaded):
+    z, f, _ = loaded
+    e = f.split("test").test_entries()
+    assert e.dtype == np.int64 and np.array_equal(e, z["test/entries"])
+    assert len(set((int(u), int(q)) for q, u, _, _ in e)) == len(e)                      # distinct (user, query)
+
+
+def test_item_corpus_needs_a_gpu(loaded):
+    _, f, df = loaded
+    with pytest.raises(RuntimeError):
+        df.item_corpus("cpu", f, f.split("test"))
