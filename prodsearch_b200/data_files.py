@@ -125,6 +125,39 @@ class SplitFiles(object):
     def product_query_idx(self):
         return _uncsr(self.item_query_off, self.item_query)
 
+    def train_samples(self, pv_window_size=1, py_random=None, np_random=None):
+        """ItemPVDataset.collect_train_samples (item_pv_dataset.py:71-93): the (word window, review) samples of one
+        epoch -> (words int64 [n, pv_window_size], review_idx int64 [n]).  The reference draws from the GLOBAL python and
+        numpy generators (one ``np.random.random`` call for all words, one ``random.shuffle`` per review, in file
+        order); the same calls are made here on ``py_random`` / ``np_random`` (default: those globals), so a run
+        seeded like main.py:172-173 enumerates the identical samples.  Quirk kept: a sub-sampled (skipped) word does
+        not advance the random-number cursor (:84-85).  The corpus' review words are NOT shuffled in place."""
+        import random as _random
+        py_random = py_random if py_random is not None else _random
+        np_random = np_random if np_random is not None else np.random
+        c = self.corpus
+        rand_numbers = np_random.random(int(c.review_length.sum()))
+        rate = self.sub_sampling_rate
+        W = int(pv_window_size)
+        words, reviews, cur, entry_id = [], [], [], 0
+        off, flat = c.review_word_off, c.review_word
+        for _, _, _, review_idx in self.review_info.tolist():
+            ws = flat[off[review_idx]:off[review_idx + 1]].tolist()
+            py_random.shuffle(ws)
+            for w in ws:
+                if rand_numbers[entry_id] > rate[w]:
+                    continue
+                cur.append(w)
+                if len(cur) == W:
+                    words.append(cur)
+                    reviews.append(review_idx)
+                    cur = []
+                entry_id += 1
+        if len(cur) > 0:
+            words.append(cur + [c.word_pad_idx] * (W - len(cur)))
+            reviews.append(review_idx)
+        return np.asarray(words, dtype=np.int64).reshape(len(words), W), np.asarray(reviews, dtype=np.int64)
+
     def test_entries(self):
         """ItemPVDataset.collect_test_samples (item_pv_dataset.py:36-68) when the whole catalog is the candidate set
         (``test_candi_size < 1``, no ranklist file): the distinct (user, query) pairs in file order, one query per

@@ -99,6 +99,18 @@ def main():
         args2 = argparse.Namespace(**dict(vars(args), prod_freq_neg_sample=True))
         tr_freq = ProdSearchData(args2, inp, "train", g)
         ds = ItemPVDataset(args, g, te)
+        # training samples: python / numpy global RNGs seeded like main.py:172-173 does; collect_train_samples
+        # shuffles every review's word list IN PLACE, so it runs on a deep copy of the loaded corpus
+        import copy
+        import random
+        g2 = copy.deepcopy(g)
+        train_samples = {}
+        for W in (1, 3):
+            args_w = argparse.Namespace(**dict(vars(args), pv_window_size=W))
+            g3 = copy.deepcopy(g2)
+            random.seed(666)
+            np.random.seed(666)
+            train_samples[W] = ItemPVDataset(args_w, g3, tr)._data
     out["g/product_ids"], out["g/user_ids"] = np.asarray(g.product_ids), np.asarray(g.user_ids)
     out["g/vocab_size"], out["g/review_count"] = np.int64(g.vocab_size), np.int64(g.review_count)
     out["g/query_words"] = np.asarray(g.query_words, np.int64)
@@ -130,6 +142,9 @@ def main():
     entries = [e[:4] for e in ds._data]
     assert all(e[4] == list(range(g.product_size)) for e in ds._data)
     out["test/entries"] = np.asarray(entries, np.int64)
+    for W, data_ in train_samples.items():
+        out["train_samples_w%d/words" % W] = np.asarray([d[0] for d in data_], np.int64).reshape(len(data_), W)
+        out["train_samples_w%d/review" % W] = np.asarray([d[1] for d in data_], np.int64)
     np.savez_compressed(os.path.join(OUT, "files.npz"), **out)
     print("files ok: %d files, %d reviews, %d train / %d test lines, %d test entries" % (
         sum(1 for k in out if k.startswith("file/")), len(g.review_u_p), len(tr.review_info), len(te.review_info),

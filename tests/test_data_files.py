@@ -71,3 +71,22 @@ def test_item_corpus_needs_a_gpu(loaded):
     _, f, df = loaded
     with pytest.raises(RuntimeError):
         df.item_corpus("cpu", f, f.split("test"))
+
+
+def test_train_samples_match_reference_rng_stream(loaded):
+    """Seeded like main.py:172-173, the sample enumeration is the reference's, word for word (python's shuffle and
+    numpy's legacy generator are consumed in the same order)."""
+    import random
+    z, f, _ = loaded
+    tr = f.split("train", subsampling_rate=1e-3)
+    before = f.review_word.copy()
+    for W in (1, 3):
+        random.seed(666)
+        np.random.seed(666)
+        words, reviews = tr.train_samples(pv_window_size=W)
+        assert np.array_equal(words, z["train_samples_w%d/words" % W]), W
+        assert np.array_equal(reviews, z["train_samples_w%d/review" % W]), W
+    assert np.array_equal(f.review_word, before)                 # no in-place shuffle of the corpus
+    # private generators give the same stream without touching the globals
+    words2, _ = tr.train_samples(1, py_random=random.Random(666), np_random=np.random.RandomState(666))
+    assert np.array_equal(words2, z["train_samples_w1/words"])
