@@ -47,6 +47,14 @@ class ItemCorpus(object):
 
     def __init__(self, device, user_seq, review_u_p, query_words, item_queries, train_reviews=None,
                  review_uloc=None, product_size=None, vocab_size=None, item_seq=None, review_time=None):
+        self._setup(device, vocab_size=vocab_size, **self.lists_to_arrays(
+            user_seq, review_u_p, query_words, item_queries, train_reviews, review_uloc, product_size, item_seq,
+            review_time))
+
+    @staticmethod
+    def lists_to_arrays(user_seq, review_u_p, query_words, item_queries, train_reviews=None, review_uloc=None,
+                        product_size=None, item_seq=None, review_time=None):
+        """Nested lists of the reference's data objects -> the keyword arguments of ``host_arrays``."""
         rup = np.asarray(review_u_p, dtype=np.int64).reshape(-1, 2)
         R = rup.shape[0]
         P = int(product_size) if product_size is not None else len(item_queries)
@@ -63,11 +71,11 @@ class ItemCorpus(object):
         if review_time is None and review_uloc is not None and len(review_uloc) and np.ndim(review_uloc[0]) and \
                 len(review_uloc[0]) >= 3:
             review_time = [x[2] for x in review_uloc]
-        self._setup(device, review_u_p=rup, review_uloc=uloc, review_time=review_time, review_in_set=in_set,
-                    user_seq=_csr(user_seq), item_seq=None if item_seq is None else
-                    _csr(list(item_seq) + [[]] * (P - len(item_seq))),
+        return dict(review_u_p=rup, review_uloc=uloc, review_time=review_time, review_in_set=in_set,
+                    user_seq=_csr(user_seq),
+                    item_seq=None if item_seq is None else _csr(list(item_seq) + [[]] * (P - len(item_seq))),
                     item_query=_csr(list(item_queries) + [[]] * (P - len(item_queries))), query_words=query_words,
-                    product_size=P, vocab_size=vocab_size)
+                    product_size=P)
 
     @classmethod
     def from_arrays(cls, device, review_u_p, review_in_set, user_seq, item_query, query_words, product_size,
@@ -80,36 +88,46 @@ class ItemCorpus(object):
                     product_size=int(product_size), vocab_size=vocab_size)
         return self
 
+    @staticmethod
+    def host_arrays(review_u_p, review_uloc, review_time, review_in_set, user_seq, item_seq, item_query, query_words,
+                    product_size):
+        """The flat arrays exactly as they are uploaded (name -> contiguous numpy array or None); pure host code, so
+        the CPU tests can hold both constructors to the nested lists of the reference's loaders."""
+        rup = np.asarray(review_u_p, dtype=np.int64).reshape(-1, 2)
+        qw = np.asarray(query_words, dtype=np.int64)
+        if qw.ndim != 2:
+            raise ValueError("query_words must be padded to a rectangle (global_data.query_words is)")
+        P = int(product_size)
+        if len(item_query[0]) - 1 != P or (item_seq is not None and len(item_seq[0]) - 1 != P):
+            raise ValueError("item_query / item_seq need one (possibly empty) row per product")
+
+        def arr(a, dtype):
+            return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=dtype))
+        h = dict(review_user=arr(rup[:, 0], np.int32), review_item=arr(rup[:, 1], np.int32),
+                 review_uloc=arr(review_uloc, np.int32), review_in_set=arr(review_in_set, np.uint8),
+                 user_seq_off=arr(user_seq[0], np.int64), user_seq=arr(user_seq[1], np.int32),
+                 item_query_off=arr(item_query[0], np.int64), item_query=arr(item_query[1], np.int32),
+                 query_words=arr(qw, np.int64), item_seq_off=None, item_seq=None,
+                 review_time=arr(review_time, np.int64))
+        # review-transformer batches: every item's reviews in time order + the time stamps (i_r_seq, review_loc_time[:, 2])
+        if item_seq is not None:
+            h["item_seq_off"], h["item_seq"] = arr(item_seq[0], np.int64), arr(item_seq[1], np.int32)
+        if h["review_in_set"].shape[0] != rup.shape[0]:
+            raise ValueError("review_in_set needs one flag per review")
+        return h
+
     def _setup(self, device, review_u_p, review_uloc, review_time, review_in_set, user_seq, item_seq, item_query,
                query_words, product_size, vocab_size):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("ItemCorpus lives in GPU memory (no CPU fallback for batch construction)")
-        rup = review_u_p
-        R, P = rup.shape[0], product_size
-        U = len(user_seq[0]) - 1
-        qw = np.asarray(query_words, dtype=np.int64)
-        if qw.ndim != 2:
-            raise ValueError("query_words must be padded to a rectangle (global_data.query_words is)")
-        if len(item_query[0]) - 1 != P or (item_seq is not None and len(item_seq[0]) - 1 != P):
-            raise ValueError("item_query / item_seq need one (possibly empty) row per product")
-
-        def put(a, dtype=None):
-            if a is None:
-                return None
-            a = np.ascontiguousarray(a if dtype is None else np.asarray(a, dtype=dtype))
-            return torch.from_numpy(a).to(dev)
+        h = self.host_arrays(review_u_p, review_uloc, review_time, review_in_set, user_seq, item_seq, item_query,
+                             query_words, product_size)
         self.device = dev
-        self.review_user, self.review_item = put(rup[:, 0], np.int32), put(rup[:, 1], np.int32)
-        self.review_uloc, self.review_in_set = put(review_uloc, np.int32), put(review_in_set, np.uint8)
-        self.user_seq_off, self.user_seq = put(user_seq[0], np.int64), put(user_seq[1], np.int32)
-        self.item_query_off, self.item_query = put(item_query[0], np.int64), put(item_query[1], np.int32)
-        self.query_words = put(qw)
-        # review-transformer batches: every item's reviews in time order + the time stamps (i_r_seq, review_loc_time[:, 2])
-        self.item_seq_off = self.item_seq = None
-        if item_seq is not None:
-            self.item_seq_off, self.item_seq = put(item_seq[0], np.int64), put(item_seq[1], np.int32)
-        self.review_time = put(review_time, np.int64)
+        for name, a in h.items():
+            setattr(self, name, None if a is None else torch.from_numpy(a).to(dev))
+        qw = h["query_words"]
+        R, P, U = h["review_user"].shape[0], int(product_size), len(h["user_seq_off"]) - 1
         self.n_reviews, self.n_users, self.n_items, self.n_queries, self.wq = R, U, P, qw.shape[0], qw.shape[1]
         self.prod_pad_idx = P                                       # item_pv_dataset.py:24
         self.word_pad_idx = (int(vocab_size) if vocab_size is not None else int(qw.max()) + 1) - 1

@@ -196,10 +196,11 @@ def neg_distributes(weights, distortion=0.75):
     return wf / wf.sum()
 
 
-def item_corpus(device, files, split):
+def item_corpus(device, files, split, cls=None):
     """``corpus.ItemCorpus`` (CSR arrays in HBM) straight from the files: no nested lists in between."""
-    from .corpus import ItemCorpus
-    return ItemCorpus.from_arrays(
+    if cls is None:
+        from .corpus import ItemCorpus as cls
+    return cls.from_arrays(
         device, review_u_p=files.review_u_p, review_uloc=files.review_loc_time[:, 0],
         review_time=files.review_loc_time[:, 2], review_in_set=files.review_in_train,
         user_seq=(files.user_seq_off, files.user_seq), item_seq=(files.item_seq_off, files.item_seq),
