@@ -299,6 +299,142 @@ def bandwidth_regime(peaks, rows=16_000_000, d=128):
                 ent["frac_of_hbm_peak"] = n_items * d * 4 / sec / GB / peaks["hbm"]
             cat["%s_m%d" % (mname, m)] = ent
     out["G5_catalog_topk_1M"] = cat
+    # the same fused top-100 over the whole 16M-row table (BASELINE configs[4] on one GPU: the N=1 end of
+    # extra.sharded_16M.catalog_topk_16M of the multi-GPU runs)
+    try:
+        del prep
+        prep16 = ops.catalog_prepare_f16(table, rows)
+        m = 4096
+        q = torch.randn(m, d, device=dev)
+        mode, mname = (_lib.TOPK_TC16, "tcgen05_f16") if prep16.fits else (_lib.TOPK_TC, "tcgen05_tf32")
+        norm16 = ops.table_max_row_sqnorm(table, rows)
+        sec = timed(lambda: ops.catalog_topk(q, table, 100, n_items=rows, mode=mode, max_row_sqnorm=norm16,
+                                             prepared=prep16 if mode == _lib.TOPK_TC16 else None), 3, warmup=1)
+        flops = 2.0 * m * rows * d
+        out["G5_catalog_topk_16M"] = {
+            "ms": sec * 1e3, "queries": m, "k": 100, "mode": mname, "queries_per_s": m / sec,
+            "tflops": flops / sec / 1e12,
+            "frac_of_tensor_peak": flops / sec / 1e12 / (peaks["bf16"] if mode == _lib.TOPK_TC16 else peaks["bf16"] / 2),
+            "table_GBps": rows * d * (2 if mode == _lib.TOPK_TC16 else 4) * ((m + 511) // 512) / sec / GB,
+            "note": "table_GBps counts one shortlist-table pass per 512 queries"}
+    except RuntimeError as ex:
+        out["G5_catalog_topk_16M"] = {"unavailable": str(ex)[:120]}
+    return out
+
+
+def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096, k=100, n_gather=1_000_000, dev="cuda",
+                   table_cls=None, timer=None):
+    """BASELINE configs[4]: a 16M x 128 fp32 table row-sharded over the ranks of one box (owner = id % G), in peer
+    memory.  (1) training-side row gathers of global ids from their owners over NVLink (psb_peer_gather_rows),
+    (2) sharded full-catalog top-100: all-gather the queries, local fused top-k per shard, all-gather the per-shard
+    lists, merge (psb_topk_merge).  Every rank runs this; seconds are the MAX over ranks.  A failure on one rank is
+    agreed on by all ranks BEFORE the next collective, so nobody is left waiting inside NCCL.
+    ``dev`` / ``table_cls`` / ``timer`` exist for the world-2 gloo test of this control flow (tests/test_sharding_gloo.py)."""
+    import torch
+    import torch.distributed as dist
+    from prodsearch_b200 import _lib, ops, synth
+    if table_cls is None:
+        from prodsearch_b200.peer import PeerShardedTable as table_cls
+    timer = timer or timed
+
+    def sync():
+        dist.barrier()
+        if str(dev).startswith("cuda"):
+            torch.cuda.synchronize()
+    out = {"table": "%d x %d fp32 row-sharded over %d ranks (%.2f GB per rank), peer memory" %
+                    (rows, d, world, (rows // world) * d * 4 / 1e9)}
+    GB = 1e9
+
+    def agree(err):
+        """True when every rank got here without an error (one small all-reduce)."""
+        t = torch.tensor([0 if err is None else 1], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item()) == 0
+
+    def max_over_ranks(sec):
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    table = None
+    err = None
+    try:
+        table = table_cls(rows + 1, d, pg, pad_idx=rows)                  # collective: alloc + IPC handle exchange
+        with torch.no_grad():
+            table.weight.normal_()
+            if rows % world == rank:
+                table.weight[rows // world] = 0                           # the pad row lives on rank rows % G
+        table.weight.requires_grad_(False)
+    except Exception as ex:                                               # noqa: BLE001 -- reported in the JSON line
+        err = "%s: %s" % (type(ex).__name__, str(ex)[:120])
+    if not agree(err):
+        out["unavailable"] = err or "another rank failed to allocate its shard"
+        return out
+    sync()
+    # ---- (1) row gathers from the owners: 1M uniform global ids per rank, (G-1)/G of them cross NVLink
+    n = int(n_gather)
+    sec = None
+    try:
+        idx = synth.gather_indices(n, rows, seed=11 + rank, dist="uniform").to(dev)
+        with torch.no_grad():
+            sec = timer(lambda: table.fetch([idx]), 5, warmup=2)
+    except Exception as ex:                                               # noqa: BLE001
+        err = "%s: %s" % (type(ex).__name__, str(ex)[:120])
+    if agree(err):
+        sec = max_over_ranks(sec)
+        nbytes = n * (d * 4 * 2 + 8)
+        out["peer_gather_rows"] = {
+            "ms": sec * 1e3, "rows_per_rank": n, "algorithmic_bytes_per_rank": nbytes,
+            "achieved_per_rank": nbytes / sec / GB, "achieved": world * nbytes / sec / GB, "unit": "GB/s",
+            "nvlink_GBps_per_rank": n * (world - 1) / world * d * 4 / sec / GB,
+            "note": "1M uniform global ids per rank fetched from their owners into a local mini table (read + "
+                    "materialised write + int64 id); (G-1)/G of the rows travel over NVLink, so the link (900 GB/s per "
+                    "direction per GPU), not HBM, is the ceiling; includes the id concat / remap of fetch()"}
+    else:
+        out["peer_gather_rows"] = {"unavailable": err or "failed on another rank"}
+        err = None
+    sync()
+    # ---- (2) sharded full-catalog top-k: m_total queries in all, m_total / G contributed by every rank
+    n_local = max(0, (rows - rank + world - 1) // world)
+    m_local = max(1, m_total // world)
+    sec = None
+    mode_name = "tcgen05_f16"
+    try:
+        w = table.weight.detach()
+        prep = ops.catalog_prepare_f16(w, n_local)
+        mode = _lib.TOPK_TC16
+        if not prep.fits:
+            mode, prep, mode_name = _lib.TOPK_TC, None, "tcgen05_tf32"
+        q = torch.randn(m_local, d, device=dev)
+
+        def ranked():
+            qs = [torch.empty_like(q) for _ in range(world)]
+            dist.all_gather(qs, q)
+            ids, sc = ops.catalog_topk(torch.cat(qs, 0), w, k, n_items=n_local, id_base=rank, id_stride=world,
+                                       mode=mode, prepared=prep)
+            ids_all = [torch.empty_like(ids) for _ in range(world)]
+            sc_all = [torch.empty_like(sc) for _ in range(world)]
+            dist.all_gather(ids_all, ids)
+            dist.all_gather(sc_all, sc)
+            return ops.topk_merge(torch.stack(ids_all), torch.stack(sc_all))
+    except Exception as ex:                                               # noqa: BLE001
+        err = "%s: %s" % (type(ex).__name__, str(ex)[:120])
+    if agree(err):
+        # the timed function contains collectives: every rank runs the same number of calls
+        sec = max_over_ranks(timer(ranked, 3, warmup=1))
+        m_all = m_local * world
+        out["catalog_topk_16M"] = {
+            "ms": sec * 1e3, "queries": m_all, "k": k, "mode": mode_name, "queries_per_s": m_all / sec,
+            "tflops": 2.0 * m_all * rows * d / sec / 1e12,
+            "frac_of_tensor_peak": 2.0 * m_all * rows * d / sec / 1e12 /
+                                   ((peaks["bf16"] if mode_name == "tcgen05_f16" else peaks["bf16"] / 2) * world),
+            "table_GBps": rows * d * (2 if mode_name == "tcgen05_f16" else 4) * ((m_all + 511) // 512) / sec / GB,
+            "note": "all-gather of the queries (NCCL), per-shard fused top-k on the shard's rows (ids = rank + G * "
+                    "local row), all-gather of the [M, k] lists (NCCL), psb_topk_merge; exact-mode ids and scores.  "
+                    "table_GBps counts one shortlist-table pass per 512 queries (fp16 copy), over all ranks; tensor "
+                    "peak = measured bf16 cuBLAS burst (half of it in tf32 mode) x ranks"}
+    else:
+        out["catalog_topk_16M"] = {"unavailable": err or "failed on another rank"}
     return out
 
 
@@ -462,6 +598,9 @@ def run_b200_arm(a):
     barrier()
     kprof = _lib.profile_dump()
     _lib.profile_enable(False)
+    sharded = None
+    if world > 1 and transport == "nvlink-peer" and not a.no_extra:
+        sharded = sharded_regime(peaks, pg, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -547,6 +686,8 @@ def run_b200_arm(a):
     extra = None
     if world == 1 and not a.no_extra:
         extra = {"bandwidth_regime": bandwidth_regime(peaks), "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
+    elif sharded is not None:
+        extra = {"sharded_16M": sharded}
     cpu = None
     if world == 1 and not a.no_cpu:
         sec, cores = cpu_reference_step_time(a.cpu_steps, 2, a.dropout)

@@ -119,3 +119,106 @@ def test_sharded_table_world2_gloo():
         p.join(timeout=30)
     for rank, msg in res:
         assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.sharded_regime (extra.sharded_16M of the N>1 bench lines): its control flow contains collectives, so a
+# failure on ONE rank must be agreed on before the next collective instead of leaving the others inside it.
+# ---------------------------------------------------------------------------------------------------------------
+class _FakeShards(object):
+    """CPU stand-in for peer.PeerShardedTable (test infrastructure): local shard only, fetch() gathers local rows."""
+    fail_ctor_on = None
+    fail_fetch_on = None
+
+    def __init__(self, rows, d, pg, pad_idx):
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if _FakeShards.fail_ctor_on == rank:
+            raise MemoryError("simulated allocation failure")
+        self.rank, self.world = rank, world
+        self.weight = torch.nn.Parameter(torch.zeros((rows - rank + world - 1) // world, d))
+
+    def fetch(self, index_tensors):
+        if _FakeShards.fail_fetch_on == self.rank:
+            raise RuntimeError("simulated gather failure")
+        ids = index_tensors[0]
+        return self.weight.detach()[(ids // self.world) % self.weight.shape[0]], [ids], ids.numel()
+
+
+def _regime_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import argparse
+        import time
+
+        import bench
+        import oracle
+        from prodsearch_b200 import ops
+
+        def timer(fn, iters, warmup=3):
+            for _ in range(warmup):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                fn()
+            return max(time.perf_counter() - t0, 1e-9) / iters
+        seen = {}
+
+        def prepare(w, n_local):
+            return argparse.Namespace(fits=True, n_items=n_local)
+
+        def topk(qa, w, kk, n_items, id_base, id_stride, mode, prepared):
+            ids = id_base + id_stride * torch.arange(n_items)
+            i, s_ = oracle.topk_lower_id_first((qa @ w[:n_items].t()).numpy(), kk, np.tile(ids.numpy(), (qa.shape[0], 1)))
+            return torch.from_numpy(i), torch.from_numpy(s_)
+
+        def merge(ids, sc):
+            i, s_ = oracle.merge_shard_topk(list(ids.numpy()), list(sc.numpy()), ids.shape[2])
+            seen["merged"] = (i, s_)
+            return torch.from_numpy(i), torch.from_numpy(s_)
+        ops.catalog_prepare_f16, ops.catalog_topk, ops.topk_merge = prepare, topk, merge
+        peaks = {"hbm": 6500.0, "bf16": 1600.0, "src": "test"}
+        kw = dict(rows=1001, d=8, m_total=6, k=5, n_gather=64, dev="cpu", table_cls=_FakeShards, timer=timer)
+        # 1. every rank healthy: both sections measured, the same numbers on every rank (max over ranks)
+        r1 = bench.sharded_regime(peaks, None, rank, world, **kw)
+        assert "unavailable" not in r1 and r1["peer_gather_rows"]["ms"] > 0, r1
+        cat = r1["catalog_topk_16M"]
+        assert cat["queries"] == 6 and cat["queries_per_s"] > 0 and cat["mode"] == "tcgen05_f16", cat
+        ids, _ = seen["merged"]
+        assert ids.shape == (6, 5) and (ids >= 0).all() and (ids < 1001).all()
+        both = [None] * world
+        dist.all_gather_object(both, (r1["peer_gather_rows"]["ms"], cat["ms"]))
+        assert both[0] == both[1]
+        # 2. one rank cannot allocate its shard: every rank reports it and nobody waits inside a collective
+        _FakeShards.fail_ctor_on = 1
+        r2 = bench.sharded_regime(peaks, None, rank, world, **kw)
+        assert "unavailable" in r2 and "catalog_topk_16M" not in r2, r2
+        assert ("MemoryError" in r2["unavailable"]) == (rank == 1)
+        _FakeShards.fail_ctor_on = None
+        # 3. the gather fails on one rank: that section is dropped everywhere, the catalog section still runs
+        _FakeShards.fail_fetch_on = 0
+        r3 = bench.sharded_regime(peaks, None, rank, world, **kw)
+        assert "unavailable" in r3["peer_gather_rows"] and r3["catalog_topk_16M"]["queries_per_s"] > 0, r3
+        out.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_bench_sharded_regime_agrees_on_failures_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 30100 + os.getpid() % 500
+    procs = [ctx.Process(target=_regime_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d: %s" % (rank, msg)
