@@ -568,6 +568,230 @@ tc16_score_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------ fp16 shortlist, epilogue v2 (PSB_TC16_EPI=2)
+// Same TMA producer and MMA issuer as tc16_score_kernel; the hand-off and the epilogue differ:
+//  (1) the accumulator set is handed over per QUERY TILE (one mbarrier per (set, tile), committed right after the
+//      tile's 8 MMAs): the epilogue of tile 0 runs while the MMAs of tiles 1.. are still in flight;
+//  (2) every epilogue warp owns a FIXED run of 32-column chunks of ONE query tile, so threshold, count and list
+//      base are scalars for the whole kernel (v1 deals chunks round-robin over the parts and re-selects the
+//      per-tile state for every chunk: ~35 of its ~80 instructions per chunk in the SASS);
+//  (3) a row therefore has AP candidate lists per item slice (the parts that own chunks of its tile), not kParts.
+// Written at the end of round 1 without GPU time left: compiled and SASS-checked only, OFF by default.
+template <int MT>
+struct Tc16V2 {
+  static constexpr int TN = MT <= 2 ? 128 : 64;
+  static constexpr int kChunksPerTile = TN / 32;
+  static constexpr int kChunks = MT * kChunksPerTile;                 // 32-column chunks per accumulator set
+  static constexpr int CPP = (kChunks + kParts - 1) / kParts;         // chunks per part: a contiguous run
+  static constexpr int kActiveParts = (kChunks + CPP - 1) / CPP;      // parts that own chunks (MT = 3: 3 of 4)
+  static constexpr int AP = kChunksPerTile / CPP;                     // parts (= candidate lists) per query tile
+  static_assert(kChunksPerTile % CPP == 0, "a part's run of chunks must stay inside one query tile");
+};
+
+template <bool DUMP, int MT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
+                     const Tc16Params P) {
+  using V = Tc16V2<MT>;
+  constexpr int TN = V::TN;
+  constexpr int kAccCols = MT * TN;
+  constexpr int kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+  constexpr uint32_t kIdesc16 = (1u << 4) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(kTM >> 4) << 24);
+  constexpr int kMaxStages = 8;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q_bytes = static_cast<uint32_t>(MT * P.kblocks) * kQBlock16;
+  const uint32_t e_block = static_cast<uint32_t>(TN) * 128u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(P.kblocks) * e_block;
+  const int S = P.stages;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = bars + 1 + kMaxStages;
+  uint64_t* t_full = bars + 1 + 2 * kMaxStages;          // [2 sets][MT tiles] (8 slots reserved)
+  uint64_t* t_empty = bars + 9 + 2 * kMaxStages;         // [2 sets]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * kMaxStages);
+
+  const int n_slices = gridDim.x, slice = blockIdx.x, mtile0 = blockIdx.y * MT;
+  const int per = (P.n_tiles + n_slices - 1) / n_slices;
+  const int p_lo = slice * per;
+  const int p_hi = min(P.n_tiles, p_lo + per);
+  const int my_tiles = max(0, p_hi - p_lo);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int st = 0; st < S; ++st) {
+      mbar_init(b_full + st, 1);
+      mbar_init(b_empty + st, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      for (int mt = 0; mt < MT; ++mt) mbar_init(t_full + a * MT + mt, 1);
+      mbar_init(t_empty + a, 4 * V::kActiveParts);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (as v1) =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, q_bytes);
+      for (int mt = 0; mt < MT; ++mt)
+        for (int kb = 0; kb < P.kblocks; ++kb)
+          tma_load_2d(sA + (mt * P.kblocks + kb) * kQBlock16, &map_q, kb * kKB16, (mtile0 + mt) * kTM, a_full);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(b_empty + st, ph ^ 1);
+        mbar_expect_tx(b_full + st, stage_bytes);
+        const int tile = P.tile_begin + (p_lo + it) * P.tile_step;
+        for (int kb = 0; kb < P.kblocks; ++kb)
+          tma_load_2d(sB + static_cast<size_t>(st) * stage_bytes + kb * e_block, &map_e, kb * kKB16, tile * TN, b_full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one commit per query tile =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      const uint64_t a_base = umma_desc(smem_u32(sA));
+      const uint64_t b_base = umma_desc(smem_u32(sB));
+      const uint32_t kb_a = kQBlock16 >> 4, kb_b = e_block >> 4, st_b = stage_bytes >> 4;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(t_empty + acc, aph ^ 1);
+        mbar_wait(b_full + st, ph);
+        tc_fence_after();
+        const uint64_t b_tile = b_base + static_cast<uint64_t>(st) * st_b;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols + mt * TN);
+          const uint64_t a_tile = a_base + static_cast<uint64_t>(mt * P.kblocks) * kb_a;
+#pragma unroll 2
+          for (int kb = 0; kb < P.kblocks; ++kb) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              tc_mma_f16(d_addr, a_tile + static_cast<uint64_t>(kb) * kb_a + k4 * 2, b_tile + static_cast<uint64_t>(kb) * kb_b + k4 * 2,
+                         kIdesc16, (kb | k4) != 0 ? 1u : 0u);
+          }
+          tc_commit(t_full + acc * MT + mt);
+        }
+        tc_commit(b_empty + st);
+      }
+    }
+  } else if (((warp - 2) >> 2) < V::kActiveParts) {
+    // ===== epilogue: thread = (TMEM lane = query row of ONE tile, fixed run of CPP chunks) =====
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int chunk0 = part * V::CPP;
+    const int mt = chunk0 / V::kChunksPerTile;
+    const int col0 = (chunk0 % V::kChunksPerTile) * 32;     // first column inside the tile's accumulator
+    const int row = (mtile0 + mt) * kTM + quarter * 32 + lane;
+    const bool ok = row < P.m;
+    const int n_lists = n_slices * V::AP;
+    const int64_t lidx = static_cast<int64_t>(row) * n_lists + slice * V::AP + (part % V::AP);
+    const int64_t li = lidx * P.cap;
+    float th = INFINITY;
+    int cn = 0;
+    if (!DUMP && ok) {
+      th = P.thr[row];
+      if (P.append) cn = P.cand_n[lidx];
+    }
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(mt * TN + col0);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int p = p_lo + it;
+      const int tile = P.tile_begin + p * P.tile_step;
+      const bool full_tile = (tile + 1) * TN <= P.n_items && P.bias == nullptr;
+      mbar_wait(t_full + acc * MT + mt, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < V::CPP; ++j) {
+        const int c0 = col0 + j * 32;
+        uint32_t v[32];
+        __syncwarp();
+        tc_ld32(t_addr + static_cast<uint32_t>(acc * kAccCols + j * 32), v);
+        const int id0 = tile * TN + c0;
+        if (DUMP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float sc = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+            if (ok) P.dump[static_cast<int64_t>(row) * P.ld_dump + p * TN + c0 + i] = id < P.n_items ? sc : -INFINITY;
+          }
+        } else if (full_tile) {
+          float mx8[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int g8 = g * 8;
+            const float m0 = fmaxf(fmaxf(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1])),
+                                   fmaxf(__uint_as_float(v[g8 + 2]), __uint_as_float(v[g8 + 3])));
+            mx8[g] = fmaxf(m0, fmaxf(fmaxf(__uint_as_float(v[g8 + 4]), __uint_as_float(v[g8 + 5])),
+                                     fmaxf(__uint_as_float(v[g8 + 6]), __uint_as_float(v[g8 + 7]))));
+          }
+          if (!(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])) < th)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int g8 = g * 8;
+              if (!(mx8[g] < th)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sc = __uint_as_float(v[g8 + i]);
+                  if (!(sc < th)) {
+                    if (cn < P.cap) {
+                      P.cand_s[li + cn] = sc;
+                      P.cand_i[li + cn] = id0 + g8 + i;
+                    }
+                    ++cn;
+                  }
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int id = id0 + i;
+            float sc = __uint_as_float(v[i]);
+            if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+            if (!(sc < th) && id < P.n_items) {
+              if (cn < P.cap) {
+                P.cand_s[li + cn] = sc;
+                P.cand_i[li + cn] = id;
+              }
+              ++cn;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + acc);
+    }
+    if (!DUMP && ok) P.cand_n[lidx] = cn;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 // fp32 table -> fp16 copy (round to nearest) + stats[0] = max |e|^2, stats[1] = max |e - half(e)|^2,
 // stats[2] = 1.0 if any element overflows fp16.  One warp per row; maxima via integer atomicMax (order-free).
 __global__ void __launch_bounds__(256)
@@ -1192,8 +1416,31 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS ? PSB_OK : PSB_E_ARG;
 }
 
+// Epilogue variant of the fp16 shortlist kernel: 1 = tc16_score_kernel (validated on B200, default),
+// 2 = tc16_score_v2_kernel (PSB_TC16_EPI=2; see its header).  Read once per process.
+static int tc16_epilogue_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSB_TC16_EPI");
+    v = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
+
+// candidate lists per (query row, item slice): one per epilogue part that scores columns of the row's query tile
+static int tc16_lists_per_slice(int MT) {
+  if (tc16_epilogue_variant() != 2) return kParts;
+  switch (MT) {
+    case 1: return Tc16V2<1>::AP;
+    case 2: return Tc16V2<2>::AP;
+    case 3: return Tc16V2<3>::AP;
+    default: return Tc16V2<4>::AP;
+  }
+}
+
 struct Tc16Plan {
   int m_tiles, groups, MT, TN, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap, stages;
+  int lists;    // candidate lists per (row, slice)
   int seg[3];   // main-pass segment ends in tiles: [0, seg0) | [seg0, seg1) | [seg1, total)
   int final_cap; // candidates per row the select kernels hold in shared memory (4x the expectation: several CTAs / SM)
   size_t smem;
@@ -1226,7 +1473,8 @@ static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   double cands = static_cast<double>(k) * p.seg[0] / pil;
   if (p.seg[1] > p.seg[0]) cands += static_cast<double>(k) * (p.seg[1] - p.seg[0]) / p.seg[0];
   if (p.seg[2] > p.seg[1]) cands += static_cast<double>(k) * (p.seg[2] - p.seg[1]) / p.seg[1];
-  const double expect = cands / (p.n_slices * kParts);
+  p.lists = tc16_lists_per_slice(p.MT);
+  const double expect = cands / (p.n_slices * p.lists);
   p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
   p.final_cap = (static_cast<int>(4.0 * cands) + 1024 + 255) / 256 * 256;
   if (p.final_cap > kFinalCap) p.final_cap = kFinalCap;
@@ -1241,11 +1489,11 @@ static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   p.off_eps = o; o += up256(p.m_pad * 4);
   p.off_epsin = o; o += up256(p.m_pad * 4);
   p.off_flag = o; o += up256(p.m_pad * 4);
-  p.off_cand_n = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * 4);
+  p.off_cand_n = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * p.lists * 4);
   p.off_q16 = o; o += up256(static_cast<int64_t>(p.m_pad) * d * 2);
   p.off_dump = o; o += up256(static_cast<int64_t>(p.m_pad) * p.pilot_tiles * p.TN * 4);
-  p.off_cand_s = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
-  p.off_cand_i = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * kParts * p.cap * 4);
+  p.off_cand_s = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * p.lists * p.cap * 4);
+  p.off_cand_i = o; o += up256(static_cast<int64_t>(p.m_pad) * p.n_slices * p.lists * p.cap * 4);
   p.total = o + 256;
   return p;
 }
@@ -1281,6 +1529,28 @@ static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUt
 #undef PSB_TC16_ATTR
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done = true;
+  }
+  if (tc16_epilogue_variant() == 2) {
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      const int lim = 227 * 1024;
+      cudaError_t e = cudaSuccess;
+#define PSB_TC16_ATTR2(D, M) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+      PSB_TC16_ATTR2(true, 1); PSB_TC16_ATTR2(true, 2); PSB_TC16_ATTR2(true, 3); PSB_TC16_ATTR2(true, 4);
+      PSB_TC16_ATTR2(false, 1); PSB_TC16_ATTR2(false, 2); PSB_TC16_ATTR2(false, 3); PSB_TC16_ATTR2(false, 4);
+#undef PSB_TC16_ATTR2
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr2_done = true;
+    }
+    PSB_PROF("tc16_score_v2_kernel", s);
+    switch (MT) {
+      case 1: tc16_score_v2_kernel<DUMP, 1><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 2: tc16_score_v2_kernel<DUMP, 2><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 3: tc16_score_v2_kernel<DUMP, 3><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      default: tc16_score_v2_kernel<DUMP, 4><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+    }
+    return launch_status();
   }
   PSB_PROF("tc16_score_kernel", s);
   switch (MT) {
@@ -1376,7 +1646,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
       if (sgi < 2 && seg_hi < pl.total_tiles) {
         PSB_PROF("refine_threshold_kernel", s);
         refine_threshold_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(pl.final_cap) * 4, s>>>(
-            cand_s, cand_n, pl.n_slices * kParts, pl.cap, eps, static_cast<int>(k), thr, pl.final_cap);
+            cand_s, cand_n, pl.n_slices * pl.lists, pl.cap, eps, static_cast<int>(k), thr, pl.final_cap);
         if ((st = launch_status()) != PSB_OK) return st;
       }
     }
@@ -1385,7 +1655,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
   // 4. final select + exact fp32 rescoring, 5. exact fallback for flagged rows
   const size_t fsmem = static_cast<size_t>(pl.final_cap) * 8 + kKeepCap * 8 + static_cast<size_t>(d) * 4 + 64;
   PSB_PROF("final_select_kernel", s);
-  final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * kParts, pl.cap, eps, queries,
+  final_select_kernel<<<static_cast<int>(m), 256, fsmem, s>>>(cand_s, cand_i, cand_n, pl.n_slices * pl.lists, pl.cap, eps, queries,
                                                               table, static_cast<int>(d), bias, static_cast<int>(k),
                                                               id_base, id_stride, out_ids, out_scores, flag, pl.final_cap);
   if ((st = launch_status()) != PSB_OK) return st;

@@ -1,0 +1,72 @@
+"""Round-2 first step for G5: validate and time the v2 epilogue of the fp16 shortlist kernel (PSB_TC16_EPI=2,
+csrc/catalog_tc.cu: tc16_score_v2_kernel) against the validated v1 kernel.  The knob is read once per process, so
+each variant runs in its own subprocess, under a hard timeout (a hand-off bug in a tcgen05 pipeline shows up as a
+hang, not as a wrong answer).  Run under gpurun on ONE GPU:
+
+    timeout 900 python profiles/check_tc16_v2.py            # prints one JSON line per (M, N, variant) + a verdict
+
+Both variants must return bit-identical ids and scores (every mode rescored exactly in fp32); v2 is only worth
+switching on if its ms is lower.  Written at the end of round 1 with no GPU budget left: v2 has been compiled and its
+SASS read (per 32-score chunk: 38 instructions against v1's 80), never run."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import hashlib, json, os, sys, torch
+sys.path.insert(0, %r)
+from prodsearch_b200 import _lib, ops
+n, d = int(sys.argv[1]), 128
+torch.manual_seed(0)
+table = torch.empty(n + 1, d, device="cuda").normal_()
+prep = ops.catalog_prepare_f16(table, n)
+for m in (24, 128, 384, 1024, 4096):
+    q = torch.randn(m, d, device="cuda")
+    f = lambda: ops.catalog_topk(q, table, 100, n_items=n, mode=_lib.TOPK_TC16, prepared=prep)
+    ids, sc = f()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5): f()
+    b.record(); torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    for _ in range(3): f()
+    split = {k_: round(v[1] / 3 * 1e3, 1) for k_, v in _lib.profile_dump().items()}
+    _lib.profile_enable(False)
+    h = hashlib.sha256(ids.cpu().numpy().tobytes() + sc.cpu().numpy().tobytes()).hexdigest()[:16]
+    print(json.dumps({"n_items": n, "m": m, "epi": os.environ.get("PSB_TC16_EPI", "1"), "ms": round(a.elapsed_time(b) / 5, 4),
+                      "kernel_us": split, "tflops": round(2.0 * m * n * d / (a.elapsed_time(b) / 5) / 1e9, 1), "sha": h}), flush=True)
+''' % ROOT
+
+
+def run(n, epi):
+    env = dict(os.environ, PSB_TC16_EPI=str(epi))
+    try:
+        r = subprocess.run([sys.executable, "-c", CHILD, str(n)], env=env, capture_output=True, text=True, timeout=240)
+    except subprocess.TimeoutExpired as ex:
+        print(json.dumps({"n_items": n, "epi": epi, "error": "timeout (hang?)", "partial": (ex.stdout or b"")[-400:].decode("utf8", "replace")}))
+        return {}
+    if r.returncode != 0:
+        print(json.dumps({"n_items": n, "epi": epi, "error": r.stderr[-600:]}))
+    out = {}
+    for line in r.stdout.splitlines():
+        if line.startswith("{"):
+            print(line)
+            j = json.loads(line)
+            out[j["m"]] = j
+    return out
+
+
+if __name__ == "__main__":
+    ok = True
+    for n in (1_000_000, 16_000_000 if "--big" in sys.argv else 250_000):
+        v1, v2 = run(n, 1), run(n, 2)
+        for m in sorted(v1):
+            same = m in v2 and v2[m]["sha"] == v1[m]["sha"]
+            ok = ok and same
+            print(json.dumps({"n_items": n, "m": m, "identical": same, "v1_ms": v1[m]["ms"],
+                              "v2_ms": v2.get(m, {}).get("ms"), "speedup": round(v1[m]["ms"] / v2[m]["ms"], 3) if m in v2 else None}))
+    print("VERDICT:", "v2 returns v1's lists bit for bit" if ok else "v2 DIFFERS or failed -- keep PSB_TC16_EPI unset")
+    sys.exit(0 if ok else 1)
