@@ -229,6 +229,13 @@ int psb_catalog_topk_f16(const float* queries, int64_t m, const float* table, co
                          int64_t id_base, int64_t id_stride, void* workspace, int64_t workspace_bytes,
                          int64_t* out_ids, float* out_scores, psb_stream_t stream);
 
+/* Debug aid for the fp16 shortlist kernel's v2 epilogue (environment PSB_TC16_EPI=2 and PSB_TC16_STATS=1, both read
+ * once per process): sums over CTAs and launches of clock64 counters -- host_out[0] MMA-issuer total, [1] issuer
+ * waiting for a free accumulator set (epilogue-bound), [2] issuer waiting for item tiles (TMA-bound), [3] epilogue
+ * warp total, [4] epilogue warp waiting for scores (MMA-bound), [5] TMA producer waiting for a free stage, [6] item
+ * tiles, [7] CTA launches.  Synchronises the device; all zeros when the knobs are unset.  host_out: 8 words (host). */
+int psb_debug_tc16_stats(uint64_t* host_out, int32_t reset);
+
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */
 int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,

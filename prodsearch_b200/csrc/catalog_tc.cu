@@ -330,6 +330,7 @@ struct Tc16Params {
   int32_t* cand_i;
   int32_t* cand_n;
   int cap;
+  unsigned long long* stat;            // v2 + PSB_TC16_STATS only: 8 cycle counters per CTA (see tc16_score_v2_kernel)
 };
 
 // MT query tiles per CTA; item tile TN = 128 (MT <= 2) or 64 (MT = 3, 4): two accumulator sets of MT * TN
@@ -588,7 +589,11 @@ struct Tc16V2 {
   static_assert(kChunksPerTile % CPP == 0, "a part's run of chunks must stay inside one query tile");
 };
 
-template <bool DUMP, int MT>
+// STATS: clock64 split of the three roles of one CTA, accumulated over launches into P.stat[cta * 8 + ...]:
+//   0 issuer total, 1 issuer waiting for a free accumulator set (epilogue-bound), 2 issuer waiting for item tiles
+//   (TMA / HBM / L2-bound), 3 epilogue warp 2 total, 4 epilogue warp 2 waiting for scores (MMA-bound),
+//   5 producer waiting for a free stage, 6 item tiles, 7 launches.  issuer total - 1 - 2 = MMA issue time.
+template <bool DUMP, int MT, bool STATS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                      const Tc16Params P) {
@@ -649,15 +654,20 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int mt = 0; mt < MT; ++mt)
         for (int kb = 0; kb < P.kblocks; ++kb)
           tma_load_2d(sA + (mt * P.kblocks + kb) * kQBlock16, &map_q, kb * kKB16, (mtile0 + mt) * kTM, a_full);
+      long long w_prod = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int st = it % S;
         const uint32_t ph = (it / S) & 1;
+        long long w0 = 0;
+        if (STATS) w0 = clock64();
         mbar_wait(b_empty + st, ph ^ 1);
+        if (STATS) w_prod += clock64() - w0;
         mbar_expect_tx(b_full + st, stage_bytes);
         const int tile = P.tile_begin + (p_lo + it) * P.tile_step;
         for (int kb = 0; kb < P.kblocks; ++kb)
           tma_load_2d(sB + static_cast<size_t>(st) * stage_bytes + kb * e_block, &map_e, kb * kKB16, tile * TN, b_full + st);
       }
+      if (STATS && P.stat != nullptr) P.stat[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 5] += static_cast<unsigned long long>(w_prod);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one commit per query tile =====
@@ -666,13 +676,22 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const uint64_t a_base = umma_desc(smem_u32(sA));
       const uint64_t b_base = umma_desc(smem_u32(sB));
       const uint32_t kb_a = kQBlock16 >> 4, kb_b = e_block >> 4, st_b = stage_bytes >> 4;
+      long long w_acc = 0, w_tile = 0, t_begin = 0;
+      if (STATS) t_begin = clock64();
       for (int it = 0; it < my_tiles; ++it) {
         const int st = it % S;
         const uint32_t ph = (it / S) & 1;
         const int acc = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        long long w0 = 0, w1 = 0;
+        if (STATS) w0 = clock64();
         mbar_wait(t_empty + acc, aph ^ 1);
+        if (STATS) w1 = clock64();
         mbar_wait(b_full + st, ph);
+        if (STATS) {
+          w_acc += w1 - w0;
+          w_tile += clock64() - w1;
+        }
         tc_fence_after();
         const uint64_t b_tile = b_base + static_cast<uint64_t>(st) * st_b;
 #pragma unroll
@@ -689,6 +708,14 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_commit(t_full + acc * MT + mt);
         }
         tc_commit(b_empty + st);
+      }
+      if (STATS && P.stat != nullptr) {
+        unsigned long long* o = P.stat + (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        o[0] += static_cast<unsigned long long>(clock64() - t_begin);
+        o[1] += static_cast<unsigned long long>(w_acc);
+        o[2] += static_cast<unsigned long long>(w_tile);
+        o[6] += static_cast<unsigned long long>(my_tiles);
+        o[7] += 1ull;
       }
     }
   } else if (((warp - 2) >> 2) < V::kActiveParts) {
@@ -710,13 +737,18 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (P.append) cn = P.cand_n[lidx];
     }
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(mt * TN + col0);
+    long long w_sc = 0, e_begin = 0;
+    if (STATS) e_begin = clock64();
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int p = p_lo + it;
       const int tile = P.tile_begin + p * P.tile_step;
       const bool full_tile = (tile + 1) * TN <= P.n_items && P.bias == nullptr;
+      long long w0 = 0;
+      if (STATS) w0 = clock64();
       mbar_wait(t_full + acc * MT + mt, aph);
+      if (STATS) w_sc += clock64() - w0;
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < V::CPP; ++j) {
@@ -783,6 +815,11 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (lane == 0) mbar_arrive(t_empty + acc);
     }
     if (!DUMP && ok) P.cand_n[lidx] = cn;
+    if (STATS && P.stat != nullptr && warp == 2 && lane == 0) {
+      unsigned long long* o = P.stat + (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      o[3] += static_cast<unsigned long long>(clock64() - e_begin);
+      o[4] += static_cast<unsigned long long>(w_sc);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1427,6 +1464,26 @@ static int tc16_epilogue_variant() {
   return v;
 }
 
+// PSB_TC16_STATS=1 (with PSB_TC16_EPI=2): a library-owned counter block the v2 kernel adds its cycle split to
+// (debug aid, the one allocation this library makes besides the peer buffers); read by psb_debug_tc16_stats.
+constexpr int kTc16StatCtas = 256;
+static unsigned long long* g_tc16_stat = nullptr;
+static unsigned long long* tc16_stat_buffer() {
+  static int wanted = -1;
+  if (wanted < 0) {
+    const char* e = getenv("PSB_TC16_STATS");
+    wanted = (e != nullptr && atoi(e) != 0 && tc16_epilogue_variant() == 2) ? 1 : 0;
+  }
+  if (wanted == 1 && g_tc16_stat == nullptr) {
+    if (cudaMalloc(reinterpret_cast<void**>(&g_tc16_stat), kTc16StatCtas * 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(g_tc16_stat, 0, kTc16StatCtas * 8 * sizeof(unsigned long long)) != cudaSuccess) {
+      g_tc16_stat = nullptr;
+      wanted = 0;
+    }
+  }
+  return g_tc16_stat;
+}
+
 // candidate lists per (query row, item slice): one per epilogue part that scores columns of the row's query tile
 static int tc16_lists_per_slice(int MT) {
   if (tc16_epilogue_variant() != 2) return kParts;
@@ -1536,7 +1593,8 @@ static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUt
       const int lim = 227 * 1024;
       cudaError_t e = cudaSuccess;
 #define PSB_TC16_ATTR2(D, M) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
       PSB_TC16_ATTR2(true, 1); PSB_TC16_ATTR2(true, 2); PSB_TC16_ATTR2(true, 3); PSB_TC16_ATTR2(true, 4);
       PSB_TC16_ATTR2(false, 1); PSB_TC16_ATTR2(false, 2); PSB_TC16_ATTR2(false, 3); PSB_TC16_ATTR2(false, 4);
 #undef PSB_TC16_ATTR2
@@ -1544,11 +1602,20 @@ static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUt
       attr2_done = true;
     }
     PSB_PROF("tc16_score_v2_kernel", s);
+    if (P.stat != nullptr && !DUMP && static_cast<int>(grid.x * grid.y) <= kTc16StatCtas) {
+      switch (MT) {
+        case 1: tc16_score_v2_kernel<DUMP, 1, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+        case 2: tc16_score_v2_kernel<DUMP, 2, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+        case 3: tc16_score_v2_kernel<DUMP, 3, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+        default: tc16_score_v2_kernel<DUMP, 4, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      }
+      return launch_status();
+    }
     switch (MT) {
-      case 1: tc16_score_v2_kernel<DUMP, 1><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      case 2: tc16_score_v2_kernel<DUMP, 2><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      case 3: tc16_score_v2_kernel<DUMP, 3><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      default: tc16_score_v2_kernel<DUMP, 4><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 1: tc16_score_v2_kernel<DUMP, 1, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 2: tc16_score_v2_kernel<DUMP, 2, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 3: tc16_score_v2_kernel<DUMP, 3, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      default: tc16_score_v2_kernel<DUMP, 4, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
     }
     return launch_status();
   }
@@ -1614,6 +1681,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
   P.cand_n = cand_n;
   P.cap = pl.cap;
   P.append = 0;
+  P.stat = tc16_stat_buffer();
   // 1. pilot
   P.tile_begin = 0;
   P.tile_step = pl.pilot_step;
@@ -1667,3 +1735,17 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
 }
 
 }  // namespace psb
+
+extern "C" int psb_debug_tc16_stats(uint64_t* host_out, int32_t reset) {
+  if (host_out == nullptr) return PSB_E_ARG;
+  for (int i = 0; i < 8; ++i) host_out[i] = 0;
+  if (psb::g_tc16_stat == nullptr) return PSB_OK;                  // knobs not set: all zeros
+  static unsigned long long h[psb::kTc16StatCtas * 8];
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(h, psb::g_tc16_stat, sizeof(h), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && reset != 0) e = cudaMemset(psb::g_tc16_stat, 0, sizeof(h));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  for (int c = 0; c < psb::kTc16StatCtas; ++c)
+    for (int i = 0; i < 8; ++i) host_out[i] += h[c * 8 + i];
+  return PSB_OK;
+}

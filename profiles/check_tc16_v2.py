@@ -4,6 +4,7 @@ each variant runs in its own subprocess, under a hard timeout (a hand-off bug in
 hang, not as a wrong answer).  Run under gpurun on ONE GPU:
 
     timeout 900 python profiles/check_tc16_v2.py            # prints one JSON line per (M, N, variant) + a verdict
+    timeout 900 python profiles/check_tc16_v2.py --stats    # v2 with its cycle split per item tile (who waits for whom)
 
 Both variants must return bit-identical ids and scores (every mode rescored exactly in fp32); v2 is only worth
 switching on if its ms is lower.  Written at the end of round 1 with no GPU budget left: v2 has been compiled and its
@@ -35,14 +36,29 @@ for m in (24, 128, 384, 1024, 4096):
     for _ in range(3): f()
     split = {k_: round(v[1] / 3 * 1e3, 1) for k_, v in _lib.profile_dump().items()}
     _lib.profile_enable(False)
+    stats = None
+    if os.environ.get("PSB_TC16_STATS") == "1" and os.environ.get("PSB_TC16_EPI") == "2":
+        import ctypes
+        buf = (ctypes.c_uint64 * 8)()
+        _lib.load().psb_debug_tc16_stats(buf, 1)                      # reset, then one call on its own
+        f(); _lib.load().psb_debug_tc16_stats(buf, 1)
+        c = [int(x) for x in buf]
+        tiles, ctas = max(c[6], 1), max(c[7], 1)
+        stats = {"cycles_per_tile": {"issuer_total": round(c[0] / tiles, 1), "issuer_wait_accumulator": round(c[1] / tiles, 1),
+                                     "issuer_wait_items": round(c[2] / tiles, 1), "issuer_issue": round((c[0] - c[1] - c[2]) / tiles, 1),
+                                     "epilogue_total": round(c[3] / tiles, 1), "epilogue_wait_scores": round(c[4] / tiles, 1),
+                                     "producer_wait_stage": round(c[5] / tiles, 1)},
+                 "tiles": c[6], "cta_launches": c[7], "mma_floor_cycles_per_tile": 32 * 8 * min(4, (m + 127) // 128)}
     h = hashlib.sha256(ids.cpu().numpy().tobytes() + sc.cpu().numpy().tobytes()).hexdigest()[:16]
     print(json.dumps({"n_items": n, "m": m, "epi": os.environ.get("PSB_TC16_EPI", "1"), "ms": round(a.elapsed_time(b) / 5, 4),
-                      "kernel_us": split, "tflops": round(2.0 * m * n * d / (a.elapsed_time(b) / 5) / 1e9, 1), "sha": h}), flush=True)
+                      "kernel_us": split, "tflops": round(2.0 * m * n * d / (a.elapsed_time(b) / 5) / 1e9, 1), "sha": h, "stats": stats}), flush=True)
 ''' % ROOT
 
 
 def run(n, epi):
     env = dict(os.environ, PSB_TC16_EPI=str(epi))
+    if epi == 2 and "--stats" in sys.argv:
+        env["PSB_TC16_STATS"] = "1"     # the instrumented kernel (a few clock reads per tile): not a timing run
     try:
         r = subprocess.run([sys.executable, "-c", CHILD, str(n)], env=env, capture_output=True, text=True, timeout=240)
     except subprocess.TimeoutExpired as ex:
