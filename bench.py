@@ -682,7 +682,6 @@ def run_b200_arm(a):
             roofline["note"] = ("GEMM-shaped (B*(1+K) rows x 128 -> 512 -> 128) but computed in fp32 FFMA on CUDA cores to "
                                 "hold the 1e-5 parity bar; %.1f%% of the fp32 FFMA peak (%.1f TFLOP/s at the sampled clock)"
                                 % (100.0 * ent.get("frac_of_fp32_ffma_peak", 0.0), ffma_peak))
-    compute = None
     extra = None
     if world == 1 and not a.no_extra:
         extra = {"bandwidth_regime": bandwidth_regime(peaks), "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}

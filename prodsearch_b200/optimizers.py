@@ -3,8 +3,6 @@ eps=1e-9 (:186), optional noam schedule (:214-219) and global-norm gradient clip
 Row N2 of SURVEY.md 8(f): the clip + Adam update of every parameter tensor runs as ONE fused multi-tensor
 call (psb_adam_step) on the dense ``.grad`` tensors the gradient sinks attach, with the step counter and the
 global norm in device memory (CUDA-graph replayable).  Dense semantics, identical to the reference's."""
-import ctypes
-
 import torch
 from torch.nn.utils import clip_grad_norm_
 

@@ -12,7 +12,6 @@ from collections import OrderedDict
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 def sinusoid_table(max_len, dim):
