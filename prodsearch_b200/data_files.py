@@ -173,6 +173,65 @@ class SplitFiles(object):
         return np.asarray(out, dtype=np.int64).reshape(-1, 4)
 
 
+    def test_samples(self, valid_candi_size=-1, candi_batch_size=1000, uq_pids=None, py_random=None, np_random=None,
+                     pad_id=-1):
+        """collect_test_samples in full (item_pv_dataset.py:36-68 = prod_search_dataset.py:43-84): one entry per
+        distinct (user, query) pair and per segment of ``candi_batch_size`` candidates.  Candidates are
+        * ``uq_pids[(user id string, query_idx)]`` (``read_ranklist``) shuffled with ``random.shuffle``, or
+        * for the "valid" split with ``valid_candi_size > 1``: ``valid_candi_size - 1`` items drawn without
+          replacement by ``numpy.random.choice(p=product_dists)`` plus the purchased item (which may therefore
+          appear twice), shuffled, or
+        * the whole catalog (then ``candidates`` is None and ``test_entries`` is the cheaper call).
+        The generators are the reference's (global ``random`` / ``numpy.random`` unless given), called in its order.
+        Returns (entries int64 [n, 4] of (query_idx, user_idx, prod_idx, review_idx), candidates int64
+        [n, width] padded with ``pad_id`` (-1 in the review-transformer's test collate, prod_search_dataloader.py:92;
+        the item-transformer's pads with the item pad index, item_pv_dataloader.py:44) -- or None)."""
+        import random as _random
+        py_random = py_random if py_random is not None else _random
+        np_random = np_random if np_random is not None else np.random
+        c = self.corpus
+        whole = uq_pids is None and not (self.set_name == "valid" and valid_candi_size > 1)
+        if whole and c.product_size <= candi_batch_size:
+            return self.test_entries(), None
+        seen, entries, cands = set(), [], []
+        off, flat = self.item_query_off, self.item_query
+        for _, user_idx, prod_idx, review_idx in self.review_info.tolist():
+            for query_idx in flat[off[prod_idx]:off[prod_idx + 1]].tolist():
+                if (user_idx, query_idx) in seen:
+                    continue
+                seen.add((user_idx, query_idx))
+                if uq_pids is not None:
+                    items = uq_pids[(c.user_ids[user_idx], query_idx)]
+                    py_random.shuffle(items)                      # in place, like the reference
+                elif whole:
+                    items = list(range(c.product_size))
+                else:
+                    items = np_random.choice(c.product_size, size=valid_candi_size - 1, replace=False,
+                                             p=self.product_dists).tolist()
+                    items.append(prod_idx)
+                    py_random.shuffle(items)
+                for i in range(int((len(items) - 1) / candi_batch_size) + 1):
+                    entries.append((query_idx, user_idx, prod_idx, review_idx))
+                    cands.append(items[i * candi_batch_size:(i + 1) * candi_batch_size])
+        width = max((len(x) for x in cands), default=0)
+        cand = np.full((len(cands), width), pad_id, dtype=np.int64)
+        for i, x in enumerate(cands):
+            cand[i, :len(x)] = x
+        return np.asarray(entries, dtype=np.int64).reshape(-1, 4), cand
+
+def read_ranklist(path, product_ids):
+    """ProdSearchData.read_ranklist (data_util.py:64-72): a TREC run file (``<user>_<query> Q0 <asin> <rank> ...``) ->
+    {(user id string, query idx): [product idx, ...]} in file order -- the candidate lists of ``test_candi_size > 0``."""
+    index = {x: i for i, x in enumerate(product_ids)}
+    out = {}
+    with open(path, "r") as f:
+        for line in f:
+            arr = line.strip().split(" ")
+            uid, qid = arr[0].split("_")
+            out.setdefault((uid, int(qid)), []).append(index[arr[2]])
+    return out
+
+
 def sub_sampling(vocab_distribute, subsample_threshold):
     """data_util.py:138-153."""
     vd = np.asarray(vocab_distribute, dtype=np.float64)

@@ -103,3 +103,68 @@ def test(model, corpus, entries, args, user_ids, product_ids, rank_path=None, cu
     if rank_path is not None:
         write_ranklist(rank_path, user_ids, u_idx, q_idx, product_ids, ids, scores, cutoff)
     return mrr, prec
+
+
+def rank_candidates(cand_ids, cand_scores, target, pad_ids=(-1,)):
+    """Rank explicit candidate lists: descending score, ties -> lower item id; entries whose id is a padding value
+    rank last.  cand_ids / cand_scores [M, C] (any device), target [M].  Returns (ranked ids [M, C], ranked scores
+    [M, C], rank [M] int32: 1-based position of the target's first occurrence, 0 if absent) -- what
+    ``argsort(axis=-1)[:, ::-1]`` + ``np.where`` compute at trainer.py:136,:174-178, with the tie rule made definite."""
+    ids = cand_ids.to(torch.int64)
+    sc = cand_scores.to(torch.float32).clone()
+    pad = torch.zeros_like(ids, dtype=torch.bool)
+    for p in pad_ids:
+        pad |= ids == int(p)
+    sc[pad] = float("-inf")
+    key = torch.where(pad, torch.full_like(ids, torch.iinfo(torch.int64).max), ids)
+    by_id = torch.argsort(key, dim=1, stable=True)                                   # ascending id, padding last
+    order = torch.gather(by_id, 1, torch.argsort(torch.gather(sc, 1, by_id), dim=1, descending=True, stable=True))
+    r_ids, r_sc = torch.gather(ids, 1, order), torch.gather(sc, 1, order)
+    hit = (r_ids == target.to(ids.device, torch.int64).view(-1, 1)) & ~torch.gather(pad, 1, order)
+    first = torch.argmax(hit.to(torch.int8), dim=1)
+    rank = torch.where(hit.any(dim=1), first + 1, torch.zeros_like(first)).to(torch.int32)
+    return r_ids, r_sc, rank
+
+
+def validate(model, corpus, entries, candidates, args, cutoff=100, batch_size=4096, pad_id=-1):
+    """Trainer.validate (trainer.py:124-138) / the candidate-list form of Trainer.test: score explicit candidate
+    lists (``data_files.SplitFiles.test_samples``: one row per (user, query) pair and per segment of
+    ``candi_batch_size`` candidates, padded with ``pad_id``) with ``model.test`` and report MRR / P@1.  Segments of the
+    same pair are consecutive rows and are joined before ranking, as get_prod_scores does (trainer.py:215-221).
+    Returns (mrr, prec, ranked ids [pairs, C], ranked scores [pairs, C], query_idx [pairs], user_idx [pairs])."""
+    e = np.asarray(entries, dtype=np.int64).reshape(-1, 4)
+    cand = np.asarray(candidates, dtype=np.int64).reshape(e.shape[0], -1)
+    # segments per pair: consecutive rows with the same (query, user, item, review)
+    new_pair = np.ones(e.shape[0], dtype=bool)
+    new_pair[1:] = (e[1:] != e[:-1]).any(axis=1)
+    pair_of = np.cumsum(new_pair) - 1
+    n_pairs = int(pair_of[-1]) + 1 if e.shape[0] else 0
+    seg_of = np.arange(e.shape[0]) - np.flatnonzero(new_pair)[pair_of]
+    seg_count = int(seg_of.max()) + 1 if e.shape[0] else 1
+    item_pad = corpus.prod_pad_idx
+    scores = []
+    was_training = model.training
+    model.eval()
+    try:
+        with torch.no_grad():
+            for s in range(0, e.shape[0], batch_size):
+                c = e[s:s + batch_size]
+                cb = np.where(cand[s:s + batch_size] == pad_id, item_pad, cand[s:s + batch_size])   # :44: item pad row
+                batch = corpus.test_batch(c[:, 0], c[:, 1], c[:, 2], c[:, 3], args, candi_prod_idxs=cb)
+                scores.append(model.test(batch))
+    finally:
+        model.train(was_training)
+    dev = scores[0].device if scores else torch.device("cpu")
+    sc = torch.cat(scores) if scores else torch.empty(0, cand.shape[1])
+    W = cand.shape[1]
+    ids_all = torch.full((n_pairs, seg_count * W), pad_id, dtype=torch.int64, device=dev)
+    sc_all = torch.full((n_pairs, seg_count * W), float("-inf"), dtype=torch.float32, device=dev)
+    rows = torch.as_tensor(pair_of, device=dev)
+    cols = torch.as_tensor(seg_of * W, device=dev).view(-1, 1) + torch.arange(W, device=dev).view(1, -1)
+    ids_all[rows.view(-1, 1), cols] = torch.as_tensor(cand, device=dev)
+    sc_all[rows.view(-1, 1), cols] = sc.to(torch.float32)
+    first = np.flatnonzero(new_pair)
+    r_ids, r_sc, rank = rank_candidates(ids_all, sc_all, torch.as_tensor(e[first, 2], device=dev), pad_ids=(pad_id,))
+    mrr, prec = calc_metrics(rank, cutoff)
+    return mrr, prec, r_ids, r_sc, e[first, 0], e[first, 1]
+

@@ -90,3 +90,34 @@ def test_train_samples_match_reference_rng_stream(loaded):
     # private generators give the same stream without touching the globals
     words2, _ = tr.train_samples(1, py_random=random.Random(666), np_random=np.random.RandomState(666))
     assert np.array_equal(words2, z["train_samples_w1/words"])
+
+
+def test_eval_samples_with_candidate_lists_match_reference(loaded, tmp_path):
+    """collect_test_samples with candidate lists (tests/golden/samples.npz from make_golden_samples.py): the "valid"
+    split's sampled candidates and a run file's candidate lists, segmented, on the reference's random streams."""
+    import random
+    z, f, df = loaded
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "samples.npz"))
+    va = f.split("valid", subsampling_rate=1e-3)              # has_valid False: reads the test files (:38-40)
+    random.seed(666)
+    np.random.seed(666)
+    entries, cand = va.test_samples(valid_candi_size=5, candi_batch_size=3)
+    assert np.array_equal(entries, g["valid/entries"]) and np.array_equal(cand, g["valid/candidates"])
+    assert cand.shape[1] == 3 and (cand[1::2, 2] == -1).all()          # 5 candidates -> segments of 3 + 2
+    run = tmp_path / "test.bias_product.ranklist"
+    run.write_bytes(g["run/bytes"].tobytes())
+    uq = df.read_ranklist(str(run), f.product_ids)
+    assert all(len(v) == 6 for v in uq.values())
+    te = f.split("test", subsampling_rate=1e-3)
+    random.seed(666)
+    np.random.seed(666)
+    entries, cand = te.test_samples(candi_batch_size=4, uq_pids=uq)
+    assert np.array_equal(entries, g["run/entries"]) and np.array_equal(cand, g["run/candidates"])
+    # the item-transformer's collate pads candidate lists with the item pad index (item_pv_dataloader.py:44)
+    random.seed(666)
+    uq = df.read_ranklist(str(run), f.product_ids)
+    _, cand_p = te.test_samples(candi_batch_size=4, uq_pids=uq, pad_id=f.product_size)
+    assert np.array_equal(cand_p == f.product_size, g["run/candidates"] == -1)
+    # whole catalog: no candidate matrix, the entries of test_entries()
+    e2, c2 = te.test_samples()
+    assert c2 is None and np.array_equal(e2, te.test_entries())
