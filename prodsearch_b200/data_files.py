@@ -232,6 +232,43 @@ def read_ranklist(path, product_ids):
     return out
 
 
+def load_pretrain_embeddings(path):
+    """others/util.py:4-20: gzip text, line 1 = count, line 2 = size, then ``<key>\t<v0> <v1> ...`` per row ->
+    ({key: row}, float32 [rows, size]).  The reference parses to python floats and builds a FloatTensor: the same
+    double -> float32 rounding as here."""
+    index, rows = {}, []
+    with gzip.open(path, "rt") as f:
+        f.readline()
+        f.readline()
+        for line_no, line in enumerate(f):
+            arr = line.strip(" ").split("\t")
+            index[arr[0]] = line_no
+            rows.append([float(x) for x in arr[1].split()])
+    return index, np.asarray(rows, dtype=np.float64).astype(np.float32)
+
+
+def load_user_item_embeddings(path):
+    """others/util.py:22-34: plain text, count / size header, one space-separated row per line -> float32 [rows, size]."""
+    rows = []
+    with open(path, "r") as f:
+        f.readline()
+        f.readline()
+        for line in f:
+            rows.append([float(x) for x in line.strip().split(" ")])
+    return np.asarray(rows, dtype=np.float64).astype(np.float32)
+
+
+def pretrained_word_table(path, vocab_words, word_pad_idx):
+    """The word table the reference builds from a pretrained file (models/item_transformer.py:58-66,
+    models/PVC.py:24-28): row i = the file's vector of ``vocab_words[i]``, except row 0 (the file's first row) and
+    the last row (the file's row ``word_pad_idx``) -- float32 [len(vocab_words) + 1, size], ready for
+    ``model.word_embeddings.weight.data.copy_`` / ``load_state_dict``.  The reference wraps it in
+    ``nn.Embedding.from_pretrained`` (frozen): set ``requires_grad = False`` on the table to train like it."""
+    index, weights = load_pretrain_embeddings(path)
+    rows = [0] + [index[w] for w in vocab_words[1:]] + [word_pad_idx]
+    return weights[np.asarray(rows, dtype=np.int64)]
+
+
 def sub_sampling(vocab_distribute, subsample_threshold):
     """data_util.py:138-153."""
     vd = np.asarray(vocab_distribute, dtype=np.float64)

@@ -31,7 +31,8 @@ class ItemTransformerRanker(nn.Module):
         if getattr(args, "pretrain_emb_dir", "") or getattr(args, "pretrain_up_emb_dir", ""):
             import os
             if os.path.exists(args.pretrain_emb_dir) or os.path.exists(args.pretrain_up_emb_dir):
-                raise NotImplementedError("pretrained embedding files: load them with load_state_dict")
+                raise NotImplementedError("pretrained embedding files: build the table with data_files.pretrained_word_table "
+                                          "and copy it into word_embeddings.weight (requires_grad False to freeze it)")
         self.args = args
         self.device = device
         self.train_review_only = args.train_review_only

@@ -14,7 +14,8 @@ class ParagraphVector(nn.Module):
                  fix_emb=False, word_sink=None):
         super().__init__()
         if pretrain_emb_path is not None:
-            raise NotImplementedError("pretrained review embeddings: load them into review_embeddings.weight")
+            raise NotImplementedError("pretrained review embeddings: read them with data_files.load_pretrain_embeddings "
+                                      "and copy them into review_embeddings.weight")
         self.word_embeddings = word_embeddings
         self.fix_emb = fix_emb
         self.dropout_ = 0 if fix_emb else dropout

@@ -15,7 +15,8 @@ class ParagraphVectorCorruption(nn.Module):
                  vocab_words=None, fix_emb=False, word_sink=None):
         super().__init__()
         if pretrain_emb_path is not None:
-            raise NotImplementedError("pretrained context embeddings: load them into the word table")
+            raise NotImplementedError("pretrained context embeddings: build the table with "
+                                      "data_files.pretrained_word_table and copy it into the word table")
         self.word_embeddings = word_embeddings
         self.context_embeddings = word_embeddings           # PVC.py:30
         self.word_dists = word_dists

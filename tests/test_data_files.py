@@ -121,3 +121,20 @@ def test_eval_samples_with_candidate_lists_match_reference(loaded, tmp_path):
     # whole catalog: no candidate matrix, the entries of test_entries()
     e2, c2 = te.test_samples()
     assert c2 is None and np.array_equal(e2, te.test_entries())
+
+
+def test_pretrained_embedding_readers_match_reference(tmp_path):
+    """others/util.py readers + the word-table alignment of models/item_transformer.py:58-66
+    (tests/golden/pretrain.npz from make_golden_pretrain.py): float32 bits identical."""
+    from prodsearch_b200 import data_files as df
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "pretrain.npz"))
+    wpath, upath = tmp_path / "word_emb.txt.gz", tmp_path / "product_emb.txt"
+    wpath.write_bytes(g["word_file"].tobytes())
+    upath.write_bytes(g["ui_file"].tobytes())
+    index, weights = df.load_pretrain_embeddings(str(wpath))
+    assert list(index.keys()) == [str(x) for x in g["index_keys"]] and list(index.values()) == g["index_vals"].tolist()
+    assert weights.dtype == np.float32 and np.array_equal(weights.view(np.uint32), g["weights"].view(np.uint32))
+    words = [str(x) for x in g["vocab_words"]]
+    table = df.pretrained_word_table(str(wpath), words, len(words))
+    assert np.array_equal(table.view(np.uint32), g["word_table"].view(np.uint32))
+    assert np.array_equal(df.load_user_item_embeddings(str(upath)).view(np.uint32), g["ui"].view(np.uint32))
