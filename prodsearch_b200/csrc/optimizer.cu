@@ -108,29 +108,38 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, const Ad
                                                    const int64_t* __restrict__ step_dev) {
   int ti;
   int64_t start;
-  if (!locate(T, blockIdx.x, &ti, &start)) return;
-  const float step = static_cast<float>(*step_dev);
-  float clip = 1.f;
-  if (h.max_norm > 0.f) {
-    const float total = sqrtf(*sqnorm);
-    clip = fminf(h.max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
+  if (!locate(T, blockIdx.x, &ti, &start)) return;      // uniform per CTA
+  // The step's coefficients are the same for every element: ONE thread per CTA forms them (double-precision pow /
+  // sqrt: a few hundred FP64 instructions) and the CTA reads them from shared memory -- evaluated by all 256
+  // threads they kept the SM's FP64 pipe busy for longer than the CTA's memory traffic takes.
+  __shared__ AdamCoef coef;
+  if (threadIdx.x == 0) {
+    const float step = static_cast<float>(*step_dev);
+    float clip = 1.f;
+    if (h.max_norm > 0.f) {
+      const float total = sqrtf(*sqnorm);
+      clip = fminf(h.max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
+    }
+    double lr = h.lr;
+    if (h.noam) {  // optimizers.py:214-219
+      const double sd = static_cast<double>(step);
+      lr = h.lr * fmin(1.0 / sqrt(sd), sd * pow(static_cast<double>(h.warmup), -1.5));
+    }
+    const double bc1 = 1.0 - pow(h.beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - pow(h.beta2, static_cast<double>(step));
+    AdamCoef c0;
+    c0.clip = clip;
+    c0.wd = h.weight_decay;
+    c0.omb1 = h.omb1;
+    c0.b2 = h.b2;
+    c0.omb2 = h.omb2;
+    c0.step_size = static_cast<float>(lr / bc1);
+    c0.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+    c0.eps = h.eps;
+    coef = c0;
   }
-  double lr = h.lr;
-  if (h.noam) {  // optimizers.py:214-219
-    const double sd = static_cast<double>(step);
-    lr = h.lr * fmin(1.0 / sqrt(sd), sd * pow(static_cast<double>(h.warmup), -1.5));
-  }
-  const double bc1 = 1.0 - pow(h.beta1, static_cast<double>(step));
-  const double bc2 = 1.0 - pow(h.beta2, static_cast<double>(step));
-  AdamCoef c;
-  c.clip = clip;
-  c.wd = h.weight_decay;
-  c.omb1 = h.omb1;
-  c.b2 = h.b2;
-  c.omb2 = h.omb2;
-  c.step_size = static_cast<float>(lr / bc1);
-  c.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
-  c.eps = h.eps;
+  __syncthreads();
+  const AdamCoef c = coef;
   const psb_adam_tensor_t t = T.t[ti];
   const int64_t end = min(t.n, start + kAdamChunk);
   const bool al = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
