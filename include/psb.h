@@ -236,6 +236,12 @@ int psb_catalog_topk_f16(const float* queries, int64_t m, const float* table, co
  * tiles, [7] CTA launches.  Synchronises the device; all zeros when the knobs are unset.  host_out: 8 words (host). */
 int psb_debug_tc16_stats(uint64_t* host_out, int32_t reset);
 
+/* Debug aid: TMEM read rate of tcgen05.ld.32x32b.x32 issued back to back by `warps` (1..16) warps of one CTA,
+ * in bytes per SM clock -- bytes_per_clk[0] with one CTA on the GPU, [1] with one CTA per SM.  The catalog
+ * contraction (K = 128) reads every accumulator element back after 8 MMAs, so this rate bounds its tensor-pipe
+ * utilisation.  Synchronises the device, allocates and frees 20 KB.  bytes_per_clk: 2 doubles (host). */
+int psb_debug_tmem_read_bw(int32_t warps, int32_t iters, double* bytes_per_clk);
+
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */
 int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,

@@ -5,6 +5,7 @@ hang, not as a wrong answer).  Run under gpurun on ONE GPU:
 
     timeout 900 python profiles/check_tc16_v2.py            # prints one JSON line per (M, N, variant) + a verdict
     timeout 900 python profiles/check_tc16_v2.py --stats    # v2 with its cycle split per item tile (who waits for whom)
+    timeout 200 python profiles/check_tc16_v2.py --tmem     # TMEM read bytes / clock / SM (psb_debug_tmem_read_bw)
 
 Both variants must return bit-identical ids and scores (every mode rescored exactly in fp32); v2 is only worth
 switching on if its ms is lower.  Written at the end of round 1 with no GPU budget left: v2 has been compiled and its
@@ -75,7 +76,25 @@ def run(n, epi):
     return out
 
 
+TMEM_CHILD = r'''
+import ctypes, json, sys
+sys.path.insert(0, %r)
+import torch
+from prodsearch_b200 import _lib
+torch.zeros(1, device="cuda")
+out = (ctypes.c_double * 2)()
+for warps in (4, 8, 12, 16):
+    _lib.check(_lib.load().psb_debug_tmem_read_bw(warps, 20000, out), "psb_debug_tmem_read_bw")
+    print(json.dumps({"tmem_read": "tcgen05.ld.32x32b.x32 + wait::ld", "warps": warps, "bytes_per_clk_one_cta": round(out[0], 1),
+                      "bytes_per_clk_all_sms": round(out[1], 1), "needed_for_f16_peak_at_K128": 128.0}))
+''' % ROOT
+
+
 if __name__ == "__main__":
+    if "--tmem" in sys.argv:
+        r = subprocess.run([sys.executable, "-c", TMEM_CHILD], capture_output=True, text=True, timeout=120)
+        print(r.stdout.strip() or r.stderr[-600:])
+        sys.exit(r.returncode)
     ok = True
     for n in (1_000_000, 16_000_000 if "--big" in sys.argv else 250_000):
         v1, v2 = run(n, 1), run(n, 2)
