@@ -108,3 +108,42 @@ def test_batch_to_device_contract(corpus):
     assert b.pos_prod_rword_masks.dtype == torch.uint8 and b.neg_prod_rword_masks.dtype == torch.uint8
     assert b.pos_seg_idxs.shape[1] == b.pos_prod_ridxs.shape[1] + 1          # the query slot leads the sequence
     assert b.neg_prod_rword_idxs.shape[:3] == b.neg_prod_ridxs.shape
+
+
+@pytest.mark.parametrize("enc,train_pv", [("fs", False), ("avg", False), ("pv", True), ("pvc", True)])
+def test_collate_output_feeds_the_review_transformer_forward(corpus, enc, train_pv):
+    """End to end on the host: files -> collate -> the oracle's restatement of ProductRanker.forward
+    (ps_model.py:241-358) with the parameter shapes of the product's module: every field has the layout the forward
+    pass indexes with (the product's forward runs on the GPU and is checked there against the same oracle)."""
+    from oracle import ref_models as rm
+    from prodsearch_b200.ps_model import ProductRanker
+    from prodsearch_b200.review_batches import ReviewTrainCollate
+    files, split = corpus
+    args = argparse.Namespace(
+        review_encoder_name=enc, do_subsample_mask=True, shuffle_review_words=True, do_seq_review_train=False,
+        pv_window_size=2, review_word_limit=6, uprev_review_limit=2, iprev_review_limit=3, neg_per_pos=3,
+        train_review_only=True, embedding_size=16, dropout=0.0, fix_emb=False, use_user_emb=True, use_item_emb=True,
+        use_seg_emb=True, ff_size=32, heads=2, inter_layers=1, corrupt_rate=0.5, query_encoder_name="fs",
+        use_pos_emb=True, model_name="review_transformer", sim_func="product", pos_weight=False)
+    random.seed(1)
+    np.random.seed(1)
+    torch.manual_seed(0)
+    c = ReviewTrainCollate(files, split, args)
+    c.initialize_epoch()
+    out = c.train_batch(split.review_info[:BATCH], prepare_pv=train_pv, shuffle=True)
+    out = out if isinstance(out, list) else [out]
+    assert len(out) == (3 if train_pv else 1)
+    model = ProductRanker(args, "cpu", files.vocab_size, files.review_count, files.product_size, files.user_size,
+                          c.review_words.tolist(), files.words, word_dists=split.word_dists)   # shapes only: no compute
+    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cfg = argparse.Namespace(**vars(args))
+    cfg.review_pad_idx = files.review_count - 1
+    for b in out:
+        negw = torch.randint(0, files.vocab_size - 1, (b.pos_prod_rword_idxs.numel() * args.neg_per_pos,)) \
+            if train_pv else None
+        masks = None
+        if enc == "pvc":
+            masks = [torch.zeros(t.reshape(-1, t.shape[-1]).shape, dtype=torch.bool)
+                     for t in (b.pos_prod_rword_idxs_pvc, b.neg_prod_rword_idxs_pvc)]
+        loss = rm.rtm_forward(P, cfg, b, train_pv, neg_word_idxs=negw, corrupt_masks=masks, training=True)[0]
+        assert torch.isfinite(loss) and float(loss) > 0
