@@ -367,6 +367,7 @@ if __name__ == "__main__":
     make_tem("tem_avg_bias", 102, query_encoder_name="avg", sim_func="bias_product", pos_weight=True,
              sep_prod_emb=True, inter_layers=2, embedding_size=32, heads=4, ff_size=48)
     make_tem("tem_d128", 103, embedding_size=128, ff_size=32, neg_per_pos=5)
+    make_tem("tem_itempos", 104, use_item_pos=True, use_pos_emb=False, neg_per_pos=4)   # last (maybe padded) position
     for enc in ("pv", "pvc", "fs", "avg"):
         make_rtm("rtm_%s_trainpv" % enc, 200 + len(enc), True, review_encoder_name=enc)
         make_rtm("rtm_%s" % enc, 300 + len(enc), False, review_encoder_name=enc,

@@ -84,7 +84,7 @@ def _zero_pad_rows(P, grads):
     return out
 
 
-@pytest.mark.parametrize("name", ["tem_fs", "tem_avg_bias", "tem_d128"])
+@pytest.mark.parametrize("name", ["tem_fs", "tem_avg_bias", "tem_d128", "tem_itempos"])
 def test_tem(name):
     G = Golden(name)
     P = G.leaf_params(oracle.sinusoid_table)
