@@ -24,7 +24,7 @@ n, d = int(sys.argv[1]), 128
 torch.manual_seed(0)
 table = torch.empty(n + 1, d, device="cuda").normal_()
 prep = ops.catalog_prepare_f16(table, n)
-for m in (24, 128, 384, 1024, 4096):
+for m in ((384, 4096) if os.environ.get("PSB_CHECK_QUICK") == "1" else (24, 128, 384, 1024, 4096)):
     q = torch.randn(m, d, device="cuda")
     f = lambda: ops.catalog_topk(q, table, 100, n_items=n, mode=_lib.TOPK_TC16, prepared=prep)
     ids, sc = f()
@@ -58,10 +58,14 @@ for m in (24, 128, 384, 1024, 4096):
 
 def run(n, epi):
     env = dict(os.environ, PSB_TC16_EPI=str(epi))
+    quick = "--quick" in sys.argv
+    if quick:
+        env["PSB_CHECK_QUICK"] = "1"
     if epi == 2 and "--stats" in sys.argv:
         env["PSB_TC16_STATS"] = "1"     # the instrumented kernel (a few clock reads per tile): not a timing run
     try:
-        r = subprocess.run([sys.executable, "-c", CHILD, str(n)], env=env, capture_output=True, text=True, timeout=240)
+        r = subprocess.run([sys.executable, "-c", CHILD, str(n)], env=env, capture_output=True, text=True,
+                           timeout=25 if quick else 240)
     except subprocess.TimeoutExpired as ex:
         print(json.dumps({"n_items": n, "epi": epi, "error": "timeout (hang?)", "partial": (ex.stdout or b"")[-400:].decode("utf8", "replace")}))
         return {}
@@ -96,7 +100,7 @@ if __name__ == "__main__":
         print(r.stdout.strip() or r.stderr[-600:])
         sys.exit(r.returncode)
     ok = True
-    for n in (1_000_000, 16_000_000 if "--big" in sys.argv else 250_000):
+    for n in ((1_000_000,) if "--quick" in sys.argv else (1_000_000, 16_000_000 if "--big" in sys.argv else 250_000)):
         v1, v2 = run(n, 1), run(n, 2)
         for m in sorted(v1):
             same = m in v2 and v2[m]["sha"] == v1[m]["sha"]
