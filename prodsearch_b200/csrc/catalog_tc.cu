@@ -317,6 +317,30 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       : "memory");
 }
 
+// Issue from a warp whose 32 lanes all execute the instruction stream (uniform control flow), with the instruction
+// itself predicated on the elected lane: the descriptors stay in uniform registers and ptxas has no reason to wrap
+// every tcgen05.mma in the per-lane "waterfall" loop it emits when the issue sits inside `if (lane == 0)`.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t leader;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+  return leader;
+}
+__device__ __forceinline__ void tc_mma_f16_if(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+
 struct Tc16Params {
   int m, n_items, kblocks;             // kblocks = d / 64
   int tile_begin, tile_step, n_tiles;  // item tiles of TN items
@@ -593,7 +617,8 @@ struct Tc16V2 {
 //   0 issuer total, 1 issuer waiting for a free accumulator set (epilogue-bound), 2 issuer waiting for item tiles
 //   (TMA / HBM / L2-bound), 3 epilogue warp 2 total, 4 epilogue warp 2 waiting for scores (MMA-bound),
 //   5 producer waiting for a free stage, 6 item tiles, 7 launches.  issuer total - 1 - 2 = MMA issue time.
-template <bool DUMP, int MT, bool STATS>
+// ELECT (PSB_TC16_EPI=3): the MMA issuer is the whole warp 1 with elected-lane predication (see tc_mma_f16_if).
+template <bool DUMP, int MT, bool STATS, bool ELECT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                      const Tc16Params P) {
@@ -671,7 +696,8 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one commit per query tile =====
-    if (lane == 0) {
+    if (ELECT || lane == 0) {
+      const uint32_t leader = ELECT ? elect_one() : 1u;
       mbar_wait(a_full, 0);
       const uint64_t a_base = umma_desc(smem_u32(sA));
       const uint64_t b_base = umma_desc(smem_u32(sB));
@@ -702,14 +728,18 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int kb = 0; kb < P.kblocks; ++kb) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              tc_mma_f16(d_addr, a_tile + static_cast<uint64_t>(kb) * kb_a + k4 * 2, b_tile + static_cast<uint64_t>(kb) * kb_b + k4 * 2,
-                         kIdesc16, (kb | k4) != 0 ? 1u : 0u);
+              if (ELECT)
+                tc_mma_f16_if(leader, d_addr, a_tile + static_cast<uint64_t>(kb) * kb_a + k4 * 2,
+                              b_tile + static_cast<uint64_t>(kb) * kb_b + k4 * 2, kIdesc16, (kb | k4) != 0 ? 1u : 0u);
+              else
+                tc_mma_f16(d_addr, a_tile + static_cast<uint64_t>(kb) * kb_a + k4 * 2, b_tile + static_cast<uint64_t>(kb) * kb_b + k4 * 2,
+                           kIdesc16, (kb | k4) != 0 ? 1u : 0u);
           }
-          tc_commit(t_full + acc * MT + mt);
+          if (ELECT) tc_commit_if(leader, t_full + acc * MT + mt); else tc_commit(t_full + acc * MT + mt);
         }
-        tc_commit(b_empty + st);
+        if (ELECT) tc_commit_if(leader, b_empty + st); else tc_commit(b_empty + st);
       }
-      if (STATS && P.stat != nullptr) {
+      if (STATS && P.stat != nullptr && lane == 0) {
         unsigned long long* o = P.stat + (blockIdx.y * gridDim.x + blockIdx.x) * 8;
         o[0] += static_cast<unsigned long long>(clock64() - t_begin);
         o[1] += static_cast<unsigned long long>(w_acc);
@@ -1459,7 +1489,8 @@ static int tc16_epilogue_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSB_TC16_EPI");
-    v = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+    const int x = e != nullptr ? atoi(e) : 1;
+    v = (x == 2 || x == 3) ? x : 1;
   }
   return v;
 }
@@ -1472,7 +1503,7 @@ static unsigned long long* tc16_stat_buffer() {
   static int wanted = -1;
   if (wanted < 0) {
     const char* e = getenv("PSB_TC16_STATS");
-    wanted = (e != nullptr && atoi(e) != 0 && tc16_epilogue_variant() == 2) ? 1 : 0;
+    wanted = (e != nullptr && atoi(e) != 0 && tc16_epilogue_variant() != 1) ? 1 : 0;
   }
   if (wanted == 1 && g_tc16_stat == nullptr) {
     if (cudaMalloc(reinterpret_cast<void**>(&g_tc16_stat), kTc16StatCtas * 8 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -1486,7 +1517,7 @@ static unsigned long long* tc16_stat_buffer() {
 
 // candidate lists per (query row, item slice): one per epilogue part that scores columns of the row's query tile
 static int tc16_lists_per_slice(int MT) {
-  if (tc16_epilogue_variant() != 2) return kParts;
+  if (tc16_epilogue_variant() == 1) return kParts;
   switch (MT) {
     case 1: return Tc16V2<1>::AP;
     case 2: return Tc16V2<2>::AP;
@@ -1587,36 +1618,39 @@ static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUt
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done = true;
   }
-  if (tc16_epilogue_variant() == 2) {
+  if (tc16_epilogue_variant() != 1) {
+    const bool elect = tc16_epilogue_variant() == 3;
+    const bool stats = P.stat != nullptr && !DUMP && static_cast<int>(grid.x * grid.y) <= kTc16StatCtas;
     static bool attr2_done = false;
     if (!attr2_done) {
       const int lim = 227 * 1024;
       cudaError_t e = cudaSuccess;
 #define PSB_TC16_ATTR2(D, M) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
       PSB_TC16_ATTR2(true, 1); PSB_TC16_ATTR2(true, 2); PSB_TC16_ATTR2(true, 3); PSB_TC16_ATTR2(true, 4);
       PSB_TC16_ATTR2(false, 1); PSB_TC16_ATTR2(false, 2); PSB_TC16_ATTR2(false, 3); PSB_TC16_ATTR2(false, 4);
 #undef PSB_TC16_ATTR2
       if (e != cudaSuccess) return static_cast<int>(e);
       attr2_done = true;
     }
-    PSB_PROF("tc16_score_v2_kernel", s);
-    if (P.stat != nullptr && !DUMP && static_cast<int>(grid.x * grid.y) <= kTc16StatCtas) {
-      switch (MT) {
-        case 1: tc16_score_v2_kernel<DUMP, 1, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-        case 2: tc16_score_v2_kernel<DUMP, 2, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-        case 3: tc16_score_v2_kernel<DUMP, 3, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-        default: tc16_score_v2_kernel<DUMP, 4, true><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      }
-      return launch_status();
-    }
+    PSB_PROF(elect ? "tc16_score_v3_kernel" : "tc16_score_v2_kernel", s);
+#define PSB_TC16_GO(M)                                                                                      \
+  do {                                                                                                      \
+    if (stats && elect) tc16_score_v2_kernel<DUMP, M, true, true><<<grid, kTcThreads, smem, s>>>(mq, me, P);       \
+    else if (stats) tc16_score_v2_kernel<DUMP, M, true, false><<<grid, kTcThreads, smem, s>>>(mq, me, P);          \
+    else if (elect) tc16_score_v2_kernel<DUMP, M, false, true><<<grid, kTcThreads, smem, s>>>(mq, me, P);          \
+    else tc16_score_v2_kernel<DUMP, M, false, false><<<grid, kTcThreads, smem, s>>>(mq, me, P);                    \
+  } while (0)
     switch (MT) {
-      case 1: tc16_score_v2_kernel<DUMP, 1, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      case 2: tc16_score_v2_kernel<DUMP, 2, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      case 3: tc16_score_v2_kernel<DUMP, 3, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
-      default: tc16_score_v2_kernel<DUMP, 4, false><<<grid, kTcThreads, smem, s>>>(mq, me, P); break;
+      case 1: PSB_TC16_GO(1); break;
+      case 2: PSB_TC16_GO(2); break;
+      case 3: PSB_TC16_GO(3); break;
+      default: PSB_TC16_GO(4); break;
     }
+#undef PSB_TC16_GO
     return launch_status();
   }
   PSB_PROF("tc16_score_kernel", s);

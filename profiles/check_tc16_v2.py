@@ -38,7 +38,7 @@ for m in ((384, 4096) if os.environ.get("PSB_CHECK_QUICK") == "1" else (24, 128,
     split = {k_: round(v[1] / 3 * 1e3, 1) for k_, v in _lib.profile_dump().items()}
     _lib.profile_enable(False)
     stats = None
-    if os.environ.get("PSB_TC16_STATS") == "1" and os.environ.get("PSB_TC16_EPI") == "2":
+    if os.environ.get("PSB_TC16_STATS") == "1" and os.environ.get("PSB_TC16_EPI") in ("2", "3"):
         import ctypes
         buf = (ctypes.c_uint64 * 8)()
         _lib.load().psb_debug_tc16_stats(buf, 1)                      # reset, then one call on its own
@@ -61,7 +61,7 @@ def run(n, epi):
     quick = "--quick" in sys.argv
     if quick:
         env["PSB_CHECK_QUICK"] = "1"
-    if epi == 2 and "--stats" in sys.argv:
+    if epi in (2, 3) and "--stats" in sys.argv:
         env["PSB_TC16_STATS"] = "1"     # the instrumented kernel (a few clock reads per tile): not a timing run
     try:
         r = subprocess.run([sys.executable, "-c", CHILD, str(n)], env=env, capture_output=True, text=True,
@@ -99,6 +99,10 @@ if __name__ == "__main__":
         r = subprocess.run([sys.executable, "-c", TMEM_CHILD], capture_output=True, text=True, timeout=120)
         print(r.stdout.strip() or r.stderr[-600:])
         sys.exit(r.returncode)
+    if "--only" in sys.argv:       # one variant alone (its sha is compared by hand with an earlier run: same seed, same data)
+        epi = int(sys.argv[sys.argv.index("--only") + 1])
+        got = run(1_000_000, epi)
+        sys.exit(0 if got else 1)
     ok = True
     for n in ((1_000_000,) if "--quick" in sys.argv else (1_000_000, 16_000_000 if "--big" in sys.argv else 250_000)):
         v1, v2 = run(n, 1), run(n, 2)
