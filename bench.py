@@ -427,6 +427,11 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
         if not prep.fits:
             mode, prep, mode_name = _lib.TOPK_TC, None, "tcgen05_tf32"
         q = torch.randn(m_local, d, device=dev)
+        # the shard-local kernel once on its own (same shapes as below, no collective): a rank whose kernel fails
+        # says so at the agree() below instead of leaving the others inside the all-gather of the timed loop
+        ops.catalog_topk(q.repeat(world, 1), w, k, n_items=n_local, id_base=rank, id_stride=world, mode=mode, prepared=prep)
+        if str(dev).startswith("cuda"):
+            torch.cuda.synchronize()
 
         def ranked():
             qs = [torch.empty_like(q) for _ in range(world)]
@@ -622,9 +627,21 @@ def run_b200_arm(a):
     do_sharded = world > 1 and transport == "nvlink-peer" and not a.no_extra
     if rank != 0:
         if do_sharded:      # every rank takes part; a rank that hangs leaves after the same time-out as rank 0
-            guarded(lambda: sharded_regime(peaks, pg, rank, world), a.extra_timeout, lambda: None)
+            def take_part():
+                try:
+                    sharded_regime(peaks, pg, rank, world)
+                except Exception:                                     # noqa: BLE001
+                    # a rank that leaves now (non-zero exit: torchrun tears the job down; exit 0: NCCL reports the lost
+                    # peer to the others) could take rank 0 down before it has printed the headline line -- stay until
+                    # the watchdog ends this process, which is when rank 0's own watchdog prints the line
+                    while True:
+                        time.sleep(1.0)
+            guarded(take_part, a.extra_timeout + 5, lambda: None)
         if world > 1:
-            dist.destroy_process_group()
+            try:
+                dist.destroy_process_group()
+            except Exception:                                         # noqa: BLE001 -- after a failed collective
+                pass
         return
     d = WORKLOAD["embedding_size"]
     K, L, W, F = WORKLOAD["neg_per_pos"], WORKLOAD["uprev_review_limit"], 1, WORKLOAD["ff_size"]
@@ -703,9 +720,6 @@ def run_b200_arm(a):
             roofline["note"] = ("GEMM-shaped (B*(1+K) rows x 128 -> 512 -> 128) but computed in fp32 FFMA on CUDA cores to "
                                 "hold the 1e-5 parity bar; %.1f%% of the fp32 FFMA peak (%.1f TFLOP/s at the sampled clock)"
                                 % (100.0 * ent.get("frac_of_fp32_ffma_peak", 0.0), ffma_peak))
-    extra = None
-    if world == 1 and not a.no_extra:
-        extra = {"bandwidth_regime": bandwidth_regime(peaks), "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
     cpu = None
     if world == 1 and not a.no_cpu:
         sec, cores = cpu_reference_step_time(a.cpu_steps, 2, a.dropout)
@@ -726,8 +740,19 @@ def run_b200_arm(a):
         "e2e": {"value": B * a.steps * world / e2e_sec, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_sec / a.steps * 1e3},
         "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-        "extra": extra,
+        "extra": None,
     }
+    if world == 1 and not a.no_extra:
+        # everything above is final; the 16M-row section (seconds of GPU time when healthy) runs last, under the same
+        # watchdog as the multi-GPU one: its 16M-row catalog entry had no GPU run when it was written
+        def give_up_bw():
+            line["extra"] = {"bandwidth_regime": {"unavailable": "no result after %d s (watchdog)" % a.extra_timeout}}
+            print(json.dumps(line))
+        try:
+            line["extra"] = {"bandwidth_regime": guarded(lambda: bandwidth_regime(peaks), a.extra_timeout, give_up_bw),
+                             "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
+        except Exception as ex:                                       # noqa: BLE001 -- the headline line must appear
+            line["extra"] = {"bandwidth_regime": {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}}
     if do_sharded:
         # everything above is final; the 16M-row section runs last, under a watchdog that prints the line without it
         def give_up():
@@ -758,7 +783,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extra-timeout", type=int, default=240, dest="extra_timeout",
-                    help="N>1: seconds the 16M-row sharded section may take before the line is printed without it")
+                    help="seconds the 16M-row section (extra) may take before the line is printed without it")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],
                     help="N>1: auto = NVLink peer memory when CUDA IPC works, else NCCL all-to-all; nccl forces the latter")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")

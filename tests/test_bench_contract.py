@@ -54,3 +54,31 @@ def test_clock_sampler_summary_uses_the_timed_window():
     c.rows = []
     assert c.summary()["reasons"] == ["unavailable"]
     c.stop()
+
+
+def test_guarded_section_prints_the_line_and_exits_zero_when_it_hangs():
+    """bench.guarded wraps the 16M-row sections that run after the headline numbers are final: a section that never
+    returns must still end in ONE printed line and exit status 0; results and exceptions pass through otherwise."""
+    b = _bench_module()
+    assert b.guarded(lambda: 7, 30, lambda: None) == 7
+    try:
+        b.guarded(lambda: 1 // 0, 30, lambda: None)
+        raise AssertionError("the section's exception must reach the caller")
+    except ZeroDivisionError:
+        pass
+    prog = ("import importlib.util, json, time\n"
+            "spec = importlib.util.spec_from_file_location('bench_mod', %r)\n"
+            "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+            "line = {'value': 1.0, 'extra': None}\n"
+            "def give_up():\n"
+            "    line['extra'] = {'unavailable': 'watchdog'}\n"
+            "    print(json.dumps(line))\n"
+            "def hang():\n"
+            "    while True:\n"
+            "        time.sleep(0.05)\n"
+            "b.guarded(hang, 1, give_up)\n"
+            "print('not reached')\n") % os.path.join(ROOT, "bench.py")
+    out = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {"value": 1.0, "extra": {"unavailable": "watchdog"}}

@@ -169,6 +169,8 @@ def _regime_worker(rank, world, port, out):
             return argparse.Namespace(fits=True, n_items=n_local)
 
         def topk(qa, w, kk, n_items, id_base, id_stride, mode, prepared):
+            if seen.get("fail_topk_on") == rank:
+                raise RuntimeError("simulated shortlist failure")
             ids = id_base + id_stride * torch.arange(n_items)
             i, s_ = oracle.topk_lower_id_first((qa @ w[:n_items].t()).numpy(), kk, np.tile(ids.numpy(), (qa.shape[0], 1)))
             return torch.from_numpy(i), torch.from_numpy(s_)
@@ -200,6 +202,12 @@ def _regime_worker(rank, world, port, out):
         _FakeShards.fail_fetch_on = 0
         r3 = bench.sharded_regime(peaks, None, rank, world, **kw)
         assert "unavailable" in r3["peer_gather_rows"] and r3["catalog_topk_16M"]["queries_per_s"] > 0, r3
+        _FakeShards.fail_fetch_on = None
+        # 4. the shard-local top-k fails on one rank: found by the local run before the timed loop's collectives
+        seen["fail_topk_on"] = 1
+        r4 = bench.sharded_regime(peaks, None, rank, world, **kw)
+        assert r4["peer_gather_rows"]["ms"] > 0 and "unavailable" in r4["catalog_topk_16M"], r4
+        assert ("simulated shortlist" in r4["catalog_topk_16M"]["unavailable"]) == (rank == 1)
         out.put((rank, "ok"))
     except Exception:  # noqa: BLE001
         import traceback
