@@ -88,6 +88,27 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// Two adjacent 32-column chunks with ONE wait: both loads are in flight together (the second does not queue behind the
+// first one's wait), and the caller can hand the accumulator back before it looks at a single score.
+__device__ __forceinline__ void tc_ld32x2(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]),
+        "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]),
+        "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+      : "r"(taddr + 32u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // K-major, 128-byte-swizzled operand tile (rows x 32 fp32, 8-row atoms of 1024 B): UMMA shared
 // memory descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30) = 1,
@@ -617,12 +638,17 @@ struct Tc16V2 {
 //   0 issuer total, 1 issuer waiting for a free accumulator set (epilogue-bound), 2 issuer waiting for item tiles
 //   (TMA / HBM / L2-bound), 3 epilogue warp 2 total, 4 epilogue warp 2 waiting for scores (MMA-bound),
 //   5 producer waiting for a free stage, 6 item tiles, 7 launches.  issuer total - 1 - 2 = MMA issue time.
-// ELECT (PSB_TC16_EPI=3): the MMA issuer is the whole warp 1 with elected-lane predication (see tc_mma_f16_if).
-template <bool DUMP, int MT, bool STATS, bool ELECT>
+// VAR = PSB_TC16_EPI: 2 = the above; 3 = the MMA issuer is the whole warp 1 with elected-lane predication (see
+// tc_mma_f16_if); 4 = 3 + a part whose run is two chunks reads BOTH from TMEM under one wait (tc_ld32x2) and hands the
+// accumulator set back BEFORE it scans the 64 scores it now holds in registers, so the issuer's wait for a free set
+// (655 of 2554 cycles per tile in the v3 split at M = 4096) overlaps the scan instead of following it.
+template <bool DUMP, int MT, bool STATS, int VAR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                      const Tc16Params P) {
   using V = Tc16V2<MT>;
+  constexpr bool ELECT = VAR >= 3;
+  constexpr bool DUAL = VAR == 4 && !DUMP && V::CPP == 2;
   constexpr int TN = V::TN;
   constexpr int kAccCols = MT * TN;
   constexpr int kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
@@ -780,6 +806,63 @@ tc16_score_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_wait(t_full + acc * MT + mt, aph);
       if (STATS) w_sc += clock64() - w0;
       tc_fence_after();
+      if (DUAL) {
+        uint32_t v2[2][32];
+        __syncwarp();
+        tc_ld32x2(t_addr + static_cast<uint32_t>(acc * kAccCols), v2[0], v2[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + acc);       // the scores are in registers: the set is free again
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int id0 = tile * TN + col0 + j * 32;
+          if (full_tile) {
+            float mx8[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int g8 = g * 8;
+              const float m0 = fmaxf(fmaxf(__uint_as_float(v2[j][g8]), __uint_as_float(v2[j][g8 + 1])),
+                                     fmaxf(__uint_as_float(v2[j][g8 + 2]), __uint_as_float(v2[j][g8 + 3])));
+              mx8[g] = fmaxf(m0, fmaxf(fmaxf(__uint_as_float(v2[j][g8 + 4]), __uint_as_float(v2[j][g8 + 5])),
+                                       fmaxf(__uint_as_float(v2[j][g8 + 6]), __uint_as_float(v2[j][g8 + 7]))));
+            }
+            if (!(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])) < th)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int g8 = g * 8;
+                if (!(mx8[g] < th)) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float sc = __uint_as_float(v2[j][g8 + i]);
+                    if (!(sc < th)) {
+                      if (cn < P.cap) {
+                        P.cand_s[li + cn] = sc;
+                        P.cand_i[li + cn] = id0 + g8 + i;
+                      }
+                      ++cn;
+                    }
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int id = id0 + i;
+              float sc = __uint_as_float(v2[j][i]);
+              if (P.bias != nullptr && id < P.n_items) sc += P.bias[id];
+              if (!(sc < th) && id < P.n_items) {
+                if (cn < P.cap) {
+                  P.cand_s[li + cn] = sc;
+                  P.cand_i[li + cn] = id;
+                }
+                ++cn;
+              }
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int j = 0; j < V::CPP; ++j) {
         const int c0 = col0 + j * 32;
@@ -1484,13 +1567,13 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 }
 
 // Epilogue variant of the fp16 shortlist kernel: 1 = tc16_score_kernel (validated on B200, default),
-// 2 = tc16_score_v2_kernel (PSB_TC16_EPI=2; see its header).  Read once per process.
+// 2 / 3 / 4 = tc16_score_v2_kernel<.., VAR> (PSB_TC16_EPI=2|3|4; see its header).  Read once per process.
 static int tc16_epilogue_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSB_TC16_EPI");
     const int x = e != nullptr ? atoi(e) : 1;
-    v = (x == 2 || x == 3) ? x : 1;
+    v = (x >= 2 && x <= 4) ? x : 1;
   }
   return v;
 }
@@ -1513,6 +1596,20 @@ static unsigned long long* tc16_stat_buffer() {
     }
   }
   return g_tc16_stat;
+}
+
+// Query tiles resident per CTA: 4 (default) = 512 queries per pass over the table at 64 items per MMA; PSB_TC16_MT=2
+// = 256 queries per pass at 128 items per MMA -- half the tcgen05.mma instructions for the same flops (the issuing
+// thread, not the tensor pipe, paces the MT = 4 kernel: DESIGN.md section 8) against twice the table passes.
+// Tuning knob, read once per process.
+static int tc16_max_tiles_per_cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSB_TC16_MT");
+    const int x = e != nullptr ? atoi(e) : 4;
+    v = (x >= 1 && x <= 4) ? x : 4;
+  }
+  return v;
 }
 
 // candidate lists per (query row, item slice): one per epilogue part that scores columns of the row's query tile
@@ -1538,7 +1635,8 @@ struct Tc16Plan {
 static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   Tc16Plan p;
   p.m_tiles = static_cast<int>((m + kTM - 1) / kTM);
-  p.groups = (p.m_tiles + 3) / 4;
+  const int max_mt = tc16_max_tiles_per_cta();
+  p.groups = (p.m_tiles + max_mt - 1) / max_mt;
   p.MT = (p.m_tiles + p.groups - 1) / p.groups;
   p.TN = p.MT <= 2 ? 128 : 64;
   p.m_pad = p.groups * p.MT * kTM;
@@ -1619,30 +1717,35 @@ static int launch_tc16(int MT, dim3 grid, size_t smem, cudaStream_t s, const CUt
     attr_done = true;
   }
   if (tc16_epilogue_variant() != 1) {
-    const bool elect = tc16_epilogue_variant() == 3;
+    // the pilot (DUMP) pass has no scan to overlap: variant 4 runs it as variant 3
+    const int var = (DUMP && tc16_epilogue_variant() == 4) ? 3 : tc16_epilogue_variant();
     const bool stats = P.stat != nullptr && !DUMP && static_cast<int>(grid.x * grid.y) <= kTc16StatCtas;
     static bool attr2_done = false;
     if (!attr2_done) {
       const int lim = 227 * 1024;
       cudaError_t e = cudaSuccess;
 #define PSB_TC16_ATTR2(D, M) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc16_score_v2_kernel<D, M, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess && !D) e = cudaFuncSetAttribute(tc16_score_v2_kernel<false, M, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim); \
+  if (e == cudaSuccess && !D) e = cudaFuncSetAttribute(tc16_score_v2_kernel<false, M, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
       PSB_TC16_ATTR2(true, 1); PSB_TC16_ATTR2(true, 2); PSB_TC16_ATTR2(true, 3); PSB_TC16_ATTR2(true, 4);
       PSB_TC16_ATTR2(false, 1); PSB_TC16_ATTR2(false, 2); PSB_TC16_ATTR2(false, 3); PSB_TC16_ATTR2(false, 4);
 #undef PSB_TC16_ATTR2
       if (e != cudaSuccess) return static_cast<int>(e);
       attr2_done = true;
     }
-    PSB_PROF(elect ? "tc16_score_v3_kernel" : "tc16_score_v2_kernel", s);
+    PSB_PROF(var == 4 ? "tc16_score_v4_kernel" : var == 3 ? "tc16_score_v3_kernel" : "tc16_score_v2_kernel", s);
 #define PSB_TC16_GO(M)                                                                                      \
   do {                                                                                                      \
-    if (stats && elect) tc16_score_v2_kernel<DUMP, M, true, true><<<grid, kTcThreads, smem, s>>>(mq, me, P);       \
-    else if (stats) tc16_score_v2_kernel<DUMP, M, true, false><<<grid, kTcThreads, smem, s>>>(mq, me, P);          \
-    else if (elect) tc16_score_v2_kernel<DUMP, M, false, true><<<grid, kTcThreads, smem, s>>>(mq, me, P);          \
-    else tc16_score_v2_kernel<DUMP, M, false, false><<<grid, kTcThreads, smem, s>>>(mq, me, P);                    \
+    if (var == 4 && stats) tc16_score_v2_kernel<false, M, true, 4><<<grid, kTcThreads, smem, s>>>(mq, me, P);      \
+    else if (var == 4) tc16_score_v2_kernel<false, M, false, 4><<<grid, kTcThreads, smem, s>>>(mq, me, P);         \
+    else if (var == 3 && stats) tc16_score_v2_kernel<DUMP, M, true, 3><<<grid, kTcThreads, smem, s>>>(mq, me, P);  \
+    else if (var == 3) tc16_score_v2_kernel<DUMP, M, false, 3><<<grid, kTcThreads, smem, s>>>(mq, me, P);          \
+    else if (stats) tc16_score_v2_kernel<DUMP, M, true, 2><<<grid, kTcThreads, smem, s>>>(mq, me, P);              \
+    else tc16_score_v2_kernel<DUMP, M, false, 2><<<grid, kTcThreads, smem, s>>>(mq, me, P);                        \
   } while (0)
     switch (MT) {
       case 1: PSB_TC16_GO(1); break;

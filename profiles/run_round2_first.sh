@@ -1,25 +1,28 @@
 #!/bin/bash
 # First gpurun call of round 2 (one GPU): everything written after round 1's GPU budget was spent gets its first run.
-#   gpurun --timeout 1500 -- 'bash profiles/run_round2_first.sh r02a'
-# 1. GPU parity suite (includes the Adam kernel's per-CTA coefficient change and the corpus-from-files test);
-# 2. TMEM read-bandwidth probe, then the v2 epilogue of the fp16 shortlist kernel against v1 (bit-identical lists
-#    required), then v2's cycle split per role -- each in subprocesses under timeouts (a tcgen05 hand-off bug hangs);
-# 3. the default bench line (now with extra.bandwidth_regime.G5_catalog_topk_16M);
-# 4. one ncu --set full capture of the v2 kernel at M = 4096 if (2) passed.
+#   gpurun --timeout 1700 -- 'bash profiles/run_round2_first.sh r02a'
+# 1. GPU parity suite with the DEFAULT kernels (includes the corpus-from-files test);
+# 2. the fp16 shortlist tests again with PSB_TC16_EPI=3 (measured in round 1: identical lists, 13-19 % faster) -- if they
+#    pass, 3 becomes the default (tc16_epilogue_variant() in csrc/catalog_tc.cu);
+# 3. variants 3, 4 and the PSB_TC16_MT=2 plan (128 items per MMA, 2 query tiles per CTA) against v1 at 1M items, lists
+#    must be bit-identical; then the cycle split of each -- all in subprocesses under timeouts (a tcgen05 hand-off bug hangs);
+# 4. the default bench line (extra.bandwidth_regime.G5_catalog_topk_16M gets its first run here);
+# 5. one ncu --set full capture of the best variant's main pass at M = 4096.
 R=${1:-r02a}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${R}_pytest.log
 tail -5 gpurun_out/${R}_pytest.log
-timeout 200 python profiles/check_tc16_v2.py --tmem > gpurun_out/${R}_tmem.jsonl 2>&1; cat gpurun_out/${R}_tmem.jsonl
-timeout 900 python profiles/check_tc16_v2.py > gpurun_out/${R}_tc16_v2.jsonl 2>&1; V2=$?; tail -12 gpurun_out/${R}_tc16_v2.jsonl
-if [ $V2 -eq 0 ]; then
-  timeout 600 python profiles/check_tc16_v2.py --stats > gpurun_out/${R}_tc16_v2_stats.jsonl 2>&1
-  grep '"epi": "2"' gpurun_out/${R}_tc16_v2_stats.jsonl | cut -c1-700
-fi
+PSB_TC16_EPI=3 timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_full_size.py -m gpu -q -k "f16 or catalog or rank" \
+    > gpurun_out/${R}_pytest_epi3.log 2>&1; echo "pytest (EPI=3) exit $?" >> gpurun_out/${R}_pytest_epi3.log
+tail -3 gpurun_out/${R}_pytest_epi3.log
+timeout 900 python profiles/check_tc16_v2.py --quick --variants 3,4,3/2,4/2 > gpurun_out/${R}_tc16_variants.jsonl 2>&1; VX=$?
+grep -v '"kernel_us"' gpurun_out/${R}_tc16_variants.jsonl | tail -12
+timeout 600 python profiles/check_tc16_v2.py --quick --stats --variants 3,4,3/2,4/2 > gpurun_out/${R}_tc16_variants_stats.jsonl 2>&1
+grep '"stats": {' gpurun_out/${R}_tc16_variants_stats.jsonl | cut -c1-900
 timeout 700 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; echo "bench exit $?"
 tail -c 400 gpurun_out/${R}_bench.err
-if [ $V2 -eq 0 ]; then
-  PSB_TC16_EPI=2 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'tc16_score_v2_kernel' -s 2 -c 1 \
-      -o gpurun_out/${R}_tc16v2_full python profiles/catalog_once.py 4096 > gpurun_out/${R}_tc16v2_full.log 2>&1
+if [ $VX -eq 0 ]; then
+  PSB_TC16_EPI=4 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'tc16_score_v2_kernel' -s 2 -c 1 \
+      -o gpurun_out/${R}_tc16v4_full python profiles/catalog_once.py 4096 > gpurun_out/${R}_tc16v4_full.log 2>&1
 fi
 ls -la gpurun_out | tail -8
