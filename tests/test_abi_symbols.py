@@ -64,3 +64,52 @@ def test_forked_sink_plumbing_present():
     assert callable(F_.run_forked) and callable(F_.RowGradSink._join_forked)
     for cls in (F_.RowGradSink, peer.PeerGradSink):
         assert callable(getattr(cls, "_finalize_callback")) and callable(getattr(cls, "finalize"))
+
+
+def _prototypes():
+    """name -> (return type, [parameter types]) parsed from include/psb.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "psb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    for ret, name, params in re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)\b(psb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        plist = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        out[name] = (ret.strip(), [re.sub(r"\s*\b[A-Za-z_][A-Za-z0-9_]*$", "", p).strip() for p in plist])
+    return out
+
+
+def _ctype_class(t):
+    """Coarse class of a C type as ctypes has to pass it."""
+    t = t.replace("const", "").strip()
+    if "*" in t or t in ("psb_stream_t",):
+        return "ptr"
+    return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "float": "f32", "double": "f64", "uint64_t": "u64",
+            "uint32_t": "u32"}[t]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """A ctypes call with the wrong arity or integer width is silent undefined behaviour: every prototype of
+    include/psb.h must agree, parameter by parameter, with the (restype, argtypes) entry _lib.py binds it with."""
+    from prodsearch_b200 import _lib
+    protos = _prototypes()
+    assert sorted(protos) == _declared()
+    by_ctype = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int32: "i32", ctypes.c_int64: "i64",
+                ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_uint64: "u64", ctypes.c_uint32: "u32",
+                ctypes.c_int: "i32"}
+
+    def cls(ct):
+        if ct in by_ctype:
+            return by_ctype[ct]
+        assert issubclass(ct, (ctypes._Pointer, ctypes.Structure, ctypes.Array)) or hasattr(ct, "contents"), ct
+        return "ptr" if not issubclass(ct, ctypes.Structure) else "struct"
+    for name, (ret, params) in sorted(protos.items()):
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(params), "%s: header has %d parameters, ctypes binds %d" % (name, len(params), len(args))
+        got = [cls(a) for a in args]
+        want = []
+        for p in params:
+            base = p.replace("const", "").strip()
+            want.append("struct" if (base.endswith("_t") and base.startswith("psb_") and "*" not in base
+                                     and base != "psb_stream_t") else _ctype_class(p))
+        assert got == want, "%s: header %s, ctypes %s" % (name, want, got)
+        assert cls(res) == ("ptr" if "*" in ret else _ctype_class(ret)), "%s: return type" % name
