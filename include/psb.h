@@ -242,6 +242,14 @@ int psb_debug_tc16_stats(uint64_t* host_out, int32_t reset);
  * utilisation.  Synchronises the device, allocates and frees 20 KB.  bytes_per_clk: 2 doubles (host). */
 int psb_debug_tmem_read_bw(int32_t warps, int32_t iters, double* bytes_per_clk);
 
+/* Debug aid / building block under validation: out[m, j] = a[m, k] . bt[j, k]^T (+ bias[j]) on tcgen05 with the
+ * 3xTF32 split (csrc/gemm3_tf32.cu) -- the tensor-core form of the encoder's linear layers (models/neural.py:118-120
+ * linear_keys / linear_values / linear_query; models/transformer.py:37-88), which the FFMA kernels compute today.
+ * k % 64 == 0, j % 64 == 0, lda % 4 == 0, ldo % 4 == 0, 16-byte aligned pointers; PSB_E_UNSUPPORTED otherwise.  The
+ * encoder forward uses it for the q and K|V projections when PSB_ENC_TC=1 (off by default: no GPU run yet). */
+int psb_debug_gemm3_tf32(const float* a, int64_t lda, int64_t m, int64_t k, const float* bt, int64_t j,
+                         const float* bias, float* out, int64_t ldo, psb_stream_t stream);
+
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */
 int psb_topk_merge(const int64_t* ids, const float* scores, int64_t g, int64_t m, int64_t k,

@@ -592,12 +592,21 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
 
   // [K | V] rows of the active tokens, q of the output position
   // (independent products: the small q projection runs on the library's side stream next to the K|V one)
+  // PSB_ENC_TC=1: both products on tcgen05 (gemm3_tf32.cu) straight from the K-major weights Wq / Wk / Wv
+  const bool tc_q = rows_gemm_tc_enabled() && rows_gemm_tc_supported(sv + L.xno, d, d, p->wq, nullptr, 0, d, p->bq, sv + L.qv, d);
+  const bool tc_kv = rows_gemm_tc_enabled() &&
+                     rows_gemm_tc_supported(sv + L.xn, d, d, p->wk, p->wv, d, 2 * d, ws + W.bkv, sv + L.kv, 2 * d);
   st = fork_join(
       s, 1,
       [&](cudaStream_t s2) {
+        if (tc_q)
+          return launch_rows_gemm_tc(sv + L.xno, d, nullptr, D.S, D.S, d, p->wq, nullptr, 0, d, p->bq, sv + L.qv, d, s2);
         return launch_rows_gemm(sv + L.xno, d, nullptr, D.S, D.S, d, ws + W.wq_t, d, p->bq, sv + L.qv, d, s2);
       },
       [&]() {
+        if (tc_kv)
+          return launch_rows_gemm_tc(sv + L.xn, d, off + D.S, 0, D.S * D.T, d, p->wk, p->wv, d, 2 * d, ws + W.bkv,
+                                     sv + L.kv, 2 * d, s);
         return launch_rows_gemm(sv + L.xn, d, off + D.S, 0, D.S * D.T, d, ws + W.wkv_t, 2 * d, ws + W.bkv, sv + L.kv,
                                 2 * d, s);
       });

@@ -6,6 +6,7 @@
 #    pass, 3 becomes the default (tc16_epilogue_variant() in csrc/catalog_tc.cu);
 # 3. variants 3, 4 and the PSB_TC16_MT=2 plan (128 items per MMA, 2 query tiles per CTA) against v1 at 1M items, lists
 #    must be bit-identical; then the cycle split of each -- all in subprocesses under timeouts (a tcgen05 hand-off bug hangs);
+# 3b. the 3xTF32 GEMM standalone (accuracy against fp64, us per launch), then the encoder tests and a bench line with PSB_ENC_TC=1;
 # 4. the default bench line (extra.bandwidth_regime.G5_catalog_topk_16M gets its first run here);
 # 5. one ncu --set full capture of the best variant's main pass at M = 4096.
 R=${1:-r02a}
@@ -19,6 +20,14 @@ timeout 900 python profiles/check_tc16_v2.py --quick --variants 3,4,3/2,4/2 > gp
 grep -v '"kernel_us"' gpurun_out/${R}_tc16_variants.jsonl | tail -12
 timeout 600 python profiles/check_tc16_v2.py --quick --stats --variants 3,4,3/2,4/2 > gpurun_out/${R}_tc16_variants_stats.jsonl 2>&1
 grep '"stats": {' gpurun_out/${R}_tc16_variants_stats.jsonl | cut -c1-900
+# 3b. the 3xTF32 tcgen05 GEMM (csrc/gemm3_tf32.cu) on its own, then the encoder / model / train-step tests with it switched in
+timeout 300 python profiles/check_gemm3.py > gpurun_out/${R}_gemm3.jsonl 2>&1; G3=$?; cat gpurun_out/${R}_gemm3.jsonl
+if [ $G3 -eq 0 ]; then
+  PSB_ENC_TC=1 timeout 600 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_models.py tests/test_gpu_train_step.py -m gpu -q \
+      > gpurun_out/${R}_pytest_enc_tc.log 2>&1; echo "pytest (PSB_ENC_TC=1) exit $?" >> gpurun_out/${R}_pytest_enc_tc.log
+  tail -3 gpurun_out/${R}_pytest_enc_tc.log
+  PSB_ENC_TC=1 timeout 400 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_enc_tc.json 2> gpurun_out/${R}_bench_enc_tc.err
+fi
 timeout 700 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; echo "bench exit $?"
 tail -c 400 gpurun_out/${R}_bench.err
 if [ $VX -eq 0 ]; then
