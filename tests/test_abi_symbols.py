@@ -42,6 +42,12 @@ def test_argument_validation_without_gpu():
     assert lib.psb_gather_rows(16, 10, 128, None, 0, None, None, None) == 0             # n == 0: no launch
     assert lib.psb_scatter_reduce_workspace_bytes(1000, 50) > 16 * 1000
     assert lib.psb_catalog_topk_workspace_bytes(4, 100, 128, 10, 7) == -5               # bad mode
+    # 3xTF32 GEMM entry: shape / alignment rules are checked on the host before any CUDA call
+    assert lib.psb_debug_gemm3_tf32(1024, 100, 10, 100, 2048, 64, None, 4096, 64, None) == -5      # k % 64 != 0
+    assert lib.psb_debug_gemm3_tf32(1024, 128, 10, 128, 2048, 96, None, 4096, 96, None) == -5      # j % 64 != 0
+    assert lib.psb_debug_gemm3_tf32(1032, 128, 10, 128, 2048, 64, None, 4096, 64, None) == -5      # a not 16-byte aligned
+    assert lib.psb_debug_gemm3_tf32(1024, 64, 10, 128, 2048, 64, None, 4096, 64, None) == -1       # lda < k
+    assert lib.psb_debug_gemm3_tf32(1024, 128, 0, 128, 2048, 64, None, 4096, 64, None) == 0        # no rows: no launch
     assert lib.psb_launch_count() == 0
 
 
