@@ -675,6 +675,7 @@ def run_b200_arm(a):
         "peer_fold_rows_kernel": ("hbm", (n_item_slots + n_word_slots) * (d * 4 * 3 + 4)),
         "peer_allreduce_kernel": ("hbm", 0),
         "rows_gemm_kernel": ("tensor", 2.0 * (ntok * d * 2 * d + B * d * d) * 2),    # K|V and q projections + their dgrads
+        "gemm3_tf32_kernel": ("tensor", 2.0 * (ntok * d * 2 * d + B * d * d)),       # PSB_ENC_TC=1: forward K|V and q projections
         "attn_fwd_kernel": ("tensor", 2.0 * 2 * ntok * d),
         "tail_fwd_kernel": ("tensor", tail_flop),
         "tail_bwd_kernel": ("tensor", tail_flop),                                    # dgrad half; dW is wgrad_kernel
