@@ -764,6 +764,11 @@ def run_b200_arm(a):
                                                     give_up)}
         except Exception as ex:                                       # noqa: BLE001 -- the headline line must appear
             line["extra"] = {"sharded_16M": {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}}
+            # the other ranks may be inside a collective this rank has left: no orderly shutdown is possible (it could
+            # block on them); they leave through their own watchdogs
+            print(json.dumps(line))
+            sys.stdout.flush()
+            os._exit(0)
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
