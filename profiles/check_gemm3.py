@@ -48,9 +48,27 @@ for m, k, j, with_bias in ((384, 128, 128, True), (3500, 128, 256, True), (1000,
                       "rel_err_cublas_fp32": (f32.double() - ref).abs().max().item() / scale,
                       "rel_err_cublas_tf32": (tf32.double() - ref).abs().max().item() / scale,
                       "us_per_launch": round(e0.elapsed_time(e1) / 20 * 1e3, 2), "ok": good}), flush=True)
+# which accumulate rounding does tcgen05 kind::tf32 use?  The kernel's two-accumulator result against the two CPU models
+# of tools/tf32x3_numerics.py (exact sum of the 8 products of a K = 8 step, then fp32 accumulate with truncation /
+# round-to-nearest): the closer model -- ideally bit-equal -- decides whether one accumulator would do.
+import numpy as np
+sys.path.insert(0, %r)
+import tf32x3_numerics as tn
+m, k, j = 128, 128, 64
+a = torch.randn(m, k, device="cuda"); bt = torch.randn(j, k, device="cuda")
+out = torch.zeros(m, j, device="cuda")
+st = lib.psb_debug_gemm3_tf32(a.data_ptr(), k, m, k, bt.data_ptr(), j, None, out.data_ptr(), j, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+an, bn, got = a.cpu().numpy(), bt.cpu().numpy(), out.cpu().numpy()
+a_lo, b_lo = an - tn.trunc13(an), bn - tn.trunc13(bn)
+for model in ("trunc", "rn"):
+    tn.ACCUMULATE = model
+    pred = tn.mma_chain([(an, bn)]) + tn.mma_chain([(a_lo, bn), (an, b_lo)])
+    print(json.dumps({"probe": "accumulate model " + model, "status": st, "bit_equal_fraction": float((pred == got).mean()),
+                      "max_abs_diff": float(np.abs(pred.astype(np.float64) - got).max())}), flush=True)
 print("VERDICT:", "3xTF32 GEMM within 5e-6 of fp64 on every shape" if ok else "FAILED -- keep PSB_ENC_TC unset")
 sys.exit(0 if ok else 1)
-''' % ROOT
+''' % (ROOT, os.path.join(ROOT, "tools"))
 
 if __name__ == "__main__":
     try:
