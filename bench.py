@@ -676,6 +676,9 @@ def run_b200_arm(a):
         "peer_allreduce_kernel": ("hbm", 0),
         "rows_gemm_kernel": ("tensor", 2.0 * (ntok * d * 2 * d + B * d * d) * 2),    # K|V and q projections + their dgrads
         "gemm3_tf32_kernel": ("tensor", 2.0 * (ntok * d * 2 * d + B * d * d)),       # PSB_ENC_TC=1: forward K|V and q projections
+        "gemm3_out_proj_ln_kernel": ("tensor", 2.0 * B * C * d * d),                 # PSB_ENC_TC=2: the forward tail as three GEMMs
+        "gemm3_ffn_up_kernel": ("tensor", 2.0 * B * C * d * F),
+        "gemm3_ffn_down_ln_kernel": ("tensor", 2.0 * B * C * d * F),
         "attn_fwd_kernel": ("tensor", 2.0 * 2 * ntok * d),
         "tail_fwd_kernel": ("tensor", tail_flop),
         "tail_bwd_kernel": ("tensor", tail_flop),                                    # dgrad half; dW is wgrad_kernel

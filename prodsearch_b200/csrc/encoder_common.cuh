@@ -295,6 +295,21 @@ bool rows_gemm_tc_supported(const float* A, int lda, int K, const float* Bt0, co
                             const float* bias, const float* out, int ldo);
 int launch_rows_gemm_tc(const float* A, int lda, const int32_t* m_dev, int m_host, int m_max, int K, const float* Bt0,
                         const float* Bt1, int split, int J, const float* bias, float* out, int ldo, cudaStream_t s);
+// PSB_ENC_TC=2: the forward tail (encoder_fwd.cu tail_fwd_kernel) as a ctx kernel + three of those GEMMs with fused
+// epilogues, on the original (K-major) weights; same saved tensors, same dropout streams
+struct TailTcArgs {
+  Dims D;
+  const int32_t *nact, *off, *tok;
+  const float *P, *kv, *xo;
+  const float *wo, *bo, *w1, *b1, *w2, *b2;      // wo [d][d], w1 [F][d], w2 [d][F] as the modules hold them
+  const float *ln_ff_g, *ln_ff_b, *ln_out_g, *ln_out_b;
+  float *ctx, *y, *n, *z, *pre1, *h1;            // saved for the backward pass
+  float* out;
+  const uint64_t* seed_dev;
+};
+bool tail_tc_enabled();
+bool tail_tc_supported(const TailTcArgs& a);
+int launch_tail_fwd_tc(const TailTcArgs& a, cudaStream_t s);
 
 }  // namespace enc
 }  // namespace psb

@@ -617,6 +617,19 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
                                                                                    sv + L.kv, sv + L.p);
   if ((st = launch_status()) != PSB_OK) return st;
 
+  if (tail_tc_enabled()) {
+    // PSB_ENC_TC=2: ctx kernel + three 3xTF32 tcgen05 GEMMs with fused epilogues (gemm3_tf32.cu) on the original weights
+    TailTcArgs t;
+    t.D = D;
+    t.nact = nact; t.off = off; t.tok = tok;
+    t.P = sv + L.p; t.kv = sv + L.kv; t.xo = sv + L.xo;
+    t.wo = p->wo; t.bo = p->bo; t.w1 = p->w1; t.b1 = p->b1; t.w2 = p->w2; t.b2 = p->b2;
+    t.ln_ff_g = p->ln_ff_g; t.ln_ff_b = p->ln_ff_b; t.ln_out_g = p->ln_out_g; t.ln_out_b = p->ln_out_b;
+    t.ctx = sv + L.ctx; t.y = sv + L.y; t.n = sv + L.n; t.z = sv + L.z; t.pre1 = sv + L.pre1; t.h1 = sv + L.h1;
+    t.out = out;
+    t.seed_dev = cfg->seed_dev;
+    if (tail_tc_supported(t)) return launch_tail_fwd_tc(t, s);
+  }
   TailFwdArgs a;
   a.D = D;
   a.nact = nact; a.off = off; a.tok = tok;

@@ -27,6 +27,10 @@ if [ $G3 -eq 0 ]; then
       > gpurun_out/${R}_pytest_enc_tc.log 2>&1; echo "pytest (PSB_ENC_TC=1) exit $?" >> gpurun_out/${R}_pytest_enc_tc.log
   tail -3 gpurun_out/${R}_pytest_enc_tc.log
   PSB_ENC_TC=1 timeout 400 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_enc_tc.json 2> gpurun_out/${R}_bench_enc_tc.err
+  PSB_ENC_TC=2 timeout 600 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_models.py tests/test_gpu_train_step.py -m gpu -q \
+      > gpurun_out/${R}_pytest_enc_tc2.log 2>&1; echo "pytest (PSB_ENC_TC=2) exit $?" >> gpurun_out/${R}_pytest_enc_tc2.log
+  tail -3 gpurun_out/${R}_pytest_enc_tc2.log
+  PSB_ENC_TC=2 timeout 400 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_enc_tc2.json 2> gpurun_out/${R}_bench_enc_tc2.err
 fi
 timeout 700 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; echo "bench exit $?"
 tail -c 400 gpurun_out/${R}_bench.err
