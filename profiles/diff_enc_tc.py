@@ -1,0 +1,107 @@
+"""Stage-by-stage comparison of the encoder forward's tensor-core paths (PSB_ENC_TC=1 | 2, csrc/gemm3_tf32.cu) with the
+default FFMA kernels: the same seeded TEM-layout call (batch 384, 21 positions, d 128, ff 512, 8 heads, 1 + 5 copies,
+dropout 0.1 on a fixed Philox seed) runs once per level in its own subprocess (the knob is read once per process, and
+a tcgen05 hand-off bug hangs), the whole saved-activation buffer is dumped, and every region of it (encoder_common.cuh
+saved_layout) is compared with level 0's: the first region that differs by more than fp32 noise names the stage that
+is wrong -- qv / kv (projections), ctx, y, n (out-projection + LayerNorm), pre1, h1 (FFN up), z, out (FFN down + LN).
+
+    timeout 300 python profiles/diff_enc_tc.py          # one JSON line per (level, region)"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+S, T, D, FF, H, C = 384, 21, 128, 512, 8, 6
+CHILD = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from prodsearch_b200 import ops
+S, T, d, ff, heads, copies = %d, %d, %d, %d, %d, %d
+g = torch.Generator().manual_seed(0)
+shapes = dict(wq=(d, d), bq=(d,), wk=(d, d), bk=(d,), wv=(d, d), bv=(d,), wo=(d, d), bo=(d,), ln_attn_g=(d,), ln_attn_b=(d,),
+              ln_ff_g=(d,), ln_ff_b=(d,), w1=(ff, d), b1=(ff,), w2=(d, ff), b2=(d,), ln_out_g=(d,), ln_out_b=(d,))
+P = {}
+for k, s in shapes.items():
+    if len(s) == 2:
+        P[k] = (torch.randn(s, generator=g) * (2.0 / (s[0] + s[1])) ** 0.5).cuda()
+    elif k.endswith("_g"):
+        P[k] = (1.0 + 0.3 * torch.randn(s, generator=g)).cuda()
+    else:
+        P[k] = (0.1 * torch.randn(s, generator=g)).cuda()
+rows = 500
+table = torch.randn(rows + 1, d, generator=g); table[rows] = 0
+hist_len = torch.randint(0, T, (S,), generator=g)
+idx = torch.randint(0, rows, (S, T - 1), generator=g)
+idx[torch.arange(T - 1)[None, :] >= hist_len[:, None]] = rows
+first = torch.randn(S, d, generator=g)
+pos = torch.arange(64)[:, None].float(); div = torch.exp(torch.arange(0, d, 2).float() * -(np.log(10000.0) / d))
+pe = torch.zeros(64, d); pe[:, 0::2] = torch.sin(pos * div); pe[:, 1::2] = torch.cos(pos * div)
+seed_t = torch.tensor([0x1234ABCD5678], dtype=torch.int64, device="cuda")
+out, call = ops.encoder_fwd(P, heads, first=first.cuda(), table=table.cuda(), idx=idx.cuda(), pad_idx=rows, copies=copies,
+                            out_pos=0, pre_ln=False, p_drop=0.1, seed=seed_t, raw_input=False, pe=pe.cuda())
+torch.cuda.synchronize()
+np.savez(sys.argv[1], saved=call.saved.cpu().numpy().view(np.float32), out=out.cpu().numpy())
+''' % (ROOT, S, T, D, FF, H, C)
+
+
+def layout():
+    """encoder_common.cuh saved_layout, in floats."""
+    a4 = lambda x: (x + 3) & ~3
+    sc = S * C
+    sizes = [("nact", a4(S)), ("off", a4(S + 1)), ("tok", a4(S * T)), ("xo", S * D), ("xno", S * D), ("qv", S * D),
+             ("xn", S * T * D), ("kv", S * T * 2 * D), ("p", a4(S * T * H)), ("ctx", sc * D), ("y", sc * D), ("n", sc * D),
+             ("z", sc * D), ("pre1", sc * FF), ("h1", sc * FF)]
+    out, p = {}, 0
+    for name, n in sizes:
+        out[name] = (p, n)
+        p += n
+    return out
+
+
+def run(level, path):
+    env = dict(os.environ, PSB_ENC_TC=str(level))
+    try:
+        r = subprocess.run([sys.executable, "-c", CHILD, path], env=env, capture_output=True, text=True, timeout=120)
+    except subprocess.TimeoutExpired:
+        print(json.dumps({"level": level, "error": "timeout (hang?)"}))
+        return None
+    if r.returncode != 0:
+        print(json.dumps({"level": level, "error": r.stderr[-600:]}))
+        return None
+    return np.load(path)
+
+
+if __name__ == "__main__":
+    tmp = tempfile.mkdtemp()
+    base = run(0, os.path.join(tmp, "l0.npz"))
+    ok = base is not None
+    L = layout()
+    for level in (1, 2):
+        got = run(level, os.path.join(tmp, "l%d.npz" % level)) if ok else None
+        if got is None:
+            ok = False
+            continue
+        n_act = int(base["saved"].view(np.int32)[L["off"][0] + S])        # active tokens: compact rows beyond hold garbage
+        for name, (p, n) in L.items():
+            a, b = base["saved"][p:p + n], got["saved"][p:p + n]
+            if name in ("nact", "off", "tok"):
+                same = bool(np.array_equal(a.view(np.int32), b.view(np.int32)))
+                print(json.dumps({"level": level, "region": name, "identical": same}))
+                ok = ok and same
+                continue
+            if name in ("xn", "kv", "p"):                                  # compact token rows: only the active ones
+                w = {"xn": D, "kv": 2 * D, "p": H}[name]
+                a, b = a[:n_act * w], b[:n_act * w]
+            err = float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(a).max(), 1e-30))
+            good = err < 2e-5 and bool(np.isfinite(b).all())
+            ok = ok and good
+            print(json.dumps({"level": level, "region": name, "max_abs_diff_over_max": err, "ok": good}))
+        err = float(np.abs(base["out"].astype(np.float64) - got["out"]).max() / np.abs(base["out"]).max())
+        print(json.dumps({"level": level, "region": "out", "max_abs_diff_over_max": err, "ok": err < 2e-5}))
+        ok = ok and err < 2e-5
+    print("VERDICT:", "tensor-core encoder paths agree with the FFMA kernels stage by stage" if ok else "MISMATCH or failure (see the first bad region)")
+    sys.exit(0 if ok else 1)

@@ -23,6 +23,7 @@ grep '"stats": {' gpurun_out/${R}_tc16_variants_stats.jsonl | cut -c1-900
 # 3b. the 3xTF32 tcgen05 GEMM (csrc/gemm3_tf32.cu) on its own, then the encoder / model / train-step tests with it switched in
 timeout 300 python profiles/check_gemm3.py > gpurun_out/${R}_gemm3.jsonl 2>&1; G3=$?; cat gpurun_out/${R}_gemm3.jsonl
 if [ $G3 -eq 0 ]; then
+  timeout 400 python profiles/diff_enc_tc.py > gpurun_out/${R}_diff_enc_tc.jsonl 2>&1; grep -v '"ok": true\|"identical": true' gpurun_out/${R}_diff_enc_tc.jsonl | tail -8
   PSB_ENC_TC=1 timeout 600 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_models.py tests/test_gpu_train_step.py -m gpu -q \
       > gpurun_out/${R}_pytest_enc_tc.log 2>&1; echo "pytest (PSB_ENC_TC=1) exit $?" >> gpurun_out/${R}_pytest_enc_tc.log
   tail -3 gpurun_out/${R}_pytest_enc_tc.log
