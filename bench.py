@@ -12,7 +12,8 @@ P=18k items, V=32k words, d=128, 1 layer / 8 heads / ff 512, uprev_review_limit 
   e2e    : the same step through the module API from pinned HOST batches (H2D inside) + loss.item()
   roofline / extra : the dominant hand-written kernel of the step, and every hot-path kernel in the
            bandwidth regime on a 16M x 128 table (the regime the HBM-roofline target is defined on)
-  cpu_baseline : the oracle's CPU restatement of the same step on this box's host cores
+  cpu_baseline : the oracle's CPU restatement of the same step on this box's host cores; cpu_baseline.others: the
+           PV step (BASELINE configs[0]), 1M-item catalog ranking and gather / scatter-add on the same cores
   --impl reference : times that CPU path alone (all host threads), same metric / config
 """
 import argparse
@@ -175,6 +176,92 @@ def cpu_reference_step_time(steps, warmup, dropout, seed=666):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times), cores
+
+
+def cpu_reference_others(seed=666):
+    """The other CPU timings SURVEY.md 8(d) asks for next to the TEM step, each on a bounded sample (seconds of host
+    time in all): (ii) BASELINE configs[0], a ParagraphVector train step (models/PV.py:50-80 through the oracle port,
+    dense [R, d] table gradient + Adam as torch does it); (iii) full-catalog ranking over 1M items -- the reference's
+    literal path (scores [24, N] then a full argsort, trainer.py:136,:152) and the restated fair baseline (one GEMM +
+    torch.topk(100)); (iv) index_select / index_add_ on a large fp32 table.  All host threads."""
+    import numpy as np
+    import torch
+    import oracle
+    from prodsearch_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    d, V, K = WORKLOAD["embedding_size"], WORKLOAD["vocab_size"], WORKLOAD["neg_per_pos"]
+    out = {"cores": cores}
+
+    def median_time(fn, iters, warmup=1):
+        for _ in range(warmup):
+            fn()
+        ts = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts)
+
+    # (ii) PV train step: R = 300k reviews, N = 384 reviews per batch, one target word each, 5 negatives
+    R, N = 300_000, WORKLOAD["batch_per_gpu"]
+    review_table = torch.randn(R, d, generator=g).requires_grad_(True)
+    word_table = torch.randn(V, d, generator=g).requires_grad_(True)
+    opt = torch.optim.Adam([review_table, word_table], lr=WORKLOAD["lr"], eps=1e-9)
+    wd = torch.as_tensor(synth.word_dists(V))
+    rid = torch.randint(0, R - 1, (N,), generator=g)
+    pos_w = torch.multinomial(wd, N, replacement=True, generator=g).view(N, 1)
+    mask = torch.ones(N, 1, dtype=torch.uint8)
+
+    def pv_step():
+        neg_w = torch.multinomial(wd, N * K, replacement=True)
+        _, loss = oracle.pv_forward(review_table, word_table, rid, pos_w, mask, neg_w, K)
+        opt.zero_grad()
+        loss.mean().backward()
+        opt.step()
+    sec = median_time(pv_step, 5)
+    out["pv_train_step"] = {"value": N / sec, "unit": "reviews/s", "ms_per_step": sec * 1e3,
+                            "sample": "BASELINE configs[0]: 5 ParagraphVector steps (fwd + bwd + Adam), 384 reviews, "
+                                      "R = 300k x 128 review table, 5 negatives, oracle port"}
+    del review_table, word_table, opt
+    # (iii) full-catalog ranking over N = 1M items
+    n_items = 1_000_000
+    table = torch.randn(n_items, d, generator=g)
+    q24 = torch.randn(24, d, generator=g)
+    sec = median_time(lambda: oracle.reference_rank((q24 @ table.t()).numpy())[:, :100], 1, warmup=0)
+    out["catalog_rank_1M_literal"] = {"value": 24 / sec, "unit": "queries/s", "ms": sec * 1e3,
+                                      "sample": "one batch of 24 queries: scores [24, 1M] + full argsort (trainer.py:136,:152)"}
+    q = torch.randn(384, d, generator=g)
+
+    def gemm_topk():
+        best_s, best_i = None, None
+        for c0 in range(0, n_items, 250_000):                      # [384, 250k] score chunks: 384 MB each
+            sc, ix = torch.topk(q @ table[c0:c0 + 250_000].t(), 100, dim=1)
+            ix = ix + c0
+            if best_s is None:
+                best_s, best_i = sc, ix
+            else:
+                sc, sel = torch.topk(torch.cat([best_s, sc], 1), 100, dim=1)
+                best_s, best_i = sc, torch.gather(torch.cat([best_i, ix], 1), 1, sel)
+        return best_i
+    sec = median_time(gemm_topk, 2)
+    out["catalog_rank_1M_gemm_topk"] = {"value": 384 / sec, "unit": "queries/s", "ms": sec * 1e3,
+                                        "sample": "384 queries x 1M items: chunked GEMM + torch.topk(100) + merge (restated fair CPU baseline)"}
+    del table
+    # (iv) gather / scatter-add on a table far larger than the CPU caches (bounded: 4M rows = 2 GB, not 16M)
+    rows, n = 4_000_000, 1_000_000
+    big = torch.empty(rows, d).normal_(generator=g)
+    idx = synth.gather_indices(n, rows, seed=1, dist="uniform")
+    sec = median_time(lambda: big.index_select(0, idx), 3)
+    out["gather_rows"] = {"value": n * (d * 4 * 2 + 8) / sec / 1e9, "unit": "GB/s", "ms": sec * 1e3,
+                          "sample": "index_select of 1M uniform rows from a 4M x 128 fp32 table (2 GB)"}
+    src = torch.randn(n, d, generator=g)
+    acc = torch.zeros(rows, d)
+    sec = median_time(lambda: acc.index_add_(0, idx, src), 3)
+    out["scatter_add_rows"] = {"value": n * (d * 4 * 2 + 8) / sec / 1e9, "unit": "GB/s", "ms": sec * 1e3,
+                               "sample": "index_add_ of 1M uniform rows into a 4M x 128 fp32 table (aten::embedding_dense_backward's core)"}
+    return out
 
 
 def run_reference_arm(a):
@@ -730,6 +817,10 @@ def run_b200_arm(a):
         cpu = {"value": B / sec, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": "%d TEM train steps of batch 384 (fwd+bwd+clipped Adam) on the oracle port, %.0f ms/step"
                          % (a.cpu_steps, sec * 1e3)}
+        try:        # the other CPU timings of SURVEY.md 8(d): PV step, catalog ranking, gather / scatter-add (~20 s)
+            cpu["others"] = cpu_reference_others()
+        except Exception as ex:                                       # noqa: BLE001 -- reported, never fatal
+            cpu["others"] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:120])}
     value = B * a.steps * world / dev_sec
     line = {
         "metric": "tem_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
