@@ -452,10 +452,15 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
     float w0 = pw[h0], w1 = pw[h1], w2 = pw[h2], w3 = pw[h3];
     if (drop.on()) {
       const uint64_t t = static_cast<uint64_t>(tok[base + al]);
-      w0 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + t);
-      w1 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h1) * T + t);
-      w2 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h2) * T + t);
-      w3 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h3) * T + t);
+      const float m0 = drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + t);
+      if (h0 == h3) {                       // dh % 4 == 0: the lane's four columns belong to one head -> one draw
+        w0 *= m0; w1 *= m0; w2 *= m0; w3 *= m0;
+      } else {
+        w0 *= m0;
+        w1 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h1) * T + t);
+        w2 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h2) * T + t);
+        w3 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h3) * T + t);
+      }
     }
     const float4 v = *reinterpret_cast<const float4*>(kv + static_cast<size_t>(base + al) * 2 * d + d + j);
     acc.x = fmaf(w0, v.x, acc.x);
