@@ -178,12 +178,13 @@ def cpu_reference_step_time(steps, warmup, dropout, seed=666):
     return sum(times) / len(times), cores
 
 
-def cpu_reference_others(seed=666):
+def cpu_reference_others(seed=666, scale=1):
     """The other CPU timings SURVEY.md 8(d) asks for next to the TEM step, each on a bounded sample (seconds of host
     time in all): (ii) BASELINE configs[0], a ParagraphVector train step (models/PV.py:50-80 through the oracle port,
     dense [R, d] table gradient + Adam as torch does it); (iii) full-catalog ranking over 1M items -- the reference's
     literal path (scores [24, N] then a full argsort, trainer.py:136,:152) and the restated fair baseline (one GEMM +
-    torch.topk(100)); (iv) index_select / index_add_ on a large fp32 table.  All host threads."""
+    torch.topk(100)); (iv) index_select / index_add_ on a large fp32 table.  All host threads.  ``scale`` > 1 divides
+    the table sizes (the CPU test of this function)."""
     import numpy as np
     import torch
     import oracle
@@ -205,7 +206,7 @@ def cpu_reference_others(seed=666):
         return statistics.median(ts)
 
     # (ii) PV train step: R = 300k reviews, N = 384 reviews per batch, one target word each, 5 negatives
-    R, N = 300_000, WORKLOAD["batch_per_gpu"]
+    R, N = 300_000 // scale, WORKLOAD["batch_per_gpu"]
     review_table = torch.randn(R, d, generator=g).requires_grad_(True)
     word_table = torch.randn(V, d, generator=g).requires_grad_(True)
     opt = torch.optim.Adam([review_table, word_table], lr=WORKLOAD["lr"], eps=1e-9)
@@ -226,7 +227,8 @@ def cpu_reference_others(seed=666):
                                       "R = 300k x 128 review table, 5 negatives, oracle port"}
     del review_table, word_table, opt
     # (iii) full-catalog ranking over N = 1M items
-    n_items = 1_000_000
+    n_items = 1_000_000 // scale
+    chunk = max(n_items // 4, 100)
     table = torch.randn(n_items, d, generator=g)
     q24 = torch.randn(24, d, generator=g)
     sec = median_time(lambda: oracle.reference_rank((q24 @ table.t()).numpy())[:, :100], 1, warmup=0)
@@ -236,8 +238,8 @@ def cpu_reference_others(seed=666):
 
     def gemm_topk():
         best_s, best_i = None, None
-        for c0 in range(0, n_items, 250_000):                      # [384, 250k] score chunks: 384 MB each
-            sc, ix = torch.topk(q @ table[c0:c0 + 250_000].t(), 100, dim=1)
+        for c0 in range(0, n_items, chunk):                        # [384, 250k] score chunks: 384 MB each
+            sc, ix = torch.topk(q @ table[c0:c0 + chunk].t(), 100, dim=1)
             ix = ix + c0
             if best_s is None:
                 best_s, best_i = sc, ix
@@ -250,7 +252,7 @@ def cpu_reference_others(seed=666):
                                         "sample": "384 queries x 1M items: chunked GEMM + torch.topk(100) + merge (restated fair CPU baseline)"}
     del table
     # (iv) gather / scatter-add on a table far larger than the CPU caches (bounded: 4M rows = 2 GB, not 16M)
-    rows, n = 4_000_000, 1_000_000
+    rows, n = 4_000_000 // scale, 1_000_000 // scale
     big = torch.empty(rows, d).normal_(generator=g)
     idx = synth.gather_indices(n, rows, seed=1, dist="uniform")
     sec = median_time(lambda: big.index_select(0, idx), 3)

@@ -82,3 +82,14 @@ def test_guarded_section_prints_the_line_and_exits_zero_when_it_hangs():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = out.stdout.strip().splitlines()
     assert len(lines) == 1 and json.loads(lines[0]) == {"value": 1.0, "extra": {"unavailable": "watchdog"}}
+
+
+def test_cpu_reference_others_shape_of_the_entry():
+    """cpu_baseline.others (PV step, catalog ranking literal / GEMM + topk, gather / scatter-add on the
+    host cores), at 1/50 of the bench's table sizes: every entry carries value / unit / sample and a positive number."""
+    b = _bench_module()
+    out = b.cpu_reference_others(scale=50)
+    assert out["cores"] >= 1
+    for key, unit in (("pv_train_step", "reviews/s"), ("catalog_rank_1M_literal", "queries/s"),
+                      ("catalog_rank_1M_gemm_topk", "queries/s"), ("gather_rows", "GB/s"), ("scatter_add_rows", "GB/s")):
+        assert out[key]["unit"] == unit and out[key]["value"] > 0 and out[key]["sample"], key
