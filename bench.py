@@ -884,7 +884,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--extra-timeout", type=int, default=240, dest="extra_timeout",
+    ap.add_argument("--extra-timeout", type=int, default=120, dest="extra_timeout",
                     help="seconds the 16M-row section (extra) may take before the line is printed without it")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],
                     help="N>1: auto = NVLink peer memory when CUDA IPC works, else NCCL all-to-all; nccl forces the latter")
