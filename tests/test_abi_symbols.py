@@ -119,3 +119,20 @@ def test_ctypes_signatures_match_the_header_prototypes():
                                      and base != "psb_stream_t") else _ctype_class(p))
         assert got == want, "%s: header %s, ctypes %s" % (name, want, got)
         assert cls(res) == ("ptr" if "*" in ret else _ctype_class(ret)), "%s: return type" % name
+
+
+def test_stage_diff_script_layout_matches_the_library():
+    """profiles/diff_enc_tc.py restates encoder_common.cuh's saved_layout to name the regions it compares: its total has
+    to be what psb_encoder_saved_bytes reports for the same configuration (a host-side size query, no GPU)."""
+    import importlib.util
+    from prodsearch_b200 import _lib
+    spec = importlib.util.spec_from_file_location("diff_enc_tc", os.path.join(ROOT, "profiles", "diff_enc_tc.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    cfg = _lib.EncoderCfg()
+    cfg.S, cfg.T, cfg.d, cfg.heads, cfg.ff, cfg.copies, cfg.out_pos = m.S, m.T, m.D, m.H, m.FF, m.C, 0
+    cfg.ln_eps, cfg.p_drop = 1e-6, 0.0
+    cfg.first = cfg.table = cfg.idx = 16            # non-null, aligned stand-ins: the query only validates them
+    cfg.table_rows = 10
+    total = sum(n for _, n in m.layout().values())
+    assert _lib.load().psb_encoder_saved_bytes(ctypes.byref(cfg)) == 4 * total
