@@ -185,7 +185,6 @@ def cpu_reference_others(seed=666, scale=1):
     literal path (scores [24, N] then a full argsort, trainer.py:136,:152) and the restated fair baseline (one GEMM +
     torch.topk(100)); (iv) index_select / index_add_ on a large fp32 table.  All host threads.  ``scale`` > 1 divides
     the table sizes (the CPU test of this function)."""
-    import numpy as np
     import torch
     import oracle
     from prodsearch_b200 import synth
