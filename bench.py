@@ -410,6 +410,30 @@ def bandwidth_regime(peaks, rows=16_000_000, d=128):
     return out
 
 
+def variant3_side_measurement(peaks):
+    """The measured-but-not-yet-default main-pass kernel of the fp16 shortlist (PSB_TC16_EPI=3) next
+    to the default one, each in its own subprocess under a timeout (the knob is read once per process): same seeded
+    1M-item table, lists compared by digest.  Reported as a labelled variant; no other number depends on it."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "check_tc16_v2.py"), "--quick", "--variants", "3"],
+                           capture_output=True, text=True, timeout=100)
+        rows_ = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+        runs = {(j.get("epi"), j.get("m")): j for j in rows_ if "sha" in j}
+        cmp_ = []
+        for j in rows_:
+            if "variant" in j:
+                v3 = runs.get(("3", j["m"]), {})
+                cmp_.append({"m": j["m"], "identical_lists": j["identical"], "default_ms": j["v1_ms"], "variant_ms": j["ms"],
+                             "speedup": j["speedup"], "variant_queries_per_s": j["m"] / (j["ms"] * 1e-3) if j["ms"] else None,
+                             "variant_tflops": v3.get("tflops"),
+                             "variant_frac_of_tensor_peak": v3["tflops"] / peaks["bf16"] if v3.get("tflops") else None})
+        return {"knob": "PSB_TC16_EPI=3 (per-query-tile accumulator hand-off + MMA issue from a converged warp); off by default",
+                "table": "1M x 128, top-100, whole psb_catalog_topk_f16 call", "exit": r.returncode, "runs": cmp_,
+                "errors": [dict(j, error=str(j["error"])[-200:]) for j in rows_ if "error" in j][:2]}
+    except Exception as ex:                                           # noqa: BLE001 -- a side measurement, never fatal
+        return {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:120])}
+
+
 def guarded(fn, seconds, on_timeout):
     """Run fn() with a watchdog: if it has not returned after ``seconds``, on_timeout() runs on the watchdog thread
     and the process exits with status 0.  extra.sharded_16M contains collectives and peer-memory kernels that had no
@@ -849,6 +873,12 @@ def run_b200_arm(a):
                              "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
         except Exception as ex:                                       # noqa: BLE001 -- the headline line must appear
             line["extra"] = {"bandwidth_regime": {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}}
+        if not a.no_variants:
+            # a side measurement in subprocesses, after everything else is final, under its own watchdog
+            def give_up_v3():
+                line["extra"]["G5_catalog_topk_1M_variant3"] = {"unavailable": "no result after 110 s (watchdog)"}
+                print(json.dumps(line))
+            line["extra"]["G5_catalog_topk_1M_variant3"] = guarded(lambda: variant3_side_measurement(peaks), 110, give_up_v3)
     if do_sharded:
         # everything above is final; the 16M-row section runs last, under a watchdog that prints the line without it
         def give_up():
@@ -883,6 +913,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true", dest="no_variants",
+                    help="skip the side measurement of the off-by-default fp16 shortlist variant (subprocesses, ~20 s)")
     ap.add_argument("--extra-timeout", type=int, default=120, dest="extra_timeout",
                     help="seconds the 16M-row section (extra) may take before the line is printed without it")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],
