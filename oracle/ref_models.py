@@ -39,23 +39,26 @@ def masked_mean(x, mask):
     return total / count.to(x.dtype)
 
 
-def avg_encoder(x, mask, p=0.0, training=False):
-    """AVGEncoder.forward, models/text_encoder.py:75-82 (mean -> nn.Dropout)."""
-    return F.dropout(masked_mean(x, mask), p=p, training=training)
+def avg_encoder(x, mask, p=0.0, training=False, keep_mul=None):
+    """AVGEncoder.forward, models/text_encoder.py:75-82 (mean -> nn.Dropout).  ``keep_mul`` [N,d] supplies the
+    dropout multipliers (0 or 1/(1-p)) instead of drawing them (parity runs under dropout)."""
+    mean = masked_mean(x, mask)
+    return mean * keep_mul if keep_mul is not None else F.dropout(mean, p=p, training=training)
 
 
-def fs_encoder(x, mask, weight, bias, p=0.0, training=False):
+def fs_encoder(x, mask, weight, bias, p=0.0, training=False, keep_mul=None):
     """FSEncoder.forward, models/text_encoder.py:32-40 (mean -> dropout -> tanh(W x + b))."""
-    mean = F.dropout(masked_mean(x, mask), p=p, training=training)
+    mean = masked_mean(x, mask)
+    mean = mean * keep_mul if keep_mul is not None else F.dropout(mean, p=p, training=training)
     return torch.tanh(F.linear(mean, weight, bias))
 
 
-def query_encoder(P, cfg, word_emb, mask, training=False):
+def query_encoder(P, cfg, word_emb, mask, training=False, keep_mul=None):
     """Dispatch used at models/item_transformer.py:80-83,:450 / models/ps_model.py:153-156,:258."""
     if cfg.query_encoder_name == "fs":
         return fs_encoder(word_emb, mask, P["query_encoder.f_W.weight"],
-                          P["query_encoder.f_W.bias"], cfg.dropout, training)
-    return avg_encoder(word_emb, mask, cfg.dropout, training)
+                          P["query_encoder.f_W.bias"], cfg.dropout, training, keep_mul)
+    return avg_encoder(word_emb, mask, cfg.dropout, training, keep_mul)
 
 
 # --------------------------------------------------------------------------
@@ -216,17 +219,20 @@ def item_to_words(P, cfg, target_prod_idxs, target_word_idxs, neg_word_idxs, n_n
 # --------------------------------------------------------------------------
 # TEM  (models/item_transformer.py)
 # --------------------------------------------------------------------------
-def tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training=False, copies=1):
+def tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training=False, copies=1, q_emb=None, muls=None):
     """Shared front half of forward_dotproduct (:449-484) and test_dotproduct
     (:118-140): query encoder + history gather + transformer encode -> [B*copies,d].
 
     ``copies`` replays the reference's expansion of the same sequence for every
-    negative / candidate (:473-476, :130-133)."""
+    negative / candidate (:473-476, :130-133).  ``q_emb``: the query vector computed once by the caller
+    (the reference encodes the query once, :450, and feeds it to both encoder calls); ``muls``: supplied
+    dropout multipliers of the (last) encoder layer for the B*copies sequences (encoder_layer)."""
     V = P["word_embeddings.weight"].shape[0]
     Pp1 = P["product_emb.weight"].shape[0]
     B, L = u_item_idxs.shape
-    q_emb = query_encoder(P, cfg, P["word_embeddings.weight"][query_word_idxs],
-                          query_word_idxs.ne(V - 1), training)
+    if q_emb is None:
+        q_emb = query_encoder(P, cfg, P["word_embeddings.weight"][query_word_idxs],
+                              query_word_idxs.ne(V - 1), training)
     hist_table = P["hist_product_emb.weight"] if cfg.sep_prod_emb else P["product_emb.weight"]
     u_emb = hist_table[u_item_idxs]
     seq = torch.cat([q_emb.unsqueeze(1), u_emb], dim=1)                   # [B,1+L,d]
@@ -235,21 +241,31 @@ def tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training=False, cop
         seq = seq.unsqueeze(1).expand(-1, copies, -1, -1).reshape(B * copies, 1 + L, -1)
         mask = mask.unsqueeze(1).expand(-1, copies, -1).reshape(B * copies, 1 + L)
     out_pos = -1 if cfg.use_item_pos else 0
-    top = encoder_encode(P, cfg, seq, mask, cfg.use_pos_emb, training=training)
+    top = encoder_encode(P, cfg, seq, mask, cfg.use_pos_emb, training=training, last_layer_muls=muls)
     return top[:, out_pos, :]
 
 
 def tem_forward(P, cfg, query_word_idxs, target_prod_idxs, u_item_idxs, pos_iword_idxs,
-                neg_item_idxs, neg_word_idxs, training=False):
+                neg_item_idxs, neg_word_idxs, training=False, drop=None):
     """ItemTransformerRanker.forward_dotproduct, models/item_transformer.py:440-520.
 
     neg_item_idxs [B,K] replaces the multinomial at :447, neg_word_idxs [B*W*K] the
-    one at :268.  Returns (loss, ps_loss, item_loss) as 0-dim tensors."""
+    one at :268.  ``drop`` (parity under dropout > 0): dict(query_keep [B,d], enc_pos, enc_neg) -- the
+    multipliers of the query encoder's dropout (drawn ONCE, :450) and of the two encoder calls (:479, :482-486;
+    dicts as encoder_layer takes them, for B and B*K sequences).  Returns (loss, ps_loss, item_loss)."""
     B = target_prod_idxs.shape[0]
     K = cfg.neg_per_pos
     E = P["product_emb.weight"]
-    pos_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training)          # [B,d]
-    neg_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training, copies=K)  # [B*K,d]
+    if drop is not None:
+        V = P["word_embeddings.weight"].shape[0]
+        q_emb = query_encoder(P, cfg, P["word_embeddings.weight"][query_word_idxs], query_word_idxs.ne(V - 1),
+                              True, drop["query_keep"])
+        pos_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, True, q_emb=q_emb, muls=drop["enc_pos"])
+        neg_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, True, copies=K, q_emb=q_emb,
+                                     muls=drop["enc_neg"])
+    else:
+        pos_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training)          # [B,d]
+        neg_out = tem_encode_queries(P, cfg, query_word_idxs, u_item_idxs, training, copies=K)  # [B*K,d]
     pos_scores = torch.bmm(pos_out.unsqueeze(1), E[target_prod_idxs].unsqueeze(2)).view(B)
     neg_scores = torch.bmm(neg_out.unsqueeze(1), E[neg_item_idxs].view(B * K, -1).unsqueeze(2)).view(B, K)
     if cfg.sim_func == "bias_product":

@@ -135,6 +135,15 @@ SIGNATURES = {
 
 _lib = None
 
+# Parameter-write epoch: psb_adam_step and CUDA-graph replays update parameters through raw pointers, so
+# ``tensor._version`` does not change.  Every such writer bumps this counter; caches derived from parameter
+# values (the fp16 shortlist copy of the item table, its row-norm bound) carry it in their key.
+PARAM_EPOCH = [0]
+
+
+def note_param_write():
+    PARAM_EPOCH[0] += 1
+
 
 def load():
     """Load the shared library (once).  Raises if it has not been built."""

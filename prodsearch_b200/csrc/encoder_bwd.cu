@@ -283,12 +283,12 @@ template <int R>
 static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
   const Dims& D = a.D;
   const size_t smem = tail_bwd_smem_floats(R, D.d, D.F, D.H, D.T, D.spt) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DeviceAttr configured;
+  if (configured.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(tail_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
+    configured.done(smem);
   }
   PSB_PROF("tail_bwd_kernel", s);
   tail_bwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);

@@ -266,12 +266,12 @@ int launch_rows_gemm(const float* A, int lda, const int32_t* m_dev, int m_host, 
                      int J, const float* bias, float* out, int ldo, cudaStream_t s) {
   constexpr int R = 16;
   const size_t smem = (static_cast<size_t>(a4_floats(R, I)) + red_floats(R, J)) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DeviceAttr configured;
+  if (configured.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(rows_gemm_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
+    configured.done(smem);
   }
   const int grid = (m_max + R - 1) / R;
   if (grid <= 0) return PSB_OK;
@@ -500,12 +500,12 @@ template <int R>
 static int launch_tail_fwd(const TailFwdArgs& a, cudaStream_t s) {
   const Dims& D = a.D;
   const size_t smem = tail_smem_floats(R, D.d, D.F, D.H, D.T) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DeviceAttr configured;
+  if (configured.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(tail_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
+    configured.done(smem);
   }
   PSB_PROF("tail_fwd_kernel", s);
   tail_fwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);

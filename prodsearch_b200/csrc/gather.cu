@@ -391,12 +391,12 @@ static int launch_meanpool(const float* table, int64_t table_rows, int64_t d, co
   PSB_PROF("meanpool_kernel", s);
   if (fs_weight != nullptr && C == 1) {
     const size_t smem = (static_cast<size_t>(d) * (d / 4 + 1) + 8 * (d / 4)) * sizeof(float4);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static DeviceAttr configured;
+    if (configured.need(smem)) {
       cudaError_t e = cudaFuncSetAttribute(meanpool_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
       if (e != cudaSuccess) return static_cast<int>(e);
-      configured = smem;
+      configured.done(smem);
     }
     const int grid_w = grid_for(n, 8, 2);            // W is re-staged per CTA: few, persistent CTAs
     meanpool_kernel<1, true, true><<<grid_w, 256, smem, s>>>(t4, table_rows, static_cast<int>(d / 4), idx, n,

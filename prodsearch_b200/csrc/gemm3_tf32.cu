@@ -385,12 +385,12 @@ static int g3_launch(const char* name, const float* A, int lda, const int32_t* m
                      const float* Bt0, const float* Bt1, int split, int J, const Epi& epi, cudaStream_t s) {
   using C = G3Cfg<N, KC>;
   if (m_max <= 0) return PSB_OK;
-  static bool attr_done = false;                            // one flag per instantiation
-  if (!attr_done) {
+  static DeviceAttr attr_done;                            // one flag per instantiation
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(gemm3_tf32_kernel<N, KC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(C::kSmem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
+    attr_done.done();
   }
   alignas(64) CUtensorMap map_a, map_b0, map_b1;
   const int rows0 = Bt1 != nullptr ? split : J;

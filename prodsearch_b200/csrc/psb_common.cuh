@@ -20,6 +20,15 @@ inline int check_table_args(const void* table, int64_t rows, int64_t d) {
   return PSB_OK;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so "already configured" is remembered per device (a process
+// may drive several GPUs: the single-process peer simulation, multi-device tests).
+struct DeviceAttr {
+  size_t bytes[64] = {};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool need(size_t want = 1) const { return want > bytes[dev()]; }
+  void done(size_t want = 1) { bytes[dev()] = want; }
+};
+
 inline bool misaligned16(const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 
 // Per-kernel timing (runtime.cu): when psb_profile_enable(1) is in effect, PSB_PROF records a CUDA event on the

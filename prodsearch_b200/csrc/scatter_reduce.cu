@@ -979,14 +979,14 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
 
   const int64_t cs_per = ((table_rows + 1 + kSmallNT - 1) / kSmallNT) | 1;   // odd number of bins per thread
   if (n_total <= kSmallCap && cs_per <= kCsMaxPer) {
-    static size_t attr_smem = 0;
+    static DeviceAttr attr_smem;
     const size_t smem = static_cast<size_t>(cs_per) * kSmallNT * 4 + kCsBitmaps * 512 * 4 + (kCsMaxLong + 3) * 4 +
                         static_cast<size_t>(kSmallCap) * 2 + kCsBitmaps * 512 * 2 + 33 * 4;
-    if (smem > attr_smem) {
+    if (attr_smem.need(smem)) {
       cudaError_t e = cudaFuncSetAttribute(count_sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
       if (e != cudaSuccess) return static_cast<int>(e);
-      attr_smem = smem;
+      attr_smem.done(smem);
     }
     PSB_PROF("count_sort_segments_kernel", s);
     count_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,
@@ -996,13 +996,13 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     sorted_slots = vals_a;
     sorted_keys = keys_a;
   } else if (n_total <= kSmallCap) {
-    static bool attr_set = false;
+    static DeviceAttr attr_set;
     const size_t smem = static_cast<size_t>(kSmallCap) * 8 + (kSmallNT / 32) * 256 * 4 + 256 * 4 + 32 * 4;
-    if (!attr_set) {
+    if (attr_set.need()) {
       cudaError_t e = cudaFuncSetAttribute(small_sort_segments_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return static_cast<int>(e);
-      attr_set = true;
+      attr_set.done();
     }
     PSB_PROF("small_sort_segments_kernel", s);
     small_sort_segments_kernel<<<1, kSmallNT, smem, s>>>(T, static_cast<int>(n_total), table_rows, drop_idx,

@@ -97,8 +97,10 @@ def rank_test_set(model, corpus, entries, args, k=100, batch_size=4096, mode=Non
 
 def test(model, corpus, entries, args, user_ids, product_ids, rank_path=None, cutoff=100, batch_size=4096):
     """Trainer.test (trainer.py:140-169): rank, report MRR / P@1, write the run file."""
-    ids, scores, target, q_idx, u_idx = rank_test_set(model, corpus, entries, args, k=max(cutoff, 1),
-                                                      batch_size=batch_size)
+    # cutoff < 0 = "no cutoff" (calc_metrics); the reference writes min(cutoff, candidate_size) rows (trainer.py:164)
+    n_items = int(corpus.prod_pad_idx)
+    k = n_items if cutoff < 0 else max(1, min(int(cutoff), n_items))
+    ids, scores, target, q_idx, u_idx = rank_test_set(model, corpus, entries, args, k=k, batch_size=batch_size)
     mrr, prec = calc_metrics(target_ranks(ids, target), cutoff)
     if rank_path is not None:
         write_ranklist(rank_path, user_ids, u_idx, q_idx, product_ids, ids, scores, cutoff)

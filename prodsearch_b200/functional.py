@@ -99,9 +99,17 @@ class RowGradSink(object):
             chunk = pending[lo:lo + ops._lib.MAX_CONTRIBS]
             first = lo == 0
             if self.mode == "dense":
-                self._prepare_dense(want_bias, clear=first)
                 if not first:
                     raise RuntimeError("more than %d contributions to one table in a step" % ops._lib.MAX_CONTRIBS)
+                # A second backward() without zero_grad (micro-batch accumulation, two losses sharing a table):
+                # param.grad IS the persistent buffer and holds the earlier gradient -- reduce this pass into a
+                # scratch buffer and add it, as AccumulateGrad does for the dense parameters.
+                acc_w = w.grad is not None and w.grad is self._dense
+                acc_b = want_bias and self.bias.grad is not None and self.bias.grad is self._dense_bias
+                if acc_w or acc_b:
+                    self._accumulate_dense(chunk, rows, d, want_bias)
+                    continue
+                self._prepare_dense(want_bias, clear=first)
                 n_total = sum(int(c.n) for c, _ in chunk)
                 if self._uniq_buf is None or self._uniq_buf.numel() < n_total:
                     self._uniq_buf = torch.empty(max(n_total, 1), dtype=torch.int32, device=w.device)
@@ -121,6 +129,33 @@ class RowGradSink(object):
                 if want_bias:
                     self.bias.row_grad = (uniq, redb, nu)
 
+    def _accumulate_dense(self, chunk, rows, d, want_bias):
+        """Gradient accumulation into the persistent buffers: row-sparse reduce of this pass, then a deterministic
+        indexed add (every row occurs once in the reduced list).  The touched-row list of the buffers is now a
+        union nobody tracks, so the next clear is a full memset."""
+        w = self.weight
+        uniq, red, redb, nu = ops.scatter_reduce(chunk, rows, d, self.drop_idx, want_rows=True, want_bias=want_bias,
+                                                 device=w.device)
+        n = int(nu.item())
+        r = uniq[:n].long()
+        if w.grad is None:                 # only the bias was accumulating
+            self._prepare_dense(False, clear=True)
+            self._dense.index_add_(0, r, red[:n])
+            w.grad = self._dense
+        else:
+            w.grad.index_add_(0, r, red[:n])
+        if want_bias:
+            if self.bias.grad is None:
+                if self._dense_bias is None:
+                    self._dense_bias = torch.zeros_like(self.bias)
+                else:
+                    self._dense_bias.zero_()
+                self._dense_bias.index_add_(0, r, redb[:n])
+                self.bias.grad = self._dense_bias
+            else:
+                self.bias.grad.index_add_(0, r, redb[:n])
+        self._prev = "all"
+
     def _prepare_dense(self, want_bias, clear):
         w = self.weight
         if self._dense is None:
@@ -129,8 +164,8 @@ class RowGradSink(object):
         if want_bias and self._dense_bias is None:
             self._dense_bias = torch.zeros_like(self.bias)
         if clear and self._prev is not None:
-            uniq, nu = self._prev
-            if w.numel() * 4 <= (64 << 20):       # small table: a memset beats a row list
+            uniq, nu = self._prev if self._prev != "all" else (None, None)
+            if uniq is None or w.numel() * 4 <= (64 << 20):       # small table: a memset beats a row list
                 self._dense.zero_()
                 if self._dense_bias is not None:
                     self._dense_bias.zero_()
@@ -231,6 +266,44 @@ class NSLossFn(Function):
         if ctx.has_b and ctx.needs_input_grad[1]:
             grad_b = gb * g.repeat_interleave(k).unsqueeze(1)
         return grad_a, grad_b, None, None, None, None, None, None, None, None, None, None
+
+
+class DensePosLossFn(Function):
+    """Positive half of the NS loss against ALREADY GATHERED target rows [n, w, d] -- the reference's call form of
+    ParagraphVector.forward / ParagraphVectorCorruption.forward (PV.py:50, PVC.py:69 take ``review_word_emb``, the
+    output of ``word_embeddings(idx)``).  Same kernel, identity index over the flattened rows; the gradient goes back
+    to the dense tensor through autograd (and from there into whatever produced it), not into a sink."""
+
+    @staticmethod
+    def forward(ctx, anchor, dense, mask):
+        n, w, d = dense.shape
+        flat = dense.contiguous().view(n * w, d)
+        idx = torch.arange(n * w, device=dense.device).view(n, w)
+        loss, cp, _, ga, _ = ops.ns_loss(anchor.contiguous(), flat, idx, idx.new_empty((n, w, 0)), mask=mask)
+        ctx.save_for_backward(anchor, cp, ga)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        anchor, cp, ga = ctx.saved_tensors
+        g = g.contiguous()
+        grad_anchor = ga * g.unsqueeze(1) if ctx.needs_input_grad[0] else None
+        grad_dense = None
+        if ctx.needs_input_grad[1]:
+            grad_dense = anchor.unsqueeze(1) * (cp * g.unsqueeze(1)).unsqueeze(-1)
+        return grad_anchor, grad_dense, None
+
+
+def ns_loss_dense_pos(anchor, dense_pos, table, neg_idx, sink, mask=None):
+    """NS loss with the positive rows given as a dense tensor [n, w, d] and the negatives as indices into ``table``
+    (the reference's PV / PVC forward signature).  Two launches of the fused kernel: positives by identity index over
+    the dense rows (k = 0), negatives with the positive term weighted 0 (its index is the dropped pad row); both
+    halves are masked means over the same mask, so their sum is the reference's loss [n]."""
+    n, w, _ = dense_pos.shape
+    pos = DensePosLossFn.apply(anchor, dense_pos, mask)
+    pad = torch.full((n, w), table.shape[0] - 1, dtype=torch.int64, device=table.device)
+    neg = NSLossFn.apply(anchor, None, table, None, pad, neg_idx, sink, -1, mask, None, 0.0, None)
+    return pos + neg
 
 
 class SeqEncoderFn(Function):

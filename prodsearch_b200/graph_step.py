@@ -12,6 +12,8 @@ import argparse
 
 import torch
 
+from . import _lib
+
 
 class GraphedTrainStep(object):
     def __init__(self, model, optim, sample_batch, pad_values=None, warmup=3, sync_grads=None):
@@ -25,7 +27,6 @@ class GraphedTrainStep(object):
         for k, v in vars(sample_batch).items():
             setattr(self.static, k, v.to(dev).clone() if torch.is_tensor(v) else v)
         self.sync_grads = sync_grads
-        from . import _lib
         snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -117,4 +118,5 @@ class GraphedTrainStep(object):
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        _lib.note_param_write()        # the replayed optimizer wrote the parameters behind autograd's back
         return self.loss

@@ -231,7 +231,7 @@ class ItemTransformerRanker(nn.Module):
     def _max_row_sqnorm(self):
         """|e|^2 bound of the tensor-core shortlist, cached while the item table is unchanged."""
         w = self.product_emb.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, _lib.PARAM_EPOCH[0])
         if getattr(self, "_norm_cache", (None, None))[0] != key:
             self._norm_cache = (key, ops.table_max_row_sqnorm(w, self.prod_pad_idx))
         return self._norm_cache[1]
@@ -239,7 +239,7 @@ class ItemTransformerRanker(nn.Module):
     def _prepared_catalog(self):
         """fp16 shortlist copy of the item table, rebuilt when the table changes (evaluation: once)."""
         w = self.product_emb.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, _lib.PARAM_EPOCH[0])      # FusedAdam / graph replays bump the epoch
         if getattr(self, "_prep_cache", (None, None))[0] != key:
             self._prep_cache = (key, ops.catalog_prepare_f16(w.detach(), self.prod_pad_idx))
         return self._prep_cache[1]
@@ -532,7 +532,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         w = self.item_table.weight.detach()
         prepared = None
         if mode == _lib.TOPK_TC16:
-            key = (w.data_ptr(), self.item_table.weight._version, n_local)
+            key = (w.data_ptr(), self.item_table.weight._version, n_local, _lib.PARAM_EPOCH[0])
             if getattr(self, "_shard_prep", (None, None))[0] != key:
                 self._shard_prep = (key, ops.catalog_prepare_f16(w, n_local))
             prepared = self._shard_prep[1]

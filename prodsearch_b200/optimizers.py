@@ -87,6 +87,7 @@ class FusedAdam(object):
                                      self._sqnorm.data_ptr(),
                                      self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()), "psb_adam_step")
         self._norm_given = 0
+        _lib.note_param_write()        # raw-pointer update: tensor._version does not move
         if ev is not None:
             ev[1].record()
             ops.PROFILE.setdefault("adam_step", []).append(ev)

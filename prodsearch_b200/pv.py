@@ -6,9 +6,11 @@ from . import functional as F_
 
 
 class ParagraphVector(nn.Module):
-    """Same constructor as models/PV.py:16.  ``forward`` takes the target-word INDICES where the
-    reference takes their gathered embeddings: gathering them first is exactly the [N,W,d]
-    round trip the fused kernel removes (documented in INTEGRATION.md)."""
+    """Same constructor as models/PV.py:16.  ``forward`` accepts both call forms: the reference's
+    ``(review_ids, review_word_emb [N,W,d], review_word_mask, n_negs)`` (PV.py:50; the caller has gathered
+    the target-word rows, their gradient returns through autograd) and the fused form with the target-word
+    INDICES [N,W] in the same argument position, which skips the [N,W,d] round trip (what the model classes
+    of this package pass)."""
 
     def __init__(self, word_embeddings, word_dists, review_count, dropout=0.0, pretrain_emb_path=None,
                  fix_emb=False, word_sink=None):
@@ -39,8 +41,10 @@ class ParagraphVector(nn.Module):
         return F_.gather_rows(self.review_embeddings.weight, review_ids, self.review_sink)
 
     def forward(self, review_ids, review_word_idxs, review_word_mask, n_negs):
-        """PV.py:50-80 -> (review_emb [N,d], loss [N,1])."""
-        n, w = review_word_idxs.shape
+        """PV.py:50-80 -> (review_emb [N,d], loss [N,1]).  ``review_word_idxs``: int64 indices [N,W], or the
+        reference's dense ``review_word_emb`` [N,W,d]."""
+        dense = review_word_idxs.is_floating_point()
+        n, w = review_word_idxs.shape[:2]
         review_emb = self.get_para_vector(review_ids)
         keep = F_._dropout_keep(review_emb.shape, self.dropout_, self.training, review_emb.device)
         if keep is not None:
@@ -49,8 +53,13 @@ class ParagraphVector(nn.Module):
             neg = self.injected_negatives
         else:
             neg = torch.multinomial(self.word_dists, n * w * n_negs, replacement=True)
-        loss = F_.ns_loss(review_emb, self.word_embeddings.weight, review_word_idxs, neg.view(n, w, n_negs),
-                          self.word_sink, mask=review_word_mask.to(torch.uint8).contiguous())
+        mask = review_word_mask.to(torch.uint8).contiguous()
+        if dense:
+            loss = F_.ns_loss_dense_pos(review_emb, review_word_idxs, self.word_embeddings.weight,
+                                        neg.view(n, w, n_negs), self.word_sink, mask=mask)
+        else:
+            loss = F_.ns_loss(review_emb, self.word_embeddings.weight, review_word_idxs, neg.view(n, w, n_negs),
+                              self.word_sink, mask=mask)
         return review_emb, loss.unsqueeze(-1)
 
     def initialize_parameters(self, logger=None):

@@ -54,9 +54,10 @@ class ParagraphVectorCorruption(nn.Module):
                            pad_idx=self.word_pad_idx, tok_scale=scale)
 
     def forward(self, review_word_idxs, review_word_mask, prod_rword_idxs_pvc, n_negs):
-        """PVC.py:69-95 -> (uncorrupted review_emb [N,d], loss [N,1]); review_word_idxs are the
-        target-word indices (the reference passes their embeddings)."""
-        n, w = review_word_idxs.shape
+        """PVC.py:69-95 -> (uncorrupted review_emb [N,d], loss [N,1]).  ``review_word_idxs``: the target-word
+        indices [N,W] (fused form) or the reference's dense ``review_word_emb`` [N,W,d] (PVC.py:69)."""
+        dense = review_word_idxs.is_floating_point()
+        n, w = review_word_idxs.shape[:2]
         table = self.context_embeddings.weight
         review_emb = F_.meanpool(table, prod_rword_idxs_pvc, self.word_sink, pad_idx=self.word_pad_idx)
         # the reference draws the mask even at rate 0 (PVC.py:78); rate 0 keeps every token
@@ -66,8 +67,13 @@ class ParagraphVectorCorruption(nn.Module):
             neg = self.injected_negatives
         else:
             neg = torch.multinomial(self.word_dists, n * w * n_negs, replacement=True)
-        loss = F_.ns_loss(corr, self.word_embeddings.weight, review_word_idxs, neg.view(n, w, n_negs),
-                          self.word_sink, mask=review_word_mask.to(torch.uint8).contiguous())
+        mask = review_word_mask.to(torch.uint8).contiguous()
+        if dense:
+            loss = F_.ns_loss_dense_pos(corr, review_word_idxs, self.word_embeddings.weight, neg.view(n, w, n_negs),
+                                        self.word_sink, mask=mask)
+        else:
+            loss = F_.ns_loss(corr, self.word_embeddings.weight, review_word_idxs, neg.view(n, w, n_negs),
+                              self.word_sink, mask=mask)
         return review_emb, loss.unsqueeze(-1)
 
     def initialize_parameters(self, logger=None):

@@ -155,6 +155,7 @@ def make_tem(name, seed, **kw):
 # ---------------------------------------------------------------- encoders / PV / PVC
 def make_text(seed=11):
     from models.text_encoder import get_vector_mean, FSEncoder, AVGEncoder
+    torch.manual_seed(seed)            # parameters come from the global RNG: seeded, so the file reproduces bit for bit
     g = torch.Generator().manual_seed(seed)
     N, W, d = 7, 5, 128
     x = torch.randn(N, W, d, generator=g, requires_grad=True)
@@ -179,6 +180,7 @@ def make_text(seed=11):
 
 def make_pv(seed=21):
     from models.PV import ParagraphVector
+    torch.manual_seed(seed)            # parameters come from the global RNG: seeded, so the file reproduces bit for bit
     g = torch.Generator().manual_seed(seed)
     V, R, N, W, K, d = 50, 41, 10, 3, 4, 128
     wemb = torch.nn.Embedding(V, d, padding_idx=V - 1)
@@ -209,6 +211,7 @@ def make_pv(seed=21):
 
 def make_pvc(seed=31):
     from models.PVC import ParagraphVectorCorruption
+    torch.manual_seed(seed)            # parameters come from the global RNG: seeded, so the file reproduces bit for bit
     g = torch.Generator().manual_seed(seed)
     V, N, W, K, Wr, d, rate = 50, 9, 2, 3, 12, 128, 0.5
     wemb = torch.nn.Embedding(V, d, padding_idx=V - 1)

@@ -49,7 +49,7 @@ def check_grads(model, G, rtol=1e-4, atol=2e-6):
 
 
 # ---------------------------------------------------------------- TEM vs golden
-@pytest.mark.parametrize("name", ["tem_fs", "tem_avg_bias", "tem_d128"])
+@pytest.mark.parametrize("name", ["tem_fs", "tem_avg_bias", "tem_d128", "tem_itempos"])
 @pytest.mark.parametrize("grad_mode", ["dense", "rowsparse"])
 def test_tem_golden(name, grad_mode):
     from prodsearch_b200.item_transformer import ItemTransformerRanker
