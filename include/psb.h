@@ -373,6 +373,54 @@ int psb_adam_step(const psb_adam_tensor_t* tensors /* host */, int32_t n_tensors
 int psb_grad_sqnorm(const psb_adam_tensor_t* tensors /* host; only g and n are read */, int32_t n_tensors,
                     float* sqnorm_out, void* workspace, int64_t workspace_bytes, psb_stream_t stream);
 
+/* Row-sparse Adam for embedding tables (SURVEY.md 8(f) N2 as written: "consume G2's (unique_rows, grad_rows)
+ * directly ... lazy per-row step counters").  Replaces, for the tables, the dense sweep of
+ * torch.optim.Adam(eps=1e-9) + clip_grad_norm_ (models/optimizers.py:186,:205-243) by work proportional to the rows
+ * a step touches, with DENSE-EQUIVALENT results: a row that rests for k steps is replayed when it is next read or
+ * updated -- its first min(k, psb_adam_catchup_steps) zero-gradient updates exactly (they shrink like
+ * (b1/sqrt(b2))^j and are below 1e-12 of the first one after that), the decay of its moments beyond that in closed
+ * form.  weight_decay is not supported here (use psb_adam_step).  The global clip norm is taken over the dense
+ * tensors' gradients plus the compact row gradients (all other rows have gradient zero). */
+typedef struct psb_adam_rows {
+  float* p;                /* [table_rows, d] the table                                                      */
+  float* m;                /* [table_rows, d] exp_avg                                                        */
+  float* v;                /* [table_rows, d] exp_avg_sq                                                     */
+  int32_t* last_step;      /* [table_rows] optimizer step up to which the row (and its bias element) is current */
+  const int32_t* rows;     /* [cap] unique rows with a gradient this step (psb_scatter_reduce_rows unique_rows) */
+  const float* grad;       /* [cap, d] their reduced gradients                                               */
+  const int32_t* n_rows;   /* device scalar: valid entries of rows / grad / bias_grad                        */
+  int64_t cap, d, table_rows;
+  float* bias_p;           /* optional [table_rows] bias vector indexed like the table (product_bias, word_bias) */
+  float* bias_m;
+  float* bias_v;
+  const float* bias_grad;  /* [cap] or NULL (bias present but without gradient this step)                    */
+} psb_adam_rows_t;
+
+#define PSB_ADAM_MAX_ROW_TABLES 8
+#define PSB_ADAM_MAX_IDX_LISTS 8
+
+/* Steps replayed exactly per catch-up for these betas (264 at 0.9 / 0.999). */
+int32_t psb_adam_catchup_steps(double beta1, double beta2);
+int64_t psb_adam_sparse_workspace_bytes(const psb_adam_tensor_t* dense /* host */, int32_t n_dense,
+                                        const psb_adam_rows_t* tables /* host */, int32_t n_tables);
+/* One optimizer step: dense tensors exactly as psb_adam_step, tables through their row lists.  coef_hist: device
+ * array of coef_cap float2 (8-byte aligned) the call appends this step's (lr_t / (1 - b1^t), 1 / sqrt(1 - b2^t)) to
+ * and reads earlier steps' values from (steps >= coef_cap are recomputed on the fly); may be NULL.  norm_given as in
+ * psb_adam_step. */
+int psb_adam_sparse_step(const psb_adam_tensor_t* dense /* host */, int32_t n_dense,
+                         const psb_adam_rows_t* tables /* host */, int32_t n_tables, double lr, double beta1,
+                         double beta2, double eps, double max_grad_norm, int32_t noam, double warmup_steps,
+                         int32_t norm_given, int64_t* step_dev, float* sqnorm_dev, float* coef_hist, int64_t coef_cap,
+                         void* workspace, int64_t workspace_bytes, psb_stream_t stream);
+/* Bring rows up to the current step (*step_dev) BEFORE they are read: idx_lists[0..n_lists) are device index arrays
+ * (the ones the forward pass is about to gather with), idx_counts their lengths (host); n_lists == 0 catches up every
+ * row of the table (before evaluation / a checkpoint).  skip_row: a row that never moves (the pad row) or -1.
+ * Only p / m / v / last_step / bias_* / d / table_rows of ``table`` are read. */
+int psb_adam_rows_catchup(const psb_adam_rows_t* table /* host */, const int64_t* const* idx_lists /* host array */,
+                          const int64_t* idx_counts /* host */, int32_t n_lists, int64_t skip_row, double lr,
+                          double beta1, double beta2, double eps, int32_t noam, double warmup_steps,
+                          const int64_t* step_dev, const float* coef_hist, int64_t coef_cap, psb_stream_t stream);
+
 /* ------------------------------------------------------------ multi-GPU ---
  * Row-sharded tables over NVLink peer memory: owner of row id = id % G, local row =
  * id / G.  One process per GPU; buffers that peers read (table shards, gradient staging lists, the flat

@@ -48,7 +48,16 @@ class AdamTensor(ctypes.Structure):
     _fields_ = [("p", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("n", c_i64)]
 
 
+class AdamRows(ctypes.Structure):
+    """psb_adam_rows_t."""
+    _fields_ = [("p", c_vp), ("m", c_vp), ("v", c_vp), ("last_step", c_vp), ("rows", c_vp), ("grad", c_vp),
+                ("n_rows", c_vp), ("cap", c_i64), ("d", c_i64), ("table_rows", c_i64), ("bias_p", c_vp),
+                ("bias_m", c_vp), ("bias_v", c_vp), ("bias_grad", c_vp)]
+
+
 ADAM_MAX_TENSORS = 64
+ADAM_MAX_ROW_TABLES = 8
+ADAM_MAX_IDX_LISTS = 8
 PEER_MAX = 16
 PEER_HANDLE_BYTES = 64
 
@@ -107,6 +116,13 @@ SIGNATURES = {
     "psb_adam_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_f64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i32,
                               c_f64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "psb_grad_sqnorm": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "psb_adam_catchup_steps": (c_i32, [c_f64, c_f64]),
+    "psb_adam_sparse_workspace_bytes": (c_i64, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamRows), c_i32]),
+    "psb_adam_sparse_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamRows), c_i32, c_f64, c_f64,
+                                     c_f64, c_f64, c_f64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64,
+                                     c_vp]),
+    "psb_adam_rows_catchup": (c_i32, [ctypes.POINTER(AdamRows), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i32,
+                                      c_i64, c_f64, c_f64, c_f64, c_f64, c_i32, c_f64, c_vp, c_vp, c_i64, c_vp]),
     "psb_peer_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),
     "psb_peer_free": (c_i32, [c_vp]),
     "psb_peer_export": (c_i32, [c_vp, ctypes.c_char_p]),

@@ -169,6 +169,293 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, const Ad
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-sparse, lazily caught-up Adam for embedding tables (psb_adam_sparse_step / psb_adam_rows_catchup).
+//
+// Dense Adam updates EVERY row every step, also rows whose gradient is zero: their moments decay (m *= b1, v *= b2)
+// and the parameter keeps moving by -lr_t m_hat / (sqrt(v_hat) + eps).  At 16M rows that sweep is 57 GB per step for
+// ~10k rows with a gradient.  Here a row carries `last_step` (the optimizer step up to which it is current) and is
+// brought up to date only when somebody is about to read or update it:
+//   * the first min(gap, catchup_max) skipped steps are replayed EXACTLY (same fmaf sequence as adam_one with g = 0,
+//     per-step coefficients from the step history table);
+//   * after that the skipped updates are below fp32 resolution of the parameter -- their size falls like
+//     (b1 / sqrt(b2))^k, 1e-12 of the first one after catchup_max = 264 steps at the reference's betas -- and only
+//     the moments still change, in closed form: m *= b1^rest, v *= b2^rest.
+// The result equals the dense sweep within fp32 rounding (tests/test_gpu_sparse_adam.py holds it to the same
+// tolerance as the dense kernel against torch.optim.Adam).  weight_decay must be 0 (a decayed row never rests).
+struct RowTables {
+  psb_adam_rows_t t[PSB_ADAM_MAX_ROW_TABLES];
+  int n;
+};
+
+struct StepCoef {
+  float step_size, inv_bc2_sqrt;
+};
+
+__device__ __forceinline__ StepCoef step_coef(const AdamHyper& h, int64_t step) {
+  const double sd = static_cast<double>(step);
+  double lr = h.lr;
+  if (h.noam) lr = h.lr * fmin(1.0 / sqrt(sd), sd * pow(static_cast<double>(h.warmup), -1.5));
+  const double bc1 = 1.0 - pow(h.beta1, sd);
+  const double bc2 = 1.0 - pow(h.beta2, sd);
+  StepCoef c;
+  c.step_size = static_cast<float>(lr / bc1);
+  c.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  return c;
+}
+
+// coefficients of step tau: from the history table when it holds them (written by the optimizer step itself),
+// else recomputed (steps beyond the table's capacity)
+__device__ __forceinline__ StepCoef load_coef(const AdamHyper& h, const float2* __restrict__ hist, int64_t cap,
+                                              int64_t tau) {
+  if (hist != nullptr && tau < cap) {
+    const float2 c = hist[tau];
+    StepCoef r;
+    r.step_size = c.x;
+    r.inv_bc2_sqrt = c.y;
+    return r;
+  }
+  return step_coef(h, tau);
+}
+
+__device__ __forceinline__ void rest_one(float& p, float& m, float& v, float omb1, float b2, float step_size,
+                                         float inv_bc2_sqrt, float eps) {
+  m = fmaf(omb1, 0.f - m, m);                 // adam_one with g = 0
+  v = v * b2;
+  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p = fmaf(-step_size, m / denom, p);
+}
+
+// Warp-cooperative: bring row r (and its bias element) from step `from` to step `to` (both counted in completed
+// optimizer steps; from < to), all lanes of the warp active.
+__device__ void catchup_row(const psb_adam_rows_t& t, int64_t r, int64_t from, int64_t to, const AdamHyper& h,
+                            const float2* __restrict__ hist, int64_t hist_cap, int catchup_max) {
+  const int lane = threadIdx.x & 31;
+  const int d4 = static_cast<int>(t.d >> 2);
+  const int64_t gap = to - from;
+  const int exact = static_cast<int>(gap < catchup_max ? gap : catchup_max);
+  const int64_t rest = gap - exact;
+  float m_rest = 1.f, v_rest = 1.f;
+  if (rest > 0) {
+    m_rest = static_cast<float>(pow(h.beta1, static_cast<double>(rest)));
+    v_rest = static_cast<float>(pow(h.beta2, static_cast<double>(rest)));
+  }
+  float4* p4 = reinterpret_cast<float4*>(t.p + r * t.d);
+  float4* m4 = reinterpret_cast<float4*>(t.m + r * t.d);
+  float4* v4 = reinterpret_cast<float4*>(t.v + r * t.d);
+  const bool has_bias = t.bias_p != nullptr && lane == 0;
+  float bp = 0.f, bm = 0.f, bv = 0.f;
+  if (has_bias) {
+    bp = t.bias_p[r];
+    bm = t.bias_m[r];
+    bv = t.bias_v[r];
+  }
+  for (int c0 = 0; c0 < d4; c0 += 32) {
+    const int c = c0 + lane;
+    const bool on = c < d4;
+    float4 p = zero4(), m = zero4(), v = zero4();
+    if (on) {
+      p = p4[c];
+      m = m4[c];
+      v = v4[c];
+    }
+    for (int j0 = 0; j0 < exact; j0 += 32) {       // 32 steps' coefficients per trip: one per lane, then shuffled
+      const int nj = min(32, exact - j0);
+      StepCoef mine;
+      mine.step_size = 0.f;
+      mine.inv_bc2_sqrt = 1.f;
+      if (lane < nj) mine = load_coef(h, hist, hist_cap, from + 1 + j0 + lane);
+      for (int j = 0; j < nj; ++j) {
+        const float ss = __shfl_sync(kFull, mine.step_size, j);
+        const float ib = __shfl_sync(kFull, mine.inv_bc2_sqrt, j);
+        rest_one(p.x, m.x, v.x, h.omb1, h.b2, ss, ib, h.eps);
+        rest_one(p.y, m.y, v.y, h.omb1, h.b2, ss, ib, h.eps);
+        rest_one(p.z, m.z, v.z, h.omb1, h.b2, ss, ib, h.eps);
+        rest_one(p.w, m.w, v.w, h.omb1, h.b2, ss, ib, h.eps);
+        if (c0 == 0 && has_bias) rest_one(bp, bm, bv, h.omb1, h.b2, ss, ib, h.eps);
+      }
+    }
+    if (rest > 0) {
+      m.x *= m_rest; m.y *= m_rest; m.z *= m_rest; m.w *= m_rest;
+      v.x *= v_rest; v.y *= v_rest; v.z *= v_rest; v.w *= v_rest;
+    }
+    if (on) {
+      p4[c] = p;
+      m4[c] = m;
+      v4[c] = v;
+    }
+  }
+  if (has_bias) {
+    if (rest > 0) {
+      bm *= m_rest;
+      bv *= v_rest;
+    }
+    t.bias_p[r] = bp;
+    t.bias_m[r] = bm;
+    t.bias_v[r] = bv;
+  }
+}
+
+struct IdxLists {
+  const int64_t* idx[PSB_ADAM_MAX_IDX_LISTS];
+  int64_t start[PSB_ADAM_MAX_IDX_LISTS + 1];   // prefix sums of the list lengths
+  int n;
+};
+
+// One warp per index occurrence (or per table row when L.n == 0: flush).  Duplicates -- within the launch or from an
+// earlier launch of the same step -- are resolved by an atomicMax claim on last_step: exactly one warp replays the
+// row, the others see it claimed and leave.  Readers of the rows run in LATER kernels (stream order), so nobody
+// observes a half-updated row.
+__global__ void __launch_bounds__(256) adam_rows_catchup_kernel(const psb_adam_rows_t t, const IdxLists L,
+                                                                int64_t total, int64_t skip_row, const AdamHyper h,
+                                                                const int64_t* __restrict__ step_dev,
+                                                                const float2* __restrict__ hist, int64_t hist_cap,
+                                                                int catchup_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cur = *step_dev;
+  if (cur <= 0) return;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < total; i += nwarp) {
+    int64_t r = i;
+    if (L.n > 0) {
+      int q = 0;
+      while (q + 1 < L.n && i >= L.start[q + 1]) ++q;
+      r = L.idx[q][i - L.start[q]];
+    }
+    if (r < 0 || r >= t.table_rows || r == skip_row) continue;
+    int prev = 0;
+    if (lane == 0) {
+      prev = t.last_step[r];
+      if (prev < cur) prev = atomicMax(t.last_step + r, static_cast<int>(cur));
+    }
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev >= cur) continue;
+    catchup_row(t, r, prev, cur, h, hist, hist_cap, catchup_max);
+  }
+}
+
+// |g|^2 partials of the compact row gradients (and bias gradients) of the row-sparse tables, appended to the dense
+// tensors' partials: block b covers rows [32 b, 32 b + 32) of one table's list; rows past *n_rows count 0.
+__global__ void __launch_bounds__(256) sqnorm_rows_partial_kernel(const RowTables R, float* __restrict__ partial) {
+  __shared__ float wsum[8];
+  int b = blockIdx.x, ti = -1;
+  for (int q = 0; q < R.n; ++q) {
+    const int blocks = static_cast<int>((R.t[q].cap + 31) / 32);
+    if (b < blocks) {
+      ti = q;
+      break;
+    }
+    b -= blocks;
+  }
+  float acc = 0.f;
+  if (ti >= 0) {
+    const psb_adam_rows_t& t = R.t[ti];
+    const int64_t n = *t.n_rows;
+    const int64_t lo = static_cast<int64_t>(b) * 32, hi = min(n, lo + 32);
+    if (lo < hi) {
+      const float4* g4 = reinterpret_cast<const float4*>(t.grad + lo * t.d);
+      const int64_t n4 = (hi - lo) * (t.d >> 2);
+      for (int64_t i = threadIdx.x; i < n4; i += 256) {
+        const float4 v = g4[i];
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+      if (t.bias_grad != nullptr && threadIdx.x < hi - lo) {
+        const float gb = t.bias_grad[lo + threadIdx.x];
+        acc = fmaf(gb, gb, acc);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__device__ __forceinline__ AdamCoef make_coef(const AdamHyper& h, const float* sqnorm, int64_t step) {
+  float clip = 1.f;
+  if (h.max_norm > 0.f) {
+    const float total = sqrtf(*sqnorm);
+    clip = fminf(h.max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
+  }
+  const StepCoef sc = step_coef(h, step);
+  AdamCoef c0;
+  c0.clip = clip;
+  c0.wd = h.weight_decay;
+  c0.omb1 = h.omb1;
+  c0.b2 = h.b2;
+  c0.omb2 = h.omb2;
+  c0.step_size = sc.step_size;
+  c0.inv_bc2_sqrt = sc.inv_bc2_sqrt;
+  c0.eps = h.eps;
+  return c0;
+}
+
+// The update of the step's touched rows: one warp per list entry.  The row is first caught up to step - 1 (normally
+// a no-op: the forward pass read the row, so psb_adam_rows_catchup has already run for it), then takes the ordinary
+// Adam update with its reduced gradient and is stamped with the new step.  Block 0 also appends the step's
+// coefficients to the history table.
+__global__ void __launch_bounds__(256) adam_rows_kernel(const RowTables R, const AdamHyper h,
+                                                        const float* __restrict__ sqnorm,
+                                                        const int64_t* __restrict__ step_dev, float2* __restrict__ hist,
+                                                        int64_t hist_cap, int catchup_max) {
+  __shared__ AdamCoef coef;
+  const int64_t step = *step_dev;
+  if (threadIdx.x == 0) {
+    coef = make_coef(h, sqnorm, step);
+    if (blockIdx.x == 0 && hist != nullptr && step < hist_cap) hist[step] = make_float2(coef.step_size, coef.inv_bc2_sqrt);
+  }
+  __syncthreads();
+  const AdamCoef c = coef;
+  int b = blockIdx.x, ti = -1;
+  for (int q = 0; q < R.n; ++q) {
+    const int blocks = static_cast<int>((R.t[q].cap + 7) / 8);
+    if (b < blocks) {
+      ti = q;
+      break;
+    }
+    b -= blocks;
+  }
+  if (ti < 0) return;
+  const psb_adam_rows_t& t = R.t[ti];
+  const int lane = threadIdx.x & 31;
+  const int64_t i = static_cast<int64_t>(b) * 8 + (threadIdx.x >> 5);
+  if (i >= *t.n_rows) return;
+  const int64_t r = t.rows[i];
+  if (r < 0 || r >= t.table_rows) return;
+  const int prev = t.last_step[r];
+  if (prev < step - 1) catchup_row(t, r, prev, step - 1, h, hist, hist_cap, catchup_max);
+  __syncwarp();
+  const int d4 = static_cast<int>(t.d >> 2);
+  float4* p4 = reinterpret_cast<float4*>(t.p + r * t.d);
+  float4* m4 = reinterpret_cast<float4*>(t.m + r * t.d);
+  float4* v4 = reinterpret_cast<float4*>(t.v + r * t.d);
+  const float4* g4 = reinterpret_cast<const float4*>(t.grad + i * t.d);
+  for (int k = lane; k < d4; k += 32) {
+    float4 p = p4[k], m = m4[k], v = v4[k];
+    const float4 g = g4[k];
+    adam_one(p.x, g.x, m.x, v.x, c);
+    adam_one(p.y, g.y, m.y, v.y, c);
+    adam_one(p.z, g.z, m.z, v.z, c);
+    adam_one(p.w, g.w, m.w, v.w, c);
+    p4[k] = p;
+    m4[k] = m;
+    v4[k] = v;
+  }
+  if (lane == 0) {
+    if (t.bias_p != nullptr) {
+      const float g = t.bias_grad != nullptr ? t.bias_grad[i] : 0.f;
+      adam_one(t.bias_p[r], g, t.bias_m[r], t.bias_v[r], c);
+    }
+    t.last_step[r] = static_cast<int>(step);
+  }
+}
+
 }  // namespace psb
 
 using namespace psb;
@@ -260,5 +547,154 @@ extern "C" int psb_grad_sqnorm(const psb_adam_tensor_t* tensors, int32_t n_tenso
   if ((st = launch_status()) != PSB_OK) return st;
   PSB_PROF("sqnorm_final_kernel", s);
   sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks), sqnorm_out, nullptr);
+  return launch_status();
+}
+
+
+// ---- row-sparse Adam (see the kernels above) ------------------------------------------------------------------
+static int check_row_table(const psb_adam_rows_t& t, bool need_list) {
+  if (t.p == nullptr || t.m == nullptr || t.v == nullptr || t.last_step == nullptr || t.table_rows <= 0) return PSB_E_ARG;
+  if (t.d <= 0 || (t.d & 3) != 0 || t.d > 512) return PSB_E_DIM;
+  if (misaligned16(t.p) || misaligned16(t.m) || misaligned16(t.v) || misaligned16(t.grad)) return PSB_E_ALIGN;
+  if (need_list && (t.rows == nullptr || t.grad == nullptr || t.n_rows == nullptr || t.cap <= 0)) return PSB_E_ARG;
+  if (t.bias_p != nullptr && (t.bias_m == nullptr || t.bias_v == nullptr)) return PSB_E_ARG;
+  return PSB_OK;
+}
+
+static AdamHyper make_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,
+                            int32_t noam, double warmup_steps) {
+  AdamHyper h;
+  h.lr = lr;
+  h.beta1 = beta1;
+  h.beta2 = beta2;
+  h.b1 = static_cast<float>(beta1);
+  h.b2 = static_cast<float>(beta2);
+  h.omb1 = static_cast<float>(1.0 - beta1);
+  h.omb2 = static_cast<float>(1.0 - beta2);
+  h.eps = static_cast<float>(eps);
+  h.max_norm = static_cast<float>(max_grad_norm);
+  h.weight_decay = static_cast<float>(weight_decay);
+  h.noam = noam;
+  h.warmup = static_cast<float>(warmup_steps);
+  return h;
+}
+
+static int64_t row_norm_blocks(const psb_adam_rows_t* t, int32_t n) {
+  int64_t b = 0;
+  for (int i = 0; i < n; ++i) b += (t[i].cap + 31) / 32;
+  return b;
+}
+
+extern "C" int32_t psb_adam_catchup_steps(double beta1, double beta2) {
+  // skipped updates shrink like (b1 / sqrt(b2))^k: replay them exactly until they are 1e-12 of the first one
+  const double r = beta1 / sqrt(beta2);
+  if (!(r > 0.0) || r >= 1.0) return 4096;
+  const double k = ceil(log(1e-12) / log(r));
+  return static_cast<int32_t>(k < 1.0 ? 1.0 : (k > 4096.0 ? 4096.0 : k));
+}
+
+extern "C" int64_t psb_adam_sparse_workspace_bytes(const psb_adam_tensor_t* dense, int32_t n_dense,
+                                                   const psb_adam_rows_t* tables, int32_t n_tables) {
+  if (n_dense < 0 || n_dense > PSB_ADAM_MAX_TENSORS || n_tables < 0 || n_tables > PSB_ADAM_MAX_ROW_TABLES ||
+      (n_dense > 0 && dense == nullptr) || (n_tables > 0 && tables == nullptr))
+    return PSB_E_ARG;
+  return (adam_chunks(dense, n_dense) + row_norm_blocks(tables, n_tables) + 4) * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int psb_adam_sparse_step(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables,
+                                    int32_t n_tables, double lr, double beta1, double beta2, double eps,
+                                    double max_grad_norm, int32_t noam, double warmup_steps, int32_t norm_given,
+                                    int64_t* step_dev, float* sqnorm_dev, float* coef_hist, int64_t coef_cap,
+                                    void* workspace, int64_t workspace_bytes, psb_stream_t stream) {
+  if (n_dense < 0 || n_dense > PSB_ADAM_MAX_TENSORS || n_tables < 0 || n_tables > PSB_ADAM_MAX_ROW_TABLES ||
+      n_dense + n_tables == 0 || step_dev == nullptr || sqnorm_dev == nullptr || workspace == nullptr ||
+      (n_dense > 0 && dense == nullptr) || (n_tables > 0 && tables == nullptr))
+    return PSB_E_ARG;
+  if (coef_hist != nullptr && ((reinterpret_cast<uintptr_t>(coef_hist) & 7) != 0 || coef_cap <= 0)) return PSB_E_ALIGN;
+  AdamTensors T;
+  T.n = n_dense;
+  for (int i = 0; i < n_dense; ++i) {
+    if (dense[i].p == nullptr || dense[i].g == nullptr || dense[i].m == nullptr || dense[i].v == nullptr || dense[i].n <= 0)
+      return PSB_E_ARG;
+    T.t[i] = dense[i];
+  }
+  RowTables R;
+  R.n = n_tables;
+  int st;
+  for (int i = 0; i < n_tables; ++i) {
+    if ((st = check_row_table(tables[i], true)) != PSB_OK) return st;
+    R.t[i] = tables[i];
+  }
+  const int64_t chunks = adam_chunks(dense, n_dense);
+  const int64_t nblocks = row_norm_blocks(tables, n_tables);
+  int64_t ublocks = 0;
+  for (int i = 0; i < n_tables; ++i) ublocks += (tables[i].cap + 7) / 8;
+  if (chunks + nblocks > (1ll << 30) || ublocks > (1ll << 30)) return PSB_E_DIM;
+  if (workspace_bytes < (chunks + nblocks + 4) * static_cast<int64_t>(sizeof(float))) return PSB_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  if (norm_given == 2) {
+    // norm and step counter were both written by the caller
+  } else if (norm_given) {
+    PSB_PROF("bump_step_kernel", s);
+    bump_step_kernel<<<1, 1, 0, s>>>(step_dev);
+    if ((st = launch_status()) != PSB_OK) return st;
+  } else {
+    if (chunks > 0) {
+      PSB_PROF("sqnorm_partial_kernel", s);
+      sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
+      if ((st = launch_status()) != PSB_OK) return st;
+    }
+    if (nblocks > 0) {
+      PSB_PROF("sqnorm_rows_partial_kernel", s);
+      sqnorm_rows_partial_kernel<<<static_cast<int>(nblocks), 256, 0, s>>>(R, partial + chunks);
+      if ((st = launch_status()) != PSB_OK) return st;
+    }
+    PSB_PROF("sqnorm_final_kernel", s);
+    sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks + nblocks), sqnorm_dev, step_dev);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, 0.0, max_grad_norm, noam, warmup_steps);
+  if (chunks > 0) {
+    PSB_PROF("adam_kernel", s);
+    adam_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, h, sqnorm_dev, step_dev);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  if (ublocks > 0) {
+    PSB_PROF("adam_rows_kernel", s);
+    adam_rows_kernel<<<static_cast<int>(ublocks), 256, 0, s>>>(R, h, sqnorm_dev, step_dev,
+                                                              reinterpret_cast<float2*>(coef_hist), coef_cap,
+                                                              psb_adam_catchup_steps(beta1, beta2));
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  return PSB_OK;
+}
+
+extern "C" int psb_adam_rows_catchup(const psb_adam_rows_t* table, const int64_t* const* idx_lists,
+                                     const int64_t* idx_counts, int32_t n_lists, int64_t skip_row, double lr,
+                                     double beta1, double beta2, double eps, int32_t noam, double warmup_steps,
+                                     const int64_t* step_dev, const float* coef_hist, int64_t coef_cap,
+                                     psb_stream_t stream) {
+  if (table == nullptr || step_dev == nullptr || n_lists < 0 || n_lists > PSB_ADAM_MAX_IDX_LISTS ||
+      (n_lists > 0 && (idx_lists == nullptr || idx_counts == nullptr)))
+    return PSB_E_ARG;
+  int st = check_row_table(*table, false);
+  if (st != PSB_OK) return st;
+  IdxLists L;
+  L.n = n_lists;
+  L.start[0] = 0;
+  for (int i = 0; i < n_lists; ++i) {
+    if (idx_counts[i] < 0 || (idx_counts[i] > 0 && idx_lists[i] == nullptr)) return PSB_E_ARG;
+    L.idx[i] = idx_lists[i];
+    L.start[i + 1] = L.start[i] + idx_counts[i];
+  }
+  const int64_t total = n_lists > 0 ? L.start[n_lists] : table->table_rows;      // no lists: every row (flush)
+  if (total == 0) return PSB_OK;
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, 0.0, 0.0, noam, warmup_steps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("adam_rows_catchup_kernel", s);
+  adam_rows_catchup_kernel<<<grid_for(total, 8, 32), 256, 0, s>>>(*table, L, total, skip_row, h, step_dev,
+                                                                 reinterpret_cast<const float2*>(coef_hist), coef_cap,
+                                                                 psb_adam_catchup_steps(beta1, beta2));
   return launch_status();
 }

@@ -75,7 +75,7 @@ class RowGradSink(object):
             Variable._execution_engine.queue_callback(self._finalize_callback)
 
     def _finalize_callback(self):
-        if not (RowGradSink.concurrent and self.mode == "dense" and self.weight.is_cuda):
+        if not (RowGradSink.concurrent and self.weight.is_cuda):
             return self.finalize()
         run_forked(self)
 
@@ -126,8 +126,10 @@ class RowGradSink(object):
                 uniq, red, redb, nu = ops.scatter_reduce(chunk, rows, d, self.drop_idx, want_rows=True,
                                                          want_bias=want_bias, device=w.device)
                 w.row_grad = (uniq, red, nu)
+                w._psb_drop_idx = self.drop_idx          # the row-sparse optimizer never replays the pad row
                 if want_bias:
                     self.bias.row_grad = (uniq, redb, nu)
+                    w._psb_row_bias = self.bias          # updated with (and stamped like) the table's rows
 
     def _accumulate_dense(self, chunk, rows, d, want_bias):
         """Gradient accumulation into the persistent buffers: row-sparse reduce of this pass, then a deterministic
@@ -179,6 +181,31 @@ class RowGradSink(object):
             param.grad = buf
         else:                          # user-side gradient accumulation: keep torch semantics
             param.grad = param.grad + buf
+
+
+class LazyFlushMixin(object):
+    """nn.Module mixin: tables updated by the row-sparse optimizer are made dense-equivalent before anything reads
+    them wholesale -- switching to eval mode (ranking, scoring candidate lists, the review table) and
+    ``state_dict()`` (checkpoints)."""
+
+    def flush_lazy_rows(self):
+        done = False
+        for p in self.parameters():
+            lazy = getattr(p, "_psb_lazy", None)
+            if lazy is not None:
+                lazy.flush()
+                done = True
+        if done:
+            ops._lib.note_param_write()
+
+    def train(self, mode=True):
+        if not mode:
+            self.flush_lazy_rows()
+        return super().train(mode)
+
+    def state_dict(self, *args, **kwargs):
+        self.flush_lazy_rows()
+        return super().state_dict(*args, **kwargs)
 
 
 def _dropout_keep(shape, p, training, device):
@@ -302,6 +329,7 @@ def ns_loss_dense_pos(anchor, dense_pos, table, neg_idx, sink, mask=None):
     n, w, _ = dense_pos.shape
     pos = DensePosLossFn.apply(anchor, dense_pos, mask)
     pad = torch.full((n, w), table.shape[0] - 1, dtype=torch.int64, device=table.device)
+    ensure_current(table, (neg_idx,))
     neg = NSLossFn.apply(anchor, None, table, None, pad, neg_idx, sink, -1, mask, None, 0.0, None)
     return pos + neg
 
@@ -381,12 +409,33 @@ class SeqEncoderFn(Function):
             grads.pop(n, None) for n in ctx.names)
 
 
+def ensure_current(weight, idx_list, stream=None):
+    """Row-sparse optimizer (optimizers.FusedAdam): a table whose rows are updated lazily carries ``_psb_lazy``; the
+    rows about to be gathered are brought up to the current optimizer step first, on the stream the reader runs on.
+    No-op (one attribute lookup) for every other tensor."""
+    lazy = getattr(weight, "_psb_lazy", None)
+    if lazy is None:
+        return
+    if stream is None:
+        lazy.ensure(idx_list)
+    else:
+        with torch.cuda.stream(stream):
+            keep = lazy.ensure(idx_list)
+        held = getattr(stream, "_psb_keep", None)       # converted index copies stay alive until the stream is joined
+        if held is None:
+            held = stream._psb_keep = []
+        held.append(tuple(keep or ()))
+        del held[:-8]
+
+
 def gather_rows(weight, idx, sink, stream=None):
+    ensure_current(weight, (idx,), stream)
     return GatherRowsFn.apply(weight, idx, sink, stream)
 
 
 def meanpool(weight, idx, sink, pad_idx=-1, mask=None, tok_scale=None, keep_scale=None, fs_weight=None,
              fs_bias=None, stream=None):
+    ensure_current(weight, (idx,), stream)
     return MeanPoolFn.apply(weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale, stream)
 
 
@@ -394,6 +443,7 @@ def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, 
             neg_weight=None, pos_weight=1.0, stream=None):
     """stream: enqueue the forward kernel on a side stream the caller has forked and will join (the autograd node
     -- and therefore its backward -- still belongs to the current stream)."""
+    ensure_current(weight, (pos_idx, neg_idx), stream)
     return NSLossFn.apply(anchor_a, anchor_b, weight, bias, pos_idx, neg_idx, sink, pad_idx, mask, neg_weight,
                           pos_weight, stream)
 
@@ -401,5 +451,7 @@ def ns_loss(anchor_a, weight, pos_idx, neg_idx, sink, anchor_b=None, bias=None, 
 def seq_encoder(params, opts, first=None, table=None, idx=None, sink=None, pad_idx=-1, dense=None, mask=None,
                 pe=None):
     """params: ordered dict name -> Parameter (psb_encoder_params_t member names)."""
+    if table is not None:
+        ensure_current(table, (idx,))
     names = tuple(params.keys())
     return SeqEncoderFn.apply(first, dense, table, idx, sink, pad_idx, mask, pe, opts, names, *params.values())

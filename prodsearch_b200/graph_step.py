@@ -7,6 +7,11 @@ capture and replays it with new batch contents copied into static input buffers.
 needs is device-resident and replay-safe: negatives come from the device generator (``torch.multinomial``,
 Philox offsets advance per replay), dropout keys from a device seed, the Adam step counter / clip norm
 live in device memory, the gradient sinks keep their touched-row lists in persistent buffers.
+
+Capture rule inherited from torch: no autograd graph of an EARLIER eager pass over the same parameters may still be
+alive (a loss tensor kept in a variable): its AccumulateGrad nodes are bound to the stream of that pass -- usually the
+legacy default stream -- and the captured backward would try to run them there ("operation would make the legacy
+stream depend on a capturing blocking stream").  Drop such tensors before constructing a GraphedTrainStep.
 """
 import argparse
 
@@ -48,7 +53,7 @@ class GraphedTrainStep(object):
         snap = dict(params=[p.detach().clone() for p in self.model.parameters()], host_step=getattr(self.optim, "_step", 0),
                     opt_state=None, opt_step=None, acc=None)
         if opt is not None and hasattr(opt, "_step_dev"):
-            snap["opt_state"] = {p: (st["exp_avg"].clone(), st["exp_avg_sq"].clone()) for p, st in opt.state.items()}
+            snap["opt_state"] = {p: {k: v.clone() for k, v in st.items()} for p, st in opt.state.items()}
             snap["opt_step"] = None if opt._step_dev is None else opt._step_dev.clone()
         elif opt is not None:
             import copy
@@ -64,13 +69,12 @@ class GraphedTrainStep(object):
             opt = getattr(self.optim, "optimizer", None)
             if opt is not None and hasattr(opt, "_step_dev"):
                 for p, st in opt.state.items():
-                    old = snap["opt_state"].get(p)
-                    if old is None:
-                        st["exp_avg"].zero_()
-                        st["exp_avg_sq"].zero_()
-                    else:
-                        st["exp_avg"].copy_(old[0])
-                        st["exp_avg_sq"].copy_(old[1])
+                    old = snap["opt_state"].get(p) or {}
+                    for k, v in st.items():          # exp_avg, exp_avg_sq, (row-sparse tables) last_step
+                        if k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
                 if opt._step_dev is not None:
                     if snap["opt_step"] is None:
                         opt._step_dev.zero_()

@@ -19,7 +19,7 @@ from .text_encoder import AVGEncoder, FSEncoder
 from .transformer import TransformerEncoder
 
 
-class ItemTransformerRanker(nn.Module):
+class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
     overlap_query_pooling = True     # query pooling on a side stream under the encoder's plan / transpose kernels
     overlap_item_to_words = True     # item -> word loss kernels on a side stream next to the encoder
 
@@ -159,18 +159,33 @@ class ItemTransformerRanker(nn.Module):
         B, _ = u_item_idxs.shape
         K = self.args.neg_per_pos
         W = pos_iword_idxs.shape[1]
-        neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
-        item_w, item_sink, tgt_idx, neg_idx, hist = self._resolve_item_rows(target_prod_idxs, neg_item_idxs,
-                                                                            u_item_idxs)
-        # the item -> word objective shares nothing with the encoder: its two kernels run on a side stream (a
-        # parallel branch of the captured graph) and are joined before the losses are combined
-        cur = torch.cuda.current_stream(item_w.device) if item_w.is_cuda else None
+        # Neither the negatives nor the item -> word objective are needed by the encoder: the two torch.multinomial
+        # chains (renorm + scan + sample, ~70 us of serialised kernels for two constant distributions) and the item ->
+        # word kernels run on a side stream -- a parallel branch of the captured graph -- and are joined right before
+        # the ranking loss, the first reader of the sampled items.  The draw ORDER on the device generator is the
+        # reference's (items, then words: item_transformer.py:447, :268); only where the kernels are enqueued moves.
+        dev_t = self.product_emb.weight
+        cur = torch.cuda.current_stream(dev_t.device) if dev_t.is_cuda else None
         side = None
         if cur is not None and self.overlap_item_to_words:
             if getattr(self, "_iw_stream", None) is None:
-                self._iw_stream = torch.cuda.Stream(device=item_w.device)
+                self._iw_stream = torch.cuda.Stream(device=dev_t.device)
             side = self._iw_stream
             side.wait_stream(cur)
+        sharded = type(self)._resolve_item_rows is not ItemTransformerRanker._resolve_item_rows
+        if side is not None and not sharded and self.injected_negatives is None:
+            with torch.cuda.stream(side):
+                neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+            # (allocated on the side stream and alive until backward has run; the side stream's next allocation
+            # happens after its next wait on the current stream, so the allocator cannot recycle them early)
+        else:
+            neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+            if side is not None:
+                side.wait_stream(cur)
+        item_w, item_sink, tgt_idx, neg_idx, hist = self._resolve_item_rows(target_prod_idxs, neg_item_idxs,
+                                                                            u_item_idxs)
+        if side is not None and sharded:
+            side.wait_stream(cur)                # the fetched mini table is produced on the current stream
         item_loss_rows = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink, stream=side,
                                             reduce=False)
         stochastic = self.training and self.args.dropout > 0
@@ -186,11 +201,11 @@ class ItemTransformerRanker(nn.Module):
             neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
         bias = self.product_bias if self.args.sim_func == "bias_product" else None
         pos_weight = float(K) if self.args.pos_weight else 1.0
+        if side is not None:
+            cur.wait_stream(side)                # the sampled item negatives (and the item -> word losses) are ready
         ps = F_.ns_loss(pos_out.contiguous(), item_w, tgt_idx.view(B, 1), neg_idx.view(B, 1, K), item_sink,
                         anchor_b=neg_out.contiguous(), bias=bias, pos_weight=pos_weight)
         ps_loss = ps.mean()
-        if side is not None:
-            cur.wait_stream(side)
         item_loss = item_loss_rows.mean()
         with torch.no_grad():   # lazily synchronised running sums (the reference calls .item() here); in place,
             if self._ps_acc is None:   # so a CUDA-graph replay keeps accumulating into the same buffers
@@ -223,6 +238,7 @@ class ItemTransformerRanker(nn.Module):
         """Scores of an explicit candidate list [B, candi_k] (item_transformer.py:111-146).  The
         encoder output does not depend on the candidate, so it is computed once
         per query instead of candi_k times."""
+        self.flush_lazy_rows()
         with torch.no_grad():
             q = self.encode_queries(batch_data.query_word_idxs, batch_data.u_item_idxs).contiguous()
             bias = self.product_bias if self.args.sim_func == "bias_product" else None
@@ -250,6 +266,7 @@ class ItemTransformerRanker(nn.Module):
         mode TOPK_TC16 (default): tcgen05 fp16 shortlist on a cached half-precision copy of the table + exact fp32
         rescoring; TOPK_TC: tf32 shortlist straight from the fp32 table.  Both return exactly what TOPK_EXACT
         returns; shapes they do not cover (and tables that overflow fp16) run the next mode down."""
+        self.flush_lazy_rows()             # row-sparse optimizer: every resting row is replayed before a full scan
         with torch.no_grad():
             if torch.is_tensor(batch_or_queries):
                 q = batch_or_queries

@@ -1,8 +1,17 @@
 """Optimizer wrapper with the reference's semantics (models/optimizers.py:111-245): Adam with
 eps=1e-9 (:186), optional noam schedule (:214-219) and global-norm gradient clipping (:241-242).
-Row N2 of SURVEY.md 8(f): the clip + Adam update of every parameter tensor runs as ONE fused multi-tensor
-call (psb_adam_step) on the dense ``.grad`` tensors the gradient sinks attach, with the step counter and the
-global norm in device memory (CUDA-graph replayable).  Dense semantics, identical to the reference's."""
+Row N2 of SURVEY.md 8(f).  Two forms, both one fused multi-tensor call with the step counter and the global norm in
+device memory (CUDA-graph replayable):
+  * dense (``psb_adam_step``): the clip + Adam update of every element of every tensor, on the dense ``.grad``
+    tensors the gradient sinks attach in ``grad_mode="dense"`` -- literally the reference's sweep;
+  * row-sparse (``psb_adam_sparse_step``): embedding tables whose sinks run in ``grad_mode="rowsparse"`` hand over
+    ``param.row_grad = (unique_rows, reduced_rows, n)``; only those rows are updated, every other row rests and is
+    replayed (``psb_adam_rows_catchup``) right before something reads it -- the gather wrappers of ``functional.py``
+    call ``ensure_current`` -- or when ``flush()`` is called (evaluation, checkpoints).  Dense-equivalent results
+    within fp32 rounding; the step costs O(rows touched), not O(table).
+
+Known difference from torch.optim.Adam: ONE step counter for all tensors (torch keeps one per parameter; they only
+differ for a parameter that receives its first gradient later than the others -- none does in these models)."""
 import torch
 from torch.nn.utils import clip_grad_norm_
 
@@ -23,6 +32,9 @@ class FusedAdam(object):
         self._sqnorm = None
         self._ws = None
         self._norm_given = 0
+        self.coef_cap = 1 << 18              # steps whose coefficients the catch-up reads from a table (2 MB)
+        self._coef_hist = None
+        self._lazy = {}                      # table parameter -> LazyRows
 
     def _ensure(self, dev):
         if self._step_dev is None:
@@ -54,9 +66,151 @@ class FusedAdam(object):
         """Global gradient norm of the last step (device tensor; reading it synchronises)."""
         return self._sqnorm.sqrt()
 
+    # ---- row-sparse tables -------------------------------------------------------------------------------
+    def _rows_struct(self, p, lists=True):
+        """psb_adam_rows_t of table parameter ``p`` (+ the bias vector indexed like it) and the tensors it points to."""
+        st = self._state_of(p)
+        if "last_step" not in st:
+            st["last_step"] = torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)
+        bias = getattr(p, "_psb_row_bias", None)
+        if bias is not None and not bias.requires_grad:
+            bias = None
+        keep = [st["exp_avg"], st["exp_avg_sq"], st["last_step"]]
+        R = _lib.AdamRows()
+        R.p, R.m, R.v, R.last_step = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["last_step"].data_ptr()
+        R.d, R.table_rows = p.shape[1], p.shape[0]
+        if bias is not None:
+            sb = self._state_of(bias)
+            R.bias_p, R.bias_m, R.bias_v = bias.data_ptr(), sb["exp_avg"].data_ptr(), sb["exp_avg_sq"].data_ptr()
+            keep += [sb["exp_avg"], sb["exp_avg_sq"]]
+        if lists:
+            rows, vals, nu = p.row_grad
+            R.rows, R.grad, R.n_rows, R.cap = rows.data_ptr(), vals.data_ptr(), nu.data_ptr(), min(rows.numel(), vals.shape[0])
+            keep += [rows, vals, nu]
+            bg = getattr(bias, "row_grad", None) if bias is not None else None
+            if bg is not None:
+                if bg[0].data_ptr() != rows.data_ptr():
+                    raise RuntimeError("bias row gradient does not share its table's row list")
+                R.bias_grad = bg[1].data_ptr()
+                keep.append(bg[1])
+        return R, keep, bias
+
+    def _hyper(self):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return float(g["lr"]), float(b1), float(b2), float(g["eps"])
+
+    def _catchup(self, p, idx_list, noam=None, warmup=None):
+        """Bring the rows of lazily updated table ``p`` up to the current step before they are read
+        (``idx_list``: index tensors about to be gathered; None = every row).  Runs on the current stream."""
+        if self._step_dev is None:
+            return
+        R, keep, _ = self._rows_struct(p, lists=False)
+        lr, b1, b2, eps = self._hyper()
+        noam = self._last_noam if noam is None else noam
+        warmup = self._last_warmup if warmup is None else warmup
+        n = 0
+        ptrs = cnts = None
+        if idx_list is not None:
+            idx_list = [t if (t.dtype == torch.int64 and t.is_contiguous()) else t.long().contiguous() for t in idx_list
+                        if t is not None and t.numel() > 0]
+            n = len(idx_list)
+            if n == 0:
+                return
+            if n > _lib.ADAM_MAX_IDX_LISTS:
+                raise RuntimeError("more than %d index lists in one catch-up" % _lib.ADAM_MAX_IDX_LISTS)
+            ptrs = (_lib.c_vp * n)(*[t.data_ptr() for t in idx_list])
+            cnts = (_lib.c_i64 * n)(*[t.numel() for t in idx_list])
+            keep += idx_list
+        skip = int(getattr(p, "_psb_drop_idx", -1))
+        _lib.check(_lib.load().psb_adam_rows_catchup(
+            R, ptrs, cnts, n, skip, lr, b1, b2, eps, 1 if noam else 0, float(warmup), self._step_dev.data_ptr(),
+            self._coef_hist.data_ptr() if self._coef_hist is not None else None, self.coef_cap, _lib.stream_ptr()),
+            "psb_adam_rows_catchup")
+        return keep
+
+    def flush(self):
+        """Make every lazily updated table dense-equivalent NOW (before evaluation, ranking, checkpoints)."""
+        for p in list(self._lazy):
+            self._catchup(p, None)
+        if self._lazy:
+            _lib.note_param_write()
+
+    _last_noam, _last_warmup = False, 4000.0
+
+    def _sparse_step(self, live, sparse, max_grad_norm, noam, warmup_steps):
+        g = self.param_groups[0]
+        if g["weight_decay"]:
+            raise RuntimeError("row-sparse Adam does not support weight_decay (a decayed row never rests): "
+                               "use grad_mode='dense'")
+        if len(sparse) > _lib.ADAM_MAX_ROW_TABLES:
+            raise RuntimeError("more than %d row-sparse tables" % _lib.ADAM_MAX_ROW_TABLES)
+        dev = (sparse[0] if sparse else live[0]).device
+        self._ensure(dev)
+        if self._coef_hist is None:
+            self._coef_hist = torch.zeros(self.coef_cap * 2, dtype=torch.float32, device=dev)
+        rows_arr = (_lib.AdamRows * max(len(sparse), 1))()
+        keep, covered = [], set()
+        for i, p in enumerate(sparse):
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.dim() == 2):
+                raise RuntimeError("row-sparse Adam needs contiguous fp32 CUDA tables")
+            R, k, bias = self._rows_struct(p)
+            rows_arr[i] = R
+            keep.append(k)
+            if bias is not None:
+                covered.add(id(bias))
+            if p not in self._lazy:
+                self._lazy[p] = p._psb_lazy = LazyRows(self, p)
+        live = [p for p in live if id(p) not in covered]
+        if len(live) > _lib.ADAM_MAX_TENSORS:
+            raise RuntimeError("FusedAdam: more than %d parameter tensors" % _lib.ADAM_MAX_TENSORS)
+        arr = (_lib.AdamTensor * max(len(live), 1))()
+        for i, p in enumerate(live):
+            st = self._state_of(p)
+            grad = p.grad
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and grad.is_contiguous()
+                    and grad.dtype == torch.float32 and not grad.is_sparse):
+                raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and dense gradients")
+            arr[i] = _lib.AdamTensor(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(),
+                                     st["exp_avg_sq"].data_ptr(), p.numel())
+        lib = _lib.load()
+        wb = int(lib.psb_adam_sparse_workspace_bytes(arr, len(live), rows_arr, len(sparse)))
+        if wb < 0:
+            _lib.check(wb, "psb_adam_sparse_workspace_bytes")
+        if self._ws is None or self._ws.numel() < wb:
+            self._ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        lr, b1, b2, eps = self._hyper()
+        self._last_noam, self._last_warmup = bool(noam), float(warmup_steps)
+        from . import ops
+        ev = None
+        if ops.PROFILE is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(lib.psb_adam_sparse_step(arr, len(live), rows_arr, len(sparse), lr, b1, b2, eps,
+                                            float(max_grad_norm or 0.0), 1 if noam else 0, float(warmup_steps),
+                                            int(self._norm_given), self._step_dev.data_ptr(), self._sqnorm.data_ptr(),
+                                            self._coef_hist.data_ptr(), self.coef_cap, self._ws.data_ptr(),
+                                            self._ws.numel(), _lib.stream_ptr()), "psb_adam_sparse_step")
+        self._norm_given = 0
+        for p in sparse:                      # consumed: a step without a new backward must not re-apply them
+            p.row_grad = None
+            b = getattr(p, "_psb_row_bias", None)
+            if b is not None:
+                b.row_grad = None
+        _lib.note_param_write()
+        if ev is not None:
+            ev[1].record()
+            ops.PROFILE.setdefault("adam_step", []).append(ev)
+
     def step(self, max_grad_norm=0.0, noam=False, warmup_steps=4000.0):
         g = self.param_groups[0]
         live = [p for p in self.params if p.grad is not None]
+        sparse = [p for p in self.params if p.dim() == 2 and getattr(p, "row_grad", None) is not None]
+        if any(p in self._lazy for p in live):
+            raise RuntimeError("a table that has been updated row-sparsely received a dense gradient: keep its sink in "
+                               "grad_mode='rowsparse' (or call flush() and build a new optimizer)")
+        if sparse or (self._lazy and live):
+            return self._sparse_step(live, sparse, max_grad_norm, noam, warmup_steps)
         if not live:
             return
         if len(live) > _lib.ADAM_MAX_TENSORS:
@@ -94,6 +248,7 @@ class FusedAdam(object):
 
     # ---- torch.optim.Adam-compatible checkpoint format ----------------------------------------
     def state_dict(self):
+        self.flush()                       # lazily updated tables: dense-equivalent moments and parameters
         step = int(self._step_dev.item()) if self._step_dev is not None else 0
         state = {}
         for i, p in enumerate(self.params):
@@ -118,10 +273,40 @@ class FusedAdam(object):
         if self.params:
             self._ensure(self.params[0].device)
             self._step_dev.fill_(step)
+        for st in self.state.values():     # a torch-format checkpoint is dense: every row is current at ``step``
+            if "last_step" in st:
+                st["last_step"].fill_(step)
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
             p.grad = None
+
+
+class LazyRows(object):
+    """Handle a lazily updated table parameter carries (``param._psb_lazy``): the gather wrappers call ``ensure``
+    with the indices they are about to read.  Catch-up launches of one table are chained by an event, so that two
+    streams never replay the same table concurrently (a reader on one stream must not meet a row the other stream's
+    launch is half-way through); the chain is per step -- the streams of a step are joined before the optimizer."""
+
+    def __init__(self, optim, weight):
+        self.optim, self.weight = optim, weight
+        self._event = None
+        self._key = None
+
+    def ensure(self, idx_list):
+        cur = torch.cuda.current_stream(self.weight.device)
+        key = (torch.cuda.is_current_stream_capturing(), _lib.PARAM_EPOCH[0])
+        if self._event is None:
+            self._event = torch.cuda.Event()
+        elif self._key == key:
+            cur.wait_event(self._event)
+        keep = self.optim._catchup(self.weight, idx_list)
+        self._event.record(cur)
+        self._key = key
+        return keep
+
+    def flush(self):
+        self.optim._catchup(self.weight, None)
 
 
 class Optimizer(object):
@@ -162,6 +347,21 @@ class Optimizer(object):
             return
         self.optimizer.param_groups[0]["lr"] = self.original_lr if noam else self.learning_rate
         self.optimizer.step(self.max_grad_norm, noam, self.warmup_steps)
+
+    def flush(self):
+        """Row-sparse tables: replay every resting row (before evaluation / saving a checkpoint)."""
+        if hasattr(self.optimizer, "flush"):
+            self.optimizer.flush()
+
+    def sync_host_step(self):
+        """CUDA-graph replays advance only the device step counter: bring the host mirror (``_step``, the noam
+        ``learning_rate``) in line before pickling the optimizer into a checkpoint."""
+        dev = getattr(self.optimizer, "_step_dev", None)
+        if dev is not None:
+            self._step = int(dev.item())
+            if self.decay_method == "noam" and self._step > 0:
+                self.learning_rate = self.original_lr * min(self._step ** (-0.5),
+                                                            self._step * self.warmup_steps ** (-1.5))
 
 
 def build_optim(args, model, checkpoint=None):

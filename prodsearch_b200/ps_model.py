@@ -25,7 +25,7 @@ def pad_reviews(data, pad_id, width):
     return [list(d[:width]) + [pad_id] * (width - len(d)) for d in data]
 
 
-class ProductRanker(nn.Module):
+class ProductRanker(F_.LazyFlushMixin, nn.Module):
     def __init__(self, args, device, vocab_size, review_count, product_size, user_size, review_words,
                  vocab_words, word_dists=None, grad_mode="dense"):
         super().__init__()
@@ -117,6 +117,7 @@ class ProductRanker(nn.Module):
         (ps_model.py:194-203), here one fused gather + mean (+fs) launch covers all reviews."""
         if self.review_embeddings is not None:
             return
+        self.flush_lazy_rows()
         if self.review_encoder_name == "pv":
             # a plain attribute, not a registered alias of the parameter (state_dict stays clean)
             object.__setattr__(self, "review_embeddings", self.review_encoder.review_embeddings.weight)
@@ -148,6 +149,7 @@ class ProductRanker(nn.Module):
 
     def test(self, batch_data):
         """ps_model.py:205-239."""
+        self.flush_lazy_rows()
         with torch.no_grad():
             cand = batch_data.candi_prod_ridxs
             B, C, Rc = cand.shape

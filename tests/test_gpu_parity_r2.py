@@ -193,8 +193,8 @@ def test_pv_train_step_shape_vs_oracle():
     gr, gw = rt.grad.clone(), wt.grad.clone()
     gr[-1] = 0
     gw[-1] = 0
-    close(pv.review_embeddings.weight.grad, gr, rtol=1e-4, what="review table grad")
-    close(wemb.weight.grad, gw, rtol=1e-4, what="word table grad")
+    for got, ref, what in ((pv.review_embeddings.weight.grad, gr, "review table grad"), (wemb.weight.grad, gw, "word table grad")):
+        close(got, ref, rtol=1e-4, atol=max(2e-5 * float(ref.abs().max()), 2e-7), what=what)   # sums with cancellation
 
 
 # ------------------------------------------------------------------ A11: sampled indices on the device generator
@@ -339,7 +339,9 @@ def test_rank_train_rank_follows_the_updated_table():
         ide, sce = model.rank_catalog(b, k=100, mode=_lib.TOPK_EXACT)
         assert torch.equal(ids1, ide) and torch.equal(sc1, sce)
         assert not torch.equal(sc0, sc1)
-    # the same through CUDA-graph replays
+    # the same through CUDA-graph replays (the eager loss above still holds its autograd graph, whose AccumulateGrad
+    # nodes are bound to the stream of that eager pass: release it before capturing)
+    del loss
     model.train()
     step = GraphedTrainStep(model, opt, b)
     model.eval()
@@ -405,10 +407,12 @@ def test_catalog_topk_1m_spot_check_fp64():
     assert bool(((got - sc[rows].double()).abs() <= tol).all())
     ref_s, ref_i = torch.topk(S, k, dim=1)
     assert bool(((ref_s - sc[rows].double()).abs() <= tol).all())
-    gap = (ref_s[:, :-1] - ref_s[:, 1:]).min(dim=1).values                    # ids are defined where gaps exceed fp32 noise
-    kth_gap = ref_s[:, -1] - torch.topk(S, k + 1, dim=1).values[:, -1]
-    clear = (gap > 2 * tol.view(-1)) & (kth_gap > 2 * tol.view(-1))
-    assert bool(clear.any())
+    # ids are defined at the positions whose score gaps to both neighbours exceed the fp32 noise
+    ref_s1 = torch.topk(S, k + 1, dim=1).values
+    gaps = ref_s1[:, :-1] - ref_s1[:, 1:]                                      # [rows, k]: gap below position j
+    inf = torch.full_like(gaps[:, :1], float("inf"))
+    clear = (gaps > 2 * tol) & (torch.cat([inf, gaps[:, :-1]], dim=1) > 2 * tol)
+    assert float(clear.float().mean()) > 0.5
     assert torch.equal(ids[rows][clear], ref_i[clear])
     d = sc[:, 1:] - sc[:, :-1]
     assert bool((d <= 0).all()) and bool((ids[:, 1:][d == 0] > ids[:, :-1][d == 0]).all())
