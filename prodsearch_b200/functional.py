@@ -419,6 +419,9 @@ def ensure_current(weight, idx_list, stream=None):
     if stream is None:
         lazy.ensure(idx_list)
     else:
+        # fork first: the side stream must be ordered behind the calling stream (the previous optimizer step) -- and,
+        # under stream capture, must have JOINED the capture -- before the catch-up is enqueued on it
+        stream.wait_stream(torch.cuda.current_stream(weight.device))
         with torch.cuda.stream(stream):
             keep = lazy.ensure(idx_list)
         held = getattr(stream, "_psb_keep", None)       # converted index copies stay alive until the stream is joined

@@ -31,7 +31,9 @@ def _on(stream, dev, *inputs):
     keep = getattr(stream, "_psb_keep", None)
     if keep is None:
         keep = stream._psb_keep = []
-    keep.append(tuple(t for t in inputs if t is not None))
+    # detached aliases: a tensor with a grad_fn would keep its autograd graph -- and the AccumulateGrad nodes of the
+    # parameters behind it, bound to the stream of THAT pass -- alive into the next step (breaks a later graph capture)
+    keep.append(tuple(t.detach() for t in inputs if t is not None))
     del keep[:-8]
     return torch.cuda.stream(stream)
 
