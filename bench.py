@@ -616,7 +616,7 @@ def run_b200_arm(a):
             model = ShardedItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
             transport = "nccl-all-to-all"
     else:
-        model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V))
+        model = ItemTransformerRanker(args, "cuda", V, P, None, word_dists=synth.word_dists(V), grad_mode=a.grad_mode)
     optim = build_optim(args, model)
     model.train()
     torch.manual_seed(666 + 7919 * rank)      # per-rank negatives / dropout masks from here on
@@ -919,6 +919,9 @@ def main():
                     help="seconds the 16M-row section (extra) may take before the line is printed without it")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],
                     help="N>1: auto = NVLink peer memory when CUDA IPC works, else NCCL all-to-all; nccl forces the latter")
+    ap.add_argument("--grad-mode", default="dense", choices=["dense", "rowsparse"], dest="grad_mode",
+                    help="N=1: dense = the reference's dense table gradients + dense Adam sweep; rowsparse = compact row "
+                         "gradients + row-sparse lazily caught-up Adam (dense-equivalent results, O(rows touched))")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)

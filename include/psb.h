@@ -131,6 +131,22 @@ int psb_ns_loss_fwd(const float* anchor_a, const float* anchor_b,
                     float* grad_anchor_a, float* grad_anchor_b,
                     psb_stream_t stream);
 
+/* The TEM score + loss tail (models/item_transformer.py:485,:493-514) straight from the fused encoder's output
+ * block: enc_out [n, 1 + k, d] holds, per sample, the encoder output of the positive sequence and of its k negative
+ * copies (psb_encoder_fwd with copies = 1 + k).  Same arithmetic as psb_ns_loss_fwd(anchor_a = enc_out[:, 0],
+ * anchor_b = enc_out[:, 1:], w = 1) without the two repacking copies; coef_pos / coef_neg / grad_enc_out
+ * ([n, 1 + k, d], the gradient of  grad_scale * sum_i loss_rows[i]  with respect to enc_out) come out multiplied by
+ * grad_scale -- 1 / n for the reference's .mean() (:514).  k <= 7, d <= 128. */
+int psb_tem_loss_fwd(const float* enc_out, const float* table, int64_t table_rows, int64_t d, const float* bias,
+                     const int64_t* pos_idx /* [n] */, const int64_t* neg_idx /* [n, k] */, float pos_weight,
+                     int64_t n, int64_t k, float grad_scale, float* loss_rows /* [n] */, float* coef_pos /* [n] */,
+                     float* coef_neg /* [n, k] */, float* grad_enc_out, psb_stream_t stream);
+/* *loss_out = mean(ps_rows[0..n_ps)) + mean(il_rows[0..n_il)) (ps_loss + item_loss, :515-520), fixed summation order;
+ * *acc_ps += mean(ps_rows), *acc_il += mean(il_rows): the running sums the trainer prints (trainer.py:88-98; the
+ * reference adds .item() values on the host).  acc pointers may be NULL; n_il may be 0. */
+int psb_tem_loss_finish(const float* ps_rows, const float* il_rows, int64_t n_ps, int64_t n_il, float* loss_out,
+                        float* acc_ps, float* acc_il, psb_stream_t stream);
+
 /* scores[i,c] = <anchor[i], table[idx[i,c]]> (+ bias[idx[i,c]]): candidate scoring of
  * test_dotproduct (models/item_transformer.py:141-145) for an explicit candidate list
  * idx [n, c_per] (the reference's 500-candidate segments, item_pv_dataset.py:65-68). */

@@ -96,6 +96,9 @@ SIGNATURES = {
     "psb_meanpool_token_weights": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "psb_ns_loss_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32,
                                 c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_tem_loss_fwd": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp,
+                                 c_vp, c_vp]),
+    "psb_tem_loss_finish": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "psb_score_rows": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "psb_scatter_reduce_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "psb_scatter_reduce_rows": (c_i32, [ctypes.POINTER(Contrib), c_i32, c_i64, c_i64, c_i64, c_vp, c_i64,

@@ -301,7 +301,13 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
                   const int64_t* __restrict__ neg_idx, const uint8_t* __restrict__ mask, int64_t pad_idx,
                   const float* __restrict__ neg_weight, float pos_weight, int64_t n, int k,
                   float* __restrict__ loss, float* __restrict__ coef_pos, float* __restrict__ coef_neg,
-                  float4* __restrict__ grad_a, float4* __restrict__ grad_b) {
+                  float4* __restrict__ grad_a, float4* __restrict__ grad_b, int a_stride = 1, int b_stride = -1,
+                  float grad_scale = 1.f) {
+  // Anchor layout: anchor_a row of anchor i at row i * a_stride, anchor_b row of (i, c) at row i * b_stride + c (the
+  // gradient outputs use the same layout).  Defaults (1, k): two packed matrices [n, d] and [n * k, d].  The TEM tail
+  // reads / writes the encoder's [n, 1 + k, d] block in place: a_stride = b_stride = 1 + k, anchor_b = block + d.
+  // grad_scale multiplies coefficients and anchor gradients (the 1 / n of the batch mean).
+  if (b_stride < 0) b_stride = k;
   const int lane = threadIdx.x & 31;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t i = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -327,7 +333,7 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
     m.idx = (r < 0 || r >= table_rows) ? -1 : static_cast<int>(r);
   };
   auto issue = [&](const Meta& m, int64_t a_i, float4 (&row)[NR], float4& a, float& bias_v) {
-    a = col_ok ? anchor_a[a_i * d4 + lane] : zero4();
+    a = col_ok ? anchor_a[a_i * a_stride * d4 + lane] : zero4();
     bias_v = (bias != nullptr && m.idx >= 0) ? bias[m.idx] : 0.f;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
@@ -341,7 +347,7 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
     for (int s = 0; s < 8; ++s) {
       if (s < NR) {
         float4 anc = a;
-        if (HAS_B && s >= 1 && s <= k && col_ok) anc = anchor_b[(a_i * k + (s - 1)) * d4 + lane];
+        if (HAS_B && s >= 1 && s <= k && col_ok) anc = anchor_b[(a_i * b_stride + (s - 1)) * d4 + lane];
         v[s] = dot4(anc, row[s]);
       } else {
         v[s] = 0.f;
@@ -374,7 +380,7 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
     const float mv = __shfl_sync(kFull, m.valid ? 1.f : 0.f, 0);
     float g = 0.f, lterm = 0.f;
     if (my_s <= k) {
-      g = mv * wt * (sigmoidf_(x) - tgt);          // masked-mean denominator is 1 when w == 1
+      g = grad_scale * (mv * wt * (sigmoidf_(x) - tgt));   // masked-mean denominator is 1 when w == 1
       if (writer) {
         lterm = wt * bce_value(x, tgt);
         if (my_s == 0) coef_pos[a_i] = g;
@@ -391,14 +397,14 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
         if (s <= k && col_ok) {
           float4 o = zero4();
           fma4(o, gs, row[s]);
-          grad_b[(a_i * k + (s - 1)) * d4 + lane] = o;
+          grad_b[(a_i * b_stride + (s - 1)) * d4 + lane] = o;
         }
       } else {
         fma4(ga, gs, row[s]);   // gs == 0 for s > k
       }
     }
     if (lane == 0) loss[a_i] = lsum;
-    if (col_ok) grad_a[a_i * d4 + lane] = ga;
+    if (col_ok) grad_a[a_i * a_stride * d4 + lane] = ga;
   };
 
   if (!DB) {
@@ -493,9 +499,82 @@ score_rows_kernel(const float4* __restrict__ anchor, const float4* __restrict__ 
   }
 }
 
+// loss = mean(ps_rows) + mean(il_rows) with fixed-order sums (one CTA); the running sums the trainer reads
+// (model.ps_loss / item_loss, trainer.py:88-98) are advanced in the same launch.
+__global__ void __launch_bounds__(256) tem_loss_finish_kernel(const float* __restrict__ ps_rows,
+                                                              const float* __restrict__ il_rows, int n_ps, int n_il,
+                                                              float* __restrict__ loss_out, float* __restrict__ acc_ps,
+                                                              float* __restrict__ acc_il) {
+  __shared__ float wa[8], wb[8];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < n_ps; i += 256) a += ps_rows[i];
+  for (int i = threadIdx.x; i < n_il; i += 256) b += il_rows[i];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    wa[threadIdx.x >> 5] = a;
+    wb[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, sb = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      sa += wa[w];
+      sb += wb[w];
+    }
+    const float ps = sa / static_cast<float>(n_ps > 0 ? n_ps : 1);
+    const float il = n_il > 0 ? sb / static_cast<float>(n_il) : 0.f;
+    *loss_out = ps + il;
+    if (acc_ps != nullptr) *acc_ps += ps;
+    if (acc_il != nullptr) *acc_il += il;
+  }
+}
+
 }  // namespace psb
 
 using namespace psb;
+
+extern "C" int psb_tem_loss_fwd(const float* enc_out, const float* table, int64_t table_rows, int64_t d,
+                                const float* bias, const int64_t* pos_idx, const int64_t* neg_idx, float pos_weight,
+                                int64_t n, int64_t k, float grad_scale, float* loss_rows, float* coef_pos,
+                                float* coef_neg, float* grad_enc_out, psb_stream_t stream) {
+  int st = check_table_args(table, table_rows, d);
+  if (st != PSB_OK) return st;
+  if (n < 0 || k < 1 || k > 7 || d > 128) return PSB_E_DIM;
+  if (n == 0) return PSB_OK;
+  if (enc_out == nullptr || pos_idx == nullptr || neg_idx == nullptr || loss_rows == nullptr || coef_pos == nullptr ||
+      coef_neg == nullptr || grad_enc_out == nullptr)
+    return PSB_E_ARG;
+  if (misaligned16(enc_out) || misaligned16(grad_enc_out)) return PSB_E_ALIGN;
+  if (table_rows >= (1ll << 31)) return PSB_E_DIM;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int d4 = static_cast<int>(d / 4);
+  const int C = static_cast<int>(k) + 1;
+  const int gridf = grid_for(n, 8, 32);
+  const float4* a4 = reinterpret_cast<const float4*>(enc_out);
+  float4* g4 = reinterpret_cast<float4*>(grad_enc_out);
+  PSB_PROF("ns_loss_w1_kernel", s);
+#define PSB_TEM_LAUNCH(NR)                                                                                          \
+  ns_loss_w1_kernel<true, NR, false><<<gridf, 256, 0, s>>>(a4, a4 + d4, reinterpret_cast<const float4*>(table),     \
+                                                           table_rows, d4, bias, pos_idx, neg_idx, nullptr, -1, nullptr, \
+                                                           pos_weight, n, static_cast<int>(k), loss_rows, coef_pos,  \
+                                                           coef_neg, g4, g4 + d4, C, C, grad_scale)
+  if (k <= 5) PSB_TEM_LAUNCH(6); else PSB_TEM_LAUNCH(8);
+#undef PSB_TEM_LAUNCH
+  return launch_status();
+}
+
+extern "C" int psb_tem_loss_finish(const float* ps_rows, const float* il_rows, int64_t n_ps, int64_t n_il,
+                                   float* loss_out, float* acc_ps, float* acc_il, psb_stream_t stream) {
+  if (ps_rows == nullptr || loss_out == nullptr || n_ps <= 0 || n_il < 0 || (n_il > 0 && il_rows == nullptr) ||
+      n_ps > (1 << 30) || n_il > (1 << 30))
+    return PSB_E_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PSB_PROF("tem_loss_finish_kernel", s);
+  tem_loss_finish_kernel<<<1, 256, 0, s>>>(ps_rows, il_rows, static_cast<int>(n_ps), static_cast<int>(n_il), loss_out,
+                                           acc_ps, acc_il);
+  return launch_status();
+}
 
 // Tuning knob read once: PSB_NS_W1 selects the w == 1 kernel variant (see psb_ns_loss_fwd).
 static int ns_w1_variant() {

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) adam_rows_catchup_kernel(const psb_adam_r
       if (prev < cur) prev = atomicMax(t.last_step + r, static_cast<int>(cur));
     }
     prev = __shfl_sync(kFull, prev, 0);
-    if (prev >= cur) continue;
+    if (prev >= cur || prev == 0) continue;      // current, or never updated: moments are zero, nothing to replay
     catchup_row(t, r, prev, cur, h, hist, hist_cap, catchup_max);
   }
 }
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(const RowTables R, const
   const int64_t r = t.rows[i];
   if (r < 0 || r >= t.table_rows) return;
   const int prev = t.last_step[r];
-  if (prev < step - 1) catchup_row(t, r, prev, step - 1, h, hist, hist_cap, catchup_max);
+  if (prev > 0 && prev < step - 1) catchup_row(t, r, prev, step - 1, h, hist, hist_cap, catchup_max);
   __syncwarp();
   const int d4 = static_cast<int>(t.d >> 2);
   float4* p4 = reinterpret_cast<float4*>(t.p + r * t.d);

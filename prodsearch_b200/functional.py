@@ -334,6 +334,48 @@ def ns_loss_dense_pos(anchor, dense_pos, table, neg_idx, sink, mask=None):
     return pos + neg
 
 
+class TemTailFn(Function):
+    """The TEM tail in two launches: ranking loss on the encoder's [B, 1 + K, d] output block in place
+    (psb_tem_loss_fwd; no repacking copies of the positive / negative rows) and
+    ``loss = mean(ps_rows) + mean(item_loss_rows)`` with the trainer's running sums (psb_tem_loss_finish) --
+    item_transformer.py:485,:493-520.  The gradient with respect to the block comes out of the forward kernel already
+    laid out and scaled by 1 / B, so backward is one multiply by the upstream scalar plus the sink contributions."""
+
+    @staticmethod
+    def forward(ctx, enc_out, il_rows, weight, bias, pos_idx, neg_idx, sink, pos_weight, acc_ps, acc_il, src_rows):
+        B = pos_idx.numel()
+        rows, cp, cn, g_enc = ops.tem_loss(enc_out, weight, pos_idx, neg_idx, bias=bias, pos_weight=pos_weight,
+                                           grad_scale=1.0 / B)
+        loss = ops.tem_loss_finish(rows, il_rows, acc_ps, acc_il)
+        ctx.sink, ctx.pos_idx, ctx.neg_idx, ctx.src_rows = sink, pos_idx, neg_idx, src_rows
+        ctx.has_bias = bias is not None
+        ctx.n_il = il_rows.numel()
+        ctx.save_for_backward(enc_out, cp, cn, g_enc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        enc_out, cp, cn, g_enc = ctx.saved_tensors
+        g = g.contiguous()                                      # 0-dim upstream gradient
+        B, K = cn.shape
+        flat = enc_out.view(B * (1 + K), -1)
+        pos_rows, neg_rows = ctx.src_rows
+        every = B * K + 1                                       # scale2 index = slot / every = 0: the scalar g
+        ctx.sink.add(ctx.pos_idx.reshape(-1), flat, src_row=pos_rows, scale=cp.view(-1), scale2=g.view(1),
+                     scale2_div=every, to_bias=ctx.has_bias)
+        ctx.sink.add(ctx.neg_idx.reshape(-1), flat, src_row=neg_rows, scale=cn.view(-1), scale2=g.view(1),
+                     scale2_div=every, to_bias=ctx.has_bias)
+        grad_enc = g_enc * g if ctx.needs_input_grad[0] else None
+        grad_il = (g / ctx.n_il).expand(ctx.n_il) if ctx.needs_input_grad[1] else None
+        return grad_enc, grad_il, None, None, None, None, None, None, None, None, None
+
+
+def tem_tail(enc_out, il_rows, weight, pos_idx, neg_idx, sink, bias=None, pos_weight=1.0, acc_ps=None, acc_il=None,
+             src_rows=None):
+    ensure_current(weight, (pos_idx, neg_idx))
+    return TemTailFn.apply(enc_out, il_rows, weight, bias, pos_idx, neg_idx, sink, pos_weight, acc_ps, acc_il, src_rows)
+
+
 class SeqEncoderFn(Function):
     """Fused last encoder layer + final LayerNorm at one output position (psb_encoder_fwd / _bwd).
     Token inputs: (first [S,d], table, idx [S,T-1]) -- gradients of the table rows go to ``sink`` --

@@ -22,6 +22,7 @@ from .transformer import TransformerEncoder
 class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
     overlap_query_pooling = True     # query pooling on a side stream under the encoder's plan / transpose kernels
     overlap_item_to_words = True     # item -> word loss kernels on a side stream next to the encoder
+    fused_loss_tail = True           # training under dropout: ranking loss on the encoder's output block in place
 
     def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None,
                  grad_mode="dense"):
@@ -173,9 +174,19 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
             side = self._iw_stream
             side.wait_stream(cur)
         sharded = type(self)._resolve_item_rows is not ItemTransformerRanker._resolve_item_rows
+        if not sharded:
+            # row-sparse optimizer: the rows this step reads are brought up to date in as few launches as possible
+            # (no-ops for ordinary tables) -- history + target rows and query + target words now, the sampled
+            # negatives on the side branch as soon as they exist; the gather wrappers then find nothing left to do
+            F_.ensure_current(self.hist_product_emb.weight if self.args.sep_prod_emb else self.product_emb.weight,
+                              (u_item_idxs,))
+            F_.ensure_current(self.product_emb.weight, (target_prod_idxs,))
+            F_.ensure_current(self.word_embeddings.weight, (query_word_idxs, pos_iword_idxs))
         if side is not None and not sharded and self.injected_negatives is None:
             with torch.cuda.stream(side):
                 neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
+                F_.ensure_current(self.product_emb.weight, (neg_item_idxs,))
+                F_.ensure_current(self.word_embeddings.weight, (neg_word_idxs,))
             # (allocated on the side stream and alive until backward has run; the side stream's next allocation
             # happens after its next wait on the current stream, so the allocator cannot recycle them early)
         else:
@@ -189,18 +200,28 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
         item_loss_rows = self.item_to_words(tgt_idx, pos_iword_idxs, K, neg_word_idxs, item_w, item_sink, stream=side,
                                             reduce=False)
         stochastic = self.training and self.args.dropout > 0
+        bias = self.product_bias if self.args.sim_func == "bias_product" else None
+        pos_weight = float(K) if self.args.pos_weight else 1.0
         if stochastic:
             # dropout makes the positive and the K negative encodes differ (transformer.py:56, neural.py:226):
             # 1 + K dropout draws of the SAME sequence, K/V projections shared between them
             out = self.encode_queries(query_word_idxs, u_item_idxs, copies=1 + K, hist=hist).view(B, 1 + K, -1)
+            if self.fused_loss_tail and K <= 7 and self.embedding_size <= 128 and out.is_cuda:
+                # ranking loss on the encoder's output block in place + loss combination and running sums: two launches
+                if side is not None:
+                    cur.wait_stream(side)        # sampled item negatives and the item -> word losses are ready
+                if self._ps_acc is None:
+                    self._ps_acc = torch.zeros((), device=out.device)
+                    self._item_acc = torch.zeros((), device=out.device)
+                return F_.tem_tail(out, item_loss_rows, item_w, tgt_idx, neg_idx, item_sink, bias=bias,
+                                   pos_weight=pos_weight, acc_ps=self._ps_acc, acc_il=self._item_acc,
+                                   src_rows=self._tail_src_rows(B, K, out.device))
             pos_out = out[:, 0].contiguous()
             neg_out = out[:, 1:].reshape(B * K, -1)
         else:
             # deterministic encoder: the K copies the reference re-encodes (:473-476) are identical
             pos_out = self.encode_queries(query_word_idxs, u_item_idxs, hist=hist)
             neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
-        bias = self.product_bias if self.args.sim_func == "bias_product" else None
-        pos_weight = float(K) if self.args.pos_weight else 1.0
         if side is not None:
             cur.wait_stream(side)                # the sampled item negatives (and the item -> word losses) are ready
         ps = F_.ns_loss(pos_out.contiguous(), item_w, tgt_idx.view(B, 1), neg_idx.view(B, 1, K), item_sink,
@@ -214,6 +235,17 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
             self._ps_acc.add_(ps_loss.detach())
             self._item_acc.add_(item_loss.detach())
         return ps_loss + item_loss
+
+    def _tail_src_rows(self, B, K, device):
+        """Rows of the encoder's [B * (1 + K), d] output block that score the target item (b, 0) and the negatives
+        (b, 1 + c): the source-row lists of the item table's gradient contributions (cached: static across replays)."""
+        key = (B, K, str(device))
+        cache = getattr(self, "_tail_rows_cache", None)
+        if cache is None or cache[0] != key:
+            base = torch.arange(B, device=device, dtype=torch.int64) * (1 + K)
+            neg = (base.view(B, 1) + 1 + torch.arange(K, device=device, dtype=torch.int64).view(1, K)).reshape(-1)
+            cache = self._tail_rows_cache = (key, (base.contiguous(), neg.contiguous()))
+        return cache[1]
 
     def item_to_words(self, target_prod_idxs, target_word_idxs, n_negs, neg_sample_idxs=None, item_w=None,
                       item_sink=None, stream=None, reduce=True):

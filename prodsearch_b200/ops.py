@@ -127,6 +127,34 @@ def ns_loss(anchor_a, table, pos_idx, neg_idx, anchor_b=None, bias=None, mask=No
     return loss, cp, cn, ga, gb
 
 
+def tem_loss(enc_out, table, pos_idx, neg_idx, bias=None, pos_weight=1.0, grad_scale=1.0):
+    """TEM score + loss tail on the encoder's output block enc_out [n, 1 + k, d] (psb_tem_loss_fwd).  Returns
+    (loss_rows [n], coef_pos [n], coef_neg [n, k], grad_enc_out [n, 1 + k, d]); coefficients and gradient are
+    multiplied by grad_scale."""
+    pos_idx, neg_idx = _idx(pos_idx), _idx(neg_idx)
+    n = pos_idx.numel()
+    k = neg_idx.numel() // max(n, 1)
+    d = table.shape[1]
+    dev = table.device
+    rows = torch.empty((n,), dtype=f32, device=dev)
+    cp = torch.empty((n,), dtype=f32, device=dev)
+    cn = torch.empty((n, k), dtype=f32, device=dev)
+    g = torch.empty((n, 1 + k, d), dtype=f32, device=dev)
+    check(load().psb_tem_loss_fwd(ptr(enc_out, f32), ptr(table, f32), table.shape[0], d, ptr(bias, f32), ptr(pos_idx),
+                                  ptr(neg_idx), float(pos_weight), n, k, float(grad_scale), ptr(rows), ptr(cp), ptr(cn),
+                                  ptr(g), stream_ptr()), "psb_tem_loss_fwd")
+    return rows, cp, cn, g
+
+
+def tem_loss_finish(ps_rows, il_rows, acc_ps=None, acc_il=None):
+    """0-dim loss = mean(ps_rows) + mean(il_rows); the running sums are advanced in the same launch."""
+    out = torch.empty((), dtype=f32, device=ps_rows.device)
+    check(load().psb_tem_loss_finish(ptr(ps_rows, f32), ptr(il_rows, f32), ps_rows.numel(),
+                                     il_rows.numel() if il_rows is not None else 0, ptr(out), ptr(acc_ps, f32),
+                                     ptr(acc_il, f32), stream_ptr()), "psb_tem_loss_finish")
+    return out
+
+
 def score_rows(anchor, table, idx, bias=None):
     """scores[i,c] = <anchor[i], table[idx[i,c]]> (+bias) for an explicit candidate list (psb_score_rows)."""
     idx = _idx(idx)
@@ -367,6 +395,6 @@ def _profiled(name, fn):
     return wrapper
 
 
-for _n in ("catalog_prepare_f16", "table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "score_rows",
+for _n in ("catalog_prepare_f16", "table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "tem_loss", "tem_loss_finish", "score_rows",
            "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge", "encoder_fwd", "encoder_bwd"):
     globals()[_n] = _profiled(_n, globals()[_n])

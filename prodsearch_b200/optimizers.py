@@ -292,17 +292,26 @@ class LazyRows(object):
         self.optim, self.weight = optim, weight
         self._event = None
         self._key = None
+        self._seen = set()          # (data_ptr, numel) of the index tensors already made current in this step
 
     def ensure(self, idx_list):
+        """Index tensors already handled in this step (a model pre-ensures everything it will read in as few launches
+        as possible; the gather wrappers then find nothing left to do) are skipped -- by identity of their storage."""
         cur = torch.cuda.current_stream(self.weight.device)
         key = (torch.cuda.is_current_stream_capturing(), _lib.PARAM_EPOCH[0])
+        if self._key != key:
+            self._seen = set()
+        todo = [t for t in idx_list if t is not None and t.numel() > 0 and (t.data_ptr(), t.numel()) not in self._seen]
+        if not todo:
+            return None
         if self._event is None:
             self._event = torch.cuda.Event()
         elif self._key == key:
             cur.wait_event(self._event)
-        keep = self.optim._catchup(self.weight, idx_list)
+        keep = self.optim._catchup(self.weight, todo)
         self._event.record(cur)
         self._key = key
+        self._seen.update((t.data_ptr(), t.numel()) for t in todo)
         return keep
 
     def flush(self):
