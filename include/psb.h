@@ -196,6 +196,21 @@ int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs,
                             int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
                             psb_stream_t stream);
 
+/* The same in two calls, so that the SORT -- which only reads the index lists -- can run long before the gradient
+ * values exist (on a side stream next to the backward pass; the index tensors of a training step are all known when
+ * its forward pass ends): psb_scatter_sort_rows reads only idx / n of the contributions and leaves the sorted slots,
+ * segment table, unique_rows and n_unique in the workspace / outputs; psb_scatter_reduce_sorted, given contributions
+ * with the SAME idx / n in the SAME order and the same workspace, runs the segmented reduce.  Together they produce
+ * bit for bit what psb_scatter_reduce_rows produces. */
+int psb_scatter_sort_rows(const psb_contrib_t* contribs /* host; idx and n only */, int32_t n_contribs,
+                          int64_t table_rows, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                          int32_t* unique_rows, int32_t* n_unique, psb_stream_t stream);
+int psb_scatter_reduce_sorted(const psb_contrib_t* contribs /* host */, int32_t n_contribs, int64_t table_rows,
+                              int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                              const int32_t* unique_rows, float* reduced, float* reduced_bias,
+                              const int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                              psb_stream_t stream);
+
 /* dense[rows[u], :] = 0 (and dense_bias[rows[u]] = 0) for u < *n_rows: clears the
  * rows a previous step touched so a persistent dense .grad costs O(batch). */
 int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows,

@@ -103,6 +103,9 @@ SIGNATURES = {
     "psb_scatter_reduce_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "psb_scatter_reduce_rows": (c_i32, [ctypes.POINTER(Contrib), c_i32, c_i64, c_i64, c_i64, c_vp, c_i64,
                                         c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "psb_scatter_sort_rows": (c_i32, [ctypes.POINTER(Contrib), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "psb_scatter_reduce_sorted": (c_i32, [ctypes.POINTER(Contrib), c_i32, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "psb_zero_rows": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "psb_catalog_topk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i32]),
     "psb_catalog_topk": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp,

@@ -1500,14 +1500,17 @@ static unsigned long long* tc16_stat_buffer() {
 // = 256 queries per pass at 128 items per MMA -- half the tcgen05.mma instructions for the same flops (the issuing
 // thread, not the tensor pipe, paces the MT = 4 kernel: DESIGN.md section 8) against twice the table passes.
 // Tuning knob, read once per process.
-static int tc16_max_tiles_per_cta() {
+static int tc16_max_tiles_per_cta(int m_tiles) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSB_TC16_MT");
-    const int x = e != nullptr ? atoi(e) : 4;
-    v = (x >= 1 && x <= 4) ? x : 4;
+    const int x = e != nullptr ? atoi(e) : 0;
+    v = (x >= 1 && x <= 4) ? x : 0;
   }
-  return v;
+  if (v > 0) return v;
+  // unset: measured on B200 (profiles/r02a_tc16_variants.jsonl, 1M items): 4 tiles per CTA win up to a few hundred
+  // queries (M = 384: 0.305 vs 0.314 ms), 2 tiles x 128 items per MMA from a few thousand on (M = 4096: 2.01 vs 2.06 ms)
+  return m_tiles >= 16 ? 2 : 4;
 }
 
 // candidate lists per (query row, item slice): one per epilogue part that scores columns of the row's query tile
@@ -1533,7 +1536,7 @@ struct Tc16Plan {
 static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   Tc16Plan p;
   p.m_tiles = static_cast<int>((m + kTM - 1) / kTM);
-  const int max_mt = tc16_max_tiles_per_cta();
+  const int max_mt = tc16_max_tiles_per_cta(p.m_tiles);
   p.groups = (p.m_tiles + max_mt - 1) / max_mt;
   p.MT = (p.m_tiles + p.groups - 1) / p.groups;
   p.TN = p.MT <= 2 ? 128 : 64;

@@ -930,11 +930,14 @@ extern "C" int64_t psb_scatter_reduce_workspace_bytes(int64_t n_total, int64_t t
   return layout_for(n_total > 0 ? n_total : 1).total;
 }
 
-extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
-                                       int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
-                                       int32_t* unique_rows, float* reduced, float* reduced_bias,
-                                       int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
-                                       psb_stream_t stream) {
+// phase 0: sort + reduce (psb_scatter_reduce_rows); 1: sort only -- only idx / n of the contributions are read
+// (psb_scatter_sort_rows); 2: reduce only, the workspace holds the result of a phase-1 call over the same idx / n /
+// order (psb_scatter_reduce_sorted).  Which buffers hold the sorted slots is a pure function of (n_total, table_rows).
+static int scatter_run(int phase, const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
+                       int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                       int32_t* unique_rows, float* reduced, float* reduced_bias,
+                       int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                       psb_stream_t stream) {
   if (contribs == nullptr || n_contribs <= 0 || n_contribs > PSB_MAX_CONTRIBS || workspace == nullptr ||
       unique_rows == nullptr || n_unique == nullptr || table_rows <= 0 || table_rows >= (1ll << 31))
     return PSB_E_ARG;
@@ -945,10 +948,12 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   int64_t n_total = 0;
   for (int c = 0; c < n_contribs; ++c) {
     const psb_contrib_t& cc = contribs[c];
-    if (cc.n < 0 || (cc.n > 0 && (cc.idx == nullptr || cc.src == nullptr))) return PSB_E_ARG;
-    if (cc.src_row == nullptr && cc.src_div < 1) return PSB_E_ARG;
-    if (cc.scale2 != nullptr && cc.scale2_div < 1) return PSB_E_ARG;
-    if (misaligned16(cc.src)) return PSB_E_ALIGN;
+    if (cc.n < 0 || (cc.n > 0 && (cc.idx == nullptr || (phase != 1 && cc.src == nullptr)))) return PSB_E_ARG;
+    if (phase != 1) {
+      if (cc.src_row == nullptr && cc.src_div < 1) return PSB_E_ARG;
+      if (cc.scale2 != nullptr && cc.scale2_div < 1) return PSB_E_ARG;
+      if (misaligned16(cc.src)) return PSB_E_ALIGN;
+    }
     T.c[c] = cc;
     T.off[c] = static_cast<uint32_t>(n_total);
     n_total += cc.n;
@@ -978,7 +983,15 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
   int st;
 
   const int64_t cs_per = ((table_rows + 1 + kSmallNT - 1) / kSmallNT) | 1;   // odd number of bins per thread
-  if (n_total <= kSmallCap && cs_per <= kCsMaxPer) {
+  if (phase == 2) {                         // already sorted: where the sort phase left its result
+    if (n_total <= kSmallCap || (passes & 1) == 0) {
+      sorted_slots = vals_a;
+      sorted_keys = keys_a;
+    } else {
+      sorted_slots = vals_b;
+      sorted_keys = keys_b;
+    }
+  } else if (n_total <= kSmallCap && cs_per <= kCsMaxPer) {
     static DeviceAttr attr_smem;
     const size_t smem = static_cast<size_t>(cs_per) * kSmallNT * 4 + kCsBitmaps * 512 * 4 + (kCsMaxLong + 3) * 4 +
                         static_cast<size_t>(kSmallCap) * 2 + kCsBitmaps * 512 * 2 + 33 * 4;
@@ -1046,7 +1059,7 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     sorted_keys = ki;
   }
 
-  if (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr) {
+  if (phase != 1 && (reduced != nullptr || reduced_bias != nullptr || dense_grad != nullptr || dense_bias_grad != nullptr)) {
     const int ch_shift = unit_shift_for(n_total);
     const int grid = grid_for((n_total >> ch_shift) + 1, 8, 16);
     const int grid_fix = grid_for((n_total >> ch_shift) + 1, 8, 8);
@@ -1075,6 +1088,32 @@ extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_
     if ((st = launch_status()) != PSB_OK) return st;
   }
   return PSB_OK;
+}
+
+extern "C" int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
+                                       int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                                       int32_t* unique_rows, float* reduced, float* reduced_bias,
+                                       int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                                       psb_stream_t stream) {
+  return scatter_run(0, contribs, n_contribs, table_rows, d, drop_idx, workspace, workspace_bytes, unique_rows, reduced,
+                     reduced_bias, n_unique, dense_grad, dense_bias_grad, stream);
+}
+
+extern "C" int psb_scatter_sort_rows(const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
+                                     int64_t drop_idx, void* workspace, int64_t workspace_bytes, int32_t* unique_rows,
+                                     int32_t* n_unique, psb_stream_t stream) {
+  return scatter_run(1, contribs, n_contribs, table_rows, 4, drop_idx, workspace, workspace_bytes, unique_rows, nullptr,
+                     nullptr, n_unique, nullptr, nullptr, stream);
+}
+
+extern "C" int psb_scatter_reduce_sorted(const psb_contrib_t* contribs, int32_t n_contribs, int64_t table_rows,
+                                         int64_t d, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
+                                         const int32_t* unique_rows, float* reduced, float* reduced_bias,
+                                         const int32_t* n_unique, float* dense_grad, float* dense_bias_grad,
+                                         psb_stream_t stream) {
+  return scatter_run(2, contribs, n_contribs, table_rows, d, drop_idx, workspace, workspace_bytes,
+                     const_cast<int32_t*>(unique_rows), reduced, reduced_bias, const_cast<int32_t*>(n_unique), dense_grad,
+                     dense_bias_grad, stream);
 }
 
 extern "C" int psb_zero_rows(const int32_t* rows, const int32_t* n_rows, int64_t max_rows, int64_t d,

@@ -47,7 +47,23 @@ class RowGradSink(object):
     chains of the item and the word table overlap (inside a captured CUDA graph they become parallel branches)."""
 
     concurrent = True
+    presort = True                    # sort the step's index lists next to the backward pass (see expect())
     _forked = []                      # sinks whose chain is in flight on a side stream (not yet joined)
+    _seq = 0                          # global order of expect() / mark_forward_end() calls
+    _fwd_mark = {}                    # device -> (event recorded when a model's forward pass ended, its sequence number)
+
+    @staticmethod
+    def mark_forward_end(device):
+        """A model calls this when its forward pass is complete and every side stream has been joined into the current
+        one: an event recorded here covers the producers of ALL index lists announced so far (sampled negatives
+        included), so the sinks' sorts can start behind it instead of behind whatever backward has enqueued by the
+        time the first contribution arrives."""
+        dev = torch.device(device)
+        mark = RowGradSink._fwd_mark.get(dev)
+        ev = mark[0] if mark is not None else torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        RowGradSink._seq += 1
+        RowGradSink._fwd_mark[dev] = (ev, RowGradSink._seq)
 
     def __init__(self, weight, drop_idx=-1, bias=None, mode="dense"):
         self.weight = weight
@@ -63,6 +79,75 @@ class RowGradSink(object):
         self._nu_buf = None
         self._stream = None
         self._hold = None
+        self._expected = []           # index tensors the forward pass announced (expect), in forward order
+        self._exp_event = None
+        self._sort_stream = None
+        self._sort_done = None
+        self._presort = None          # dict(exp, ws, uniq, nu, cleared) of the sort launched for this step
+        self._sort_bufs = None
+        self._last_seq = 0
+
+    # -- called from Function.forward ---------------------------------------------------
+    def expect(self, idx):
+        """Announce an index list that backward will contribute with.  The sort of a step's contributions only needs
+        the index lists, and those all exist when the forward pass ends: at the first contribution of the backward
+        pass the sink sorts the announced lists on its own stream -- ordered behind the forward pass only, so it runs
+        NEXT TO the backward kernels -- and finalize() is left with the segmented reduce.  If what backward delivers
+        does not match what forward announced (a branch without gradient, a second forward), finalize() falls back to
+        the one-call sort + reduce; the result is the same."""
+        if not (RowGradSink.presort and self.weight.is_cuda and self.weight.requires_grad):
+            return
+        if len(self._expected) >= 2 * ops._lib.MAX_CONTRIBS:
+            return
+        t = ops._idx(idx).reshape(-1)
+        if t.numel() == 0:
+            return
+        self._expected.append(t)
+        RowGradSink._seq += 1
+        self._last_seq = RowGradSink._seq
+
+    def _launch_presort(self):
+        exp, w = self._expected, self.weight
+        if not exp or len(exp) > ops._lib.MAX_CONTRIBS:
+            return
+        if self.mode == "dense" and w.grad is not None and w.grad is self._dense:
+            return                                   # gradient accumulation: finalize() takes its own path
+        dev = w.device
+        n_total = sum(t.numel() for t in exp)
+        if self._sort_stream is None:
+            self._sort_stream = torch.cuda.Stream(device=dev)
+            self._sort_done = torch.cuda.Event()
+        bufs = self._sort_bufs
+        wb = ops.scatter_workspace_bytes(n_total, w.shape[0])
+        if bufs is None or bufs[0].numel() < wb or bufs[1].numel() < n_total:
+            if self._prev is not None and self._prev != "all" and bufs is not None and self._prev[0] is bufs[1]:
+                self._prev = "all"               # the old row list goes away with its buffer: next clear is a memset
+            bufs = self._sort_bufs = (torch.empty(wb, dtype=torch.uint8, device=dev),
+                                      torch.empty(max(n_total, 1), dtype=torch.int32, device=dev),
+                                      torch.zeros(1, dtype=torch.int32, device=dev))
+        ws, uniq, nu = bufs
+        st = self._sort_stream
+        # behind the end of the forward pass when the model marked it after this sink's last announcement, else
+        # behind everything enqueued so far (still correct, less overlap)
+        mark = RowGradSink._fwd_mark.get(dev)
+        if mark is not None and mark[1] >= self._last_seq:
+            st.wait_event(mark[0])
+        else:
+            if self._exp_event is None:
+                self._exp_event = torch.cuda.Event()
+            self._exp_event.record(torch.cuda.current_stream(dev))
+            st.wait_event(self._exp_event)
+        cleared = False
+        with torch.cuda.stream(st):
+            if self.mode == "dense":    # clear last step's rows of the persistent gradient buffers here, off the critical
+                # path -- and BEFORE the sort overwrites the row list they are cleared by (a CUDA-graph replay finds
+                # the previous replay's rows in the same buffer)
+                self._prepare_dense(self.bias is not None and self._dense_bias is not None, clear=True)
+                cleared = True
+            nu.zero_()
+            ops.scatter_sort(exp, w.shape[0], self.drop_idx, ws, uniq, nu)
+            self._sort_done.record(st)
+        self._presort = dict(exp=exp, ws=ws, uniq=uniq, nu=nu, cleared=cleared)
 
     # -- called from Function.backward ------------------------------------------------
     def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
@@ -73,6 +158,8 @@ class RowGradSink(object):
         if not self._queued:
             self._queued = True
             Variable._execution_engine.queue_callback(self._finalize_callback)
+            if self._expected and self._presort is None:
+                self._launch_presort()
 
     def _finalize_callback(self):
         if not (RowGradSink.concurrent and self.weight.is_cuda):
@@ -90,11 +177,18 @@ class RowGradSink(object):
     def finalize(self):
         self._queued = False
         pending, self._pending = self._pending, []
+        ps, self._presort, self._expected = self._presort, None, []
+        if ps is not None:            # join the sort stream whatever happens next (a captured graph needs it joined)
+            torch.cuda.current_stream(self.weight.device).wait_event(self._sort_done)
         if not pending:
             return
         w = self.weight
         rows, d = w.shape
         want_bias = self.bias is not None and any(c.to_bias for c, _ in pending)
+        if ps is not None and self._finalize_presorted(ps, pending, rows, d, want_bias):
+            return
+        if ps is not None and ps["cleared"]:
+            self._prev = None         # the persistent buffers were already cleared next to the sort
         for lo in range(0, len(pending), ops._lib.MAX_CONTRIBS):
             chunk = pending[lo:lo + ops._lib.MAX_CONTRIBS]
             first = lo == 0
@@ -130,6 +224,47 @@ class RowGradSink(object):
                 if want_bias:
                     self.bias.row_grad = (uniq, redb, nu)
                     w._psb_row_bias = self.bias          # updated with (and stamped like) the table's rows
+
+    def _finalize_presorted(self, ps, pending, rows, d, want_bias):
+        """Reduce over the sort launched at the start of backward.  The contributions are put into the order the
+        forward pass announced their index lists in; any mismatch -> False (the caller runs the one-call path)."""
+        exp = ps["exp"]
+        if len(pending) != len(exp):
+            return False
+        left = list(pending)
+        ordered = []
+        for t in exp:
+            hit = None
+            for j, (c, _) in enumerate(left):
+                if c.idx == t.data_ptr() and int(c.n) == t.numel():
+                    hit = j
+                    break
+            if hit is None:
+                return False
+            ordered.append(left.pop(hit))
+        w = self.weight
+        if self.mode == "dense":
+            if w.grad is not None and w.grad is self._dense:
+                return False
+            if not ps["cleared"]:
+                self._prepare_dense(want_bias, clear=True)
+            elif want_bias and self._dense_bias is None:
+                self._dense_bias = torch.zeros_like(self.bias)
+            ops.scatter_reduce_sorted(ordered, rows, d, self.drop_idx, ps["ws"], ps["uniq"], ps["nu"],
+                                      dense_grad=self._dense, dense_bias_grad=self._dense_bias if want_bias else None)
+            self._prev = (ps["uniq"], ps["nu"])
+            self._attach(w, self._dense)
+            if want_bias:
+                self._attach(self.bias, self._dense_bias)
+        else:
+            red, redb = ops.scatter_reduce_sorted(ordered, rows, d, self.drop_idx, ps["ws"], ps["uniq"], ps["nu"],
+                                                  want_rows=True, want_bias=want_bias)
+            w.row_grad = (ps["uniq"], red, ps["nu"])
+            w._psb_drop_idx = self.drop_idx
+            if want_bias:
+                self.bias.row_grad = (ps["uniq"], redb, ps["nu"])
+                w._psb_row_bias = self.bias
+        return True
 
     def _accumulate_dense(self, chunk, rows, d, want_bias):
         """Gradient accumulation into the persistent buffers: row-sparse reduce of this pass, then a deterministic
@@ -208,6 +343,12 @@ class LazyFlushMixin(object):
         return super().state_dict(*args, **kwargs)
 
 
+def _expect(sink, idx):
+    fn = getattr(sink, "expect", None)
+    if fn is not None:
+        fn(idx)
+
+
 def _dropout_keep(shape, p, training, device):
     """Dropout mask already scaled by 1/(1-p) (None when inactive)."""
     if not training or p <= 0.0:
@@ -221,6 +362,8 @@ class GatherRowsFn(Function):
     @staticmethod
     def forward(ctx, weight, idx, sink, stream=None):
         ctx.sink, ctx.idx = sink, idx
+        if ctx.needs_input_grad[0]:
+            _expect(sink, idx)
         return ops.gather_rows(weight, idx, stream=stream)
 
     @staticmethod
@@ -239,6 +382,8 @@ class MeanPoolFn(Function):
                                            keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias,
                                            stream=stream)
         ctx.sink, ctx.idx, ctx.pad_idx, ctx.mask, ctx.keep = sink, idx, pad_idx, mask, keep_scale
+        if ctx.needs_input_grad[0]:
+            _expect(sink, idx)
         ctx.fs = fs_weight is not None
         if ctx.fs:
             ctx.save_for_backward(out, mean, fs_weight)
@@ -269,6 +414,10 @@ class NSLossFn(Function):
                                            mask=mask, pad_idx=pad_idx, neg_weight=neg_weight,
                                            pos_weight=pos_weight, stream=stream)
         ctx.sink, ctx.pos_idx, ctx.neg_idx = sink, pos_idx, neg_idx
+        if ctx.needs_input_grad[2] or (bias is not None and ctx.needs_input_grad[3]):
+            _expect(sink, pos_idx)
+            if neg_idx.numel() > 0:
+                _expect(sink, neg_idx)
         ctx.has_b, ctx.has_bias = anchor_b is not None, bias is not None
         ctx.save_for_backward(anchor_a, anchor_b, cp, cn, ga, gb)
         return loss
@@ -348,6 +497,9 @@ class TemTailFn(Function):
                                            grad_scale=1.0 / B)
         loss = ops.tem_loss_finish(rows, il_rows, acc_ps, acc_il)
         ctx.sink, ctx.pos_idx, ctx.neg_idx, ctx.src_rows = sink, pos_idx, neg_idx, src_rows
+        if ctx.needs_input_grad[2] or (bias is not None and ctx.needs_input_grad[3]):
+            _expect(sink, pos_idx)
+            _expect(sink, neg_idx)
         ctx.has_bias = bias is not None
         ctx.n_il = il_rows.numel()
         ctx.save_for_backward(enc_out, cp, cn, g_enc)
@@ -390,6 +542,8 @@ class SeqEncoderFn(Function):
                                     seed=opts["seed"], raw_input=opts.get("raw_input", False),
                                     first_ready=opts.get("first_ready"))
         ctx.call, ctx.sink, ctx.idx, ctx.names = call, sink, idx, names
+        if call.tem and sink is not None and call.T > 1 and ctx.needs_input_grad[2]:
+            _expect(sink, idx)
         ctx.shapes = {n: tuple(w.shape) for n, w in zip(names, weights)}
         ctx.pre_ln = opts["pre_ln"]
         ctx.weights = weights

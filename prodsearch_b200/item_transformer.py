@@ -213,9 +213,11 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
                 if self._ps_acc is None:
                     self._ps_acc = torch.zeros((), device=out.device)
                     self._item_acc = torch.zeros((), device=out.device)
-                return F_.tem_tail(out, item_loss_rows, item_w, tgt_idx, neg_idx, item_sink, bias=bias,
+                loss = F_.tem_tail(out, item_loss_rows, item_w, tgt_idx, neg_idx, item_sink, bias=bias,
                                    pos_weight=pos_weight, acc_ps=self._ps_acc, acc_il=self._item_acc,
                                    src_rows=self._tail_src_rows(B, K, out.device))
+                F_.RowGradSink.mark_forward_end(out.device)     # every index list of the step exists: sorts may start
+                return loss
             pos_out = out[:, 0].contiguous()
             neg_out = out[:, 1:].reshape(B * K, -1)
         else:
@@ -234,6 +236,8 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
                 self._item_acc = torch.zeros((), device=ps_loss.device)
             self._ps_acc.add_(ps_loss.detach())
             self._item_acc.add_(item_loss.detach())
+        if ps_loss.is_cuda:
+            F_.RowGradSink.mark_forward_end(ps_loss.device)
         return ps_loss + item_loss
 
     def _tail_src_rows(self, B, K, device):

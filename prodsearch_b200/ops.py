@@ -203,6 +203,33 @@ def scatter_reduce(contribs, table_rows, d, drop_idx=-1, dense_grad=None, dense_
     return uniq, red, redb, nu
 
 
+def scatter_sort(idx_list, table_rows, drop_idx, ws, uniq, nu):
+    """Sort phase of the embedding backward (psb_scatter_sort_rows): only the index lists are read.  ``ws`` /
+    ``uniq`` / ``nu``: caller-owned workspace (psb_scatter_reduce_workspace_bytes), unique-row list and count."""
+    arr = (Contrib * len(idx_list))(*[Contrib(ptr(t), t.numel(), None, None, 1, None, None, 1, 0, 0) for t in idx_list])
+    check(load().psb_scatter_sort_rows(arr, len(idx_list), table_rows, int(drop_idx), ptr(ws), ws.numel(), ptr(uniq),
+                                       ptr(nu), stream_ptr()), "psb_scatter_sort_rows")
+
+
+def scatter_reduce_sorted(contribs, table_rows, d, drop_idx, ws, uniq, nu, dense_grad=None, dense_bias_grad=None,
+                          want_rows=False, want_bias=False):
+    """Reduce phase over a workspace psb_scatter_sort_rows has filled for the same index lists in the same order."""
+    n_total = sum(int(c.n) for c, _ in contribs)
+    arr = (Contrib * len(contribs))(*[c for c, _ in contribs])
+    dev = uniq.device
+    cap = max(n_total, 1)
+    red = torch.empty((cap, d), dtype=f32, device=dev) if want_rows else None
+    redb = torch.empty((cap,), dtype=f32, device=dev) if want_bias else None
+    check(load().psb_scatter_reduce_sorted(arr, len(contribs), table_rows, d, int(drop_idx), ptr(ws), ws.numel(),
+                                           ptr(uniq), ptr(red), ptr(redb), ptr(nu), ptr(dense_grad, f32),
+                                           ptr(dense_bias_grad, f32), stream_ptr()), "psb_scatter_reduce_sorted")
+    return red, redb
+
+
+def scatter_workspace_bytes(n_total, table_rows):
+    return int(load().psb_scatter_reduce_workspace_bytes(n_total, table_rows))
+
+
 def zero_rows(rows, n_rows, d, dense=None, dense_bias=None):
     check(load().psb_zero_rows(ptr(rows, i32), ptr(n_rows, i32), rows.numel(), d, ptr(dense, f32),
                                ptr(dense_bias, f32), stream_ptr()), "psb_zero_rows")
@@ -396,5 +423,5 @@ def _profiled(name, fn):
 
 
 for _n in ("catalog_prepare_f16", "table_max_row_sqnorm", "gather_rows", "gather_meanpool", "fs_bwd", "token_weights", "ns_loss", "tem_loss", "tem_loss_finish", "score_rows",
-           "scatter_reduce", "zero_rows", "catalog_topk", "topk_merge", "encoder_fwd", "encoder_bwd"):
+           "scatter_reduce", "scatter_sort", "scatter_reduce_sorted", "zero_rows", "catalog_topk", "topk_merge", "encoder_fwd", "encoder_bwd"):
     globals()[_n] = _profiled(_n, globals()[_n])
