@@ -410,28 +410,131 @@ def bandwidth_regime(peaks, rows=16_000_000, d=128):
     return out
 
 
-def variant3_side_measurement(peaks):
-    """The measured-but-not-yet-default main-pass kernel of the fp16 shortlist (PSB_TC16_EPI=3) next
-    to the default one, each in its own subprocess under a timeout (the knob is read once per process): same seeded
-    1M-item table, lists compared by digest.  Reported as a labelled variant; no other number depends on it."""
-    try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "check_tc16_v2.py"), "--quick", "--variants", "3"],
-                           capture_output=True, text=True, timeout=100)
-        rows_ = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
-        runs = {(j.get("epi"), j.get("m")): j for j in rows_ if "sha" in j}
-        cmp_ = []
-        for j in rows_:
-            if "variant" in j:
-                v3 = runs.get(("3", j["m"]), {})
-                cmp_.append({"m": j["m"], "identical_lists": j["identical"], "default_ms": j["v1_ms"], "variant_ms": j["ms"],
-                             "speedup": j["speedup"], "variant_queries_per_s": j["m"] / (j["ms"] * 1e-3) if j["ms"] else None,
-                             "variant_tflops": v3.get("tflops"),
-                             "variant_frac_of_tensor_peak": v3["tflops"] / peaks["bf16"] if v3.get("tflops") else None})
-        return {"knob": "PSB_TC16_EPI=3 (per-query-tile accumulator hand-off + MMA issue from a converged warp); off by default",
-                "table": "1M x 128, top-100, whole psb_catalog_topk_f16 call", "exit": r.returncode, "runs": cmp_,
-                "errors": [dict(j, error=str(j["error"])[-200:]) for j in rows_ if "error" in j][:2]}
-    except Exception as ex:                                           # noqa: BLE001 -- a side measurement, never fatal
-        return {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:120])}
+def train_16m_regime(peaks, rows=16_000_000, steps=8):
+    """BASELINE configs[4] as a TRAINING step on one GPU: the TEM step of the headline (batch 384, same encoder) with a
+    16M-row item table.  grad_mode rowsparse + the row-sparse lazily caught-up Adam: the step touches ~10k rows and its
+    cost must not depend on the table size; the dense form (the reference's semantics taken literally: dense table
+    gradient + dense Adam sweep, 28 B x 2.05 G parameters per step) is timed next to it on a few steps."""
+    import torch
+    from prodsearch_b200 import synth
+    from prodsearch_b200.graph_step import GraphedTrainStep
+    from prodsearch_b200.item_transformer import ItemTransformerRanker
+    from prodsearch_b200.optimizers import build_optim
+    out = {"table": "%d x 128 fp32 item table (8.2 GB) + Adam moments (16.4 GB), batch 384, dropout 0.1" % rows}
+    V, B = WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
+    args = model_args(WORKLOAD["dropout"])
+    for mode in ("rowsparse", "dense"):
+        try:
+            torch.manual_seed(666)
+            with torch.device("cuda"):          # the 8.2 GB table is created and initialised on the GPU, not on the host
+                model = ItemTransformerRanker(args, "cuda", V, rows, None, word_dists=synth.word_dists(V), grad_mode=mode)
+            optim = build_optim(args, model)
+            model.train()
+            batches = []
+            for it in range(steps + 3):
+                b, _, _ = synth.tem_batch(B, rows, V, seed=900 + it, permute=False)
+                batches.append(argparse.Namespace(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vars(b).items()}))
+            sample = argparse.Namespace(**vars(batches[0]))
+            sample.query_word_idxs = torch.full((B, 12), V - 1, dtype=torch.int64)
+            step = GraphedTrainStep(model, optim, sample, pad_values={"query_word_idxs": V - 1, "u_item_idxs": rows})
+            n = steps if mode == "rowsparse" else 3
+            for it in range(3):
+                step(batches[it])
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for it in range(n):
+                step(batches[3 + it])
+            s1.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(s1) / n
+            out[mode] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "steps": n,
+                         "launches_per_step": step.launches_per_replay}
+            if mode == "dense":
+                nparam = sum(p.numel() for p in model.parameters())
+                out[mode]["adam_sweep_GB"] = nparam * 28 / 1e9
+                out[mode]["note"] = "dominated by the dense Adam / clip-norm sweep and the dense gradient buffer"
+            del step, model, optim
+        except Exception as ex:                                       # noqa: BLE001 -- reported, never fatal
+            out[mode] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}
+        torch.cuda.empty_cache()
+    if "ms_per_step" in out.get("rowsparse", {}) and "ms_per_step" in out.get("dense", {}):
+        out["dense_over_rowsparse"] = out["dense"]["ms_per_step"] / out["rowsparse"]["ms_per_step"]
+    return out
+
+
+def rtm_regime(peaks, steps=5):
+    """BASELINE configs[2]: an RTM (ProductRanker) train step at batch 384, 20 + 30 reviews per sequence, 100 words per
+    review, R = 300k reviews, pv and pvc review encoders with the review-word objective (train_pv) -- forward,
+    backward, gradient sinks, clipped Adam, launched eagerly.  The gather-heavy kernels of the step are reported
+    against the HBM roofline (library profiler: CUDA events around every launch); the encoder over 2304 sequences
+    of 51 tokens is the rest of the step."""
+    import torch
+    from prodsearch_b200 import _lib, synth
+    from prodsearch_b200.optimizers import build_optim
+    from prodsearch_b200.ps_model import ProductRanker
+    V, R, P, U, K, B, Wr, d = 32000, 300_000, 18000, 35000, 5, WORKLOAD["batch_per_gpu"], 100, 128
+    rw = synth.review_words_table(R, V, Wr)
+    out = {"shape": "batch %d, 20 + 30 reviews / sequence, %d words / review, R = %d, V = %d, d = %d, K = %d" % (B, Wr, R, V, d, K)}
+    for enc in ("pv", "pvc"):
+        try:
+            a = model_args(0.0)
+            a.model_name, a.review_encoder_name, a.review_word_limit, a.corrupt_rate = "review_transformer", enc, Wr, 0.9
+            a.fix_emb, a.do_subsample_mask, a.use_user_emb, a.use_item_emb, a.use_seg_emb = False, True, False, False, True
+            torch.manual_seed(666)
+            model = ProductRanker(a, "cuda", V, R, P, U, rw, None, word_dists=synth.word_dists(V))
+            optim = build_optim(a, model)
+            model.train()
+            batch, _ = synth.rtm_batch(B, rw, V, P, U, pvc=(enc == "pvc"), train_pv=True, seed=5)
+            cb = argparse.Namespace(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vars(batch).items()})
+
+            def one():
+                loss = model(cb, train_pv=True)
+                model.zero_grad()
+                loss.backward()
+                optim.step()
+                return loss
+            for _ in range(2):
+                one()
+            sec = timed(one, steps, warmup=1)
+            _lib.profile_enable(True)
+            for _ in range(2):
+                one()
+            kp = _lib.profile_dump()
+            _lib.profile_enable(False)
+            ent = {"ms_per_step": sec * 1e3, "samples_per_s": B / sec}
+            Rc = 50
+            if enc == "pvc":     # PVC: clean + corrupted mean of the positives, mean of the negatives: (2 + K) * B * Rc pools of Wr rows
+                pools = (2 + K) * B * Rc
+                nbytes = pools * (Wr * (d * 4 + 8) + d * 4)
+                k_ = kp.get("meanpool_kernel")
+                if k_:
+                    ms = k_[1] / 2
+                    ent["meanpool_kernel"] = {"ms_per_step": ms, "launches_per_step": k_[0] / 2, "algorithmic_bytes": nbytes,
+                                              "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peaks["hbm"],
+                                              "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                                              "note": "fused gather + masked mean over %d pools of %d word rows (the [N, Wr, d] "
+                                                      "tensors of PVC.py:76-79 / ps_model.py:293-297 never exist); the 32k x "
+                                                      "128 word table is L2-resident, so this is requested bytes/s" % (pools, Wr)}
+            else:                # PV: review rows gathered for positives (B * Rc) and negatives (B * K * Rc)
+                rows_ = B * Rc * (1 + K)
+                nbytes = rows_ * (d * 4 * 2 + 8)
+                k_ = kp.get("gather_rows_kernel")
+                if k_:
+                    ms = k_[1] / 2
+                    ent["gather_rows_kernel"] = {"ms_per_step": ms, "launches_per_step": k_[0] / 2, "algorithmic_bytes": nbytes,
+                                                 "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peaks["hbm"],
+                                                 "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                                                 "note": "review-table row gathers (PV.py:46-48, ps_model.py:281,:290) plus the "
+                                                         "segment-row gathers of the step; 154 MB review table"}
+            top = sorted(kp.items(), key=lambda kv: -kv[1][1])[:6]
+            ent["top_kernels_ms_per_step"] = {k: round(v[1] / 2, 4) for k, v in top}
+            out[enc] = ent
+            del model, optim
+        except Exception as ex:                                       # noqa: BLE001
+            out[enc] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}
+        torch.cuda.empty_cache()
+    return out
 
 
 def guarded(fn, seconds, on_timeout):
@@ -509,20 +612,36 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
     sec = None
     try:
         idx = synth.gather_indices(n, rows, seed=11 + rank, dist="uniform").to(dev)
+        sec_fetch = None
         with torch.no_grad():
-            sec = timer(lambda: table.fetch([idx]), 5, warmup=2)
+            if hasattr(table, "shard"):          # the kernel alone: psb_peer_gather_rows on preallocated buffers
+                buf = torch.empty(n, d, device=dev)
+                lib = _lib.load()
+
+                def kernel_only():
+                    _lib.check(lib.psb_peer_gather_rows(table.shard.ptr_array(), world, rows + 1, d, idx.data_ptr(), n,
+                                                        buf.data_ptr(), None, -1, 0, None, _lib.stream_ptr()),
+                               "psb_peer_gather_rows")
+                sec = timer(kernel_only, 5, warmup=2)
+                sec_fetch = timer(lambda: table.fetch([idx]), 5, warmup=2)
+            else:
+                sec = timer(lambda: table.fetch([idx]), 5, warmup=2)
     except Exception as ex:                                               # noqa: BLE001
         err = "%s: %s" % (type(ex).__name__, str(ex)[:120])
     if agree(err):
         sec = max_over_ranks(sec)
         nbytes = n * (d * 4 * 2 + 8)
+        wire = n * (world - 1) / world * d * 4
         out["peer_gather_rows"] = {
             "ms": sec * 1e3, "rows_per_rank": n, "algorithmic_bytes_per_rank": nbytes,
             "achieved_per_rank": nbytes / sec / GB, "achieved": world * nbytes / sec / GB, "unit": "GB/s",
-            "nvlink_GBps_per_rank": n * (world - 1) / world * d * 4 / sec / GB,
-            "note": "1M uniform global ids per rank fetched from their owners into a local mini table (read + "
-                    "materialised write + int64 id); (G-1)/G of the rows travel over NVLink, so the link (900 GB/s per "
-                    "direction per GPU), not HBM, is the ceiling; includes the id concat / remap of fetch()"}
+            "nvlink_GBps_per_rank": wire / sec / GB, "frac_of_nvlink_peak": wire / sec / GB / 900.0,
+            "fetch_ms": None if sec_fetch is None else max_over_ranks(sec_fetch) * 1e3,
+            "note": "1M uniform global ids per rank read from their owners by psb_peer_gather_rows (128-bit loads from "
+                    "peer memory inside the kernel; read + materialised write + int64 id); (G-1)/G of the rows travel "
+                    "over NVLink, so the link (900 GB/s per direction per GPU), not HBM, is the ceiling.  fetch_ms = "
+                    "PeerShardedTable.fetch around it: id concat, remap list and a fresh 512 MB mini table per call "
+                    "(what round 1 reported as the gather: the allocation, not the link, was the 6-13 ms)"}
     else:
         out["peer_gather_rows"] = {"unavailable": err or "failed on another rank"}
         err = None
@@ -545,16 +664,17 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
         if str(dev).startswith("cuda"):
             torch.cuda.synchronize()
 
+        q_all = torch.empty(world * m_local, d, device=dev)
+        ids_all = torch.empty(world, world * m_local, k, dtype=torch.int64, device=dev)
+        sc_all = torch.empty(world, world * m_local, k, dtype=torch.float32, device=dev)
+
         def ranked():
-            qs = [torch.empty_like(q) for _ in range(world)]
-            dist.all_gather(qs, q)
-            ids, sc = ops.catalog_topk(torch.cat(qs, 0), w, k, n_items=n_local, id_base=rank, id_stride=world,
-                                       mode=mode, prepared=prep)
-            ids_all = [torch.empty_like(ids) for _ in range(world)]
-            sc_all = [torch.empty_like(sc) for _ in range(world)]
-            dist.all_gather(ids_all, ids)
-            dist.all_gather(sc_all, sc)
-            return ops.topk_merge(torch.stack(ids_all), torch.stack(sc_all))
+            # three collectives straight into their final layouts (no list gathers, no cat / stack copies)
+            dist.all_gather_into_tensor(q_all, q)
+            ids, sc = ops.catalog_topk(q_all, w, k, n_items=n_local, id_base=rank, id_stride=world, mode=mode, prepared=prep)
+            dist.all_gather_into_tensor(ids_all.view(-1, k), ids)
+            dist.all_gather_into_tensor(sc_all.view(-1, k), sc)
+            return ops.topk_merge(ids_all, sc_all)
     except Exception as ex:                                               # noqa: BLE001
         err = "%s: %s" % (type(ex).__name__, str(ex)[:120])
     if agree(err):
@@ -573,7 +693,105 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
                     "peak = measured bf16 cuBLAS burst (half of it in tf32 mode) x ranks"}
     else:
         out["catalog_topk_16M"] = {"unavailable": err or "failed on another rank"}
+        err = None
+    # ---- (3) the TEM training step on the 16M-row item table, row-sharded over the ranks (peer-memory fetch / fold,
+    #      one CUDA graph per rank) -- BASELINE configs[4] as a training step
+    if pg is None or not str(dev).startswith("cuda"):
+        return out
+    del table
+    torch.cuda.empty_cache()
+    sync()
+    step = None
+    try:
+        from prodsearch_b200.graph_step import GraphedTrainStep
+        from prodsearch_b200.item_transformer import PeerShardedItemTransformerRanker
+        from prodsearch_b200.optimizers import build_optim
+        V, B = WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
+        args = model_args(WORKLOAD["dropout"])
+        torch.manual_seed(666)
+        with torch.device("cuda"):
+            model = PeerShardedItemTransformerRanker(args, "cuda", V, rows, None, word_dists=synth.word_dists(V), peer=pg)
+        optim = build_optim(args, model)
+        model.train()
+        torch.manual_seed(666 + 7919 * rank)
+        batches = []
+        for it in range(8):
+            b, _, _ = synth.tem_batch(B, rows, V, seed=700 + 100 * rank + it, permute=False)
+            batches.append(argparse.Namespace(**{k_: (v.cuda() if torch.is_tensor(v) else v) for k_, v in vars(b).items()}))
+        sample = argparse.Namespace(**vars(batches[0]))
+        sample.query_word_idxs = torch.full((B, 12), V - 1, dtype=torch.int64)
+        step = GraphedTrainStep(model, optim, sample, pad_values={"query_word_idxs": V - 1, "u_item_idxs": rows},
+                                sync_grads=lambda: model.sync_grads(optim))
+    except Exception as ex:                                               # noqa: BLE001
+        err = "%s: %s" % (type(ex).__name__, str(ex)[:160])
+    if agree(err):
+        for it in range(3):
+            step(batches[it])
+        sync()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for it in range(5):
+            step(batches[3 + it])
+        s1.record()
+        torch.cuda.synchronize()
+        sec = max_over_ranks(s0.elapsed_time(s1) / 5 * 1e-3)
+        shard_params = (rows // world) * d
+        out["train_step_16M"] = {
+            "ms_per_step": sec * 1e3, "samples_per_s": B * world / sec, "batch_per_gpu": B,
+            "launches_per_step": step.launches_per_replay,
+            "dense_adam_sweep_GB_per_rank": shard_params * 28 / 1e9,
+            "note": "TEM step of the headline (batch 384 / GPU, dropout 0.1) with the 16M x 128 item table row-sharded "
+                    "over the ranks: peer-memory fetch of the rows the batch needs, compact gradient lists folded by "
+                    "their owners, one-shot all-reduce of the replicated gradients, global clip norm, Adam -- one CUDA "
+                    "graph per rank.  The owner-side optimizer is still the DENSE sweep over the shard (28 B x rows / G x "
+                    "128 per step): the row-sparse lazily caught-up Adam of the single-GPU path (extra.train_16M at N = 1) "
+                    "is not wired into the sharded fold yet"}
+        try:
+            pg.check_errors()
+        except Exception as ex:                                           # noqa: BLE001
+            out["train_step_16M"]["peer_error"] = str(ex)[:120]
+    else:
+        out["train_step_16M"] = {"unavailable": err or "failed on another rank"}
     return out
+
+
+def summarize_regimes(line):
+    """Compact per-kernel fractions inside ``roofline`` (the key the driver keeps): the bandwidth-regime kernels G1-G5
+    on the 16M-row table, the 16M-row training step and the RTM step, next to the dominant kernel of the headline
+    step."""
+    rf = line.get("roofline")
+    ex = line.get("extra") or {}
+    if rf is None:
+        return
+    bw = ex.get("bandwidth_regime") or {}
+    tab = {}
+    for k in ("G1_gather_rows", "G4_gather_meanpool", "G3_ns_loss", "G2_scatter_reduce", "G2_scatter_reduce_zipf"):
+        if isinstance(bw.get(k), dict) and "frac" in bw[k]:
+            tab[k] = {"frac_of_hbm_peak": round(bw[k]["frac"], 3), "GBps": round(bw[k]["achieved"], 0)}
+    c1 = bw.get("G5_catalog_topk_1M") or {}
+    for k in ("tcgen05_f16_m384", "tcgen05_f16_m4096", "tcgen05_tf32_m24"):
+        if isinstance(c1.get(k), dict) and "ms" in c1[k]:
+            tab["G5_1M_" + k] = {"ms": round(c1[k]["ms"], 3), "frac_of_tensor_peak": round(c1[k].get("frac_of_tensor_peak", 0.0), 3),
+                                 "frac_of_hbm_peak": round(c1[k].get("frac_of_hbm_peak", 0.0), 3)}
+    c16 = bw.get("G5_catalog_topk_16M") or {}
+    if "ms" in c16:
+        tab["G5_16M_m4096"] = {"ms": round(c16["ms"], 2), "tflops": round(c16["tflops"], 0),
+                               "frac_of_tensor_peak": round(c16["frac_of_tensor_peak"], 3)}
+    t16 = ex.get("train_16M") or {}
+    for m in ("rowsparse", "dense"):
+        if isinstance(t16.get(m), dict) and "ms_per_step" in t16[m]:
+            tab["train_16M_" + m] = {"ms_per_step": round(t16[m]["ms_per_step"], 3)}
+    rtm = ex.get("rtm_configs2") or {}
+    for enc in ("pv", "pvc"):
+        if isinstance(rtm.get(enc), dict) and "ms_per_step" in rtm[enc]:
+            e = {"ms_per_step": round(rtm[enc]["ms_per_step"], 3)}
+            for kk in ("meanpool_kernel", "gather_rows_kernel"):
+                if kk in rtm[enc]:
+                    e[kk + "_frac_of_hbm_peak"] = round(rtm[enc][kk]["frac"], 3)
+            tab["rtm_" + enc] = e
+    rf["regimes"] = tab
+    rf["regimes_note"] = ("bandwidth regime = 16M x 128 fp32 table (8.2 GB >> L2); fractions of the measured peaks "
+                          "(MEASURED_PEAKS.json); full entries under extra")
 
 
 def run_b200_arm(a):
@@ -873,12 +1091,16 @@ def run_b200_arm(a):
                              "table": "16M x 128 fp32 (8.2 GB), inputs >> L2, no flush needed"}
         except Exception as ex:                                       # noqa: BLE001 -- the headline line must appear
             line["extra"] = {"bandwidth_regime": {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}}
-        if not a.no_variants:
-            # a side measurement in subprocesses, after everything else is final, under its own watchdog
-            def give_up_v3():
-                line["extra"]["G5_catalog_topk_1M_variant3"] = {"unavailable": "no result after 110 s (watchdog)"}
+        summarize_regimes(line)
+        for key, fn in (("train_16M", train_16m_regime), ("rtm_configs2", rtm_regime)):
+            def give_up_x(key=key):
+                line["extra"][key] = {"unavailable": "no result after %d s (watchdog)" % a.extra_timeout}
                 print(json.dumps(line))
-            line["extra"]["G5_catalog_topk_1M_variant3"] = guarded(lambda: variant3_side_measurement(peaks), 110, give_up_v3)
+            try:
+                line["extra"][key] = guarded(lambda fn=fn: fn(peaks), a.extra_timeout, give_up_x)
+            except Exception as ex:                                   # noqa: BLE001
+                line["extra"][key] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:160])}
+        summarize_regimes(line)
     if do_sharded:
         # everything above is final; the 16M-row section runs last, under a watchdog that prints the line without it
         def give_up():
@@ -913,8 +1135,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-extra", action="store_true", help="skip the 16M-row bandwidth-regime section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-variants", action="store_true", dest="no_variants",
-                    help="skip the side measurement of the off-by-default fp16 shortlist variant (subprocesses, ~20 s)")
+    ap.add_argument("--no-variants", action="store_true", dest="no_variants", help="accepted and ignored (round-1 flag)")
     ap.add_argument("--extra-timeout", type=int, default=120, dest="extra_timeout",
                     help="seconds the 16M-row section (extra) may take before the line is printed without it")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl"],

@@ -10,6 +10,7 @@
 //                      adds them in rank order (bit-identical result on every rank)
 //   peer_barrier       cross-GPU barrier on flag words in peer memory (release/acquire at system scope),
 //                      with a clock64 time-out that raises a device error flag instead of hanging
+#include <stdlib.h>
 #include <string.h>
 
 #include "psb_common.cuh"
@@ -67,7 +68,24 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerPtrs flags, int ra
   }
 }
 
-template <int R>
+// How a row that lives in a PEER's memory is loaded (PSB_PEER_LD, read once; profiles/peer_bw.py measures them):
+//   0  ld.global.nc.L1::no_allocate.v4   (the local-gather path: non-coherent / texture path)
+//   1  ld.global.v4                      (plain coherent load)
+//   2  ld.global.relaxed.sys.v4          (system-scope load)
+template <int MODE>
+__device__ __forceinline__ float4 ld_peer4(const float4* p) {
+  float4 v;
+  if (MODE == 0) {
+    v = ldg_row4(p);
+  } else if (MODE == 1) {
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  } else {
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  }
+  return v;
+}
+
+template <int R, int MODE>
 __global__ void __launch_bounds__(256)
 peer_gather_rows_kernel(PeerPtrs shards, int G, int64_t rows_total, int d4, const int64_t* __restrict__ idx, int64_t n,
                         float4* __restrict__ out, int64_t* __restrict__ remap, int64_t pad_id, int64_t pad_pos,
@@ -90,14 +108,17 @@ peer_gather_rows_kernel(PeerPtrs shards, int G, int64_t rows_total, int d4, cons
           // a pad entry is read at pad_pos, never at its own position: do not fetch the pad row thousands of
           // times from its one owner (same-address peer reads serialise on that GPU's memory system)
         } else {
-          src[i] = static_cast<const float4*>(shards.p[v % G]) + (v / G) * d4;
+          // ids fit 31 bits (rows_total < 2^31 is checked on the host): 32-bit divide instead of the 64-bit routine
+          const uint32_t u = static_cast<uint32_t>(v), g = static_cast<uint32_t>(G);
+          const uint32_t q = u / g;
+          src[i] = static_cast<const float4*>(shards.p[u - q * g]) + static_cast<int64_t>(q) * d4;
         }
       }
     }
     for (int c = lane; c < d4; c += 32) {
       float4 v[R];
 #pragma unroll
-      for (int i = 0; i < R; ++i) v[i] = src[i] != nullptr ? ldg_row4(src[i] + c) : zero4();
+      for (int i = 0; i < R; ++i) v[i] = src[i] != nullptr ? ld_peer4<MODE>(src[i] + c) : zero4();
 #pragma unroll
       for (int i = 0; i < R; ++i)
         if (base + i < n) stg4(out + (base + i) * d4 + c, v[i]);
@@ -345,11 +366,26 @@ extern "C" int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_
   if (misaligned16(out)) return PSB_E_ALIGN;
   if (n == 0) return PSB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  constexpr int R = 8;
+  if (rows_total >= (1ll << 31)) return PSB_E_DIM;
+  static int mode = -1, rows_in_flight = -1;
+  if (mode < 0) {
+    const char* e = getenv("PSB_PEER_LD");
+    const int x = e != nullptr ? atoi(e) : 0;
+    mode = (x >= 0 && x <= 2) ? x : 0;
+    e = getenv("PSB_PEER_ROWS");
+    rows_in_flight = (e != nullptr && atoi(e) == 16) ? 16 : 8;
+  }
   PSB_PROF("peer_gather_rows_kernel", s);
-  peer_gather_rows_kernel<R><<<grid_for(n, 8 * R), 256, 0, s>>>(S, G, rows_total, static_cast<int>(d / 4), idx, n,
-                                                                reinterpret_cast<float4*>(out), remap_out, pad_id, pad_pos,
-                                                                err_flag);
+#define PSB_PG_LAUNCH(R, M)                                                                                      \
+  peer_gather_rows_kernel<R, M><<<grid_for(n, 8 * R), 256, 0, s>>>(S, G, rows_total, static_cast<int>(d / 4), idx, n, \
+                                                                   reinterpret_cast<float4*>(out), remap_out, pad_id,  \
+                                                                   pad_pos, err_flag)
+  if (rows_in_flight == 16) {
+    if (mode == 0) PSB_PG_LAUNCH(16, 0); else if (mode == 1) PSB_PG_LAUNCH(16, 1); else PSB_PG_LAUNCH(16, 2);
+  } else {
+    if (mode == 0) PSB_PG_LAUNCH(8, 0); else if (mode == 1) PSB_PG_LAUNCH(8, 1); else PSB_PG_LAUNCH(8, 2);
+  }
+#undef PSB_PG_LAUNCH
   return launch_status();
 }
 

@@ -496,6 +496,16 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         out = self.transformer_encoder.encode_position(first=q_emb.contiguous(), table=items, idx=hist, sink=isink,
                                                        pad_idx=item_pad, use_pos=self.args.use_pos_emb,
                                                        out_pos=out_pos, copies=copies, first_ready=self._q_ready)
+        pos_weight = float(K) if self.args.pos_weight else 1.0
+        if stochastic and self.fused_loss_tail and K <= 7 and self.embedding_size <= 128:
+            # ranking loss on the encoder's output block in place + loss combination: two launches (see the base class)
+            cur.wait_stream(self._iw_stream)
+            if self._ps_acc is None:
+                self._ps_acc = torch.zeros((), device=out.device)
+                self._item_acc = torch.zeros((), device=out.device)
+            return F_.tem_tail(out.view(B, 1 + K, -1), il, items, tgt, neg, isink, pos_weight=pos_weight,
+                               acc_ps=self._ps_acc, acc_il=self._item_acc,
+                               src_rows=self._tail_src_rows(B, K, out.device))
         if stochastic:
             out = out.view(B, 1 + K, -1)
             pos_out = out[:, 0].contiguous()
@@ -503,7 +513,6 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         else:
             pos_out = out
             neg_out = pos_out.unsqueeze(1).expand(-1, K, -1).reshape(B * K, -1)
-        pos_weight = float(K) if self.args.pos_weight else 1.0
         ps = F_.ns_loss(pos_out.contiguous(), items, tgt.view(B, 1), neg.view(B, 1, K), isink,
                         anchor_b=neg_out.contiguous(), pos_weight=pos_weight)
         ps_loss = ps.mean()
@@ -607,21 +616,23 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             n_local = max(0, (self.prod_pad_idx - r + G - 1) // G)
             if G == 1:
                 return self._shard_topk(q, k, n_local, 0, 1, mode)
+            # every collective lands in its final layout (all_gather_into_tensor): no list gathers, no cat / stack
             m = torch.tensor([q.shape[0]], device=q.device)
-            ms = [torch.empty_like(m) for _ in range(G)]
-            dist.all_gather(ms, m, group=self.peer.group)
-            m_all = [int(x) for x in ms]
-            m_max = max(m_all)
-            q_pad = q.new_zeros((m_max, q.shape[1]))
-            q_pad[:q.shape[0]] = q
-            qs = [torch.empty_like(q_pad) for _ in range(G)]
-            dist.all_gather(qs, q_pad, group=self.peer.group)
-            ids, sc = self._shard_topk(torch.cat(qs, 0), k, n_local, r, G, mode)
-            ids_all = [torch.empty_like(ids) for _ in range(G)]
-            sc_all = [torch.empty_like(sc) for _ in range(G)]
-            dist.all_gather(ids_all, ids, group=self.peer.group)
-            dist.all_gather(sc_all, sc, group=self.peer.group)
-            mi, ms_ = ops.topk_merge(torch.stack(ids_all), torch.stack(sc_all))
+            ms = torch.empty(G, dtype=m.dtype, device=q.device)
+            dist.all_gather_into_tensor(ms, m, group=self.peer.group)
+            m_max = int(ms.max())
+            q_pad = q
+            if q.shape[0] != m_max:
+                q_pad = q.new_zeros((m_max, q.shape[1]))
+                q_pad[:q.shape[0]] = q
+            q_all = torch.empty((G * m_max, q.shape[1]), dtype=q.dtype, device=q.device)
+            dist.all_gather_into_tensor(q_all, q_pad, group=self.peer.group)
+            ids, sc = self._shard_topk(q_all, k, n_local, r, G, mode)
+            ids_all = torch.empty((G, G * m_max, k), dtype=ids.dtype, device=q.device)
+            sc_all = torch.empty((G, G * m_max, k), dtype=sc.dtype, device=q.device)
+            dist.all_gather_into_tensor(ids_all.view(-1, k), ids, group=self.peer.group)
+            dist.all_gather_into_tensor(sc_all.view(-1, k), sc, group=self.peer.group)
+            mi, ms_ = ops.topk_merge(ids_all, sc_all)
             lo = r * m_max
             return mi[lo:lo + q.shape[0]], ms_[lo:lo + q.shape[0]]
 

@@ -95,23 +95,18 @@ def test_cpu_reference_others_shape_of_the_entry():
         assert out[key]["unit"] == unit and out[key]["value"] > 0 and out[key]["sample"], key
 
 
-def test_variant_side_measurement_parses_the_check_scripts_lines(monkeypatch):
-    """extra.G5_catalog_topk_1M_variant3: the bench runs profiles/check_tc16_v2.py in a subprocess and folds its JSON
-    lines (per-run lines with a digest, per-(M, variant) comparison lines) into one labelled entry."""
+def test_summarize_regimes_puts_the_fractions_under_roofline():
+    """The compact per-kernel table lives under ``roofline`` (the key the driver keeps), built from extra.*."""
     b = _bench_module()
-    fake = "\n".join([
-        json.dumps({"n_items": 1000000, "m": 384, "epi": "1", "max_mt": 4, "ms": 0.34, "tflops": 290.0, "sha": "aa"}),
-        json.dumps({"n_items": 1000000, "m": 384, "epi": "3", "max_mt": 4, "ms": 0.30, "tflops": 329.0, "sha": "aa"}),
-        json.dumps({"n_items": 1000000, "m": 384, "variant": "3/4", "identical": True, "v1_ms": 0.34, "ms": 0.30, "speedup": 1.133}),
-        "VERDICT: every variant returns v1's lists bit for bit"])
-
-    class R(object):
-        returncode, stdout, stderr = 0, fake, ""
-    monkeypatch.setattr(b.subprocess, "run", lambda *a_, **k_: R())
-    out = b.variant3_side_measurement({"bf16": 1645.0})
-    assert out["exit"] == 0 and out["errors"] == []
-    (run,) = out["runs"]
-    assert run["identical_lists"] is True and run["m"] == 384 and run["variant_tflops"] == 329.0
-    assert abs(run["variant_queries_per_s"] - 384 / 0.30e-3) < 1e-6 and abs(run["variant_frac_of_tensor_peak"] - 0.2) < 1e-9
-    monkeypatch.setattr(b.subprocess, "run", lambda *a_, **k_: (_ for _ in ()).throw(OSError("no such file")))
-    assert "unavailable" in b.variant3_side_measurement({"bf16": 1645.0})
+    line = {"roofline": {"kernel": "tail_bwd_kernel"}, "extra": {
+        "bandwidth_regime": {"G1_gather_rows": {"frac": 0.94, "achieved": 6166.0},
+                             "G5_catalog_topk_1M": {"tcgen05_f16_m384": {"ms": 0.3, "frac_of_tensor_peak": 0.2, "frac_of_hbm_peak": 0.1}},
+                             "G5_catalog_topk_16M": {"ms": 16.3, "tflops": 1027.0, "frac_of_tensor_peak": 0.61}},
+        "train_16M": {"rowsparse": {"ms_per_step": 0.4}, "dense": {"unavailable": "x"}},
+        "rtm_configs2": {"pvc": {"ms_per_step": 9.0, "meanpool_kernel": {"frac": 0.8}}}}}
+    b.summarize_regimes(line)
+    tab = line["roofline"]["regimes"]
+    assert tab["G1_gather_rows"]["frac_of_hbm_peak"] == 0.94 and tab["G5_16M_m4096"]["frac_of_tensor_peak"] == 0.61
+    assert tab["train_16M_rowsparse"]["ms_per_step"] == 0.4 and "train_16M_dense" not in tab
+    assert tab["rtm_pvc"]["meanpool_kernel_frac_of_hbm_peak"] == 0.8
+    b.summarize_regimes({"roofline": None, "extra": None})          # nothing to do, nothing raised
