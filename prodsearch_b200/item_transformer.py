@@ -23,6 +23,13 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
     overlap_query_pooling = True     # query pooling on a side stream under the encoder's plan / transpose kernels
     overlap_item_to_words = True     # item -> word loss kernels on a side stream next to the encoder
     fused_loss_tail = True           # training under dropout: ranking loss on the encoder's output block in place
+    # Item negatives (item_transformer.py:447: torch.multinomial(ones(P), B * K, replacement=True)).  "multinomial" is
+    # that literal call -- bit-identical ids on the same device generator (tests/test_gpu_parity_r2.py).  Its cost is
+    # O(P) per draw: ATen renormalises the distribution with ONE thread block and rebuilds the CDF every call --
+    # 15 us at P = 18k, ~10 ms at P = 16M, measured (profiles/r02k_bench.json: the whole 16M-row step was 10.9 ms
+    # with it).  "randint": torch.randint(0, P) -- the same uniform distribution, O(1), a different random stream;
+    # for catalogs where the literal call is the bottleneck.
+    item_negative_sampler = "multinomial"
 
     def __init__(self, args, device, vocab_size, product_size, vocab_words, word_dists=None,
                  grad_mode="dense"):
@@ -148,7 +155,10 @@ class ItemTransformerRanker(F_.LazyFlushMixin, nn.Module):
             neg_items, neg_words = self.injected_negatives
             return neg_items.view(B, K), neg_words.view(B, W, K)
         # items first, then words: the reference's call order (item_transformer.py:447, :268)
-        neg_items = torch.multinomial(self.prod_dists, B * K, replacement=True).view(B, K)
+        if self.item_negative_sampler == "randint":
+            neg_items = torch.randint(0, self.prod_pad_idx, (B, K), device=self.prod_dists.device)
+        else:
+            neg_items = torch.multinomial(self.prod_dists, B * K, replacement=True).view(B, K)
         neg_words = torch.multinomial(self.word_dists, B * W * K, replacement=True).view(B, W, K)
         return neg_items, neg_words
 
