@@ -102,7 +102,13 @@ class PeerGroup(object):
 
     # ---- allocation (collective: every rank calls alloc in the same order with the same size) -------------
     def alloc(self, nbytes):
-        nbytes = (int(nbytes) + 255) // 256 * 256
+        # Sizes are rounded up to whole 2 MiB pages.  Measured on B200 / NVLink 5 (profiles/r02n_alloc_probe.jsonl): a
+        # 4 GB cudaMalloc whose size is NOT a multiple of 64 KiB is mapped into the peers (CUDA IPC) with small pages
+        # and 128-bit row loads from it run at 40 GB/s instead of 630 GB/s -- the "PCIe-class" peer gather of round 1
+        # was this, not the kernel and not the link (same kernel, same ids: 6.34 ms vs 0.42 ms per 1M rows).
+        nbytes = int(nbytes)
+        gran = (2 << 20) if nbytes >= (1 << 20) else 256
+        nbytes = (nbytes + gran - 1) // gran * gran
         out = c_vp()
         with torch.cuda.device(self.device):
             check(load().psb_peer_alloc(nbytes, ctypes.byref(out)), "psb_peer_alloc")

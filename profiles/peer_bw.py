@@ -68,6 +68,29 @@ def main():
     for name, ids in cases.items():
         sec = timed(lambda: gather(ids))
         res["gather_" + name] = {"ms": round(sec * 1e3, 3), "GBps_rows_per_gpu": round(rb / sec / 1e9, 1)}
+    # the bench's own construction: PeerShardedTable + host-generated uniform ids (profiles/r02l: 6.4 ms there)
+    from prodsearch_b200 import synth
+    from prodsearch_b200.peer import PeerShardedTable
+    table = PeerShardedTable(rows + 1, d, pg, pad_idx=rows)
+    with torch.no_grad():
+        table.weight.normal_()
+    table.weight.requires_grad_(False)
+    idx = synth.gather_indices(n, rows, seed=11 + rank, dist="uniform").cuda()
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    def kernel_only(ids_, tab):
+        check(load().psb_peer_gather_rows(tab.ptr_array(), world, rows + 1, d, ids_.data_ptr(), n, out.data_ptr(), None, -1, 0,
+                                          None, stream_ptr()), "psb_peer_gather_rows")
+    for name, ids_, tab in (("bench_table_bench_ids", idx, table.shard), ("bench_table_randint_ids", cases["random_mixed"], table.shard),
+                            ("diag_shard_bench_ids", idx, shard)):
+        sec = timed(lambda: kernel_only(ids_, tab))
+        res["kernel_" + name] = {"ms": round(sec * 1e3, 3)}
+    res["ids_stats"] = {"bench_unique": int(torch.unique(idx).numel()), "bench_max": int(idx.max()),
+                        "randint_unique": int(torch.unique(cases["random_mixed"]).numel())}
+    with torch.no_grad():
+        sec = timed(lambda: table.fetch([idx]))
+    res["fetch_bench_table"] = {"ms": round(sec * 1e3, 3)}
     # (a) copy engine from the peer mapping
     cudart = ctypes.CDLL("libcudart.so")
     src = shard.ptrs[nxt]
