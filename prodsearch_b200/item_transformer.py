@@ -467,9 +467,7 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         B, _ = u_item_idxs.shape
         K = self.args.neg_per_pos
         W = pos_iword_idxs.shape[1]
-        neg_item_idxs, neg_word_idxs = self._draw_negatives(B, W, K)
-        if neg_word_idxs is None:
-            neg_word_idxs = torch.multinomial(self.word_dists, B * W * K, replacement=True).view(B, W, K)
+        neg_item_idxs, neg_word_idxs = self._negatives_for_step(B, W, K)
         L = u_item_idxs.shape[1]
         self.item_table.reserve_stage(2 * B * (L + 2 + K))                       # collective on first use only
         self.word_table.reserve_stage(2 * B * (query_word_idxs.shape[1] + W * (1 + K)))
@@ -513,9 +511,13 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             if self._ps_acc is None:
                 self._ps_acc = torch.zeros((), device=out.device)
                 self._item_acc = torch.zeros((), device=out.device)
-            return F_.tem_tail(out.view(B, 1 + K, -1), il, items, tgt, neg, isink, pos_weight=pos_weight,
+            self._join_negative_prefetch(cur)
+            loss = F_.tem_tail(out.view(B, 1 + K, -1), il, items, tgt, neg, isink, pos_weight=pos_weight,
                                acc_ps=self._ps_acc, acc_il=self._item_acc,
                                src_rows=self._tail_src_rows(B, K, out.device))
+            F_.RowGradSink.mark_forward_end(out.device)
+            return loss
+        self._join_negative_prefetch(cur)
         if stochastic:
             out = out.view(B, 1 + K, -1)
             pos_out = out[:, 0].contiguous()
@@ -534,7 +536,53 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
                 self._item_acc = torch.zeros((), device=ps_loss.device)
             self._ps_acc.add_(ps_loss.detach())
             self._item_acc.add_(item_loss.detach())
+        F_.RowGradSink.mark_forward_end(ps_loss.device)
         return ps_loss + item_loss
+
+    # The sharded step needs the sampled negatives before anything else (their rows are part of the peer fetch), so the
+    # two torch.multinomial chains (~70 us of serialised kernels) would sit at the head of its critical path.  The
+    # distributions are constant: the draws for step t + 1 are made on a side stream DURING step t (fetch + encoder take
+    # longer) into a second pair of buffers and copied into the live pair at the start of step t + 1.  Same generator,
+    # same draw order (items, words, items, words, ...); each draw is merely issued one step early.
+    prefetch_negatives = True
+
+    def _negatives_for_step(self, B, W, K):
+        if self.injected_negatives is not None or not self.prefetch_negatives or not self.training:
+            self._neg_fork = None
+            ni, nw = self._draw_negatives(B, W, K)
+            return ni, nw
+        dev = self.peer.device
+        key = (B, W, K)
+        if getattr(self, "_neg_key", None) != key:
+            self._neg_key = key
+            self._neg_cur = (torch.empty((B, K), dtype=torch.int64, device=dev),
+                             torch.empty((B, W, K), dtype=torch.int64, device=dev))
+            self._neg_next = (torch.empty_like(self._neg_cur[0]), torch.empty_like(self._neg_cur[1]))
+            self._neg_ready = False
+            self._neg_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        if self._neg_ready:
+            self._neg_cur[0].copy_(self._neg_next[0])
+            self._neg_cur[1].copy_(self._neg_next[1])
+        else:
+            ni, nw = self._draw_negatives(B, W, K)
+            self._neg_cur[0].copy_(ni)
+            self._neg_cur[1].copy_(nw)
+        st = self._neg_stream
+        st.wait_stream(cur)                       # the copies above have read the "next" pair
+        with torch.cuda.stream(st):
+            ni, nw = self._draw_negatives(B, W, K)
+            self._neg_next[0].copy_(ni)
+            self._neg_next[1].copy_(nw)
+        self._neg_ready = True
+        self._neg_fork = st
+        return self._neg_cur
+
+    def _join_negative_prefetch(self, cur):
+        st = getattr(self, "_neg_fork", None)
+        if st is not None:
+            cur.wait_stream(st)
+            self._neg_fork = None
 
     def sync_grads(self, optim=None):
         """Between ``loss.backward()`` and ``optim.step()`` (all ranks): fold the peers' gradient lists into the

@@ -212,13 +212,19 @@ def scatter_sort(idx_list, table_rows, drop_idx, ws, uniq, nu):
 
 
 def scatter_reduce_sorted(contribs, table_rows, d, drop_idx, ws, uniq, nu, dense_grad=None, dense_bias_grad=None,
-                          want_rows=False, want_bias=False):
-    """Reduce phase over a workspace psb_scatter_sort_rows has filled for the same index lists in the same order."""
+                          want_rows=False, want_bias=False, out_red=None):
+    """Reduce phase over a workspace psb_scatter_sort_rows has filled for the same index lists in the same order.
+    out_red: caller-owned row buffer (e.g. the peer-visible staging list) instead of a fresh one."""
     n_total = sum(int(c.n) for c, _ in contribs)
     arr = (Contrib * len(contribs))(*[c for c, _ in contribs])
     dev = uniq.device
     cap = max(n_total, 1)
-    red = torch.empty((cap, d), dtype=f32, device=dev) if want_rows else None
+    if out_red is not None and want_rows:
+        if out_red.shape[0] < cap or out_red.shape[1] != d:
+            raise RuntimeError("scatter_reduce_sorted: out_red too small")
+        red = out_red
+    else:
+        red = torch.empty((cap, d), dtype=f32, device=dev) if want_rows else None
     redb = torch.empty((cap,), dtype=f32, device=dev) if want_bias else None
     check(load().psb_scatter_reduce_sorted(arr, len(contribs), table_rows, d, int(drop_idx), ptr(ws), ws.numel(),
                                            ptr(uniq), ptr(red), ptr(redb), ptr(nu), ptr(dense_grad, f32),

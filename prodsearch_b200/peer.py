@@ -334,6 +334,56 @@ class PeerGradSink(object):
         self.weight = table.weight
         self._stream = None
         self._hold = None
+        self._expected = []           # GLOBAL-id tensors the forward pass announced (see RowGradSink.expect)
+        self._last_seq = 0
+        self._presort = None
+        self._sort_stream = None
+        self._sort_done = None
+        self._sort_ws = None
+        self._exp_event = None
+
+    # ---- sort next to the backward pass (the same scheme as functional.RowGradSink.expect) ----------------------
+    def expect(self, idx):
+        from . import functional as F_
+        if not (F_.RowGradSink.presort and self.weight.requires_grad) or self._expected is None:
+            return
+        g = self._origin.get(idx.data_ptr())
+        if g is None or g.numel() != idx.numel() or len(self._expected) >= _lib.MAX_CONTRIBS:
+            self._expected = None         # an index list the fetch did not hand out: this step sorts in finalize()
+            return
+        self._expected.append(g.reshape(-1))
+        F_.RowGradSink._seq += 1
+        self._last_seq = F_.RowGradSink._seq
+
+    def _launch_presort(self):
+        from . import functional as F_
+        from . import ops
+        exp, t = self._expected, self.table
+        if not exp:
+            return
+        n_total = sum(x.numel() for x in exp)
+        if n_total > t._cap:
+            return
+        dev = self.weight.device
+        if self._sort_stream is None:
+            self._sort_stream = torch.cuda.Stream(device=dev)
+            self._sort_done = torch.cuda.Event()
+            self._exp_event = torch.cuda.Event()
+        wb = ops.scatter_workspace_bytes(n_total, t.rows)
+        if self._sort_ws is None or self._sort_ws.numel() < wb:
+            self._sort_ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        st = self._sort_stream
+        mark = F_.RowGradSink._fwd_mark.get(dev)
+        if mark is not None and mark[1] >= self._last_seq:
+            st.wait_event(mark[0])
+        else:
+            self._exp_event.record(torch.cuda.current_stream(dev))
+            st.wait_event(self._exp_event)
+        with torch.cuda.stream(st):
+            t.stage_n.zero_()
+            ops.scatter_sort(exp, t.rows, t.pad_idx, self._sort_ws, t.stage_rows, t.stage_n)
+            self._sort_done.record(st)
+        self._presort = dict(exp=exp, ws=self._sort_ws)
 
     def _finalize_callback(self):
         from . import functional as F_
@@ -344,6 +394,7 @@ class PeerGradSink(object):
 
     def begin(self, ids, origin):
         self._ids, self._origin = ids, origin
+        self._expected = []
 
     def add(self, idx, src, src_row=None, src_div=1, scale=None, scale2=None, scale2_div=1, to_bias=False):
         from . import ops
@@ -356,11 +407,16 @@ class PeerGradSink(object):
         if not self._queued:
             self._queued = True
             Variable._execution_engine.queue_callback(self._finalize_callback)
+            if self._expected and self._presort is None:
+                self._launch_presort()
 
     def finalize(self):
         from . import ops
         self._queued = False
         pending, self._pending = self._pending, []
+        ps, self._presort, self._expected = self._presort, None, []
+        if ps is not None:            # join the sort stream whatever happens next
+            torch.cuda.current_stream(self.weight.device).wait_event(self._sort_done)
         if not pending:
             return
         t = self.table
@@ -373,9 +429,23 @@ class PeerGradSink(object):
         want_bias = t.bias is not None and any(c.to_bias for c, _ in pending)
         if want_bias:
             t.bias_grad.zero_()
-        ops.scatter_reduce(pending, t.rows, t.d, t.pad_idx, dense_bias_grad=t.bias_grad if want_bias else None,
-                           want_rows=True, device=t.weight.device, out_uniq=t.stage_rows, out_nu=t.stage_n,
-                           out_red=t.stage_vals)
+        ordered = None
+        if ps is not None and len(pending) == len(ps["exp"]):      # contributions in the order forward announced them
+            left, ordered = list(pending), []
+            for x in ps["exp"]:
+                hit = next((j for j, (c, _) in enumerate(left) if c.idx == x.data_ptr() and int(c.n) == x.numel()), None)
+                if hit is None:
+                    ordered = None
+                    break
+                ordered.append(left.pop(hit))
+        if ordered is not None:
+            ops.scatter_reduce_sorted(ordered, t.rows, t.d, t.pad_idx, ps["ws"], t.stage_rows, t.stage_n,
+                                      dense_bias_grad=t.bias_grad if want_bias else None, want_rows=True,
+                                      out_red=t.stage_vals)
+        else:
+            ops.scatter_reduce(pending, t.rows, t.d, t.pad_idx, dense_bias_grad=t.bias_grad if want_bias else None,
+                               want_rows=True, device=t.weight.device, out_uniq=t.stage_rows, out_nu=t.stage_n,
+                               out_red=t.stage_vals)
         if want_bias:
             t.bias.grad = t.bias_grad
 
