@@ -423,7 +423,8 @@ def train_16m_regime(peaks, rows=16_000_000, steps=8):
     out = {"table": "%d x 128 fp32 item table (8.2 GB) + Adam moments (16.4 GB), batch 384, dropout 0.1" % rows}
     V, B = WORKLOAD["vocab_size"], WORKLOAD["batch_per_gpu"]
     args = model_args(WORKLOAD["dropout"])
-    for mode, a_sampler in (("rowsparse", "randint"), ("rowsparse_multinomial", "multinomial"), ("dense", "randint")):
+    for mode, a_sampler in (("rowsparse", "randint"), ("rowsparse_aged", "randint"), ("rowsparse_multinomial", "multinomial"),
+                            ("dense", "randint")):
         try:
             label, mode = mode, mode.split("_")[0]
             torch.manual_seed(666)
@@ -439,9 +440,24 @@ def train_16m_regime(peaks, rows=16_000_000, steps=8):
             sample = argparse.Namespace(**vars(batches[0]))
             sample.query_word_idxs = torch.full((B, 12), V - 1, dtype=torch.int64)
             step = GraphedTrainStep(model, optim, sample, pad_values={"query_word_idxs": V - 1, "u_item_idxs": rows})
-            n = steps if label == "rowsparse" else 3
+            n = steps if label.startswith("rowsparse") and a_sampler == "randint" else 3
             for it in range(3):
                 step(batches[it])
+            if label == "rowsparse_aged":
+                # steady state of a long run: every row has been updated once, long ago (step 1 of 100 000), so each row a
+                # step touches is replayed over the full catch-up window (264 steps) before it is read
+                opt = optim.optimizer
+                torch.cuda.synchronize()
+                for p_, st_ in opt.state.items():
+                    if "last_step" in st_:
+                        st_["last_step"].fill_(1)
+                        st_["exp_avg"].normal_(0, 1e-3)
+                        st_["exp_avg_sq"].fill_(1e-6)
+                opt._step_dev.fill_(100_000)
+                tau = torch.arange(opt.coef_cap, dtype=torch.float64, device="cuda").clamp_(min=1)
+                b1, b2 = opt.param_groups[0]["betas"]
+                hist = torch.stack([opt.param_groups[0]["lr"] / (1 - b1 ** tau), 1 / torch.sqrt(1 - b2 ** tau)], dim=1)
+                opt._coef_hist.copy_(hist.to(torch.float32).reshape(-1))
             torch.cuda.synchronize()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
@@ -784,7 +800,7 @@ def summarize_regimes(line):
         tab["G5_16M_m4096"] = {"ms": round(c16["ms"], 2), "tflops": round(c16["tflops"], 0),
                                "frac_of_tensor_peak": round(c16["frac_of_tensor_peak"], 3)}
     t16 = ex.get("train_16M") or {}
-    for m in ("rowsparse", "rowsparse_multinomial", "dense"):
+    for m in ("rowsparse", "rowsparse_aged", "rowsparse_multinomial", "dense"):
         if isinstance(t16.get(m), dict) and "ms_per_step" in t16[m]:
             tab["train_16M_" + m] = {"ms_per_step": round(t16[m]["ms_per_step"], 3)}
     rtm = ex.get("rtm_configs2") or {}

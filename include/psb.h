@@ -407,10 +407,10 @@ int psb_grad_sqnorm(const psb_adam_tensor_t* tensors /* host; only g and n are r
 /* Row-sparse Adam for embedding tables (SURVEY.md 8(f) N2 as written: "consume G2's (unique_rows, grad_rows)
  * directly ... lazy per-row step counters").  Replaces, for the tables, the dense sweep of
  * torch.optim.Adam(eps=1e-9) + clip_grad_norm_ (models/optimizers.py:186,:205-243) by work proportional to the rows
- * a step touches, with DENSE-EQUIVALENT results: a row that rests for k steps is replayed when it is next read or
- * updated -- its first min(k, psb_adam_catchup_steps) zero-gradient updates exactly (they shrink like
- * (b1/sqrt(b2))^j and are below 1e-12 of the first one after that), the decay of its moments beyond that in closed
- * form.  weight_decay is not supported here (use psb_adam_step).  The global clip norm is taken over the dense
+ * a step touches, with DENSE-EQUIVALENT results: a row that rests for k steps is brought up to date when it is next read or
+ * updated -- with a zero gradient its moments decay geometrically, so the skipped updates are a series with
+ * independent terms: the first min(k, psb_adam_catchup_steps) are summed with each step's own coefficients (they
+ * shrink like (b1/sqrt(b2))^j and are below 1e-9 of the first one after that), the moments decay in closed form.  weight_decay is not supported here (use psb_adam_step).  The global clip norm is taken over the dense
  * tensors' gradients plus the compact row gradients (all other rows have gradient zero). */
 typedef struct psb_adam_rows {
   float* p;                /* [table_rows, d] the table                                                      */
@@ -430,7 +430,7 @@ typedef struct psb_adam_rows {
 #define PSB_ADAM_MAX_ROW_TABLES 8
 #define PSB_ADAM_MAX_IDX_LISTS 8
 
-/* Steps replayed exactly per catch-up for these betas (264 at 0.9 / 0.999). */
+/* Terms of the catch-up series summed per resting row for these betas (198 at 0.9 / 0.999). */
 int32_t psb_adam_catchup_steps(double beta1, double beta2);
 int64_t psb_adam_sparse_workspace_bytes(const psb_adam_tensor_t* dense /* host */, int32_t n_dense,
                                         const psb_adam_rows_t* tables /* host */, int32_t n_tables);

@@ -176,14 +176,13 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, const Ad
 // Dense Adam updates EVERY row every step, also rows whose gradient is zero: their moments decay (m *= b1, v *= b2)
 // and the parameter keeps moving by -lr_t m_hat / (sqrt(v_hat) + eps).  At 16M rows that sweep is 57 GB per step for
 // ~10k rows with a gradient.  Here a row carries `last_step` (the optimizer step up to which it is current) and is
-// brought up to date only when somebody is about to read or update it:
-//   * the first min(gap, catchup_max) skipped steps are replayed EXACTLY (same fmaf sequence as adam_one with g = 0,
-//     per-step coefficients from the step history table);
-//   * after that the skipped updates are below fp32 resolution of the parameter -- their size falls like
-//     (b1 / sqrt(b2))^k, 1e-12 of the first one after catchup_max = 264 steps at the reference's betas -- and only
-//     the moments still change, in closed form: m *= b1^rest, v *= b2^rest.
-// The result equals the dense sweep within fp32 rounding (tests/test_gpu_sparse_adam.py holds it to the same
-// tolerance as the dense kernel against torch.optim.Adam).  weight_decay must be 0 (a decayed row never rests).
+// brought up to date only when somebody is about to read or update it.  A resting row's moments decay geometrically,
+// so its skipped updates form a series with independent terms (catchup_row): the first min(rest, catchup_max) terms
+// are summed with the per-step coefficients of the history table (they fall like (b1 / sqrt(b2))^j: 1e-9 of the first
+// one after catchup_max = 198 steps at the reference's betas, far below fp32 resolution of the parameter), the
+// moments decay in closed form over the whole rest.  The result equals the dense sweep within fp32 rounding
+// (tests/test_gpu_sparse_adam.py holds it to the same tolerance as the dense kernel against torch.optim.Adam).
+// weight_decay must be 0 (a decayed row never rests).
 struct RowTables {
   psb_adam_rows_t t[PSB_ADAM_MAX_ROW_TABLES];
   int n;
@@ -219,37 +218,32 @@ __device__ __forceinline__ StepCoef load_coef(const AdamHyper& h, const float2* 
   return step_coef(h, tau);
 }
 
-__device__ __forceinline__ void rest_one(float& p, float& m, float& v, float omb1, float b2, float step_size,
-                                         float inv_bc2_sqrt, float eps) {
-  m = fmaf(omb1, 0.f - m, m);                 // adam_one with g = 0
-  v = v * b2;
-  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
-  p = fmaf(-step_size, m / denom, p);
-}
-
+// One resting element over steps from+1 .. from+n: with a zero gradient the moments decay geometrically,
+// m_j = m0 b1^j, v_j = v0 b2^j, so the skipped parameter updates are a series whose terms do not depend on each other:
+//   p -= sum_j  a_j m0 / (b_j sqrt(v0) + eps),   a_j = step_size(from + j) b1^j,   b_j = b2^(j/2) inv_bc2_sqrt(from + j)
+// (a_j, b_j are the same for every element of every row that rests from the same step: one lane forms each).
 // Warp-cooperative: bring row r (and its bias element) from step `from` to step `to` (both counted in completed
-// optimizer steps; from < to), all lanes of the warp active.
+// optimizer steps; from < to), all lanes of the warp active.  The series is summed over the first
+// min(to - from, catchup_max) steps -- its terms fall like (b1 / sqrt(b2))^j --, the moments take their closed-form
+// decay over the whole rest.
 __device__ void catchup_row(const psb_adam_rows_t& t, int64_t r, int64_t from, int64_t to, const AdamHyper& h,
                             const float2* __restrict__ hist, int64_t hist_cap, int catchup_max) {
   const int lane = threadIdx.x & 31;
   const int d4 = static_cast<int>(t.d >> 2);
   const int64_t gap = to - from;
-  const int exact = static_cast<int>(gap < catchup_max ? gap : catchup_max);
-  const int64_t rest = gap - exact;
-  float m_rest = 1.f, v_rest = 1.f;
-  if (rest > 0) {
-    m_rest = static_cast<float>(pow(h.beta1, static_cast<double>(rest)));
-    v_rest = static_cast<float>(pow(h.beta2, static_cast<double>(rest)));
-  }
+  const int nterm = static_cast<int>(gap < catchup_max ? gap : catchup_max);
+  const float m_dec = static_cast<float>(pow(h.beta1, static_cast<double>(gap)));
+  const float v_dec = static_cast<float>(pow(h.beta2, static_cast<double>(gap)));
+  const float l2b1 = log2f(h.b1), hl2b2 = 0.5f * log2f(h.b2);
   float4* p4 = reinterpret_cast<float4*>(t.p + r * t.d);
   float4* m4 = reinterpret_cast<float4*>(t.m + r * t.d);
   float4* v4 = reinterpret_cast<float4*>(t.v + r * t.d);
   const bool has_bias = t.bias_p != nullptr && lane == 0;
-  float bp = 0.f, bm = 0.f, bv = 0.f;
+  float bp = 0.f, bm = 0.f, bs = 0.f, bacc = 0.f;
   if (has_bias) {
     bp = t.bias_p[r];
     bm = t.bias_m[r];
-    bv = t.bias_v[r];
+    bs = sqrtf(t.bias_v[r]);
   }
   for (int c0 = 0; c0 < d4; c0 += 32) {
     const int c = c0 + lane;
@@ -260,40 +254,38 @@ __device__ void catchup_row(const psb_adam_rows_t& t, int64_t r, int64_t from, i
       m = m4[c];
       v = v4[c];
     }
-    for (int j0 = 0; j0 < exact; j0 += 32) {       // 32 steps' coefficients per trip: one per lane, then shuffled
-      const int nj = min(32, exact - j0);
-      StepCoef mine;
-      mine.step_size = 0.f;
-      mine.inv_bc2_sqrt = 1.f;
-      if (lane < nj) mine = load_coef(h, hist, hist_cap, from + 1 + j0 + lane);
+    const float4 s = make_float4(sqrtf(v.x), sqrtf(v.y), sqrtf(v.z), sqrtf(v.w));
+    float4 acc = zero4();
+    for (int j0 = 0; j0 < nterm; j0 += 32) {        // 32 terms' coefficients per trip: one per lane, then shuffled
+      const int nj = min(32, nterm - j0);
+      float a_mine = 0.f, b_mine = 1.f;
+      if (lane < nj) {
+        const float j = static_cast<float>(j0 + lane + 1);
+        const StepCoef sc = load_coef(h, hist, hist_cap, from + j0 + lane + 1);
+        a_mine = sc.step_size * exp2f(j * l2b1);
+        b_mine = sc.inv_bc2_sqrt * exp2f(j * hl2b2);
+      }
+#pragma unroll 4
       for (int j = 0; j < nj; ++j) {
-        const float ss = __shfl_sync(kFull, mine.step_size, j);
-        const float ib = __shfl_sync(kFull, mine.inv_bc2_sqrt, j);
-        rest_one(p.x, m.x, v.x, h.omb1, h.b2, ss, ib, h.eps);
-        rest_one(p.y, m.y, v.y, h.omb1, h.b2, ss, ib, h.eps);
-        rest_one(p.z, m.z, v.z, h.omb1, h.b2, ss, ib, h.eps);
-        rest_one(p.w, m.w, v.w, h.omb1, h.b2, ss, ib, h.eps);
-        if (c0 == 0 && has_bias) rest_one(bp, bm, bv, h.omb1, h.b2, ss, ib, h.eps);
+        const float a = __shfl_sync(kFull, a_mine, j);
+        const float b = __shfl_sync(kFull, b_mine, j);
+        acc.x = fmaf(a, __fdividef(m.x, fmaf(b, s.x, h.eps)), acc.x);
+        acc.y = fmaf(a, __fdividef(m.y, fmaf(b, s.y, h.eps)), acc.y);
+        acc.z = fmaf(a, __fdividef(m.z, fmaf(b, s.z, h.eps)), acc.z);
+        acc.w = fmaf(a, __fdividef(m.w, fmaf(b, s.w, h.eps)), acc.w);
+        if (c0 == 0 && has_bias) bacc = fmaf(a, __fdividef(bm, fmaf(b, bs, h.eps)), bacc);
       }
     }
-    if (rest > 0) {
-      m.x *= m_rest; m.y *= m_rest; m.z *= m_rest; m.w *= m_rest;
-      v.x *= v_rest; v.y *= v_rest; v.z *= v_rest; v.w *= v_rest;
-    }
     if (on) {
-      p4[c] = p;
-      m4[c] = m;
-      v4[c] = v;
+      p4[c] = make_float4(p.x - acc.x, p.y - acc.y, p.z - acc.z, p.w - acc.w);
+      m4[c] = make_float4(m.x * m_dec, m.y * m_dec, m.z * m_dec, m.w * m_dec);
+      v4[c] = make_float4(v.x * v_dec, v.y * v_dec, v.z * v_dec, v.w * v_dec);
     }
   }
   if (has_bias) {
-    if (rest > 0) {
-      bm *= m_rest;
-      bv *= v_rest;
-    }
-    t.bias_p[r] = bp;
-    t.bias_m[r] = bm;
-    t.bias_v[r] = bv;
+    t.bias_p[r] = bp - bacc;
+    t.bias_m[r] = bm * m_dec;
+    t.bias_v[r] = t.bias_v[r] * v_dec;
   }
 }
 
@@ -586,10 +578,11 @@ static int64_t row_norm_blocks(const psb_adam_rows_t* t, int32_t n) {
 }
 
 extern "C" int32_t psb_adam_catchup_steps(double beta1, double beta2) {
-  // skipped updates shrink like (b1 / sqrt(b2))^k: replay them exactly until they are 1e-12 of the first one
+  // skipped updates shrink like (b1 / sqrt(b2))^k: sum them until they are 1e-9 of the first one (what is cut off is
+  // < 1e-8 of ONE update, i.e. ~1e-11 absolute at the reference's learning rate)
   const double r = beta1 / sqrt(beta2);
   if (!(r > 0.0) || r >= 1.0) return 4096;
-  const double k = ceil(log(1e-12) / log(r));
+  const double k = ceil(log(1e-9) / log(r));
   return static_cast<int32_t>(k < 1.0 ? 1.0 : (k > 4096.0 ? 4096.0 : k));
 }
 
