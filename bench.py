@@ -731,7 +731,8 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
         args = model_args(WORKLOAD["dropout"])
         torch.manual_seed(666)
         with torch.device("cuda"):
-            model = PeerShardedItemTransformerRanker(args, "cuda", V, rows, None, word_dists=synth.word_dists(V), peer=pg)
+            model = PeerShardedItemTransformerRanker(args, "cuda", V, rows, None, word_dists=synth.word_dists(V), peer=pg,
+                                                     grad_mode="rowsparse")
         model.item_negative_sampler = "randint"      # the literal multinomial(ones(16M)) draw alone is ~10 ms (see the class)
         optim = build_optim(args, model)
         model.train()
@@ -757,17 +758,15 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
         s1.record()
         torch.cuda.synchronize()
         sec = max_over_ranks(s0.elapsed_time(s1) / 5 * 1e-3)
-        shard_params = (rows // world) * d
         out["train_step_16M"] = {
             "ms_per_step": sec * 1e3, "samples_per_s": B * world / sec, "batch_per_gpu": B,
-            "launches_per_step": step.launches_per_replay,
-            "dense_adam_sweep_GB_per_rank": shard_params * 28 / 1e9,
+            "launches_per_step": step.launches_per_replay, "item_negative_sampler": "randint",
             "note": "TEM step of the headline (batch 384 / GPU, dropout 0.1) with the 16M x 128 item table row-sharded "
-                    "over the ranks: peer-memory fetch of the rows the batch needs, compact gradient lists folded by "
-                    "their owners, one-shot all-reduce of the replicated gradients, global clip norm, Adam -- one CUDA "
-                    "graph per rank.  The owner-side optimizer is still the DENSE sweep over the shard (28 B x rows / G x "
-                    "128 per step): the row-sparse lazily caught-up Adam of the single-GPU path (extra.train_16M at N = 1) "
-                    "is not wired into the sharded fold yet"}
+                    "over the ranks: peer-memory fetch of the rows the batch needs (resting rows brought up to date on "
+                    "the fly by the reader), compact gradient lists folded by their owners, one-shot all-reduce of the "
+                    "replicated gradients, global clip norm, row-sparse Adam on the owned rows the step touched -- one "
+                    "CUDA graph per rank; step cost independent of the table size (the dense owner-side sweep would move "
+                    "%.1f GB per rank and step)" % ((rows // world) * d * 28 / 1e9)}
         try:
             pg.check_errors()
         except Exception as ex:                                           # noqa: BLE001

@@ -425,6 +425,10 @@ typedef struct psb_adam_rows {
   float* bias_m;
   float* bias_v;
   const float* bias_grad;  /* [cap] or NULL (bias present but without gradient this step)                    */
+  int32_t grad_by_row;     /* 0: grad / bias_grad are compact lists (entry i belongs to rows[i]); 1: they are DENSE
+                            * [table_rows, d] / [table_rows] buffers of which only the listed rows are valid (the
+                            * owner-side fold of a row-sharded table writes such a buffer)                        */
+  int32_t reserved;
 } psb_adam_rows_t;
 
 #define PSB_ADAM_MAX_ROW_TABLES 8
@@ -443,6 +447,11 @@ int psb_adam_sparse_step(const psb_adam_tensor_t* dense /* host */, int32_t n_de
                          double beta2, double eps, double max_grad_norm, int32_t noam, double warmup_steps,
                          int32_t norm_given, int64_t* step_dev, float* sqnorm_dev, float* coef_hist, int64_t coef_cap,
                          void* workspace, int64_t workspace_bytes, psb_stream_t stream);
+/* |g|^2 over the dense tensors' gradients plus the row lists of the tables (the first phase of psb_adam_sparse_step on
+ * its own: row-sharded training publishes this partial norm to the peers).  Workspace as for psb_adam_sparse_step. */
+int psb_grad_sqnorm_sparse(const psb_adam_tensor_t* dense /* host; g and n */, int32_t n_dense,
+                           const psb_adam_rows_t* tables /* host */, int32_t n_tables, float* sqnorm_out,
+                           void* workspace, int64_t workspace_bytes, psb_stream_t stream);
 /* Bring rows up to the current step (*step_dev) BEFORE they are read: idx_lists[0..n_lists) are device index arrays
  * (the ones the forward pass is about to gather with), idx_counts their lengths (host); n_lists == 0 catches up every
  * row of the table (before evaluation / a checkpoint).  skip_row: a row that never moves (the pad row) or -1.
@@ -509,6 +518,18 @@ typedef struct psb_fold_table {
   int32_t* n_touched;                  /* device counter for `touched` (caller zeroes it) */
 } psb_fold_table_t;
 
+/* psb_peer_gather_rows for a table whose owners update it with the row-sparse Adam: a row that rests on its owner
+ * (last_step < *step_dev) is brought up to date ON THE FLY by the reader -- it loads the row's moments as well and adds
+ * the catch-up series (psb_adam_rows_catchup's arithmetic) to the value it hands out -- WITHOUT writing anything back:
+ * the owner's copy is only ever written by the owner's own optimizer step (which catches the row up first), so no
+ * cross-GPU write, no lock.  shards_p / _m / _v / _last: G peer pointers each ([local_rows, d] fp32 x3, [local_rows]
+ * int32); step_dev / coef_hist: this rank's step counter and coefficient history (identical on every rank). */
+int psb_peer_gather_rows_lazy(const void* const* shards_p, const void* const* shards_m, const void* const* shards_v,
+                              const void* const* shards_last, int32_t G, int64_t rows_total, int64_t d,
+                              const int64_t* idx, int64_t n, float* out, int64_t* remap_out, int64_t pad_id,
+                              int64_t pad_pos, int32_t* err_flag, double lr, double beta1, double beta2, double eps,
+                              int32_t noam, double warmup_steps, const int64_t* step_dev, const float* coef_hist,
+                              int64_t coef_cap, psb_stream_t stream);
 int psb_peer_fold_lists(const psb_fold_table_t* tables /* host */, int32_t n_tables, int32_t rank, int32_t G,
                         float scale, const uint32_t* stamp_dev, psb_stream_t stream);
 

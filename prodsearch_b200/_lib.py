@@ -52,7 +52,7 @@ class AdamRows(ctypes.Structure):
     """psb_adam_rows_t."""
     _fields_ = [("p", c_vp), ("m", c_vp), ("v", c_vp), ("last_step", c_vp), ("rows", c_vp), ("grad", c_vp),
                 ("n_rows", c_vp), ("cap", c_i64), ("d", c_i64), ("table_rows", c_i64), ("bias_p", c_vp),
-                ("bias_m", c_vp), ("bias_v", c_vp), ("bias_grad", c_vp)]
+                ("bias_m", c_vp), ("bias_v", c_vp), ("bias_grad", c_vp), ("grad_by_row", c_i32), ("reserved", c_i32)]
 
 
 ADAM_MAX_TENSORS = 64
@@ -127,6 +127,11 @@ SIGNATURES = {
     "psb_adam_sparse_step": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamRows), c_i32, c_f64, c_f64,
                                      c_f64, c_f64, c_f64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64,
                                      c_vp]),
+    "psb_grad_sqnorm_sparse": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamRows), c_i32, c_vp, c_vp, c_i64,
+                                       c_vp]),
+    "psb_peer_gather_rows_lazy": (c_i32, [ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                          ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
+                                          c_vp, c_f64, c_f64, c_f64, c_f64, c_i32, c_f64, c_vp, c_vp, c_i64, c_vp]),
     "psb_adam_rows_catchup": (c_i32, [ctypes.POINTER(AdamRows), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i32,
                                       c_i64, c_f64, c_f64, c_f64, c_f64, c_i32, c_f64, c_vp, c_vp, c_i64, c_vp]),
     "psb_peer_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),

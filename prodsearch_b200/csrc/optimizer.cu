@@ -5,6 +5,7 @@
 // No host synchronisation: the step counter, the norm and the clip factor live in device memory, so
 // the whole optimizer step replays inside a CUDA graph.  Deterministic (fixed-order partial sums).
 #include "psb_common.cuh"
+#include "adam_common.cuh"
 
 namespace psb {
 
@@ -81,13 +82,6 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restri
 }
 
 __global__ void bump_step_kernel(int64_t* __restrict__ step) { *step += 1; }
-
-struct AdamHyper {  // the reference's hyper-parameters are Python doubles: 1 - beta is formed in double, then rounded
-  double lr, beta1, beta2;
-  float b1, b2, omb1, omb2, eps, max_norm, weight_decay;
-  int noam;
-  float warmup;
-};
 
 struct AdamCoef {
   float clip, wd, omb1, b2, omb2, step_size, inv_bc2_sqrt, eps;
@@ -187,36 +181,6 @@ struct RowTables {
   psb_adam_rows_t t[PSB_ADAM_MAX_ROW_TABLES];
   int n;
 };
-
-struct StepCoef {
-  float step_size, inv_bc2_sqrt;
-};
-
-__device__ __forceinline__ StepCoef step_coef(const AdamHyper& h, int64_t step) {
-  const double sd = static_cast<double>(step);
-  double lr = h.lr;
-  if (h.noam) lr = h.lr * fmin(1.0 / sqrt(sd), sd * pow(static_cast<double>(h.warmup), -1.5));
-  const double bc1 = 1.0 - pow(h.beta1, sd);
-  const double bc2 = 1.0 - pow(h.beta2, sd);
-  StepCoef c;
-  c.step_size = static_cast<float>(lr / bc1);
-  c.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
-  return c;
-}
-
-// coefficients of step tau: from the history table when it holds them (written by the optimizer step itself),
-// else recomputed (steps beyond the table's capacity)
-__device__ __forceinline__ StepCoef load_coef(const AdamHyper& h, const float2* __restrict__ hist, int64_t cap,
-                                              int64_t tau) {
-  if (hist != nullptr && tau < cap) {
-    const float2 c = hist[tau];
-    StepCoef r;
-    r.step_size = c.x;
-    r.inv_bc2_sqrt = c.y;
-    return r;
-  }
-  return step_coef(h, tau);
-}
 
 // One resting element over steps from+1 .. from+n: with a zero gradient the moments decay geometrically,
 // m_j = m0 b1^j, v_j = v0 b2^j, so the skipped parameter updates are a series whose terms do not depend on each other:
@@ -346,7 +310,7 @@ __global__ void __launch_bounds__(256) sqnorm_rows_partial_kernel(const RowTable
     const psb_adam_rows_t& t = R.t[ti];
     const int64_t n = *t.n_rows;
     const int64_t lo = static_cast<int64_t>(b) * 32, hi = min(n, lo + 32);
-    if (lo < hi) {
+    if (lo < hi && !t.grad_by_row) {
       const float4* g4 = reinterpret_cast<const float4*>(t.grad + lo * t.d);
       const int64_t n4 = (hi - lo) * (t.d >> 2);
       for (int64_t i = threadIdx.x; i < n4; i += 256) {
@@ -356,6 +320,18 @@ __global__ void __launch_bounds__(256) sqnorm_rows_partial_kernel(const RowTable
       if (t.bias_grad != nullptr && threadIdx.x < hi - lo) {
         const float gb = t.bias_grad[lo + threadIdx.x];
         acc = fmaf(gb, gb, acc);
+      }
+    } else if (lo < hi) {              // dense gradient buffer, only the listed rows are valid: one warp per entry
+      const int d4 = static_cast<int>(t.d >> 2);
+      for (int64_t e = lo + (threadIdx.x >> 5); e < hi; e += 8) {
+        const int64_t r = t.rows[e];
+        if (r < 0 || r >= t.table_rows) continue;
+        const float4* g4 = reinterpret_cast<const float4*>(t.grad + r * t.d);
+        for (int c = threadIdx.x & 31; c < d4; c += 32) {
+          const float4 v = g4[c];
+          acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+        if (t.bias_grad != nullptr && (threadIdx.x & 31) == 0) acc = fmaf(t.bias_grad[r], t.bias_grad[r], acc);
       }
     }
   }
@@ -427,7 +403,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(const RowTables R, const
   float4* p4 = reinterpret_cast<float4*>(t.p + r * t.d);
   float4* m4 = reinterpret_cast<float4*>(t.m + r * t.d);
   float4* v4 = reinterpret_cast<float4*>(t.v + r * t.d);
-  const float4* g4 = reinterpret_cast<const float4*>(t.grad + i * t.d);
+  const float4* g4 = reinterpret_cast<const float4*>(t.grad + (t.grad_by_row ? r : i) * t.d);
   for (int k = lane; k < d4; k += 32) {
     float4 p = p4[k], m = m4[k], v = v4[k];
     const float4 g = g4[k];
@@ -441,7 +417,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(const RowTables R, const
   }
   if (lane == 0) {
     if (t.bias_p != nullptr) {
-      const float g = t.bias_grad != nullptr ? t.bias_grad[i] : 0.f;
+      const float g = t.bias_grad != nullptr ? t.bias_grad[t.grad_by_row ? r : i] : 0.f;
       adam_one(t.bias_p[r], g, t.bias_m[r], t.bias_v[r], c);
     }
     t.last_step[r] = static_cast<int>(step);
@@ -555,20 +531,7 @@ static int check_row_table(const psb_adam_rows_t& t, bool need_list) {
 
 static AdamHyper make_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,
                             int32_t noam, double warmup_steps) {
-  AdamHyper h;
-  h.lr = lr;
-  h.beta1 = beta1;
-  h.beta2 = beta2;
-  h.b1 = static_cast<float>(beta1);
-  h.b2 = static_cast<float>(beta2);
-  h.omb1 = static_cast<float>(1.0 - beta1);
-  h.omb2 = static_cast<float>(1.0 - beta2);
-  h.eps = static_cast<float>(eps);
-  h.max_norm = static_cast<float>(max_grad_norm);
-  h.weight_decay = static_cast<float>(weight_decay);
-  h.noam = noam;
-  h.warmup = static_cast<float>(warmup_steps);
-  return h;
+  return make_adam_hyper(lr, beta1, beta2, eps, weight_decay, max_grad_norm, noam, warmup_steps);
 }
 
 static int64_t row_norm_blocks(const psb_adam_rows_t* t, int32_t n) {
@@ -661,6 +624,49 @@ extern "C" int psb_adam_sparse_step(const psb_adam_tensor_t* dense, int32_t n_de
     if ((st = launch_status()) != PSB_OK) return st;
   }
   return PSB_OK;
+}
+
+extern "C" int psb_grad_sqnorm_sparse(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables,
+                                      int32_t n_tables, float* sqnorm_out, void* workspace, int64_t workspace_bytes,
+                                      psb_stream_t stream) {
+  if (n_dense < 0 || n_dense > PSB_ADAM_MAX_TENSORS || n_tables < 0 || n_tables > PSB_ADAM_MAX_ROW_TABLES ||
+      n_dense + n_tables == 0 || sqnorm_out == nullptr || workspace == nullptr || (n_dense > 0 && dense == nullptr) ||
+      (n_tables > 0 && tables == nullptr))
+    return PSB_E_ARG;
+  AdamTensors T;
+  T.n = n_dense;
+  for (int i = 0; i < n_dense; ++i) {
+    if (dense[i].g == nullptr || dense[i].n <= 0) return PSB_E_ARG;
+    T.t[i] = dense[i];
+  }
+  RowTables R;
+  R.n = n_tables;
+  for (int i = 0; i < n_tables; ++i) {
+    if (tables[i].rows == nullptr || tables[i].grad == nullptr || tables[i].n_rows == nullptr || tables[i].cap <= 0 ||
+        tables[i].d <= 0 || (tables[i].d & 3) != 0)
+      return PSB_E_ARG;
+    R.t[i] = tables[i];
+  }
+  const int64_t chunks = adam_chunks(dense, n_dense);
+  const int64_t nblocks = row_norm_blocks(tables, n_tables);
+  if (chunks + nblocks > (1ll << 30)) return PSB_E_DIM;
+  if (workspace_bytes < (chunks + nblocks + 4) * static_cast<int64_t>(sizeof(float))) return PSB_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  int st;
+  if (chunks > 0) {
+    PSB_PROF("sqnorm_partial_kernel", s);
+    sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  if (nblocks > 0) {
+    PSB_PROF("sqnorm_rows_partial_kernel", s);
+    sqnorm_rows_partial_kernel<<<static_cast<int>(nblocks), 256, 0, s>>>(R, partial + chunks);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  PSB_PROF("sqnorm_final_kernel", s);
+  sqnorm_final_kernel<<<1, 256, 0, s>>>(partial, static_cast<int>(chunks + nblocks), sqnorm_out, nullptr);
+  return launch_status();
 }
 
 extern "C" int psb_adam_rows_catchup(const psb_adam_rows_t* table, const int64_t* const* idx_lists,

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "psb_common.cuh"
+#include "adam_common.cuh"
 
 namespace psb {
 
@@ -119,6 +120,78 @@ peer_gather_rows_kernel(PeerPtrs shards, int G, int64_t rows_total, int d4, cons
       float4 v[R];
 #pragma unroll
       for (int i = 0; i < R; ++i) v[i] = src[i] != nullptr ? ld_peer4<MODE>(src[i] + c) : zero4();
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (base + i < n) stg4(out + (base + i) * d4 + c, v[i]);
+    }
+  }
+}
+
+// The same fetch from a table whose owners run the row-sparse Adam (psb_peer_gather_rows_lazy): a row that rests on its
+// owner is handed out as it WOULD be after the dense sweep -- value + catch-up series from the row's moments -- and
+// nothing is written back.  R rows per warp: their last_step words first (one remote 4-byte load each, all in flight),
+// then the value rows; only the resting ones pay the two extra row loads and the series.
+struct LazyShards {
+  const void* p[kMaxPeers];
+  const void* m[kMaxPeers];
+  const void* v[kMaxPeers];
+  const void* last[kMaxPeers];
+};
+
+template <int R>
+__global__ void __launch_bounds__(256)
+peer_gather_rows_lazy_kernel(LazyShards S, int G, int64_t rows_total, int d4, const int64_t* __restrict__ idx, int64_t n,
+                             float4* __restrict__ out, int64_t* __restrict__ remap, int64_t pad_id, int64_t pad_pos,
+                             int32_t* __restrict__ err, const AdamHyper h, const int64_t* __restrict__ step_dev,
+                             const float2* __restrict__ hist, int64_t hist_cap, int catchup_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t cur = *step_dev;
+  for (int64_t base = warp * R; base < n; base += nwarps * R) {
+    int owner[R];
+    int64_t local[R];
+    int last[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int64_t row = base + i;
+      owner[i] = -1;
+      local[i] = 0;
+      last[i] = 0;
+      if (row < n) {
+        const int64_t v = idx[row];
+        if (remap != nullptr && lane == 0) remap[row] = v == pad_id ? pad_pos : row;
+        if (v < 0 || v >= rows_total) {
+          if (err != nullptr && lane == 0) *err = 1;
+        } else if (remap != nullptr && v == pad_id && row != pad_pos) {
+          // pad entries are read once, at pad_pos (see peer_gather_rows_kernel)
+        } else {
+          const uint32_t u = static_cast<uint32_t>(v), g = static_cast<uint32_t>(G);
+          const uint32_t q = u / g;
+          owner[i] = static_cast<int>(u - q * g);
+          local[i] = q;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (owner[i] >= 0) last[i] = static_cast<const int*>(S.last[owner[i]])[local[i]];
+    for (int c = lane; c < d4; c += 32) {          // d <= 128: one trip
+      float4 v[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        v[i] = owner[i] >= 0 ? ld_peer4<0>(static_cast<const float4*>(S.p[owner[i]]) + local[i] * d4 + c) : zero4();
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        if (owner[i] >= 0 && last[i] > 0 && last[i] < cur) {   // warp-uniform: every lane holds the same owner / last
+          const float4 m = ld_peer4<0>(static_cast<const float4*>(S.m[owner[i]]) + local[i] * d4 + c);
+          const float4 vv = ld_peer4<0>(static_cast<const float4*>(S.v[owner[i]]) + local[i] * d4 + c);
+          const int64_t gap = cur - last[i];
+          const float4 dl = catchup_series4(m, vv, last[i], static_cast<int>(gap < catchup_max ? gap : catchup_max), h, hist,
+                                            hist_cap);
+          v[i] = make_float4(v[i].x - dl.x, v[i].y - dl.y, v[i].z - dl.z, v[i].w - dl.w);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < R; ++i)
         if (base + i < n) stg4(out + (base + i) * d4 + c, v[i]);
@@ -386,6 +459,44 @@ extern "C" int psb_peer_gather_rows(const void* const* shards, int32_t G, int64_
     if (mode == 0) PSB_PG_LAUNCH(8, 0); else if (mode == 1) PSB_PG_LAUNCH(8, 1); else PSB_PG_LAUNCH(8, 2);
   }
 #undef PSB_PG_LAUNCH
+  return launch_status();
+}
+
+extern "C" int32_t psb_adam_catchup_steps(double beta1, double beta2);
+
+extern "C" int psb_peer_gather_rows_lazy(const void* const* shards_p, const void* const* shards_m,
+                                         const void* const* shards_v, const void* const* shards_last, int32_t G,
+                                         int64_t rows_total, int64_t d, const int64_t* idx, int64_t n, float* out,
+                                         int64_t* remap_out, int64_t pad_id, int64_t pad_pos, int32_t* err_flag, double lr,
+                                         double beta1, double beta2, double eps, int32_t noam, double warmup_steps,
+                                         const int64_t* step_dev, const float* coef_hist, int64_t coef_cap,
+                                         psb_stream_t stream) {
+  PeerPtrs P, M, V, L;
+  int st;
+  if ((st = fill_ptrs(&P, shards_p, G)) != PSB_OK || (st = fill_ptrs(&M, shards_m, G)) != PSB_OK ||
+      (st = fill_ptrs(&V, shards_v, G)) != PSB_OK || (st = fill_ptrs(&L, shards_last, G)) != PSB_OK)
+    return st;
+  if (idx == nullptr || out == nullptr || n < 0 || rows_total <= 0 || step_dev == nullptr) return PSB_E_ARG;
+  if (d <= 0 || (d & 3) != 0 || d > 128) return PSB_E_DIM;          // the series runs on one float4 per lane
+  if (rows_total >= (1ll << 31)) return PSB_E_DIM;
+  for (int i = 0; i < G; ++i)
+    if (misaligned16(P.p[i]) || misaligned16(M.p[i]) || misaligned16(V.p[i])) return PSB_E_ALIGN;
+  if (misaligned16(out)) return PSB_E_ALIGN;
+  if (n == 0) return PSB_OK;
+  LazyShards S;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    S.p[i] = P.p[i];
+    S.m[i] = M.p[i];
+    S.v[i] = V.p[i];
+    S.last[i] = L.p[i];
+  }
+  const AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, 0.0, 0.0, noam, warmup_steps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  constexpr int R = 8;
+  PSB_PROF("peer_gather_rows_lazy_kernel", s);
+  peer_gather_rows_lazy_kernel<R><<<grid_for(n, 8 * R), 256, 0, s>>>(
+      S, G, rows_total, static_cast<int>(d / 4), idx, n, reinterpret_cast<float4*>(out), remap_out, pad_id, pad_pos,
+      err_flag, h, step_dev, reinterpret_cast<const float2*>(coef_hist), coef_cap, psb_adam_catchup_steps(beta1, beta2));
   return launch_status();
 }
 

@@ -428,7 +428,10 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         d = self.embedding_size
         full_items = self.product_emb.weight.detach()
         full_words = self.word_embeddings.weight.detach()
-        self.item_table = peer_mod.PeerShardedTable(product_size + 1, d, self.peer, self.prod_pad_idx, full=full_items)
+        # grad_mode "rowsparse": the owners update the item shard with the row-sparse Adam (O(rows touched) per step
+        # whatever the catalog size); readers bring resting rows up to date on the fly.  The word table stays dense.
+        self.item_table = peer_mod.PeerShardedTable(product_size + 1, d, self.peer, self.prod_pad_idx, full=full_items,
+                                                    sparse=(grad_mode == "rowsparse"))
         self.word_table = peer_mod.PeerShardedTable(vocab_size, d, self.peer, self.word_pad_idx, full=full_words,
                                                     bias=self.word_bias)
         self.product_emb = nn.Embedding(self.item_table.local_rows, d)
@@ -588,6 +591,12 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         """Between ``loss.backward()`` and ``optim.step()`` (all ranks): fold the peers' gradient lists into the
         owned shards, all-reduce the replicated gradients, hand the GLOBAL clip norm to the optimizer.  Three
         phases separated by peer barriers (the single-process simulation of the tests calls them in lockstep)."""
+        if self.item_table.sparse and optim is not None and self.item_table.lazy_optim is None:
+            opt = getattr(optim, "optimizer", optim)
+            if hasattr(opt, "adopt_state"):
+                it = self.item_table
+                opt.adopt_state(it.weight, it.exp_avg, it.exp_avg_sq, it.last_step)
+                it.lazy_optim = opt
         self.sync_stage()
         self.peer.barrier(1)       # every rank's compact lists and dense bucket are complete
         self.sync_fold()
@@ -614,6 +623,23 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         cur.wait_stream(self._reduce_stream)
         # partial |g|^2 of this rank: its two shard gradients; rank 0 adds the (replicated, identical) dense bucket
         lib = _lib.load()
+        if self.item_table.sparse:
+            # item shard: only the rows this fold wrote count (everything else in the buffer is stale, not zero)
+            it = self.item_table
+            n = 2 if self.peer.rank == 0 else 1
+            arr = (_lib.AdamTensor * 2)(
+                _lib.AdamTensor(None, self.word_table.grad.data_ptr(), None, None, self.word_table.grad.numel()),
+                _lib.AdamTensor(None, self._bucket.red.data_ptr(), None, None, self._bucket.n))
+            R = _lib.AdamRows()
+            R.rows, R.grad, R.n_rows = it._touched.data_ptr(), it.grad.data_ptr(), it._n_touched.data_ptr()
+            R.cap, R.d, R.table_rows, R.grad_by_row = it._touched.numel(), it.d, it.local_rows, 1
+            rows_arr = (_lib.AdamRows * 1)(R)
+            wb = int(lib.psb_adam_sparse_workspace_bytes(arr, n, rows_arr, 1))
+            if self._norm_ws is None or self._norm_ws.numel() < wb:
+                self._norm_ws = torch.empty(wb, dtype=torch.uint8, device=self.peer.device)
+            _lib.check(lib.psb_grad_sqnorm_sparse(arr, n, rows_arr, 1, self._sq_local.data_ptr(), self._norm_ws.data_ptr(),
+                                                  wb, _lib.stream_ptr()), "psb_grad_sqnorm_sparse")
+            return
         n = 3 if self.peer.rank == 0 else 2
         arr = (_lib.AdamTensor * 3)(
             _lib.AdamTensor(None, self.item_table.grad.data_ptr(), None, None, self.item_table.grad.numel()),

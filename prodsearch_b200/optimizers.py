@@ -41,6 +41,14 @@ class FusedAdam(object):
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             self._sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
 
+    def adopt_state(self, p, exp_avg, exp_avg_sq, last_step=None):
+        """Use caller-owned tensors as the optimizer state of ``p`` (row-sharded tables keep their moments and row
+        stamps in peer memory, where the readers of a resting row find them)."""
+        st = dict(exp_avg=exp_avg, exp_avg_sq=exp_avg_sq)
+        if last_step is not None:
+            st["last_step"] = last_step
+        self.state[p] = st
+
     def _state_of(self, p):
         st = self.state.get(p)
         if st is None:
@@ -85,7 +93,10 @@ class FusedAdam(object):
             keep += [sb["exp_avg"], sb["exp_avg_sq"]]
         if lists:
             rows, vals, nu = p.row_grad
-            R.rows, R.grad, R.n_rows, R.cap = rows.data_ptr(), vals.data_ptr(), nu.data_ptr(), min(rows.numel(), vals.shape[0])
+            by_row = bool(getattr(p, "_psb_grad_by_row", False))      # dense buffer indexed by row id (sharded fold)
+            R.rows, R.grad, R.n_rows = rows.data_ptr(), vals.data_ptr(), nu.data_ptr()
+            R.cap = rows.numel() if by_row else min(rows.numel(), vals.shape[0])
+            R.grad_by_row = 1 if by_row else 0
             keep += [rows, vals, nu]
             bg = getattr(bias, "row_grad", None) if bias is not None else None
             if bg is not None:

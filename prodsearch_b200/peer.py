@@ -202,11 +202,22 @@ def try_create(group=None, device=None):
 class PeerShardedTable(object):
     """A [rows, d] fp32 table row-sharded cyclically (owner = id % G, local row = id // G)."""
 
-    def __init__(self, rows, d, peer, pad_idx, full=None, bias=None, stage_cap=0):
+    def __init__(self, rows, d, peer, pad_idx, full=None, bias=None, stage_cap=0, sparse=False):
+        """sparse: the owners update their shard with the row-sparse lazily caught-up Adam (optimizers.FusedAdam): the
+        moments and the per-row step stamps live in peer memory next to the shard, because a reader brings a resting
+        row up to date on the fly (psb_peer_gather_rows_lazy) and needs them."""
         self.rows, self.d, self.peer, self.pad_idx = int(rows), int(d), peer, int(pad_idx)
         G, r = peer.world, peer.rank
         self.local_rows = (self.rows - r + G - 1) // G
-        self.shard = peer.alloc(max((self.rows + G - 1) // G, 1) * d * 4)    # the same size on every rank
+        per = max((self.rows + G - 1) // G, 1)
+        self.shard = peer.alloc(per * d * 4)    # the same size on every rank
+        self.sparse = bool(sparse)
+        self.lazy_optim = None                  # the FusedAdam whose step counter / coefficient history the fetch reads
+        if self.sparse:
+            self._m_buf, self._v_buf, self._last_buf = peer.alloc(per * d * 4), peer.alloc(per * d * 4), peer.alloc(per * 4)
+            self.exp_avg = self._m_buf.view(torch.float32, (self.local_rows, d))
+            self.exp_avg_sq = self._v_buf.view(torch.float32, (self.local_rows, d))
+            self.last_step = self._last_buf.view(torch.int32, (self.local_rows,))
         w = self.shard.view(torch.float32, (self.local_rows, d))
         if full is not None:
             with torch.no_grad():
@@ -264,9 +275,19 @@ class PeerShardedTable(object):
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
-            check(load().psb_peer_gather_rows(self.shard.ptr_array(), self.peer.world, self.rows, self.d,
-                                              ids.data_ptr(), n + 1, mini.data_ptr(), remap.data_ptr(), self.pad_idx, n,
-                                              None, stream_ptr()), "psb_peer_gather_rows")
+            opt = self.lazy_optim
+            if self.sparse and opt is not None and opt._step_dev is not None:
+                lr, b1, b2, eps = opt._hyper()
+                check(load().psb_peer_gather_rows_lazy(
+                    self.shard.ptr_array(), self._m_buf.ptr_array(), self._v_buf.ptr_array(), self._last_buf.ptr_array(),
+                    self.peer.world, self.rows, self.d, ids.data_ptr(), n + 1, mini.data_ptr(), remap.data_ptr(),
+                    self.pad_idx, n, None, lr, b1, b2, eps, 1 if opt._last_noam else 0, float(opt._last_warmup),
+                    opt._step_dev.data_ptr(), opt._coef_hist.data_ptr() if opt._coef_hist is not None else None,
+                    opt.coef_cap, stream_ptr()), "psb_peer_gather_rows_lazy")
+            else:
+                check(load().psb_peer_gather_rows(self.shard.ptr_array(), self.peer.world, self.rows, self.d,
+                                                  ids.data_ptr(), n + 1, mini.data_ptr(), remap.data_ptr(), self.pad_idx, n,
+                                                  None, stream_ptr()), "psb_peer_gather_rows")
         # a leaf that requires grad, so the autograd Functions reading it run their backward (which routes the row
         # gradients to the sink; nothing is ever accumulated into mini.grad)
         mini.requires_grad_(self.weight.requires_grad and torch.is_grad_enabled())
@@ -289,11 +310,13 @@ class PeerShardedTable(object):
         G = self.peer.world
         if self._posmap is None:
             self._posmap = torch.zeros(G * self.local_rows, dtype=torch.int64, device=self.weight.device)
-            self._rowwise_zero = self.grad.numel() * 4 > (64 << 20)     # big shard: clear touched rows, not a memset
+            self._rowwise_zero = self.sparse or self.grad.numel() * 4 > (64 << 20)   # big shard: clear touched rows, not a memset
             if self._rowwise_zero:
                 self._touched = torch.zeros(G * self._cap, dtype=torch.int32, device=self.weight.device)
                 self._n_touched = torch.zeros(1, dtype=torch.int32, device=self.weight.device)
-        if self._rowwise_zero:
+        if self.sparse:
+            self._n_touched.zero_()      # only the rows of THIS fold's list are ever read: nothing to clear
+        elif self._rowwise_zero:
             ops.zero_rows(self._touched, self._n_touched, self.d, self.grad, None)
             self._n_touched.zero_()
         else:
@@ -318,7 +341,13 @@ def fold_tables(tables, scale):
     check(load().psb_peer_fold_lists(arr, len(tables), peer.rank, peer.world, float(scale), peer.fold_stamp(),
                                      stream_ptr()), "psb_peer_fold_lists")
     for t in tables:
-        t.weight.grad = t.grad
+        if t.sparse:                     # (rows the fold wrote, the dense shard gradient they index, their count)
+            t.weight.grad = None
+            t.weight.row_grad = (t._touched, t.grad, t._n_touched)
+            t.weight._psb_grad_by_row = True
+            t.weight._psb_drop_idx = t.pad_idx // peer.world if t.pad_idx % peer.world == peer.rank else -1
+        else:
+            t.weight.grad = t.grad
 
 
 class PeerGradSink(object):

@@ -64,7 +64,9 @@ def main():
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, worst relative gradient error %.2e, sharded top-100 == unsharded" % (world, worst))
-    peer_check(rank, world, cfg, ref, batches, dev)
+    pg = peer_check(rank, world, cfg, ref, batches, dev)
+    if pg is not None:
+        sparse_peer_check(rank, world, cfg, dev, pg)
     dist.destroy_process_group()
 
 
@@ -98,7 +100,7 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     if pg is None:
         if rank == 0:
             print("peer_check SKIPPED: CUDA IPC / P2P unavailable on this box")
-        return
+        return None
     P, V, B = 40000, 5000, 96
     for k_, v_ in dict(optim="adam", lr=0.01, max_grad_norm=0.05, beta1=0.9, beta2=0.999, decay_method="adam",
                        warmup_steps=8000, l2_lambda=0.0, train_from="").items():
@@ -190,6 +192,66 @@ def peer_check(rank, world, cfg, ref, batches, dev):
     if rank == 0:
         print("peer_check ok: world=%d, worst relative gradient error %.2e, graph-replayed losses %s" %
               (world, worst, ["%.4f" % v for v in vals]))
+    return pg
+
+
+def sparse_peer_check(rank, world, cfg, dev, pg):
+    """Row-sharded training with the ROW-SPARSE owner-side Adam (item table: grad_mode="rowsparse"; readers bring
+    resting rows up to date on the fly, psb_peer_gather_rows_lazy) against the same sharded model with the dense
+    owner-side sweep: same loss at every step (every step reads rows that rested since an earlier one), and after
+    the final flush the same item shard up to the few elements whose gradient is rounding noise."""
+    from prodsearch_b200 import synth
+    from prodsearch_b200.item_transformer import PeerShardedItemTransformerRanker
+    from prodsearch_b200.optimizers import build_optim
+    P, V, B, steps, lr = int(os.environ.get("PSB_CHECK_ROWS", "40000")), 5000, 96, 7, 0.005
+    for k_, v_ in dict(optim="adam", lr=lr, max_grad_norm=5.0, beta1=0.9, beta2=0.999, decay_method="adam",
+                       warmup_steps=8000, l2_lambda=0.0, train_from="").items():
+        setattr(cfg, k_, v_)
+    models, opts = [], []
+    for mode in ("dense", "rowsparse"):
+        torch.manual_seed(7)
+        with torch.device("cuda"):
+            m = PeerShardedItemTransformerRanker(cfg, "cuda", V, P, None, word_dists=synth.word_dists(V), peer=pg,
+                                                 grad_mode=mode)
+        m.train()
+        models.append(m)
+        opts.append(build_optim(cfg, m))
+    assert torch.equal(models[0].item_table.weight, models[1].item_table.weight)
+
+    def padded(b):
+        out = dev(b)
+        q = torch.full((B, 12), V - 1, dtype=torch.int64, device="cuda")
+        q[:, :out.query_word_idxs.shape[1]] = out.query_word_idxs
+        out.query_word_idxs = q
+        return out
+    worst = 0.0
+    for s in range(steps):
+        b, ni, nw = synth.tem_batch(B, P, V, seed=900 + 17 * s + rank)
+        cb = padded(b)
+        ls = []
+        for m, o in zip(models, opts):
+            m.injected_negatives = (ni.cuda(), nw.cuda())
+            loss = m(cb)
+            m.zero_grad()
+            loss.backward()
+            m.sync_grads(o)
+            o.step()
+            ls.append(float(loss.detach()))
+            del loss
+        rel = abs(ls[0] - ls[1]) / abs(ls[0])
+        worst = max(worst, rel)
+        assert rel <= 2e-5, (s, ls)
+    pg.check_errors()
+    assert models[1].item_table.lazy_optim is not None and models[1].item_table.weight.grad is None
+    stale = float((models[0].item_table.weight - models[1].item_table.weight).abs().max())
+    models[1].eval()                       # flush: every resting row of the shard is brought up to date
+    err = (models[0].item_table.weight - models[1].item_table.weight).abs()
+    assert float(err.max()) <= 0.05 * lr * steps, float(err.max())
+    assert float((err > 3e-6 * steps).float().mean()) <= 2e-3
+    dist.barrier()
+    if rank == 0:
+        print("sparse_peer_check ok: world=%d, %d rows, worst relative loss difference %.1e over %d steps, shard max "
+              "difference %.1e before / %.1e after the flush" % (world, P, worst, steps, stale, float(err.max())))
 
 
 if __name__ == "__main__":
