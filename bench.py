@@ -769,6 +769,25 @@ def sharded_regime(peaks, pg, rank, world, rows=16_000_000, d=128, m_total=4096,
                     "%.1f GB per rank and step)" % ((rows // world) * d * 28 / 1e9)}
         try:
             pg.check_errors()
+            # per-kernel split of the same step, launched eagerly with the library's profiler (all ranks take part: the
+            # step contains cross-GPU barriers)
+            def eager():
+                loss = model(batches[0])
+                model.zero_grad()
+                loss.backward()
+                model.sync_grads(optim)
+                optim.step()
+            for _ in range(2):
+                eager()
+            sync()
+            _lib.profile_enable(True)
+            for _ in range(3):
+                eager()
+            sync()
+            kp = _lib.profile_dump()
+            _lib.profile_enable(False)
+            out["train_step_16M"]["kernels_us_per_step"] = {k_: round(v_[1] / 3 * 1e3, 1) for k_, v_ in
+                                                            sorted(kp.items(), key=lambda kv: -kv[1][1])[:14]}
         except Exception as ex:                                           # noqa: BLE001
             out["train_step_16M"]["peer_error"] = str(ex)[:120]
     else:

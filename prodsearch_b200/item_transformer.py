@@ -441,6 +441,11 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         del full_items, full_words
         self._make_sinks()
         skip = {"product_emb.weight", "word_embeddings.weight"}
+        if args.sim_func != "bias_product":
+            # product_bias [P + 1] is not part of this model's loss (item_transformer.py:495-499 only adds it for
+            # bias_product): keeping it in the all-reduced bucket would move 4 (P + 1) bytes per rank over NVLink and
+            # 28 (P + 1) bytes through Adam every step -- 64 MB / 457 MB at 16M items -- for a gradient that is always zero
+            skip.add("product_bias")
         dense = [p for n, p in self.named_parameters() if p.requires_grad and n not in skip]
         self._bucket = peer_mod.DenseBucket(self.peer, dense)
         self._sq = self.peer.alloc(16)                      # this rank's shard-gradient |g|^2 (peer-visible)
