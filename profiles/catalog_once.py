@@ -10,7 +10,7 @@ from prodsearch_b200 import _lib, ops  # noqa: E402
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 384
 mode = _lib.TOPK_TC if (len(sys.argv) > 2 and sys.argv[2] == "tf32") else _lib.TOPK_TC16
-n, d = 1_000_000, 128
+n, d = int(os.environ.get("PSB_N", "1000000")), 128
 table = torch.empty(n + 1, d, device="cuda").normal_()
 norm = ops.table_max_row_sqnorm(table, n)
 prep = ops.catalog_prepare_f16(table, n)
