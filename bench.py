@@ -225,6 +225,44 @@ def cpu_reference_others(seed=666, scale=1):
                             "sample": "BASELINE configs[0]: 5 ParagraphVector steps (fwd + bwd + Adam), 384 reviews, "
                                       "R = 300k x 128 review table, 5 negatives, oracle port"}
     del review_table, word_table, opt
+    # (ii-b) BASELINE configs[2]: an RTM (ProductRanker) train step through the oracle port -- pv at batch 384, pvc at
+    #        batch 96 (its [N, 100, 128] gathers need ~20 GB and ~30 s at 384: bounded sample, samples/s is the unit)
+    try:
+        from prodsearch_b200 import synth as synth_
+        from prodsearch_b200.ps_model import ProductRanker
+        Vr, Rr, Pr, Ur, Wr = V, 300_000 // scale, 18000 // scale, 35000 // scale, 100
+        rw = synth_.review_words_table(Rr, Vr, Wr)
+        for enc, Bq in (("pv", WORKLOAD["batch_per_gpu"] // (8 if scale > 1 else 1)), ("pvc", 96 // (8 if scale > 1 else 1))):
+            a = model_args(0.0)
+            a.model_name, a.review_encoder_name, a.review_word_limit, a.corrupt_rate = "review_transformer", enc, Wr, 0.9
+            a.fix_emb, a.do_subsample_mask, a.use_user_emb, a.use_item_emb, a.use_seg_emb = False, True, False, False, True
+            a.review_pad_idx = Rr - 1
+            torch.manual_seed(1)
+            ref_model = ProductRanker(a, "cpu", Vr, Rr, Pr, Ur, rw, None, word_dists=synth_.word_dists(Vr))
+            params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith("pos_emb.pe"))
+                      for k, v in ref_model.state_dict().items()}
+            leaves = [v for v in params.values() if v.requires_grad]
+            opt_r = torch.optim.Adam(leaves, lr=WORKLOAD["lr"], eps=1e-9)
+            batch, draws = synth_.rtm_batch(Bq, rw, Vr, Pr, Ur, pvc=(enc == "pvc"), train_pv=True, seed=3)
+            gm = torch.Generator().manual_seed(4)
+            masks = [(torch.rand(Bq * 50, Wr, generator=gm) < 0.9).float(), (torch.rand(Bq * K * 50, Wr, generator=gm) < 0.9).float()] \
+                if enc == "pvc" else None
+
+            def rtm_step():
+                loss, _, _ = oracle.rtm_forward(params, a, batch, True, draws["multinomial"][0], [m.clone() for m in masks] if masks else None,
+                                                training=True)
+                opt_r.zero_grad()
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(leaves, WORKLOAD["max_grad_norm"])
+                opt_r.step()
+            sec = median_time(rtm_step, 2 if enc == "pv" else 1, warmup=1 if enc == "pv" else 0)
+            out["rtm_%s_train_step" % enc] = {"value": Bq / sec, "unit": "samples/s", "ms_per_step": sec * 1e3, "batch": Bq,
+                                               "sample": "BASELINE configs[2]: RTM train step (fwd + bwd + clipped Adam), %s review encoder "
+                                                         "with the review-word objective, 20 + 30 reviews / sequence, 100 words / "
+                                                         "review, batch %d, oracle port" % (enc, Bq)}
+            del ref_model, params, leaves, opt_r
+    except Exception as ex:                                           # noqa: BLE001 -- reported, never fatal
+        out["rtm_train_step"] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:120])}
     # (iii) full-catalog ranking over N = 1M items
     n_items = 1_000_000 // scale
     chunk = max(n_items // 4, 100)
