@@ -545,6 +545,18 @@ int psb_peer_allreduce(const void* const* bufs, int32_t G, int32_t rank, int64_t
 int psb_peer_sum_sqnorm(const void* const* slots, int32_t G, float* sqnorm_out, int64_t* step_dev,
                         psb_stream_t stream);
 
+/* psb_grad_sqnorm(_sparse) + psb_peer_barrier + psb_peer_sum_sqnorm as ONE chain with a single tail launch: the partial
+ * sums of this rank's gradients (dense tensors and row lists, as psb_grad_sqnorm_sparse), then one kernel that finishes
+ * them, publishes the shard norm in slots[rank], runs the cross-GPU barrier, adds the G slots in rank order into
+ * *sqnorm_out and advances *step_dev (for psb_adam_step / psb_adam_sparse_step with norm_given = 2).  Barrier arguments
+ * as psb_peer_barrier; workspace as psb_adam_sparse_workspace_bytes. */
+int psb_peer_norm_exchange(const psb_adam_tensor_t* dense /* host; g and n */, int32_t n_dense,
+                           const psb_adam_rows_t* tables /* host */, int32_t n_tables, const void* const* slots,
+                           const void* const* flag_blocks, int32_t rank, int32_t G, uint32_t* epoch_dev,
+                           int32_t* err_dev, int64_t timeout_cycles, uint64_t* wait_cycles_dev, int32_t wait_slot,
+                           float* sqnorm_out, int64_t* step_dev, void* workspace, int64_t workspace_bytes,
+                           psb_stream_t stream);
+
 /* ------------------------------------------------------------------ N4 ---
  * On-device batch construction, metrics ranks and the ranklist writer for the item-transformer (TEM) path
  * (SURVEY.md 8(f) N4).  The corpus relations the reference keeps as nested Python lists

@@ -144,6 +144,9 @@ SIGNATURES = {
                                      c_vp, c_vp]),
     "psb_peer_fold_lists": (c_i32, [ctypes.POINTER(FoldTable), c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "psb_peer_sum_sqnorm": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_vp, c_vp, c_vp]),
+    "psb_peer_norm_exchange": (c_i32, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamRows), c_i32, ctypes.POINTER(c_vp),
+                                       ctypes.POINTER(c_vp), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp,
+                                       c_i64, c_vp]),
     "psb_peer_allreduce": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, c_f32, c_vp, c_vp]),
     "psb_build_item_batch": (c_i32, [ctypes.POINTER(Corpus), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_u32,
                                      c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -92,4 +92,8 @@ inline AdamHyper make_adam_hyper(double lr, double beta1, double beta2, double e
   return h;
 }
 
+// optimizer.cu: |g|^2 partial sums of dense tensors + row lists into partial[0 .. *n_partials) (fixed order)
+int sqnorm_partials(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables, int32_t n_tables,
+                    float* partial, int64_t partial_cap, int* n_partials, cudaStream_t s);
+
 }  // namespace psb

@@ -626,6 +626,48 @@ extern "C" int psb_adam_sparse_step(const psb_adam_tensor_t* dense, int32_t n_de
   return PSB_OK;
 }
 
+// The partial sums only (for psb_peer_norm_exchange in peer.cu, which finishes them inside its fused kernel)
+namespace psb {
+int sqnorm_partials(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables, int32_t n_tables,
+                    float* partial, int64_t partial_cap, int* n_partials, cudaStream_t s) {
+  if (n_dense < 0 || n_dense > PSB_ADAM_MAX_TENSORS || n_tables < 0 || n_tables > PSB_ADAM_MAX_ROW_TABLES ||
+      n_dense + n_tables == 0 || partial == nullptr || (n_dense > 0 && dense == nullptr) ||
+      (n_tables > 0 && tables == nullptr))
+    return PSB_E_ARG;
+  AdamTensors T;
+  T.n = n_dense;
+  for (int i = 0; i < n_dense; ++i) {
+    if (dense[i].g == nullptr || dense[i].n <= 0) return PSB_E_ARG;
+    T.t[i] = dense[i];
+  }
+  RowTables R;
+  R.n = n_tables;
+  for (int i = 0; i < n_tables; ++i) {
+    if (tables[i].rows == nullptr || tables[i].grad == nullptr || tables[i].n_rows == nullptr || tables[i].cap <= 0 ||
+        tables[i].d <= 0 || (tables[i].d & 3) != 0)
+      return PSB_E_ARG;
+    R.t[i] = tables[i];
+  }
+  const int64_t chunks = adam_chunks(dense, n_dense);
+  const int64_t nblocks = row_norm_blocks(tables, n_tables);
+  if (chunks + nblocks > (1ll << 30)) return PSB_E_DIM;
+  if (partial_cap < chunks + nblocks) return PSB_E_WORKSPACE;
+  int st;
+  if (chunks > 0) {
+    PSB_PROF("sqnorm_partial_kernel", s);
+    sqnorm_partial_kernel<<<static_cast<int>(chunks), 256, 0, s>>>(T, partial);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  if (nblocks > 0) {
+    PSB_PROF("sqnorm_rows_partial_kernel", s);
+    sqnorm_rows_partial_kernel<<<static_cast<int>(nblocks), 256, 0, s>>>(R, partial + chunks);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
+  *n_partials = static_cast<int>(chunks + nblocks);
+  return PSB_OK;
+}
+}  // namespace psb
+
 extern "C" int psb_grad_sqnorm_sparse(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables,
                                       int32_t n_tables, float* sqnorm_out, void* workspace, int64_t workspace_bytes,
                                       psb_stream_t stream) {

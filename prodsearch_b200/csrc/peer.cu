@@ -358,9 +358,87 @@ __global__ void peer_sum_sqnorm_kernel(PeerPtrs slots, int G, float* __restrict_
   if (step != nullptr) *step += 1;
 }
 
+// Norm exchange in ONE launch: finish this rank's partial sums (fixed order, double), publish the shard norm in this
+// rank's peer-visible slot, cross-GPU barrier, sum the G slots in rank order, advance the optimizer's step counter.
+// (Three launches before: sqnorm_final, peer_barrier, peer_sum_sqnorm.)
+__global__ void __launch_bounds__(256)
+peer_norm_exchange_kernel(const float* __restrict__ partial, int n_partial, PeerPtrs slots, PeerPtrs flags, int rank, int G,
+                          uint32_t* __restrict__ epoch, int32_t* __restrict__ err, long long timeout_cycles,
+                          unsigned long long* __restrict__ wait_cycles, int slot, float* __restrict__ out,
+                          int64_t* __restrict__ step) {
+  __shared__ double wsum[8];
+  __shared__ uint32_t e_sh;
+  const int t = threadIdx.x;
+  double acc = 0.0;
+  const int per = (n_partial + 255) / 256;
+  const int lo = t * per, hi = min(n_partial, lo + per);
+  for (int i = lo; i < hi; ++i) acc += static_cast<double>(partial[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if ((t & 31) == 0) wsum[t >> 5] = acc;
+  __syncthreads();
+  const long long t_in = clock64();
+  if (t == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    *static_cast<float*>(const_cast<void*>(slots.p[rank])) = static_cast<float>(s);
+    e_sh = *epoch + 1u;
+    *epoch = e_sh;
+  }
+  __syncthreads();
+  const uint32_t e = e_sh;
+  if (t < G) {
+    __threadfence_system();
+    uint32_t* theirs = static_cast<uint32_t*>(const_cast<void*>(flags.p[t])) + rank;
+    st_release_sys(theirs, e);
+    const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + t;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - e) < 0) {
+      if (clock64() - t0 > timeout_cycles) {
+        if (err != nullptr) *err = 1 + t;
+        break;
+      }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t == 0) {
+    float total = 0.f;
+    for (int r = 0; r < G; ++r) total += *static_cast<const volatile float*>(slots.p[r]);
+    *out = total;
+    if (step != nullptr) *step += 1;
+    if (wait_cycles != nullptr) wait_cycles[slot & 3] += static_cast<unsigned long long>(clock64() - t_in);
+  }
+}
+
 }  // namespace psb
 
 using namespace psb;
+
+static int fill_ptrs(PeerPtrs* P, const void* const* host_ptrs, int32_t G);
+
+extern "C" int psb_peer_norm_exchange(const psb_adam_tensor_t* dense, int32_t n_dense, const psb_adam_rows_t* tables,
+                                      int32_t n_tables, const void* const* slots, const void* const* flag_blocks,
+                                      int32_t rank, int32_t G, uint32_t* epoch_dev, int32_t* err_dev,
+                                      int64_t timeout_cycles, uint64_t* wait_cycles_dev, int32_t wait_slot,
+                                      float* sqnorm_out, int64_t* step_dev, void* workspace, int64_t workspace_bytes,
+                                      psb_stream_t stream) {
+  PeerPtrs S, F;
+  int st;
+  if ((st = fill_ptrs(&S, slots, G)) != PSB_OK || (st = fill_ptrs(&F, flag_blocks, G)) != PSB_OK) return st;
+  if (rank < 0 || rank >= G || epoch_dev == nullptr || sqnorm_out == nullptr || workspace == nullptr) return PSB_E_ARG;
+  if (timeout_cycles <= 0) timeout_cycles = 4000000000ll;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int n_partial = 0;
+  float* partial = static_cast<float*>(workspace);
+  if ((st = sqnorm_partials(dense, n_dense, tables, n_tables, partial, workspace_bytes / 4, &n_partial, s)) != PSB_OK) return st;
+  PSB_PROF("peer_norm_exchange_kernel", s);
+  peer_norm_exchange_kernel<<<1, 256, 0, s>>>(partial, n_partial, S, F, rank, G, epoch_dev, err_dev, timeout_cycles,
+                                              reinterpret_cast<unsigned long long*>(wait_cycles_dev), wait_slot, sqnorm_out,
+                                              step_dev);
+  return launch_status();
+}
 
 extern "C" int psb_peer_alloc(int64_t bytes, void** out) {
   if (bytes <= 0 || out == nullptr) return PSB_E_ARG;

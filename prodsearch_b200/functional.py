@@ -378,9 +378,14 @@ class MeanPoolFn(Function):
 
     @staticmethod
     def forward(ctx, weight, idx, fs_weight, fs_bias, sink, pad_idx, mask, tok_scale, keep_scale, stream=None):
-        out, mean, _ = ops.gather_meanpool(weight, idx, pad_idx=pad_idx, mask=mask, tok_scale=tok_scale,
-                                           keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias,
-                                           stream=stream)
+        # validity by pad id with the pad row dropped by the sink anyway: the backward weights valid / count reduce to
+        # 1 / count per pool, which the forward kernel hands out for free (no token-weights launch in backward)
+        ctx.by_count = (mask is None and pad_idx >= 0 and sink is not None and
+                        getattr(sink, "drop_idx", None) == pad_idx and ctx.needs_input_grad[0])
+        out, mean, inv = ops.gather_meanpool(weight, idx, pad_idx=pad_idx, mask=mask, tok_scale=tok_scale,
+                                             keep_scale=keep_scale, fs_weight=fs_weight, fs_bias=fs_bias,
+                                             want_inv_count=ctx.by_count, stream=stream)
+        ctx.inv_count = inv
         ctx.sink, ctx.idx, ctx.pad_idx, ctx.mask, ctx.keep = sink, idx, pad_idx, mask, keep_scale
         if ctx.needs_input_grad[0]:
             _expect(sink, idx)
@@ -399,8 +404,11 @@ class MeanPoolFn(Function):
         else:
             gm = g if ctx.keep is None else g * ctx.keep
         idx = ctx.idx
-        tw = ops.token_weights(idx, pad_idx=ctx.pad_idx, mask=ctx.mask)
-        ctx.sink.add(idx.reshape(-1), gm, src_div=idx.shape[1], scale=tw.view(-1))
+        if ctx.by_count:
+            ctx.sink.add(idx.reshape(-1), gm, src_div=idx.shape[1], scale2=ctx.inv_count, scale2_div=idx.shape[1])
+        else:
+            tw = ops.token_weights(idx, pad_idx=ctx.pad_idx, mask=ctx.mask)
+            ctx.sink.add(idx.reshape(-1), gm, src_div=idx.shape[1], scale=tw.view(-1))
         return None, None, gw, gb, None, None, None, None, None, None
 
 

@@ -604,16 +604,23 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
                 it.lazy_optim = opt
         self.sync_stage()
         self.peer.barrier(1)       # every rank's compact lists and dense bucket are complete
-        self.sync_fold()
-        if optim is None or not hasattr(getattr(optim, "optimizer", optim), "set_global_sqnorm"):
+        fused = (optim is not None and hasattr(getattr(optim, "optimizer", optim), "global_norm_slots")
+                 and self.peer.world > 1 and self.peer._sim is None and self.fused_norm_exchange)
+        self.sync_fold(norm_exchange=optim if fused else None)
+        if fused or optim is None or not hasattr(getattr(optim, "optimizer", optim), "set_global_sqnorm"):
             return
         self.peer.barrier(2)       # every rank's shard norm is published
         self.sync_norm(optim)
 
+    fused_norm_exchange = True     # shard norm, barrier and global norm in one tail launch (psb_peer_norm_exchange)
+
     def sync_stage(self):
         self._bucket.stage()
 
-    def sync_fold(self):
+    def sync_fold(self, norm_exchange=None):
+        """norm_exchange: the optimizer, when the shard norm, the barrier behind it and the global norm are to run as
+        one chain (real multi-process groups); None: only the shard norm is formed here (the simulated ranks of the
+        tests meet at explicit phases: sync_grads then runs barrier + sync_norm)."""
         G = self.peer.world
         from .peer import fold_tables
         # the owner-side fold of the two tables and the all-reduce of the replicated gradients are independent:
@@ -642,6 +649,8 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
             wb = int(lib.psb_adam_sparse_workspace_bytes(arr, n, rows_arr, 1))
             if self._norm_ws is None or self._norm_ws.numel() < wb:
                 self._norm_ws = torch.empty(wb, dtype=torch.uint8, device=self.peer.device)
+            if norm_exchange is not None:
+                return self._norm_exchange(norm_exchange, arr, n, rows_arr, 1, wb)
             _lib.check(lib.psb_grad_sqnorm_sparse(arr, n, rows_arr, 1, self._sq_local.data_ptr(), self._norm_ws.data_ptr(),
                                                   wb, _lib.stream_ptr()), "psb_grad_sqnorm_sparse")
             return
@@ -653,8 +662,19 @@ class PeerShardedItemTransformerRanker(ItemTransformerRanker):
         wb = int(lib.psb_adam_workspace_bytes(arr, n))
         if self._norm_ws is None or self._norm_ws.numel() < wb:
             self._norm_ws = torch.empty(wb, dtype=torch.uint8, device=self.peer.device)
+        if norm_exchange is not None:
+            return self._norm_exchange(norm_exchange, arr, n, None, 0, wb)
         _lib.check(lib.psb_grad_sqnorm(arr, n, self._sq_local.data_ptr(), self._norm_ws.data_ptr(), wb,
                                        _lib.stream_ptr()), "psb_grad_sqnorm")
+
+    def _norm_exchange(self, optim, arr, n, rows_arr, n_tables, wb):
+        """Partial sums, then ONE kernel: finish + publish the shard norm, barrier C, global norm, step counter."""
+        pg = self.peer
+        sq, step = getattr(optim, "optimizer", optim).global_norm_slots(pg.device)
+        _lib.check(_lib.load().psb_peer_norm_exchange(
+            arr, n, rows_arr, n_tables, self._sq.ptr_array(), pg.flags.ptr_array(), pg.rank, pg.world, pg.epoch.data_ptr(),
+            pg.err.data_ptr(), int(pg.timeout_cycles), pg.wait_cycles.data_ptr(), 2, sq.data_ptr(), step.data_ptr(),
+            self._norm_ws.data_ptr(), wb, _lib.stream_ptr()), "psb_peer_norm_exchange")
 
     def sync_norm(self, optim):
         sq, step = getattr(optim, "optimizer", optim).global_norm_slots(self.peer.device)
