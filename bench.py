@@ -569,13 +569,25 @@ def rtm_regime(peaks, steps=5):
                 return loss
             for _ in range(2):
                 one()
-            sec = timed(one, steps, warmup=1)
+            sec_eager = timed(one, steps, warmup=1)
+            # the same step captured once and replayed (graph_step.GraphedTrainStep, as the TEM headline): the eager step
+            # is bound by the host launching ~150 kernels
+            sec = sec_eager
+            launch = "eager"
+            try:
+                from prodsearch_b200.graph_step import GraphedTrainStep
+                gstep = GraphedTrainStep(model, optim, cb)
+                sec = timed(lambda: gstep(cb), steps, warmup=2)
+                launch = "CUDA graph replay"
+                del gstep
+            except Exception as ex:                                   # noqa: BLE001 -- the eager number stands
+                launch = "eager (graph capture failed: %s)" % str(ex)[:80]
             _lib.profile_enable(True)
             for _ in range(2):
                 one()
             kp = _lib.profile_dump()
             _lib.profile_enable(False)
-            ent = {"ms_per_step": sec * 1e3, "samples_per_s": B / sec}
+            ent = {"ms_per_step": sec * 1e3, "samples_per_s": B / sec, "launch": launch, "eager_ms_per_step": sec_eager * 1e3}
             Rc = 50
             if enc == "pvc":     # PVC: clean + corrupted mean of the positives, mean of the negatives: (2 + K) * B * Rc pools of Wr rows
                 pools = (2 + K) * B * Rc

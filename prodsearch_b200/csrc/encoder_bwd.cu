@@ -564,11 +564,24 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   const TokSrc ts{cfg->first, cfg->table, cfg->table_rows, cfg->idx, cfg->pad_idx, cfg->dense, cfg->mask, cfg->pe, cfg->raw_input != 0 && cfg->first == nullptr};
   const int d = D.d, F = D.F, SC = D.S * D.C;
 
-  // [Wk ; Wv] stacked so grad xn is ONE product over the 2d-wide [gK | gV] rows
-  cudaError_t ce = cudaMemcpyAsync(ws + W.wkv, p->wk, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, s);
-  if (ce == cudaSuccess)
-    ce = cudaMemcpyAsync(ws + W.wkv + static_cast<size_t>(d) * d, p->wv, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, s);
-  if (ce != cudaSuccess) return static_cast<int>(ce);
+  // [Wk ; Wv] stacked so grad xn is ONE product over the 2d-wide [gK | gV] rows.  Big token counts (RTM: 117k rows)
+  // run that product on tcgen05 (gemm3_tf32.cu), which wants the K-major operand [Wk^T | Wv^T] : [d][2d] instead
+  const bool tc_gxn = rows_gemm_tc_auto(static_cast<int64_t>(D.S) * D.T) &&
+                      rows_gemm_tc_supported(ws + W.gkv, 2 * d, 2 * d, ws + W.wkv, nullptr, 0, d, nullptr, ws + W.gxn, d);
+  cudaError_t ce = cudaSuccess;
+  if (tc_gxn) {
+    TrJobs jobs;
+    jobs.n = 0;
+    jobs.j[jobs.n++] = TrJob{p->wk, ws + W.wkv, d, d, 2 * d, 0};
+    jobs.j[jobs.n++] = TrJob{p->wv, ws + W.wkv, d, d, 2 * d, d};
+    int st0 = launch_transposes(jobs, s);
+    if (st0 != PSB_OK) return st0;
+  } else {
+    ce = cudaMemcpyAsync(ws + W.wkv, p->wk, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, s);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(ws + W.wkv + static_cast<size_t>(d) * d, p->wv, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, s);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+  }
 
   TailBwdArgs a;
   a.D = D;
@@ -604,6 +617,9 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
           return launch_rows_gemm(ws + W.g_qlin, d, nullptr, D.S, D.S, d, p->wq, d, nullptr, ws + W.gxno, d, s2);
         },
         [&]() {
+          if (tc_gxn)
+            return launch_rows_gemm_tc(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, nullptr, 0, d, nullptr,
+                                       ws + W.gxn, d, s);
           return launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr,
                                   ws + W.gxn, d, s);
         });

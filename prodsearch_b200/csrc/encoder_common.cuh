@@ -286,11 +286,22 @@ __device__ __forceinline__ bool tok_valid(const TokSrc& ts, int s, int t, int T)
 
 int dims_from_cfg(const psb_encoder_cfg_t* cfg, Dims* D);
 size_t tail_bwd_smem_floats(int R, int d, int F, int H, int T, int spt);
+struct TrJob {
+  const float* src;  // [rows][cols]
+  float* dst;        // dst[c * ldd + col0 + r]
+  int rows, cols, ldd, col0;
+};
+struct TrJobs {
+  TrJob j[8];
+  int n;
+};
+int launch_transposes(const TrJobs& jobs, cudaStream_t s);   // encoder_fwd.cu: weight transposes, one launch
 int launch_rows_gemm(const float* A, int lda, const int32_t* m_dev, int m_host, int m_max, int I, const float* B,
                      int J, const float* bias, float* out, int ldo, cudaStream_t s);
 // gemm3_tf32.cu: the same product on tcgen05 (3xTF32 split) from the K-major operand Bt [J][K] (rows [split, J) from
 // Bt1 when given); off unless PSB_ENC_TC=1
 bool rows_gemm_tc_enabled();
+bool rows_gemm_tc_auto(int64_t m_max);
 bool rows_gemm_tc_supported(const float* A, int lda, int K, const float* Bt0, const float* Bt1, int split, int J,
                             const float* bias, const float* out, int ldo);
 int launch_rows_gemm_tc(const float* A, int lda, const int32_t* m_dev, int m_host, int m_max, int K, const float* Bt0,

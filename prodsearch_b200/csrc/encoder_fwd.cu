@@ -131,15 +131,6 @@ __global__ void __launch_bounds__(1024) plan_kernel(TokSrc ts, int S, int T, int
 }
 
 // ------------------------------------------------------------------ transposes
-struct TrJob {
-  const float* src;  // [rows][cols]
-  float* dst;        // dst[c * ldd + col0 + r]
-  int rows, cols, ldd, col0;
-};
-struct TrJobs {
-  TrJob j[8];
-  int n;
-};
 __global__ void __launch_bounds__(256) transpose_kernel(TrJobs jobs) {
   __shared__ float tile[32][33];
   int b = blockIdx.x;
@@ -171,6 +162,11 @@ inline int tr_blocks(const TrJobs& J) {
   int n = 0;
   for (int q = 0; q < J.n; ++q) n += ((J.j[q].rows + 31) / 32) * ((J.j[q].cols + 31) / 32);
   return n;
+}
+int launch_transposes(const TrJobs& jobs, cudaStream_t s) {
+  PSB_PROF("transpose_kernel", s);
+  transpose_kernel<<<tr_blocks(jobs), 256, 0, s>>>(jobs);
+  return launch_status();
 }
 
 // ------------------------------------------------------------------ embed
@@ -594,7 +590,7 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   // (independent products: the small q projection runs on the library's side stream next to the K|V one)
   // PSB_ENC_TC=1: both products on tcgen05 (gemm3_tf32.cu) straight from the K-major weights Wq / Wk / Wv
   const bool tc_q = rows_gemm_tc_enabled() && rows_gemm_tc_supported(sv + L.xno, d, d, p->wq, nullptr, 0, d, p->bq, sv + L.qv, d);
-  const bool tc_kv = rows_gemm_tc_enabled() &&
+  const bool tc_kv = (rows_gemm_tc_enabled() || rows_gemm_tc_auto(static_cast<int64_t>(D.S) * D.T)) &&
                      rows_gemm_tc_supported(sv + L.xn, d, d, p->wk, p->wv, d, 2 * d, ws + W.bkv, sv + L.kv, 2 * d);
   st = fork_join(
       s, 1,

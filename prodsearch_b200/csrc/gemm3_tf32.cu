@@ -377,6 +377,18 @@ static int enc_tc_level() {
   return v;
 }
 bool rows_gemm_tc_enabled() { return enc_tc_level() >= 1; }
+// Unset PSB_ENC_TC: the K|V projection goes to tcgen05 by itself once it is big enough to be throughput- rather than
+// latency-bound: from 16 384 token rows on (RTM: 384 x 51 = 19.6k rows for the positives, 1920 x 51 = 98k for the
+// negatives: 0.31 ms on FFMA, 0.06 ms here); at TEM's 8k-row plan (~3.5k active rows) the FFMA kernel is as fast
+// (profiles/r02a_bench_enc_tc.json).  PSB_ENC_TC=0 switches the automatic choice off.
+bool rows_gemm_tc_auto(int64_t m_max) {
+  static int allowed = -1;
+  if (allowed < 0) {
+    const char* e = getenv("PSB_ENC_TC");
+    allowed = (e != nullptr && atoi(e) == 0 && e[0] == '0') ? 0 : 1;
+  }
+  return allowed == 1 && m_max >= 16384;
+}
 bool tail_tc_enabled() { return enc_tc_level() >= 2; }
 
 // One launch: out-tile epilogue `epi` over A [m rows, K] (row stride lda) and Bt rows [0, split) from Bt0, the rest from Bt1

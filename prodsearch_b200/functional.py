@@ -349,11 +349,21 @@ def _expect(sink, idx):
         fn(idx)
 
 
+_ONES = {}
+
+
 def _dropout_keep(shape, p, training, device):
-    """Dropout mask already scaled by 1/(1-p) (None when inactive)."""
+    """Dropout mask already scaled by 1/(1-p) (None when inactive): ONE launch -- dropout of a cached tensor of ones
+    (a Bernoulli draw followed by a division would be two, at the head of the step's critical path)."""
     if not training or p <= 0.0:
         return None
-    return torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
+    key = (tuple(shape), str(device))
+    ones = _ONES.get(key)
+    if ones is None:
+        if len(_ONES) > 16:
+            _ONES.clear()
+        ones = _ONES[key] = torch.ones(shape, dtype=torch.float32, device=device)
+    return torch.nn.functional.dropout(ones, p=p, training=True)
 
 
 class GatherRowsFn(Function):
