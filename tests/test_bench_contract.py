@@ -103,10 +103,10 @@ def test_summarize_regimes_puts_the_fractions_under_roofline():
                              "G5_catalog_topk_1M": {"tcgen05_f16_m384": {"ms": 0.3, "frac_of_tensor_peak": 0.2, "frac_of_hbm_peak": 0.1}},
                              "G5_catalog_topk_16M": {"ms": 16.3, "tflops": 1027.0, "frac_of_tensor_peak": 0.61}},
         "train_16M": {"rowsparse": {"ms_per_step": 0.4}, "dense": {"unavailable": "x"}},
-        "rtm_configs2": {"pvc": {"ms_per_step": 9.0, "meanpool_kernel": {"frac": 0.8}}}}}
+        "rtm_configs2": {"pvc": {"ms_per_step": 9.0, "meanpool_kernel": {"frac": 0.8, "achieved": 5000.0}}}}}
     b.summarize_regimes(line)
     tab = line["roofline"]["regimes"]
     assert tab["G1_gather_rows"]["frac_of_hbm_peak"] == 0.94 and tab["G5_16M_m4096"]["frac_of_tensor_peak"] == 0.61
     assert tab["train_16M_rowsparse"]["ms_per_step"] == 0.4 and "train_16M_dense" not in tab
-    assert tab["rtm_pvc"]["meanpool_kernel_frac_of_hbm_peak"] == 0.8
+    assert tab["rtm_pvc"]["meanpool_kernel_requested_over_hbm_peak_L2_resident"] == 0.8
     b.summarize_regimes({"roofline": None, "extra": None})          # nothing to do, nothing raised
