@@ -1156,7 +1156,7 @@ def run_b200_arm(a):
         # the cross-GPU barrier kernels are excluded: in this eager, per-kernel-timed pass they absorb the host-launch
         # skew between the ranks (hundreds of us), not device work; what the barriers cost inside the replayed graph is
         # config.peer_barrier_wait (clock64 cycles every rank spent waiting, 8-20 us per barrier)
-        cands = {k_: v_ for k_, v_ in kernels.items() if k_ != "peer_barrier_kernel"} or kernels
+        cands = {k_: v_ for k_, v_ in kernels.items() if k_ not in ("peer_barrier_kernel", "peer_norm_exchange_kernel")} or kernels
         name, ent = max(cands.items(), key=lambda kv: kv[1]["ms_per_step"])
         roofline = {"kernel": name, "bound": ent.get("bound", "hbm"), "achieved": ent.get("achieved"),
                     "peak": ent.get("peak"), "unit": ent.get("unit"), "frac": ent.get("frac"), "traffic": None,

@@ -274,45 +274,35 @@ __global__ void __launch_bounds__(256) peer_fold_kernel(const FoldArgs a) {
         if (q == r) slot[q] = static_cast<int32_t>(i);
       }
     }
-    // Four leaders at a time, one per 8-lane group (lane = 4 of a row's 32 float4 at d = 128): every round has four
-    // rows' peer loads in flight instead of one (a leader fold is a chain of NVLink round trips; at G = 8 a warp holds
-    // ~4 leaders and the serial rounds were the kernel's time)
+    // (measured at N = 8, profiles/r02A_bench_n8.json: folding four leaders per round in 8-lane groups -- more rows in
+    // flight, but 128-byte instead of 512-byte peer requests -- is SLOWER: 86 vs 54 us; one leader per round stays)
     unsigned todo = __ballot_sync(kFull, leader);
-    const int grp = lane >> 3, sub = lane & 7;
     while (todo != 0u) {
-      int lg[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        lg[g] = todo != 0u ? __ffs(todo) - 1 : -1;
-        if (todo != 0u) todo &= todo - 1;
-      }
-      const int l = grp == 0 ? lg[0] : grp == 1 ? lg[1] : grp == 2 ? lg[2] : lg[3];
-      const int src = l >= 0 ? l : 0;
-      const int64_t row = __shfl_sync(kFull, local, src);
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t row = __shfl_sync(kFull, local, l);
       int32_t sl[kMaxPeers];
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; ++q) sl[q] = __shfl_sync(kFull, slot[q], src);
-      if (l >= 0) {
-        for (int c = sub; c < t.d4; c += 8) {
-          float4 acc = zero4();
+      for (int q = 0; q < kMaxPeers; ++q) sl[q] = __shfl_sync(kFull, slot[q], l);
+      for (int c = lane; c < t.d4; c += 32) {
+        float4 acc = zero4();
 #pragma unroll
-          for (int q = 0; q < kMaxPeers; ++q) {
-            if (sl[q] >= 0) {
-              const float4 v = ldg_row4(t.vals[q] + static_cast<int64_t>(sl[q]) * t.d4 + c);
-              acc.x += v.x;
-              acc.y += v.y;
-              acc.z += v.z;
-              acc.w += v.w;
-            }
+        for (int q = 0; q < kMaxPeers; ++q) {
+          if (sl[q] >= 0) {
+            const float4 v = ldg_row4(t.vals[q] + static_cast<int64_t>(sl[q]) * t.d4 + c);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
           }
-          acc.x *= a.scale;
-          acc.y *= a.scale;
-          acc.z *= a.scale;
-          acc.w *= a.scale;
-          t.dense[row * t.d4 + c] = acc;
         }
-        if (t.touched != nullptr && sub == 0) t.touched[atomicAdd(t.n_touched, 1)] = static_cast<int32_t>(row);
+        acc.x *= a.scale;
+        acc.y *= a.scale;
+        acc.z *= a.scale;
+        acc.w *= a.scale;
+        t.dense[row * t.d4 + c] = acc;
       }
+      if (t.touched != nullptr && lane == 0) t.touched[atomicAdd(t.n_touched, 1)] = static_cast<int32_t>(row);
     }
   }
 }
