@@ -624,7 +624,18 @@ extern "C" int psb_peer_fold_lists(const psb_fold_table_t* tables, int32_t n_tab
     peer_fold_kernel<false><<<grid, 256, 0, s>>>(a);
     if ((st = launch_status()) != PSB_OK) return st;
   }
-  a.entries_per_warp = 4 * G < 32 ? 4 * G : 32;
+  {   // entries per warp and iteration (~1 / G of them are folded here, one after the other): PSB_PEER_FOLD_E overrides
+    static int e_env = -1;
+    if (e_env < 0) {
+      const char* e = getenv("PSB_PEER_FOLD_E");
+      e_env = e != nullptr ? atoi(e) : 0;
+    }
+    // measured at N = 8 (profiles/r02C_bench_n8_E*.json): 32 entries 55 us / 0.502 ms per step, 16 entries 45 us /
+    // 0.484 ms, 8 entries 50 us / 0.489 ms -> about two leaders per warp and iteration
+    int e_auto = 2 * G < 32 ? 2 * G : 32;
+    if (e_auto < 8) e_auto = 8;
+    a.entries_per_warp = (e_env >= 2 && e_env <= 32) ? e_env : e_auto;
+  }
   dim3 grid(grid_for(cap_max, 8 * a.entries_per_warp, 2), n_tables, G);
   PSB_PROF("peer_fold_sum_kernel", s);
   peer_fold_kernel<true><<<grid, 256, 0, s>>>(a);
