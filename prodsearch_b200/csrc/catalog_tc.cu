@@ -21,6 +21,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include "catalog_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -1524,10 +1526,12 @@ static int tc16_lists_per_slice(int MT) {
   }
 }
 
+constexpr int kMaxSegs = 8;
 struct Tc16Plan {
   int m_tiles, groups, MT, TN, m_pad, n_slices, total_tiles, pilot_tiles, pilot_step, cap, stages;
   int lists;    // candidate lists per (row, slice)
-  int seg[3];   // main-pass segment ends in tiles: [0, seg0) | [seg0, seg1) | [seg1, total)
+  int seg[kMaxSegs];   // main-pass segment ends in tiles: [0, seg0) | [seg0, seg1) | ... | [seg(nseg-2), total)
+  int nseg;
   int final_cap; // candidates per row the select kernels hold in shared memory (4x the expectation: several CTAs / SM)
   size_t smem;
   int64_t off_thr, off_eps, off_epsin, off_flag, off_cand_n, off_q16, off_dump, off_cand_s, off_cand_i, total;
@@ -1550,16 +1554,60 @@ static Tc16Plan plan16_for(int64_t m, int64_t n_items, int64_t d, int64_t k) {
   p.pilot_tiles = 8192 / p.TN;
   if (p.pilot_tiles > p.total_tiles) p.pilot_tiles = p.total_tiles;
   p.pilot_step = p.total_tiles / p.pilot_tiles;
-  p.seg[0] = static_cast<int>(10ll * 8192 / p.TN);             // ~80k items at the pilot threshold
-  p.seg[1] = p.seg[0] + static_cast<int>(40ll * 8192 / p.TN);  // ~320k items at the first refinement
-  if (p.seg[0] > p.total_tiles) p.seg[0] = p.total_tiles;
-  if (p.seg[1] > p.total_tiles) p.seg[1] = p.total_tiles;
-  p.seg[2] = p.total_tiles;
-  // expected candidates per row: k * (seg0 / pilot + (seg1 - seg0) / seg0 + (total - seg1) / seg1)
+  // Main-pass segments: the threshold of segment j is the k-th best of everything seen before it, so a segment that
+  // is `ratio` times what has been seen yields ~k * ratio candidates per row -- and every candidate costs epilogue
+  // slow-path work that grows with the number of queries, while every extra segment costs a refine launch (~25-55 us).
+  // Measured at 1M / 2M items (profiles/tc16_segs.py): dropping the middle segment (2150 instead of 1550 candidates
+  // per row) costs +33 us at 384 queries and +0.32 ms at 4096, but saves 17 us at 24.  Hence: few queries -> one
+  // refinement; a few hundred -> first segment 10x the pilot, then 5x steps; thousands -> 3x steps from the start.
+  // PSB_TC16_SCHED="r0:r" overrides (r = 0: no further refinement); read once.
+  // (profiles/r02D_tc16_sched.jsonl: 1M items, 4096 queries 2.02 -> 1.90 ms with 3x steps; 24 queries 0.163 -> 0.143 ms
+  // with one refinement -- but only on small tables: at 16M one refinement leaves 18k candidates per row, the lists
+  // overflow and the exact fallback answers, 341 ms)
+  const bool small_table = n_items <= 2500000;
+  int r0 = m <= 1024 ? 10 : 3, r = m <= 64 ? (small_table ? 0 : 5) : (m <= 1024 ? 5 : 3);
+  {
+    static int e_r0 = -1, e_r = -1;
+    if (e_r0 < 0) {
+      const char* e = getenv("PSB_TC16_SCHED");
+      e_r0 = 0;
+      e_r = 0;
+      if (e != nullptr) {
+        e_r0 = atoi(e);
+        const char* c = strchr(e, ':');
+        e_r = c != nullptr ? atoi(c + 1) : 0;
+        if (e_r0 < 2 || e_r0 > 64) e_r0 = 0;
+      }
+    }
+    if (e_r0 > 0) {
+      r0 = e_r0;
+      r = e_r;
+    }
+  }
+  p.nseg = 0;
+  {
+    int64_t end = static_cast<int64_t>(r0) * 8192 / p.TN;
+    while (p.nseg < kMaxSegs - 1 && end < p.total_tiles) {
+      p.seg[p.nseg++] = static_cast<int>(end);
+      if (r < 2) break;
+      // the last refinement must still pay for itself: stop when what is left is less than twice what has been seen
+      if (p.total_tiles - end < 2 * end && p.nseg >= 2) break;
+      end *= r;
+    }
+    p.seg[p.nseg++] = p.total_tiles;
+  }
+  // expected candidates per row: k * sum_j (segment j) / (items seen before segment j)
   const double pil = static_cast<double>(p.pilot_tiles);
-  double cands = static_cast<double>(k) * p.seg[0] / pil;
-  if (p.seg[1] > p.seg[0]) cands += static_cast<double>(k) * (p.seg[1] - p.seg[0]) / p.seg[0];
-  if (p.seg[2] > p.seg[1]) cands += static_cast<double>(k) * (p.seg[2] - p.seg[1]) / p.seg[1];
+  double cands = 0.0;
+  {
+    double seen = pil;
+    int lo = 0;
+    for (int j = 0; j < p.nseg; ++j) {
+      cands += static_cast<double>(k) * (p.seg[j] - lo) / seen;
+      seen = p.seg[j];      // (the pilot tiles are part of the table: seen = segment end)
+      lo = p.seg[j];
+    }
+  }
   p.lists = tc16_lists_per_slice(p.MT);
   const double expect = cands / (p.n_slices * p.lists);
   p.cap = (static_cast<int>(2.0 * expect) + 96 + 31) / 32 * 32;
@@ -1741,7 +1789,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
   P.tile_step = 1;
   P.append = 0;
   int seg_lo = 0;
-  for (int sgi = 0; sgi < 3; ++sgi) {
+  for (int sgi = 0; sgi < pl.nseg; ++sgi) {
     const int seg_hi = pl.seg[sgi];
     if (seg_hi > seg_lo) {
       P.tile_begin = seg_lo;
@@ -1749,7 +1797,7 @@ int catalog_topk_tc16(const float* queries, int64_t m, const float* table, const
       const int slices = pl.n_slices;   // the bucket index of a candidate list must not depend on the segment
       if ((st = launch_tc16<false>(pl.MT, dim3(slices, pl.groups), pl.smem, s, map_q, map_e, P)) != PSB_OK) return st;
       P.append = 1;
-      if (sgi < 2 && seg_hi < pl.total_tiles) {
+      if (sgi < pl.nseg - 1 && seg_hi < pl.total_tiles) {
         PSB_PROF("refine_threshold_kernel", s);
         refine_threshold_kernel<<<static_cast<int>(m), 256, static_cast<size_t>(pl.final_cap) * 4, s>>>(
             cand_s, cand_n, pl.n_slices * pl.lists, pl.cap, eps, static_cast<int>(k), thr, pl.final_cap);
