@@ -444,19 +444,22 @@ def bandwidth_regime(peaks, rows=16_000_000, d=128):
     try:
         del prep
         prep16 = ops.catalog_prepare_f16(table, rows)
-        m = 4096
-        q = torch.randn(m, d, device=dev)
         mode, mname = (_lib.TOPK_TC16, "tcgen05_f16") if prep16.fits else (_lib.TOPK_TC, "tcgen05_tf32")
         norm16 = ops.table_max_row_sqnorm(table, rows)
-        sec = timed(lambda: ops.catalog_topk(q, table, 100, n_items=rows, mode=mode, max_row_sqnorm=norm16,
-                                             prepared=prep16 if mode == _lib.TOPK_TC16 else None), 3, warmup=1)
-        flops = 2.0 * m * rows * d
-        out["G5_catalog_topk_16M"] = {
-            "ms": sec * 1e3, "queries": m, "k": 100, "mode": mname, "queries_per_s": m / sec,
-            "tflops": flops / sec / 1e12,
-            "frac_of_tensor_peak": flops / sec / 1e12 / (peaks["bf16"] if mode == _lib.TOPK_TC16 else peaks["bf16"] / 2),
-            "table_GBps": rows * d * (2 if mode == _lib.TOPK_TC16 else 4) * ((m + 511) // 512) / sec / GB,
-            "note": "table_GBps counts one shortlist-table pass per 512 queries"}
+        esz = 2 if mode == _lib.TOPK_TC16 else 4
+        tpeak = peaks["bf16"] if mode == _lib.TOPK_TC16 else peaks["bf16"] / 2
+        for m in (24, 384, 4096):
+            q = torch.randn(m, d, device=dev)
+            sec = timed(lambda: ops.catalog_topk(q, table, 100, n_items=rows, mode=mode, max_row_sqnorm=norm16,
+                                                 prepared=prep16 if mode == _lib.TOPK_TC16 else None), 3, warmup=1)
+            flops = 2.0 * m * rows * d
+            ent = {"ms": sec * 1e3, "queries": m, "k": 100, "mode": mname, "queries_per_s": m / sec,
+                   "tflops": flops / sec / 1e12, "frac_of_tensor_peak": flops / sec / 1e12 / tpeak,
+                   "table_GBps": rows * d * esz * ((m + 511) // 512) / sec / GB,
+                   "frac_of_hbm_peak": rows * d * esz * ((m + 511) // 512) / sec / GB / peaks["hbm"],
+                   "note": "table_GBps counts one shortlist-table pass per 512 queries (M <= 512: the table is streamed "
+                           "once, HBM-bound; thousands of queries: tensor-bound)"}
+            out["G5_catalog_topk_16M" if m == 4096 else "G5_catalog_topk_16M_m%d" % m] = ent
     except RuntimeError as ex:
         out["G5_catalog_topk_16M"] = {"unavailable": str(ex)[:120]}
     return out
@@ -878,10 +881,13 @@ def summarize_regimes(line):
         if isinstance(c1.get(k), dict) and "ms" in c1[k]:
             tab["G5_1M_" + k] = {"ms": round(c1[k]["ms"], 3), "frac_of_tensor_peak": round(c1[k].get("frac_of_tensor_peak", 0.0), 3),
                                  "frac_of_hbm_peak": round(c1[k].get("frac_of_hbm_peak", 0.0), 3)}
-    c16 = bw.get("G5_catalog_topk_16M") or {}
-    if "ms" in c16:
-        tab["G5_16M_m4096"] = {"ms": round(c16["ms"], 2), "tflops": round(c16["tflops"], 0),
-                               "frac_of_tensor_peak": round(c16["frac_of_tensor_peak"], 3)}
+    for key, name in (("G5_catalog_topk_16M_m24", "G5_16M_m24"), ("G5_catalog_topk_16M_m384", "G5_16M_m384"),
+                      ("G5_catalog_topk_16M", "G5_16M_m4096")):
+        c16 = bw.get(key) or {}
+        if "ms" in c16:
+            tab[name] = {"ms": round(c16["ms"], 3), "tflops": round(c16["tflops"], 0),
+                         "frac_of_tensor_peak": round(c16["frac_of_tensor_peak"], 3),
+                         "frac_of_hbm_peak": round(c16.get("frac_of_hbm_peak", 0.0), 3)}
     t16 = ex.get("train_16M") or {}
     for m in ("rowsparse", "rowsparse_aged", "rowsparse_multinomial", "dense"):
         if isinstance(t16.get(m), dict) and "ms_per_step" in t16[m]:
