@@ -201,7 +201,8 @@ int psb_scatter_reduce_rows(const psb_contrib_t* contribs, int32_t n_contribs,
  * its forward pass ends): psb_scatter_sort_rows reads only idx / n of the contributions and leaves the sorted slots,
  * segment table, unique_rows and n_unique in the workspace / outputs; psb_scatter_reduce_sorted, given contributions
  * with the SAME idx / n in the SAME order and the same workspace, runs the segmented reduce.  Together they produce
- * bit for bit what psb_scatter_reduce_rows produces. */
+ * bit for bit what psb_scatter_reduce_rows produces.  ONE reduce per sort: the reduce consumes the workspace (its
+ * list of segments that span work units is appended to, not rebuilt), so sort again before reducing again. */
 int psb_scatter_sort_rows(const psb_contrib_t* contribs /* host; idx and n only */, int32_t n_contribs,
                           int64_t table_rows, int64_t drop_idx, void* workspace, int64_t workspace_bytes,
                           int32_t* unique_rows, int32_t* n_unique, psb_stream_t stream);
