@@ -281,6 +281,10 @@ int psb_debug_tmem_read_bw(int32_t warps, int32_t iters, double* bytes_per_clk);
  * encoder forward uses it for the q and K|V projections when PSB_ENC_TC=1 (off by default: no GPU run yet). */
 int psb_debug_gemm3_tf32(const float* a, int64_t lda, int64_t m, int64_t k, const float* bt, int64_t j,
                          const float* bias, float* out, int64_t ldo, psb_stream_t stream);
+/* Debug aid: with PSB_FT_TRACE=1 in the environment the fused tensor-core encoder tail (tail_fused_tc_kernel,
+ * csrc/gemm3_tf32.cu) stamps %globaltimer (ns) at its phase boundaries in CTA 0; this copies the 32 stamps of the last
+ * launch to the host (synchronising).  PSB_E_UNSUPPORTED when tracing is off. */
+int psb_debug_tail_trace(uint64_t* out32 /* host */);
 
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */

@@ -196,6 +196,14 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float c = 0.7978845608028654f;
   return 0.5f * x * (1.f + tanhf(c * (x + 0.044715f * x * x * x)));
 }
+// The same function as x * sigmoid(2 u), u = sqrt(2/pi) (x + 0.044715 x^3)  [0.5 (1 + tanh u) = 1 / (1 + e^(-2u))] on the
+// special-function unit: ex2.approx + rcp.approx, relative error ~4e-7 (tanhf form: ~1e-7), a third of the instructions.
+// Used where the epilogue of a tensor-core product is the critical path (gemm3_tf32.cu tail_fused_tc_kernel).
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float c2 = -2.f * 0.7978845608028654f * 1.4426950408889634f;      // -2 sqrt(2/pi) log2(e)
+  const float t = c2 * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.f + exp2f(t));
+}
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float c = 0.7978845608028654f;
   const float t = tanhf(c * (x + 0.044715f * x * x * x));
@@ -247,7 +255,11 @@ __host__ inline Saved saved_layout(const Dims& D) {
 
 // forward workspace: transposed weights (float offsets)
 struct FwdWs {
-  size_t wq_t, wkv_t, wo_t, w1_t, w2_t, bkv, total;
+  size_t wq_t, wkv_t, wo_t, w1_t, w2_t, bkv;
+  // operands of the fused tensor-core tail (gemm3_tf32.cu tail_fused_tc_kernel), pre-split into their tf32 hi part and
+  // the exact remainder, hi rows stacked on lo rows: [2][d][d], [2][F][d], [2][d][F] (original layouts), [2][S*C][d]
+  size_t wo_hl, w1_hl, w2_hl, ctx_hl;
+  size_t total;
 };
 __host__ inline FwdWs fwd_ws_layout(const Dims& D) {
   FwdWs W;
@@ -259,6 +271,10 @@ __host__ inline FwdWs fwd_ws_layout(const Dims& D) {
   W.w1_t = p; p += d * F;
   W.w2_t = p; p += F * d;
   W.bkv = p; p += 2 * d;
+  W.wo_hl = p; p += 2 * d * d;
+  W.w1_hl = p; p += 2 * F * d;
+  W.w2_hl = p; p += 2 * d * F;
+  W.ctx_hl = p; p += 2 * static_cast<size_t>(D.S) * D.C * d;
   W.total = p;
   return W;
 }
@@ -288,11 +304,11 @@ int dims_from_cfg(const psb_encoder_cfg_t* cfg, Dims* D);
 size_t tail_bwd_smem_floats(int R, int d, int F, int H, int T, int spt);
 struct TrJob {
   const float* src;  // [rows][cols]
-  float* dst;        // dst[c * ldd + col0 + r]
+  float* dst;        // dst[c * ldd + col0 + r]; split job (ldd < 0): dst[i] = hi(src[i]), dst[rows * cols + i] = src[i] - hi
   int rows, cols, ldd, col0;
 };
 struct TrJobs {
-  TrJob j[8];
+  TrJob j[12];
   int n;
 };
 int launch_transposes(const TrJobs& jobs, cudaStream_t s);   // encoder_fwd.cu: weight transposes, one launch
@@ -317,10 +333,16 @@ struct TailTcArgs {
   float *ctx, *y, *n, *z, *pre1, *h1;            // saved for the backward pass
   float* out;
   const uint64_t* seed_dev;
+  const float *wo_hl, *w1_hl, *w2_hl;            // fused tail only: pre-split weights (FwdWs), written by the transpose launch
+  float* ctx_hl;                                 // fused tail only: pre-split ctx rows
 };
 bool tail_tc_enabled();
 bool tail_tc_supported(const TailTcArgs& a);
 int launch_tail_fwd_tc(const TailTcArgs& a, cudaStream_t s);
+// PSB_ENC_TC=3: ctx kernel + ONE cluster kernel chaining the three products (FFN hidden dimension split over 4 CTAs)
+bool tail_fused_enabled();
+bool tail_fused_supported(const TailTcArgs& a);
+int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s);
 
 }  // namespace enc
 }  // namespace psb

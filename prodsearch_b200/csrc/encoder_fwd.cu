@@ -139,6 +139,22 @@ __global__ void __launch_bounds__(256) transpose_kernel(TrJobs jobs) {
     if (J.src == nullptr) {  // plain copy job: dst[i] = src2 rows (used for bias concat) -- not used
       continue;
     }
+    if (J.ldd < 0) {         // split job: 1024 elements per block
+      const int n = J.rows * J.cols, nb = (n + 1023) / 1024;
+      if (b >= nb) {
+        b -= nb;
+        continue;
+      }
+      const int i = b * 1024 + threadIdx.x * 4;
+      if (i < n) {
+        const float4 v = *reinterpret_cast<const float4*>(J.src + i);
+        const float4 hi = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                      __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<float4*>(J.dst + i) = hi;
+        *reinterpret_cast<float4*>(J.dst + n + i) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+      }
+      return;
+    }
     const int tr = (J.rows + 31) / 32, tc = (J.cols + 31) / 32;
     if (b >= tr * tc) {
       b -= tr * tc;
@@ -160,7 +176,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(TrJobs jobs) {
 }
 inline int tr_blocks(const TrJobs& J) {
   int n = 0;
-  for (int q = 0; q < J.n; ++q) n += ((J.j[q].rows + 31) / 32) * ((J.j[q].cols + 31) / 32);
+  for (int q = 0; q < J.n; ++q)
+    n += J.j[q].ldd < 0 ? (J.j[q].rows * J.j[q].cols + 1023) / 1024 : ((J.j[q].rows + 31) / 32) * ((J.j[q].cols + 31) / 32);
   return n;
 }
 int launch_transposes(const TrJobs& jobs, cudaStream_t s) {
@@ -562,6 +579,12 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(p->w2, ws + W.w2_t, d, F, d, 0);           // W2 [d][F] -> [F][d]
   add(p->bk, ws + W.bkv, d, 1, 2 * d, 0);        // bias concat as 1-column "transposes"
   add(p->bv, ws + W.bkv, d, 1, 2 * d, d);
+  const bool fused_tail = tail_fused_enabled() && d == 128 && F == 512;
+  if (fused_tail) {                                // hi / lo parts of the tail's weights for tail_fused_tc_kernel
+    add(p->wo, ws + W.wo_hl, d, d, -1, 0);
+    add(p->w1, ws + W.w1_hl, F, d, -1, 0);
+    add(p->w2, ws + W.w2_hl, d, F, -1, 0);
+  }
   // the token plan (one CTA) and the weight transposes are independent: side by side
   st = fork_join(
       s, 0,
@@ -624,6 +647,8 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     t.ctx = sv + L.ctx; t.y = sv + L.y; t.n = sv + L.n; t.z = sv + L.z; t.pre1 = sv + L.pre1; t.h1 = sv + L.h1;
     t.out = out;
     t.seed_dev = cfg->seed_dev;
+    t.wo_hl = ws + W.wo_hl; t.w1_hl = ws + W.w1_hl; t.w2_hl = ws + W.w2_hl; t.ctx_hl = ws + W.ctx_hl;
+    if (fused_tail && tail_fused_supported(t)) return launch_tail_fwd_fused(t, s);
     if (tail_tc_supported(t)) return launch_tail_fwd_tc(t, s);
   }
   TailFwdArgs a;

@@ -372,7 +372,7 @@ static int enc_tc_level() {
   if (v < 0) {
     const char* e = getenv("PSB_ENC_TC");
     const int x = e != nullptr ? atoi(e) : 0;
-    v = (x >= 0 && x <= 2) ? x : 0;
+    v = (x >= 0 && x <= 3) ? x : 0;
   }
   return v;
 }
@@ -449,7 +449,7 @@ int launch_rows_gemm_tc(const float* A, int lda, const int32_t* m_dev, int m_hos
 __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __restrict__ nact, const int32_t* __restrict__ off,
                                                        const int32_t* __restrict__ tok, const float* __restrict__ Pw,
                                                        const float* __restrict__ kv, float* __restrict__ ctx,
-                                                       const uint64_t* __restrict__ seed_dev) {
+                                                       const uint64_t* __restrict__ seed_dev, float* __restrict__ ctx_hl = nullptr) {
   const int lane = threadIdx.x & 31;
   const int grow = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (grow >= D.S * D.C) return;
@@ -481,6 +481,12 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
     acc.w = fmaf(w3, v.w, acc.w);
   }
   *reinterpret_cast<float4*>(ctx + static_cast<size_t>(grow) * d + j) = acc;
+  if (ctx_hl != nullptr) {                  // operand of tail_fused_tc_kernel: tf32 hi part, exact remainder S*C rows further
+    float4 hi, lo;
+    g3_split(acc, hi, lo);
+    *reinterpret_cast<float4*>(ctx_hl + static_cast<size_t>(grow) * d + j) = hi;
+    *reinterpret_cast<float4*>(ctx_hl + (static_cast<size_t>(D.S) * D.C + grow) * d + j) = lo;
+  }
 }
 
 bool tail_tc_supported(const TailTcArgs& a) {
@@ -519,8 +525,511 @@ int launch_tail_fwd_tc(const TailTcArgs& a, cudaStream_t s) {
   return g3_launch<128, 32>("gemm3_ffn_down_ln_kernel", a.h1, F, nullptr, SC, SC, F, a.w2, nullptr, 0, d, e3, s);
 }
 
+
+// ------------------------------------------------------------------ forward tail as ONE cluster kernel (PSB_ENC_TC=3)
+// tail_ctx_kernel, then tail_fused_tc_kernel: the three products of the tail (out-projection, FFN up, FFN down) chained
+// inside one launch, the FFN's hidden dimension split over a cluster of 4 CTAs.
+//
+//   cluster = one tile of 128 copy rows; CTA q of the cluster owns hidden columns [128 q, 128 q + 128)
+//   phase 1  acc1 = ctx . Wo^T           (every CTA of the cluster: 128 x 128 x 128, replicated -- it is 1/9 of the flops
+//            and replicating it is cheaper than a broadcast)      epilogue: y, n = LN_ff(y) -> A operand of phase 2
+//   phase 2  acc2 = n . W1[q]^T          epilogue: pre1, h1 = dropout(gelu(pre1)) (saved) -> A operand of phase 3
+//   phase 3  acc3 = h1[:, q] . W2[:, q]^T   (partial sums over this CTA's 128 hidden columns)
+//   reduce   the four partial tiles are summed through distributed shared memory in CTA order 0..3 (deterministic);
+//            CTA q finishes rows [32 q, 32 q + 32): z, out = LN_out(z)
+// One A buffer (128 rows x 128 K as hi + lo tiles, 128 KB) is rewritten by each epilogue in the swizzled K-major layout
+// the next phase's MMAs read -- activations never leave the SM between the products; the 12 weight chunks (128 x 32
+// fp32 each) stream through 3 stages, prefetched across the phases by the TMA warp and split by warps of their own.
+// Every operand is split hi / lo as in gemm3_tf32_kernel (3 MMAs per k-step, corrections in their own accumulator).
+constexpr int kFtThreads = 576;            // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int kFtEpiWarps = 16;            // epilogue warp e = warp - 2: TMEM lane quarter warp % 4, columns [32 (e / 4), + 32)
+constexpr int kFtCluster = 4;
+constexpr uint32_t kFtABytes = 128 * 128 * 4;             // one A tile (hi or lo): 4 swizzle blocks of 16 KB
+constexpr uint32_t kFtBBytes = 128 * 32 * 4;              // one weight chunk (hi or lo)
+constexpr int kFtStages = 3;
+constexpr uint32_t kFtStage = 2 * kFtBBytes;
+constexpr size_t kFtSmem = 2 * kFtABytes + kFtStages * kFtStage + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t kFtIdesc = G3Cfg<128, 32>::kIdesc;
+
+struct FtParams {
+  Dims D;
+  int SC;
+  const float *xo, *bo, *b1, *b2, *ln_ff_g, *ln_ff_b, *ln_out_g, *ln_out_b;
+  float *y, *n, *z, *pre1, *h1, *out;
+  const uint64_t* seed_dev;
+  int exp;                     // PSB_FT_EXP (timing experiments only): 1 = no pre1 / h1 stores, 2 = no gelu
+  unsigned long long* trace;   // PSB_FT_TRACE=1: %globaltimer at the phase boundaries of CTA 0 (psb_debug_tail_trace)
+};
+
+__device__ __forceinline__ void ft_mark(const FtParams& P, int slot) {
+  if (P.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[slot] = t;
+  }
+}
+
+__device__ __forceinline__ uint32_t ft_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void ft_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ft_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps
+__device__ __forceinline__ float4 ft_ld_peer4(uint32_t local_addr, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(cta));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+// float4 chunk c4 (columns 4 c4 .. 4 c4 + 3 of K = 128) of row r inside a K-major 128-byte-swizzled A tile
+__device__ __forceinline__ uint32_t ft_a_off(int r, int c4) {
+  return static_cast<uint32_t>((c4 >> 3) * 16384 + r * 128 + (((c4 & 7) ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void ft_store_a(unsigned char* a_hi, unsigned char* a_lo, int r, int c4, const float4& v) {
+  float4 hi, lo;
+  g3_split(v, hi, lo);
+  const uint32_t o = ft_a_off(r, c4);
+  *reinterpret_cast<float4*>(a_hi + o) = hi;
+  *reinterpret_cast<float4*>(a_lo + o) = lo;
+}
+// accumulator columns [col, col + 32) of this thread's TMEM lane: main + corrections
+// (two 16-column halves: 18 warps leave 96 registers per thread, and 64 transient ones on top of the 32 sums do not fit)
+__device__ __forceinline__ void ft_ld16x2(uint32_t taddr, uint32_t (&v)[16], uint32_t (&w)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(taddr + 128u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ft_ld_acc(uint32_t taddr, float (&v)[32]) {
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t vm[16], vc[16];
+    ft_ld16x2(taddr + static_cast<uint32_t>(h * 16), vm, vc);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[h * 16 + i] = __uint_as_float(vm[i]) + __uint_as_float(vc[i]);
+  }
+}
+// out[row0 + r][c0 + ..] = hi + lo (or the hi tile alone) for rows [4 it0, 4 it1) of the 32 rows x 32 columns block one
+// epilogue warp wrote into the A tiles (rows 32 quarter .., swizzle block kb): 8 lanes read one row's 128 bytes, so every
+// store instruction writes 4 full lines -- the thread = row layout of the accumulators touches 32 lines per instruction
+template <bool kAddLo>
+__device__ __forceinline__ void ft_store_block(const unsigned char* a_hi, const unsigned char* a_lo, int quarter, int kb,
+                                               float* out, int ld, int row0, int c0, int rows_valid, int it0, int it1) {
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 7;
+  for (int it = it0; it < it1; ++it) {
+    const int r = quarter * 32 + it * 4 + (lane >> 3);
+    const uint32_t o = static_cast<uint32_t>(kb * 16384 + r * 128 + j * 16);
+    float4 h = *reinterpret_cast<const float4*>(a_hi + o);
+    if (kAddLo) {
+      const float4 l = *reinterpret_cast<const float4*>(a_lo + o);
+      h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+    }
+    if (row0 + r < rows_valid) *reinterpret_cast<float4*>(out + static_cast<size_t>(row0 + r) * ld + c0 + 4 * (j ^ (r & 7))) = h;
+  }
+}
+// keep bits of elements e .. e + 31 (e % 4 == 0) of dropout stream sid: bit i set = element e + i is kept
+__device__ __forceinline__ uint32_t ft_keep32(const Drop& drop, uint32_t sid, uint64_t e) {
+  uint32_t bits = 0xffffffffu;
+  if (drop.on()) {
+    bits = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 m = drop.mul4(sid, e + i);
+      bits |= (m.x != 0.f ? 1u : 0u) << i | (m.y != 0.f ? 2u : 0u) << i | (m.z != 0.f ? 4u : 0u) << i | (m.w != 0.f ? 8u : 0u) << i;
+    }
+  }
+  return bits;
+}
+
+__global__ void __cluster_dims__(kFtCluster, 1, 1) __launch_bounds__(kFtThreads, 1)
+tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_constant__ CUtensorMap map_wo,
+                     const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                     const FtParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + kFtABytes;
+  unsigned char* bst = smem + 2 * kFtABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst + kFtStages * kFtStage);
+  uint64_t* full = bars;                   // [3] weight chunk (hi + lo) landed
+  uint64_t* empty = bars + 3;              // [3] its MMAs have read it
+  uint64_t* a_ready = bars + 6;            // [3] the A operand of phase p is in place (hi / lo): TMA for p = 0, epilogues after
+  uint64_t* acc_full = bars + 9;           // [3] phase p's accumulators are complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // LayerNorm partial sums are exchanged through the head of the lo tile while no MMA reads it: [2][512] floats
+  float* lnsc = reinterpret_cast<float*>(a_lo);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = static_cast<int>(ft_cluster_rank());
+  const int r0 = (blockIdx.x / kFtCluster) * 128;
+  const int d = 128, F = P.D.F;
+
+  if (threadIdx.x == 0) {
+    ft_mark(P, 0);
+    for (int st = 0; st < kFtStages; ++st) {
+      mbar_init(full + st, 1);
+      mbar_init(empty + st, 1);
+    }
+    mbar_init(a_ready + 0, 1);
+    mbar_init(a_ready + 1, kFtEpiWarps);
+    mbar_init(a_ready + 2, kFtEpiWarps);
+    for (int p = 0; p < 3; ++p) mbar_init(acc_full + p, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ft_mark(P, 1);
+
+  if (warp == 0) {
+    // ===== TMA producer: the ctx tile, then the 12 weight chunks of the three phases; hi rows, lo rows `rows` further =====
+    if (lane == 0) {
+      mbar_expect_tx(a_ready + 0, 2 * kFtABytes);
+      for (int kb = 0; kb < 4; ++kb) {
+        tma_load_2d(a_hi + kb * 16384, &map_ctx, kb * 32, r0, a_ready + 0);
+        tma_load_2d(a_lo + kb * 16384, &map_ctx, kb * 32, P.SC + r0, a_ready + 0);
+      }
+      for (int c = 0; c < 12; ++c) {
+        const int st = c % kFtStages;
+        const uint32_t ph = (c / kFtStages) & 1;
+        mbar_wait(empty + st, ph ^ 1);
+        mbar_expect_tx(full + st, 2 * kFtBBytes);
+        unsigned char* dst = bst + st * kFtStage;
+        const int p = c >> 2, kc = c & 3;
+        if (p == 0) {
+          tma_load_2d(dst, &map_wo, kc * 32, 0, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_wo, kc * 32, d, full + st);
+        } else if (p == 1) {
+          tma_load_2d(dst, &map_w1, kc * 32, q * 128, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_w1, kc * 32, F + q * 128, full + st);
+        } else {
+          tma_load_2d(dst, &map_w2, q * 128 + kc * 32, 0, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_w2, q * 128 + kc * 32, d, full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t leader = g3_elect_one();
+    const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo);
+    for (int p = 0; p < 3; ++p) {
+      mbar_wait(a_ready + p, 0);
+      tc_fence_after();
+      if (lane == 0) ft_mark(P, 3 + 4 * p);
+      const uint32_t t_main = tmem_base + (p == 1 ? 256u : 0u), t_corr = t_main + 128u;
+      for (int kc = 0; kc < 4; ++kc) {
+        const int c = p * 4 + kc;
+        const int st = c % kFtStages;
+        const uint32_t ph = (c / kFtStages) & 1;
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        if (lane == 0 && kc == 0) ft_mark(P, 4 + 4 * p);
+        const uint32_t bbase = smem_u32(bst + st * kFtStage);
+        const uint64_t ah = umma_desc(a_hi_u + kc * 16384), al = umma_desc(a_lo_u + kc * 16384);
+        const uint64_t bh = umma_desc(bbase), bl = umma_desc(bbase + kFtBBytes);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t o = static_cast<uint64_t>(k4 * 2);
+          const uint32_t acc = (kc | k4) != 0 ? 1u : 0u;
+          g3_mma_tf32_if(leader, t_main, ah + o, bh + o, kFtIdesc, acc);
+          g3_mma_tf32_if(leader, t_corr, al + o, bh + o, kFtIdesc, acc);
+          g3_mma_tf32_if(leader, t_corr, ah + o, bl + o, kFtIdesc, 1u);
+        }
+        g3_commit_if(leader, empty + st);
+      }
+      g3_commit_if(leader, acc_full + p);
+      if (lane == 0) ft_mark(P, 5 + 4 * p);
+    }
+  } else {
+    // ===== epilogue warps: thread = (row of the tile, 32 columns) =====
+    const int e = warp - 2;
+    const int quarter = warp & 3;                           // TMEM lanes 32 * (warp % 4) .. + 31
+    const int cg = e >> 2;
+    const int c0 = cg * 32;                                 // first column
+    const int rl = quarter * 32 + lane;                     // row inside the tile
+    const int row = r0 + rl;
+    const bool live = row < P.SC;
+    const bool mine = (lane >> 3) == q && live;             // this CTA stores y / n for rows 8 q .. 8 q + 7 of every quarter
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0);
+    const Drop drop = make_drop(P.seed_dev, P.D.thr, P.D.keep);
+    const size_t base = static_cast<size_t>(row) * d + c0;
+    const size_t fbase = static_cast<size_t>(row) * F + q * 128 + c0;
+    // ---- before the first accumulator exists: everything epilogue 1 needs that does not depend on it
+    //      y = m (acc + bo) + x = m acc + (m bo + x)
+    float cst[32];
+    const uint32_t keep2 = ft_keep32(drop, 2u, base);
+    {
+      const int rs = live ? row : P.SC - 1;                 // rows past the end compute on a valid row, store nothing
+      const float* xr = P.xo + static_cast<size_t>(rs / P.D.C) * d + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(P.bo + c0 + i);
+        const float4 x = *reinterpret_cast<const float4*>(xr + i);
+        cst[i] = fmaf((keep2 >> i) & 1u ? drop.scale : 0.f, b.x, x.x);
+        cst[i + 1] = fmaf((keep2 >> (i + 1)) & 1u ? drop.scale : 0.f, b.y, x.y);
+        cst[i + 2] = fmaf((keep2 >> (i + 2)) & 1u ? drop.scale : 0.f, b.z, x.z);
+        cst[i + 3] = fmaf((keep2 >> (i + 3)) & 1u ? drop.scale : 0.f, b.w, x.w);
+      }
+    }
+    // ---- epilogue 1: y = dropout_2(acc + bo) + x[o];  n = LN_ff(y)
+    mbar_wait(acc_full + 0, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) ft_mark(P, 6);
+    {
+      float v[32];
+      ft_ld_acc(t_addr, v);
+      float s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = fmaf((keep2 >> i) & 1u ? drop.scale : 0.f, v[i], cst[i]);
+        s1 += v[i];
+      }
+      lnsc[cg * 128 + rl] = s1;
+      if (mine) {                                           // (the final step of this CTA re-reads these rows)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(P.y + base + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      ft_epi_sync();
+      const float mean = ((lnsc[rl] + lnsc[128 + rl]) + (lnsc[256 + rl] + lnsc[384 + rl])) / 128.f;
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float a = v[i] - mean;
+        s2 = fmaf(a, a, s2);
+      }
+      lnsc[512 + cg * 128 + rl] = s2;
+      ft_epi_sync();
+      const float var = ((lnsc[512 + rl] + lnsc[640 + rl]) + (lnsc[768 + rl] + lnsc[896 + rl])) / 128.f;
+      const RowStats st{mean, 1.f / sqrtf(var + P.D.eps)};
+      ft_epi_sync();                                        // the scratch lives inside the tile written next
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 nv = ln_apply(make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]), st,
+                                   *reinterpret_cast<const float4*>(P.ln_ff_g + c0 + i),
+                                   *reinterpret_cast<const float4*>(P.ln_ff_b + c0 + i));
+        ft_store_a(a_hi, a_lo, rl, (c0 + i) >> 2, nv);
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready + 1);
+    // off the critical path (the phase-2 MMAs only read the tiles): n = hi + lo, row-contiguous
+    ft_store_block<true>(a_hi, a_lo, quarter, cg, P.n, d, r0, c0, P.SC, 2 * q, 2 * q + 2);
+    // ---- epilogue 2: pre1 = acc + b1;  h1 = dropout_3(gelu(pre1)) for this CTA's 128 hidden columns
+    const uint32_t keep3 = ft_keep32(drop, 3u, fbase);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(P.b1 + q * 128 + c0 + i);
+      cst[i] = b.x; cst[i + 1] = b.y; cst[i + 2] = b.z; cst[i + 3] = b.w;
+    }
+    mbar_wait(acc_full + 1, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) ft_mark(P, 10);
+    {
+      float v[32];
+      ft_ld_acc(t_addr + 256u, v);
+      const float sc = drop.on() ? drop.scale : 1.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        v[i] += cst[i]; v[i + 1] += cst[i + 1]; v[i + 2] += cst[i + 2]; v[i + 3] += cst[i + 3];
+        const float4 h = make_float4((keep3 >> i) & 1u ? gelu_tanh_fast(v[i]) * sc : 0.f,
+                                     (keep3 >> (i + 1)) & 1u ? gelu_tanh_fast(v[i + 1]) * sc : 0.f,
+                                     (keep3 >> (i + 2)) & 1u ? gelu_tanh_fast(v[i + 2]) * sc : 0.f,
+                                     (keep3 >> (i + 3)) & 1u ? gelu_tanh_fast(v[i + 3]) * sc : 0.f);
+        ft_store_a(a_hi, a_lo, rl, (c0 + i) >> 2, h);
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready + 2);
+      // off the critical path, next to the phase-3 MMAs: h1 = hi + lo row-contiguous (pre1 follows at the very end)
+      if (!(P.exp & 1)) ft_store_block<true>(a_hi, a_lo, quarter, cg, P.h1, F, r0, q * 128 + c0, P.SC, 0, 8);
+    }
+    // ---- epilogue 3: this CTA's partial sums of the FFN's second product -> shared memory, [chunk][row] float4
+    mbar_wait(acc_full + 2, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) ft_mark(P, 14);
+    {
+      float v[32];
+      ft_ld_acc(t_addr, v);
+      ft_epi_sync();                                        // every warp has stored its h1 block from the tiles
+      float4* redbuf = reinterpret_cast<float4*>(a_hi);     // the phase-3 MMAs have read the A tiles: reuse
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)                        // [row][32 chunks], chunk ^ row: rows and chunks both conflict-free
+        redbuf[rl * 32 + ((((c0 + i) >> 2) ^ rl) & 31)] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    tc_fence_before();
+  }
+  // ---- CTA q finishes rows [32 q, 32 q + 32): epilogue warp e takes rows 2 e and 2 e + 1, lane = 4 columns (row-contiguous
+  //      loads and stores, LayerNorm sums by warp shuffle); what does not depend on the partial tiles is fetched first.
+  //      Rows 8 q .. 8 q + 7 of every quarter: the rows whose y this CTA stored itself
+  const int fe = warp - 2;
+  float4 yv[2], b2v, gv, bv, fm[2];
+  bool fok[2];
+  if (warp >= 2) {
+    const Drop drop = make_drop(P.seed_dev, P.D.thr, P.D.keep);
+    b2v = *reinterpret_cast<const float4*>(P.b2 + lane * 4);
+    gv = *reinterpret_cast<const float4*>(P.ln_out_g + lane * 4);
+    bv = *reinterpret_cast<const float4*>(P.ln_out_b + lane * 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int fk = fe * 2 + i;
+      const int frow = r0 + (fk >> 3) * 32 + q * 8 + (fk & 7);
+      fok[i] = frow < P.SC;
+      const size_t fb = static_cast<size_t>(frow) * d + lane * 4;
+      yv[i] = fok[i] ? *reinterpret_cast<const float4*>(P.y + fb) : zero4();   // written by this CTA in epilogue 1
+      fm[i] = drop.on() ? drop.mul4(4u, fb) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+  }
+  // every CTA's partial tile is in its shared memory
+  ft_cluster_sync();
+  if (threadIdx.x == 64) ft_mark(P, 15);
+  if (warp >= 2) {
+    const uint32_t red_u = smem_u32(a_hi);
+    float4 pz[2][kFtCluster];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int fk = fe * 2 + i;
+      const int frl = (fk >> 3) * 32 + q * 8 + (fk & 7);
+      const uint32_t addr = red_u + static_cast<uint32_t>((frl * 32 + ((lane ^ frl) & 31)) * 16);
+#pragma unroll
+      for (uint32_t src = 0; src < kFtCluster; ++src) pz[i][src] = ft_ld_peer4(addr, src);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int fk = fe * 2 + i;
+      const size_t fb = static_cast<size_t>(r0 + (fk >> 3) * 32 + q * 8 + (fk & 7)) * d + lane * 4;
+      float4 a = pz[i][0];
+#pragma unroll
+      for (uint32_t src = 1; src < kFtCluster; ++src) {
+        a.x += pz[i][src].x; a.y += pz[i][src].y; a.z += pz[i][src].z; a.w += pz[i][src].w;
+      }
+      a.x = fmaf(a.x + b2v.x, fm[i].x, yv[i].x);
+      a.y = fmaf(a.y + b2v.y, fm[i].y, yv[i].y);
+      a.z = fmaf(a.z + b2v.z, fm[i].z, yv[i].z);
+      a.w = fmaf(a.w + b2v.w, fm[i].w, yv[i].w);
+      if (fok[i]) *reinterpret_cast<float4*>(P.z + fb) = a;
+      const RowStats st = row_stats(a, true, d, P.D.eps);
+      if (fok[i]) *reinterpret_cast<float4*>(P.out + fb) = ln_apply(a, st, gv, bv);
+    }
+  }
+  // ---- pre1 = acc2 + b1, the last saved tensor: the phase-2 accumulators are still in TMEM; staged through the (dead) lo
+  //      tile in the A layout so that the stores are row-contiguous like h1's
+  if (warp >= 2 && !(P.exp & 1)) {
+    const int e = warp - 2, quarter = warp & 3, cg = e >> 2, c0 = cg * 32;
+    const int rl = quarter * 32 + lane;
+    float v[32];
+    tc_fence_after();
+    ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(c0), v);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(P.b1 + q * 128 + c0 + i);
+      *reinterpret_cast<float4*>(a_lo + ft_a_off(rl, (c0 + i) >> 2)) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+    }
+    __syncwarp();
+    ft_store_block<false>(a_lo, a_lo, quarter, cg, P.pre1, F, r0, q * 128 + c0, P.SC, 0, 8);
+    tc_fence_before();
+  }
+  // nobody leaves while a peer may still read its partial tile
+  if (threadIdx.x == 64) ft_mark(P, 16);
+  ft_cluster_sync();
+  if (threadIdx.x == 64) ft_mark(P, 17);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+bool tail_fused_enabled() { return enc_tc_level() >= 3; }
+
+// PSB_FT_TRACE=1: a 32-slot device buffer the kernel's CTA 0 stamps with %globaltimer (read back by psb_debug_tail_trace)
+static unsigned long long* ft_trace_buffer() {
+  static unsigned long long* buf = nullptr;
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("PSB_FT_TRACE");
+    state = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    if (state == 1 && (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) != cudaSuccess ||
+                       cudaMemset(buf, 0, 32 * sizeof(unsigned long long)) != cudaSuccess)) {
+      buf = nullptr;
+    }
+  }
+  return buf;
+}
+
+bool tail_fused_supported(const TailTcArgs& a) {
+  return tail_tc_supported(a) && a.D.F == 128 * kFtCluster && a.D.S * a.D.C > 0 && a.wo_hl != nullptr && a.w1_hl != nullptr &&
+         a.w2_hl != nullptr && a.ctx_hl != nullptr && !misaligned16(a.wo_hl) && !misaligned16(a.w1_hl) &&
+         !misaligned16(a.w2_hl) && !misaligned16(a.ctx_hl);
+}
+
+int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
+  if (!tail_fused_supported(a)) return PSB_E_UNSUPPORTED;
+  const Dims& D = a.D;
+  const int SC = D.S * D.C, d = D.d, F = D.F;
+  int st;
+  static DeviceAttr attr_done;
+  if (attr_done.need()) {
+    cudaError_t e = cudaFuncSetAttribute(tail_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kFtSmem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done.done();
+  }
+  PSB_PROF("tail_ctx_kernel", s);
+  tail_ctx_kernel<<<(SC + 7) / 8, 256, 0, s>>>(D, a.nact, a.off, a.tok, a.P, a.kv, a.ctx, a.seed_dev, a.ctx_hl);
+  if ((st = launch_status()) != PSB_OK) return st;
+  // hi rows stacked on lo rows: one map per operand, the lo tile `rows` further down
+  alignas(64) CUtensorMap map_ctx, map_wo, map_w1, map_w2;
+  if ((st = g3_make_map(&map_ctx, a.ctx_hl, 2 * static_cast<int64_t>(SC), d, d, 128)) != PSB_OK) return st;
+  if ((st = g3_make_map(&map_wo, a.wo_hl, 2 * d, d, d, 128)) != PSB_OK) return st;
+  if ((st = g3_make_map(&map_w1, a.w1_hl, 2 * F, d, d, 128)) != PSB_OK) return st;
+  if ((st = g3_make_map(&map_w2, a.w2_hl, 2 * d, F, F, 128)) != PSB_OK) return st;
+  FtParams P;
+  P.D = D;
+  P.SC = SC;
+  P.xo = a.xo; P.bo = a.bo; P.b1 = a.b1; P.b2 = a.b2;
+  P.ln_ff_g = a.ln_ff_g; P.ln_ff_b = a.ln_ff_b; P.ln_out_g = a.ln_out_g; P.ln_out_b = a.ln_out_b;
+  P.y = a.y; P.n = a.n; P.z = a.z; P.pre1 = a.pre1; P.h1 = a.h1; P.out = a.out;
+  P.seed_dev = a.seed_dev;
+  P.trace = ft_trace_buffer();
+  {
+    const char* e = getenv("PSB_FT_EXP");
+    P.exp = e != nullptr ? atoi(e) : 0;
+  }
+  const unsigned tiles = static_cast<unsigned>((SC + 127) / 128);
+  PSB_PROF("tail_fused_tc_kernel", s);
+  tail_fused_tc_kernel<<<tiles * kFtCluster, kFtThreads, kFtSmem, s>>>(map_ctx, map_wo, map_w1, map_w2, P);
+  return launch_status();
+}
+
 }  // namespace enc
 }  // namespace psb
+
+extern "C" int psb_debug_tail_trace(uint64_t* out32) {
+  unsigned long long* buf = psb::enc::ft_trace_buffer();
+  if (out32 == nullptr) return PSB_E_ARG;
+  if (buf == nullptr) return PSB_E_UNSUPPORTED;
+  const cudaError_t e = cudaMemcpy(out32, buf, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? PSB_OK : static_cast<int>(e);
+}
 
 extern "C" int psb_debug_gemm3_tf32(const float* a, int64_t lda, int64_t m, int64_t k, const float* bt, int64_t j,
                                     const float* bias, float* out, int64_t ldo, psb_stream_t stream) {

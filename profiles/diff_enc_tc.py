@@ -1,11 +1,11 @@
-"""Stage-by-stage comparison of the encoder forward's tensor-core paths (PSB_ENC_TC=1 | 2, csrc/gemm3_tf32.cu) with the
+"""Stage-by-stage comparison of the encoder forward's tensor-core paths (PSB_ENC_TC=1 | 2 | 3, csrc/gemm3_tf32.cu) with the
 default FFMA kernels: the same seeded TEM-layout call (batch 384, 21 positions, d 128, ff 512, 8 heads, 1 + 5 copies,
 dropout 0.1 on a fixed Philox seed) runs once per level in its own subprocess (the knob is read once per process, and
 a tcgen05 hand-off bug hangs), the whole saved-activation buffer is dumped, and every region of it (encoder_common.cuh
 saved_layout) is compared with level 0's: the first region that differs by more than fp32 noise names the stage that
 is wrong -- qv / kv (projections), ctx, y, n (out-projection + LayerNorm), pre1, h1 (FFN up), z, out (FFN down + LN).
 
-    timeout 300 python profiles/diff_enc_tc.py          # one JSON line per (level, region)"""
+    timeout 300 python profiles/diff_enc_tc.py [levels]  # one JSON line per (level, region)"""
 import json
 import os
 import subprocess
@@ -80,7 +80,8 @@ if __name__ == "__main__":
     base = run(0, os.path.join(tmp, "l0.npz"))
     ok = base is not None
     L = layout()
-    for level in (1, 2):
+    levels = [int(x) for x in sys.argv[1:]] or [1, 2, 3]
+    for level in levels:
         got = run(level, os.path.join(tmp, "l%d.npz" % level)) if ok else None
         if got is None:
             ok = False
