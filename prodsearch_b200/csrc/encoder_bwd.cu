@@ -31,9 +31,12 @@ struct TailBwdArgs {
   float *g_h2, *g_pre, *g_o1, *gxo, *g_qlin, *gkv;
   float* lnp;  // [ntile][4][d] : d ln_out_g, d ln_out_b, d ln_ff_g, d ln_ff_b
   const uint64_t* seed_dev;
+  const float *gy_in, *gctx_in;  // tail_bwd_kernel<R, true>: the product chain ran on tcgen05 (gemm3_tf32.cu), [S*C][d] each
 };
 
-template <int R>
+// kAttnOnly: steps (1)..(6) were done by tail_bwd_fused_tc_kernel; gy and g_ctx come from global memory and only the
+// residual sum and the attention backward (7a-c) run here.
+template <int R, bool kAttnOnly = false>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwdArgs a) {
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
@@ -78,6 +81,30 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
     const int s = s0 + sl;
     Ps[e] = (s < D.S && al < a.nact[s]) ? a.P[static_cast<size_t>(a.off[s] + al) * H + h] : 0.f;
   }
+  if constexpr (kAttnOnly) {
+    for (int e = threadIdx.x; e < R * (d >> 2); e += kTailThreads) {
+      const int r = e / (d >> 2), j = (e - r * (d >> 2)) * 4;
+      int s, grow;
+      float4 gy = zero4(), gc = zero4();
+      if (row_seq(r, &s, &grow)) {
+        gy = *reinterpret_cast<const float4*>(a.gy_in + static_cast<size_t>(grow) * d + j);
+        gc = *reinterpret_cast<const float4*>(a.gctx_in + static_cast<size_t>(grow) * d + j);
+      }
+      *reinterpret_cast<float4*>(rowA + r * DP + j) = gy;
+      *reinterpret_cast<float4*>(rowB + r * DP + j) = gc;
+    }
+    __syncthreads();
+    // residual gradient of x[o]: sum of gy over the copies of each sequence (copy order)
+    for (int e = threadIdx.x; e < D.spt * d; e += kTailThreads) {
+      const int sl = e / d, j = e - sl * d;
+      const int s = s0 + sl;
+      if (s < D.S) {
+        float sacc = 0.f;
+        for (int c = 0; c < C; ++c) sacc += rowA[(sl * C + c) * DP + j];
+        a.gxo[static_cast<size_t>(s) * d + j] = sacc;
+      }
+    }
+  } else {
   // (1) LN_out backward, (2) g_h2 = gz * drop4
   float4 pg = zero4(), pb = zero4();
   for (int r = warp; r < R; r += kTailWarps) {
@@ -196,6 +223,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
   __syncthreads();
   tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
   __syncthreads();
+  }
   // (7a) gA[r][h][al] = <g_ctx[r, head h], V[al, head h]>
   for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
     const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
@@ -279,19 +307,19 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
   }
 }
 
-template <int R>
+template <int R, bool kAttnOnly = false>
 static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
   const Dims& D = a.D;
   const size_t smem = tail_bwd_smem_floats(R, D.d, D.F, D.H, D.T, D.spt) * sizeof(float);
   static DeviceAttr configured;
   if (configured.need(smem)) {
-    cudaError_t e = cudaFuncSetAttribute(tail_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tail_bwd_kernel<R, kAttnOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     configured.done(smem);
   }
-  PSB_PROF("tail_bwd_kernel", s);
-  tail_bwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);
+  PSB_PROF(kAttnOnly ? "tail_attn_bwd_kernel" : "tail_bwd_kernel", s);
+  tail_bwd_kernel<R, kAttnOnly><<<D.ntile, kTailThreads, smem, s>>>(a);
   return launch_status();
 }
 
@@ -495,7 +523,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const RedJobs jobs) {
 
 // backward workspace (float offsets)
 struct BwdWs {
-  size_t wkv, g_h2, g_pre, g_o1, gxo, g_qlin, gxno, gkv, gxn, lnp_t, lnp_e;
+  size_t wkv, g_h2, g_pre, g_o1, gxo, g_qlin, gxno, gkv, gxn, lnp_t, lnp_e, gy, g_ctx;
   size_t pw[6], pb[6];
   size_t total;
 };
@@ -512,7 +540,10 @@ static BwdWs bwd_ws_layout(const Dims& D) {
   W.gxno = p; p += S * d;
   W.gkv = p; p += S * T * 2 * d;
   W.gxn = p; p += S * T * d;
-  W.lnp_t = p; p += static_cast<size_t>(D.ntile) * 4 * d;
+  const size_t nparts = static_cast<size_t>(D.ntile) > ((SC + 127) / 128) * 4 ? static_cast<size_t>(D.ntile) : ((SC + 127) / 128) * 4;
+  W.lnp_t = p; p += nparts * 4 * d;   // tail_bwd_kernel: one row per tile; tail_bwd_fused_tc_kernel: 4 per 128 rows
+  W.gy = p; p += SC * d;
+  W.g_ctx = p; p += SC * d;
   W.lnp_e = p; p += S * 2 * d;
   const size_t nch_c = (SC + kChunk - 1) / kChunk, nch_t = (S * T + kChunk - 1) / kChunk, nch_s = (S + kChunk - 1) / kChunk;
   const size_t N[6] = {d, F, d, d, d, d}, K[6] = {F, d, d, d, d, d}, nch[6] = {nch_c, nch_c, nch_c, nch_t, nch_t, nch_s};
@@ -572,8 +603,8 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   if (tc_gxn) {
     TrJobs jobs;
     jobs.n = 0;
-    jobs.j[jobs.n++] = TrJob{p->wk, ws + W.wkv, d, d, 2 * d, 0};
-    jobs.j[jobs.n++] = TrJob{p->wv, ws + W.wkv, d, d, 2 * d, d};
+    jobs.j[jobs.n++] = TrJob{p->wk, ws + W.wkv, d, d, 2 * d, 0, 0};
+    jobs.j[jobs.n++] = TrJob{p->wv, ws + W.wkv, d, d, 2 * d, d, 0};
     int st0 = launch_transposes(jobs, s);
     if (st0 != PSB_OK) return st0;
   } else {
@@ -596,7 +627,26 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   a.gkv = ws + W.gkv;
   a.lnp = ws + W.lnp_t;
   a.seed_dev = cfg->seed_dev;
-  st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
+  a.gy_in = nullptr; a.gctx_in = nullptr;
+  int ln_parts = D.ntile;
+  TailBwdTcArgs tb;
+  tb.D = D;
+  tb.z = sv + L.z; tb.gout = grad_out; tb.y = sv + L.y; tb.pre1 = sv + L.pre1;
+  tb.ln_out_g = p->ln_out_g; tb.ln_ff_g = p->ln_ff_g;
+  tb.wot_hl = sv + L.wot_hl; tb.w1t_hl = sv + L.w1t_hl; tb.w2t_hl = sv + L.w2t_hl;
+  tb.g_h2 = a.g_h2; tb.g_pre = a.g_pre; tb.g_o1 = a.g_o1; tb.gy = ws + W.gy; tb.g_ctx = ws + W.g_ctx;
+  tb.lnp = a.lnp;
+  tb.seed_dev = cfg->seed_dev;
+  if (tail_bwd_fused_enabled() && tail_bwd_fused_supported(tb)) {
+    // PSB_ENC_TC=4: the product chain on tcgen05 (gemm3_tf32.cu), then the attention backward from gy / g_ctx
+    if ((st = launch_tail_bwd_fused(tb, s)) != PSB_OK) return st;
+    a.gy_in = tb.gy;
+    a.gctx_in = tb.g_ctx;
+    ln_parts = tail_bwd_fused_parts(D);
+    st = D.R == 24 ? launch_tail_bwd<24, true>(a, s) : D.R == 20 ? launch_tail_bwd<20, true>(a, s) : launch_tail_bwd<16, true>(a, s);
+  } else {
+    st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
+  }
   if (st != PSB_OK) return st;
 
   // The weight gradients depend on the tail kernel's outputs only (and, with pre_ln, on embed_bwd's LayerNorm
@@ -681,7 +731,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     red(P.part_b, gb[i], P.N, P.N, P.m_dev, P.m_host, kChunk);
   }
   float* lnt[4] = {gr->ln_out_g, gr->ln_out_b, gr->ln_ff_g, gr->ln_ff_b};
-  for (int i = 0; i < 4; ++i) red(ws + W.lnp_t + static_cast<size_t>(i) * d, lnt[i], d, 4 * d, nullptr, D.ntile, 1);
+  for (int i = 0; i < 4; ++i) red(ws + W.lnp_t + static_cast<size_t>(i) * d, lnt[i], d, 4 * d, nullptr, ln_parts, 1);
   if (D.pre_ln) {
     red(ws + W.lnp_e, gr->ln_attn_g, d, 2 * d, nullptr, D.S, 1);
     red(ws + W.lnp_e + d, gr->ln_attn_b, d, 2 * d, nullptr, D.S, 1);

@@ -227,6 +227,10 @@ struct Saved {
   size_t xo, xno, qv;               // [S,d]
   size_t xn, kv, p;                 // compact token rows: [S*T,d], [S*T,2d], [S*T,H]
   size_t ctx, y, n, z, pre1, h1;    // [S*C,d] x4, [S*C,F] x2
+  // transposed tail weights for the tensor-core backward tail (gemm3_tf32.cu tail_bwd_fused_tc_kernel), split into tf32
+  // hi part and exact remainder, hi rows stacked on lo rows: Wo^T [2][d][d], W1^T [2][d][F], W2^T [2][F][d].  Written by
+  // the forward pass's transpose launch (they are this step's weights) when PSB_ENC_TC >= 3.
+  size_t wot_hl, w1t_hl, w2t_hl;
   size_t total;                     // floats
 };
 __host__ inline size_t align4(size_t x) { return (x + 3) & ~static_cast<size_t>(3); }
@@ -249,6 +253,9 @@ __host__ inline Saved saved_layout(const Dims& D) {
   L.z = p; p += SC * d;
   L.pre1 = p; p += SC * F;
   L.h1 = p; p += SC * F;
+  L.wot_hl = p; p += 2 * d * d;
+  L.w1t_hl = p; p += 2 * d * F;
+  L.w2t_hl = p; p += 2 * F * d;
   L.total = p;
   return L;
 }
@@ -306,9 +313,10 @@ struct TrJob {
   const float* src;  // [rows][cols]
   float* dst;        // dst[c * ldd + col0 + r]; split job (ldd < 0): dst[i] = hi(src[i]), dst[rows * cols + i] = src[i] - hi
   int rows, cols, ldd, col0;
+  int split;         // transpose job only: 1 = dst gets the tf32 hi part, dst + rows * cols the exact remainder
 };
 struct TrJobs {
-  TrJob j[12];
+  TrJob j[16];
   int n;
 };
 int launch_transposes(const TrJobs& jobs, cudaStream_t s);   // encoder_fwd.cu: weight transposes, one launch
@@ -343,6 +351,21 @@ int launch_tail_fwd_tc(const TailTcArgs& a, cudaStream_t s);
 bool tail_fused_enabled();
 bool tail_fused_supported(const TailTcArgs& a);
 int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s);
+// PSB_ENC_TC=4: the backward tail's product chain (LN_out' -> W2' -> gelu' -> W1' -> LN_ff' -> Wo') as ONE cluster kernel
+// in the transposed form (weights are the M operand, the 128 copy rows the N operand: every global access of the
+// epilogues runs along a row); the attention backward then reads gy / g_ctx from global memory (tail_bwd_kernel<R, true>)
+struct TailBwdTcArgs {
+  Dims D;
+  const float *z, *gout, *y, *pre1, *ln_out_g, *ln_ff_g;
+  const float *wot_hl, *w1t_hl, *w2t_hl;
+  float *g_h2, *g_pre, *g_o1, *gy, *g_ctx;
+  float* lnp;                                    // [4 * tiles][4][d]
+  const uint64_t* seed_dev;
+};
+bool tail_bwd_fused_enabled();
+int tail_bwd_fused_parts(const Dims& D);         // LayerNorm partial rows the kernel writes (4 per 128-row tile)
+bool tail_bwd_fused_supported(const TailBwdTcArgs& a);
+int launch_tail_bwd_fused(const TailBwdTcArgs& a, cudaStream_t s);
 
 }  // namespace enc
 }  // namespace psb

@@ -169,7 +169,17 @@ __global__ void __launch_bounds__(256) transpose_kernel(TrJobs jobs) {
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
       const int c = c0 + i, r = r0 + tx;
-      if (r < J.rows && c < J.cols) J.dst[static_cast<size_t>(c) * J.ldd + J.col0 + r] = tile[tx][i];
+      if (r < J.rows && c < J.cols) {
+        const float v = tile[tx][i];
+        float* o = J.dst + static_cast<size_t>(c) * J.ldd + J.col0 + r;
+        if (J.split) {
+          const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+          o[0] = hi;
+          o[static_cast<size_t>(J.rows) * J.cols] = v - hi;
+        } else {
+          o[0] = v;
+        }
+      }
     }
     return;
   }
@@ -569,7 +579,7 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   TrJobs jobs;
   jobs.n = 0;
   auto add = [&](const float* src, float* dst, int rows, int cols, int ldd, int col0) {
-    jobs.j[jobs.n++] = TrJob{src, dst, rows, cols, ldd, col0};
+    jobs.j[jobs.n++] = TrJob{src, dst, rows, cols, ldd, col0, 0};
   };
   add(p->wq, ws + W.wq_t, d, d, d, 0);           // Wq [n][k] -> Wq_t [k][n]
   add(p->wk, ws + W.wkv_t, d, d, 2 * d, 0);      // [Wk^T | Wv^T] : [k][2d]
@@ -584,6 +594,10 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     add(p->wo, ws + W.wo_hl, d, d, -1, 0);
     add(p->w1, ws + W.w1_hl, F, d, -1, 0);
     add(p->w2, ws + W.w2_hl, d, F, -1, 0);
+    // ... and, for the backward pass, of their transposes (kept with the saved activations)
+    jobs.j[jobs.n++] = TrJob{p->wo, sv + L.wot_hl, d, d, d, 0, 1};
+    jobs.j[jobs.n++] = TrJob{p->w1, sv + L.w1t_hl, F, d, F, 0, 1};
+    jobs.j[jobs.n++] = TrJob{p->w2, sv + L.w2t_hl, d, F, d, 0, 1};
   }
   // the token plan (one CTA) and the weight transposes are independent: side by side
   st = fork_join(

@@ -372,7 +372,7 @@ static int enc_tc_level() {
   if (v < 0) {
     const char* e = getenv("PSB_ENC_TC");
     const int x = e != nullptr ? atoi(e) : 0;
-    v = (x >= 0 && x <= 3) ? x : 0;
+    v = (x >= 0 && x <= 4) ? x : 0;
   }
   return v;
 }
@@ -1017,6 +1017,396 @@ int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
   const unsigned tiles = static_cast<unsigned>((SC + 127) / 128);
   PSB_PROF("tail_fused_tc_kernel", s);
   tail_fused_tc_kernel<<<tiles * kFtCluster, kFtThreads, kFtSmem, s>>>(map_ctx, map_wo, map_w1, map_w2, P);
+  return launch_status();
+}
+
+
+// ------------------------------------------------------------------ backward tail as ONE cluster kernel (PSB_ENC_TC=4)
+// encoder_bwd.cu tail_bwd_kernel steps (1)..(6) on tcgen05, TRANSPOSED: the weights are the M operand (128 output
+// features = TMEM lanes) and the tile's 128 copy rows the N operand (TMEM columns), so a thread of the epilogue owns one
+// feature for 32 rows and every global load / store of the epilogues runs along a row (coalesced), and the activation
+// tiles it writes for the next product are conflict-free 4-byte stores.
+//
+//   cluster = one tile of 128 copy rows; CTA q owns hidden columns [128 q, 128 q + 128) and finishes rows 8 e + 2 q + {0, 1}
+//   prologue  gz = LN_out'(gout; z), g_h2 = dropout_4 gz (saved for dW2)                         -> N operand of product 1
+//   product 1 g_h1^T[f, m] = W2^T[f, :] . g_h2[m, :]   (this CTA's 128 hidden columns f)
+//   epilogue  g_pre = g_h1 * gelu'(pre1) * dropout_3 (saved for dW1)                             -> N operand of product 2
+//   product 2 gn^T[i, m] (partial) = W1^T[i, 128 q ..] . g_pre[m, :]
+//   reduce    the four partial tiles through distributed shared memory, CTA order 0..3; for its 32 rows the CTA forms
+//             gy = gz + LN_ff'(gn; y) (-> global, for the attention backward), g_o1 = dropout_2 gy (saved for dWo)
+//   product 3 g_ctx^T[k, m] = Wo^T[k, :] . g_o1[m, :] for those 32 rows only (N = 32: no gather of the rows needed)
+//   LayerNorm parameter partials: one row of lnp per CTA, summed by the backward's reduce kernel.
+struct FbParams {
+  Dims D;
+  int SC;
+  const float *z, *gout, *y, *pre1, *ln_out_g, *ln_ff_g;
+  float *g_h2, *g_pre, *g_o1, *gy, *g_ctx, *lnp;
+  const uint64_t* seed_dev;
+};
+constexpr uint32_t kFbIdesc32 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(32 >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);          // as kFtIdesc with N = 32
+
+// one element (row m of the tile, K index k) of a K-major 128-byte-swizzled tile of `rows_per_block` rows per 32-float block
+__device__ __forceinline__ uint32_t fb_elem_off(int m, int k, int block_bytes) {
+  return static_cast<uint32_t>((k >> 5) * block_bytes + m * 128 + ((((k & 31) >> 2) ^ (m & 7)) << 4) + (k & 3) * 4);
+}
+__device__ __forceinline__ void fb_ld8x2(uint32_t taddr, uint32_t (&v)[8], uint32_t (&w)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "r"(taddr + 128u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// d gelu_tanh(x) / dx through the sigmoid form (encoder_common.cuh gelu_tanh_fast): s = sigmoid(2u), g' = s + x s (1 - s) 2u'
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float c = 0.7978845608028654f;
+  const float x2 = x * x;
+  const float t = -2.f * c * 1.4426950408889634f * (x + 0.044715f * x * x2);
+  const float sg = __fdividef(1.f, 1.f + exp2f(t));
+  return fmaf(x * sg * (1.f - sg), 2.f * c * fmaf(3.f * 0.044715f, x2, 1.f), sg);
+}
+
+__global__ void __cluster_dims__(kFtCluster, 1, 1) __launch_bounds__(kFtThreads, 1)
+tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_constant__ CUtensorMap map_w1t,
+                         const __grid_constant__ CUtensorMap map_wot, const FbParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* t_hi = smem;                       // activation tile (N operand), hi / lo
+  unsigned char* t_lo = smem + kFtABytes;
+  unsigned char* wst = smem + 2 * kFtABytes;        // weight chunk stages (M operand), hi + lo each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + kFtStages * kFtStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 3;
+  uint64_t* a_ready = bars + 6;                     // [3] the activation tile of product p is in place
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = static_cast<int>(ft_cluster_rank());
+  const int tile = blockIdx.x / kFtCluster;
+  const int r0 = tile * 128;
+  const int d = 128, F = P.D.F;
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kFtStages; ++st) {
+      mbar_init(full + st, 1);
+      mbar_init(empty + st, 1);
+    }
+    for (int p = 0; p < 3; ++p) {
+      mbar_init(a_ready + p, kFtEpiWarps);
+      mbar_init(acc_full + p, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // LayerNorm parameter partials of this CTA's rows, per lane (4 columns): ln_out gamma / beta, ln_ff gamma / beta
+  float4 pg_out = zero4(), pb_out = zero4(), pg_ff = zero4(), pb_ff = zero4();
+
+  // Product 3 runs AFTER the reduce, so the TMA and MMA warps cannot wait at the cluster barrier in between: they arrive
+  // for it at once (they never touch a peer's memory) and collect the phase when their loops are done.
+  if (warp < 2) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  if (warp == 0) {
+    // ===== TMA producer: the 12 weight chunks of the three products; hi rows, lo rows `rows` further =====
+    if (lane == 0) {
+      for (int c = 0; c < 12; ++c) {
+        const int st = c % kFtStages;
+        const uint32_t ph = (c / kFtStages) & 1;
+        mbar_wait(empty + st, ph ^ 1);
+        mbar_expect_tx(full + st, 2 * kFtBBytes);
+        unsigned char* dst = wst + st * kFtStage;
+        const int p = c >> 2, kc = c & 3;
+        if (p == 0) {                                       // W2^T [F][d]: rows 128 q .., K = j
+          tma_load_2d(dst, &map_w2t, kc * 32, q * 128, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_w2t, kc * 32, F + q * 128, full + st);
+        } else if (p == 1) {                                // W1^T [d][F]: all rows, K = hidden columns 128 q ..
+          tma_load_2d(dst, &map_w1t, q * 128 + kc * 32, 0, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_w1t, q * 128 + kc * 32, d, full + st);
+        } else {                                            // Wo^T [d][d]
+          tma_load_2d(dst, &map_wot, kc * 32, 0, full + st);
+          tma_load_2d(dst + kFtBBytes, &map_wot, kc * 32, d, full + st);
+        }
+      }
+    }
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[feature, row] += W chunk (M operand) . tile chunk (N operand) =====
+    const uint32_t leader = g3_elect_one();
+    const uint32_t t_hi_u = smem_u32(t_hi), t_lo_u = smem_u32(t_lo);
+    for (int p = 0; p < 3; ++p) {
+      mbar_wait(a_ready + p, 0);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + (p == 1 ? 256u : 0u), t_corr = t_main + 128u;
+      const uint32_t idesc = p == 2 ? kFbIdesc32 : kFtIdesc;
+      // product 3: the 32-row tile sits in the lo tile's memory, 4 KB per K block, hi then lo
+      const uint32_t nb_hi = p == 2 ? t_lo_u : t_hi_u, nb_lo = p == 2 ? t_lo_u + 16384u : t_lo_u;
+      const uint32_t nblk = p == 2 ? 4096u : 16384u;
+      for (int kc = 0; kc < 4; ++kc) {
+        const int c = p * 4 + kc;
+        const int st = c % kFtStages;
+        const uint32_t ph = (c / kFtStages) & 1;
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        const uint32_t wbase = smem_u32(wst + st * kFtStage);
+        const uint64_t wh = umma_desc(wbase), wl = umma_desc(wbase + kFtBBytes);
+        const uint64_t nh = umma_desc(nb_hi + kc * nblk), nl = umma_desc(nb_lo + kc * nblk);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t o = static_cast<uint64_t>(k4 * 2);
+          const uint32_t acc = (kc | k4) != 0 ? 1u : 0u;
+          g3_mma_tf32_if(leader, t_main, wh + o, nh + o, idesc, acc);
+          g3_mma_tf32_if(leader, t_corr, wl + o, nh + o, idesc, acc);
+          g3_mma_tf32_if(leader, t_corr, wh + o, nl + o, idesc, 1u);
+        }
+        g3_commit_if(leader, empty + st);
+      }
+      g3_commit_if(leader, acc_full + p);
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    // ===== the 16 epilogue warps =====
+    const int e = warp - 2;
+    const int quarter = warp & 3;                           // TMEM lanes 32 * (warp % 4) .. + 31
+    const int cg = e >> 2;
+    const int f = quarter * 32 + lane;                      // the feature (TMEM lane) of this thread in the epilogues
+    const Drop drop = make_drop(P.seed_dev, P.D.thr, P.D.keep);
+    const float dscale = drop.on() ? drop.scale : 1.f;
+    // ---- prologue, warp per row (lane = 4 columns): rows 8 e .. 8 e + 7 of the tile
+    {
+      const float4 g = *reinterpret_cast<const float4*>(P.ln_out_g + lane * 4);
+#pragma unroll 2
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = e * 8 + rr, row = r0 + r;
+        const bool live = row < P.SC;
+        const size_t base = static_cast<size_t>(row) * d + lane * 4;
+        const float4 z = live ? *reinterpret_cast<const float4*>(P.z + base) : zero4();
+        const float4 go = live ? *reinterpret_cast<const float4*>(P.gout + base) : zero4();
+        float4 zh;
+        const float4 gz = ln_bwd_row(z, go, g, true, d, P.D.eps, &zh);
+        float4 gh2 = gz;
+        if (drop.on()) {
+          const float4 m = drop.mul4(4u, base);
+          gh2.x *= m.x; gh2.y *= m.y; gh2.z *= m.z; gh2.w *= m.w;
+        }
+        ft_store_a(t_hi, t_lo, r, lane, gh2);
+        if ((rr >> 1) == q && live) {                       // this CTA's rows: saved operand, gz parked in gy, LN partials
+          *reinterpret_cast<float4*>(P.g_h2 + base) = gh2;
+          *reinterpret_cast<float4*>(P.gy + base) = gz;
+          pg_out.x += go.x * zh.x; pg_out.y += go.y * zh.y; pg_out.z += go.z * zh.z; pg_out.w += go.w * zh.w;
+          pb_out.x += go.x; pb_out.y += go.y; pb_out.z += go.z; pb_out.w += go.w;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready + 0);
+    // ---- epilogue 1: thread = hidden column f (of this CTA's 128), rows m = 32 cg .. + 31
+    {
+      float pre[32];
+      const size_t col = static_cast<size_t>(q) * 128 + f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int row = r0 + cg * 32 + i;
+        pre[i] = row < P.SC ? P.pre1[static_cast<size_t>(row) * F + col] : 0.f;
+      }
+      // dropout_3 keep bits of (row, col): one Philox call covers 4 adjacent columns = 4 adjacent lanes; each lane draws
+      // for the rows i % 4 == lane % 4 and the four lanes swap their words
+      uint32_t keep = 0xffffffffu;
+      if (drop.on()) {
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int row = r0 + cg * 32 + 4 * k + (lane & 3);
+          const float4 m = drop.mul4(3u, static_cast<uint64_t>(row) * F + (col & ~static_cast<size_t>(3)));
+          mine |= ((m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u)) << (4 * k);
+        }
+        keep = 0u;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const uint32_t w = __shfl_sync(kFull, mine, (lane & ~3) | s4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) keep |= ((w >> (4 * k + (lane & 3))) & 1u) << (4 * k + s4);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pre[i] = ((keep >> i) & 1u) ? gelu_tanh_grad_fast(pre[i]) * dscale : 0.f;
+      mbar_wait(acc_full + 0, 0);
+      tc_fence_after();
+      float v[32];
+      ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cg * 32), v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int m = cg * 32 + i;
+        const float gp = v[i] * pre[i];
+        const float hi = __uint_as_float(__float_as_uint(gp) & 0xFFFFE000u);
+        const uint32_t o = fb_elem_off(m, f, 16384);
+        *reinterpret_cast<float*>(t_hi + o) = hi;
+        *reinterpret_cast<float*>(t_lo + o) = gp - hi;
+        v[i] = gp;
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready + 1);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {                        // off the critical path: the saved operand of dW1
+        const int row = r0 + cg * 32 + i;
+        if (row < P.SC) P.g_pre[static_cast<size_t>(row) * F + col] = v[i];
+      }
+    }
+    // ---- epilogue 2: partial gn^T[i = f, m] -> shared memory as [m][i] (row-contiguous for the reduce)
+    mbar_wait(acc_full + 1, 0);
+    tc_fence_after();
+    {
+      float v[32];
+      ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(cg * 32), v);
+      float* redbuf = reinterpret_cast<float*>(t_hi);       // the product-2 MMAs have read the tiles
+#pragma unroll
+      for (int i = 0; i < 32; ++i) redbuf[(cg * 32 + i) * 128 + f] = v[i];
+    }
+    tc_fence_before();
+  }
+  // ---- this CTA's rows: r = 8 e + 2 q + i; what does not depend on the partial tiles first
+  const int fe = warp - 2;
+  float4 yv[2], gzv[2], m2[2], gff;
+  bool fok[2];
+  if (warp >= 2) {
+    const Drop drop = make_drop(P.seed_dev, P.D.thr, P.D.keep);
+    gff = *reinterpret_cast<const float4*>(P.ln_ff_g + lane * 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = r0 + fe * 8 + 2 * q + i;
+      fok[i] = row < P.SC;
+      const size_t base = static_cast<size_t>(row) * d + lane * 4;
+      yv[i] = fok[i] ? *reinterpret_cast<const float4*>(P.y + base) : zero4();
+      gzv[i] = fok[i] ? *reinterpret_cast<const float4*>(P.gy + base) : zero4();    // parked by this warp in the prologue
+      m2[i] = drop.on() ? drop.mul4(2u, base) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    ft_cluster_sync();                                      // every CTA's partial tile is in its shared memory
+  }
+  if (warp >= 2) {
+    const uint32_t red_u = smem_u32(t_hi);
+    float4 pz[2][kFtCluster];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t addr = red_u + static_cast<uint32_t>(((fe * 8 + 2 * q + i) * 128 + lane * 4) * 4);
+#pragma unroll
+      for (uint32_t src = 0; src < kFtCluster; ++src) pz[i][src] = ft_ld_peer4(addr, src);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int li = fe * 2 + i;                            // row of the 32-row tile of product 3
+      const size_t base = static_cast<size_t>(r0 + fe * 8 + 2 * q + i) * d + lane * 4;
+      float4 gn = pz[i][0];
+#pragma unroll
+      for (uint32_t src = 1; src < kFtCluster; ++src) {
+        gn.x += pz[i][src].x; gn.y += pz[i][src].y; gn.z += pz[i][src].z; gn.w += pz[i][src].w;
+      }
+      float4 yh;
+      const float4 gl = ln_bwd_row(yv[i], gn, gff, true, d, P.D.eps, &yh);
+      float4 go1 = zero4();
+      if (fok[i]) {
+        pg_ff.x += gn.x * yh.x; pg_ff.y += gn.y * yh.y; pg_ff.z += gn.z * yh.z; pg_ff.w += gn.w * yh.w;
+        pb_ff.x += gn.x; pb_ff.y += gn.y; pb_ff.z += gn.z; pb_ff.w += gn.w;
+        const float4 gy = make_float4(gzv[i].x + gl.x, gzv[i].y + gl.y, gzv[i].z + gl.z, gzv[i].w + gl.w);
+        go1 = make_float4(gy.x * m2[i].x, gy.y * m2[i].y, gy.z * m2[i].z, gy.w * m2[i].w);
+        *reinterpret_cast<float4*>(P.gy + base) = gy;
+        *reinterpret_cast<float4*>(P.g_o1 + base) = go1;
+      }
+      float4 hi, lo;
+      g3_split(go1, hi, lo);
+      const uint32_t o = static_cast<uint32_t>((lane >> 3) * 4096 + li * 128 + (((lane & 7) ^ (li & 7)) << 4));
+      *reinterpret_cast<float4*>(t_lo + o) = hi;            // 32-row tile: 4 KB per K block, hi then lo (the lo tile is dead)
+      *reinterpret_cast<float4*>(t_lo + 16384 + o) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready + 2);
+    // LayerNorm parameter partials: per-warp sums -> [16][4][128] floats in the upper half of the lo tile
+    float* sc = reinterpret_cast<float*>(t_lo + 32768);
+    *reinterpret_cast<float4*>(sc + (fe * 4 + 0) * 128 + lane * 4) = pg_out;
+    *reinterpret_cast<float4*>(sc + (fe * 4 + 1) * 128 + lane * 4) = pb_out;
+    *reinterpret_cast<float4*>(sc + (fe * 4 + 2) * 128 + lane * 4) = pg_ff;
+    *reinterpret_cast<float4*>(sc + (fe * 4 + 3) * 128 + lane * 4) = pb_ff;
+    ft_epi_sync();
+    {
+      const int t = threadIdx.x - 64;                       // 0..511 = (parameter, column)
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFtEpiWarps; ++w) acc += sc[w * 512 + t];
+      P.lnp[(static_cast<size_t>(tile) * kFtCluster + q) * 4 * d + t] = acc;
+    }
+    // ---- epilogue 3: g_ctx^T[k, li]: thread = feature k, 8 of the 32 rows
+    const int quarter = warp & 3, cg = fe >> 2;
+    const int k = quarter * 32 + lane;
+    mbar_wait(acc_full + 2, 0);
+    tc_fence_after();
+    uint32_t vm[8], vc[8];
+    __syncwarp();
+    fb_ld8x2(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cg * 8), vm, vc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int li = cg * 8 + i;
+      const int row = r0 + (li >> 1) * 8 + 2 * q + (li & 1);
+      if (row < P.SC) P.g_ctx[static_cast<size_t>(row) * d + k] = __uint_as_float(vm[i]) + __uint_as_float(vc[i]);
+    }
+    tc_fence_before();
+  }
+  // nobody leaves while a peer may still read its partial tile
+  ft_cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+bool tail_bwd_fused_enabled() { return enc_tc_level() >= 4; }
+int tail_bwd_fused_parts(const Dims& D) { return ((D.S * D.C + 127) / 128) * kFtCluster; }
+
+bool tail_bwd_fused_supported(const TailBwdTcArgs& a) {
+  const Dims& D = a.D;
+  if (D.d != 128 || D.F != 128 * kFtCluster || D.S * D.C <= 0) return false;
+  const float* ptrs[] = {a.z, a.gout, a.y, a.pre1, a.ln_out_g, a.ln_ff_g, a.wot_hl, a.w1t_hl, a.w2t_hl,
+                         a.g_h2, a.g_pre, a.g_o1, a.gy, a.g_ctx, a.lnp};
+  for (const float* p : ptrs)
+    if (p == nullptr || misaligned16(p)) return false;
+  return true;
+}
+
+int launch_tail_bwd_fused(const TailBwdTcArgs& a, cudaStream_t s) {
+  if (!tail_bwd_fused_supported(a)) return PSB_E_UNSUPPORTED;
+  const Dims& D = a.D;
+  const int SC = D.S * D.C, d = D.d, F = D.F;
+  int st;
+  static DeviceAttr attr_done;
+  if (attr_done.need()) {
+    cudaError_t e = cudaFuncSetAttribute(tail_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kFtSmem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done.done();
+  }
+  alignas(64) CUtensorMap map_w2t, map_w1t, map_wot;
+  if ((st = g3_make_map(&map_w2t, a.w2t_hl, 2 * F, d, d, 128)) != PSB_OK) return st;
+  if ((st = g3_make_map(&map_w1t, a.w1t_hl, 2 * d, F, F, 128)) != PSB_OK) return st;
+  if ((st = g3_make_map(&map_wot, a.wot_hl, 2 * d, d, d, 128)) != PSB_OK) return st;
+  FbParams P;
+  P.D = D;
+  P.SC = SC;
+  P.z = a.z; P.gout = a.gout; P.y = a.y; P.pre1 = a.pre1; P.ln_out_g = a.ln_out_g; P.ln_ff_g = a.ln_ff_g;
+  P.g_h2 = a.g_h2; P.g_pre = a.g_pre; P.g_o1 = a.g_o1; P.gy = a.gy; P.g_ctx = a.g_ctx; P.lnp = a.lnp;
+  P.seed_dev = a.seed_dev;
+  const unsigned tiles = static_cast<unsigned>((SC + 127) / 128);
+  PSB_PROF("tail_bwd_fused_tc_kernel", s);
+  tail_bwd_fused_tc_kernel<<<tiles * kFtCluster, kFtThreads, kFtSmem, s>>>(map_w2t, map_w1t, map_wot, P);
   return launch_status();
 }
 
