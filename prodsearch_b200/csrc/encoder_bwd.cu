@@ -34,9 +34,7 @@ struct TailBwdArgs {
   const float *gy_in, *gctx_in;  // tail_bwd_kernel<R, true>: the product chain ran on tcgen05 (gemm3_tf32.cu), [S*C][d] each
 };
 
-// kAttnOnly: steps (1)..(6) were done by tail_bwd_fused_tc_kernel; gy and g_ctx come from global memory and only the
-// residual sum and the attention backward (7a-c) run here.
-template <int R, bool kAttnOnly = false>
+template <int R>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwdArgs a) {
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
@@ -81,30 +79,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
     const int s = s0 + sl;
     Ps[e] = (s < D.S && al < a.nact[s]) ? a.P[static_cast<size_t>(a.off[s] + al) * H + h] : 0.f;
   }
-  if constexpr (kAttnOnly) {
-    for (int e = threadIdx.x; e < R * (d >> 2); e += kTailThreads) {
-      const int r = e / (d >> 2), j = (e - r * (d >> 2)) * 4;
-      int s, grow;
-      float4 gy = zero4(), gc = zero4();
-      if (row_seq(r, &s, &grow)) {
-        gy = *reinterpret_cast<const float4*>(a.gy_in + static_cast<size_t>(grow) * d + j);
-        gc = *reinterpret_cast<const float4*>(a.gctx_in + static_cast<size_t>(grow) * d + j);
-      }
-      *reinterpret_cast<float4*>(rowA + r * DP + j) = gy;
-      *reinterpret_cast<float4*>(rowB + r * DP + j) = gc;
-    }
-    __syncthreads();
-    // residual gradient of x[o]: sum of gy over the copies of each sequence (copy order)
-    for (int e = threadIdx.x; e < D.spt * d; e += kTailThreads) {
-      const int sl = e / d, j = e - sl * d;
-      const int s = s0 + sl;
-      if (s < D.S) {
-        float sacc = 0.f;
-        for (int c = 0; c < C; ++c) sacc += rowA[(sl * C + c) * DP + j];
-        a.gxo[static_cast<size_t>(s) * d + j] = sacc;
-      }
-    }
-  } else {
   // (1) LN_out backward, (2) g_h2 = gz * drop4
   float4 pg = zero4(), pb = zero4();
   for (int r = warp; r < R; r += kTailWarps) {
@@ -223,7 +197,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
   __syncthreads();
   tile_epilogue<R, kTailThreads>(red, d, [&](int r, int j, float4 v) { *reinterpret_cast<float4*>(rowB + r * DP + j) = v; });
   __syncthreads();
-  }
   // (7a) gA[r][h][al] = <g_ctx[r, head h], V[al, head h]>
   for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
     const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
@@ -307,19 +280,211 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_bwd_kernel(const TailBwd
   }
 }
 
-template <int R, bool kAttnOnly = false>
+template <int R>
 static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
   const Dims& D = a.D;
   const size_t smem = tail_bwd_smem_floats(R, D.d, D.F, D.H, D.T, D.spt) * sizeof(float);
   static DeviceAttr configured;
   if (configured.need(smem)) {
-    cudaError_t e = cudaFuncSetAttribute(tail_bwd_kernel<R, kAttnOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tail_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     configured.done(smem);
   }
-  PSB_PROF(kAttnOnly ? "tail_attn_bwd_kernel" : "tail_bwd_kernel", s);
-  tail_bwd_kernel<R, kAttnOnly><<<D.ntile, kTailThreads, smem, s>>>(a);
+  PSB_PROF("tail_bwd_kernel", s);
+  tail_bwd_kernel<R><<<D.ntile, kTailThreads, smem, s>>>(a);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------ attention backward on its own (PSB_ENC_TC=4)
+// Steps (7a-c) of tail_bwd_kernel + the residual sum for a tile of spt sequences (R = spt * C copy rows) when the product
+// chain ran on tcgen05 (gemm3_tf32.cu tail_bwd_fused_tc_kernel): gy and g_ctx come from global memory.  Everything the
+// tile reads more than once -- its K | V rows included -- is staged in shared memory with one wave of coalesced loads,
+// the softmax backward runs one warp per (sequence, head) and the grad-q sum four threads per column group, so no
+// phase is a chain of dependent global loads.
+__host__ __device__ inline size_t attn_bwd_smem_floats(int R, int d, int H, int T, int spt) {
+  return 2 * static_cast<size_t>(R) * (d + 4) + 2 * static_cast<size_t>(R) * H * T + 2 * static_cast<size_t>(spt) * H * T +
+         2 * static_cast<size_t>(spt) * T * (d + 4);
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const TailBwdArgs a, const int R) {
+  extern __shared__ float4 smem4[];
+  const Dims& D = a.D;
+  const int d = D.d, H = D.H, T = D.T, C = D.C, dh = D.dh;
+  const int DP = d + 4, HT = H * T, nd4 = d >> 2;
+  float* rowA = reinterpret_cast<float*>(smem4);   // gy
+  float* rowB = rowA + R * DP;                     // g_ctx
+  float* M1 = rowB + R * DP;                       // [R][HT] attention dropout multipliers
+  float* gA = M1 + R * HT;                         // [R][HT]
+  float* Ps = gA + R * HT;                         // [spt][HT]
+  float* gsc = Ps + D.spt * HT;                    // [spt][HT]
+  float* Ks = gsc + D.spt * HT;                    // [spt][T][DP]
+  float* Vs = Ks + D.spt * T * DP;                 // [spt][T][DP]
+  const int s0 = blockIdx.x * D.spt;
+  const int rused = D.spt * C;
+  const Drop drop = make_drop(a.seed_dev, D.thr, D.keep);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  auto row_seq = [&](int r, int* s, int* grow) -> bool {
+    if (r >= rused) return false;
+    const int sl = r / C;
+    *s = s0 + sl;
+    *grow = *s * C + (r - sl * C);
+    return *s < D.S;
+  };
+
+  // (0) one wave of loads: gy / g_ctx rows, K | V rows and P of the tile's sequences, the dropout multipliers
+  for (int e = threadIdx.x; e < R * nd4; e += kTailThreads) {
+    const int r = e / nd4, j = (e - r * nd4) * 4;
+    int s, grow;
+    float4 gy = zero4(), gc = zero4();
+    if (row_seq(r, &s, &grow)) {
+      gy = *reinterpret_cast<const float4*>(a.gy_in + static_cast<size_t>(grow) * d + j);
+      gc = *reinterpret_cast<const float4*>(a.gctx_in + static_cast<size_t>(grow) * d + j);
+    }
+    *reinterpret_cast<float4*>(rowA + r * DP + j) = gy;
+    *reinterpret_cast<float4*>(rowB + r * DP + j) = gc;
+  }
+  for (int e = threadIdx.x; e < D.spt * T * 2 * nd4; e += kTailThreads) {
+    const int sl = e / (T * 2 * nd4), rem = e - sl * (T * 2 * nd4), al = rem / (2 * nd4), c = rem - al * 2 * nd4;
+    const int s = s0 + sl;
+    float4 v = zero4();
+    if (s < D.S && al < a.nact[s]) v = *reinterpret_cast<const float4*>(a.kv + static_cast<size_t>(a.off[s] + al) * 2 * d + c * 4);
+    float* dst = (c < nd4 ? Ks : Vs) + (sl * T + al) * DP + (c < nd4 ? c : c - nd4) * 4;
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+  for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
+    const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
+    int s, grow;
+    float v = 0.f;
+    if (row_seq(r, &s, &grow) && al < a.nact[s])
+      v = drop.on() ? drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h) * T + a.tok[a.off[s] + al]) : 1.f;
+    M1[e] = v;
+  }
+  for (int e = threadIdx.x; e < D.spt * HT; e += kTailThreads) {
+    const int sl = e / HT, rem = e - sl * HT, h = rem / T, al = rem - h * T;
+    const int s = s0 + sl;
+    Ps[e] = (s < D.S && al < a.nact[s]) ? a.P[static_cast<size_t>(a.off[s] + al) * H + h] : 0.f;
+  }
+  __syncthreads();
+  // residual gradient of x[o]: sum of gy over the copies of each sequence (copy order)
+  for (int e = threadIdx.x; e < D.spt * d; e += kTailThreads) {
+    const int sl = e / d, j = e - sl * d;
+    const int s = s0 + sl;
+    if (s < D.S) {
+      float sacc = 0.f;
+      for (int c = 0; c < C; ++c) sacc += rowA[(sl * C + c) * DP + j];
+      a.gxo[static_cast<size_t>(s) * d + j] = sacc;
+    }
+  }
+  // (7a) gA[r][h][al] = <g_ctx[r, head h], V[al, head h]>
+  for (int e = threadIdx.x; e < R * HT; e += kTailThreads) {
+    const int r = e / HT, rem = e - r * HT, h = rem / T, al = rem - h * T;
+    int s, grow;
+    float acc = 0.f;
+    if (row_seq(r, &s, &grow) && al < a.nact[s]) {
+      const float* v = Vs + ((r / C) * T + al) * DP + h * dh;
+      const float* g = rowB + r * DP + h * dh;
+      for (int j = 0; j < dh; ++j) acc = fmaf(g[j], v[j], acc);
+    }
+    gA[e] = acc;
+  }
+  __syncthreads();
+  // (7b) softmax backward, one warp per (sequence, head), lanes along the tokens
+  for (int e = warp; e < D.spt * H; e += kTailWarps) {
+    const int sl = e / H, h = e - sl * H;
+    const int s = s0 + sl;
+    if (s >= D.S) continue;                                  // warp-uniform
+    const int na = a.nact[s], base = a.off[s];
+    float* gs = gsc + sl * HT + h * T;
+    const float* p = Ps + sl * HT + h * T;
+    float dot = 0.f;
+    for (int al = lane; al < na; al += 32) {
+      float gp = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const int r = sl * C + c;
+        gp += gA[r * HT + h * T + al] * M1[r * HT + h * T + al];
+      }
+      gs[al] = gp;
+      dot = fmaf(p[al], gp, dot);
+    }
+    dot = warp_sum(dot);
+    for (int al = lane; al < na; al += 32) {
+      const bool valid = tok_valid(a.ts, s, a.tok[base + al], T);  // masked scores were constants
+      gs[al] = valid ? p[al] * (gs[al] - dot) : 0.f;
+    }
+  }
+  __syncthreads();
+  // (7c) grad K | V rows of the tile's sequences
+  for (int e = threadIdx.x; e < D.spt * T * nd4; e += kTailThreads) {
+    const int sl = e / (T * nd4), rem = e - sl * (T * nd4), al = rem / nd4, j = (rem - al * nd4) * 4;
+    const int s = s0 + sl;
+    if (s >= D.S || al >= a.nact[s]) continue;
+    const int hh[4] = {j / dh, (j + 1) / dh, (j + 2) / dh, (j + 3) / dh};
+    const float4 q = *reinterpret_cast<const float4*>(a.qv + static_cast<size_t>(s) * d + j);
+    const float* gs = gsc + sl * HT;
+    const float4 gk = make_float4(gs[hh[0] * T + al] * q.x, gs[hh[1] * T + al] * q.y, gs[hh[2] * T + al] * q.z,
+                                  gs[hh[3] * T + al] * q.w);
+    float4 gv = zero4();
+    const float* p = Ps + sl * HT;
+    for (int c = 0; c < C; ++c) {
+      const int r = sl * C + c;
+      const float4 g = *reinterpret_cast<const float4*>(rowB + r * DP + j);
+      const float* m = M1 + r * HT;
+      gv.x = fmaf(p[hh[0] * T + al] * m[hh[0] * T + al], g.x, gv.x);
+      gv.y = fmaf(p[hh[1] * T + al] * m[hh[1] * T + al], g.y, gv.y);
+      gv.z = fmaf(p[hh[2] * T + al] * m[hh[2] * T + al], g.z, gv.z);
+      gv.w = fmaf(p[hh[3] * T + al] * m[hh[3] * T + al], g.w, gv.w);
+    }
+    float* dst = a.gkv + static_cast<size_t>(a.off[s] + al) * 2 * d + j;
+    *reinterpret_cast<float4*>(dst) = gk;
+    *reinterpret_cast<float4*>(dst + d) = gv;
+  }
+  // grad q: four threads per (sequence, 4 columns), each every fourth token, combined in fixed order
+  for (int e = threadIdx.x; e < D.spt * nd4 * 4; e += kTailThreads) {
+    const int part = e & 3, sl = (e >> 2) / nd4, j = ((e >> 2) - sl * nd4) * 4;
+    const int s = s0 + sl;
+    const int na = s < D.S ? a.nact[s] : 0;
+    const int hh[4] = {j / dh, (j + 1) / dh, (j + 2) / dh, (j + 3) / dh};
+    const float* gs = gsc + sl * HT;
+    float4 acc = zero4();
+    for (int al = part; al < na; al += 4) {
+      const float4 k = *reinterpret_cast<const float4*>(Ks + (sl * T + al) * DP + j);
+      acc.x = fmaf(gs[hh[0] * T + al], k.x, acc.x);
+      acc.y = fmaf(gs[hh[1] * T + al], k.y, acc.y);
+      acc.z = fmaf(gs[hh[2] * T + al], k.z, acc.z);
+      acc.w = fmaf(gs[hh[3] * T + al], k.w, acc.w);
+    }
+    // (e & 3) are adjacent lanes: parts 0 + 1, 2 + 3, then the pairs
+    acc.x += __shfl_xor_sync(kFull, acc.x, 1); acc.y += __shfl_xor_sync(kFull, acc.y, 1);
+    acc.z += __shfl_xor_sync(kFull, acc.z, 1); acc.w += __shfl_xor_sync(kFull, acc.w, 1);
+    acc.x += __shfl_xor_sync(kFull, acc.x, 2); acc.y += __shfl_xor_sync(kFull, acc.y, 2);
+    acc.z += __shfl_xor_sync(kFull, acc.z, 2); acc.w += __shfl_xor_sync(kFull, acc.w, 2);
+    if (part == 0 && s < D.S) {
+      acc.x *= D.qscale; acc.y *= D.qscale; acc.z *= D.qscale; acc.w *= D.qscale;
+      *reinterpret_cast<float4*>(a.g_qlin + static_cast<size_t>(s) * d + j) = acc;
+    }
+  }
+}
+
+static bool attn_bwd_fits(const Dims& D) {
+  return attn_bwd_smem_floats(D.spt * D.C, D.d, D.H, D.T, D.spt) * sizeof(float) <= 227 * 1024 &&
+         (D.spt * (D.d >> 2) * 4) % 32 == 0;
+}
+
+static int launch_tail_attn_bwd(const TailBwdArgs& a, cudaStream_t s) {
+  const Dims& D = a.D;
+  const int R = D.spt * D.C;
+  const size_t smem = attn_bwd_smem_floats(R, D.d, D.H, D.T, D.spt) * sizeof(float);
+  static DeviceAttr configured;
+  if (configured.need(smem)) {
+    cudaError_t e = cudaFuncSetAttribute(tail_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured.done(smem);
+  }
+  PSB_PROF("tail_attn_bwd_kernel", s);
+  tail_attn_bwd_kernel<<<D.ntile, kTailThreads, smem, s>>>(a, R);
   return launch_status();
 }
 
@@ -637,13 +802,13 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   tb.g_h2 = a.g_h2; tb.g_pre = a.g_pre; tb.g_o1 = a.g_o1; tb.gy = ws + W.gy; tb.g_ctx = ws + W.g_ctx;
   tb.lnp = a.lnp;
   tb.seed_dev = cfg->seed_dev;
-  if (tail_bwd_fused_enabled() && tail_bwd_fused_supported(tb)) {
+  if (tail_bwd_fused_enabled() && tail_bwd_fused_supported(tb) && attn_bwd_fits(D)) {
     // PSB_ENC_TC=4: the product chain on tcgen05 (gemm3_tf32.cu), then the attention backward from gy / g_ctx
     if ((st = launch_tail_bwd_fused(tb, s)) != PSB_OK) return st;
     a.gy_in = tb.gy;
     a.gctx_in = tb.g_ctx;
     ln_parts = tail_bwd_fused_parts(D);
-    st = D.R == 24 ? launch_tail_bwd<24, true>(a, s) : D.R == 20 ? launch_tail_bwd<20, true>(a, s) : launch_tail_bwd<16, true>(a, s);
+    st = launch_tail_attn_bwd(a, s);
   } else {
     st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
   }
