@@ -282,9 +282,10 @@ int psb_debug_tmem_read_bw(int32_t warps, int32_t iters, double* bytes_per_clk);
 int psb_debug_gemm3_tf32(const float* a, int64_t lda, int64_t m, int64_t k, const float* bt, int64_t j,
                          const float* bias, float* out, int64_t ldo, psb_stream_t stream);
 /* Debug aid: with PSB_FT_TRACE=1 in the environment the fused tensor-core encoder tail (tail_fused_tc_kernel,
- * csrc/gemm3_tf32.cu) stamps %globaltimer (ns) at its phase boundaries in CTA 0; this copies the 32 stamps of the last
- * launch to the host (synchronising).  PSB_E_UNSUPPORTED when tracing is off. */
-int psb_debug_tail_trace(uint64_t* out32 /* host */);
+ * csrc/gemm3_tf32.cu) and its backward counterpart (tail_bwd_fused_tc_kernel) stamp %globaltimer (ns) at their phase
+ * boundaries in CTA 0; this copies the 64 stamps of the last launches (forward 0..31, backward 32..63) to the host
+ * (synchronising).  PSB_E_UNSUPPORTED when tracing is off. */
+int psb_debug_tail_trace(uint64_t* out64 /* host */);
 
 /* Merge g per-shard top-k lists (ids [g, m, k], scores [g, m, k], as all_gather
  * lays them out) into the global top-k with the same ordering rule. */

@@ -191,6 +191,53 @@ __device__ __forceinline__ float4 ln_bwd_row(const float4& x, const float4& gy, 
                      st.rstd * (gg.z - m1 - xh.z * m2), st.rstd * (gg.w - m1 - xh.w * m2));
 }
 
+// ln_bwd_row for N rows at once (one warp, lane = 4 columns, d = 128): the N reductions of each stage share their
+// shuffle rounds, so the dependent-shuffle latency is paid three times per batch instead of four times per row.
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(kFull, v[i], o);
+  }
+}
+template <int N>
+__device__ __forceinline__ void ln_bwd_rows(const float4 (&x)[N], const float4 (&gy)[N], const float4& g, int d, float eps,
+                                            float4 (&dx)[N], float4 (&xhat)[N]) {
+  const float inv_d = 1.f / static_cast<float>(d);
+  float s[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  warp_sum_n<N>(s);
+  float mean[N], q[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    mean[i] = s[i] * inv_d;
+    const float a = x[i].x - mean[i], b = x[i].y - mean[i], c = x[i].z - mean[i], e = x[i].w - mean[i];
+    q[i] = (a * a + b * b) + (c * c + e * e);
+  }
+  warp_sum_n<N>(q);
+  float m[2 * N];
+  float4 gg[N];
+  float rstd[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    rstd[i] = 1.f / sqrtf(q[i] * inv_d + eps);
+    xhat[i] = make_float4((x[i].x - mean[i]) * rstd[i], (x[i].y - mean[i]) * rstd[i], (x[i].z - mean[i]) * rstd[i],
+                          (x[i].w - mean[i]) * rstd[i]);
+    gg[i] = make_float4(gy[i].x * g.x, gy[i].y * g.y, gy[i].z * g.z, gy[i].w * g.w);
+    m[2 * i] = (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+    m[2 * i + 1] = (gg[i].x * xhat[i].x + gg[i].y * xhat[i].y) + (gg[i].z * xhat[i].z + gg[i].w * xhat[i].w);
+  }
+  warp_sum_n<2 * N>(m);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float m1 = m[2 * i] * inv_d, m2 = m[2 * i + 1] * inv_d;
+    dx[i] = make_float4(rstd[i] * (gg[i].x - m1 - xhat[i].x * m2), rstd[i] * (gg[i].y - m1 - xhat[i].y * m2),
+                        rstd[i] * (gg[i].z - m1 - xhat[i].z * m2), rstd[i] * (gg[i].w - m1 - xhat[i].w * m2));
+  }
+}
+
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   models/neural.py:7-8
   const float c = 0.7978845608028654f;
@@ -203,6 +250,16 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float c2 = -2.f * 0.7978845608028654f * 1.4426950408889634f;      // -2 sqrt(2/pi) log2(e)
   const float t = c2 * (x + 0.044715f * x * x * x);
   return __fdividef(x, 1.f + exp2f(t));
+}
+// value and derivative from one sigmoid: g = x s, g' = s + x s (1 - s) 2 u'
+__device__ __forceinline__ float gelu_tanh_fast_both(float x, float* grad) {
+  const float c = 0.7978845608028654f;
+  const float x2 = x * x;
+  const float t = -2.f * c * 1.4426950408889634f * (x + 0.044715f * x * x2);
+  const float sg = __fdividef(1.f, 1.f + exp2f(t));
+  const float xs = x * sg;
+  *grad = fmaf(xs * (1.f - sg), 2.f * c * fmaf(3.f * 0.044715f, x2, 1.f), sg);
+  return xs;
 }
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float c = 0.7978845608028654f;

@@ -459,26 +459,39 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
   const int na = nact[s], base = off[s];
   const int h0 = j / dh, h1 = (j + 1) / dh, h2 = (j + 2) / dh, h3 = (j + 3) / dh;
   float4 acc = zero4();
-  for (int al = 0; al < na; ++al) {
-    const float* pw = Pw + static_cast<size_t>(base + al) * H;
-    float w0 = pw[h0], w1 = pw[h1], w2 = pw[h2], w3 = pw[h3];
-    if (drop.on()) {
-      const uint64_t t = static_cast<uint64_t>(tok[base + al]);
-      const float m0 = drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + t);
-      if (h0 == h3) {                       // dh % 4 == 0: the lane's four columns belong to one head -> one draw
-        w0 *= m0; w1 *= m0; w2 *= m0; w3 *= m0;
-      } else {
-        w0 *= m0;
-        w1 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h1) * T + t);
-        w2 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h2) * T + t);
-        w3 *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h3) * T + t);
+  // four tokens per trip: their loads and Philox draws are independent, only the fmaf chain is sequential (and keeps the
+  // token order of tail_fwd_kernel, so the sums are the same bits)
+  for (int a0 = 0; a0 < na; a0 += 4) {
+    float w[4][4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int al = a0 + u < na ? a0 + u : na - 1;
+      const float* pw = Pw + static_cast<size_t>(base + al) * H;
+      w[u][0] = pw[h0]; w[u][1] = pw[h1]; w[u][2] = pw[h2]; w[u][3] = pw[h3];
+      v[u] = *reinterpret_cast<const float4*>(kv + static_cast<size_t>(base + al) * 2 * d + d + j);
+      if (drop.on()) {
+        const uint64_t t = static_cast<uint64_t>(tok[base + al]);
+        const float m0 = drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + t);
+        if (h0 == h3) {                     // dh % 4 == 0: the lane's four columns belong to one head -> one draw
+          w[u][0] *= m0; w[u][1] *= m0; w[u][2] *= m0; w[u][3] *= m0;
+        } else {
+          w[u][0] *= m0;
+          w[u][1] *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h1) * T + t);
+          w[u][2] *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h2) * T + t);
+          w[u][3] *= drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h3) * T + t);
+        }
       }
     }
-    const float4 v = *reinterpret_cast<const float4*>(kv + static_cast<size_t>(base + al) * 2 * d + d + j);
-    acc.x = fmaf(w0, v.x, acc.x);
-    acc.y = fmaf(w1, v.y, acc.y);
-    acc.z = fmaf(w2, v.z, acc.z);
-    acc.w = fmaf(w3, v.w, acc.w);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (a0 + u < na) {
+        acc.x = fmaf(w[u][0], v[u].x, acc.x);
+        acc.y = fmaf(w[u][1], v[u].y, acc.y);
+        acc.z = fmaf(w[u][2], v[u].z, acc.z);
+        acc.w = fmaf(w[u][3], v[u].w, acc.w);
+      }
+    }
   }
   *reinterpret_cast<float4*>(ctx + static_cast<size_t>(grow) * d + j) = acc;
   if (ctx_hl != nullptr) {                  // operand of tail_fused_tc_kernel: tf32 hi part, exact remainder S*C rows further
@@ -558,6 +571,7 @@ struct FtParams {
   float *y, *n, *z, *pre1, *h1, *out;
   const uint64_t* seed_dev;
   int exp;                     // PSB_FT_EXP (timing experiments only): 1 = no pre1 / h1 stores, 2 = no gelu
+  int save_dact;               // the pre1 slot receives dropout_3 . gelu'(pre1) (what the tensor-core backward multiplies by)
   unsigned long long* trace;   // PSB_FT_TRACE=1: %globaltimer at the phase boundaries of CTA 0 (psb_debug_tail_trace)
 };
 
@@ -611,6 +625,31 @@ __device__ __forceinline__ void ft_ld16x2(uint32_t taddr, uint32_t (&v)[16], uin
       : "r"(taddr + 128u));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 values of this thread's TMEM lane written back to columns [taddr, taddr + 32): the forward kernel parks
+// dropout_3 . gelu'(pre1) over the main accumulator of product 2 until the end of the kernel
+__device__ __forceinline__ void ft_st32(uint32_t taddr, const float (&v)[32]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            taddr + static_cast<uint32_t>(h * 16)),
+        "r"(__float_as_uint(v[h * 16 + 0])), "r"(__float_as_uint(v[h * 16 + 1])), "r"(__float_as_uint(v[h * 16 + 2])),
+        "r"(__float_as_uint(v[h * 16 + 3])), "r"(__float_as_uint(v[h * 16 + 4])), "r"(__float_as_uint(v[h * 16 + 5])),
+        "r"(__float_as_uint(v[h * 16 + 6])), "r"(__float_as_uint(v[h * 16 + 7])), "r"(__float_as_uint(v[h * 16 + 8])),
+        "r"(__float_as_uint(v[h * 16 + 9])), "r"(__float_as_uint(v[h * 16 + 10])), "r"(__float_as_uint(v[h * 16 + 11])),
+        "r"(__float_as_uint(v[h * 16 + 12])), "r"(__float_as_uint(v[h * 16 + 13])), "r"(__float_as_uint(v[h * 16 + 14])),
+        "r"(__float_as_uint(v[h * 16 + 15]))
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ft_ld_main(uint32_t taddr, float (&v)[32]) {
+  uint32_t w[32];
+  __syncwarp();
+  tc_ld32(taddr, w);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(w[i]);
+}
 __device__ __forceinline__ void ft_ld_acc(uint32_t taddr, float (&v)[32]) {
   __syncwarp();
 #pragma unroll
@@ -640,6 +679,15 @@ __device__ __forceinline__ void ft_store_block(const unsigned char* a_hi, const 
     if (row0 + r < rows_valid) *reinterpret_cast<float4*>(out + static_cast<size_t>(row0 + r) * ld + c0 + 4 * (j ^ (r & 7))) = h;
   }
 }
+// d gelu_tanh(x) / dx through the sigmoid form (encoder_common.cuh gelu_tanh_fast): s = sigmoid(2u), g' = s + x s (1 - s) 2u'
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float c = 0.7978845608028654f;
+  const float x2 = x * x;
+  const float t = -2.f * c * 1.4426950408889634f * (x + 0.044715f * x * x2);
+  const float sg = __fdividef(1.f, 1.f + exp2f(t));
+  return fmaf(x * sg * (1.f - sg), 2.f * c * fmaf(3.f * 0.044715f, x2, 1.f), sg);
+}
+
 // keep bits of elements e .. e + 31 (e % 4 == 0) of dropout stream sid: bit i set = element e + i is kept
 __device__ __forceinline__ uint32_t ft_keep32(const Drop& drop, uint32_t sid, uint64_t e) {
   uint32_t bits = 0xffffffffu;
@@ -849,13 +897,19 @@ tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_c
       const float sc = drop.on() ? drop.scale : 1.f;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        v[i] += cst[i]; v[i + 1] += cst[i + 1]; v[i + 2] += cst[i + 2]; v[i + 3] += cst[i + 3];
-        const float4 h = make_float4((keep3 >> i) & 1u ? gelu_tanh_fast(v[i]) * sc : 0.f,
-                                     (keep3 >> (i + 1)) & 1u ? gelu_tanh_fast(v[i + 1]) * sc : 0.f,
-                                     (keep3 >> (i + 2)) & 1u ? gelu_tanh_fast(v[i + 2]) * sc : 0.f,
-                                     (keep3 >> (i + 3)) & 1u ? gelu_tanh_fast(v[i + 3]) * sc : 0.f);
-        ft_store_a(a_hi, a_lo, rl, (c0 + i) >> 2, h);
+        float hv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x = v[i + u] + cst[i + u];
+          const float m = (keep3 >> (i + u)) & 1u ? sc : 0.f;
+          float dg;
+          hv[u] = gelu_tanh_fast_both(x, &dg) * m;
+          v[i + u] = P.save_dact ? dg * m : x;
+        }
+        ft_store_a(a_hi, a_lo, rl, (c0 + i) >> 2, make_float4(hv[0], hv[1], hv[2], hv[3]));
       }
+      // with the tensor-core backward the pre1 slot gets dropout_3 . gelu'(pre1): parked over the main accumulator
+      if (P.save_dact) ft_st32(t_addr + 256u, v);
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -932,17 +986,24 @@ tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_c
     }
   }
   // ---- pre1 = acc2 + b1, the last saved tensor: the phase-2 accumulators are still in TMEM; staged through the (dead) lo
-  //      tile in the A layout so that the stores are row-contiguous like h1's
+  //      tile in the A layout so that the stores are row-contiguous like h1's.  With the tensor-core backward
+  //      (save_dact) the slot holds dropout_3 . gelu'(pre1) instead: all the backward pass ever forms from pre1.
   if (warp >= 2 && !(P.exp & 1)) {
     const int e = warp - 2, quarter = warp & 3, cg = e >> 2, c0 = cg * 32;
     const int rl = quarter * 32 + lane;
     float v[32];
     tc_fence_after();
-    ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(c0), v);
+    const uint32_t ta = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(c0);
+    if (P.save_dact) ft_ld_main(ta, v);
+    else ft_ld_acc(ta, v);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(P.b1 + q * 128 + c0 + i);
-      *reinterpret_cast<float4*>(a_lo + ft_a_off(rl, (c0 + i) >> 2)) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+      float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      if (!P.save_dact) {
+        const float4 b = *reinterpret_cast<const float4*>(P.b1 + q * 128 + c0 + i);
+        w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+      }
+      *reinterpret_cast<float4*>(a_lo + ft_a_off(rl, (c0 + i) >> 2)) = w;
     }
     __syncwarp();
     ft_store_block<false>(a_lo, a_lo, quarter, cg, P.pre1, F, r0, q * 128 + c0, P.SC, 0, 8);
@@ -960,15 +1021,16 @@ tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_c
 
 bool tail_fused_enabled() { return enc_tc_level() >= 3; }
 
-// PSB_FT_TRACE=1: a 32-slot device buffer the kernel's CTA 0 stamps with %globaltimer (read back by psb_debug_tail_trace)
+// PSB_FT_TRACE=1: a 64-slot device buffer CTA 0 of the fused tail kernels stamps with %globaltimer (forward: slots 0..31,
+// backward: 32..63; read back by psb_debug_tail_trace)
 static unsigned long long* ft_trace_buffer() {
   static unsigned long long* buf = nullptr;
   static int state = -1;
   if (state < 0) {
     const char* e = getenv("PSB_FT_TRACE");
     state = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    if (state == 1 && (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) != cudaSuccess ||
-                       cudaMemset(buf, 0, 32 * sizeof(unsigned long long)) != cudaSuccess)) {
+    if (state == 1 && (cudaMalloc(&buf, 64 * sizeof(unsigned long long)) != cudaSuccess ||
+                       cudaMemset(buf, 0, 64 * sizeof(unsigned long long)) != cudaSuccess)) {
       buf = nullptr;
     }
   }
@@ -1010,6 +1072,7 @@ int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
   P.y = a.y; P.n = a.n; P.z = a.z; P.pre1 = a.pre1; P.h1 = a.h1; P.out = a.out;
   P.seed_dev = a.seed_dev;
   P.trace = ft_trace_buffer();
+  P.save_dact = tail_bwd_fused_enabled() ? 1 : 0;
   {
     const char* e = getenv("PSB_FT_EXP");
     P.exp = e != nullptr ? atoi(e) : 0;
@@ -1042,7 +1105,15 @@ struct FbParams {
   const float *z, *gout, *y, *pre1, *ln_out_g, *ln_ff_g;
   float *g_h2, *g_pre, *g_o1, *gy, *g_ctx, *lnp;
   const uint64_t* seed_dev;
+  unsigned long long* trace;   // PSB_FT_TRACE=1 (slots 32..63 of the trace buffer)
 };
+__device__ __forceinline__ void fb_mark(const FbParams& P, int slot) {
+  if (P.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[32 + slot] = t;
+  }
+}
 constexpr uint32_t kFbIdesc32 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(32 >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);          // as kFtIdesc with N = 32
 
@@ -1059,15 +1130,6 @@ __device__ __forceinline__ void fb_ld8x2(uint32_t taddr, uint32_t (&v)[8], uint3
                : "r"(taddr + 128u));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// d gelu_tanh(x) / dx through the sigmoid form (encoder_common.cuh gelu_tanh_fast): s = sigmoid(2u), g' = s + x s (1 - s) 2u'
-__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
-  const float c = 0.7978845608028654f;
-  const float x2 = x * x;
-  const float t = -2.f * c * 1.4426950408889634f * (x + 0.044715f * x * x2);
-  const float sg = __fdividef(1.f, 1.f + exp2f(t));
-  return fmaf(x * sg * (1.f - sg), 2.f * c * fmaf(3.f * 0.044715f, x2, 1.f), sg);
-}
-
 __global__ void __cluster_dims__(kFtCluster, 1, 1) __launch_bounds__(kFtThreads, 1)
 tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_constant__ CUtensorMap map_w1t,
                          const __grid_constant__ CUtensorMap map_wot, const FbParams P) {
@@ -1089,6 +1151,7 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
   const int d = 128, F = P.D.F;
 
   if (threadIdx.x == 0) {
+    fb_mark(P, 0);
     for (int st = 0; st < kFtStages; ++st) {
       mbar_init(full + st, 1);
       mbar_init(empty + st, 1);
@@ -1180,67 +1243,53 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
     const int f = quarter * 32 + lane;                      // the feature (TMEM lane) of this thread in the epilogues
     const Drop drop = make_drop(P.seed_dev, P.D.thr, P.D.keep);
     const float dscale = drop.on() ? drop.scale : 1.f;
-    // ---- prologue, warp per row (lane = 4 columns): rows 8 e .. 8 e + 7 of the tile
+    // ---- prologue, warp per row (lane = 4 columns): rows 8 e .. 8 e + 7 of the tile, four at a time
     {
       const float4 g = *reinterpret_cast<const float4*>(P.ln_out_g + lane * 4);
-#pragma unroll 2
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = e * 8 + rr, row = r0 + r;
-        const bool live = row < P.SC;
-        const size_t base = static_cast<size_t>(row) * d + lane * 4;
-        const float4 z = live ? *reinterpret_cast<const float4*>(P.z + base) : zero4();
-        const float4 go = live ? *reinterpret_cast<const float4*>(P.gout + base) : zero4();
-        float4 zh;
-        const float4 gz = ln_bwd_row(z, go, g, true, d, P.D.eps, &zh);
-        float4 gh2 = gz;
-        if (drop.on()) {
-          const float4 m = drop.mul4(4u, base);
-          gh2.x *= m.x; gh2.y *= m.y; gh2.z *= m.z; gh2.w *= m.w;
+#pragma unroll
+      for (int b4 = 0; b4 < 2; ++b4) {
+        float4 z[4], go[4], gz[4], zh[4], mk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = r0 + e * 8 + b4 * 4 + i;
+          const size_t base = static_cast<size_t>(row) * d + lane * 4;
+          z[i] = row < P.SC ? *reinterpret_cast<const float4*>(P.z + base) : zero4();
+          go[i] = row < P.SC ? *reinterpret_cast<const float4*>(P.gout + base) : zero4();
+          mk[i] = drop.on() ? drop.mul4(4u, base) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        ft_store_a(t_hi, t_lo, r, lane, gh2);
-        if ((rr >> 1) == q && live) {                       // this CTA's rows: saved operand, gz parked in gy, LN partials
-          *reinterpret_cast<float4*>(P.g_h2 + base) = gh2;
-          *reinterpret_cast<float4*>(P.gy + base) = gz;
-          pg_out.x += go.x * zh.x; pg_out.y += go.y * zh.y; pg_out.z += go.z * zh.z; pg_out.w += go.w * zh.w;
-          pb_out.x += go.x; pb_out.y += go.y; pb_out.z += go.z; pb_out.w += go.w;
+        ln_bwd_rows<4>(z, go, g, d, P.D.eps, gz, zh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = b4 * 4 + i, r = e * 8 + rr, row = r0 + r;
+          const size_t base = static_cast<size_t>(row) * d + lane * 4;
+          const float4 gh2 = make_float4(gz[i].x * mk[i].x, gz[i].y * mk[i].y, gz[i].z * mk[i].z, gz[i].w * mk[i].w);
+          ft_store_a(t_hi, t_lo, r, lane, gh2);
+          if ((rr >> 1) == q && row < P.SC) {               // this CTA's rows: saved operand, gz parked in gy, LN partials
+            *reinterpret_cast<float4*>(P.g_h2 + base) = gh2;
+            *reinterpret_cast<float4*>(P.gy + base) = gz[i];
+            pg_out.x += go[i].x * zh[i].x; pg_out.y += go[i].y * zh[i].y; pg_out.z += go[i].z * zh[i].z; pg_out.w += go[i].w * zh[i].w;
+            pb_out.x += go[i].x; pb_out.y += go[i].y; pb_out.z += go[i].z; pb_out.w += go[i].w;
+          }
         }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready + 0);
+    if (threadIdx.x == 64) fb_mark(P, 1);
     // ---- epilogue 1: thread = hidden column f (of this CTA's 128), rows m = 32 cg .. + 31
     {
-      float pre[32];
+      float pre[32];                                        // dropout_3 . gelu'(pre1), saved by the forward kernel
       const size_t col = static_cast<size_t>(q) * 128 + f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int row = r0 + cg * 32 + i;
         pre[i] = row < P.SC ? P.pre1[static_cast<size_t>(row) * F + col] : 0.f;
       }
-      // dropout_3 keep bits of (row, col): one Philox call covers 4 adjacent columns = 4 adjacent lanes; each lane draws
-      // for the rows i % 4 == lane % 4 and the four lanes swap their words
-      uint32_t keep = 0xffffffffu;
-      if (drop.on()) {
-        uint32_t mine = 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int row = r0 + cg * 32 + 4 * k + (lane & 3);
-          const float4 m = drop.mul4(3u, static_cast<uint64_t>(row) * F + (col & ~static_cast<size_t>(3)));
-          mine |= ((m.x != 0.f ? 1u : 0u) | (m.y != 0.f ? 2u : 0u) | (m.z != 0.f ? 4u : 0u) | (m.w != 0.f ? 8u : 0u)) << (4 * k);
-        }
-        keep = 0u;
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          const uint32_t w = __shfl_sync(kFull, mine, (lane & ~3) | s4);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) keep |= ((w >> (4 * k + (lane & 3))) & 1u) << (4 * k + s4);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) pre[i] = ((keep >> i) & 1u) ? gelu_tanh_grad_fast(pre[i]) * dscale : 0.f;
+      if (threadIdx.x == 64) fb_mark(P, 2);
       mbar_wait(acc_full + 0, 0);
       tc_fence_after();
+      if (threadIdx.x == 64) fb_mark(P, 3);
       float v[32];
       ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cg * 32), v);
 #pragma unroll
@@ -1257,6 +1306,7 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + 1);
+      if (threadIdx.x == 64) fb_mark(P, 4);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {                        // off the critical path: the saved operand of dW1
         const int row = r0 + cg * 32 + i;
@@ -1264,8 +1314,10 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
       }
     }
     // ---- epilogue 2: partial gn^T[i = f, m] -> shared memory as [m][i] (row-contiguous for the reduce)
+    if (threadIdx.x == 64) fb_mark(P, 5);
     mbar_wait(acc_full + 1, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) fb_mark(P, 6);
     {
       float v[32];
       ft_ld_acc(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>(cg * 32), v);
@@ -1291,7 +1343,9 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
       gzv[i] = fok[i] ? *reinterpret_cast<const float4*>(P.gy + base) : zero4();    // parked by this warp in the prologue
       m2[i] = drop.on() ? drop.mul4(2u, base) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
+    if (threadIdx.x == 64) fb_mark(P, 7);
     ft_cluster_sync();                                      // every CTA's partial tile is in its shared memory
+    if (threadIdx.x == 64) fb_mark(P, 8);
   }
   if (warp >= 2) {
     const uint32_t red_u = smem_u32(t_hi);
@@ -1302,22 +1356,25 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
 #pragma unroll
       for (uint32_t src = 0; src < kFtCluster; ++src) pz[i][src] = ft_ld_peer4(addr, src);
     }
+    float4 gn[2], gl[2], yh[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      gn[i] = pz[i][0];
+#pragma unroll
+      for (uint32_t src = 1; src < kFtCluster; ++src) {
+        gn[i].x += pz[i][src].x; gn[i].y += pz[i][src].y; gn[i].z += pz[i][src].z; gn[i].w += pz[i][src].w;
+      }
+    }
+    ln_bwd_rows<2>(yv, gn, gff, d, P.D.eps, gl, yh);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int li = fe * 2 + i;                            // row of the 32-row tile of product 3
       const size_t base = static_cast<size_t>(r0 + fe * 8 + 2 * q + i) * d + lane * 4;
-      float4 gn = pz[i][0];
-#pragma unroll
-      for (uint32_t src = 1; src < kFtCluster; ++src) {
-        gn.x += pz[i][src].x; gn.y += pz[i][src].y; gn.z += pz[i][src].z; gn.w += pz[i][src].w;
-      }
-      float4 yh;
-      const float4 gl = ln_bwd_row(yv[i], gn, gff, true, d, P.D.eps, &yh);
       float4 go1 = zero4();
       if (fok[i]) {
-        pg_ff.x += gn.x * yh.x; pg_ff.y += gn.y * yh.y; pg_ff.z += gn.z * yh.z; pg_ff.w += gn.w * yh.w;
-        pb_ff.x += gn.x; pb_ff.y += gn.y; pb_ff.z += gn.z; pb_ff.w += gn.w;
-        const float4 gy = make_float4(gzv[i].x + gl.x, gzv[i].y + gl.y, gzv[i].z + gl.z, gzv[i].w + gl.w);
+        pg_ff.x += gn[i].x * yh[i].x; pg_ff.y += gn[i].y * yh[i].y; pg_ff.z += gn[i].z * yh[i].z; pg_ff.w += gn[i].w * yh[i].w;
+        pb_ff.x += gn[i].x; pb_ff.y += gn[i].y; pb_ff.z += gn[i].z; pb_ff.w += gn[i].w;
+        const float4 gy = make_float4(gzv[i].x + gl[i].x, gzv[i].y + gl[i].y, gzv[i].z + gl[i].z, gzv[i].w + gl[i].w);
         go1 = make_float4(gy.x * m2[i].x, gy.y * m2[i].y, gy.z * m2[i].z, gy.w * m2[i].w);
         *reinterpret_cast<float4*>(P.gy + base) = gy;
         *reinterpret_cast<float4*>(P.g_o1 + base) = go1;
@@ -1331,6 +1388,7 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready + 2);
+    if (threadIdx.x == 64) fb_mark(P, 9);
     // LayerNorm parameter partials: per-warp sums -> [16][4][128] floats in the upper half of the lo tile
     float* sc = reinterpret_cast<float*>(t_lo + 32768);
     *reinterpret_cast<float4*>(sc + (fe * 4 + 0) * 128 + lane * 4) = pg_out;
@@ -1348,8 +1406,10 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
     // ---- epilogue 3: g_ctx^T[k, li]: thread = feature k, 8 of the 32 rows
     const int quarter = warp & 3, cg = fe >> 2;
     const int k = quarter * 32 + lane;
+    if (threadIdx.x == 64) fb_mark(P, 10);
     mbar_wait(acc_full + 2, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) fb_mark(P, 11);
     uint32_t vm[8], vc[8];
     __syncwarp();
     fb_ld8x2(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cg * 8), vm, vc);
@@ -1362,7 +1422,9 @@ tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __gr
     tc_fence_before();
   }
   // nobody leaves while a peer may still read its partial tile
+  if (threadIdx.x == 64) fb_mark(P, 12);
   ft_cluster_sync();
+  if (threadIdx.x == 64) fb_mark(P, 13);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -1404,6 +1466,7 @@ int launch_tail_bwd_fused(const TailBwdTcArgs& a, cudaStream_t s) {
   P.z = a.z; P.gout = a.gout; P.y = a.y; P.pre1 = a.pre1; P.ln_out_g = a.ln_out_g; P.ln_ff_g = a.ln_ff_g;
   P.g_h2 = a.g_h2; P.g_pre = a.g_pre; P.g_o1 = a.g_o1; P.gy = a.gy; P.g_ctx = a.g_ctx; P.lnp = a.lnp;
   P.seed_dev = a.seed_dev;
+  P.trace = ft_trace_buffer();
   const unsigned tiles = static_cast<unsigned>((SC + 127) / 128);
   PSB_PROF("tail_bwd_fused_tc_kernel", s);
   tail_bwd_fused_tc_kernel<<<tiles * kFtCluster, kFtThreads, kFtSmem, s>>>(map_w2t, map_w1t, map_wot, P);
@@ -1413,11 +1476,11 @@ int launch_tail_bwd_fused(const TailBwdTcArgs& a, cudaStream_t s) {
 }  // namespace enc
 }  // namespace psb
 
-extern "C" int psb_debug_tail_trace(uint64_t* out32) {
+extern "C" int psb_debug_tail_trace(uint64_t* out64) {
   unsigned long long* buf = psb::enc::ft_trace_buffer();
-  if (out32 == nullptr) return PSB_E_ARG;
+  if (out64 == nullptr) return PSB_E_ARG;
   if (buf == nullptr) return PSB_E_UNSUPPORTED;
-  const cudaError_t e = cudaMemcpy(out32, buf, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  const cudaError_t e = cudaMemcpy(out64, buf, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return e == cudaSuccess ? PSB_OK : static_cast<int>(e);
 }
 

@@ -32,13 +32,22 @@ NAMES = {0: "start", 1: "setup done", 2: "ctx tile landed", 3: "mma: A0 ready", 
          11: "mma: A2 ready", 12: "mma: first chunk split (p2)", 13: "mma: p2 issued", 14: "epi: acc2 full",
          15: "cluster sync 1 passed", 16: "final rows stored", 17: "cluster sync 2 passed"}
 lib = _lib.load()
+BNAMES = {0: "start", 1: "prologue done (tile 0 written)", 2: "epi1: operands ready", 3: "epi1: acc0 full", 4: "epi1: tile 1 written",
+          5: "epi1: g_pre stored", 6: "epi2: acc1 full", 7: "epi2: partial tile written", 8: "cluster sync 1 passed",
+          9: "final rows done (tile 2 written)", 10: "ln partials reduced", 11: "epi3: acc2 full", 12: "g_ctx stored",
+          13: "cluster sync 2 passed"}
+gout = torch.randn(S * copies, d, generator=g).cuda()
 for it in range(4):
     out, call = ops.encoder_fwd(P, heads, first=first, table=table, idx=idx, pad_idx=rows, copies=copies, out_pos=0,
                                 pre_ln=False, p_drop=0.1, seed=seed_t, raw_input=False)
+    bw = ops.encoder_bwd(call, gout, {k: v.shape for k, v in P.items() if not k.startswith("ln_attn")})
     torch.cuda.synchronize()
-    buf = (ctypes.c_uint64 * 32)()
+    buf = (ctypes.c_uint64 * 64)()
     if lib.psb_debug_tail_trace(buf) != 0:          # tracing off (e.g. under ncu): the launches are all this run is for
         continue
     t = np.array(list(buf), dtype=np.int64)
     rel = {NAMES[i]: round(float(t[i] - t[0]) / 1000.0, 2) for i in sorted(NAMES) if t[i] != 0}
     print(json.dumps({"launch": it, "us_since_start": rel}))
+    if t[32] != 0:
+        print(json.dumps({"launch": it, "backward_us_since_start":
+                          {BNAMES[i]: round(float(t[32 + i] - t[32]) / 1000.0, 2) for i in sorted(BNAMES) if t[32 + i] != 0}}))
