@@ -302,11 +302,6 @@ static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
 // tile reads more than once -- its K | V rows included -- is staged in shared memory with one wave of coalesced loads,
 // the softmax backward runs one warp per (sequence, head) and the grad-q sum four threads per column group, so no
 // phase is a chain of dependent global loads.
-__host__ __device__ inline size_t attn_bwd_smem_floats(int R, int d, int H, int T, int spt) {
-  return 2 * static_cast<size_t>(R) * (d + 4) + 2 * static_cast<size_t>(R) * H * T + 2 * static_cast<size_t>(spt) * H * T +
-         2 * static_cast<size_t>(spt) * T * (d + 4);
-}
-
 __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const TailBwdArgs a, const int R) {
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
@@ -465,11 +460,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
       *reinterpret_cast<float4*>(a.g_qlin + static_cast<size_t>(s) * d + j) = acc;
     }
   }
-}
-
-static bool attn_bwd_fits(const Dims& D) {
-  return attn_bwd_smem_floats(D.spt * D.C, D.d, D.H, D.T, D.spt) * sizeof(float) <= 227 * 1024 &&
-         (D.spt * (D.d >> 2) * 4) % 32 == 0;
 }
 
 static int launch_tail_attn_bwd(const TailBwdArgs& a, cudaStream_t s) {
@@ -793,7 +783,27 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   a.lnp = ws + W.lnp_t;
   a.seed_dev = cfg->seed_dev;
   a.gy_in = nullptr; a.gctx_in = nullptr;
+  // weight gradients
+  WgProbs probs;
+  probs.n = 0;
+  int total_tiles = 0;
+  auto add = [&](int i, const float* G, int ldg, const float* A, int lda, const int32_t* m_dev, int m_host, int m_max,
+                 int N, int K) {
+    WgProb& P = probs.p[probs.n++];
+    P.G = G; P.ldg = ldg; P.A = A; P.lda = lda; P.m_dev = m_dev; P.m_host = m_host; P.m_max = m_max; P.N = N; P.K = K;
+    P.part_w = ws + W.pw[i]; P.part_b = ws + W.pb[i];
+    P.ntn = (N + 127) / 128; P.ntk = (K + 127) / 128; P.nch = (m_max + kChunk - 1) / kChunk;
+    P.tiles = P.ntn * P.ntk * P.nch;
+    total_tiles += P.tiles;
+  };
+  add(0, ws + W.g_h2, d, sv + L.h1, F, nullptr, SC, SC, d, F);             // dW2, db2
+  add(1, ws + W.g_pre, F, sv + L.n, d, nullptr, SC, SC, F, d);             // dW1, db1
+  add(2, ws + W.g_o1, d, sv + L.ctx, d, nullptr, SC, SC, d, d);            // dWo, dbo
+  add(3, ws + W.gkv, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWk, dbk
+  add(4, ws + W.gkv + d, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWv, dbv
+  add(5, ws + W.g_qlin, d, sv + L.xno, d, nullptr, D.S, D.S, d, d);        // dWq, dbq
   int ln_parts = D.ntile;
+  int wgrad_from = 0;          // problems [wgrad_from, 6) are still to be launched after the tail
   TailBwdTcArgs tb;
   tb.D = D;
   tb.z = sv + L.z; tb.gout = grad_out; tb.y = sv + L.y; tb.pre1 = sv + L.pre1;
@@ -802,12 +812,35 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   tb.g_h2 = a.g_h2; tb.g_pre = a.g_pre; tb.g_o1 = a.g_o1; tb.gy = ws + W.gy; tb.g_ctx = ws + W.g_ctx;
   tb.lnp = a.lnp;
   tb.seed_dev = cfg->seed_dev;
-  if (tail_bwd_fused_enabled() && tail_bwd_fused_supported(tb) && attn_bwd_fits(D)) {
+  if (tail_bwd_fused_for(D)) {
+    // (the forward pass took the same decision and saved what this path reads: no falling back from here)
+    if (!tail_bwd_fused_supported(tb)) return PSB_E_ALIGN;
     // PSB_ENC_TC=4: the product chain on tcgen05 (gemm3_tf32.cu), then the attention backward from gy / g_ctx
     if ((st = launch_tail_bwd_fused(tb, s)) != PSB_OK) return st;
     a.gy_in = tb.gy;
     a.gctx_in = tb.g_ctx;
     ln_parts = tail_bwd_fused_parts(D);
+    if (cfg->wgrad_done != nullptr && !D.pre_ln) {
+      // dW2 / dW1 / dWo (90 % of the weight-gradient flops) need the product chain's outputs only: on the side stream
+      // next to the attention backward
+      cudaStream_t sw0 = nullptr;
+      cudaEvent_t ev0 = nullptr;
+      if ((st = side_stream(&sw0, &ev0)) != PSB_OK) return st;
+      cudaError_t e0 = cudaEventRecord(ev0, s);
+      if (e0 == cudaSuccess) e0 = cudaStreamWaitEvent(sw0, ev0, 0);
+      if (e0 != cudaSuccess) return static_cast<int>(e0);
+      WgProbs first;
+      first.n = 3;
+      int tiles = 0;
+      for (int i = 0; i < 3; ++i) {
+        first.p[i] = probs.p[i];
+        tiles += probs.p[i].tiles;
+      }
+      PSB_PROF("wgrad_kernel", sw0);
+      wgrad_kernel<<<tiles, 256, 0, sw0>>>(first);
+      if ((st = launch_status()) != PSB_OK) return st;
+      wgrad_from = 3;
+    }
     st = launch_tail_attn_bwd(a, s);
   } else {
     st = D.R == 24 ? launch_tail_bwd<24>(a, s) : D.R == 20 ? launch_tail_bwd<20>(a, s) : launch_tail_bwd<16>(a, s);
@@ -819,8 +852,9 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   const bool fork_wgrad = cfg->wgrad_done != nullptr && !D.pre_ln;
   cudaStream_t sw = s;
   if (fork_wgrad) {
-    cudaEvent_t fork_ev = nullptr;
-    if ((st = side_stream(&sw, &fork_ev)) != PSB_OK) return st;
+    cudaEvent_t fork_ev = nullptr, second_ev = nullptr;
+    if ((st = side_stream(&sw, &fork_ev, 0, &second_ev)) != PSB_OK) return st;
+    if (wgrad_from > 0) fork_ev = second_ev;     // the fork event is already in use by the first part
     ce = cudaEventRecord(fork_ev, s);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sw, fork_ev, 0);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -855,28 +889,18 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   };
   if (!fork_wgrad && (st = data_grads()) != PSB_OK) return st;   // pre_ln: the reduce below reads embed_bwd's partials
 
-  // weight gradients
-  WgProbs probs;
-  probs.n = 0;
-  int total_tiles = 0;
-  auto add = [&](int i, const float* G, int ldg, const float* A, int lda, const int32_t* m_dev, int m_host, int m_max,
-                 int N, int K) {
-    WgProb& P = probs.p[probs.n++];
-    P.G = G; P.ldg = ldg; P.A = A; P.lda = lda; P.m_dev = m_dev; P.m_host = m_host; P.m_max = m_max; P.N = N; P.K = K;
-    P.part_w = ws + W.pw[i]; P.part_b = ws + W.pb[i];
-    P.ntn = (N + 127) / 128; P.ntk = (K + 127) / 128; P.nch = (m_max + kChunk - 1) / kChunk;
-    P.tiles = P.ntn * P.ntk * P.nch;
-    total_tiles += P.tiles;
-  };
-  add(0, ws + W.g_h2, d, sv + L.h1, F, nullptr, SC, SC, d, F);             // dW2, db2
-  add(1, ws + W.g_pre, F, sv + L.n, d, nullptr, SC, SC, F, d);             // dW1, db1
-  add(2, ws + W.g_o1, d, sv + L.ctx, d, nullptr, SC, SC, d, d);            // dWo, dbo
-  add(3, ws + W.gkv, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWk, dbk
-  add(4, ws + W.gkv + d, 2 * d, sv + L.xn, d, off + D.S, 0, D.S * D.T, d, d);  // dWv, dbv
-  add(5, ws + W.g_qlin, d, sv + L.xno, d, nullptr, D.S, D.S, d, d);        // dWq, dbq
-  PSB_PROF("wgrad_kernel", sw);
-  wgrad_kernel<<<total_tiles, 256, 0, sw>>>(probs);
-  if ((st = launch_status()) != PSB_OK) return st;
+  {
+    WgProbs rest;
+    rest.n = 0;
+    int tiles = 0;
+    for (int i = wgrad_from; i < 6; ++i) {
+      rest.p[rest.n++] = probs.p[i];
+      tiles += probs.p[i].tiles;
+    }
+    PSB_PROF("wgrad_kernel", sw);
+    wgrad_kernel<<<tiles, 256, 0, sw>>>(rest);
+    if ((st = launch_status()) != PSB_OK) return st;
+  }
 
   RedJobs jobs;
   jobs.n = 0;

@@ -400,8 +400,10 @@ struct TailTcArgs {
   const uint64_t* seed_dev;
   const float *wo_hl, *w1_hl, *w2_hl;            // fused tail only: pre-split weights (FwdWs), written by the transpose launch
   float* ctx_hl;                                 // fused tail only: pre-split ctx rows
+  int save_dact;                                 // fused tail only: the pre1 slot receives dropout_3 . gelu'(pre1)
 };
 bool tail_tc_enabled();
+bool tail_tc3_enabled();
 bool tail_tc_supported(const TailTcArgs& a);
 int launch_tail_fwd_tc(const TailTcArgs& a, cudaStream_t s);
 // PSB_ENC_TC=3: ctx kernel + ONE cluster kernel chaining the three products (FFN hidden dimension split over 4 CTAs)
@@ -420,6 +422,18 @@ struct TailBwdTcArgs {
   const uint64_t* seed_dev;
 };
 bool tail_bwd_fused_enabled();
+// Shared-memory floats of tail_attn_bwd_kernel (encoder_bwd.cu) for a tile of spt sequences, R = spt * C copy rows
+__host__ __device__ inline size_t attn_bwd_smem_floats(int R, int d, int H, int T, int spt) {
+  return 2 * static_cast<size_t>(R) * (d + 4) + 2 * static_cast<size_t>(R) * H * T + 2 * static_cast<size_t>(spt) * H * T +
+         2 * static_cast<size_t>(spt) * T * (d + 4);
+}
+// Does the backward pass of a call with these dimensions take the tensor-core tail?  Decided from the dimensions alone,
+// because the forward pass must know: it then saves dropout_3 . gelu'(pre1) in the pre1 slot and the transposed weights.
+inline bool tail_bwd_fused_for(const Dims& D) {
+  return tail_bwd_fused_enabled() && tail_fused_enabled() && D.d == 128 && D.F == 512 && D.S * D.C > 0 &&
+         attn_bwd_smem_floats(D.spt * D.C, D.d, D.H, D.T, D.spt) * sizeof(float) <= 227 * 1024 &&
+         (D.spt * (D.d >> 2) * 4) % 32 == 0;
+}
 int tail_bwd_fused_parts(const Dims& D);         // LayerNorm partial rows the kernel writes (4 per 128-row tile)
 bool tail_bwd_fused_supported(const TailBwdTcArgs& a);
 int launch_tail_bwd_fused(const TailBwdTcArgs& a, cudaStream_t s);

@@ -662,8 +662,9 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
     t.out = out;
     t.seed_dev = cfg->seed_dev;
     t.wo_hl = ws + W.wo_hl; t.w1_hl = ws + W.w1_hl; t.w2_hl = ws + W.w2_hl; t.ctx_hl = ws + W.ctx_hl;
-    if (fused_tail && tail_fused_supported(t)) return launch_tail_fwd_fused(t, s);
-    if (tail_tc_supported(t)) return launch_tail_fwd_tc(t, s);
+    t.save_dact = tail_bwd_fused_for(D) ? 1 : 0;
+    if (fused_tail) return tail_fused_supported(t) ? launch_tail_fwd_fused(t, s) : PSB_E_ALIGN;
+    if (tail_tc3_enabled() && tail_tc_supported(t)) return launch_tail_fwd_tc(t, s);
   }
   TailFwdArgs a;
   a.D = D;

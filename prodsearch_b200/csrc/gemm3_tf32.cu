@@ -365,14 +365,20 @@ static int g3_make_map(CUtensorMap* map, const float* base, int64_t rows, int64_
   return r == CUDA_SUCCESS ? PSB_OK : PSB_E_ARG;
 }
 
-// PSB_ENC_TC: 0 (default) = FFMA kernels; 1 = forward q and K|V projections on tcgen05; 2 = 1 + the forward tail as
-// ctx kernel + three 3xTF32 GEMMs with fused epilogues (launch_tail_fwd_tc).  Read once per process.
+// PSB_ENC_TC, read once per process.  Unset = 4: every encoder product that has a tensor-core form runs on tcgen05 --
+//   1  forward q and K|V projections (gemm3_tf32_kernel)
+//   2  1 + the forward tail as ctx kernel + three 3xTF32 GEMMs with fused epilogues (launch_tail_fwd_tc; measured slower
+//      than the FFMA tail at TEM's size, kept for comparison: only PSB_ENC_TC=2 exactly selects it)
+//   3  1 + the forward tail as ctx kernel + ONE cluster kernel (tail_fused_tc_kernel)
+//   4  3 + the backward tail's product chain as one cluster kernel (tail_bwd_fused_tc_kernel) + tail_attn_bwd_kernel
+//   0  the fp32 FFMA kernels everywhere (encoder_fwd.cu / encoder_bwd.cu), also the fallback for shapes the tensor-core
+//      kernels do not take (d != 128, ff != 512, misaligned operands)
 static int enc_tc_level() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PSB_ENC_TC");
-    const int x = e != nullptr ? atoi(e) : 0;
-    v = (x >= 0 && x <= 4) ? x : 0;
+    const int x = e != nullptr ? atoi(e) : 4;
+    v = (x >= 0 && x <= 4) ? x : 4;
   }
   return v;
 }
@@ -389,7 +395,8 @@ bool rows_gemm_tc_auto(int64_t m_max) {
   }
   return allowed == 1 && m_max >= 16384;
 }
-bool tail_tc_enabled() { return enc_tc_level() >= 2; }
+bool tail_tc_enabled() { return enc_tc_level() >= 2; }       // some tensor-core forward tail
+bool tail_tc3_enabled() { return enc_tc_level() == 2; }      // the three-GEMM form of it
 
 // One launch: out-tile epilogue `epi` over A [m rows, K] (row stride lda) and Bt rows [0, split) from Bt0, the rest from Bt1
 template <int N, int KC, class Epi>
@@ -1072,7 +1079,7 @@ int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
   P.y = a.y; P.n = a.n; P.z = a.z; P.pre1 = a.pre1; P.h1 = a.h1; P.out = a.out;
   P.seed_dev = a.seed_dev;
   P.trace = ft_trace_buffer();
-  P.save_dact = tail_bwd_fused_enabled() ? 1 : 0;
+  P.save_dact = a.save_dact;
   {
     const char* e = getenv("PSB_FT_EXP");
     P.exp = e != nullptr ? atoi(e) : 0;

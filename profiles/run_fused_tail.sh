@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 timeout 200 python profiles/diff_enc_tc.py 3 > gpurun_out/${R}_diff_enc_tc3.jsonl 2>&1; echo "fwd diff exit $?"
 timeout 200 python profiles/diff_enc_bwd_tc.py $L > gpurun_out/${R}_diff_enc_bwd_tc.jsonl 2>&1; echo "bwd diff exit $?"
 PSB_ENC_TC=$L timeout 300 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_tc$L.json 2> gpurun_out/${R}_bench_tc$L.err; echo "bench tc$L exit $?"
-timeout 300 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_tc0.json 2> gpurun_out/${R}_bench_tc0.err; echo "bench tc0 exit $?"
+PSB_ENC_TC=0 timeout 300 python bench.py --no-extra --no-cpu > gpurun_out/${R}_bench_tc0.json 2> gpurun_out/${R}_bench_tc0.err; echo "bench tc0 exit $?"
 python - <<PY
 import json
 for t in ("tc$L","tc0"):
