@@ -752,10 +752,16 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
 
   // [Wk ; Wv] stacked so grad xn is ONE product over the 2d-wide [gK | gV] rows.  Big token counts (RTM: 117k rows)
   // run that product on tcgen05 (gemm3_tf32.cu), which wants the K-major operand [Wk^T | Wv^T] : [d][2d] instead
-  const bool tc_gxn = rows_gemm_tc_auto(static_cast<int64_t>(D.S) * D.T) &&
-                      rows_gemm_tc_supported(ws + W.gkv, 2 * d, 2 * d, ws + W.wkv, nullptr, 0, d, nullptr, ws + W.gxn, d);
+  // With the tensor-core encoder (PSB_ENC_TC >= 1, the default) the forward pass left that operand in the saved state.
+  const bool tc_saved = rows_gemm_tc_enabled() &&
+                        rows_gemm_tc_supported(ws + W.gkv, 2 * d, 2 * d, sv + L.wkv_t, nullptr, 0, d, nullptr, ws + W.gxn, d);
+  const bool tc_gxn = tc_saved || (rows_gemm_tc_auto(static_cast<int64_t>(D.S) * D.T) &&
+                      rows_gemm_tc_supported(ws + W.gkv, 2 * d, 2 * d, ws + W.wkv, nullptr, 0, d, nullptr, ws + W.gxn, d));
+  const float* wkv_op = tc_saved ? sv + L.wkv_t : ws + W.wkv;
   cudaError_t ce = cudaSuccess;
-  if (tc_gxn) {
+  if (tc_saved) {
+    // nothing to prepare
+  } else if (tc_gxn) {
     TrJobs jobs;
     jobs.n = 0;
     jobs.j[jobs.n++] = TrJob{p->wk, ws + W.wkv, d, d, 2 * d, 0, 0};
@@ -867,7 +873,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
         },
         [&]() {
           if (tc_gxn)
-            return launch_rows_gemm_tc(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, nullptr, 0, d, nullptr,
+            return launch_rows_gemm_tc(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, wkv_op, nullptr, 0, d, nullptr,
                                        ws + W.gxn, d, s);
           return launch_rows_gemm(ws + W.gkv, 2 * d, off + D.S, 0, D.S * D.T, 2 * d, ws + W.wkv, d, nullptr,
                                   ws + W.gxn, d, s);

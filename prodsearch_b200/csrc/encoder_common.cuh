@@ -288,6 +288,7 @@ struct Saved {
   // hi part and exact remainder, hi rows stacked on lo rows: Wo^T [2][d][d], W1^T [2][d][F], W2^T [2][F][d].  Written by
   // the forward pass's transpose launch (they are this step's weights) when PSB_ENC_TC >= 3.
   size_t wot_hl, w1t_hl, w2t_hl;
+  size_t wkv_t;                     // [Wk^T | Wv^T] : [d][2d], the K-major operand of the backward's grad-xn product on tcgen05
   size_t total;                     // floats
 };
 __host__ inline size_t align4(size_t x) { return (x + 3) & ~static_cast<size_t>(3); }
@@ -313,6 +314,7 @@ __host__ inline Saved saved_layout(const Dims& D) {
   L.wot_hl = p; p += 2 * d * d;
   L.w1t_hl = p; p += 2 * d * F;
   L.w2t_hl = p; p += 2 * F * d;
+  L.wkv_t = p; p += 2 * d * d;
   L.total = p;
   return L;
 }

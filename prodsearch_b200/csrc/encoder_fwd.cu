@@ -589,6 +589,10 @@ extern "C" int psb_encoder_fwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(p->w2, ws + W.w2_t, d, F, d, 0);           // W2 [d][F] -> [F][d]
   add(p->bk, ws + W.bkv, d, 1, 2 * d, 0);        // bias concat as 1-column "transposes"
   add(p->bv, ws + W.bkv, d, 1, 2 * d, d);
+  if (rows_gemm_tc_enabled()) {                    // the backward's grad-xn product reads [Wk^T | Wv^T] from the saved state
+    add(p->wk, sv + L.wkv_t, d, d, 2 * d, 0);
+    add(p->wv, sv + L.wkv_t, d, d, 2 * d, d);
+  }
   const bool fused_tail = tail_fused_enabled() && d == 128 && F == 512;
   if (fused_tail) {                                // hi / lo parts of the tail's weights for tail_fused_tc_kernel
     add(p->wo, ws + W.wo_hl, d, d, -1, 0);

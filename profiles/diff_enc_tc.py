@@ -54,7 +54,7 @@ def layout():
     sc = S * C
     sizes = [("nact", a4(S)), ("off", a4(S + 1)), ("tok", a4(S * T)), ("xo", S * D), ("xno", S * D), ("qv", S * D),
              ("xn", S * T * D), ("kv", S * T * 2 * D), ("p", a4(S * T * H)), ("ctx", sc * D), ("y", sc * D), ("n", sc * D),
-             ("z", sc * D), ("pre1", sc * FF), ("h1", sc * FF), ("wot_hl", 2 * D * D), ("w1t_hl", 2 * D * FF), ("w2t_hl", 2 * FF * D)]
+             ("z", sc * D), ("pre1", sc * FF), ("h1", sc * FF), ("wot_hl", 2 * D * D), ("w1t_hl", 2 * D * FF), ("w2t_hl", 2 * FF * D), ("wkv_t", 2 * D * D)]
     out, p = {}, 0
     for name, n in sizes:
         out[name] = (p, n)
@@ -89,7 +89,7 @@ if __name__ == "__main__":
         n_act = int(base["saved"].view(np.int32)[L["off"][0] + S])        # active tokens: compact rows beyond hold garbage
         for name, (p, n) in L.items():
             a, b = base["saved"][p:p + n], got["saved"][p:p + n]
-            if name.endswith("_hl"):                                       # transposed weights of the tensor-core backward: level >= 3 only
+            if name.endswith("_hl") or name == "wkv_t":                                       # transposed weights of the tensor-core backward: level >= 3 only
                 continue
             if name in ("nact", "off", "tok"):
                 same = bool(np.array_equal(a.view(np.int32), b.view(np.int32)))
