@@ -31,7 +31,8 @@ struct TailBwdArgs {
   float *g_h2, *g_pre, *g_o1, *gxo, *g_qlin, *gkv;
   float* lnp;  // [ntile][4][d] : d ln_out_g, d ln_out_b, d ln_ff_g, d ln_ff_b
   const uint64_t* seed_dev;
-  const float *gy_in, *gctx_in;  // tail_bwd_kernel<R, true>: the product chain ran on tcgen05 (gemm3_tf32.cu), [S*C][d] each
+  unsigned long long* trace;     // tail_attn_bwd_kernel: phase stamps of CTA 0 (slots 48..55 of the trace buffer) or NULL
+  const float *gy_in, *gctx_in;  // tail_attn_bwd_kernel: the product chain ran on tcgen05 (gemm3_tf32.cu), [S*C][d] each
 };
 
 template <int R>
@@ -328,18 +329,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
     return *s < D.S;
   };
 
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 0] = t_; }
   // (0) one wave of loads: gy / g_ctx rows, K | V rows and P of the tile's sequences, the dropout multipliers
-  for (int e = threadIdx.x; e < R * nd4; e += kTailThreads) {
-    const int r = e / nd4, j = (e - r * nd4) * 4;
-    int s, grow;
-    float4 gy = zero4(), gc = zero4();
-    if (row_seq(r, &s, &grow)) {
-      gy = *reinterpret_cast<const float4*>(a.gy_in + static_cast<size_t>(grow) * d + j);
-      gc = *reinterpret_cast<const float4*>(a.gctx_in + static_cast<size_t>(grow) * d + j);
-    }
-    *reinterpret_cast<float4*>(rowA + r * DP + j) = gy;
-    *reinterpret_cast<float4*>(rowB + r * DP + j) = gc;
-  }
   for (int e = threadIdx.x; e < D.spt * T * 2 * nd4; e += kTailThreads) {
     const int sl = e / (T * 2 * nd4), rem = e - sl * (T * 2 * nd4), al = rem / (2 * nd4), c = rem - al * 2 * nd4;
     const int s = s0 + sl;
@@ -361,7 +352,22 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
     const int s = s0 + sl;
     Ps[e] = (s < D.S && al < a.nact[s]) ? a.P[static_cast<size_t>(a.off[s] + al) * H + h] : 0.f;
   }
+  // everything above reads the forward pass's saved state only; gy / g_ctx come from the kernel before this one in the
+  // stream (tail_bwd_fused_tc_kernel; programmatic dependent launch: this kernel may have started before it finished)
+  pdl_wait();
+  for (int e = threadIdx.x; e < R * nd4; e += kTailThreads) {
+    const int r = e / nd4, j = (e - r * nd4) * 4;
+    int s, grow;
+    float4 gy = zero4(), gc = zero4();
+    if (row_seq(r, &s, &grow)) {
+      gy = *reinterpret_cast<const float4*>(a.gy_in + static_cast<size_t>(grow) * d + j);
+      gc = *reinterpret_cast<const float4*>(a.gctx_in + static_cast<size_t>(grow) * d + j);
+    }
+    *reinterpret_cast<float4*>(rowA + r * DP + j) = gy;
+    *reinterpret_cast<float4*>(rowB + r * DP + j) = gc;
+  }
   __syncthreads();
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 1] = t_; }
   // residual gradient of x[o]: sum of gy over the copies of each sequence (copy order)
   for (int e = threadIdx.x; e < D.spt * d; e += kTailThreads) {
     const int sl = e / d, j = e - sl * d;
@@ -380,11 +386,23 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
     if (row_seq(r, &s, &grow) && al < a.nact[s]) {
       const float* v = Vs + ((r / C) * T + al) * DP + h * dh;
       const float* g = rowB + r * DP + h * dh;
-      for (int j = 0; j < dh; ++j) acc = fmaf(g[j], v[j], acc);
+      if ((dh & 3) == 0) {                                   // 128-bit shared-memory reads (rows are 16-byte aligned)
+        for (int j = 0; j < dh; j += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(g + j);
+          const float4 vv = *reinterpret_cast<const float4*>(v + j);
+          acc = fmaf(gv.x, vv.x, acc);
+          acc = fmaf(gv.y, vv.y, acc);
+          acc = fmaf(gv.z, vv.z, acc);
+          acc = fmaf(gv.w, vv.w, acc);
+        }
+      } else {
+        for (int j = 0; j < dh; ++j) acc = fmaf(g[j], v[j], acc);
+      }
     }
     gA[e] = acc;
   }
   __syncthreads();
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 2] = t_; }
   // (7b) softmax backward, one warp per (sequence, head), lanes along the tokens
   for (int e = warp; e < D.spt * H; e += kTailWarps) {
     const int sl = e / H, h = e - sl * H;
@@ -410,6 +428,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
     }
   }
   __syncthreads();
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 3] = t_; }
   // (7c) grad K | V rows of the tile's sequences
   for (int e = threadIdx.x; e < D.spt * T * nd4; e += kTailThreads) {
     const int sl = e / (T * nd4), rem = e - sl * (T * nd4), al = rem / nd4, j = (rem - al * nd4) * 4;
@@ -435,6 +454,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
     *reinterpret_cast<float4*>(dst) = gk;
     *reinterpret_cast<float4*>(dst + d) = gv;
   }
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 4] = t_; }
   // grad q: four threads per (sequence, 4 columns), each every fourth token, combined in fixed order
   for (int e = threadIdx.x; e < D.spt * nd4 * 4; e += kTailThreads) {
     const int part = e & 3, sl = (e >> 2) / nd4, j = ((e >> 2) - sl * nd4) * 4;
@@ -460,6 +480,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
       *reinterpret_cast<float4*>(a.g_qlin + static_cast<size_t>(s) * d + j) = acc;
     }
   }
+  if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 5] = t_; }
 }
 
 static int launch_tail_attn_bwd(const TailBwdArgs& a, cudaStream_t s) {
@@ -474,7 +495,10 @@ static int launch_tail_attn_bwd(const TailBwdArgs& a, cudaStream_t s) {
     configured.done(smem);
   }
   PSB_PROF("tail_attn_bwd_kernel", s);
-  tail_attn_bwd_kernel<<<D.ntile, kTailThreads, smem, s>>>(a, R);
+  {
+    const cudaError_t le = launch_pdl(tail_attn_bwd_kernel, dim3(D.ntile), dim3(kTailThreads), smem, s, a, R);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  }
   return launch_status();
 }
 
@@ -789,6 +813,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   a.lnp = ws + W.lnp_t;
   a.seed_dev = cfg->seed_dev;
   a.gy_in = nullptr; a.gctx_in = nullptr;
+  a.trace = ft_trace_buffer();
   // weight gradients
   WgProbs probs;
   probs.n = 0;

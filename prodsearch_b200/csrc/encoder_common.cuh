@@ -424,6 +424,7 @@ struct TailBwdTcArgs {
   const uint64_t* seed_dev;
 };
 bool tail_bwd_fused_enabled();
+unsigned long long* ft_trace_buffer();           // PSB_FT_TRACE=1: 64 %globaltimer slots (psb_debug_tail_trace), else NULL
 // Shared-memory floats of tail_attn_bwd_kernel (encoder_bwd.cu) for a tile of spt sequences, R = spt * C copy rows
 __host__ __device__ inline size_t attn_bwd_smem_floats(int R, int d, int H, int T, int spt) {
   return 2 * static_cast<size_t>(R) * (d + 4) + 2 * static_cast<size_t>(R) * H * T + 2 * static_cast<size_t>(spt) * H * T +

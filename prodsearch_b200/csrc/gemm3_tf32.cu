@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
                                                        const int32_t* __restrict__ tok, const float* __restrict__ Pw,
                                                        const float* __restrict__ kv, float* __restrict__ ctx,
                                                        const uint64_t* __restrict__ seed_dev, float* __restrict__ ctx_hl = nullptr) {
+  pdl_trigger();                            // tail_fused_tc_kernel may set itself up and prefetch its weights
   const int lane = threadIdx.x & 31;
   const int grow = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (grow >= D.S * D.C) return;
@@ -756,12 +757,17 @@ tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_c
   if (warp == 0) {
     // ===== TMA producer: the ctx tile, then the 12 weight chunks of the three phases; hi rows, lo rows `rows` further =====
     if (lane == 0) {
-      mbar_expect_tx(a_ready + 0, 2 * kFtABytes);
-      for (int kb = 0; kb < 4; ++kb) {
-        tma_load_2d(a_hi + kb * 16384, &map_ctx, kb * 32, r0, a_ready + 0);
-        tma_load_2d(a_lo + kb * 16384, &map_ctx, kb * 32, P.SC + r0, a_ready + 0);
-      }
       for (int c = 0; c < 12; ++c) {
+        if (c == kFtStages) {
+          // the first weight chunks are in flight; the ctx rows come from the kernel before this one in the stream
+          // (programmatic dependent launch: wait for it to have finished only now)
+          pdl_wait();
+          mbar_expect_tx(a_ready + 0, 2 * kFtABytes);
+          for (int kb = 0; kb < 4; ++kb) {
+            tma_load_2d(a_hi + kb * 16384, &map_ctx, kb * 32, r0, a_ready + 0);
+            tma_load_2d(a_lo + kb * 16384, &map_ctx, kb * 32, P.SC + r0, a_ready + 0);
+          }
+        }
         const int st = c % kFtStages;
         const uint32_t ph = (c / kFtStages) & 1;
         mbar_wait(empty + st, ph ^ 1);
@@ -1030,7 +1036,7 @@ bool tail_fused_enabled() { return enc_tc_level() >= 3; }
 
 // PSB_FT_TRACE=1: a 64-slot device buffer CTA 0 of the fused tail kernels stamps with %globaltimer (forward: slots 0..31,
 // backward: 32..63; read back by psb_debug_tail_trace)
-static unsigned long long* ft_trace_buffer() {
+unsigned long long* ft_trace_buffer() {
   static unsigned long long* buf = nullptr;
   static int state = -1;
   if (state < 0) {
@@ -1086,7 +1092,11 @@ int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
   }
   const unsigned tiles = static_cast<unsigned>((SC + 127) / 128);
   PSB_PROF("tail_fused_tc_kernel", s);
-  tail_fused_tc_kernel<<<tiles * kFtCluster, kFtThreads, kFtSmem, s>>>(map_ctx, map_wo, map_w1, map_w2, P);
+  {
+    const cudaError_t le = launch_pdl(tail_fused_tc_kernel, dim3(tiles * kFtCluster), dim3(kFtThreads), kFtSmem, s, map_ctx,
+                                      map_wo, map_w1, map_w2, P);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  }
   return launch_status();
 }
 
@@ -1140,6 +1150,7 @@ __device__ __forceinline__ void fb_ld8x2(uint32_t taddr, uint32_t (&v)[8], uint3
 __global__ void __cluster_dims__(kFtCluster, 1, 1) __launch_bounds__(kFtThreads, 1)
 tail_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_constant__ CUtensorMap map_w1t,
                          const __grid_constant__ CUtensorMap map_wot, const FbParams P) {
+  pdl_trigger();                                    // tail_attn_bwd_kernel may start staging its K | V rows
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* t_hi = smem;                       // activation tile (N operand), hi / lo

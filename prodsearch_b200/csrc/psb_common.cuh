@@ -70,6 +70,23 @@ inline int fork_join(cudaStream_t s, int slot, FSide&& side_work, FMain&& main_w
   return PSB_OK;
 }
 
+// kernel<<<grid, block, smem, s>>>(args...) with the programmatic-stream-serialization attribute: the launch may begin
+// before the previous kernel of the stream has finished (see pdl_trigger / pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int grid_for(int64_t work_items, int items_per_block, int max_waves = 16) {
   int64_t need = (work_items + items_per_block - 1) / items_per_block;
   int64_t cap = static_cast<int64_t>(kNumSMs) * max_waves;
@@ -108,6 +125,13 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
   acc.z = fmaf(s, v.z, acc.z);
   acc.w = fmaf(s, v.w, acc.w);
 }
+
+// Programmatic dependent launch (stream order K1 -> K2, K2 launched with launch_pdl): K1 lets the runtime start K2's CTAs
+// while it is still running (pdl_trigger, first instruction), K2 does the part of its work that does not read K1's
+// outputs and only then waits for K1's grid to have completed and flushed (pdl_wait).  Both are no-ops in a kernel
+// launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 

@@ -48,6 +48,10 @@ for it in range(4):
     t = np.array(list(buf), dtype=np.int64)
     rel = {NAMES[i]: round(float(t[i] - t[0]) / 1000.0, 2) for i in sorted(NAMES) if t[i] != 0}
     print(json.dumps({"launch": it, "us_since_start": rel}))
+    if t[48] != 0:
+        AN = {0: "start", 1: "loads + dropout multipliers staged", 2: "gxo + gA done", 3: "softmax backward done", 4: "gK | gV stored", 5: "gq stored"}
+        print(json.dumps({"launch": it, "attn_backward_us_since_start":
+                          {AN[i]: round(float(t[48 + i] - t[48]) / 1000.0, 2) for i in sorted(AN) if t[48 + i] != 0}}))
     if t[32] != 0:
         print(json.dumps({"launch": it, "backward_us_since_start":
                           {BNAMES[i]: round(float(t[32 + i] - t[32]) / 1000.0, 2) for i in sorted(BNAMES) if t[32 + i] != 0}}))
