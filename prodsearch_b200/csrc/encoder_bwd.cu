@@ -304,6 +304,7 @@ static int launch_tail_bwd(const TailBwdArgs& a, cudaStream_t s) {
 // the softmax backward runs one warp per (sequence, head) and the grad-q sum four threads per column group, so no
 // phase is a chain of dependent global loads.
 __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const TailBwdArgs a, const int R) {
+  pdl_trigger();                                   // the grad-xn product may set itself up
   extern __shared__ float4 smem4[];
   const Dims& D = a.D;
   const int d = D.d, H = D.H, T = D.T, C = D.C, dh = D.dh;

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(128) embed_kernel(TokSrc ts, Dims D, const flo
                                                     const int32_t* __restrict__ nact, const int32_t* __restrict__ off,
                                                     const int32_t* __restrict__ tok, float* __restrict__ xn,
                                                     float* __restrict__ xo, float* __restrict__ xno) {
+  pdl_trigger();   // the K | V projection (gemm3_tf32_kernel) may set itself up
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na = nact[s], base = off[s], d = D.d, T = D.T;
   const int j = lane * 4;
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(Dims D, const int32_t* __
                                                        const int32_t* __restrict__ tok, TokSrc ts,
                                                        float* __restrict__ qv /* in: q + bq, out: scaled */,
                                                        const float* __restrict__ kv, float* __restrict__ P) {
+  pdl_trigger();   // tail_ctx_kernel may be scheduled
   __shared__ float q_s[128];
   extern __shared__ float dyn[];
   float* scd = dyn;  // [H][T] scores

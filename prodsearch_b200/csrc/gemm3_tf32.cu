@@ -219,7 +219,10 @@ gemm3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   using C = G3Cfg<N, KC>;
   const int M = P.m_dev != nullptr ? *P.m_dev : P.m_host;
   const int r0 = blockIdx.x * kG3M;
-  if (r0 >= M) return;                                      // uniform: before any barrier / TMEM allocation
+  if (r0 >= M) {                                            // uniform: before any barrier / TMEM allocation
+    pdl_wait();                                             // (a grid that completes has waited for its predecessor)
+    return;
+  }
   extern __shared__ unsigned char smem_dyn[];
   // 128-byte-swizzled operand tiles need a 1024-byte aligned base
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -254,6 +257,7 @@ gemm3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      pdl_wait();                                           // A rows come from the kernel before this one in the stream
       const bool first = n0 < P.split;
       const CUtensorMap* mb = first ? &map_b0 : &map_b1;
       const int brow = first ? n0 : n0 - P.split;
@@ -428,7 +432,11 @@ static int g3_launch(const char* name, const float* A, int lda, const int32_t* m
   P.split = rows0;
   const dim3 grid(static_cast<unsigned>((m_max + kG3M - 1) / kG3M), static_cast<unsigned>(J / N));
   PSB_PROF(name, s);
-  gemm3_tf32_kernel<N, KC, Epi><<<grid, kG3Threads, C::kSmem, s>>>(map_a, map_b0, map_b1, P, epi);
+  {
+    const cudaError_t le = launch_pdl(gemm3_tf32_kernel<N, KC, Epi>, grid, dim3(kG3Threads), C::kSmem, s, map_a, map_b0, map_b1,
+                                      P, epi);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  }
   return launch_status();
 }
 
@@ -458,6 +466,7 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
                                                        const float* __restrict__ kv, float* __restrict__ ctx,
                                                        const uint64_t* __restrict__ seed_dev, float* __restrict__ ctx_hl = nullptr) {
   pdl_trigger();                            // tail_fused_tc_kernel may set itself up and prefetch its weights
+  pdl_wait();                               // P comes from attn_fwd_kernel, the kernel before this one
   const int lane = threadIdx.x & 31;
   const int grow = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (grow >= D.S * D.C) return;
@@ -714,6 +723,7 @@ __global__ void __cluster_dims__(kFtCluster, 1, 1) __launch_bounds__(kFtThreads,
 tail_fused_tc_kernel(const __grid_constant__ CUtensorMap map_ctx, const __grid_constant__ CUtensorMap map_wo,
                      const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
                      const FtParams P) {
+  pdl_trigger();                                    // the loss kernel behind this one may be scheduled
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* a_hi = smem;
@@ -1069,7 +1079,11 @@ int launch_tail_fwd_fused(const TailTcArgs& a, cudaStream_t s) {
     attr_done.done();
   }
   PSB_PROF("tail_ctx_kernel", s);
-  tail_ctx_kernel<<<(SC + 7) / 8, 256, 0, s>>>(D, a.nact, a.off, a.tok, a.P, a.kv, a.ctx, a.seed_dev, a.ctx_hl);
+  {
+    const cudaError_t le = launch_pdl(tail_ctx_kernel, dim3((SC + 7) / 8), dim3(256), 0, s, D, a.nact, a.off, a.tok, a.P, a.kv,
+                                      a.ctx, a.seed_dev, a.ctx_hl);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  }
   if ((st = launch_status()) != PSB_OK) return st;
   // hi rows stacked on lo rows: one map per operand, the lo tile `rows` further down
   alignas(64) CUtensorMap map_ctx, map_wo, map_w1, map_w2;

@@ -308,6 +308,8 @@ ns_loss_w1_kernel(const float4* __restrict__ anchor_a, const float4* __restrict_
   // reads / writes the encoder's [n, 1 + k, d] block in place: a_stride = b_stride = 1 + k, anchor_b = block + d.
   // grad_scale multiplies coefficients and anchor gradients (the 1 / n of the batch mean).
   if (b_stride < 0) b_stride = k;
+  pdl_trigger();   // (TEM tail: launched programmatically behind the encoder's tail kernel, and the loss combination behind it)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t i = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -506,6 +508,7 @@ __global__ void __launch_bounds__(256) tem_loss_finish_kernel(const float* __res
                                                               float* __restrict__ loss_out, float* __restrict__ acc_ps,
                                                               float* __restrict__ acc_il) {
   __shared__ float wa[8], wb[8];
+  pdl_wait();
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < n_ps; i += 256) a += ps_rows[i];
   for (int i = threadIdx.x; i < n_il; i += 256) b += il_rows[i];
@@ -555,11 +558,14 @@ extern "C" int psb_tem_loss_fwd(const float* enc_out, const float* table, int64_
   float4* g4 = reinterpret_cast<float4*>(grad_enc_out);
   PSB_PROF("ns_loss_w1_kernel", s);
 #define PSB_TEM_LAUNCH(NR)                                                                                          \
-  ns_loss_w1_kernel<true, NR, false><<<gridf, 256, 0, s>>>(a4, a4 + d4, reinterpret_cast<const float4*>(table),     \
-                                                           table_rows, d4, bias, pos_idx, neg_idx, nullptr, -1, nullptr, \
-                                                           pos_weight, n, static_cast<int>(k), loss_rows, coef_pos,  \
-                                                           coef_neg, g4, g4 + d4, C, C, grad_scale)
-  if (k <= 5) PSB_TEM_LAUNCH(6); else PSB_TEM_LAUNCH(8);
+  {                                                                                                                 \
+    const cudaError_t le = launch_pdl(ns_loss_w1_kernel<true, NR, false>, dim3(gridf), dim3(256), 0, s, a4, a4 + d4,  \
+                                      reinterpret_cast<const float4*>(table), table_rows, d4, bias, pos_idx, neg_idx, \
+                                      nullptr, -1, nullptr, pos_weight, n, static_cast<int>(k), loss_rows, coef_pos,  \
+                                      coef_neg, g4, g4 + d4, C, C, grad_scale);                                       \
+    if (le != cudaSuccess) return static_cast<int>(le);                                                               \
+  }
+  if (k <= 5) PSB_TEM_LAUNCH(6) else PSB_TEM_LAUNCH(8)
 #undef PSB_TEM_LAUNCH
   return launch_status();
 }
@@ -571,8 +577,11 @@ extern "C" int psb_tem_loss_finish(const float* ps_rows, const float* il_rows, i
     return PSB_E_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PSB_PROF("tem_loss_finish_kernel", s);
-  tem_loss_finish_kernel<<<1, 256, 0, s>>>(ps_rows, il_rows, static_cast<int>(n_ps), static_cast<int>(n_il), loss_out,
-                                           acc_ps, acc_il);
+  {
+    const cudaError_t le = launch_pdl(tem_loss_finish_kernel, dim3(1), dim3(256), 0, s, ps_rows, il_rows, static_cast<int>(n_ps),
+                                      static_cast<int>(n_il), loss_out, acc_ps, acc_il);
+    if (le != cudaSuccess) return static_cast<int>(le);
+  }
   return launch_status();
 }
 
