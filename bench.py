@@ -1216,6 +1216,8 @@ def run_b200_arm(a):
                        dropout=a.dropout, l2="flushed between timed steps (256 MiB write), flush not timed",
                        parallelism="dp%d, item/word tables %s" % (world, "row-sharded (%s)" % transport if world > 1 else "local"),
                        launch="CUDA graph replay of the whole step" if graphed is not None else "eager",
+                       encoder_products=("3xTF32 on tcgen05, fp32 accumulation in TMEM (PSB_ENC_TC=%s): within 1e-6 of the fp32 "
+                                         "FFMA kernels, which PSB_ENC_TC=0 selects" % os.environ.get("PSB_ENC_TC", "4 (default)")),
                        peer_barrier_wait=barrier_wait),
         "clocks": clocks.summary(),
         "e2e": {"value": B * a.steps * world / e2e_sec, "unit": "samples/s", "h2d_bytes_per_step": h2d,
