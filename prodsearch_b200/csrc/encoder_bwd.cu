@@ -484,7 +484,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_attn_bwd_kernel(const Ta
   if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[48 + 5] = t_; }
 }
 
-static int launch_tail_attn_bwd(const TailBwdArgs& a, cudaStream_t s) {
+static int launch_tail_attn_bwd(const TailBwdArgs& a_in, cudaStream_t s) {
+  TailBwdArgs a = a_in;                             // its own tiling: as many sequences per CTA as shared memory holds
+  a.D.spt = attn_bwd_spt(a_in.D);
+  if (a.D.spt <= 0) return PSB_E_UNSUPPORTED;
+  a.D.ntile = (a.D.S + a.D.spt - 1) / a.D.spt;
   const Dims& D = a.D;
   const int R = D.spt * D.C;
   const size_t smem = attn_bwd_smem_floats(R, D.d, D.H, D.T, D.spt) * sizeof(float);

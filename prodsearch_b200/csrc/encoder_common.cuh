@@ -432,10 +432,14 @@ __host__ __device__ inline size_t attn_bwd_smem_floats(int R, int d, int H, int 
 }
 // Does the backward pass of a call with these dimensions take the tensor-core tail?  Decided from the dimensions alone,
 // because the forward pass must know: it then saves dropout_3 . gelu'(pre1) in the pre1 slot and the transposed weights.
+// sequences per CTA of tail_attn_bwd_kernel: as many of the tail kernels' spt as fit in shared memory (0: none does)
+inline int attn_bwd_spt(const Dims& D) {
+  int spt = D.spt;
+  while (spt > 0 && attn_bwd_smem_floats(spt * D.C, D.d, D.H, D.T, spt) * sizeof(float) > 227 * 1024) --spt;
+  return spt;
+}
 inline bool tail_bwd_fused_for(const Dims& D) {
-  return tail_bwd_fused_enabled() && tail_fused_enabled() && D.d == 128 && D.F == 512 && D.S * D.C > 0 &&
-         attn_bwd_smem_floats(D.spt * D.C, D.d, D.H, D.T, D.spt) * sizeof(float) <= 227 * 1024 &&
-         (D.spt * (D.d >> 2) * 4) % 32 == 0;
+  return tail_bwd_fused_enabled() && tail_fused_enabled() && D.d == 128 && D.F == 512 && D.S * D.C > 0 && attn_bwd_spt(D) > 0;
 }
 int tail_bwd_fused_parts(const Dims& D);         // LayerNorm partial rows the kernel writes (4 per 128-row tile)
 bool tail_bwd_fused_supported(const TailBwdTcArgs& a);
