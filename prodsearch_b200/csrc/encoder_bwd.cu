@@ -7,6 +7,8 @@
 //   embed_bwd  (+ pre-LN') + residual, masked -> grad of the token inputs
 //   wgrad      every dW = G^T A as split-M 128x128 FFMA tiles with per-chunk partials
 //   reduce     partials summed in chunk order (deterministic; no float atomics anywhere)
+#include <stdlib.h>
+
 #include "encoder_common.cuh"
 
 namespace psb {
@@ -745,6 +747,17 @@ static BwdWs bwd_ws_layout(const Dims& D) {
 using namespace psb;
 using namespace psb::enc;
 
+// PSB_DEBUG_SKIP (timing experiments only, results are WRONG): bit 0 / 1 / 2 = do not launch the first / second
+// weight-gradient kernel / the partial-sum reduce -- is the side-stream chain on the step's critical path?
+static int debug_skip() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PSB_DEBUG_SKIP");
+    v = e != nullptr ? atoi(e) : 0;
+  }
+  return v;
+}
+
 extern "C" int64_t psb_encoder_workspace_bytes(const psb_encoder_cfg_t* cfg, int32_t backward) {
   Dims D;
   const int st = dims_from_cfg(cfg, &D);
@@ -840,6 +853,17 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   add(5, ws + W.g_qlin, d, sv + L.xno, d, nullptr, D.S, D.S, d, d);        // dWq, dbq
   int ln_parts = D.ntile;
   int wgrad_from = 0;          // problems [wgrad_from, 6) are still to be launched after the tail
+  cudaEvent_t first_done = nullptr;   // recorded behind the first part (its stream) when the weight gradients are split
+  float* gw[6] = {gr->w2, gr->w1, gr->wo, gr->wk, gr->wv, gr->wq};
+  float* gb[6] = {gr->b2, gr->b1, gr->bo, gr->bk, gr->bv, gr->bq};
+  auto red_into = [&](RedJobs& J, int& blocks, const float* part, float* out, int count, int stride, const int32_t* m_dev,
+                      int m_host, int chunk) {
+    if (out == nullptr) return;
+    RedJob& R = J.j[J.n++];
+    R.part = part; R.out = out; R.count = count; R.stride = stride; R.m_dev = m_dev; R.m_host = m_host; R.chunk = chunk;
+    R.blocks = (count / 4 + 255) / 256;
+    blocks += R.blocks;
+  };
   TailBwdTcArgs tb;
   tb.D = D;
   tb.z = sv + L.z; tb.gout = grad_out; tb.y = sv + L.y; tb.pre1 = sv + L.pre1;
@@ -861,7 +885,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
       // next to the attention backward
       cudaStream_t sw0 = nullptr;
       cudaEvent_t ev0 = nullptr;
-      if ((st = side_stream(&sw0, &ev0)) != PSB_OK) return st;
+      if ((st = side_stream(&sw0, &ev0, 0, &first_done)) != PSB_OK) return st;
       cudaError_t e0 = cudaEventRecord(ev0, s);
       if (e0 == cudaSuccess) e0 = cudaStreamWaitEvent(sw0, ev0, 0);
       if (e0 != cudaSuccess) return static_cast<int>(e0);
@@ -873,8 +897,24 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
         tiles += probs.p[i].tiles;
       }
       PSB_PROF("wgrad_kernel", sw0);
-      wgrad_kernel<<<tiles, 256, 0, sw0>>>(first);
+      if (!(debug_skip() & 1)) wgrad_kernel<<<tiles, 256, 0, sw0>>>(first);
       if ((st = launch_status()) != PSB_OK) return st;
+      // ... and their partial sums are reduced right behind them, on the same stream; the rest of the weight gradients
+      // (dWk / dWv / dWq, which wait for the attention backward) get a stream of their own
+      RedJobs ja;
+      ja.n = 0;
+      int blocks_a = 0;
+      for (int i = 0; i < 3; ++i) {
+        const WgProb& P = probs.p[i];
+        red_into(ja, blocks_a, P.part_w, gw[i], P.N * P.K, P.N * P.K, P.m_dev, P.m_host, kChunk);
+        red_into(ja, blocks_a, P.part_b, gb[i], P.N, P.N, P.m_dev, P.m_host, kChunk);
+      }
+      if (blocks_a > 0) {
+        PSB_PROF("reduce_kernel", sw0);
+        if (!(debug_skip() & 4)) reduce_kernel<<<blocks_a, 256, 0, sw0>>>(ja);
+        if ((st = launch_status()) != PSB_OK) return st;
+      }
+      if ((e0 = cudaEventRecord(first_done, sw0)) != cudaSuccess) return static_cast<int>(e0);
       wgrad_from = 3;
     }
     st = launch_tail_attn_bwd(a, s);
@@ -888,9 +928,8 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   const bool fork_wgrad = cfg->wgrad_done != nullptr && !D.pre_ln;
   cudaStream_t sw = s;
   if (fork_wgrad) {
-    cudaEvent_t fork_ev = nullptr, second_ev = nullptr;
-    if ((st = side_stream(&sw, &fork_ev, 0, &second_ev)) != PSB_OK) return st;
-    if (wgrad_from > 0) fork_ev = second_ev;     // the fork event is already in use by the first part
+    cudaEvent_t fork_ev = nullptr;
+    if ((st = side_stream(&sw, &fork_ev, wgrad_from > 0 ? 2 : 0)) != PSB_OK) return st;   // slot 0 runs the first part
     ce = cudaEventRecord(fork_ev, s);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sw, fork_ev, 0);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -934,7 +973,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
       tiles += probs.p[i].tiles;
     }
     PSB_PROF("wgrad_kernel", sw);
-    wgrad_kernel<<<tiles, 256, 0, sw>>>(rest);
+    if (!(debug_skip() & 2)) wgrad_kernel<<<tiles, 256, 0, sw>>>(rest);
     if ((st = launch_status()) != PSB_OK) return st;
   }
 
@@ -942,15 +981,9 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   jobs.n = 0;
   int total_blocks = 0;
   auto red = [&](const float* part, float* out, int count, int stride, const int32_t* m_dev, int m_host, int chunk) {
-    if (out == nullptr) return;
-    RedJob& J = jobs.j[jobs.n++];
-    J.part = part; J.out = out; J.count = count; J.stride = stride; J.m_dev = m_dev; J.m_host = m_host; J.chunk = chunk;
-    J.blocks = (count / 4 + 255) / 256;
-    total_blocks += J.blocks;
+    red_into(jobs, total_blocks, part, out, count, stride, m_dev, m_host, chunk);
   };
-  float* gw[6] = {gr->w2, gr->w1, gr->wo, gr->wk, gr->wv, gr->wq};
-  float* gb[6] = {gr->b2, gr->b1, gr->bo, gr->bk, gr->bv, gr->bq};
-  for (int i = 0; i < 6; ++i) {
+  for (int i = wgrad_from; i < 6; ++i) {
     const WgProb& P = probs.p[i];
     red(P.part_w, gw[i], P.N * P.K, P.N * P.K, P.m_dev, P.m_host, kChunk);
     red(P.part_b, gb[i], P.N, P.N, P.m_dev, P.m_host, kChunk);
@@ -963,10 +996,11 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   }
   if (total_blocks > 0) {
     PSB_PROF("reduce_kernel", sw);
-    reduce_kernel<<<total_blocks, 256, 0, sw>>>(jobs);
+    if (!(debug_skip() & 4)) reduce_kernel<<<total_blocks, 256, 0, sw>>>(jobs);
     if ((st = launch_status()) != PSB_OK) return st;
   }
   if (fork_wgrad) {
+    if (first_done != nullptr && (ce = cudaStreamWaitEvent(sw, first_done, 0)) != cudaSuccess) return static_cast<int>(ce);
     ce = cudaEventRecord(static_cast<cudaEvent_t>(cfg->wgrad_done), sw);
     if (ce != cudaSuccess) return static_cast<int>(ce);
     if ((st = data_grads()) != PSB_OK) return st;

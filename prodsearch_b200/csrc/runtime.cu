@@ -48,7 +48,7 @@ void recycle() {
 }  // namespace
 
 int side_stream(cudaStream_t* stream, cudaEvent_t* fork_event, int slot, cudaEvent_t* join_event) {
-  constexpr int kMaxDev = 64, kSlots = 2;
+  constexpr int kMaxDev = 64, kSlots = 3;
   static cudaStream_t streams[kMaxDev][kSlots] = {};
   static cudaEvent_t forks[kMaxDev][kSlots] = {};
   static cudaEvent_t joins[kMaxDev][kSlots] = {};
