@@ -597,7 +597,18 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const EmbedBwdArgs a) {
 }
 
 // ------------------------------------------------------------------ weight gradients dW = G^T A
-constexpr int kChunk = 128;   // rows of M per CTA
+// rows of M per CTA (PSB_WG_CHUNK overrides, multiple of kSub; 96 / 128 / 160 / 192 measured within 1 % of each other on
+// the batch-384 step: profiles/r02_summary.md)
+static int wg_chunk() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("PSB_WG_CHUNK");
+    const int x = e != nullptr ? atoi(e) : 128;
+    v = (x >= 32 && x <= 4096 && x % 32 == 0) ? x : 128;
+  }
+  return v;
+}
+#define kChunk wg_chunk()
 constexpr int kSub = 32;      // rows staged in shared memory at a time
 struct WgProb {
   const float* G;  // [M][ldg], columns n0.. of the gradient operand
@@ -613,6 +624,7 @@ struct WgProb {
 struct WgProbs {
   WgProb p[6];
   int n;
+  int chunk;   // rows of M per CTA (wg_chunk())
 };
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgProbs probs) {
@@ -624,9 +636,9 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgProbs probs) {
   const WgProb& P = probs.p[q];
   const int ch = b / (P.ntn * P.ntk), t2 = b - ch * (P.ntn * P.ntk), tn = t2 / P.ntk, tk = t2 - tn * P.ntk;
   const int M = P.m_dev != nullptr ? *P.m_dev : P.m_host;
-  const int m0 = ch * kChunk;
+  const int m0 = ch * probs.chunk;
   if (m0 >= M) return;
-  const int m1 = min(M, m0 + kChunk);
+  const int m1 = min(M, m0 + probs.chunk);
   const int n0 = tn * 128, k0 = tk * 128;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[8][8];
@@ -835,6 +847,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   // weight gradients
   WgProbs probs;
   probs.n = 0;
+  probs.chunk = kChunk;
   int total_tiles = 0;
   auto add = [&](int i, const float* G, int ldg, const float* A, int lda, const int32_t* m_dev, int m_host, int m_max,
                  int N, int K) {
@@ -891,6 +904,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
       if (e0 != cudaSuccess) return static_cast<int>(e0);
       WgProbs first;
       first.n = 3;
+      first.chunk = probs.chunk;
       int tiles = 0;
       for (int i = 0; i < 3; ++i) {
         first.p[i] = probs.p[i];
@@ -967,6 +981,7 @@ extern "C" int psb_encoder_bwd(const psb_encoder_cfg_t* cfg, const psb_encoder_p
   {
     WgProbs rest;
     rest.n = 0;
+    rest.chunk = probs.chunk;
     int tiles = 0;
     for (int i = wgrad_from; i < 6; ++i) {
       rest.p[rest.n++] = probs.p[i];
