@@ -478,9 +478,17 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
   float4 acc = zero4();
   // four tokens per trip: their loads and Philox draws are independent, only the fmaf chain is sequential (and keeps the
   // token order of tail_fwd_kernel, so the sums are the same bits)
+  // dh % 16 == 0: the four lanes lane & ~3 .. + 3 hold columns of ONE head, so each of them draws the multiplier of one of
+  // the trip's four tokens and the four are swapped by shuffle -- a quarter of the Philox calls
+  const bool share = (dh & 15) == 0;
   for (int a0 = 0; a0 < na; a0 += 4) {
     float w[4][4];
     float4 v[4];
+    float msh = 1.f;
+    if (drop.on() && share) {
+      const int al = a0 + (lane & 3) < na ? a0 + (lane & 3) : na - 1;
+      msh = drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + static_cast<uint64_t>(tok[base + al]));
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int al = a0 + u < na ? a0 + u : na - 1;
@@ -488,6 +496,11 @@ __global__ void __launch_bounds__(256) tail_ctx_kernel(Dims D, const int32_t* __
       w[u][0] = pw[h0]; w[u][1] = pw[h1]; w[u][2] = pw[h2]; w[u][3] = pw[h3];
       v[u] = *reinterpret_cast<const float4*>(kv + static_cast<size_t>(base + al) * 2 * d + d + j);
       if (drop.on()) {
+        if (share) {
+          const float m0 = __shfl_sync(kFull, msh, (lane & ~3) | u);
+          w[u][0] *= m0; w[u][1] *= m0; w[u][2] *= m0; w[u][3] *= m0;
+          continue;
+        }
         const uint64_t t = static_cast<uint64_t>(tok[base + al]);
         const float m0 = drop.mul1(1u, (static_cast<uint64_t>(grow) * H + h0) * T + t);
         if (h0 == h3) {                     // dh % 4 == 0: the lane's four columns belong to one head -> one draw
