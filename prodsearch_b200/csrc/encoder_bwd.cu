@@ -7,6 +7,9 @@
 //   embed_bwd  (+ pre-LN') + residual, masked -> grad of the token inputs
 //   wgrad      every dW = G^T A as split-M 128x128 FFMA tiles with per-chunk partials
 //   reduce     partials summed in chunk order (deterministic; no float atomics anywhere)
+// With PSB_ENC_TC = 4 (the default) tail_bwd becomes tail_bwd_fused_tc_kernel (gemm3_tf32.cu: the product chain on
+// tcgen05) + tail_attn_bwd_kernel (below), the grad-xn product runs on gemm3_tf32_kernel, and wgrad / reduce are
+// launched in two halves on streams of their own (see psb_encoder_bwd).
 #include <stdlib.h>
 
 #include "encoder_common.cuh"

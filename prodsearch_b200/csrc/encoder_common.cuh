@@ -3,10 +3,11 @@
 //
 // Work shape: after restricting the last layer to the one output position the
 // model reads, a TEM step has S*copies = 2304 rows of 128..512-wide projections and ~3.3k token
-// rows of K/V projections -- ~1.2 GFLOP forward.  That is far too little for 128-row tcgen05 tiles
-// to fill 148 SMs, and fp32 parity (1e-5) rules TF32 out, so the projections run as fp32 FFMA
-// CTA tiles of R = 16/24 rows: ~100-200 CTAs, one per SM, weights streamed from L2 exactly once
-// per CTA with register prefetch, activations broadcast from shared memory.
+// rows of K/V projections -- ~1.2 GFLOP forward: latency-bound whatever computes it.  Two forms of
+// every product exist: fp32 FFMA CTA tiles of R = 16/24 rows (this header's tile_gemm; ~100-200
+// CTAs, weights streamed from L2 once per CTA, activations broadcast from shared memory) -- the
+// fallback for any d <= 128 / ff <= 1024 -- and, for d = 128 / ff = 512, 3xTF32 products on tcgen05
+// chained inside cluster kernels (gemm3_tf32.cu), the default since round 2 (PSB_ENC_TC).
 #pragma once
 #include "psb_common.cuh"
 

@@ -9,6 +9,8 @@
 //   attn       per sequence: scores of the ONE query position, softmax -> P
 //   tail       per tile of R copy-rows: dropout(P) V -> Wo -> +x[o] -> LN -> W1 -> gelu -> W2 ->
 //              +y -> LN, everything between the two HBM touches kept in shared memory
+// With PSB_ENC_TC >= 1 (default 4) the projections run on tcgen05 (gemm3_tf32_kernel) and the tail is
+// tail_ctx_kernel + tail_fused_tc_kernel (gemm3_tf32.cu); the FFMA kernels below stay the fallback.
 #include "encoder_common.cuh"
 
 namespace psb {

@@ -24,14 +24,13 @@
 // Rows >= M (M may live on the device: the number of active tokens) are computed on whatever the buffer holds and not
 // stored; a GEMM row depends on its own A row only.  CTAs whose first row is >= M exit at once.
 //
-// PSB_ENC_TC=1: the encoder forward's q and K|V projections run here (rows_gemm_kernel otherwise).
-// PSB_ENC_TC=2: additionally the forward tail (tail_fwd_kernel: 52 us at batch 384) becomes tail_ctx_kernel + three of
-// these GEMMs -- out-projection + LN (18 CTAs), FFN up (144 CTAs), FFN down + LN (18 CTAs) -- writing the same saved
-// tensors with the same dropout streams, so the FFMA backward kernels consume them unchanged.
-//
-// Status: written at the end of round 1 WITHOUT a GPU run (compiled, SASS read).  Off by default; the standalone entry
-// psb_debug_gemm3_tf32 + profiles/check_gemm3.py are its first GPU call in round 2, then the encoder / model GPU tests
-// with PSB_ENC_TC=1 and 2 (profiles/run_round2_first.sh).
+// This file holds every tensor-core form of the encoder (levels of PSB_ENC_TC, see enc_tc_level below; 4 is the default):
+//   gemm3_tf32_kernel          one product with a fused epilogue: the q / K|V projections, the backward's grad-xn product
+//   tail_ctx_kernel + tail_fused_tc_kernel      the forward tail as ONE cluster kernel (three chained products)
+//   tail_bwd_fused_tc_kernel   the backward tail's product chain as one cluster kernel, transposed form
+//                              (+ encoder_bwd.cu tail_attn_bwd_kernel for the attention backward)
+// All of them have run on B200s: profiles/r02a_gemm3.jsonl (accuracy against fp64), profiles/r02W_diff_enc_*.jsonl (stage by
+// stage against the FFMA kernels), tests/test_gpu_enc_tc_levels.py (every level, every round).
 #include <stdlib.h>
 
 #include "encoder_common.cuh"

@@ -3,9 +3,11 @@
 Same parameter names as the reference (models/transformer.py, models/neural.py) so a reference
 checkpoint loads unchanged: ``pos_emb.pe``, ``transformer_inter.{i}.self_attn.linear_{keys,values,
 query}``, ``.final_linear``, ``.feed_forward.{w_1,w_2,layer_norm}``, ``.layer_norm``, ``layer_norm``,
-``wo``.  The encoder is NOT one of the hot-path subsystems (1)-(4) of the north star (SURVEY.md 2.1
-C5/C6: "stays torch"); it is row N1 of the "next" list.  This implementation runs the reference's
-arithmetic through cuBLAS/ATen on the device and is the piece a fused sm_100a encoder replaces.
+``wo``.  The encoder is row N1 of SURVEY.md 8(f): the last layer + final LayerNorm at the one position
+the models read run in the fused sm_100a encoder (``encode_position`` -> functional.SeqEncoderFn ->
+psb_encoder_fwd / _bwd; 3xTF32 products on tcgen05 by default, fp32 FFMA kernels as the fallback,
+DESIGN.md section 4).  Earlier layers (inter_layers > 1) and the full-sequence ``forward`` the
+reference also exposes run the reference's arithmetic through cuBLAS / ATen on the device.
 """
 import math
 from collections import OrderedDict
