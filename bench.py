@@ -913,6 +913,14 @@ def summarize_regimes(line):
     t16s = sh.get("train_step_16M") or {}
     if "ms_per_step" in t16s:
         tab["sharded_train_step_16M"] = {"ms_per_step": round(t16s["ms_per_step"], 3)}
+    # the encoder's kernels in the headline step (eager per-launch times of the profiled pass, cold L2; the ncu capture of
+    # the same kernels is profiles/r02X_tails_full_raw.csv: tensor pipe active 19 % / 15 % of the cluster kernels' cycles)
+    kn = line.get("kernels") or {}
+    for k, name in (("tail_fused_tc_kernel", "N1_tail_fwd_tcgen05"), ("tail_bwd_fused_tc_kernel", "N1_tail_bwd_tcgen05"),
+                    ("tail_fwd_kernel", "N1_tail_fwd_ffma"), ("tail_bwd_kernel", "N1_tail_bwd_ffma"), ("wgrad_kernel", "N1_wgrad_ffma")):
+        if isinstance(kn.get(k), dict) and "frac" in kn[k]:
+            tab[name] = {"us_per_launch": round(kn[k]["avg_launch_us"], 1), "launches_per_step": kn[k]["launches_per_step"],
+                         "frac_of_tf32_peak": round(kn[k]["frac"], 4)}
     rf["regimes"] = tab
     rf["regimes_note"] = ("bandwidth regime = 16M x 128 fp32 table (8.2 GB >> L2); fractions of the measured peaks "
                           "(MEASURED_PEAKS.json); full entries under extra")
