@@ -20,6 +20,13 @@ import torch
 from . import _lib
 
 
+class PackedBatch(object):
+    """A batch as one host byte buffer in the layout of a GraphedTrainStep's static inputs (GraphedTrainStep.pack)."""
+
+    def __init__(self, buf):
+        self.buf = buf
+
+
 class GraphedTrainStep(object):
     def __init__(self, model, optim, sample_batch, pad_values=None, warmup=3, sync_grads=None):
         """sample_batch: a batch whose tensor fields have the LARGEST shapes that will be fed (narrower
@@ -29,8 +36,23 @@ class GraphedTrainStep(object):
         self.pad_values = dict(pad_values or {})
         self.static = argparse.Namespace()
         dev = next(model.parameters()).device
+        # every tensor field of the batch lives in ONE device allocation (16-byte aligned slices), so that a batch packed
+        # the same way on the host (``pack``) arrives with a single host -> device copy
+        self._layout, off = {}, 0
         for k, v in vars(sample_batch).items():
-            setattr(self.static, k, v.to(dev).clone() if torch.is_tensor(v) else v)
+            if torch.is_tensor(v):
+                nbytes = v.numel() * v.element_size()
+                self._layout[k] = (off, nbytes, tuple(v.shape), v.dtype)
+                off += (nbytes + 15) // 16 * 16
+        self._pack_bytes = max(off, 16)
+        self._dev_pack = torch.zeros(self._pack_bytes, dtype=torch.uint8, device=dev)
+        for k, v in vars(sample_batch).items():
+            if torch.is_tensor(v):
+                dst = self._view(self._dev_pack, k)
+                dst.copy_(v)
+                setattr(self.static, k, dst)
+            else:
+                setattr(self.static, k, v)
         self.sync_grads = sync_grads
         snap = self._snapshot()
         side = torch.cuda.Stream()
@@ -101,8 +123,41 @@ class GraphedTrainStep(object):
         self.optim.step()
         return loss.detach()
 
+    def _view(self, buf, k):
+        off, nbytes, shape, dtype = self._layout[k]
+        return buf[off:off + nbytes].view(dtype).view(shape)
+
+    def pack(self, batch, pin=True):
+        """Host side of the one-copy load: the batch's tensor fields laid out (and right-padded) like the static device
+        buffers in one (pinned) byte buffer.  Part of collating a batch, like pinning it; ``load`` / ``__call__`` accept
+        the result."""
+        buf = torch.zeros(self._pack_bytes, dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            buf = buf.pin_memory()
+        for k, v in vars(batch).items():
+            if not torch.is_tensor(v):
+                continue
+            dst = self._view(buf, k)
+            v = v.detach().cpu()
+            if v.shape == dst.shape:
+                dst.copy_(v)
+                continue
+            if v.dim() != dst.dim() or v.shape[0] != dst.shape[0] or any(a > b for a, b in zip(v.shape, dst.shape)):
+                raise ValueError("batch field %s has shape %s, graph was captured for %s" % (k, tuple(v.shape), tuple(dst.shape)))
+            if k not in self.pad_values:
+                raise ValueError("no pad value for the narrower batch field " + k)
+            dst.fill_(self.pad_values[k])
+            dst[tuple(slice(0, n) for n in v.shape)].copy_(v)
+        return PackedBatch(buf)
+
     def load(self, batch, non_blocking=True):
-        """Copy a (host or device) batch into the static input buffers, right-padding narrower tensors."""
+        """Copy a (host or device) batch into the static input buffers, right-padding narrower tensors.  A PackedBatch
+        (``pack``) takes one copy."""
+        if isinstance(batch, PackedBatch):
+            if batch.buf.numel() != self._pack_bytes:
+                raise ValueError("packed batch of %d bytes, graph was captured for %d" % (batch.buf.numel(), self._pack_bytes))
+            self._dev_pack.copy_(batch.buf, non_blocking=non_blocking)
+            return
         for k, v in vars(batch).items():
             if not torch.is_tensor(v):
                 continue

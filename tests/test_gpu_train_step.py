@@ -92,7 +92,7 @@ def test_graph_step_equals_eager_steps():
         out.query_word_idxs = q
         return out
 
-    def run(graphed):
+    def run(graphed, packed=False):
         model, optim, cfg, P, V = _tem(0.0, seed=7)
         model.train()
         neg_i = batches[0][1].clone()
@@ -107,8 +107,8 @@ def test_graph_step_equals_eager_steps():
         for b, ni, nw in batches:
             neg_i.copy_(ni)
             neg_w.copy_(nw)
-            if graphed:
-                losses.append(float(step(b)))
+            if graphed:      # plain batch: one copy per field; packed: the narrower batch is padded on the host, one copy
+                losses.append(float(step(step.pack(b) if packed else b)))
             else:
                 db = argparse.Namespace(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vars(padded(b)).items()})
                 loss = model(db)
@@ -123,6 +123,10 @@ def test_graph_step_equals_eager_steps():
     assert l_e == l_g, (l_e, l_g)
     assert abs(ps_e - ps_g) <= 1e-6 * abs(ps_e)
     for a, b in zip(p_e, p_g):
+        assert torch.equal(a, b)
+    l_p, p_p, _ = run(True, packed=True)
+    assert l_p == l_g
+    for a, b in zip(p_p, p_g):
         assert torch.equal(a, b)
 
 
