@@ -54,6 +54,7 @@ class GraphedTrainStep(object):
             else:
                 setattr(self.static, k, v)
         self.sync_grads = sync_grads
+        self._one = None
         snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -117,7 +118,9 @@ class GraphedTrainStep(object):
     def _step_body(self):
         loss = self.model(self.static)
         self.model.zero_grad()
-        loss.backward()
+        if self._one is None or self._one.shape != loss.shape:
+            self._one = torch.ones_like(loss)
+        loss.backward(self._one)           # a persistent root gradient: no fill kernel at the head of every backward pass
         if self.sync_grads is not None:
             self.sync_grads()
         self.optim.step()
